@@ -1,0 +1,323 @@
+/*
+ * nest_b200.h -- C-ABI of the B200-native NEST detector-response chain.
+ *
+ * The reference (NESTCollaboration/nest) has no FFI layer: its operator API is the
+ * C++ class surface NESTcalc/VDetector plus the execNEST()/runNESTvec() drivers.
+ * Every entry point below names the reference interface it replaces (file:line,
+ * relative to the reference root).  Plain pointers and sizes only; no C++ or
+ * torch types cross this boundary.  INTEGRATION.md shows the reference-side
+ * binding (a header-only flattener VDetector* -> nb200_detector and the
+ * ctypes stub used by the tests).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative NB200_E* code otherwise
+ *     (the reference's "cerr << msg; return 1" / throw std::runtime_error,
+ *     src/execNEST.cpp:1410-1413); nb200_last_error() holds the message.
+ *   - one context per device and per host thread; calls are stream-ordered on
+ *     the context's stream (nb200_set_stream) and synchronous at return unless
+ *     the function name ends in _async.
+ *   - results for event id e depend only on (seed, e, parameters): they are
+ *     independent of batch split, launch geometry and GPU count.
+ *   - there is no CPU fallback: without a CUDA device every compute entry
+ *     point fails with NB200_ENODEV.
+ */
+#ifndef NEST_B200_H
+#define NEST_B200_H 1
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NB200_ABI_VERSION 1
+
+/* error codes */
+#define NB200_OK 0
+#define NB200_EINVAL (-1)   /* bad argument (reference: cerr + return 1)        */
+#define NB200_ENODEV (-2)   /* no CUDA device / wrong architecture              */
+#define NB200_ECUDA (-3)    /* CUDA runtime error, see nb200_last_error         */
+#define NB200_EPHYSICS (-4) /* reference would throw std::runtime_error         */
+#define NB200_ENOMEM (-5)
+
+/* INTERACTION_TYPE, include/NEST/NEST.hh:133-156 (same numeric values) */
+enum {
+  NB200_NR = 0, NB200_WIMP = 1, NB200_B8 = 2, NB200_DD = 3, NB200_AmBe = 4,
+  NB200_Cf = 5, NB200_ion = 6, NB200_gammaRay = 7, NB200_beta = 8,
+  NB200_CH3T = 9, NB200_C14 = 10, NB200_Kr83m = 11, NB200_ppSolar = 12,
+  NB200_atmNu = 13, NB200_NoneType = 17
+};
+
+/* S1CalculationMode / S2CalculationMode, NEST.hh:158-160.  The Waveform modes
+ * are out of scope and rejected with NB200_EINVAL. */
+enum { NB200_S1_FULL = 0, NB200_S1_PARAMETRIC = 1, NB200_S1_HYBRID = 2 };
+enum { NB200_S2_FULL = 0 };
+
+/* ---- position maps: the four VDetector virtuals on the path ------------------
+ * VDetector.hh:131-154 (FitS1, FitEF, FitS2, FitTBA).  Virtual C++ functions
+ * cannot run on the device, so a detector is flattened to one of:
+ *   CONST      value = c[0]                                (VDetector defaults)
+ *   LUX_RUN03  the closed forms of include/Detectors/LUX_Run03.hh:90-167,
+ *              coefficients in c[] (layout documented in nest_b200/csrc/maps.cuh)
+ *   LUT_RZ     bilinear table over (r [mm], z [mm]) tabulated from the
+ *              virtual at flatten time; lut is a HOST pointer to n0*n1 doubles
+ *              (row = r index), axes r in [c[0],c[1]], z in [c[2],c[3]]
+ */
+enum { NB200_MAP_CONST = 0, NB200_MAP_LUX_RUN03 = 1, NB200_MAP_LUT_RZ = 2 };
+
+typedef struct nb200_map {
+  int32_t kind;
+  int32_t n0, n1;
+  int32_t _pad;
+  double c[16];
+  const double* lut;
+} nb200_map;
+
+/* ---- VDetector flattened: include/Detectors/VDetector.hh:157-224 -------------
+ * Same member names and units as the reference class. */
+typedef struct nb200_detector {
+  double g1, sPEres, sPEthr, sPEeff;
+  double noiseBaseline[4];
+  double P_dphe;
+  double coinWind;
+  int32_t coinLevel, numPMTs;
+  int32_t OldW13eV, inGas;
+  double noiseLinear[2], noiseQuadratic[2];
+  double g1_gas, s2Fano, s2_thr, E_gas, eLife_us;
+  double T_Kelvin, p_bar;
+  double dtCntr, dt_min, dt_max;
+  double radius, radmax, TopDrift, anode, cathode, gate;
+  double PosResFlat, PosResBase;
+  double molarMass;
+  nb200_map FitS1, FitS2, FitEF, FitTBA; /* FitTBA: value = BotTotRat[1] */
+} nb200_detector;
+
+/* Built-in flattenings of shipped detectors (closed-form maps).
+ * name: "LUX_Run03" (LUX_Run03.hh:30-88) or "VDetector" (VDetector.hh:157-224
+ * defaults; also what LArDetector really is). */
+int nb200_detector_builtin(const char* name, nb200_detector* out);
+
+/* ---- model parameter vectors ---------------------------------------------------
+ * NRYieldsParam[12], ERYieldsParam[10], NRERWidthsParam[17]: NEST.hh:120-124,
+ * src/execNEST.cpp:185-249.  n_widths is the reference vector's size() (13..17:
+ * RecombOmegaER reads [13..16] only when present, NEST.cpp:206-212).
+ * SkewnessER: GetQuanta's 4th argument (NEST.cpp:248-250; -999 = LUX model).
+ * er_model: which ER yield the "ER" CLI type uses (execNEST.cpp:1032-1048):
+ *   0 GetYieldBetaGR(multFact), 1 GetYieldGamma(-multFact), 2 GetYieldERWeighted
+ *   and -1 = plain GetYields(species) dispatch (NEST.cpp:1211-1252). */
+typedef struct nb200_model {
+  double NRYieldsParam[12];
+  double ERYieldsParam[10];
+  double NRERWidthsParam[17];
+  int32_t n_widths;
+  int32_t er_model;
+  double SkewnessER;
+  double multFact;
+  double massNum;  /* 0 => random Xe isotope per NR event (execNEST.cpp:670) */
+  double atomNum;
+} nb200_model;
+
+/* which==0: default_* vectors of NEST.hh:120-124 (what runNESTvec uses);
+ * which==1: the hard-coded CLI vectors of execNEST.cpp:188-248, SkewnessER=0. */
+int nb200_model_default(int which, nb200_model* out);
+
+/* ---- analysis.hh compile-time globals as a runtime struct ----------------------
+ * include/NEST/analysis.hh:7-77 / analysis_G2.hh. */
+typedef struct nb200_analysis {
+  int32_t usePD, useS2;
+  int32_t numBins, logBins;
+  double minS1, maxS1, minS2, maxS2, logMin, logMax;
+  int32_t MCtruthE, MCtruthPos;
+  int32_t s1mode, s2mode;
+  double z_step;
+} nb200_analysis;
+
+/* which==0: analysis.hh (LUX band); which==1: analysis_G2.hh (as shipped). */
+int nb200_analysis_default(int which, nb200_analysis* out);
+
+/* ---- energy source: TestSpectra / execNEST.cpp:681-790 -------------------------
+ * kind FLAT/GAUSS/EXP are the "default:" branch (execNEST.cpp:763-781), MONO is
+ * eMin==eMax (:681-683); CH3T TestSpectra.cpp:31-58, DD :192-211 with the five
+ * shape parameters of execNEST.cpp:705 in par[0..4], B8 :110-128, AMBE = PowLawFit
+ * :151-167 with the exponent of execNEST.cpp:698 in par[0].
+ * LIST: energies (and optionally positions) supplied by the caller, the
+ * runNESTvec form (execNEST.cpp:329-409). */
+enum {
+  NB200_SRC_MONO = 0, NB200_SRC_FLAT = 1, NB200_SRC_GAUSS = 2, NB200_SRC_EXP = 3,
+  NB200_SRC_CH3T = 4, NB200_SRC_DD = 5, NB200_SRC_B8 = 6, NB200_SRC_LIST = 7,
+  NB200_SRC_WIMP = 8, NB200_SRC_AMBE = 9
+};
+
+typedef struct nb200_source {
+  int32_t kind;
+  int32_t species;   /* INTERACTION_TYPE */
+  double eMin, eMax;
+  double par[8];
+  /* position: fixed_pos==0 => random (z,r,phi) with drift-time window retry
+   * (execNEST.cpp:806-814, 962-967); else xyz[] used for every event (a -1 z or -999 x,y
+   * on the reference CLI = the random-z / random-xy variants 2 and 3, :845-853). */
+  int32_t fixed_pos; /* 0 random; 1 fixed xyz; 2 fixed xy, random z; 3 random xy, fixed z */
+  int32_t vec_mode;  /* 1 = runNESTvec semantics (execNEST.cpp:357-406): positions as given,
+                      * no xy smearing, no cathode cut, no drift-window retry, vD from the
+                      * per-event field, yields through FullCalculation (NEST.cpp:22-42) */
+  double xyz[3];
+  double inField;    /* V/cm; -1 => FitEF(x,y,z) per event (execNEST.cpp:857-861) */
+  /* LIST only: n_events entries each, host or device memory per list_mem_kind
+   * (NB200_MEM_*); x/y/z may be NULL (then fixed_pos/xyz apply) */
+  int32_t list_mem_kind;
+  int32_t _pad;
+  const double* E;
+  const double* x;
+  const double* y;
+  const double* z;
+  /* WIMP only: table from nb200_wimp_prep (TestSpectra.hh:43-49) */
+  const double* wimp_base;
+  const double* wimp_exponent;
+  double wimp_xMax, wimp_divisor, wimp_mass, wimp_day;
+} nb200_source;
+
+/* ---- per-run constants computed on the host once -------------------------------
+ * SetDensity (NEST.cpp:2270-2350), WorkFunction (:2829-2848), SetDriftVelocity
+ * (:2352-2521), CalculateG2 (:2065-2235), FindNewMean (RandomGen.cpp:63-70). */
+typedef struct nb200_run_consts {
+  double rho, Wq_eV, alpha;
+  double vD, vD_middle;
+  double g2_params[5]; /* elYield, ExtEff, SE, g2, gasGap */
+  double NewMean;
+  double field;        /* uniform drift field used, V/cm */
+} nb200_run_consts;
+
+/* ---- outputs --------------------------------------------------------------------
+ * Structure-of-arrays record per event.  Any pointer may be NULL (column not
+ * written).  Column meaning = the reference vectors:
+ *   GetS1 scintillation[0..8] NEST.cpp:1632-1645, GetS2 ionization[0..8]
+ *   :2019-2060 (sign = below-threshold flag, :1689-1716, :2051-2057),
+ *   quanta NEST.hh:171-178, truth as NESTObservableArray execNEST.hh:30-44,
+ *   signal1/signal2/signalE execNEST.cpp:1121-1158,1245-1250. */
+enum { NB200_MEM_HOST = 0, NB200_MEM_DEVICE = 1 };
+
+typedef struct nb200_soa_out {
+  int32_t mem_kind;
+  int32_t _pad;
+  double *energy_kev, *x_mm, *y_mm, *z_mm, *field, *driftTime;
+  double *smear_x, *smear_y;
+  int32_t *photons, *electrons, *ions, *excitons;
+  double *s1[9];
+  double *s2[9];
+  double *signal1, *signal2, *signalE; /* band inputs; keV_recon */
+  double *Nph_mean, *Ne_mean;          /* yields.PhotonYield / ElectronYield */
+} nb200_soa_out;
+
+/* Band accumulator = what GetBand (execNEST.cpp:1508-1621) reduces, kept as exact
+ * integers so that any GPU count / batch split gives bit-identical results:
+ * per S1 bin: accepted count, rejected count, and fixed-point sums of S1, y,
+ * y^2, y^3 (y = log10(S2/S1) or the 0 the reference pushes when y is outside
+ * (logMin,logMax), :1551-1555); plus the numBins x logBins 2-D histogram of y.
+ * All arrays are caller-owned (HOST), sized by nb200_band_hist_bytes(). */
+#define NB200_FX_S1 1048576.0        /* 2^20  */
+#define NB200_FX_Y 1073741824.0      /* 2^30  */
+#define NB200_FX_Y2 67108864.0       /* 2^26  */
+#define NB200_FX_Y3 4194304.0        /* 2^22  */
+
+typedef struct nb200_band_hist {
+  int32_t numBins, logBins;
+  uint64_t n_events;    /* events simulated into this accumulator */
+  uint64_t* accepted;   /* [numBins] */
+  uint64_t* rejected;   /* [numBins] */
+  int64_t* sumS1;       /* [numBins] units 2^-20 */
+  int64_t* sumY;        /* [numBins] units 2^-30 */
+  int64_t* sumY2;       /* [numBins] units 2^-26 */
+  int64_t* sumY3;       /* [numBins] units 2^-22 */
+  uint64_t* hist2d;     /* [numBins*logBins], log axis (logMin,logMax) */
+} nb200_band_hist;
+
+typedef struct nb200_ctx nb200_ctx;
+
+int nb200_abi_version(void);
+/* sizeof() of the ABI structs as this library was compiled, for FFI layout checks:
+ * which = 0 nb200_map, 1 nb200_detector, 2 nb200_model, 3 nb200_analysis, 4 nb200_source,
+ * 5 nb200_run_consts, 6 nb200_soa_out, 7 nb200_band_hist; -1 for anything else */
+int nb200_sizeof(int which);
+int nb200_create(int device, nb200_ctx** out);
+void nb200_destroy(nb200_ctx* ctx);
+const char* nb200_last_error(const nb200_ctx* ctx);
+/* cudaStream_t as void*; NULL = the context's own stream */
+int nb200_set_stream(nb200_ctx* ctx, void* cuda_stream);
+int nb200_synchronize(nb200_ctx* ctx);
+
+/* Host-only: replaces NESTcalc::SetDensity + WorkFunction + SetDriftVelocity +
+ * CalculateG2(0) + FindNewMean as called at execNEST.cpp:612-631,878-890. */
+/* Sets det->inGas as SetDensity does (NEST.cpp:2270-2276, execNEST.cpp:618-619).
+ * inField == -1: vD_middle is read from the SetDriftVelocity_NonUniform table at centralZ
+ * (execNEST.cpp:635-637, 882-883) built with z_step (0 => analysis.hh's 0.1 mm). */
+int nb200_prepare(nb200_detector* det, double inField, double z_step, nb200_run_consts* out);
+
+/* Host-only: TestSpectra::WIMP_prep_spectrum (TestSpectra.cpp:392-454).  The reference
+ * draws a random Xe isotope inside every WIMP_dRate call (:278); those draws come from the
+ * Philox host stream keyed by seed.  base/exponent: caller arrays of 100 doubles. */
+int nb200_wimp_prep(double mass_GeV, double eStep, double dayNum, uint64_t seed, double* base,
+                    double* exponent, double* integral, double* xMax, double* divisor);
+/* Poisson draw for the WIMP/8B event count (execNEST.cpp:482-488), host stream keyed by seed */
+uint64_t nb200_poisson(double mean, uint64_t seed);
+
+/* Deterministic mean yields on the device: replaces NESTcalc::GetYields
+ * (NEST.cpp:1211-1252) + YieldResultValidity (:1254-1271) for n independent
+ * (E, field) pairs.  out columns [6][n] = PhotonYield, ElectronYield,
+ * ExcitonRatio, Lindhard, ElectricField, DeltaT_Scint (NEST.hh:162-169).
+ * massNum must be non-zero here (no RNG on this entry point). E/field/out are
+ * pointers of kind mem_kind. */
+int nb200_yields(nb200_ctx* ctx, const nb200_detector* det, const nb200_model* model,
+                 int species, size_t n, const double* E, const double* field,
+                 double density, int mem_kind, double* out);
+
+/* The per-event chain: replaces the loop body of execNEST() (execNEST.cpp:676-1414)
+ * and of runNESTvec() (:357-406) for event ids [first_event, first_event+n).
+ * soa and hist may each be NULL.  hist is ACCUMULATED into (caller zeroes it). */
+int nb200_run(nb200_ctx* ctx, const nb200_detector* det, const nb200_model* model,
+              const nb200_analysis* ana, const nb200_source* src,
+              const nb200_run_consts* rc, uint64_t seed, uint64_t first_event,
+              uint64_t n_events, nb200_soa_out* soa, nb200_band_hist* hist);
+
+/* Device-resident variant used for throughput measurement: the band accumulator
+ * stays in device memory owned by ctx between calls; fetch adds it into hist. */
+int nb200_run_async(nb200_ctx* ctx, const nb200_detector* det, const nb200_model* model,
+                    const nb200_analysis* ana, const nb200_source* src,
+                    const nb200_run_consts* rc, uint64_t seed, uint64_t first_event,
+                    uint64_t n_events, nb200_soa_out* soa_device_or_null);
+int nb200_band_reset(nb200_ctx* ctx, const nb200_analysis* ana);
+int nb200_band_fetch(nb200_ctx* ctx, nb200_band_hist* hist);
+/* Use a caller-owned device buffer of nb200_band_hist_bytes(ana) bytes as the accumulator
+ * (e.g. a torch tensor that torch.distributed all-reduces); the caller zeroes it. */
+int nb200_band_attach(nb200_ctx* ctx, const nb200_analysis* ana, void* device_buffer);
+/* device pointer + element count (uint64) of the packed accumulator, for an
+ * external all-reduce (torch.distributed / NCCL) over the event shards */
+int nb200_band_device_buffer(nb200_ctx* ctx, void** dptr, size_t* n_u64);
+/* ncclComm_t as void*; sums the device accumulator over ranks in place */
+int nb200_allreduce_hist(nb200_ctx* ctx, void* nccl_comm);
+
+/* GetBand's final statistics (execNEST.cpp:1582-1618) from the accumulator:
+ * band[j][0..6] = centre, mean S1, mean y, sigma (N-1), sigma/sqrt(N), eff, skew */
+size_t nb200_band_hist_bytes(const nb200_analysis* ana);
+int nb200_band_finalize(const nb200_analysis* ana, const nb200_band_hist* hist,
+                        double* band /* [numBins][7] */);
+
+/* LAr: replaces LArNEST::FullCalculation (src/LArNEST.cpp:17-33) for species
+ * NR=0, ER=1, Alpha=2 (LArParameters.hh:27-34).  yields [9][n] in the field order
+ * of LArYieldResult (LArNEST.hh:19-29), fluct [4][n] LArYieldFluctuationResult
+ * (:31-36); either may be NULL.  Event i uses Philox stream (seed, first_event+i). */
+int nb200_lar(nb200_ctx* ctx, int species, size_t n, const double* E, const double* field,
+              double density, uint64_t seed, uint64_t first_event, int mem_kind,
+              double* yields, double* fluct);
+
+/* Measured FP64 pipe peak of this device: a register-resident DFMA chain kernel timed with
+ * CUDA events (the roofline denominator of the chain kernel). */
+int nb200_fp64_peak(nb200_ctx* ctx, double* tflops);
+
+/* counters for the bench: kernels launched by this context since creation */
+uint64_t nb200_launch_count(const nb200_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEST_B200_H */

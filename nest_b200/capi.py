@@ -1,0 +1,344 @@
+"""ctypes binding of the C-ABI in include/nest_b200.h (libnest_b200.so).
+
+This is the Python-side stub of INTEGRATION.md: plain structs and pointers, no torch types.
+The library is built in-tree by ``nest_b200.build.build()``; loading fails loudly when it is
+missing -- there is no CPU fallback behind these calls.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libnest_b200.so")
+
+# error codes
+OK, EINVAL, ENODEV, ECUDA, EPHYSICS, ENOMEM = 0, -1, -2, -3, -4, -5
+# INTERACTION_TYPE (NEST.hh:133-156)
+NR, WIMP, B8, DD, AmBe, Cf, ion, gammaRay, beta, CH3T, C14, Kr83m, ppSolar, atmNu = range(14)
+NoneType = 17
+S1_FULL, S1_PARAMETRIC, S1_HYBRID = 0, 1, 2
+MAP_CONST, MAP_LUX_RUN03, MAP_LUT_RZ = 0, 1, 2
+(SRC_MONO, SRC_FLAT, SRC_GAUSS, SRC_EXP, SRC_CH3T, SRC_DD, SRC_B8, SRC_LIST, SRC_WIMP,
+ SRC_AMBE) = range(10)
+MEM_HOST, MEM_DEVICE = 0, 1
+FX_S1, FX_Y, FX_Y2, FX_Y3 = 2.0 ** 20, 2.0 ** 30, 2.0 ** 26, 2.0 ** 22
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int32)
+c_u64p = C.POINTER(C.c_uint64)
+c_i64p = C.POINTER(C.c_int64)
+
+
+class Map(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("n0", C.c_int32), ("n1", C.c_int32), ("_pad", C.c_int32),
+                ("c", C.c_double * 16), ("lut", c_dp)]
+
+
+class Detector(C.Structure):
+    _fields_ = [
+        ("g1", C.c_double), ("sPEres", C.c_double), ("sPEthr", C.c_double), ("sPEeff", C.c_double),
+        ("noiseBaseline", C.c_double * 4), ("P_dphe", C.c_double), ("coinWind", C.c_double),
+        ("coinLevel", C.c_int32), ("numPMTs", C.c_int32), ("OldW13eV", C.c_int32), ("inGas", C.c_int32),
+        ("noiseLinear", C.c_double * 2), ("noiseQuadratic", C.c_double * 2),
+        ("g1_gas", C.c_double), ("s2Fano", C.c_double), ("s2_thr", C.c_double), ("E_gas", C.c_double),
+        ("eLife_us", C.c_double), ("T_Kelvin", C.c_double), ("p_bar", C.c_double),
+        ("dtCntr", C.c_double), ("dt_min", C.c_double), ("dt_max", C.c_double),
+        ("radius", C.c_double), ("radmax", C.c_double), ("TopDrift", C.c_double), ("anode", C.c_double),
+        ("cathode", C.c_double), ("gate", C.c_double), ("PosResFlat", C.c_double),
+        ("PosResBase", C.c_double), ("molarMass", C.c_double),
+        ("FitS1", Map), ("FitS2", Map), ("FitEF", Map), ("FitTBA", Map)]
+
+
+class Model(C.Structure):
+    _fields_ = [("NRYieldsParam", C.c_double * 12), ("ERYieldsParam", C.c_double * 10),
+                ("NRERWidthsParam", C.c_double * 17), ("n_widths", C.c_int32), ("er_model", C.c_int32),
+                ("SkewnessER", C.c_double), ("multFact", C.c_double), ("massNum", C.c_double),
+                ("atomNum", C.c_double)]
+
+
+class Analysis(C.Structure):
+    _fields_ = [("usePD", C.c_int32), ("useS2", C.c_int32), ("numBins", C.c_int32), ("logBins", C.c_int32),
+                ("minS1", C.c_double), ("maxS1", C.c_double), ("minS2", C.c_double), ("maxS2", C.c_double),
+                ("logMin", C.c_double), ("logMax", C.c_double), ("MCtruthE", C.c_int32),
+                ("MCtruthPos", C.c_int32), ("s1mode", C.c_int32), ("s2mode", C.c_int32),
+                ("z_step", C.c_double)]
+
+
+class Source(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("species", C.c_int32), ("eMin", C.c_double), ("eMax", C.c_double),
+                ("par", C.c_double * 8), ("fixed_pos", C.c_int32), ("vec_mode", C.c_int32),
+                ("xyz", C.c_double * 3), ("inField", C.c_double), ("list_mem_kind", C.c_int32),
+                ("_pad", C.c_int32), ("E", C.c_void_p), ("x", C.c_void_p), ("y", C.c_void_p),
+                ("z", C.c_void_p), ("wimp_base", c_dp), ("wimp_exponent", c_dp),
+                ("wimp_xMax", C.c_double), ("wimp_divisor", C.c_double), ("wimp_mass", C.c_double),
+                ("wimp_day", C.c_double)]
+
+
+class RunConsts(C.Structure):
+    _fields_ = [("rho", C.c_double), ("Wq_eV", C.c_double), ("alpha", C.c_double), ("vD", C.c_double),
+                ("vD_middle", C.c_double), ("g2_params", C.c_double * 5), ("NewMean", C.c_double),
+                ("field", C.c_double)]
+
+
+SOA_F64 = ["energy_kev", "x_mm", "y_mm", "z_mm", "field", "driftTime", "smear_x", "smear_y"]
+SOA_I32 = ["photons", "electrons", "ions", "excitons"]
+SOA_TAIL = ["signal1", "signal2", "signalE", "Nph_mean", "Ne_mean"]
+
+
+class SoaOut(C.Structure):
+    _fields_ = ([("mem_kind", C.c_int32), ("_pad", C.c_int32)] + [(n, C.c_void_p) for n in SOA_F64] +
+                [(n, C.c_void_p) for n in SOA_I32] + [("s1", C.c_void_p * 9), ("s2", C.c_void_p * 9)] +
+                [(n, C.c_void_p) for n in SOA_TAIL])
+
+
+class BandHist(C.Structure):
+    _fields_ = [("numBins", C.c_int32), ("logBins", C.c_int32), ("n_events", C.c_uint64),
+                ("accepted", c_u64p), ("rejected", c_u64p), ("sumS1", c_i64p), ("sumY", c_i64p),
+                ("sumY2", c_i64p), ("sumY3", c_i64p), ("hist2d", c_u64p)]
+
+
+EXPORTS = [
+    "nb200_abi_version", "nb200_sizeof", "nb200_create", "nb200_destroy", "nb200_last_error", "nb200_set_stream",
+    "nb200_synchronize", "nb200_detector_builtin", "nb200_model_default", "nb200_analysis_default",
+    "nb200_prepare", "nb200_wimp_prep", "nb200_poisson", "nb200_yields", "nb200_run", "nb200_run_async",
+    "nb200_band_reset", "nb200_band_attach", "nb200_fp64_peak", "nb200_band_fetch", "nb200_band_device_buffer", "nb200_allreduce_hist",
+    "nb200_band_hist_bytes", "nb200_band_finalize", "nb200_lar", "nb200_launch_count"]
+
+_lib = None
+
+
+class NestB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("nest_b200 error %d: %s" % (code, msg))
+        self.code = code
+        self.msg = msg
+
+
+def lib():
+    """Load libnest_b200.so (once).  Raises if it has not been built -- no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback for this path)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.nb200_abi_version.restype = C.c_int
+    L.nb200_sizeof.argtypes = [C.c_int]
+    for i, t in enumerate([Map, Detector, Model, Analysis, Source, RunConsts, SoaOut, BandHist]):
+        if L.nb200_sizeof(i) != C.sizeof(t):
+            raise ImportError("ABI layout mismatch for %s: library %d, binding %d" %
+                              (t.__name__, L.nb200_sizeof(i), C.sizeof(t)))
+    L.nb200_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.nb200_destroy.argtypes = [vp]
+    L.nb200_destroy.restype = None
+    L.nb200_last_error.argtypes = [vp]
+    L.nb200_last_error.restype = C.c_char_p
+    L.nb200_set_stream.argtypes = [vp, vp]
+    L.nb200_synchronize.argtypes = [vp]
+    L.nb200_detector_builtin.argtypes = [C.c_char_p, C.POINTER(Detector)]
+    L.nb200_model_default.argtypes = [C.c_int, C.POINTER(Model)]
+    L.nb200_analysis_default.argtypes = [C.c_int, C.POINTER(Analysis)]
+    L.nb200_prepare.argtypes = [C.POINTER(Detector), C.c_double, C.c_double, C.POINTER(RunConsts)]
+    L.nb200_wimp_prep.argtypes = [C.c_double, C.c_double, C.c_double, C.c_uint64, c_dp, c_dp, c_dp, c_dp, c_dp]
+    L.nb200_poisson.argtypes = [C.c_double, C.c_uint64]
+    L.nb200_poisson.restype = C.c_uint64
+    L.nb200_yields.argtypes = [vp, C.POINTER(Detector), C.POINTER(Model), C.c_int, C.c_size_t, vp, vp,
+                               C.c_double, C.c_int, vp]
+    run_args = [vp, C.POINTER(Detector), C.POINTER(Model), C.POINTER(Analysis), C.POINTER(Source),
+                C.POINTER(RunConsts), C.c_uint64, C.c_uint64, C.c_uint64]
+    L.nb200_run.argtypes = run_args + [C.POINTER(SoaOut), C.POINTER(BandHist)]
+    L.nb200_run_async.argtypes = run_args + [C.POINTER(SoaOut)]
+    L.nb200_band_reset.argtypes = [vp, C.POINTER(Analysis)]
+    L.nb200_band_fetch.argtypes = [vp, C.POINTER(BandHist)]
+    L.nb200_band_attach.argtypes = [vp, C.POINTER(Analysis), vp]
+    L.nb200_fp64_peak.argtypes = [vp, c_dp]
+    L.nb200_band_device_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.nb200_allreduce_hist.argtypes = [vp, vp]
+    L.nb200_band_hist_bytes.argtypes = [C.POINTER(Analysis)]
+    L.nb200_band_hist_bytes.restype = C.c_size_t
+    L.nb200_band_finalize.argtypes = [C.POINTER(Analysis), C.POINTER(BandHist), c_dp]
+    L.nb200_lar.argtypes = [vp, C.c_int, C.c_size_t, vp, vp, C.c_double, C.c_uint64, C.c_uint64, C.c_int,
+                            vp, vp]
+    L.nb200_launch_count.argtypes = [vp]
+    L.nb200_launch_count.restype = C.c_uint64
+    _lib = L
+    return L
+
+
+def _dptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Band:
+    """Host-side band accumulator (integers) + GetBand statistics (execNEST.cpp:1508-1621)."""
+
+    def __init__(self, ana):
+        self.ana = ana
+        nb, lb = ana.numBins, ana.logBins
+        self.accepted = np.zeros(nb, np.uint64)
+        self.rejected = np.zeros(nb, np.uint64)
+        self.sumS1 = np.zeros(nb, np.int64)
+        self.sumY = np.zeros(nb, np.int64)
+        self.sumY2 = np.zeros(nb, np.int64)
+        self.sumY3 = np.zeros(nb, np.int64)
+        self.hist2d = np.zeros(nb * max(lb, 0), np.uint64)
+        self.c = BandHist(nb, lb, 0, self.accepted.ctypes.data_as(c_u64p), self.rejected.ctypes.data_as(c_u64p),
+                          self.sumS1.ctypes.data_as(c_i64p), self.sumY.ctypes.data_as(c_i64p),
+                          self.sumY2.ctypes.data_as(c_i64p), self.sumY3.ctypes.data_as(c_i64p),
+                          self.hist2d.ctypes.data_as(c_u64p))
+
+    def finalize(self):
+        out = np.zeros((self.ana.numBins, 7))
+        rc = lib().nb200_band_finalize(C.byref(self.ana), C.byref(self.c), out.ctypes.data_as(c_dp))
+        if rc:
+            raise NestB200Error(rc, "nb200_band_finalize")
+        return out
+
+    def words(self):
+        """all integer words, for exact comparisons"""
+        return np.concatenate([self.accepted.view(np.int64), self.rejected.view(np.int64), self.sumS1,
+                               self.sumY, self.sumY2, self.sumY3, self.hist2d.view(np.int64)])
+
+
+def detector(name="LUX_Run03"):
+    d = Detector()
+    rc = lib().nb200_detector_builtin(name.encode(), C.byref(d))
+    if rc:
+        raise NestB200Error(rc, lib().nb200_last_error(None).decode())
+    return d
+
+
+def model(which=1):
+    m = Model()
+    lib().nb200_model_default(which, C.byref(m))
+    return m
+
+
+def analysis(which=0):
+    a = Analysis()
+    lib().nb200_analysis_default(which, C.byref(a))
+    return a
+
+
+def prepare(det, inField, z_step=0.0):
+    rc_ = RunConsts()
+    rc = lib().nb200_prepare(C.byref(det), inField, z_step, C.byref(rc_))
+    if rc:
+        raise NestB200Error(rc, lib().nb200_last_error(None).decode())
+    return rc_
+
+
+def source(kind, species, eMin=0.0, eMax=0.0, inField=180.0, fixed_pos=0, xyz=(0.0, 0.0, 0.0), par=(),
+           vec_mode=0):
+    s = Source()
+    s.kind, s.species, s.eMin, s.eMax, s.inField = kind, species, eMin, eMax, inField
+    s.fixed_pos, s.vec_mode = fixed_pos, vec_mode
+    for i, v in enumerate(xyz):
+        s.xyz[i] = v
+    for i, v in enumerate(par):
+        s.par[i] = v
+    return s
+
+
+SOA_COLUMNS = (SOA_F64 + SOA_I32 + ["s1_%d" % i for i in range(9)] + ["s2_%d" % i for i in range(9)] + SOA_TAIL)
+
+
+class Context:
+    """One context per device (nb200_create / nb200_destroy)."""
+
+    def __init__(self, device=0):
+        self.h = C.c_void_p()
+        rc = lib().nb200_create(device, C.byref(self.h))
+        if rc:
+            raise NestB200Error(rc, lib().nb200_last_error(None).decode())
+
+    def close(self):
+        if self.h:
+            lib().nb200_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc:
+            raise NestB200Error(rc, lib().nb200_last_error(self.h).decode())
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(lib().nb200_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    def synchronize(self):
+        self._check(lib().nb200_synchronize(self.h))
+
+    def launch_count(self):
+        return int(lib().nb200_launch_count(self.h))
+
+    def yields(self, det, mo, species, E, field, density):
+        """GetYields on the device for host arrays E, field -> dict of 6 columns."""
+        E = np.ascontiguousarray(E, np.float64)
+        F = np.ascontiguousarray(np.broadcast_to(field, E.shape), np.float64)
+        out = np.empty((6, E.size))
+        self._check(lib().nb200_yields(self.h, C.byref(det), C.byref(mo), species, E.size, _dptr(E), _dptr(F),
+                                       density, MEM_HOST, _dptr(out)))
+        return out
+
+    def run(self, det, mo, ana, src, rc, seed, n, first_event=0, columns=None, band=None):
+        """nb200_run with host outputs. columns: names from SOA_COLUMNS (None = all)."""
+        cols = {}
+        soa = SoaOut()
+        soa.mem_kind = MEM_HOST
+        names = SOA_COLUMNS if columns is None else columns
+        for nme in names:
+            if nme in SOA_I32:
+                a = np.zeros(n, np.int32)
+                setattr(soa, nme, a.ctypes.data)
+            elif nme.startswith("s1_") or nme.startswith("s2_"):
+                a = np.zeros(n, np.float64)
+                getattr(soa, nme[:2])[int(nme[3:])] = a.ctypes.data
+            else:
+                a = np.zeros(n, np.float64)
+                setattr(soa, nme, a.ctypes.data)
+            cols[nme] = a
+        self._check(lib().nb200_run(self.h, C.byref(det), C.byref(mo), C.byref(ana), C.byref(src), C.byref(rc),
+                                    seed, first_event, n, C.byref(soa) if names else None,
+                                    C.byref(band.c) if band is not None else None))
+        return cols
+
+    def band_reset(self, ana):
+        self._check(lib().nb200_band_reset(self.h, C.byref(ana)))
+
+    def run_async(self, det, mo, ana, src, rc, seed, first_event, n, soa=None):
+        self._check(lib().nb200_run_async(self.h, C.byref(det), C.byref(mo), C.byref(ana), C.byref(src),
+                                          C.byref(rc), seed, first_event, n, C.byref(soa) if soa else None))
+
+    def band_attach(self, ana, device_ptr):
+        self._check(lib().nb200_band_attach(self.h, C.byref(ana), C.c_void_p(device_ptr)))
+
+    def fp64_peak(self):
+        v = C.c_double()
+        self._check(lib().nb200_fp64_peak(self.h, C.byref(v)))
+        return v.value
+
+    def band_fetch(self, band):
+        self._check(lib().nb200_band_fetch(self.h, C.byref(band.c)))
+
+    def band_device_buffer(self):
+        p = C.c_void_p()
+        n = C.c_size_t()
+        self._check(lib().nb200_band_device_buffer(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def lar(self, species, E, field, density, seed=0, first_event=0, want_fluct=True):
+        E = np.ascontiguousarray(E, np.float64)
+        F = np.ascontiguousarray(np.broadcast_to(field, E.shape), np.float64)
+        y = np.empty((9, E.size))
+        f = np.empty((4, E.size)) if want_fluct else None
+        self._check(lib().nb200_lar(self.h, species, E.size, _dptr(E), _dptr(F), density, seed, first_event,
+                                    MEM_HOST, _dptr(y), _dptr(f) if want_fluct else None))
+        return y, f

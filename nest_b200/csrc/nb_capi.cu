@@ -1,0 +1,998 @@
+// nb_capi.cu -- the C-ABI of include/nest_b200.h over the sm_100a kernels.
+// No CPU fallback: every compute entry point needs a CUDA device and fails with
+// NB200_ENODEV / NB200_ECUDA otherwise.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "nb_host.h"
+#include "nb_kernels.cuh"
+
+using namespace nb;
+
+struct nb200_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  uint64_t launches = 0;
+  int* d_err = nullptr;
+  // device-resident band accumulator (async API)
+  unsigned long long* d_band = nullptr;
+  bool band_external = false;
+  size_t band_words = 0;
+  int band_numBins = 0, band_logBins = 0;
+  uint64_t band_events = 0;
+  // scratch accumulator for the synchronous nb200_run
+  unsigned long long* d_band_tmp = nullptr;
+  size_t band_tmp_words = 0;
+  // cached device copies of map LUTs / WIMP tables / drift table
+  struct Blob {
+    const void* host;
+    size_t bytes;
+    void* dev;
+  };
+  std::vector<Blob> blobs;
+  std::vector<double> vtable_host;
+  nb200_detector vtable_det;
+  double vtable_zstep = 0.;
+  double* d_vtable = nullptr;
+};
+
+namespace {
+
+thread_local std::string g_err_noctx;
+
+int fail(nb200_ctx* c, int code, const std::string& msg) {
+  if (c)
+    c->err = msg;
+  else
+    g_err_noctx = msg;
+  return code;
+}
+#define NB_CUDA(c, call)                                                                   \
+  do {                                                                                     \
+    cudaError_t e_ = (call);                                                               \
+    if (e_ != cudaSuccess)                                                                 \
+      return fail(c, NB200_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));     \
+  } while (0)
+
+size_t band_word_count(const nb200_analysis* a) {
+  return size_t(a->numBins) * BAND_WORDS + size_t(a->numBins) * size_t(a->logBins > 0 ? a->logBins : 0);
+}
+
+// upload (or reuse) a host table; keyed on pointer+size+content hash
+int upload_blob(nb200_ctx* c, const void* host, size_t bytes, void** dev) {
+  for (auto& b : c->blobs)
+    if (b.host == host && b.bytes == bytes) {
+      NB_CUDA(c, cudaMemcpyAsync(b.dev, host, bytes, cudaMemcpyHostToDevice, c->stream));
+      *dev = b.dev;
+      return 0;
+    }
+  void* d = nullptr;
+  NB_CUDA(c, cudaMalloc(&d, bytes));
+  NB_CUDA(c, cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, c->stream));
+  c->blobs.push_back({host, bytes, d});
+  *dev = d;
+  return 0;
+}
+
+int upload_map(nb200_ctx* c, nb200_map* m) {
+  if (m->kind != NB200_MAP_LUT_RZ) {
+    m->lut = nullptr;
+    return 0;
+  }
+  if (!m->lut || m->n0 < 1 || m->n1 < 1) return fail(c, NB200_EINVAL, "LUT map without table");
+  void* d = nullptr;
+  int rc = upload_blob(c, m->lut, sizeof(double) * size_t(m->n0) * size_t(m->n1), &d);
+  if (rc) return rc;
+  m->lut = static_cast<const double*>(d);
+  return 0;
+}
+
+int validate(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo, const nb200_analysis* ana,
+             const nb200_source* src) {
+  if (!det || !mo || !ana || !src) return fail(c, NB200_EINVAL, "null argument");
+  // execNEST.cpp:419-426
+  if (det->TopDrift <= 0. || det->anode <= 0. || det->gate <= 0.)
+    return fail(c, NB200_EINVAL, "ERROR, unphysical value(s) of position within the detector geometry.");
+  if (mo->n_widths < 13 || mo->n_widths > 17)  // NEST.cpp:255-259
+    return fail(c, NB200_EPHYSICS, "ERROR: You need a minimum of 13 free parameters for the resolution model.");
+  if (ana->numBins < 1 || ana->numBins > 1000)  // NUMBINS_MAX TestSpectra.hh:34, execNEST.cpp:1510-1516
+    return fail(c, NB200_EINVAL, "ERROR: Too many bins. Decrease numBins (analysis.hh) or increase NUMBINS_MAX");
+  if (ana->s1mode < NB200_S1_FULL || ana->s1mode > NB200_S1_HYBRID || ana->s2mode != NB200_S2_FULL)
+    return fail(c, NB200_EINVAL, "Waveform S1/S2 calculation modes are not part of this path");
+  if (src->species == NB200_Kr83m || src->species > NB200_atmNu)
+    return fail(c, NB200_EINVAL, "species not supported by the GPU chain");
+  if (src->inField < 0. && src->inField != -1. && !src->vec_mode)  // execNEST.cpp:863-868
+    return fail(c, NB200_EINVAL, "ERROR: Neg field is not permitted. We don't simulate field dir (yet). Put in magnitude.");
+  if (det->E_gas < 0.) return fail(c, NB200_EINVAL, "ERROR: Neg field is not permitted.");
+  if (src->kind == NB200_SRC_LIST && !src->E) return fail(c, NB200_EINVAL, "LIST source without energies");
+  if (src->kind == NB200_SRC_WIMP && (!src->wimp_base || !src->wimp_exponent))
+    return fail(c, NB200_EINVAL, "WIMP source without nb200_wimp_prep table");
+  // RecombOmegaER's throw (NEST.cpp:183-184) is reached by every ER-like event
+  const bool erlike = src->species >= NB200_gammaRay || mo->er_model >= 0;
+  if (erlike && mo->NRERWidthsParam[9] > mo->NRERWidthsParam[8])
+    return fail(c, NB200_EPHYSICS,
+                "Low-E r-fluct Gauss peak's width greater than centroid. This is physically wrong so "
+                "please check your inputs, in NRERWidthsParam: they must be in the old wrong order.");
+  return 0;
+}
+
+// Everything the kernel needs beyond the caller's PODs
+int build_params(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo, const nb200_analysis* ana,
+                 const nb200_source* src, const nb200_run_consts* rc, uint64_t seed, uint64_t first,
+                 uint64_t n, RunParams* P) {
+  int r = validate(c, det, mo, ana, src);
+  if (r) return r;
+  if (!rc) return fail(c, NB200_EINVAL, "null run constants (call nb200_prepare)");
+  std::memset(P, 0, sizeof *P);
+  P->det = *det;
+  P->model = *mo;
+  P->ana = *ana;
+  P->src = *src;
+  P->rc = *rc;
+  if ((r = upload_map(c, &P->det.FitS1))) return r;
+  if ((r = upload_map(c, &P->det.FitS2))) return r;
+  if ((r = upload_map(c, &P->det.FitEF))) return r;
+  if ((r = upload_map(c, &P->det.FitTBA))) return r;
+  // ion: execNEST.cpp:1056-1063 swaps the width vector
+  if (!src->vec_mode && src->species == NB200_ion) {
+    const double w[13] = {1.00, 1.00, 0., 0.50, 0.19, 0., 1., 0.046452, 0.45, 0.205, -0.2, 0., 0.};
+    std::memset(P->model.NRERWidthsParam, 0, sizeof P->model.NRERWidthsParam);
+    std::memcpy(P->model.NRERWidthsParam, w, sizeof w);
+    P->model.n_widths = 13;
+  }
+  // per-run hoists (host maps evaluate the caller's LUT, not the device copy)
+  const double zc = det->TopDrift - rc->vD_middle * det->dtCntr;
+  P->s1_center = fit_s1(det->FitS1, 0., 0., zc);
+  P->s2_center = fit_s2(det->FitS2, 0., 0.);
+  P->coin_u_min = exp(-det->coinWind / 20.);
+  {
+    const double sq2 = sqrt(2.);
+    double a_spe = 0.5 * (1. + erf(-1. / det->sPEres / sq2));
+    double x_spe = 0.5 * (1. + erf((det->sPEthr - 1.) / det->sPEres / sq2));
+    double spe = (x_spe - a_spe) / (1. - a_spe);
+    double a_dpe = 0.5 * (1. + erf(-2. / (sq2 * det->sPEres) / sq2));
+    double x_dpe = 0.5 * (1. + erf((det->sPEthr - 2.) / (sq2 * det->sPEres) / sq2));
+    double dpe = (x_dpe - a_dpe) / (1. - a_dpe);
+    P->below_thr_pct = spe * (1. - det->P_dphe) + dpe * det->P_dphe;
+    P->recon_mult = 0.5 * (1. + erf((det->sPEthr - 1.) / (det->sPEres * sqrt(2.)))) /
+                    (det->sPEres * sqrt(2. * M_PI));
+  }
+  if (ana->useS2 == 2) {
+    P->band_width = (ana->maxS2 - ana->minS2) / double(ana->numBins);
+    P->band_border = ana->minS2;
+  } else {
+    P->band_width = (ana->maxS1 - ana->minS1) / double(ana->numBins);
+    P->band_border = ana->minS1;
+  }
+  {
+    double K = det->T_Kelvin;
+    int i = host::drift_bracket(K);
+    if (i < 0) return fail(c, NB200_EPHYSICS, "ERROR: TEMPERATURE OUT OF RANGE (100-230 K)");
+    std::memcpy(P->dv_row[0], host::kPolyExp[i], sizeof(double) * 7);
+    std::memcpy(P->dv_row[1], host::kPolyExp[i + 1], sizeof(double) * 7);
+    P->dv_Ti = host::kDriftT[i];
+    P->dv_Tf = host::kDriftT[i + 1];
+    P->dv_T = K;
+    P->dv_mode = nearly_equal(K, P->dv_Ti) ? 1 : (nearly_equal(K, P->dv_Tf) ? 2 : 0);
+  }
+  if (src->inField == -1. && !src->vec_mode) {
+    const double zs = ana->z_step > 0. ? ana->z_step : 0.1;
+    if (c->vtable_host.empty() || std::memcmp(&c->vtable_det, det, sizeof *det) != 0 || c->vtable_zstep != zs) {
+      c->vtable_host = host::drift_table_nonuniform(*det, zs, 0., 0.);
+      c->vtable_det = *det;
+      c->vtable_zstep = zs;
+      if (c->d_vtable) cudaFree(c->d_vtable);
+      NB_CUDA(c, cudaMalloc(&c->d_vtable, sizeof(double) * c->vtable_host.size()));
+      NB_CUDA(c, cudaMemcpyAsync(c->d_vtable, c->vtable_host.data(), sizeof(double) * c->vtable_host.size(),
+                                 cudaMemcpyHostToDevice, c->stream));
+    }
+    P->vtable = c->d_vtable;
+    P->vtable_n = int(c->vtable_host.size());
+  }
+  if (src->kind == NB200_SRC_WIMP) {
+    void* d = nullptr;
+    if ((r = upload_blob(c, src->wimp_base, sizeof(double) * 100, &d))) return r;
+    P->src.wimp_base = static_cast<const double*>(d);
+    if ((r = upload_blob(c, src->wimp_exponent, sizeof(double) * 100, &d))) return r;
+    P->src.wimp_exponent = static_cast<const double*>(d);
+    for (int k = 0; k < 9; ++k) {
+      bool ok;
+      P->wimp_dr0[k] = host::wimp_drate(0., src->wimp_mass, src->wimp_day, double(host::kXeIsotopes[k]), &ok);
+      if (!ok) return fail(c, NB200_EPHYSICS, "\tThe velocity integral in the WIMP generator broke!!!");
+    }
+  }
+  P->seed = seed;
+  P->first_event = first;
+  P->n_events = n;
+  P->species = src->species;
+  P->vec_mode = src->vec_mode;
+  return 0;
+}
+
+constexpr int kBlock = 512;
+
+int launch_event(nb200_ctx* c, RunParams& P) {
+  if (P.n_events == 0) return 0;
+  size_t smem = 0;
+  P.band_in_smem = 0;
+  if (P.do_band) {
+    smem = size_t(P.ana.numBins) * BAND_WORDS * 8 + size_t(P.ana.numBins) * size_t(P.ana.logBins) * 4;
+    if (smem <= 160 * 1024)
+      P.band_in_smem = 1;
+    else
+      smem = 0;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    NB_CUDA(c, cudaFuncSetAttribute(k_event<kBlock>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_set = true;
+  }
+  uint64_t batches = (P.n_events + kBlock - 1) / kBlock;
+  unsigned grid = unsigned(std::min<uint64_t>(batches, uint64_t(c->sm_count)));
+  k_event<kBlock><<<grid, kBlock, smem, c->stream>>>(P, c->d_err);
+  NB_CUDA(c, cudaGetLastError());
+  ++c->launches;
+  return 0;
+}
+
+int check_device_error(nb200_ctx* c) {
+  int h = 0;
+  NB_CUDA(c, cudaMemcpyAsync(&h, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  NB_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (h) {
+    NB_CUDA(c, cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream));
+    if (h & 2) return fail(c, NB200_EINVAL, "species not supported by the GPU chain");
+    return fail(c, NB200_EPHYSICS, "ERROR: Quanta not conserved. Tell Matthew Immediately!");
+  }
+  return 0;
+}
+
+// SplitMix-free URBG over the Philox host stream, for libstdc++ distributions
+struct HostUrbg {
+  Stream s;
+  using result_type = uint64_t;
+  static constexpr result_type min() { return 0; }
+  static constexpr result_type max() { return ~result_type(0); }
+  result_type operator()() {
+    uint32_t a, b;
+    s.next2(a, b);
+    return (uint64_t(a) << 32) | b;
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+int nb200_abi_version(void) { return NB200_ABI_VERSION; }
+
+int nb200_sizeof(int which) {
+  switch (which) {
+    case 0: return int(sizeof(nb200_map));
+    case 1: return int(sizeof(nb200_detector));
+    case 2: return int(sizeof(nb200_model));
+    case 3: return int(sizeof(nb200_analysis));
+    case 4: return int(sizeof(nb200_source));
+    case 5: return int(sizeof(nb200_run_consts));
+    case 6: return int(sizeof(nb200_soa_out));
+    case 7: return int(sizeof(nb200_band_hist));
+    default: return -1;
+  }
+}
+
+int nb200_create(int device, nb200_ctx** out) {
+  if (!out) return NB200_EINVAL;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0)
+    return fail(nullptr, NB200_ENODEV, std::string("no CUDA device: ") + cudaGetErrorString(e));
+  if (device < 0 || device >= count) return fail(nullptr, NB200_EINVAL, "bad device ordinal");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, NB200_ECUDA, "cudaGetDeviceProperties");
+  if (prop.major != 10)
+    return fail(nullptr, NB200_ENODEV, "device is not sm_100 (this library carries sm_100a code only)");
+  nb200_ctx* c = new nb200_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMalloc(&c->d_err, sizeof(int)) != cudaSuccess || cudaMemset(c->d_err, 0, sizeof(int)) != cudaSuccess) {
+    g_err_noctx = std::string("context setup: ") + cudaGetErrorString(cudaGetLastError());
+    delete c;
+    return NB200_ECUDA;
+  }
+  c->stream = c->own_stream;
+  *out = c;
+  return 0;
+}
+
+void nb200_destroy(nb200_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (auto& b : c->blobs) cudaFree(b.dev);
+  if (c->d_band && !c->band_external) cudaFree(c->d_band);
+  if (c->d_band_tmp) cudaFree(c->d_band_tmp);
+  if (c->d_vtable) cudaFree(c->d_vtable);
+  if (c->d_err) cudaFree(c->d_err);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+}
+
+const char* nb200_last_error(const nb200_ctx* c) { return c ? c->err.c_str() : g_err_noctx.c_str(); }
+
+int nb200_set_stream(nb200_ctx* c, void* s) {
+  if (!c) return NB200_EINVAL;
+  c->stream = s ? static_cast<cudaStream_t>(s) : c->own_stream;
+  return 0;
+}
+
+int nb200_synchronize(nb200_ctx* c) {
+  if (!c) return NB200_EINVAL;
+  NB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+uint64_t nb200_launch_count(const nb200_ctx* c) { return c ? c->launches : 0; }
+
+// ---- host-only helpers ------------------------------------------------------------------
+
+int nb200_detector_builtin(const char* name, nb200_detector* d) {
+  if (!name || !d) return NB200_EINVAL;
+  std::memset(d, 0, sizeof *d);
+  std::string n(name);
+  auto cmap = [](double v) {
+    nb200_map m;
+    std::memset(&m, 0, sizeof m);
+    m.kind = NB200_MAP_CONST;
+    m.c[0] = v;
+    return m;
+  };
+  if (n == "VDetector" || n == "LArDetector") {  // VDetector.hh:157-224
+    d->g1 = 0.0760; d->sPEres = 0.58; d->sPEthr = 0.35; d->sPEeff = 1.00;
+    d->P_dphe = 0.2; d->coinWind = 100; d->coinLevel = 2; d->numPMTs = 89; d->OldW13eV = 1;
+    d->noiseLinear[0] = 3e-2; d->noiseLinear[1] = 3e-2;
+    d->g1_gas = 0.06; d->s2Fano = 3.61; d->s2_thr = 300.; d->E_gas = 12.; d->eLife_us = 2200.;
+    d->T_Kelvin = 177.; d->p_bar = 2.14; d->dtCntr = 40.; d->dt_min = 20.; d->dt_max = 60.;
+    d->radius = 50.; d->radmax = 50.; d->TopDrift = 150.; d->anode = 152.5; d->gate = 147.5; d->cathode = 1.00;
+    d->PosResFlat = 3.00; d->PosResBase = 70.8364; d->molarMass = 131.293;
+    d->FitS1 = cmap(1.); d->FitS2 = cmap(1.); d->FitEF = cmap(730.); d->FitTBA = cmap(0.5);
+    return 0;
+  }
+  if (n == "LUX_Run03" || n == "LUX Run03") {  // LUX_Run03.hh:30-88
+    d->g1 = 0.1170; d->sPEres = 0.37; d->sPEthr = (0.3 * 1.173) / 0.915; d->sPEeff = 1.00;
+    d->noiseBaseline[0] = 0.00; d->noiseBaseline[1] = 0.08;
+    d->P_dphe = 0.173; d->coinWind = 100; d->coinLevel = 2; d->numPMTs = 119; d->OldW13eV = 1;
+    d->noiseLinear[0] = 0.0e-2; d->noiseLinear[1] = 9.0e-2;
+    d->g1_gas = 0.1; d->s2Fano = 3.6; d->s2_thr = (150. * 1.173) / 0.915; d->E_gas = 6.25; d->eLife_us = 800.;
+    d->T_Kelvin = 173.; d->p_bar = 1.57; d->dtCntr = 160.; d->dt_min = 38.; d->dt_max = 305.;
+    d->radius = 200.; d->radmax = 235.; d->TopDrift = 544.95; d->anode = 549.2; d->gate = 539.2; d->cathode = 55.90;
+    d->PosResFlat = 3.00; d->PosResBase = 70.8364; d->molarMass = 131.293;
+    nb200_map m;
+    std::memset(&m, 0, sizeof m);
+    m.kind = NB200_MAP_LUX_RUN03;
+    const double s1c[7] = {307.9, 0.3071, 0.0002257, 1.1525e-7, 318.84, 307.9, 235.};
+    std::memcpy(m.c, s1c, sizeof s1c);
+    d->FitS1 = m;
+    std::memset(&m, 0, sizeof m);
+    m.kind = NB200_MAP_LUX_RUN03;
+    const double s2c[10] = {9156.3, 6.22750, 0.38126, 0.017144, 0.0002474, 1.6953e-6, 5.6513e-9, 7.3989e-12, 9156.3, 235.};
+    std::memcpy(m.c, s2c, sizeof s2c);
+    d->FitS2 = m;
+    std::memset(&m, 0, sizeof m);
+    m.kind = NB200_MAP_LUX_RUN03;
+    const double efc[6] = {158.92, 0.2209000, 0.0024485, 8.7098e-6, 1.5049e-8, 1.0110e-11};
+    std::memcpy(m.c, efc, sizeof efc);
+    d->FitEF = m;
+    d->FitTBA = cmap(0.449);
+    return 0;
+  }
+  return fail(nullptr, NB200_EINVAL, "unknown built-in detector " + n);
+}
+
+int nb200_model_default(int which, nb200_model* m) {
+  if (!m) return NB200_EINVAL;
+  std::memset(m, 0, sizeof *m);
+  const double nr[12] = {11., 1.1, 0.0480, -0.0533, 12.6, 0.3, 2., 0.3, 2., 0.5, 1., 1.};  // NEST.hh:120-121
+  std::memcpy(m->NRYieldsParam, nr, sizeof nr);
+  for (int i = 0; i < 10; ++i) m->ERYieldsParam[i] = -1.;  // NEST.hh:124
+  if (which == 0) {  // NEST.hh:122-123
+    const double w[13] = {0.4, 0.4, 0.04, 0.5, 0.19, 2.25, -0.001, 0.046452, 0.45, 0.205, -0.2, 0., 0.};
+    std::memcpy(m->NRERWidthsParam, w, sizeof w);
+    m->SkewnessER = -999.;
+  } else {  // execNEST.cpp:188-204, :1065
+    const double w[13] = {0.4, 0.4, 0.04, 0.50, 0.19, 2.25, -0.00050, 0.03290, 2.629, 0.2964, -.3343, 0.0000, 0.0000};
+    std::memcpy(m->NRERWidthsParam, w, sizeof w);
+    m->SkewnessER = 0.;
+  }
+  m->n_widths = 13;
+  m->er_model = -1;
+  m->multFact = 1.;
+  m->massNum = 0.;
+  m->atomNum = 0.;
+  return 0;
+}
+
+int nb200_analysis_default(int which, nb200_analysis* a) {
+  if (!a) return NB200_EINVAL;
+  std::memset(a, 0, sizeof *a);
+  a->s1mode = NB200_S1_HYBRID;
+  a->s2mode = NB200_S2_FULL;
+  a->logBins = 30;
+  if (which == 0) {  // analysis.hh
+    a->usePD = 2; a->useS2 = 0; a->numBins = 98; a->minS1 = 1.5; a->maxS1 = 99.5;
+    a->minS2 = 42.; a->maxS2 = 1e4; a->logMin = 0.6; a->logMax = 3.6;
+    a->MCtruthE = 0; a->MCtruthPos = 0; a->z_step = 0.1;
+  } else {  // analysis_G2.hh
+    a->usePD = 1; a->useS2 = 1; a->numBins = 118; a->minS1 = 2.5; a->maxS1 = 120.5;
+    a->minS2 = 200.; a->maxS2 = 9e4; a->logMin = 2.; a->logMax = 5.;
+    a->MCtruthE = 1; a->MCtruthPos = 0; a->z_step = 1.;
+  }
+  return 0;
+}
+
+int nb200_prepare(nb200_detector* det, double inField, double z_step, nb200_run_consts* out) {
+  if (!det || !out) return NB200_EINVAL;
+  std::memset(out, 0, sizeof *out);
+  bool inGas = false;
+  std::string warn;
+  double rho = host::density(det->T_Kelvin, det->p_bar, inGas, det->molarMass, &warn);
+  det->inGas = inGas ? 1 : 0;
+  if (rho <= 0. || det->T_Kelvin <= 0. || det->p_bar <= 0.)  // execNEST.cpp:613-617
+    return fail(nullptr, NB200_EINVAL, "ERR: Unphysical thermodynamic property!");
+  if (rho < 1.75) det->inGas = 1;  // execNEST.cpp:618-619
+  if (det->inGas)
+    return fail(nullptr, NB200_EINVAL, "gas-phase detectors (MagBoltz drift) are not part of this path");
+  Wvalue w = work_function(rho, det->molarMass, det->OldW13eV != 0);
+  out->rho = rho;
+  out->Wq_eV = det->OldW13eV ? w.Wq_eV : 11.5;  // execNEST.cpp:626-627
+  out->alpha = w.alpha;
+  if (!host::calculate_g2(*det, out->g2_params))
+    return fail(nullptr, NB200_EPHYSICS, "\tERR: The gas gap in the S2 calculation broke!!!!");
+  out->NewMean = host::find_new_mean(det->sPEres);
+  out->field = inField;
+  bool ok = true;
+  if (inField == -1.) {
+    const double zs = z_step > 0. ? z_step : 0.1;
+    std::vector<double> t = host::drift_table_nonuniform(*det, zs, 0., 0.);
+    double centralZ = (det->gate * 0.8 + det->cathode * 1.03) / 2.;
+    size_t i = size_t(floor(centralZ / zs + 0.5));
+    if (t.empty() || i >= t.size()) return fail(nullptr, NB200_EINVAL, "drift table does not reach centralZ");
+    out->vD_middle = t[i];
+    out->vD = out->vD_middle;
+  } else {
+    out->vD_middle = host::drift_velocity_liquid(det->T_Kelvin, inField, &ok);
+    out->vD = out->vD_middle;
+  }
+  if (!ok) return fail(nullptr, NB200_EPHYSICS, "ERROR: TEMPERATURE OUT OF RANGE (100-230 K)");
+  // execNEST.cpp:955-961
+  if (inField != -1. && det->dt_min > (det->TopDrift - 0.) / out->vD && inField >= NB_FIELD_MIN)
+    return fail(nullptr, NB200_EINVAL, "ERROR: dt_min is too restrictive (too large)");
+  return 0;
+}
+
+int nb200_wimp_prep(double mass, double eStep, double dayNum, uint64_t seed, double* base, double* exponent,
+                    double* integral, double* xMaxOut, double* divisorOut) {
+  if (!base || !exponent || !integral || !xMaxOut || !divisorOut) return NB200_EINVAL;
+  Stream g;
+  g.init(seed, 0, STREAM_HOST);
+  for (int i = 0; i < 100; ++i) {  // TestSpectra.hh:44-45 initialisers
+    base[i] = (i == 0) ? 1. : 0.;
+    exponent[i] = 0.;
+  }
+  double divisor;
+  int numberPoints;
+  if (mass < 10.) {
+    divisor = 10. / eStep;
+    numberPoints = int(1000. / eStep);
+  } else {
+    divisor = 1.0 / eStep;
+    numberPoints = int(100. / eStep);
+  }
+  std::vector<double> spec;
+  int nZeros = 0;
+  bool ok = true;
+  for (int i = 0; i < numberPoints + 1; ++i) {
+    spec.push_back(host::wimp_drate(double(i) / divisor, mass, dayNum, double(host::select_xe_atom(g)), &ok));
+    if (!ok) return fail(nullptr, NB200_EPHYSICS, "\tThe velocity integral in the WIMP generator broke!!!");
+    if (nearly_equal(spec[i], 0.))
+      ++nZeros;
+    else
+      nZeros = 0;
+    if (nZeros == 100) break;
+  }
+  double integ = 0.;
+  for (uint64_t i = 0; i < 1000000; ++i)
+    integ += host::wimp_drate(double(i) / 1e4, mass, dayNum, double(host::select_xe_atom(g)), &ok) / 1e4;
+  double xMax = (double(spec.size()) - 1.) / divisor;
+  for (int i = 0; i < int(spec.size()) - 1; ++i) {
+    if (i >= 100) return fail(nullptr, NB200_EPHYSICS, "ERROR: WIMP E_step is too small: more than 100 table intervals");
+    double x1 = double(i) / divisor, x2 = double(i + 1) / divisor;
+    base[i] = spec[i + 1] * pow(spec[i + 1] / spec[i], x2 / (x1 - x2));
+    exponent[i] = log(spec[i + 1] / spec[i]) / (x1 - x2);
+    if (base[i] > 0. && base[i] < DBL_MAX && exponent[i] > 0. && exponent[i] < DBL_MAX)
+      ;
+    else {
+      if (spec[i + 1] > 10.)
+        return fail(nullptr, NB200_EPHYSICS,
+                    "ERROR: WIMP E_step is too small (or large)! Increase(decrease) it slightly to avoid "
+                    "noise in the calculation.");
+      xMax = double(i - 1) / divisor;
+      if (xMax <= 0.0)
+        return fail(nullptr, NB200_EPHYSICS,
+                    "ERROR: The maximum possible WIMP recoil is not +-ive, which usually means your E_step "
+                    "is too small (OR it is too large).");
+      break;
+    }
+  }
+  *integral = integ;
+  *xMaxOut = xMax;
+  *divisorOut = divisor;
+  return 0;
+}
+
+uint64_t nb200_poisson(double mean, uint64_t seed) {
+  HostUrbg u;
+  u.s.init(seed, 1, STREAM_HOST);
+  return std::poisson_distribution<uint64_t>(mean)(u);
+}
+
+// ---- deterministic yields ----------------------------------------------------------------
+
+int nb200_yields(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo, int species, size_t n,
+                 const double* E, const double* field, double density, int mem_kind, double* out) {
+  if (!c) return NB200_EINVAL;
+  if (!det || !mo || !E || !field || !out) return fail(c, NB200_EINVAL, "null argument");
+  if (n == 0) return 0;
+  if (species == NB200_Kr83m || species > NB200_NoneType) return fail(c, NB200_EINVAL, "species not supported");
+  NB_CUDA(c, cudaSetDevice(c->device));
+  YieldsParams P;
+  std::memset(&P, 0, sizeof P);
+  P.det = *det;
+  P.model = *mo;
+  P.species = species;
+  P.which = mo->er_model;
+  P.density = density;
+  P.n = n;
+  P.seed = 0;
+  double *dE = nullptr, *dF = nullptr, *dO = nullptr;
+  if (mem_kind == NB200_MEM_HOST) {
+    NB_CUDA(c, cudaMalloc(&dE, n * 8));
+    NB_CUDA(c, cudaMalloc(&dF, n * 8));
+    NB_CUDA(c, cudaMalloc(&dO, n * 48));
+    NB_CUDA(c, cudaMemcpyAsync(dE, E, n * 8, cudaMemcpyHostToDevice, c->stream));
+    NB_CUDA(c, cudaMemcpyAsync(dF, field, n * 8, cudaMemcpyHostToDevice, c->stream));
+    P.E = dE;
+    P.field = dF;
+    P.out = dO;
+  } else {
+    P.E = E;
+    P.field = field;
+    P.out = out;
+  }
+  unsigned grid = unsigned(std::min<uint64_t>((n + 255) / 256, uint64_t(c->sm_count) * 8));
+  k_yields<<<grid, 256, 0, c->stream>>>(P, c->d_err);
+  cudaError_t le = cudaGetLastError();
+  ++c->launches;
+  int rc = 0;
+  if (le != cudaSuccess) rc = fail(c, NB200_ECUDA, std::string("k_yields: ") + cudaGetErrorString(le));
+  if (!rc && mem_kind == NB200_MEM_HOST) {
+    cudaError_t e = cudaMemcpyAsync(out, dO, n * 48, cudaMemcpyDeviceToHost, c->stream);
+    if (e != cudaSuccess) rc = fail(c, NB200_ECUDA, cudaGetErrorString(e));
+  }
+  if (!rc) rc = check_device_error(c);
+  if (dE) cudaFree(dE);
+  if (dF) cudaFree(dF);
+  if (dO) cudaFree(dO);
+  return rc;
+}
+
+// ---- the chain ---------------------------------------------------------------------------
+
+size_t nb200_band_hist_bytes(const nb200_analysis* a) { return a ? band_word_count(a) * 8 : 0; }
+
+int nb200_band_reset(nb200_ctx* c, const nb200_analysis* ana) {
+  if (!c || !ana) return NB200_EINVAL;
+  if (ana->numBins < 1 || ana->numBins > 1000 || ana->logBins < 0) return fail(c, NB200_EINVAL, "bad band geometry");
+  NB_CUDA(c, cudaSetDevice(c->device));
+  size_t w = band_word_count(ana);
+  if (w != c->band_words || c->band_external) {
+    if (c->d_band && !c->band_external) cudaFree(c->d_band);
+    c->d_band = nullptr;
+    c->band_external = false;
+    NB_CUDA(c, cudaMalloc(&c->d_band, w * 8));
+    c->band_words = w;
+  }
+  c->band_numBins = ana->numBins;
+  c->band_logBins = ana->logBins;
+  c->band_events = 0;
+  NB_CUDA(c, cudaMemsetAsync(c->d_band, 0, w * 8, c->stream));
+  return 0;
+}
+
+int nb200_band_attach(nb200_ctx* c, const nb200_analysis* ana, void* buf) {
+  if (!c || !ana || !buf) return NB200_EINVAL;
+  if (ana->numBins < 1 || ana->numBins > 1000 || ana->logBins < 0) return fail(c, NB200_EINVAL, "bad band geometry");
+  if (c->d_band && !c->band_external) cudaFree(c->d_band);
+  c->d_band = static_cast<unsigned long long*>(buf);
+  c->band_external = true;
+  c->band_words = band_word_count(ana);
+  c->band_numBins = ana->numBins;
+  c->band_logBins = ana->logBins;
+  c->band_events = 0;
+  return 0;
+}
+
+int nb200_run_async(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo, const nb200_analysis* ana,
+                    const nb200_source* src, const nb200_run_consts* rc, uint64_t seed, uint64_t first_event,
+                    uint64_t n_events, nb200_soa_out* soa) {
+  if (!c) return NB200_EINVAL;
+  NB_CUDA(c, cudaSetDevice(c->device));
+  RunParams P;
+  int r = build_params(c, det, mo, ana, src, rc, seed, first_event, n_events, &P);
+  if (r) return r;
+  if (src->kind == NB200_SRC_LIST && src->list_mem_kind != NB200_MEM_DEVICE)
+    return fail(c, NB200_EINVAL, "nb200_run_async needs a device-resident energy list");
+  if (soa) {
+    if (soa->mem_kind != NB200_MEM_DEVICE) return fail(c, NB200_EINVAL, "nb200_run_async needs device SoA pointers");
+    P.write_soa = 1;
+    static_assert(sizeof(SoaDev) == sizeof(nb200_soa_out) - 8, "SoA layouts must match");
+    std::memcpy(&P.soa, reinterpret_cast<const char*>(soa) + 8, sizeof(SoaDev));
+  }
+  if (c->d_band && !src->vec_mode) {
+    if (c->band_numBins != ana->numBins || c->band_logBins != ana->logBins)
+      return fail(c, NB200_EINVAL, "band accumulator geometry differs from the analysis (call nb200_band_reset)");
+    P.do_band = 1;
+    P.band = c->d_band;
+    c->band_events += n_events;
+  }
+  return launch_event(c, P);
+}
+
+int nb200_band_fetch(nb200_ctx* c, nb200_band_hist* h) {
+  if (!c || !h) return NB200_EINVAL;
+  if (!c->d_band) return fail(c, NB200_EINVAL, "no device band accumulator (call nb200_band_reset)");
+  if (h->numBins != c->band_numBins || h->logBins != c->band_logBins) return fail(c, NB200_EINVAL, "band geometry mismatch");
+  std::vector<unsigned long long> w(c->band_words);
+  NB_CUDA(c, cudaMemcpyAsync(w.data(), c->d_band, c->band_words * 8, cudaMemcpyDeviceToHost, c->stream));
+  int rc = check_device_error(c);  // synchronises
+  if (rc) return rc;
+  for (int j = 0; j < h->numBins; ++j) {
+    const unsigned long long* b = &w[size_t(j) * BAND_WORDS];
+    if (h->accepted) h->accepted[j] += b[0];
+    if (h->rejected) h->rejected[j] += b[1];
+    if (h->sumS1) h->sumS1[j] += (int64_t)b[2];
+    if (h->sumY) h->sumY[j] += (int64_t)b[3];
+    if (h->sumY2) h->sumY2[j] += (int64_t)b[4];
+    if (h->sumY3) h->sumY3[j] += (int64_t)b[5];
+  }
+  if (h->hist2d)
+    for (size_t i = 0; i < size_t(h->numBins) * size_t(h->logBins); ++i)
+      h->hist2d[i] += w[size_t(h->numBins) * BAND_WORDS + i];
+  h->n_events += c->band_events;
+  return 0;
+}
+
+int nb200_band_device_buffer(nb200_ctx* c, void** dptr, size_t* n_u64) {
+  if (!c || !dptr || !n_u64) return NB200_EINVAL;
+  *dptr = c->d_band;
+  *n_u64 = c->band_words;
+  return c->d_band ? 0 : fail(c, NB200_EINVAL, "no device band accumulator");
+}
+
+int nb200_allreduce_hist(nb200_ctx* c, void* comm) {
+  if (!c || !comm) return NB200_EINVAL;
+  if (!c->d_band) return fail(c, NB200_EINVAL, "no device band accumulator");
+  // ncclAllReduce(sendbuff, recvbuff, count, ncclUint64 = 5, ncclSum = 0, comm, stream)
+  typedef int (*allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+  static allreduce_fn fn = nullptr;
+  if (!fn) {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW);
+    if (!h) return fail(c, NB200_EINVAL, std::string("libnccl.so.2 not loadable: ") + dlerror());
+    fn = reinterpret_cast<allreduce_fn>(dlsym(h, "ncclAllReduce"));
+    if (!fn) return fail(c, NB200_EINVAL, "ncclAllReduce not found");
+  }
+  int r = fn(c->d_band, c->d_band, c->band_words, 5, 0, comm, c->stream);
+  if (r != 0) return fail(c, NB200_ECUDA, "ncclAllReduce failed with code " + std::to_string(r));
+  return 0;
+}
+
+int nb200_run(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo, const nb200_analysis* ana,
+              const nb200_source* src, const nb200_run_consts* rc, uint64_t seed, uint64_t first_event,
+              uint64_t n_events, nb200_soa_out* soa, nb200_band_hist* hist) {
+  if (!c) return NB200_EINVAL;
+  NB_CUDA(c, cudaSetDevice(c->device));
+  int r = validate(c, det, mo, ana, src);
+  if (r) return r;
+  if (hist && (hist->numBins != ana->numBins || hist->logBins != ana->logBins))
+    return fail(c, NB200_EINVAL, "band geometry mismatch");
+  if (n_events == 0) return 0;
+  const bool host_soa = soa && soa->mem_kind == NB200_MEM_HOST;
+  const bool host_list = src->kind == NB200_SRC_LIST && src->list_mem_kind == NB200_MEM_HOST;
+  const uint64_t chunk_max = 1ull << 22;
+  // device staging for host SoA columns
+  struct Col {
+    void** host_slot;
+    void* host;
+    void* dev;
+    size_t elt;
+  };
+  std::vector<Col> cols;
+  nb200_soa_out dsoa;
+  std::vector<void*> to_free;
+  auto cleanup = [&]() {
+    for (void* p : to_free) cudaFree(p);
+  };
+  const uint64_t cap = std::min<uint64_t>(n_events, chunk_max);
+  if (soa) {
+    dsoa = *soa;
+    dsoa.mem_kind = NB200_MEM_DEVICE;
+    if (host_soa) {
+      void** hp = reinterpret_cast<void**>(reinterpret_cast<char*>(soa) + 8);
+      void** dp = reinterpret_cast<void**>(reinterpret_cast<char*>(&dsoa) + 8);
+      const size_t ncol = (sizeof(nb200_soa_out) - 8) / sizeof(void*);
+      for (size_t k = 0; k < ncol; ++k) {
+        if (!hp[k]) continue;
+        const bool is_int = (k >= 8 && k < 12);
+        size_t elt = is_int ? 4 : 8;
+        void* d = nullptr;
+        cudaError_t e = cudaMalloc(&d, elt * cap);
+        if (e != cudaSuccess) {
+          cleanup();
+          return fail(c, NB200_ENOMEM, cudaGetErrorString(e));
+        }
+        to_free.push_back(d);
+        dp[k] = d;
+        cols.push_back({&dp[k], hp[k], d, elt});
+      }
+    }
+  }
+  double *dE = nullptr, *dx = nullptr, *dy = nullptr, *dz = nullptr;
+  if (host_list) {
+    auto mk = [&](double** d) {
+      cudaError_t e = cudaMalloc(d, 8 * cap);
+      if (e == cudaSuccess) to_free.push_back(*d);
+      return e;
+    };
+    if (mk(&dE) != cudaSuccess || (src->x && (mk(&dx) != cudaSuccess || mk(&dy) != cudaSuccess || mk(&dz) != cudaSuccess))) {
+      cleanup();
+      return fail(c, NB200_ENOMEM, "device staging for the energy list");
+    }
+  }
+  if (hist) {
+    size_t w = band_word_count(ana);
+    if (w != c->band_tmp_words) {
+      if (c->d_band_tmp) cudaFree(c->d_band_tmp);
+      c->d_band_tmp = nullptr;
+      cudaError_t e = cudaMalloc(&c->d_band_tmp, w * 8);
+      if (e != cudaSuccess) {
+        cleanup();
+        return fail(c, NB200_ENOMEM, cudaGetErrorString(e));
+      }
+      c->band_tmp_words = w;
+    }
+    cudaMemsetAsync(c->d_band_tmp, 0, w * 8, c->stream);
+  }
+
+  int rcode = 0;
+  for (uint64_t done = 0; done < n_events && !rcode; done += chunk_max) {
+    const uint64_t m = std::min<uint64_t>(chunk_max, n_events - done);
+    nb200_source s = *src;
+    if (src->kind == NB200_SRC_LIST) {
+      if (host_list) {
+        cudaMemcpyAsync(dE, src->E + done, 8 * m, cudaMemcpyHostToDevice, c->stream);
+        s.E = dE;
+        if (src->x) {
+          cudaMemcpyAsync(dx, src->x + done, 8 * m, cudaMemcpyHostToDevice, c->stream);
+          cudaMemcpyAsync(dy, src->y + done, 8 * m, cudaMemcpyHostToDevice, c->stream);
+          cudaMemcpyAsync(dz, src->z + done, 8 * m, cudaMemcpyHostToDevice, c->stream);
+          s.x = dx;
+          s.y = dy;
+          s.z = dz;
+        }
+      } else {
+        s.E = src->E + done;
+        if (src->x) {
+          s.x = src->x + done;
+          s.y = src->y + done;
+          s.z = src->z + done;
+        }
+      }
+    }
+    RunParams P;
+    rcode = build_params(c, det, mo, ana, &s, rc, seed, first_event + done, m, &P);
+    if (rcode) break;
+    if (soa) {
+      P.write_soa = 1;
+      nb200_soa_out tmp = dsoa;
+      if (!host_soa) {  // advance caller's device columns
+        void** dp = reinterpret_cast<void**>(reinterpret_cast<char*>(&tmp) + 8);
+        const size_t ncol = (sizeof(nb200_soa_out) - 8) / sizeof(void*);
+        for (size_t k = 0; k < ncol; ++k)
+          if (dp[k]) dp[k] = static_cast<char*>(dp[k]) + ((k >= 8 && k < 12) ? 4 : 8) * done;
+      }
+      std::memcpy(&P.soa, reinterpret_cast<const char*>(&tmp) + 8, sizeof(SoaDev));
+    }
+    if (hist && !src->vec_mode) {
+      P.do_band = 1;
+      P.band = c->d_band_tmp;
+    }
+    rcode = launch_event(c, P);
+    if (rcode) break;
+    if (host_soa)
+      for (auto& col : cols)
+        cudaMemcpyAsync(static_cast<char*>(col.host) + col.elt * done, col.dev, col.elt * m, cudaMemcpyDeviceToHost,
+                        c->stream);
+    rcode = check_device_error(c);
+  }
+  if (!rcode && hist) {
+    std::vector<unsigned long long> w(c->band_tmp_words);
+    cudaError_t e = cudaMemcpyAsync(w.data(), c->d_band_tmp, c->band_tmp_words * 8, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess)
+      rcode = fail(c, NB200_ECUDA, cudaGetErrorString(e));
+    else {
+      for (int j = 0; j < hist->numBins; ++j) {
+        const unsigned long long* b = &w[size_t(j) * BAND_WORDS];
+        if (hist->accepted) hist->accepted[j] += b[0];
+        if (hist->rejected) hist->rejected[j] += b[1];
+        if (hist->sumS1) hist->sumS1[j] += (int64_t)b[2];
+        if (hist->sumY) hist->sumY[j] += (int64_t)b[3];
+        if (hist->sumY2) hist->sumY2[j] += (int64_t)b[4];
+        if (hist->sumY3) hist->sumY3[j] += (int64_t)b[5];
+      }
+      if (hist->hist2d)
+        for (size_t i = 0; i < size_t(hist->numBins) * size_t(hist->logBins); ++i)
+          hist->hist2d[i] += w[size_t(hist->numBins) * BAND_WORDS + i];
+      hist->n_events += n_events;
+    }
+  }
+  cudaStreamSynchronize(c->stream);
+  cleanup();
+  return rcode;
+}
+
+// GetBand's closing statistics (execNEST.cpp:1582-1618) from the integer accumulator
+int nb200_band_finalize(const nb200_analysis* ana, const nb200_band_hist* h, double* band) {
+  if (!ana || !h || !band) return NB200_EINVAL;
+  if (!h->accepted || !h->rejected || !h->sumS1 || !h->sumY || !h->sumY2 || !h->sumY3) return NB200_EINVAL;
+  double binWidth, border;
+  if (ana->useS2 == 2) {
+    binWidth = (ana->maxS2 - ana->minS2) / double(ana->numBins);
+    border = ana->minS2;
+  } else {
+    binWidth = (ana->maxS1 - ana->minS1) / double(ana->numBins);
+    border = ana->minS1;
+  }
+  for (int j = 0; j < ana->numBins; ++j) {
+    double* b = band + 7 * size_t(j);
+    const double N = double(h->accepted[j]);
+    const double Sy = double(h->sumY[j]) / NB200_FX_Y, Sy2 = double(h->sumY2[j]) / NB200_FX_Y2,
+                 Sy3 = double(h->sumY3[j]) / NB200_FX_Y3, Sx = double(h->sumS1[j]) / NB200_FX_S1;
+    b[0] = border + binWidth / 2. + double(j) * binWidth;
+    b[1] = Sx / N;
+    const double mu = Sy / N;
+    b[2] = mu;
+    double var = (Sy2 - 2. * mu * Sy + N * mu * mu) / (N - 1.);
+    b[3] = sqrt(var);
+    b[4] = b[3] / sqrt(N);
+    b[5] = N / (N + double(h->rejected[j]));
+    double m3 = Sy3 - 3. * mu * Sy2 + 3. * mu * mu * Sy - N * mu * mu * mu;
+    b[6] = m3 / (b[3] * b[3] * b[3]) / (N - 2.);
+  }
+  return 0;
+}
+
+// ---- FP64 pipe peak ---------------------------------------------------------------------
+}  // extern "C"
+namespace {
+__global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x * 1e-3, x1 = x0 + 1., x2 = x0 + 2., x3 = x0 + 3., x4 = x0 + 4., x5 = x0 + 5.,
+         x6 = x0 + 6., x7 = x0 + 7.;
+  for (int i = 0; i < iters; ++i) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+  if (s == 123.456) out[0] = s;
+}
+}  // namespace
+extern "C" {
+int nb200_fp64_peak(nb200_ctx* c, double* tflops) {
+  if (!c || !tflops) return NB200_EINVAL;
+  NB_CUDA(c, cudaSetDevice(c->device));
+  double* d = nullptr;
+  NB_CUDA(c, cudaMalloc(&d, 8));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int iters = 1 << 15, blocks = c->sm_count * 8;
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0, c->stream);
+    k_dfma_peak<<<blocks, 256, 0, c->stream>>>(d, iters, 0.999999, 1e-9);
+    cudaEventRecord(e1, c->stream);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+    ++c->launches;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  NB_CUDA(c, cudaGetLastError());
+  *tflops = 2.0 * 8.0 * double(iters) * 256.0 * double(blocks) / (double(best) * 1e-3) / 1e12;
+  return 0;
+}
+
+// ---- liquid argon ---------------------------------------------------------------------------
+
+int nb200_lar(nb200_ctx* c, int species, size_t n, const double* E, const double* field, double density,
+              uint64_t seed, uint64_t first_event, int mem_kind, double* yields, double* fluct) {
+  if (!c) return NB200_EINVAL;
+  if (!E || !field) return fail(c, NB200_EINVAL, "null argument");
+  if (species < 0 || species > 2)
+    return fail(c, NB200_EINVAL, "LAr species must be NR(0), ER(1) or Alpha(2); dE/dx and LET models are not part of this path");
+  if (n == 0) return 0;
+  NB_CUDA(c, cudaSetDevice(c->device));
+  LArParams P;
+  std::memset(&P, 0, sizeof P);
+  P.species = species;
+  P.n = n;
+  P.seed = seed;
+  P.first_event = first_event;
+  P.density = density;
+  std::vector<void*> fr;
+  auto cleanup = [&]() {
+    for (void* p : fr) cudaFree(p);
+  };
+  double *dE = nullptr, *dF = nullptr, *dY = nullptr, *dFl = nullptr;
+  if (mem_kind == NB200_MEM_HOST) {
+    cudaError_t e = cudaMalloc(&dE, n * 8);
+    if (e == cudaSuccess) { fr.push_back(dE); e = cudaMalloc(&dF, n * 8); }
+    if (e == cudaSuccess) { fr.push_back(dF); if (yields) { e = cudaMalloc(&dY, n * 72); if (e == cudaSuccess) fr.push_back(dY); } }
+    if (e == cudaSuccess && fluct) { e = cudaMalloc(&dFl, n * 32); if (e == cudaSuccess) fr.push_back(dFl); }
+    if (e != cudaSuccess) {
+      cleanup();
+      return fail(c, NB200_ENOMEM, cudaGetErrorString(e));
+    }
+    cudaMemcpyAsync(dE, E, n * 8, cudaMemcpyHostToDevice, c->stream);
+    cudaMemcpyAsync(dF, field, n * 8, cudaMemcpyHostToDevice, c->stream);
+    P.E = dE;
+    P.field = dF;
+    P.yields = dY;
+    P.fluct = dFl;
+  } else {
+    P.E = E;
+    P.field = field;
+    P.yields = yields;
+    P.fluct = fluct;
+  }
+  unsigned grid = unsigned(std::min<uint64_t>((n + 255) / 256, uint64_t(c->sm_count) * 8));
+  k_lar<<<grid, 256, 0, c->stream>>>(P);
+  cudaError_t le = cudaGetLastError();
+  ++c->launches;
+  int rc = 0;
+  if (le != cudaSuccess) rc = fail(c, NB200_ECUDA, std::string("k_lar: ") + cudaGetErrorString(le));
+  if (!rc && mem_kind == NB200_MEM_HOST) {
+    if (yields) cudaMemcpyAsync(yields, dY, n * 72, cudaMemcpyDeviceToHost, c->stream);
+    if (fluct) cudaMemcpyAsync(fluct, dFl, n * 32, cudaMemcpyDeviceToHost, c->stream);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) rc = fail(c, NB200_ECUDA, cudaGetErrorString(e));
+  }
+  cleanup();
+  return rc;
+}
+
+}  // extern "C"

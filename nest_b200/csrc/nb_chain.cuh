@@ -1,0 +1,761 @@
+// nb_chain.cuh -- the stochastic stages of the per-event chain (device).
+//
+// GetQuanta, GetS1 (split into prelude / per-hit / epilogue so that the hit loop can be
+// regrouped across threads), GetS2, xyResolution, the TestSpectra samplers, the
+// execNEST() signal selection + energy reconstruction and the GetBand binning.
+// Reference lines are cited per function (src/NEST.cpp, src/execNEST.cpp,
+// src/TestSpectra.cpp of NESTCollaboration/nest).
+#pragma once
+#include "nb_yields.cuh"
+
+namespace nb {
+#ifdef __CUDACC__
+
+struct Quanta {  // QuantaResult NEST.hh:171-178
+  int photons, electrons, ions, excitons;
+  double recombProb, Variance;
+};
+
+// NESTcalc::RecombOmegaNR NEST.cpp:164-171
+NB_D double recomb_omega_nr(double elecFrac, const double* w) {
+  double d = elecFrac - w[3];
+  double omega = w[2] * exp(-0.5 * (d * d) / (w[4] * w[4]));
+  if (omega < 0.) omega = 0;
+  return omega;
+}
+
+// NESTcalc::RecombOmegaER NEST.cpp:173-225 (the wide > cntr throw is checked on the host)
+NB_D double recomb_omega_er(double efield, double elecFrac, double numQuanta, const double* w,
+                            int nw) {
+  double ampl = 0.07 + (w[7] - 0.07) / pow(1. + pow(efield / 295.2, 251.6), 0.0069114);
+  if (ampl < 0.) ampl = 0.;
+  double cntr = w[8], wide = w[9], skew = w[10];
+  double mode = cntr + 2. * NB_INV_SQRT2PI * skew * wide / sqrt(1. + skew * skew);
+  double dm = mode - cntr;
+  double norm =
+      1. / (exp(-0.5 * (dm * dm) / (wide * wide)) * (1. + erf(skew * (mode - cntr) / (wide * NB_SQRT2))));
+  double omega;
+  if (cntr < 1.) {
+    double d = elecFrac - cntr;
+    omega = norm * ampl * exp(-0.5 * (d * d) / (wide * wide)) *
+            (1. + erf(skew * (elecFrac - cntr) / (wide * NB_SQRT2)));
+  } else {
+    double ampl2 = 0.06103, cntr2 = 5.207, wide2 = 1.361, skew2 = -2.495;
+    if (nw > 15) {
+      ampl2 = w[13];
+      cntr2 = w[14];
+      wide2 = w[15];
+    }
+    if (nw > 16) skew2 = w[16];
+    double mode2 = cntr2 + 2. * NB_INV_SQRT2PI * skew2 * wide2 / sqrt(1. + skew2 * skew2);
+    double logNQ = log10(numQuanta);
+    double dm2 = mode2 - cntr2;
+    double norm2 = 1. / (exp(-0.5 * (dm2 * dm2) / (wide2 * wide2)) *
+                         (1. + erf(skew2 * (mode2 - cntr2) / (wide2 * NB_SQRT2))));
+    double d1 = logNQ - cntr, d2 = logNQ - cntr2;
+    omega = 0.00 +
+            norm * ampl * exp(-0.5 * (d1 * d1) / (wide * wide)) *
+                (1. + erf(skew * (logNQ - cntr) / (wide * NB_SQRT2))) +
+            norm2 * ampl2 * exp(-0.5 * (d2 * d2) / (wide2 * wide2)) *
+                (1. + erf(skew2 * (logNQ - cntr2) / (wide2 * NB_SQRT2)));
+  }
+  if (omega < 0.) omega = 0;
+  return omega;
+}
+
+// NESTcalc::FanoER NEST.cpp:227-246
+NB_D double fano_er(double density, double Nq_mean, double efield, const double* w, bool inGas) {
+  double Fano = 0.12707 - 0.029623 * density - 0.0057042 * (density * density) +
+                0.0015957 * (density * density * density);
+  if (!inGas) {
+    if (w[6] < 0.)
+      Fano += fabs(w[6]) * sqrt(Nq_mean) * sqrt(efield);
+    else
+      Fano = w[6];
+  }
+  return Fano;
+}
+
+NB_D int to_int_round(double x) { return int(floor(x + 0.5)); }
+
+// NESTcalc::GetQuanta NEST.cpp:248-432
+NB_D Quanta get_quanta(Stream& g, const Yields& y, double density, const nb200_detector& det,
+                       const nb200_model& mo, int* err) {
+  const double* w = mo.NRERWidthsParam;
+  Quanta q{0, 0, 0, 0, 0., 0.};
+  bool HighE;
+  int Nq_actual, Ne, Nph, Ni, Nex;
+  double excitonRatio = y.NexONi;
+  double Nq_mean = y.Nph + y.Ne;
+  double elecFrac = smax(0., smin(y.Ne / Nq_mean, 1.));
+  if (excitonRatio < 0.) {
+    excitonRatio = 0.;
+    HighE = true;
+  } else
+    HighE = false;
+  double alf = 1. / (1. + excitonRatio);
+  double recombProb = 1. - (excitonRatio + 1.) * elecFrac;
+  if (recombProb < 0.) excitonRatio = 1. / elecFrac - 1.;
+
+  const bool isER = nearly_equal(y.L, 1.);
+  if (isER) {
+    if (nearly_equal(Nq_mean, 0.))
+      Nq_actual = 0;
+    else {
+      double Fano = fano_er(density, Nq_mean, y.field, w, det.inGas != 0);
+      Nq_actual = to_int_round(gauss(g, Nq_mean, sqrt(Fano * Nq_mean), true));
+    }
+    Ni = int(binomial(g, Nq_actual, alf));
+    Nex = Nq_actual - Ni;
+  } else {
+    // two independent Gaussians (:294-311); both come from one Box-Muller pair
+    double z0, z1;
+    normal_pair(g, z0, z1);
+    double Ni_mean = Nq_mean * alf;
+    double Fano = w[0] + w[11] * Ni_mean;
+    if (Fano < 0.) Fano = 0.;
+    double d = Ni_mean + sqrt(Fano * Ni_mean) * z0;
+    Ni = to_int_round((d < 0.) ? 0. : d);
+    double Nex_mean = Nq_mean * excitonRatio * alf;
+    Fano = w[1] + w[12] * Nex_mean;
+    if (Fano < 0.) Fano = 0.;
+    d = Nex_mean + sqrt(Fano * Nex_mean) * z1;
+    Nex = to_int_round((d < 0.) ? 0. : d);
+    Nq_actual = Nex + Ni;
+  }
+  if (Nq_actual == 0) return q;
+
+  if (Nex < 0) Nex = 0;
+  if (Ni < 0) Ni = 0;
+  if (Nex > Nq_actual) Nex = Nq_actual;
+  if (Ni > Nq_actual) Ni = Nq_actual;
+  q.ions = Ni;
+  q.excitons = Nex;
+
+  if (Nex <= 0 && HighE) recombProb = y.Nph / double(Ni);
+  recombProb = smax(0., smin(recombProb, 1.));
+  if (isnan(recombProb) || isnan(elecFrac) || Ni == 0 || nearly_equal(recombProb, 0.0)) {
+    q.photons = Nex;
+    q.electrons = Ni;
+    q.recombProb = 0.;
+    q.Variance = 0.;
+    return q;
+  }
+
+  double omega = y.L < 1 ? recomb_omega_nr(elecFrac, w)
+                         : recomb_omega_er(y.field, elecFrac, Nq_mean, w, mo.n_widths);
+  double lambdaChen;
+  if (w[2] < 0. && y.L < 1)
+    lambdaChen = 1.0 + w[2];
+  else
+    lambdaChen = 1.0;
+  if (lambdaChen <= 0.) lambdaChen = 1E-6;
+  double Variance = lambdaChen * recombProb * (1. - recombProb) * Ni + omega * omega * Ni * Ni;
+
+  double skewness;
+  if ((y.Nph + y.Ne) > 1e4 || y.field > 4e3 || y.field < 50.) {
+    skewness = 0.00;
+  } else {
+    skewness = 0.;
+    if (isER) {
+      if (mo.SkewnessER != -999.) {
+        skewness = mo.SkewnessER;
+      } else {  // LUX skewness model :366-388
+        Wvalue wv = work_function(density, det.molarMass, det.OldW13eV != 0);
+        double engy = 1e-3 * wv.Wq_eV * (y.Nph + y.Ne);
+        double fld = y.field;
+        const double alpha0 = 1.39, cc0 = 4.0, cc1 = 22.1, E0 = 7.7, E1 = 54., E2 = 26.7, E3 = 6.4,
+                     F0 = 225., F1 = 71.;
+        skewness = 1. / (1. + exp((engy - E2) / E3)) *
+                       (alpha0 + cc0 * exp(-1. * fld / F0) * (1. - exp(-1. * engy / E0))) +
+                   1. / (1. + exp(-1. * (engy - E2) / E3)) * cc1 * exp(-1. * engy / E1) *
+                       exp(-1. * sqrt(fld) / sqrt(F1));
+      }
+    } else {
+      skewness = w[5];
+    }
+  }
+
+  double widthCorrection = sqrt(1. - (2. / NB_PI) * skewness * skewness / (1. + skewness * skewness));
+  double muCorrection = (sqrt(Variance) / widthCorrection) *
+                        (skewness / sqrt(1. + skewness * skewness)) * 2. * NB_INV_SQRT2PI;
+  if (fabs(skewness) > DBL_MIN)
+    Ne = to_int_round(skew_gauss(g, (1. - recombProb) * Ni - muCorrection,
+                                 sqrt(Variance) / widthCorrection, skewness));
+  else
+    Ne = to_int_round(gauss(g, (1. - recombProb) * Ni, sqrt(Variance), true));
+
+  Ne = min(max(Ne, 0), Ni);  // NESTcalc::clamp
+  Nph = Nq_actual - Ne;
+  if (Nph > Nq_actual) Nph = Nq_actual;
+  if (Nph < Nex) Nph = Nex;
+  if ((Nph + Ne) != (Nex + Ni)) *err = 1;
+  q.Variance = Variance;
+  q.recombProb = recombProb;
+  q.photons = Nph;
+  q.electrons = Ne;
+  return q;
+}
+
+// NESTcalc::xyResolution NEST.cpp:2699-2736
+NB_D void xy_resolution(Stream& g, const nb200_detector& det, double x, double y, double A_top,
+                        double& sx, double& sy) {
+  A_top *= 1. - fit_tba(det.FitTBA, x, y, det.TopDrift / 2.);
+  double kappa = det.PosResBase;
+  double sigmaR = kappa / sqrt(A_top);
+  sigmaR = sqrt(sigmaR * sigmaR + det.PosResFlat * det.PosResFlat);
+  double phi2 = 2. * g.uniform();  // phi = 2 pi u
+  sigmaR = fabs(gauss(g, 0.0, sigmaR, false));
+  double s, c;
+  sincospi(phi2, &s, &c);
+  double sigmaX = sigmaR * c, sigmaY = sigmaR * s;
+  if (sigmaR > 1e2 || isnan(sigmaR) || sigmaR < 0. || fabs(sigmaX) > 1e2 || fabs(sigmaY) > 1e2) {
+    if (A_top > 40.) {
+      sigmaX = 0.;
+      sigmaY = 0.;
+    }
+  }
+  sx = x + sigmaX;
+  sy = y + sigmaY;
+}
+
+// ---- S1 ---------------------------------------------------------------------------------
+struct S1Pre {
+  double posDepSm, fitSm;  // FitS1(smear)/centre, and FitS1(smear) itself (GetSpike)
+  double eff;
+  int nHits;
+  bool full;  // Full per-hit loop (true) or Parametric
+};
+
+// eff ramp NEST.cpp:1339-1347
+NB_D double s1_eff(const nb200_detector& det, int nHits) {
+  double eff = det.sPEeff;
+  if (eff < 1.) eff += ((1. - eff) / (2. * double(det.numPMTs))) * double(nHits);
+  return smax(0., smin(eff, 1.));
+}
+
+// GetS1 up to the per-hit loop: NEST.cpp:1288-1362
+NB_D S1Pre s1_prelude(Stream& g, const RunParams& P, int Nph, double tx, double ty, double tz,
+                      double sx, double sy, double sz, double energy) {
+  const nb200_detector& det = P.det;
+  S1Pre r;
+  double posDep = fit_s1(det.FitS1, tx, ty, tz);
+  r.fitSm = fit_s1(det.FitS1, sx, sy, sz);
+  posDep /= P.s1_center;
+  r.posDepSm = r.fitSm / P.s1_center;
+  double g1_XYZ = smax(0., smin(det.g1 * posDep, 1.));
+  if (nearly_equal(det.g1, 1.)) {
+    g1_XYZ = 1.;
+    r.posDepSm = 1.;
+  }
+  if (nearly_equal(det.g1, 0.)) {
+    g1_XYZ = 0.;
+    r.posDepSm = 0.;
+  }
+  r.nHits = int(binomial(g, Nph, g1_XYZ));
+  r.eff = s1_eff(det, r.nHits);
+  int mode = P.ana.s1mode;
+  if (mode == NB200_S1_HYBRID) mode = energy < 100. ? NB200_S1_FULL : NB200_S1_PARAMETRIC;
+  r.full = (mode == NB200_S1_FULL);
+  return r;
+}
+
+struct S1Acc {
+  double area;
+  int spike, nphe;
+};
+
+// One PMT hit of the Full S1 loop, NEST.cpp:1367-1429, on its own counter block
+// (seed; event, hit index).  Same distribution as the reference per hit:
+//   * phe = zero-truncated Gaussian(1/NewMean, sPEres) + Gaussian baseline noise; the two
+//     normals are the two outputs of ONE Box-Muller transform (independent N(0,1));
+//   * u > eff kills the area only when eff < 1 (u <= 1 always);
+//   * the double-phe decision uses a 32-bit uniform;
+//   * -20 ln u < coinWind is tested as u > exp(-coinWind/20) and the draw is skipped when
+//     nHits > coinLevel makes the test irrelevant.
+NB_D double s1_ztg_redraw(uint64_t seed, uint64_t event, uint32_t blk, double mean, double sigma) {
+  Stream x;
+  x.init(seed, event, STREAM_HITX);
+  x.blk = blk;
+  double t;
+  int guard = 0;
+  do {
+    t = mean + sigma * normal(x);
+  } while (t <= 0. && ++guard < 60);
+  return t;
+}
+NB_D void s1_hit(const RunParams& P, uint64_t seed, uint64_t event, uint32_t k, double eff,
+                 bool need_coin, double spe_mean, S1Acc& acc) {
+  const nb200_detector& det = P.det;
+  const uint32_t k0 = uint32_t(seed), k1 = uint32_t(seed >> 32);
+  const uint32_t e0 = uint32_t(event), e1 = uint32_t(event >> 32);
+  // block 1: radius (53 bits), angle (32 bits), double-phe decision (32 bits)
+  u128 r = philox4x32_10(e0, e1, k, STREAM_HIT, k0, k1);
+  double rad = sqrt(-2.0 * log(u53(r.x, r.y)));
+  double s, c;
+  sincospi(2.0 * u32d(r.z), &s, &c);
+  double tg = fma(det.sPEres, rad * c, spe_mean);
+  if (tg <= 0.)  // redraw the truncated Gaussian (P ~ 0.4 % at sPEres 0.37)
+    tg = s1_ztg_redraw(seed, event, k * 64u, spe_mean, det.sPEres);
+  double phe1 = tg + fma(det.noiseBaseline[1], rad * s, det.noiseBaseline[0]);
+  int nphe = 1;
+  const bool dphe = u32d(r.w) < det.P_dphe;
+  double phe2 = 0., ucoin = 1.;
+  bool lost1 = false, lost2 = false;
+  if (eff < 1.) {  // block 3: the two single-phe efficiency decisions (:1381-1386, :1403)
+    u128 t = philox4x32_10(e0, e1, k, STREAM_HIT3, k0, k1);
+    lost1 = u32d(t.x) > eff;
+    lost2 = u32d(t.y) > eff;
+  }
+  if (dphe || need_coin) {
+    // block 2: second photo-electron (radius, angle) and the coincidence-window draw
+    u128 q = philox4x32_10(e0, e1, k, STREAM_HIT2, k0, k1);
+    ucoin = u32d(q.w);
+    if (dphe) {
+      double rad2 = sqrt(-2.0 * log(u53(q.x, q.y)));
+      double s2, c2;
+      sincospi(2.0 * u32d(q.z), &s2, &c2);
+      double tg2 = fma(det.sPEres, rad2 * c2, spe_mean);
+      if (tg2 <= 0.) tg2 = s1_ztg_redraw(seed, event, k * 64u + 32u, spe_mean, det.sPEres);
+      phe2 = tg2 + fma(det.noiseBaseline[1], rad2 * s2, det.noiseBaseline[0]);
+      ++nphe;
+      if (lost2 && lost1) phe2 = 0.;
+    }
+  }
+  if (lost1) phe1 = 0.;
+  double a = phe1 + phe2;
+  acc.nphe += nphe;
+  if (a > det.sPEthr && (!need_coin || ucoin > P.coin_u_min)) {
+    acc.spike += 1;
+    acc.area += a;
+  }
+}
+
+// Parametric S1, NEST.cpp:1432-1481
+NB_D void s1_parametric(Stream& g, const RunParams& P, int nHits, S1Acc& acc) {
+  const nb200_detector& det = P.det;
+  int Nphe = nHits + int(binomial(g, nHits, det.P_dphe));
+  double eff = s1_eff(det, nHits);
+  double Nphe_det = double(binomial(g, Nphe, 1. - (1. - eff) / (1. + det.P_dphe)));
+  acc.area = gauss(g, Nphe_det * (1. / P.rc.NewMean), det.sPEres * sqrt(Nphe_det / P.rc.NewMean), true);
+  acc.spike = int(binomial(g, nHits, eff * (1. - P.below_thr_pct)));
+  acc.nphe = Nphe;
+}
+
+// n-choose-r as the ratio of factorials the reference forms with tgammal (NEST.cpp:2237-2241)
+NB_D double n_choose_r(double n, int r) {
+  double c = 1.;
+  for (int j = 1; j <= r; ++j) c = c * (n - double(r) + double(j)) / double(j);
+  return c;
+}
+
+// GetS1 after the hit loop: noise, thresholds, corrections, n-fold coincidence, GetSpike,
+// below-threshold sign flag.  NEST.cpp:1608-1721, 2243-2268.  out[9] = scintillation.
+NB_D void s1_epilogue(Stream& g, const RunParams& P, const S1Pre& pre, const S1Acc& acc,
+                      double* out) {
+  const nb200_detector& det = P.det;
+  double pulseArea = acc.area;
+  double spike = double(acc.spike);
+  double sig;
+  if (det.noiseQuadratic[0] != 0) {
+    double a = det.noiseQuadratic[0] * pulseArea * pulseArea, b = det.noiseLinear[0] * pulseArea;
+    sig = sqrt(a * a + b * b);
+  } else
+    sig = det.noiseLinear[0] * pulseArea;
+  // gauss(mu, 0, true) == max(mu, 0): skip the draw when the width is exactly zero
+  if (sig != 0.)
+    pulseArea = gauss(g, pulseArea, sig, true);
+  else
+    pulseArea = (pulseArea < 0.) ? 0. : pulseArea;
+  if (pulseArea < det.sPEthr) pulseArea = 0.;
+  if (spike < 0) spike = 0;
+  double pulseAreaC = pulseArea / pre.posDepSm;
+  double Nphd = pulseArea / (1. + det.P_dphe);
+  double NphdC = pulseAreaC / (1. + det.P_dphe);
+  double spikeC = spike / pre.posDepSm;
+  out[0] = pre.nHits;
+  out[1] = acc.nphe;
+  out[2] = pulseArea;
+  out[3] = pulseAreaC;
+  out[4] = Nphd;
+  out[5] = NphdC;
+  out[6] = spike;
+  out[7] = spikeC;
+  out[8] = spike;
+
+  double prob;
+  if (spike < det.coinLevel)
+    prob = 0.;
+  else if (spike > 10.)
+    prob = 1.;
+  else if (det.coinLevel == 0)
+    prob = 1.;
+  else if (det.coinLevel == 1)
+    prob = (spike >= 1.) ? 1. : 0.;
+  else if (det.coinLevel == 2)
+    prob = 1. - pow(double(det.numPMTs), 1. - spike);
+  else {
+    double numer = 0., denom = 0.;
+    for (int i = int(spike); i > 0; --i) {
+      double c = n_choose_r(double(det.numPMTs), i);
+      denom += c;
+      if (i >= det.coinLevel) numer += c;
+    }
+    prob = numer / denom;
+  }
+
+  if (spike >= 1. && spikeC > 0.) {  // GetSpike NEST.cpp:2243-2268
+    if (spikeC > NB_SPIKES_MAXM) {
+      out[6] = Nphd;
+      out[7] = NphdC;
+    } else {
+      double ns = zero_trunc_gauss(g, spike, (det.sPEres / 4.) * sqrt(fabs(spike)));
+      out[6] = ns;
+      out[7] = ns / pre.fitSm * P.s1_center;
+    }
+  }
+
+  // rand_uniform() > prob && prob < 1: the draw is irrelevant when prob >= 1
+  if (prob < 1. && g.uniform() > prob) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      double v = out[i];
+      if (nearly_equal(v, 0.)) v = NB_PHE_MIN;
+      out[i] = -1. * fabs(v);
+    }
+  }
+}
+
+// NESTcalc::GetS2, S2CalculationMode::Full: NEST.cpp:1724-1776, 1975-2063.  out[9] = ionization
+NB_D void get_s2(Stream& g, const RunParams& P, int Ne, double tx, double ty, double tz, double sx,
+                 double sy, double dt, double dfield, double* out) {
+  const nb200_detector& det = P.det;
+  const double elYield = P.rc.g2_params[0], ExtEff = P.rc.g2_params[1], SE = P.rc.g2_params[2],
+               g2 = P.rc.g2_params[3], gasGap = P.rc.g2_params[4];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) out[i] = 0.;
+  if (dfield < NB_FIELD_MIN || elYield <= 0. || ExtEff <= 0. || SE <= 0. || g2 <= 0. || gasGap <= 0.)
+    return;
+  double posDep = fit_s2(det.FitS2, tx, ty) / P.s2_center;
+  double posDepSm = fit_s2(det.FitS2, sx, sy) / P.s2_center;
+  if (nearly_equal(det.g1_gas, 1.)) {
+    posDep = 1.;
+    posDepSm = 1.;
+  }
+  if (nearly_equal(det.g1_gas, 0.)) {
+    posDep = 0.;
+    posDepSm = 0.;
+  }
+  const double life = exp(-dt / det.eLife_us);
+  long long Nee = binomial(g, Ne, ExtEff * life);
+  double mu = elYield * double(Nee);
+  double nphd = floor(gauss(g, mu, sqrt(det.s2Fano * elYield * double(Nee)), true) + 0.5);
+  long long Nph = (long long)nphd;
+  long long nHits = binomial(g, Nph, det.g1_gas * posDep);
+  long long Nphe = nHits + binomial(g, nHits, det.P_dphe);
+  double m = double(Nphe) / P.rc.NewMean;
+  double pulseArea = gauss(g, m, det.sPEres * sqrt(m), true);
+  double sig;
+  if (det.noiseQuadratic[1] != 0) {
+    double a = det.noiseQuadratic[1] * (pulseArea * pulseArea), b = det.noiseLinear[1] * pulseArea;
+    sig = sqrt(a * a + b * b);
+  } else
+    sig = det.noiseLinear[1] * pulseArea;
+  if (sig != 0.)
+    pulseArea = gauss(g, pulseArea, sig, true);
+  else
+    pulseArea = (pulseArea < 0.) ? 0. : pulseArea;
+  double pulseAreaC = pulseArea / life / posDepSm;
+  double Nphd = pulseArea / (1. + det.P_dphe);
+  double NphdC = pulseAreaC / (1. + det.P_dphe);
+  out[0] = double(Nee);
+  out[1] = double(Nph);
+  out[2] = double(nHits);
+  out[3] = double(Nphe);
+  if (det.s2_thr >= 0) {
+    out[4] = pulseArea;
+    out[5] = pulseAreaC;
+    out[6] = Nphd;
+    out[7] = NphdC;
+  } else {  // bottom-array S2 (:2010-2049); the S2b draw only matters on this branch
+    double tba = fit_tba(det.FitTBA, tx, ty, tz);
+    double S2b = gauss(g, tba * pulseArea, sqrt(tba * pulseArea * (1. - tba)), true);
+    double S2bc = S2b / life / posDepSm;
+    out[4] = S2b;
+    out[5] = S2bc;
+    out[6] = S2b / (1. + det.P_dphe);
+    out[7] = S2bc / (1. + det.P_dphe);
+  }
+  if (pulseArea < fabs(det.s2_thr)) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      double v = out[i];
+      if (nearly_equal(v, 0.)) v = NB_PHE_MIN;
+      out[i] = -1. * fabs(v);
+    }
+  }
+  out[8] = g2;
+}
+
+// ---- energy sources: src/TestSpectra.cpp, execNEST.cpp:681-790 -----------------------------
+
+// TestSpectra::CH3T_spectrum TestSpectra.cpp:31-58 (Von Neumann rejection, yMax 1.1e7)
+NB_D double ch3t_spectrum(Stream& g, double xMin, double xMax) {
+  const double m_e = 510.9989461, aa = 0.0072973525664, ZZ = 2., qValue = 18.5898, yMax = 1.1e7;
+  if (xMax > qValue) xMax = qValue;
+  if (xMin < 0.) xMin = 0.;
+  for (int it = 0; it < 100000; ++it) {
+    double x0 = xMin + (xMax - xMin) * g.uniform();
+    double y0 = yMax * g.uniform();
+    double B = sqrt(x0 * x0 + 2. * x0 * m_e) / (x0 + m_e);
+    double x = (2. * NB_PI * ZZ * aa) * (x0 + m_e) / sqrt(x0 * x0 + 2. * x0 * m_e);
+    double f = (sqrt(2. * x0 * m_e) * (x0 + m_e) * (qValue - x0) * (qValue - x0) * x *
+                (1. / (1. - exp(-x))) * (1.002037 - 0.001427 * (B)));
+    if (!(y0 > f)) return x0;
+  }
+  return xMin;
+}
+// TestSpectra::B8_spectrum TestSpectra.cpp:110-128 (range forced to [0,5] keV)
+NB_D double b8_spectrum(Stream& g) {
+  const double m1 = -2.6455e-10, m2 = 5.0843;
+  const double xMin = 0., xMax = 5.;
+  const double yMax = pow(10., 3.4155);
+  for (int it = 0; it < 100000; ++it) {
+    double x0 = xMin + (xMax - xMin) * g.uniform();
+    double y0 = yMax * g.uniform();
+    double f = 3.4155 - 1.2184 * x0 + 0.32849 * (x0 * x0) - 0.12441 * (x0 * x0 * x0) + m1 * exp(m2 * x0);
+    f = pow(10., f);
+    if (!(y0 > f)) return x0;
+  }
+  return xMin;
+}
+// TestSpectra::DD_spectrum TestSpectra.cpp:192-211
+NB_D double dd_spectrum(Stream& g, double xMin, double xMax, double expFall, double peakFrac,
+                        double peakMu, double peakSig, double peakSkew) {
+  if (xMax > 80.) xMax = 80.;
+  if (xMin < 0.000) xMin = 0.000;
+  double yMax = 1.;
+  if (peakMu < xMax) yMax += peakFrac;
+  for (int it = 0; it < 100000; ++it) {
+    double x0 = xMin + (xMax - xMin) * g.uniform();
+    double y0 = yMax * g.uniform();
+    double d = (x0 - peakMu) / peakSig;
+    double f = exp(-x0 / expFall) + peakFrac * exp(-(d * d)) * (erf(peakSkew * (x0 - peakMu) / peakSig) + 1);
+    if (!(y0 > f)) return x0;
+  }
+  return xMin;
+}
+// TestSpectra::PowLawFit_spectrum TestSpectra.cpp:151-167 (AmBe, expo -0.95351)
+NB_D double powlaw_spectrum(Stream& g, double xMin, double xMax, double expo) {
+  double yMax, yMin;
+  expo += 1.;
+  if (expo < 0.) {
+    if (xMin <= 0.) xMin = 0.1;
+    yMax = pow(xMin, expo);
+    yMin = pow(xMax, expo);
+  } else {
+    yMax = pow(xMax, expo);
+    yMin = pow(xMin, expo);
+  }
+  double xTry = pow(yMin + (yMax - yMin) * g.uniform(), 1. / expo);
+  if (xTry < xMin) xTry = xMin;
+  if (xTry > xMax) xTry = xMax;
+  return xTry;
+}
+NB_D int xe_isotope_index(int A) {
+  switch (A) {
+    case 124: return 0;
+    case 126: return 1;
+    case 128: return 2;
+    case 129: return 3;
+    case 130: return 4;
+    case 131: return 5;
+    case 132: return 6;
+    case 134: return 7;
+    default: return 8;
+  }
+}
+// TestSpectra::WIMP_spectrum TestSpectra.cpp:456-499.  WIMP_dRate(0, m, day) depends only on
+// the random isotope it draws (:278), so its 9 possible values are tabulated on the host
+// (P.wimp_dr0) and every call of the reference becomes an isotope draw + lookup.
+NB_D double wimp_spectrum(Stream& g, const RunParams& P) {
+  const nb200_source& S = P.src;
+  const double xMax = S.wimp_xMax, xMin = 0.;
+  const double step = 1. / S.wimp_divisor;
+  int count = 0;
+  double f = 0.00;  // FuncValue persists across tries (:458)
+  double yMax = P.wimp_dr0[xe_isotope_index(select_xe_atom(g))];
+  double x0 = xMin + (xMax - xMin) * g.uniform();
+  double y0 = yMax * g.uniform();
+  for (;;) {
+    for (int guard = 0; guard < 100000; ++guard) {  // triangle pre-cut (:465-475)
+      double a = P.wimp_dr0[xe_isotope_index(select_xe_atom(g))];
+      double b = P.wimp_dr0[xe_isotope_index(select_xe_atom(g))];
+      if (!(y0 > (-a / xMax * x0 + b))) break;
+      x0 = (xMax - xMin) * g.uniform();
+      y0 = yMax * g.uniform();
+    }
+    // table interval lookup (:476-487): open interval (x, x + 1/divisor), x < xMax
+    int idx = int(x0 * S.wimp_divisor);
+    double xl = double(idx) * step;
+    if (idx >= 0 && idx < 100 && xl < xMax && x0 > xl && x0 < xl + step)
+      f = S.wimp_base[idx] * exp(-S.wimp_exponent[idx] * x0);
+    const bool rejected = y0 > f;  // RandomGen::VonNeumann RandomGen.cpp:140-157
+    if (rejected) {
+      x0 = xMin + (xMax - xMin) * g.uniform();
+      y0 = 0. + (yMax - 0.) * g.uniform();
+    }
+    if (++count >= 100) return 0.;  // :491-495, taken even when the 100th try was accepted
+    if (!rejected) return x0;
+  }
+}
+
+// energy per event: execNEST.cpp:681-790
+NB_D double sample_energy(Stream& g, const RunParams& P, uint64_t idx) {
+  const nb200_source& S = P.src;
+  double keV;
+  switch (S.kind) {
+    case NB200_SRC_MONO: keV = S.eMin; break;
+    case NB200_SRC_LIST: return S.E[idx];
+    case NB200_SRC_CH3T: keV = ch3t_spectrum(g, S.eMin, S.eMax); break;
+    case NB200_SRC_B8: keV = b8_spectrum(g); break;
+    case NB200_SRC_DD:
+      keV = dd_spectrum(g, S.eMin, S.eMax, S.par[0], S.par[1], S.par[2], S.par[3], S.par[4]);
+      break;
+    case NB200_SRC_AMBE: keV = powlaw_spectrum(g, S.eMin, S.eMax, S.par[0]); break;
+    case NB200_SRC_WIMP: return wimp_spectrum(g, P);
+    case NB200_SRC_GAUSS: keV = zero_trunc_gauss(g, S.eMin, S.eMax); break;
+    case NB200_SRC_EXP: keV = exponential(g, -S.eMax * log(2.), 0., S.eMin); break;
+    default: keV = S.eMin + (S.eMax - S.eMin) * g.uniform(); break;
+  }
+  if (S.kind != NB200_SRC_B8 && S.eMax > 0. && S.eMin < S.eMax) {  // :786-790
+    if (keV > S.eMax) keV = S.eMax;
+    if (keV < S.eMin) keV = S.eMin;
+  }
+  return keV;
+}
+
+// signal selection execNEST.cpp:1121-1158
+NB_D void select_signals(const nb200_analysis& A, const double* scint, const double* scint2,
+                         double& signal1, double& signal2) {
+  if (A.usePD == 0 && fabs(scint[3]) > A.minS1 && scint[3] < A.maxS1)
+    signal1 = scint[3];
+  else if (A.usePD == 1 && fabs(scint[5]) > A.minS1 && scint[5] < A.maxS1)
+    signal1 = scint[5];
+  else if ((A.usePD >= 2 && fabs(scint[7]) > A.minS1 && scint[7] < A.maxS1) || A.maxS1 >= 998.5)
+    signal1 = scint[7];
+  else
+    signal1 = -999.;
+  if (A.usePD == 0 && fabs(scint2[5]) > A.minS2 && scint2[5] < A.maxS2)
+    signal2 = scint2[5];
+  else if (A.usePD >= 1 && fabs(scint2[7]) > A.minS2 && scint2[7] < A.maxS2)
+    signal2 = scint2[7];
+  else
+    signal2 = -999.;
+}
+
+// energy reconstruction execNEST.cpp:1170-1250; returns signalE, keV updated in place
+NB_D double reconstruct_energy(const RunParams& P, const Yields& y, const double* scint,
+                               const double* scint2, double signal1, double signal2, double field,
+                               double& keV) {
+  const nb200_detector& det = P.det;
+  const nb200_analysis& A = P.ana;
+  const double g1 = det.g1, g2 = fabs(P.rc.g2_params[3]);
+  if (!A.MCtruthE) {
+    double MultFact = 1., eff = det.sPEeff;
+    if (A.s1mode != NB200_S1_PARAMETRIC) {
+      if (det.sPEthr >= 0. && det.sPEres > 0. && eff > 0.) {
+        MultFact = P.recon_mult;
+        if (A.usePD == 2 && scint[7] < NB_SPIKES_MAXM)
+          MultFact = 1.04;
+        else
+          MultFact = 1. + MultFact * det.P_dphe;
+        if (eff < 1.) eff += ((1. - eff) / (2. * double(det.numPMTs))) * scint[0];
+        eff = smax(0., smin(eff, 1.));
+        MultFact /= eff;
+      } else
+        MultFact = 1.;
+    }
+    double Nph, Ne;
+    if (A.usePD == 0)
+      Nph = fabs(scint[3]) / (g1 * (1. + det.P_dphe));
+    else if (A.usePD == 1)
+      Nph = fabs(scint[5]) / g1;
+    else
+      Nph = fabs(scint[7]) / g1;
+    if (A.usePD == 0)
+      Ne = fabs(scint2[5]) / (g2 * (1. + det.P_dphe));
+    else
+      Ne = fabs(scint2[7]) / g2;
+    Nph *= MultFact;
+    if (signal1 <= 0.) Nph = 0.;
+    if (signal2 <= 0.) Ne = 0.;
+    if (det.coinLevel <= 0 && Nph <= NB_PHE_MIN) Nph = DBL_MIN;
+    if (y.L > DBL_MIN && Nph > 0. && Ne > 0.) {
+      if (nearly_equal(y.L, 1.))
+        keV = (Nph + Ne) * P.rc.Wq_eV * 1e-3;
+      else if (P.species <= NB200_Cf) {
+        const double* n = P.model.NRYieldsParam;
+        keV = pow((Ne + Nph) / n[0], 1. / n[1]);
+        Ne *= 1. - 1. / pow(1. + pow((keV / n[5]), n[6]), n[10]);
+        Nph *= 1. - 1. / pow(1. + pow((keV / n[7]), n[8]), n[11]);
+        keV = pow((Ne + Nph) / n[0], 1. / n[1]);
+      } else {
+        const double logden = log10(P.rc.rho);
+        const double Wq_eV_alpha =
+            28.259 + 25.667 * logden - 33.611 * pow(logden, 2.) - 123.73 * pow(logden, 3.) -
+            136.47 * pow(logden, 4.) - 74.194 * pow(logden, 5.) - 20.276 * pow(logden, 6.) -
+            2.2352 * pow(logden, 7.);
+        keV = (Nph + Ne) * Wq_eV_alpha * 1e-3 / y.L;
+      }
+    } else
+      keV = 0.;
+  }
+  if ((signal1 <= 0. || signal2 <= 0.) && field >= NB_FIELD_MIN && det.coinLevel != 0) return 0.;
+  return keV;
+}
+
+// GetBand bin search + value, execNEST.cpp:1508-1580 (resol == false).  Returns the bin or -1;
+// accepted/value as the reference pushes them (0 when log10 falls outside (logMin, logMax)).
+NB_D int band_bin(const RunParams& P, double signal1, double signal2, bool& accepted, double& xval,
+                  double& yval) {
+  const nb200_analysis& A = P.ana;
+  const int nFold = P.det.coinLevel;
+  const double X = (A.useS2 == 2) ? signal2 : signal1;
+  const double O = (A.useS2 == 2) ? signal1 : signal2;
+  const double binWidth = P.band_width, border = P.band_border;
+  const double aX = fabs(X);
+  int bin = -1;
+  if (!nFold)
+    bin = 0;
+  else {
+    int j0 = int(floor((aX - border) / binWidth)) - 1;
+    if (j0 < 0) j0 = 0;
+    for (int j = j0; j < j0 + 3 && j < A.numBins; ++j) {
+      double s1c = border + binWidth / 2. + double(j) * binWidth;
+      if (aX > (s1c - binWidth / 2.) && aX <= (s1c + binWidth / 2.)) {
+        bin = j;
+        break;
+      }
+    }
+  }
+  if (bin < 0) return -1;
+  const double ReqS1 = nFold == 0 ? -DBL_MAX : 0.;
+  accepted = (X >= ReqS1 && O >= 0.);
+  xval = X;
+  yval = 0.;
+  if (accepted) {
+    double v;
+    if (A.useS2 == 0)
+      v = log10(O / X);
+    else if (A.useS2 == 1)
+      v = log10(O);
+    else
+      v = log10(X / O);
+    if (X != 0. && O != 0. && v > A.logMin && v < A.logMax) yval = v;
+  }
+  return bin;
+}
+
+#endif  // __CUDACC__
+}  // namespace nb

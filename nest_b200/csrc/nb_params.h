@@ -1,0 +1,60 @@
+// nb_params.h -- the kernel-parameter block: the C-ABI PODs of include/nest_b200.h
+// with device pointers substituted, plus per-run constants hoisted out of the event loop
+// on the host.  Passed by value as a __grid_constant__ kernel argument (constant bank),
+// the B200 stand-in for the reference's VDetector* getter calls inside the hot loop
+// (src/NEST.cpp:1288-2063).
+#pragma once
+#include <stdint.h>
+
+#include "../../include/nest_b200.h"
+
+namespace nb {
+
+// packed band accumulator in device memory (u64 words), per S1 bin
+//   [0] accepted  [1] rejected  [2] sumS1  [3] sumY  [4] sumY2  [5] sumY3
+// followed by numBins*logBins u64 of the 2-D histogram
+enum { BAND_WORDS = 6 };
+
+struct SoaDev {  // nb200_soa_out with device pointers (null = column not written)
+  double *energy_kev, *x_mm, *y_mm, *z_mm, *field, *driftTime, *smear_x, *smear_y;
+  int32_t *photons, *electrons, *ions, *excitons;
+  double* s1[9];
+  double* s2[9];
+  double *signal1, *signal2, *signalE, *Nph_mean, *Ne_mean;
+};
+
+struct RunParams {
+  nb200_detector det;  // map.lut -> device memory
+  nb200_model model;
+  nb200_analysis ana;
+  nb200_source src;  // E/x/y/z/wimp_* -> device memory
+  nb200_run_consts rc;
+
+  // hoisted per-run constants
+  double s1_center;      // FitS1(0,0,TopDrift - vD_middle*dtCntr)   NEST.cpp:1317-1321
+  double s2_center;      // FitS2(0,0)                               NEST.cpp:1762-1763
+  double coin_u_min;     // exp(-coinWind/20): -20 ln u < coinWind <=> u > this  NEST.cpp:1422
+  double below_thr_pct;  // Parametric S1 threshold percentile       NEST.cpp:1437-1457
+  double recon_mult;     // MultFact prefactor, execNEST.cpp:1179-1182
+  double wimp_dr0[9];    // WIMP_dRate(0) per Xe isotope             TestSpectra.cpp:459,466
+  double band_width, band_border;  // GetBand bin geometry           execNEST.cpp:1521-1527
+  // GetDriftVelocity_Liquid rows bracketing T_Kelvin (NEST.cpp:2429-2502); dv_mode 0 blend,
+  // 1 = T on the lower node, 2 = T on the upper node
+  double dv_row[2][7];
+  double dv_Ti, dv_Tf, dv_T;
+  int32_t dv_mode;
+  int32_t vtable_n;      // SetDriftVelocity_NonUniform table (NEST.cpp:2664-2697), inField == -1
+  const double* vtable;
+
+  uint64_t seed, first_event, n_events;
+  int32_t species;
+  int32_t vec_mode;   // 1 = runNESTvec semantics (execNEST.cpp:357-406)
+  int32_t write_soa;
+  int32_t do_band;
+  int32_t band_in_smem;  // accumulate the band in shared memory (fits) or straight in global
+  int32_t _pad;
+  SoaDev soa;
+  unsigned long long* band;  // device accumulator or null
+};
+
+}  // namespace nb

@@ -1,0 +1,275 @@
+// nb_rng.cuh -- counter-based random streams and the distribution samplers of the chain.
+//
+// Replaces the reference's process-global sequential generator (RandomGen singleton over
+// xoroshiro128+, src/RandomGen.cpp:8-42) with Philox4x32-10 keyed by the run seed and
+// counted by (event id, draw block, stream id): every event owns its streams, so the
+// result for event e depends only on (seed, e, parameters).  Only the *distributions* of
+// the reference samplers are kept (src/RandomGen.cpp:39-182); where a cheaper exact
+// construction of the same distribution exists it is used and said so at the sampler.
+#pragma once
+#include <cstdint>
+#include <cfloat>
+
+#ifdef __CUDACC__
+#define NB_HD __host__ __device__ __forceinline__
+#define NB_D __device__ __forceinline__
+#else
+#define NB_HD inline
+#define NB_D inline
+#endif
+
+namespace nb {
+
+// stream ids (counter word 3)
+enum : uint32_t {
+  STREAM_MAIN = 0,   // per-event scalar draws, sequential blocks
+  STREAM_HIT = 1,    // S1 PMT hits: block = hit index (SPE part)
+  STREAM_HIT2 = 2,   // S1 PMT hits: second photo-electron of a double-phe hit
+  STREAM_HITX = 3,   // S1 PMT hits: rare redraws of the zero-truncated Gaussian
+  STREAM_HIT3 = 4,   // S1 PMT hits: single-phe efficiency decisions (sPEeff < 1 only)
+  STREAM_LAR = 8,
+  STREAM_HOST = 16   // host-side draws (Poisson event count, WIMP table)
+};
+
+struct u128 {
+  uint32_t x, y, z, w;
+};
+
+NB_HD void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+#ifdef __CUDA_ARCH__
+  lo = a * b;
+  hi = __umulhi(a, b);
+#else
+  uint64_t p = uint64_t(a) * uint64_t(b);
+  lo = uint32_t(p);
+  hi = uint32_t(p >> 32);
+#endif
+}
+
+// Philox4x32-10 (Salmon et al., SC'11); constants of the Random123 reference implementation.
+NB_HD u128 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                         uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0, lo0, hi1, lo1;
+    mulhilo(0xD2511F53u, c0, hi0, lo0);
+    mulhilo(0xCD9E8D57u, c2, hi1, lo1);
+    uint32_t n0 = hi1 ^ c1 ^ k0;
+    uint32_t n2 = hi0 ^ c3 ^ k1;
+    c0 = n0;
+    c1 = lo1;
+    c2 = n2;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return u128{c0, c1, c2, c3};
+}
+
+// 53-bit uniform on the OPEN interval (0,1).  The reference's rand_uniform is
+// u64/(2^64-1) on the closed interval (RandomGen.cpp:39-42); the end points have
+// probability 2^-64 each and only matter as log(0) hazards, which the open interval removes.
+NB_HD double u53(uint32_t hi, uint32_t lo) {
+  uint64_t v = (uint64_t(hi) << 21) | (uint64_t(lo) >> 11);
+  return (double(v) + 0.5) * 1.1102230246251565404e-16;  // 2^-53
+}
+// 32-bit uniform on (0,1) for yes/no decisions and angles
+NB_HD double u32d(uint32_t a) { return (double(a) + 0.5) * 2.3283064365386962891e-10; }
+
+// Sequential stream over one (seed, event, stream) triple.
+struct Stream {
+  uint32_t k0, k1, e0, e1, blk, sid;
+  uint32_t s0, s1;  // second half of the last block
+  bool have;
+
+  NB_HD void init(uint64_t seed, uint64_t event, uint32_t stream) {
+    k0 = uint32_t(seed);
+    k1 = uint32_t(seed >> 32);
+    e0 = uint32_t(event);
+    e1 = uint32_t(event >> 32);
+    blk = 0;
+    sid = stream;
+    have = false;
+    s0 = s1 = 0;
+  }
+  NB_HD void next2(uint32_t& a, uint32_t& b) {
+    if (have) {
+      have = false;
+      a = s0;
+      b = s1;
+      return;
+    }
+    u128 r = philox4x32_10(e0, e1, blk, sid, k0, k1);
+    ++blk;
+    s0 = r.z;
+    s1 = r.w;
+    have = true;
+    a = r.x;
+    b = r.y;
+  }
+  NB_HD double uniform() {
+    uint32_t a, b;
+    next2(a, b);
+    return u53(a, b);
+  }
+};
+
+#ifdef __CUDACC__
+// ---- samplers (device) -------------------------------------------------------------
+
+// two independent standard normals from one Box-Muller transform.  The reference's
+// rand_gauss (RandomGen.cpp:44-53) evaluates mean + sigma*sqrt2*sqrt(-ln u)*cos(2 pi v)
+// and throws the sine partner away; the partner is an independent N(0,1), so using it
+// halves the log/sqrt work without changing any distribution.
+NB_D void normal_pair(Stream& g, double& z0, double& z1) {
+  uint32_t a, b, c, d;
+  g.next2(a, b);
+  g.next2(c, d);
+  double u = u53(a, b);
+  double v = u53(c, d);
+  double r = sqrt(-2.0 * log(u));
+  double s, co;
+  sincospi(2.0 * v, &s, &co);
+  z0 = r * co;
+  z1 = r * s;
+}
+NB_D double normal(Stream& g) {
+  uint32_t a, b, c, d;
+  g.next2(a, b);
+  g.next2(c, d);
+  return sqrt(-2.0 * log(u53(a, b))) * cospi(2.0 * u53(c, d));
+}
+// rand_gauss(mean, sigma, zero_min) RandomGen.cpp:44-53
+NB_D double gauss(Stream& g, double mean, double sigma, bool zero_min) {
+  double d = mean + sigma * normal(g);
+  // max(draw, 0.) with std::max semantics: NaN draw stays NaN (max(a,b) = a<b ? b : a)
+  if (zero_min) return (d < 0.) ? 0. : d;
+  return d;
+}
+// rand_zero_trunc_gauss RandomGen.cpp:55-61 (redraw while <= 0)
+NB_D double zero_trunc_gauss(Stream& g, double mean, double sigma) {
+  double r = mean + sigma * normal(g);
+  int guard = 0;
+  while (r <= 0. && ++guard < 100000) r = mean + sigma * normal(g);
+  return r;
+}
+// rand_exponential RandomGen.cpp:72-85
+NB_D double exponential(Stream& g, double half_life, double t_min, double t_max) {
+  const double ln2 = 0.693147180559945309417;
+  double r = g.uniform();
+  double r_min = 0., r_max = 1.;
+  if (t_min >= 0) r_min = 1 - exp(-t_min * ln2 / half_life);
+  if (t_max >= 0) r_max = 1 - exp(-t_max * ln2 / half_life);
+  r = (r_max - r_min) * r + r_min;
+  return -log(1 - r) * half_life / ln2;
+}
+// rand_skewGauss RandomGen.cpp:87-126.  The reference samples the skew-normal density
+// 2/omega phi(z) Phi(alpha z), z=(x-xi)/omega, by box rejection over xi +- 6 omega
+// (acceptance ~14 %).  Same distribution, exact: z = delta|a| + sqrt(1-delta^2) b with
+// a,b iid N(0,1), delta = alpha/sqrt(1+alpha^2) (Azzalini 1985), redrawn when |z|>6 to
+// keep the reference's +-6 omega support.
+NB_D double skew_gauss(Stream& g, double xi, double omega, double alpha) {
+  double delta = alpha / sqrt(1. + alpha * alpha);
+  double cd = sqrt(1. - delta * delta);
+  double z;
+  int guard = 0;
+  do {
+    double a, b;
+    normal_pair(g, a, b);
+    z = delta * fabs(a) + cd * b;
+  } while (fabs(z) > 6. && ++guard < 1000);
+  return xi + omega * z;
+}
+// SelectRanXeAtom RandomGen.cpp:159-182 (natural-abundance cumulative table in percent)
+NB_D int select_xe_atom(Stream& g) {
+  double iso = g.uniform() * 100.;
+  if (iso <= 0.090) return 124;
+  if (iso <= 0.180) return 126;
+  if (iso <= 2.100) return 128;
+  if (iso <= 28.54) return 129;
+  if (iso <= 32.62) return 130;
+  if (iso <= 53.80) return 131;
+  if (iso <= 80.69) return 132;
+  if (iso <= 91.13) return 134;
+  return 136;
+}
+
+// Stirling-series tail log(k!) - [ (k+1/2)log(k+1) - (k+1) + log(2 pi)/2 ]
+static __constant__ double c_stirling[10] = {
+    0.08106146679532726, 0.04134069595540929, 0.02767792568499834, 0.02079067210376509,
+    0.01664469118982119, 0.01387612882307075, 0.01189670994589177, 0.01041126526197209,
+    0.009255462182712733, 0.008330563433362871};
+NB_D double stirling_tail(double k) {
+  if (k < 10.) return c_stirling[int(k)];
+  double kp1sq = (k + 1.) * (k + 1.);
+  return (1.0 / 12. - (1.0 / 360. - 1.0 / 1260. / kp1sq) / kp1sq) / (k + 1.);
+}
+
+// binom_draw RandomGen.cpp:132-134 = std::binomial_distribution<int64_t>(n,p).  Exact
+// binomial sampler: sequential CDF inversion while n*min(p,1-p) < 10, Hormann's BTRS
+// transformed rejection (J. Stat. Comput. Simul. 46 (1993) 101) above.
+NB_D long long binomial(Stream& g, long long n, double p) {
+  if (!(n > 0) || !(p > 0.)) return 0;
+  if (p >= 1.) return n;
+  bool flip = p > 0.5;
+  double pp = flip ? 1. - p : p;
+  double q = 1. - pp;
+  double dn = double(n);
+  long long k;
+  if (dn * pp < 10.) {
+    double r0 = exp(dn * log1p(-pp));
+    double s = pp / q;
+    for (;;) {
+      double u = g.uniform();
+      double r = r0;
+      long long x = 0;
+      bool ok = true;
+      while (u > r) {
+        u -= r;
+        ++x;
+        if (x > n || x > 200) {
+          ok = false;
+          break;
+        }
+        r *= s * (double(n - x + 1) / double(x));
+      }
+      if (ok) {
+        k = x;
+        break;
+      }
+    }
+  } else {
+    double spq = sqrt(dn * pp * q);
+    double b = 1.15 + 2.53 * spq;
+    double a = -0.0873 + 0.0248 * b + 0.01 * pp;
+    double c = dn * pp + 0.5;
+    double vr = 0.92 - 4.2 / b;
+    double r = pp / q;
+    double alpha = (2.83 + 5.1 / b) * spq;
+    double m = floor((dn + 1.) * pp);
+    for (;;) {
+      double u = g.uniform() - 0.5;
+      double v = g.uniform();
+      double us = 0.5 - fabs(u);
+      double kk = floor((2. * a / us + b) * u + c);
+      if (us >= 0.07 && v <= vr) {
+        k = (long long)kk;
+        break;
+      }
+      if (kk < 0. || kk > dn) continue;
+      v = log(v * alpha / (a / (us * us) + b));
+      double ub = (m + 0.5) * log((m + 1.) / (r * (dn - m + 1.))) +
+                  (dn + 1.) * log((dn - m + 1.) / (dn - kk + 1.)) +
+                  (kk + 0.5) * log(r * (dn - kk + 1.) / (kk + 1.)) + stirling_tail(m) +
+                  stirling_tail(dn - m) - stirling_tail(kk) - stirling_tail(dn - kk);
+      if (v <= ub) {
+        k = (long long)kk;
+        break;
+      }
+    }
+  }
+  return flip ? n - k : k;
+}
+#endif  // __CUDACC__
+
+}  // namespace nb

@@ -1,0 +1,142 @@
+"""Statistical parity of the stochastic chain on the GPU against the compiled reference.
+
+The GPU path replaces the reference's sequential xoroshiro stream by Philox(seed, event), so
+equal seeds do not give equal numbers: every output column is compared as a distribution
+(two-sample Kolmogorov-Smirnov) and the band by the reference's own chi^2
+(examples/rootNEST.cpp:619-643).  Fixed seeds make the outcome reproducible."""
+import numpy as np
+import pytest
+
+import refprobe
+from helpers import COLUMN_NAMES, band_chi2, gpu_chain, ks_report, mean_z, ref_chain
+from nest_b200 import capi
+
+pytestmark = pytest.mark.gpu
+P_MIN = 1e-4   # per-column KS p-value floor (about 40 columns x 10 configurations)
+
+
+def check(a, b, skip=(), label=""):
+    ks = ks_report(a, b, skip)
+    bad = {k: v for k, v in ks.items() if v < P_MIN}
+    z = mean_z(a, b)
+    assert not bad, "%s: KS failures %r (mean z-scores %r)" % (label, bad, {k: z[k] for k in bad})
+
+
+MONO = [
+    ("beta_5keV", capi.beta, 5.0, 0, 1.0, 1),
+    ("beta_0.7keV", capi.beta, 0.7, 0, 1.0, 1),
+    ("beta_50keV_defaultwidths_skew", capi.beta, 50.0, -1, 1.0, 0),
+    ("gamma_41keV", capi.gammaRay, 41.5, -1, 1.0, 1),
+    ("NR_3keV", capi.NR, 3.0, -1, 1.0, 1),
+    ("NR_30keV", capi.NR, 30.0, -1, 1.0, 1),
+    ("NR_250keV_parametric", capi.NR, 250.0, -1, 1.0, 1),
+]
+
+
+@pytest.mark.parametrize("label,species,E,er_model,mult,which", MONO)
+def test_mono_fixed_position(ctx, ref, label, species, E, er_model, mult, which):
+    """mono-energetic source at a fixed vertex: isolates quanta, S1 and S2 distributions"""
+    n = 60000
+    xyz = (70.0, -40.0, 300.0)
+    g, _ = gpu_chain(ctx, 11, n, species, capi.SRC_MONO, E, E, 180.0, 1, xyz, er_model, mult, which)
+    r = ref_chain(ref, 7, n, species, capi.SRC_MONO, E, E, 180.0, 1, xyz, er_model, mult, which)
+    check(g, r, label=label)
+
+
+@pytest.mark.parametrize("label,species,kind,emin,emax,er_model", [
+    ("config1_ER_flat", capi.beta, capi.SRC_FLAT, 0.1, 20.0, 0),
+    ("config2_NR_flat", capi.NR, capi.SRC_FLAT, 0.0, 100.0, -1),
+    ("CH3T", capi.CH3T, capi.SRC_CH3T, 0.0, 18.5898, -1),
+    ("DD", capi.DD, capi.SRC_DD, 0.0, 80.0, -1),
+    ("B8", capi.B8, capi.SRC_B8, 0.0, 5.0, -1),
+])
+def test_random_vertex_chain_and_band(ctx, ref, label, species, kind, emin, emax, er_model):
+    n = 100000
+    par = (13., 0.12, 71.2, 20., -20.5) if kind == capi.SRC_DD else ()
+    ana = capi.analysis(0)
+    band = capi.Band(ana)
+    g, cols = gpu_chain(ctx, 3, n, species, kind, emin, emax, 180.0, 0, (0, 0, 0), er_model, 1.0, 1, ana=ana,
+                        band=band, par=par)
+    r = ref_chain(ref, 5, n, species, kind, emin, emax, 180.0, 0, (0, 0, 0), er_model, 1.0, 1)
+    check(g, r, label=label)
+    # band: GPU accumulator vs the reference's GetBand on the reference's own signals
+    bg = band.finalize()
+    br = ref.getband(r[:, refprobe.SIG1], r[:, refprobe.SIG2])
+    if label != "B8":
+        cm, cw, dof = band_chi2(bg, br)
+        assert cm < 2.0 and cw < 2.0, "%s band chi2/dof mean %.2f width %.2f (dof %d)" % (label, cm, cw, dof)
+    # and the GPU accumulator reproduces GetBand on the GPU's own signals (same events)
+    bs = ref.getband(cols["signal1"], cols["signal2"])
+    ok = np.isfinite(bs).all(axis=1) & np.isfinite(bg).all(axis=1)
+    assert np.allclose(bg[ok][:, [0, 1, 2, 3, 4, 5]], bs[ok][:, [0, 1, 2, 3, 4, 5]], rtol=2e-6, atol=1e-7)
+
+
+def test_nonuniform_field(ctx, ref):
+    n = 40000
+    g, _ = gpu_chain(ctx, 21, n, capi.beta, capi.SRC_FLAT, 1.0, 15.0, -1.0, 0, (0, 0, 0), 0, 1.0, 1)
+    r = ref_chain(ref, 22, n, capi.beta, capi.SRC_FLAT, 1.0, 15.0, -1.0, 0, (0, 0, 0), 0, 1.0, 1)
+    check(g, r, label="FitEF field")
+
+
+def test_event_results_do_not_depend_on_batching(ctx):
+    """event e depends only on (seed, e): shards and chunk sizes reproduce the same records"""
+    n = 5000
+    a, _ = gpu_chain(ctx, 9, n, capi.NR, capi.SRC_FLAT, 0.0, 100.0)
+    b1, _ = gpu_chain(ctx, 9, 1777, capi.NR, capi.SRC_FLAT, 0.0, 100.0, first_event=0)
+    b2, _ = gpu_chain(ctx, 9, n - 1777, capi.NR, capi.SRC_FLAT, 0.0, 100.0, first_event=1777)
+    assert np.array_equal(a, np.vstack([b1, b2]))
+    c, _ = gpu_chain(ctx, 10, n, capi.NR, capi.SRC_FLAT, 0.0, 100.0)
+    assert not np.array_equal(a, c)
+
+
+def test_band_accumulator_is_exact(ctx):
+    """integer band words == recomputation from the per-event signals; shards add up exactly"""
+    ana = capi.analysis(0)
+    n = 30000
+    full = capi.Band(ana)
+    _, cols = gpu_chain(ctx, 4, n, capi.beta, capi.SRC_FLAT, 0.1, 20.0, er_model=0, ana=ana, band=full)
+    parts = capi.Band(ana)
+    for lo, hi in [(0, 7000), (7000, 7001), (7001, 30000)]:
+        gpu_chain(ctx, 4, hi - lo, capi.beta, capi.SRC_FLAT, 0.1, 20.0, er_model=0, ana=ana, band=parts,
+                  first_event=lo)
+    assert np.array_equal(full.words(), parts.words())
+    s1, s2 = cols["signal1"], cols["signal2"]
+    w = (ana.maxS1 - ana.minS1) / ana.numBins
+    acc = np.zeros(ana.numBins, np.int64)
+    rej = np.zeros(ana.numBins, np.int64)
+    for j in range(ana.numBins):
+        c = ana.minS1 + w / 2. + j * w
+        m = (np.abs(s1) > c - w / 2.) & (np.abs(s1) <= c + w / 2.)
+        good = m & (s1 >= 0) & (s2 >= 0)
+        acc[j] = good.sum()
+        rej[j] = (m & ~good).sum()
+    assert np.array_equal(acc, full.accepted.astype(np.int64))
+    assert np.array_equal(rej, full.rejected.astype(np.int64))
+    assert full.hist2d.sum() <= full.accepted.sum()
+
+
+def test_edge_cases(ctx):
+    det = capi.detector("LUX_Run03")
+    rc = capi.prepare(det, 180.0)
+    mo, ana = capi.model(1), capi.analysis(0)
+    # no events: nothing to do, no error
+    src = capi.source(capi.SRC_FLAT, capi.NR, 0.0, 100.0)
+    assert ctx.run(det, mo, ana, src, rc, 1, 0) is not None
+    # energy below the work function: zero quanta, zero signals (execNEST.cpp:1066-1077)
+    g, cols = gpu_chain(ctx, 1, 100, capi.NR, capi.SRC_MONO, 0.005, 0.005)
+    assert not cols["photons"].any() and not cols["electrons"].any()
+    assert np.all(cols["signal1"] == -999.) and np.all(cols["signalE"] == 0.)
+    # zero drift field: no S2 (NEST.cpp:1746-1750)
+    g, cols = gpu_chain(ctx, 1, 100, capi.beta, capi.SRC_MONO, 10.0, 10.0, inField=0.5, fixed_pos=1,
+                        xyz=(0., 0., 300.))
+    assert not cols["s2_4"].any()
+    # bad parameters are refused like the reference (return 1 + message)
+    bad = capi.model(1)
+    bad.NRERWidthsParam[9] = 5.0
+    with pytest.raises(capi.NestB200Error) as e:
+        ctx.run(det, bad, ana, capi.source(capi.SRC_FLAT, capi.beta, 0.1, 20.0), rc, 1, 10)
+    assert e.value.code == capi.EPHYSICS
+    ana2 = capi.analysis(0)
+    ana2.numBins = 5000
+    with pytest.raises(capi.NestB200Error):
+        ctx.run(det, mo, ana2, src, rc, 1, 10)
