@@ -154,7 +154,11 @@ def main():
 
     capi.lib()
     ctx = capi.Context(local)
-    stream = torch.cuda.current_stream()
+    # one non-default stream carries the chain kernel, torch's fills, the NCCL all-reduce and
+    # the timing events (a null handle would select the library's own stream instead)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
     det = capi.detector("LUX_Run03")
     rc = capi.prepare(det, 180.0)

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <random>
@@ -39,6 +40,10 @@ struct nb200_ctx {
     void* dev;
   };
   std::vector<Blob> blobs;
+  // k_pre -> k_hits -> k_post workspace (one chunk)
+  void* d_work = nullptr;
+  uint64_t work_cap = 0;
+  int occ_pre = 0, occ_hits = 0, occ_post = 0;
   std::vector<double> vtable_host;
   nb200_detector vtable_det;
   double vtable_zstep = 0.;
@@ -48,6 +53,23 @@ struct nb200_ctx {
 namespace {
 
 thread_local std::string g_err_noctx;
+
+// NB200_TRACE=1: wall-clock phases of the synchronous entry points on stderr
+struct Trace {
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  const char* what;
+  explicit Trace(const char* w) : on(std::getenv("NB200_TRACE") != nullptr), what(w) {
+    if (on) t0 = std::chrono::steady_clock::now();
+  }
+  void mark(const char* phase) {
+    if (!on) return;
+    auto t1 = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[nb200 trace] %s: %s %.3f ms\n", what, phase,
+                 std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
 
 int fail(nb200_ctx* c, int code, const std::string& msg) {
   if (c)
@@ -218,8 +240,31 @@ int build_params(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo,
   return 0;
 }
 
-constexpr int kBlock = 512;
+// events per internal chunk: the workspace holds one chunk (140 B/event); large enough that the
+// ragged last wave of each kernel is a few per cent of its run time
+constexpr uint64_t kChunk = 1ull << 22;
 
+int ensure_workspace(nb200_ctx* c, uint64_t n, Work* w) {
+  const uint64_t need = std::min<uint64_t>(kChunk, std::max<uint64_t>(n, 1024));
+  if (need > c->work_cap) {
+    if (c->d_work) cudaFree(c->d_work);
+    c->d_work = nullptr;
+    c->work_cap = 0;
+    NB_CUDA(c, cudaMalloc(&c->d_work, need * (WORK_F64 * 8 + WORK_I32 * 4)));
+    c->work_cap = need;
+  }
+  const uint64_t cap = c->work_cap;
+  double* f = static_cast<double*>(c->d_work);
+  double** fp[WORK_F64] = {&w->keV, &w->px, &w->py, &w->pz, &w->sx, &w->sy, &w->field, &w->dt,
+                           &w->yNph, &w->yNe, &w->yL, &w->posDepSm, &w->fitSm, &w->area};
+  for (int k = 0; k < WORK_F64; ++k) *fp[k] = f + cap * k;
+  int32_t* i32 = reinterpret_cast<int32_t*>(f + cap * WORK_F64);
+  int32_t** ip[WORK_I32] = {&w->photons, &w->electrons, &w->ions, &w->excitons, &w->nHits, &w->spike, &w->nphe};
+  for (int k = 0; k < WORK_I32; ++k) *ip[k] = i32 + cap * k;
+  return 0;
+}
+
+// k_pre -> k_hits -> k_post over the call's events in chunks of the workspace size
 int launch_event(nb200_ctx* c, RunParams& P) {
   if (P.n_events == 0) return 0;
   size_t smem = 0;
@@ -231,16 +276,33 @@ int launch_event(nb200_ctx* c, RunParams& P) {
     else
       smem = 0;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    NB_CUDA(c, cudaFuncSetAttribute(k_event<kBlock>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_set = true;
+  if (!c->occ_pre) {
+    NB_CUDA(c, cudaFuncSetAttribute(k_post, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    NB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_pre, k_pre, kPreBlock, 0));
+    NB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_hits, k_hits, kHitBlock, 0));
+    if (c->occ_pre < 1) c->occ_pre = 1;
+    if (c->occ_hits < 1) c->occ_hits = 1;
   }
-  uint64_t batches = (P.n_events + kBlock - 1) / kBlock;
-  unsigned grid = unsigned(std::min<uint64_t>(batches, uint64_t(c->sm_count)));
-  k_event<kBlock><<<grid, kBlock, smem, c->stream>>>(P, c->d_err);
-  NB_CUDA(c, cudaGetLastError());
-  ++c->launches;
+  NB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_post, k_post, kPostBlock, smem));
+  if (c->occ_post < 1) c->occ_post = 1;
+  int r = ensure_workspace(c, P.n_events, &P.work);
+  if (r) return r;
+  const uint64_t total = P.n_events, cap = c->work_cap;
+  for (uint64_t off = 0; off < total; off += cap) {
+    const uint64_t m = std::min<uint64_t>(cap, total - off);
+    RunParams Q = P;
+    Q.n_events = m;
+    Q.chunk_off = P.chunk_off + off;
+    const uint64_t sm = uint64_t(c->sm_count);
+    unsigned g_pre = unsigned(std::min<uint64_t>((m + kPreBlock - 1) / kPreBlock, sm * c->occ_pre * 8));
+    unsigned g_hits = unsigned(std::min<uint64_t>((m + kHitGroup - 1) / kHitGroup, sm * c->occ_hits * 4));
+    unsigned g_post = unsigned(std::min<uint64_t>((m + kPostBlock - 1) / kPostBlock, sm * c->occ_post));
+    k_pre<<<g_pre, kPreBlock, 0, c->stream>>>(Q, c->d_err);
+    k_hits<<<g_hits, kHitBlock, 0, c->stream>>>(Q);
+    k_post<<<g_post, kPostBlock, smem, c->stream>>>(Q, c->d_err);
+    NB_CUDA(c, cudaGetLastError());
+    c->launches += 3;
+  }
   return 0;
 }
 
@@ -323,6 +385,7 @@ void nb200_destroy(nb200_ctx* c) {
   if (c->d_band && !c->band_external) cudaFree(c->d_band);
   if (c->d_band_tmp) cudaFree(c->d_band_tmp);
   if (c->d_vtable) cudaFree(c->d_vtable);
+  if (c->d_work) cudaFree(c->d_work);
   if (c->d_err) cudaFree(c->d_err);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
@@ -717,6 +780,7 @@ int nb200_run(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo, co
   if (hist && (hist->numBins != ana->numBins || hist->logBins != ana->logBins))
     return fail(c, NB200_EINVAL, "band geometry mismatch");
   if (n_events == 0) return 0;
+  Trace tr("nb200_run");
   const bool host_soa = soa && soa->mem_kind == NB200_MEM_HOST;
   const bool host_list = src->kind == NB200_SRC_LIST && src->list_mem_kind == NB200_MEM_HOST;
   const uint64_t chunk_max = 1ull << 22;
@@ -784,6 +848,7 @@ int nb200_run(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo, co
     cudaMemsetAsync(c->d_band_tmp, 0, w * 8, c->stream);
   }
 
+  tr.mark("staging alloc");
   int rcode = 0;
   for (uint64_t done = 0; done < n_events && !rcode; done += chunk_max) {
     const uint64_t m = std::min<uint64_t>(chunk_max, n_events - done);
@@ -834,6 +899,7 @@ int nb200_run(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo, co
         cudaMemcpyAsync(static_cast<char*>(col.host) + col.elt * done, col.dev, col.elt * m, cudaMemcpyDeviceToHost,
                         c->stream);
     rcode = check_device_error(c);
+    tr.mark("chunk kernel + copies");
   }
   if (!rcode && hist) {
     std::vector<unsigned long long> w(c->band_tmp_words);
@@ -858,7 +924,9 @@ int nb200_run(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo, co
     }
   }
   cudaStreamSynchronize(c->stream);
+  tr.mark("band fetch");
   cleanup();
+  tr.mark("staging free");
   return rcode;
 }
 

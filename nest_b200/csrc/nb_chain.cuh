@@ -79,8 +79,8 @@ NB_D double fano_er(double density, double Nq_mean, double efield, const double*
 NB_D int to_int_round(double x) { return int(floor(x + 0.5)); }
 
 // NESTcalc::GetQuanta NEST.cpp:248-432
-NB_D Quanta get_quanta(Stream& g, const Yields& y, double density, const nb200_detector& det,
-                       const nb200_model& mo, int* err) {
+NB_D Quanta get_quanta(Stream& g, uint64_t seed, uint64_t ev, const Yields& y, double density,
+                       const nb200_detector& det, const nb200_model& mo, int* err) {
   const double* w = mo.NRERWidthsParam;
   Quanta q{0, 0, 0, 0, 0., 0.};
   bool HighE;
@@ -105,7 +105,7 @@ NB_D Quanta get_quanta(Stream& g, const Yields& y, double density, const nb200_d
       double Fano = fano_er(density, Nq_mean, y.field, w, det.inGas != 0);
       Nq_actual = to_int_round(gauss(g, Nq_mean, sqrt(Fano * Nq_mean), true));
     }
-    Ni = int(binomial(g, Nq_actual, alf));
+    Ni = int(binomial(seed, ev, STREAM_BIN_NI, Nq_actual, alf));
     Nex = Nq_actual - Ni;
   } else {
     // two independent Gaussians (:294-311); both come from one Box-Muller pair
@@ -235,7 +235,7 @@ NB_D double s1_eff(const nb200_detector& det, int nHits) {
 }
 
 // GetS1 up to the per-hit loop: NEST.cpp:1288-1362
-NB_D S1Pre s1_prelude(Stream& g, const RunParams& P, int Nph, double tx, double ty, double tz,
+NB_D S1Pre s1_prelude(uint64_t ev, const RunParams& P, int Nph, double tx, double ty, double tz,
                       double sx, double sy, double sz, double energy) {
   const nb200_detector& det = P.det;
   S1Pre r;
@@ -252,7 +252,7 @@ NB_D S1Pre s1_prelude(Stream& g, const RunParams& P, int Nph, double tx, double 
     g1_XYZ = 0.;
     r.posDepSm = 0.;
   }
-  r.nHits = int(binomial(g, Nph, g1_XYZ));
+  r.nHits = int(binomial(P.seed, ev, STREAM_BIN_S1, Nph, g1_XYZ));
   r.eff = s1_eff(det, r.nHits);
   int mode = P.ana.s1mode;
   if (mode == NB200_S1_HYBRID) mode = energy < 100. ? NB200_S1_FULL : NB200_S1_PARAMETRIC;
@@ -270,7 +270,9 @@ struct S1Acc {
 //   * phe = zero-truncated Gaussian(1/NewMean, sPEres) + Gaussian baseline noise; the two
 //     normals are the two outputs of ONE Box-Muller transform (independent N(0,1));
 //   * u > eff kills the area only when eff < 1 (u <= 1 always);
-//   * the double-phe decision uses a 32-bit uniform;
+//   * the double-phe decision uses a 32-bit uniform, and the second photo-electron (17 % of
+//     hits) is computed by s1_hit_second from its own counter block so that the caller can
+//     defer it and run 32 of them together instead of one lane in six;
 //   * -20 ln u < coinWind is tested as u > exp(-coinWind/20) and the draw is skipped when
 //     nHits > coinLevel makes the test irrelevant.
 NB_D double s1_ztg_redraw(uint64_t seed, uint64_t event, uint32_t blk, double mean, double sigma) {
@@ -284,11 +286,11 @@ NB_D double s1_ztg_redraw(uint64_t seed, uint64_t event, uint32_t blk, double me
   } while (t <= 0. && ++guard < 60);
   return t;
 }
-NB_D void s1_hit(const RunParams& P, uint64_t seed, uint64_t event, uint32_t k, double eff,
-                 bool need_coin, double spe_mean, S1Acc& acc) {
+// First photo-electron of hit k: returns phe1 (zeroed when the single-phe efficiency draw loses
+// it, :1381-1386) and whether the photon makes a second one (:1390).
+NB_D double s1_hit_first(const RunParams& P, uint32_t k0, uint32_t k1, uint32_t e0, uint32_t e1,
+                         uint32_t k, double eff, double spe_mean, bool& dphe) {
   const nb200_detector& det = P.det;
-  const uint32_t k0 = uint32_t(seed), k1 = uint32_t(seed >> 32);
-  const uint32_t e0 = uint32_t(event), e1 = uint32_t(event >> 32);
   // block 1: radius (53 bits), angle (32 bits), double-phe decision (32 bits)
   u128 r = philox4x32_10(e0, e1, k, STREAM_HIT, k0, k1);
   double rad = sqrt(-2.0 * log(u53(r.x, r.y)));
@@ -296,49 +298,48 @@ NB_D void s1_hit(const RunParams& P, uint64_t seed, uint64_t event, uint32_t k, 
   sincospi(2.0 * u32d(r.z), &s, &c);
   double tg = fma(det.sPEres, rad * c, spe_mean);
   if (tg <= 0.)  // redraw the truncated Gaussian (P ~ 0.4 % at sPEres 0.37)
-    tg = s1_ztg_redraw(seed, event, k * 64u, spe_mean, det.sPEres);
+    tg = s1_ztg_redraw((uint64_t(k1) << 32) | k0, (uint64_t(e1) << 32) | e0, k * 64u, spe_mean, det.sPEres);
   double phe1 = tg + fma(det.noiseBaseline[1], rad * s, det.noiseBaseline[0]);
-  int nphe = 1;
-  const bool dphe = u32d(r.w) < det.P_dphe;
-  double phe2 = 0., ucoin = 1.;
-  bool lost1 = false, lost2 = false;
-  if (eff < 1.) {  // block 3: the two single-phe efficiency decisions (:1381-1386, :1403)
+  dphe = u32d(r.w) < det.P_dphe;
+  if (eff < 1.) {  // block 3: the single-phe efficiency decisions (:1381-1386, :1403)
     u128 t = philox4x32_10(e0, e1, k, STREAM_HIT3, k0, k1);
-    lost1 = u32d(t.x) > eff;
-    lost2 = u32d(t.y) > eff;
+    if (u32d(t.x) > eff) phe1 = 0.;
   }
-  if (dphe || need_coin) {
-    // block 2: second photo-electron (radius, angle) and the coincidence-window draw
-    u128 q = philox4x32_10(e0, e1, k, STREAM_HIT2, k0, k1);
-    ucoin = u32d(q.w);
-    if (dphe) {
-      double rad2 = sqrt(-2.0 * log(u53(q.x, q.y)));
-      double s2, c2;
-      sincospi(2.0 * u32d(q.z), &s2, &c2);
-      double tg2 = fma(det.sPEres, rad2 * c2, spe_mean);
-      if (tg2 <= 0.) tg2 = s1_ztg_redraw(seed, event, k * 64u + 32u, spe_mean, det.sPEres);
-      phe2 = tg2 + fma(det.noiseBaseline[1], rad2 * s2, det.noiseBaseline[0]);
-      ++nphe;
-      if (lost2 && lost1) phe2 = 0.;
-    }
+  return phe1;
+}
+// coincidence-window draw of hit k (block 2, word w): only events with nHits <= coinLevel need it
+NB_D double s1_hit_ucoin(uint32_t k0, uint32_t k1, uint32_t e0, uint32_t e1, uint32_t k) {
+  u128 q = philox4x32_10(e0, e1, k, STREAM_HIT2, k0, k1);
+  return u32d(q.w);
+}
+// Second photo-electron of a double-phe hit (:1390-1409): returns phe2 and the coincidence draw
+NB_D double s1_hit_second(const RunParams& P, uint32_t k0, uint32_t k1, uint32_t e0, uint32_t e1,
+                          uint32_t k, double eff, double spe_mean, double& ucoin) {
+  const nb200_detector& det = P.det;
+  u128 q = philox4x32_10(e0, e1, k, STREAM_HIT2, k0, k1);
+  ucoin = u32d(q.w);
+  double rad2 = sqrt(-2.0 * log(u53(q.x, q.y)));
+  double s2, c2;
+  sincospi(2.0 * u32d(q.z), &s2, &c2);
+  double tg2 = fma(det.sPEres, rad2 * c2, spe_mean);
+  if (tg2 <= 0.)
+    tg2 = s1_ztg_redraw((uint64_t(k1) << 32) | k0, (uint64_t(e1) << 32) | e0, k * 64u + 32u, spe_mean, det.sPEres);
+  double phe2 = tg2 + fma(det.noiseBaseline[1], rad2 * s2, det.noiseBaseline[0]);
+  if (eff < 1.) {
+    u128 t = philox4x32_10(e0, e1, k, STREAM_HIT3, k0, k1);
+    if (u32d(t.y) > eff && u32d(t.x) > eff) phe2 = 0.;
   }
-  if (lost1) phe1 = 0.;
-  double a = phe1 + phe2;
-  acc.nphe += nphe;
-  if (a > det.sPEthr && (!need_coin || ucoin > P.coin_u_min)) {
-    acc.spike += 1;
-    acc.area += a;
-  }
+  return phe2;
 }
 
 // Parametric S1, NEST.cpp:1432-1481
-NB_D void s1_parametric(Stream& g, const RunParams& P, int nHits, S1Acc& acc) {
+NB_D void s1_parametric(Stream& g, uint64_t ev, const RunParams& P, int nHits, S1Acc& acc) {
   const nb200_detector& det = P.det;
-  int Nphe = nHits + int(binomial(g, nHits, det.P_dphe));
+  int Nphe = nHits + int(binomial(P.seed, ev, STREAM_BIN_PAR0, nHits, det.P_dphe));
   double eff = s1_eff(det, nHits);
-  double Nphe_det = double(binomial(g, Nphe, 1. - (1. - eff) / (1. + det.P_dphe)));
+  double Nphe_det = double(binomial(P.seed, ev, STREAM_BIN_PAR1, Nphe, 1. - (1. - eff) / (1. + det.P_dphe)));
   acc.area = gauss(g, Nphe_det * (1. / P.rc.NewMean), det.sPEres * sqrt(Nphe_det / P.rc.NewMean), true);
-  acc.spike = int(binomial(g, nHits, eff * (1. - P.below_thr_pct)));
+  acc.spike = int(binomial(P.seed, ev, STREAM_BIN_PAR2, nHits, eff * (1. - P.below_thr_pct)));
   acc.nphe = Nphe;
 }
 
@@ -427,8 +428,8 @@ NB_D void s1_epilogue(Stream& g, const RunParams& P, const S1Pre& pre, const S1A
 }
 
 // NESTcalc::GetS2, S2CalculationMode::Full: NEST.cpp:1724-1776, 1975-2063.  out[9] = ionization
-NB_D void get_s2(Stream& g, const RunParams& P, int Ne, double tx, double ty, double tz, double sx,
-                 double sy, double dt, double dfield, double* out) {
+NB_D void get_s2(Stream& g, uint64_t ev, const RunParams& P, int Ne, double tx, double ty, double tz,
+                 double sx, double sy, double dt, double dfield, double* out) {
   const nb200_detector& det = P.det;
   const double elYield = P.rc.g2_params[0], ExtEff = P.rc.g2_params[1], SE = P.rc.g2_params[2],
                g2 = P.rc.g2_params[3], gasGap = P.rc.g2_params[4];
@@ -447,12 +448,12 @@ NB_D void get_s2(Stream& g, const RunParams& P, int Ne, double tx, double ty, do
     posDepSm = 0.;
   }
   const double life = exp(-dt / det.eLife_us);
-  long long Nee = binomial(g, Ne, ExtEff * life);
+  long long Nee = binomial(P.seed, ev, STREAM_BIN_NEE, Ne, ExtEff * life);
   double mu = elYield * double(Nee);
   double nphd = floor(gauss(g, mu, sqrt(det.s2Fano * elYield * double(Nee)), true) + 0.5);
   long long Nph = (long long)nphd;
-  long long nHits = binomial(g, Nph, det.g1_gas * posDep);
-  long long Nphe = nHits + binomial(g, nHits, det.P_dphe);
+  long long nHits = binomial(P.seed, ev, STREAM_BIN_S2HIT, Nph, det.g1_gas * posDep);
+  long long Nphe = nHits + binomial(P.seed, ev, STREAM_BIN_S2DPE, nHits, det.P_dphe);
   double m = double(Nphe) / P.rc.NewMean;
   double pulseArea = gauss(g, m, det.sPEres * sqrt(m), true);
   double sig;

@@ -1,6 +1,6 @@
-// nb_kernels.cuh -- the sm_100a kernels: k_event (whole chain, one thread = one event,
-// S1 hit loops regrouped by hit count inside the block), k_yields (deterministic means)
-// and k_lar (liquid-argon yields + fluctuations).
+// nb_kernels.cuh -- the sm_100a kernels: k_pre / k_hits / k_post (the chain, with the S1 hit
+// loops flattened across events), k_yields (deterministic means) and k_lar (liquid-argon
+// yields + fluctuations).
 #pragma once
 #include "nb_chain.cuh"
 #include "nb_lar.cuh"
@@ -57,20 +57,25 @@ __global__ void __launch_bounds__(256) k_yields(const __grid_constant__ YieldsPa
 }
 
 // -------------------------------------------------------------------------------------------
-// k_event: the loop body of execNEST() (execNEST.cpp:676-1414) / runNESTvec() (:357-406).
+// The chain: the loop body of execNEST() (execNEST.cpp:676-1414) / runNESTvec() (:357-406) as
+// three kernels over a chunk of events whose per-event state lives in a device workspace
+// (structure of arrays, ~140 B/event, written by one stage and read by the next):
 //
-// Thread t of a block owns event (batch*BLOCK + t) and keeps its state in registers through
-// three phases:
-//   A  energy, vertex (drift-window retry), yields, quanta, xy smearing, S1 prelude -> nHits
-//   B  the per-hit S1 loop.  Hit counts differ by orders of magnitude between events, so the
-//      block counting-sorts its events by nHits in shared memory and thread t runs the loop
-//      of the event of rank t: the 32 lanes of a warp then carry near-equal trip counts.
-//      Hits draw from Philox blocks keyed (seed; event, hit index), so which thread runs a
-//      loop cannot change its result.
-//   C  S1 epilogue, S2, signal selection, energy reconstruction, band accumulation
-//      (shared-memory integer accumulators, flushed once per block), optional SoA record.
+//   k_pre   one thread = one event: energy, vertex (drift-window retry), yields, quanta, xy
+//           smearing and the S1 prelude up to nHits = binomial(Nph, g1(x,y,z)).
+//   k_hits  the per-hit S1 loop (NEST.cpp:1367-1429), the dominant cost.  Hit counts differ by
+//           orders of magnitude between events, so a block takes a GROUP of events, prefix-sums
+//           their hit counts in shared memory and deals the flattened hit range out evenly:
+//           every thread runs the same number of hits (+-1) whatever events they belong to.
+//           Each hit draws from its own Philox block keyed (seed; event, hit index) and the
+//           areas are accumulated as 2^-32 phe integers, so the result for an event does not
+//           depend on how the range was cut (bit-identical for any batch split / GPU count).
+//           The kernel carries no event state: few registers, high occupancy, small code.
+//   k_post  one thread = one event: S1 epilogue (noise, thresholds, coincidence, spike smearing),
+//           S2, signal selection, energy reconstruction, band accumulation (shared-memory
+//           integer accumulators flushed once per block) and the optional SoA record.
 // -------------------------------------------------------------------------------------------
-template <int BLOCK>
+template <int T>
 __device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   int x = v;
@@ -82,13 +87,13 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp) {
   if (lane == 31) s_warp[wid] = x;
   __syncthreads();
   if (wid == 0) {
-    int w = (lane < BLOCK / 32) ? s_warp[lane] : 0;
+    int w = (lane < T / 32) ? s_warp[lane] : 0;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       int t = __shfl_up_sync(0xffffffffu, w, o);
       if (lane >= o) w += t;
     }
-    if (lane < BLOCK / 32) s_warp[lane] = w;
+    if (lane < T / 32) s_warp[lane] = w;
   }
   __syncthreads();
   int base = wid ? s_warp[wid - 1] : 0;
@@ -121,236 +126,401 @@ NB_D double drift_velocity_dev(const RunParams& P, double eField) {
   return speed;
 }
 
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK, 1)
-    k_event(const __grid_constant__ RunParams P, int* __restrict__ err_flag) {
-  extern __shared__ __align__(16) unsigned long long s_band[];  // [numBins*6] then u32 hist2d
-  __shared__ int s_key[BLOCK];
-  __shared__ int s_perm[BLOCK];
-  __shared__ int s_cnt[BLOCK];
-  __shared__ int s_warp[32];
-  __shared__ double s_area[BLOCK];
-  __shared__ int s_spike[BLOCK];
-  __shared__ int s_nphe[BLOCK];
+constexpr int kPreBlock = 256;
+constexpr int kPostBlock = 256;
+constexpr int kHitGroup = 1024;  // events per k_hits group
+constexpr int kHitBlock = 256;   // threads per k_hits block
+#define NB_AREA_FX 4294967296.0  // 2^32: S1 hit areas are summed in units of 2^-32 phe
 
+__global__ void __launch_bounds__(kPreBlock, 2)
+    k_pre(const __grid_constant__ RunParams P, int* __restrict__ err_flag) {
+  const nb200_detector& det = P.det;
+  const Work& W = P.work;
+  const bool cli = !P.vec_mode;
+  for (uint64_t idx = blockIdx.x * uint64_t(kPreBlock) + threadIdx.x; idx < P.n_events;
+       idx += uint64_t(gridDim.x) * kPreBlock) {
+    const uint64_t gidx = P.chunk_off + idx;
+    const uint64_t ev = P.first_event + gidx;
+    Stream g;
+    g.init(P.seed, ev, STREAM_MAIN);
+    double px, py, pz, sx, sy, field = 0., dt = 0., vD = P.rc.vD;
+    Yields y{0., 0., 0., 0., 0., 0.};
+    Quanta q{0, 0, 0, 0, 0., 0.};
+    int err = 0;
+    double keV = sample_energy(g, P, gidx);
+    const nb200_source& S = P.src;
+    const bool nonuni = (S.inField == -1.);
+    const bool listed = (S.kind == NB200_SRC_LIST && S.x != nullptr);
+    if (listed) {
+      px = S.x[gidx];
+      py = S.y[gidx];
+      pz = S.z[gidx];
+    } else {
+      px = S.xyz[0];
+      py = S.xyz[1];
+      pz = S.xyz[2];
+    }
+    const bool ranXY = (S.fixed_pos == 0 || S.fixed_pos == 3) && !listed;
+    const bool ranZ = (S.fixed_pos == 0 || S.fixed_pos == 2) && !listed;
+    for (int guard = 0; guard < 10000; ++guard) {  // Z_NEW loop execNEST.cpp:806-967
+      if (ranZ) pz = 0. + (det.TopDrift - 0.) * g.uniform();
+      if (ranXY && (guard == 0 || S.fixed_pos == 0)) {
+        double r = det.radius * sqrt(g.uniform());
+        double sn, cs;
+        sincospi(2. * g.uniform(), &sn, &cs);
+        px = r * cs;
+        py = r * sn;
+      }
+      if (cli)
+        field = nonuni ? fit_ef(det.FitEF, px, py, pz) : S.inField;
+      else
+        field = (S.inField < 0.0) ? fit_ef(det.FitEF, px, py, pz) : S.inField;
+      if (cli) {
+        if (nonuni) vD = P.vtable[min(max(int(floor(pz / P.ana.z_step + 0.5)), 0), P.vtable_n - 1)];
+      } else if (S.inField < 0.0)
+        vD = drift_velocity_dev(P, field);
+      dt = (det.TopDrift - pz) / vD;
+      if (cli && ranZ && (dt > det.dt_max || dt < det.dt_min) && field >= NB_FIELD_MIN) continue;
+      break;
+    }
+    if (cli) {  // execNEST.cpp:975-992
+      if (pz <= 0) pz = P.ana.z_step;
+      if ((pz > (det.TopDrift + P.ana.z_step) || dt < 0.0) && field >= NB_FIELD_MIN) {
+        dt = 0.0;
+        pz = det.TopDrift - P.ana.z_step;
+      }
+    }
+    // yields + quanta: execNEST.cpp:1031-1077 / FullCalculation NEST.cpp:22-42
+    const int sp = P.species;
+    const bool nrlike = sp <= NB200_Cf || sp == NB200_atmNu;
+    if (!cli || keV > 0.001 * P.rc.Wq_eV) {
+      int A2 = 131;
+      if (P.model.er_model < 0 && ((nrlike && nearly_equal(P.model.massNum, 0.)) || sp == NB200_ion))
+        A2 = select_xe_atom(g);
+      if (P.model.er_model == 0)
+        y = yield_beta(keV, P.rc.rho, field, det, P.model.ERYieldsParam, P.model.multFact);
+      else if (P.model.er_model == 1)
+        y = yield_gamma(keV, P.rc.rho, field, det, P.model.multFact);
+      else if (P.model.er_model == 2)
+        y = yield_er_weighted(keV, P.rc.rho, field, det, P.model.ERYieldsParam);
+      else
+        y = get_yields(sp, keV, P.rc.rho, field, P.model.massNum, P.model.atomNum, A2, det, P.model, &err);
+      q = get_quanta(g, P.seed, ev, y, P.rc.rho, det, P.model, &err);
+    }
+    if (cli && (det.noiseBaseline[2] != 0. || det.noiseBaseline[3] != 0.))
+      q.electrons += to_int_round(gauss(g, det.noiseBaseline[2], det.noiseBaseline[3], false));
+    // position smearing execNEST.cpp:1090-1099
+    sx = px;
+    sy = py;
+    if (cli) {
+      double Nphd_S2 = fabs(P.rc.g2_params[3]) * q.electrons * exp(-dt / det.eLife_us);
+      if (!P.ana.MCtruthPos && Nphd_S2 > NB_PHE_MIN) xy_resolution(g, det, px, py, Nphd_S2, sx, sy);
+    }
+    S1Pre pre = s1_prelude(ev, P, q.photons, px, py, pz, sx, sy, pz, keV);
+
+    W.keV[idx] = keV;
+    W.px[idx] = px;
+    W.py[idx] = py;
+    W.pz[idx] = pz;
+    W.sx[idx] = sx;
+    W.sy[idx] = sy;
+    W.field[idx] = field;
+    W.dt[idx] = dt;
+    W.yNph[idx] = y.Nph;
+    W.yNe[idx] = y.Ne;
+    W.yL[idx] = y.L;
+    W.posDepSm[idx] = pre.posDepSm;
+    W.fitSm[idx] = pre.fitSm;
+    W.photons[idx] = q.photons;
+    W.electrons[idx] = q.electrons;
+    W.ions[idx] = q.ions;
+    W.excitons[idx] = q.excitons;
+    W.nHits[idx] = pre.full ? pre.nHits : -(pre.nHits + 1);  // negative: Parametric S1 in k_post
+    if (err) atomicOr(err_flag, err);
+  }
+}
+
+// finish one double-phe hit taken from the warp queue: add the second photo-electron, apply the
+// threshold / coincidence test (NEST.cpp:1421-1427) and add to the owning event's accumulators
+NB_D void hit_finish_dphe(const RunParams& P, const int* s_pref, unsigned long long* s_area,
+                          unsigned int* s_spike, uint64_t ev0, int slot, uint32_t k, double phe1,
+                          double spe_mean) {
+  const nb200_detector& det = P.det;
+  const int ne = s_pref[slot + 1] - s_pref[slot];
+  const double eff = s1_eff(det, ne);
+  const bool need_coin = !(ne > det.coinLevel);
+  const uint64_t ev = ev0 + slot;
+  double ucoin;
+  double phe2 = s1_hit_second(P, uint32_t(P.seed), uint32_t(P.seed >> 32), uint32_t(ev), uint32_t(ev >> 32), k,
+                              eff, spe_mean, ucoin);
+  double a = phe1 + phe2;
+  if (a > det.sPEthr && (!need_coin || ucoin > P.coin_u_min)) {
+    atomicAdd(&s_area[slot], (unsigned long long)__double2ll_rn(a * NB_AREA_FX));
+    atomicAdd(&s_spike[slot], 1u);
+  }
+}
+
+__global__ void __launch_bounds__(kHitBlock, 4)
+    k_hits(const __grid_constant__ RunParams P) {
+  __shared__ int s_pref[kHitGroup + 1];
+  __shared__ unsigned long long s_area[kHitGroup];
+  __shared__ unsigned int s_spike[kHitGroup];
+  __shared__ unsigned int s_nphe[kHitGroup];
+  __shared__ int s_warp[32];
+  // per-warp queue of double-phe hits waiting for their second photo-electron
+  __shared__ double s_qphe[kHitBlock / 32][64];
+  __shared__ uint32_t s_qk[kHitBlock / 32][64];
+  __shared__ uint16_t s_qslot[kHitBlock / 32][64];
+  constexpr int PER = kHitGroup / kHitBlock;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const nb200_detector& det = P.det;
+  const Work& W = P.work;
+  const double spe_mean = 1. / P.rc.NewMean;
+  const uint32_t k0 = uint32_t(P.seed), k1 = uint32_t(P.seed >> 32);
+  const uint64_t n_groups = (P.n_events + kHitGroup - 1) / kHitGroup;
+  double* qphe = s_qphe[wid];
+  uint32_t* qk = s_qk[wid];
+  uint16_t* qslot = s_qslot[wid];
+
+  for (uint64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    const uint64_t gbase = grp * kHitGroup;
+    const uint64_t ev0 = P.first_event + P.chunk_off + gbase;
+    // hit counts of my PER consecutive events -> exclusive prefix over the group
+    int cnt[PER];
+    int mine = 0;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const uint64_t idx = gbase + uint64_t(tid) * PER + j;
+      int n = (idx < P.n_events) ? W.nHits[idx] : 0;
+      cnt[j] = n > 0 ? n : 0;
+      mine += cnt[j];
+      s_area[tid * PER + j] = 0ull;
+      s_spike[tid * PER + j] = 0u;
+      s_nphe[tid * PER + j] = 0u;
+    }
+    int off = block_exclusive_scan<kHitBlock>(mine, s_warp);
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      s_pref[tid * PER + j] = off;
+      off += cnt[j];
+    }
+    if (tid == kHitBlock - 1) s_pref[kHitGroup] = off;
+    __syncthreads();
+    const int H = s_pref[kHitGroup];
+    const int h0 = int((long long)H * tid / kHitBlock);
+    const int h1 = int((long long)H * (tid + 1) / kHitBlock);
+    const int len = h1 - h0;
+    const int maxlen = __reduce_max_sync(0xffffffffu, len);
+    int e = 0, e_end = 0, ne = 0, k = 0;
+    double eff = 1.;
+    bool need_coin = false;
+    uint64_t hev = ev0;
+    if (len > 0) {
+      // event owning hit h0: largest e with s_pref[e] <= h0
+      int lo = 0, hi = kHitGroup;
+      while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (s_pref[mid] <= h0)
+          lo = mid;
+        else
+          hi = mid;
+      }
+      e = lo;
+      e_end = s_pref[e + 1];
+      ne = e_end - s_pref[e];
+      k = h0 - s_pref[e];
+      eff = s1_eff(det, ne);
+      need_coin = !(ne > det.coinLevel);
+      hev = ev0 + e;
+    }
+    unsigned long long a_fx = 0ull;
+    unsigned int a_spike = 0u, a_nphe = 0u;
+    int qcount = 0;  // warp-uniform
+    for (int i = 0; i < maxlen; ++i) {
+      const int h = h0 + i;
+      const bool act = i < len;
+      bool dphe = false;
+      double phe1 = 0.;
+      if (act) {
+        if (h == e_end) {  // crossed into the next event with hits: flush, then advance
+          atomicAdd(&s_area[e], a_fx);
+          atomicAdd(&s_spike[e], a_spike);
+          atomicAdd(&s_nphe[e], a_nphe);
+          a_fx = 0ull;
+          a_spike = a_nphe = 0u;
+          do {
+            ++e;
+            e_end = s_pref[e + 1];
+          } while (e_end == h);
+          ne = e_end - s_pref[e];
+          k = 0;
+          eff = s1_eff(det, ne);
+          need_coin = !(ne > det.coinLevel);
+          hev = ev0 + e;
+        }
+        phe1 = s1_hit_first(P, k0, k1, uint32_t(hev), uint32_t(hev >> 32), uint32_t(k), eff, spe_mean, dphe);
+        a_nphe += dphe ? 2u : 1u;
+        if (!dphe) {
+          bool pass = phe1 > det.sPEthr;
+          if (pass && need_coin)
+            pass = s1_hit_ucoin(k0, k1, uint32_t(hev), uint32_t(hev >> 32), uint32_t(k)) > P.coin_u_min;
+          if (pass) {
+            a_spike += 1u;
+            a_fx += (unsigned long long)__double2ll_rn(phe1 * NB_AREA_FX);
+          }
+        }
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, dphe);
+      if (m) {
+        if (dphe) {
+          const int pos = qcount + __popc(m & ((1u << lane) - 1u));
+          qphe[pos] = phe1;
+          qk[pos] = uint32_t(k);
+          qslot[pos] = uint16_t(e);
+        }
+        qcount += __popc(m);
+        __syncwarp();
+        if (qcount >= 32) {
+          const int j = qcount - 32 + lane;
+          hit_finish_dphe(P, s_pref, s_area, s_spike, ev0, int(qslot[j]), qk[j], qphe[j], spe_mean);
+          qcount -= 32;
+          __syncwarp();
+        }
+      }
+      ++k;
+    }
+    if (lane < qcount)
+      hit_finish_dphe(P, s_pref, s_area, s_spike, ev0, int(qslot[lane]), qk[lane], qphe[lane], spe_mean);
+    if (len > 0) {
+      atomicAdd(&s_area[e], a_fx);
+      atomicAdd(&s_spike[e], a_spike);
+      atomicAdd(&s_nphe[e], a_nphe);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const int i = j * kHitBlock + tid;  // coalesced
+      const uint64_t idx = gbase + i;
+      if (idx < P.n_events) {
+        W.area[idx] = double(s_area[i]) * (1. / NB_AREA_FX);
+        W.spike[idx] = int(s_spike[i]);
+        W.nphe[idx] = int(s_nphe[i]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kPostBlock, 2)
+    k_post(const __grid_constant__ RunParams P, int* __restrict__ err_flag) {
+  extern __shared__ __align__(16) unsigned long long s_band[];  // [numBins*6] then u32 hist2d
   const int tid = threadIdx.x;
   const nb200_detector& det = P.det;
+  const Work& W = P.work;
   const int nb = P.ana.numBins, lb = P.ana.logBins;
   const bool band_smem = P.do_band && P.band_in_smem;
   unsigned int* s_h2 = reinterpret_cast<unsigned int*>(s_band + size_t(nb) * BAND_WORDS);
   if (band_smem) {
-    for (int i = tid; i < nb * BAND_WORDS; i += BLOCK) s_band[i] = 0ull;
-    for (int i = tid; i < nb * lb; i += BLOCK) s_h2[i] = 0u;
+    for (int i = tid; i < nb * BAND_WORDS; i += kPostBlock) s_band[i] = 0ull;
+    for (int i = tid; i < nb * lb; i += kPostBlock) s_h2[i] = 0u;
+    __syncthreads();
   }
-  __syncthreads();
-
-  const uint64_t n_batches = (P.n_events + BLOCK - 1) / BLOCK;
-  const double spe_mean = 1. / P.rc.NewMean;
   const bool cli = !P.vec_mode;
-
-  for (uint64_t batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
-    const uint64_t idx = batch * BLOCK + tid;
-    const bool active = idx < P.n_events;
-    const uint64_t ev = P.first_event + idx;
-
-    // ---------------- phase A ----------------
+  for (uint64_t idx = blockIdx.x * uint64_t(kPostBlock) + tid; idx < P.n_events;
+       idx += uint64_t(gridDim.x) * kPostBlock) {
+    const uint64_t gidx = P.chunk_off + idx;
+    const uint64_t ev = P.first_event + gidx;
     Stream g;
-    g.init(P.seed, ev, STREAM_MAIN);
-    double keV = 0., px = 0., py = 0., pz = 0., sx = 0., sy = 0., field = 0., dt = 0., vD = P.rc.vD;
-    Yields y{0., 0., 0., 0., 0., 0.};
-    Quanta q{0, 0, 0, 0, 0., 0.};
-    S1Pre pre{1., 1., 1., 0, false};
-    int err = 0;
-    if (active) {
-      keV = sample_energy(g, P, idx);
-      const nb200_source& S = P.src;
-      const bool nonuni = (S.inField == -1.);
-      if (S.kind == NB200_SRC_LIST && S.x != nullptr) {
-        px = S.x[idx];
-        py = S.y[idx];
-        pz = S.z[idx];
-      } else {
-        px = S.xyz[0];
-        py = S.xyz[1];
-        pz = S.xyz[2];
+    g.init(P.seed, ev, STREAM_POST);
+    double keV = W.keV[idx];
+    const double px = W.px[idx], py = W.py[idx], pz = W.pz[idx], sx = W.sx[idx], sy = W.sy[idx];
+    const double field = W.field[idx], dt = W.dt[idx];
+    Yields y{W.yNph[idx], W.yNe[idx], 0., W.yL[idx], field, -999.};
+    S1Pre pre;
+    pre.posDepSm = W.posDepSm[idx];
+    pre.fitSm = W.fitSm[idx];
+    const int nh = W.nHits[idx];
+    pre.full = nh >= 0;
+    pre.nHits = pre.full ? nh : -(nh + 1);
+    pre.eff = 0.;
+    S1Acc acc{0., 0, 0};
+    if (pre.full) {
+      if (nh > 0) {
+        acc.area = W.area[idx];
+        acc.spike = W.spike[idx];
+        acc.nphe = W.nphe[idx];
       }
-      const bool ranXY = (S.fixed_pos == 0 || S.fixed_pos == 3) && !(S.kind == NB200_SRC_LIST && S.x);
-      const bool ranZ = (S.fixed_pos == 0 || S.fixed_pos == 2) && !(S.kind == NB200_SRC_LIST && S.x);
-      for (int guard = 0; guard < 10000; ++guard) {  // Z_NEW loop execNEST.cpp:806-967
-        if (ranZ) pz = 0. + (det.TopDrift - 0.) * g.uniform();
-        if (ranXY && (guard == 0 || S.fixed_pos == 0)) {
-          double r = det.radius * sqrt(g.uniform());
-          double sn, cs;
-          sincospi(2. * g.uniform(), &sn, &cs);
-          px = r * cs;
-          py = r * sn;
+    } else
+      s1_parametric(g, ev, P, pre.nHits, acc);
+    double scint[9], scint2[9];
+    s1_epilogue(g, P, pre, acc, scint);
+    int Ne = W.electrons[idx];
+    if (cli && pz < det.cathode) Ne = 0;  // execNEST.cpp:1107
+    get_s2(g, ev, P, Ne, px, py, pz, sx, sy, dt, field, scint2);
+    double signal1 = 0., signal2 = 0., signalE = 0.;
+    const double keV_true = keV;
+    if (cli) {
+      select_signals(P.ana, scint, scint2, signal1, signal2);
+      signalE = reconstruct_energy(P, y, scint, scint2, signal1, signal2, field, keV);
+      if (P.do_band) {
+        bool acc_ok = false;
+        double xv = 0., yv = 0.;
+        int bin = band_bin(P, signal1, signal2, acc_ok, xv, yv);
+        if (bin >= 0) {
+          unsigned long long* B = band_smem ? s_band : P.band;
+          unsigned long long* b = B + size_t(bin) * BAND_WORDS;
+          if (acc_ok) {
+            atomicAdd(&b[0], 1ull);
+            atomicAdd(&b[2], (unsigned long long)(long long)llrint(xv * NB200_FX_S1));
+            atomicAdd(&b[3], (unsigned long long)(long long)llrint(yv * NB200_FX_Y));
+            atomicAdd(&b[4], (unsigned long long)(long long)llrint(yv * yv * NB200_FX_Y2));
+            atomicAdd(&b[5], (unsigned long long)(long long)llrint(yv * yv * yv * NB200_FX_Y3));
+            if (yv != 0. && lb > 0) {
+              int jb = int((yv - P.ana.logMin) / (P.ana.logMax - P.ana.logMin) * double(lb));
+              jb = min(max(jb, 0), lb - 1);
+              if (band_smem)
+                atomicAdd(&s_h2[bin * lb + jb], 1u);
+              else
+                atomicAdd(&P.band[size_t(nb) * BAND_WORDS + size_t(bin) * lb + jb], 1ull);
+            }
+          } else
+            atomicAdd(&b[1], 1ull);
         }
-        if (cli)
-          field = nonuni ? fit_ef(det.FitEF, px, py, pz) : S.inField;
-        else
-          field = (S.inField < 0.0) ? fit_ef(det.FitEF, px, py, pz) : S.inField;
-        if (cli) {
-          if (nonuni) vD = P.vtable[min(max(int(floor(pz / P.ana.z_step + 0.5)), 0), P.vtable_n - 1)];
-        } else if (S.inField < 0.0)
-          vD = drift_velocity_dev(P, field);
-        dt = (det.TopDrift - pz) / vD;
-        if (cli && ranZ && (dt > det.dt_max || dt < det.dt_min) && field >= NB_FIELD_MIN) continue;
-        break;
-      }
-      if (cli) {  // execNEST.cpp:975-992
-        if (pz <= 0) pz = P.ana.z_step;
-        if ((pz > (det.TopDrift + P.ana.z_step) || dt < 0.0) && field >= NB_FIELD_MIN) {
-          dt = 0.0;
-          pz = det.TopDrift - P.ana.z_step;
-        }
-      }
-
-      // yields + quanta: execNEST.cpp:1031-1077 / FullCalculation NEST.cpp:22-42
-      const int sp = P.species;
-      const bool nrlike = sp <= NB200_Cf || sp == NB200_atmNu;
-      if (!cli || keV > 0.001 * P.rc.Wq_eV) {
-        int A2 = 131;
-        if (P.model.er_model < 0 && ((nrlike && nearly_equal(P.model.massNum, 0.)) || sp == NB200_ion))
-          A2 = select_xe_atom(g);
-        if (P.model.er_model == 0)
-          y = yield_beta(keV, P.rc.rho, field, det, P.model.ERYieldsParam, P.model.multFact);
-        else if (P.model.er_model == 1)
-          y = yield_gamma(keV, P.rc.rho, field, det, P.model.multFact);
-        else if (P.model.er_model == 2)
-          y = yield_er_weighted(keV, P.rc.rho, field, det, P.model.ERYieldsParam);
-        else
-          y = get_yields(sp, keV, P.rc.rho, field, P.model.massNum, P.model.atomNum, A2, det, P.model, &err);
-        q = get_quanta(g, y, P.rc.rho, det, P.model, &err);
-      }
-      if (cli && (det.noiseBaseline[2] != 0. || det.noiseBaseline[3] != 0.))
-        q.electrons += to_int_round(gauss(g, det.noiseBaseline[2], det.noiseBaseline[3], false));
-
-      // position smearing execNEST.cpp:1090-1099
-      sx = px;
-      sy = py;
-      if (cli) {
-        double Nphd_S2 = fabs(P.rc.g2_params[3]) * q.electrons * exp(-dt / det.eLife_us);
-        if (!P.ana.MCtruthPos && Nphd_S2 > NB_PHE_MIN) xy_resolution(g, det, px, py, Nphd_S2, sx, sy);
-      }
-      pre = s1_prelude(g, P, q.photons, px, py, pz, sx, sy, pz, keV);
-    }
-
-    // ---------------- phase B: hit loops regrouped by trip count ----------------
-    const int myHits = (active && pre.full) ? pre.nHits : 0;
-    const int key = min(myHits, BLOCK - 1);
-    s_key[tid] = myHits;
-    s_cnt[tid] = 0;
-    __syncthreads();
-    atomicAdd(&s_cnt[key], 1);
-    __syncthreads();
-    {
-      int c = s_cnt[tid];
-      int off = block_exclusive_scan<BLOCK>(c, s_warp);
-      s_cnt[tid] = off;
-    }
-    __syncthreads();
-    s_perm[atomicAdd(&s_cnt[key], 1)] = tid;
-    __syncthreads();
-    {
-      // descending: warp 0 takes the longest loops so that they start first
-      const int slot = s_perm[BLOCK - 1 - tid];
-      const int n = s_key[slot];
-      if (n > 0) {
-        const uint64_t hev = P.first_event + batch * BLOCK + slot;
-        const double eff = s1_eff(det, n);
-        const bool need_coin = !(n > det.coinLevel);
-        S1Acc acc{0., 0, 0};
-        for (int k = 0; k < n; ++k) s1_hit(P, P.seed, hev, uint32_t(k), eff, need_coin, spe_mean, acc);
-        s_area[slot] = acc.area;
-        s_spike[slot] = acc.spike;
-        s_nphe[slot] = acc.nphe;
       }
     }
-    __syncthreads();
-
-    // ---------------- phase C ----------------
-    if (active) {
-      S1Acc acc{0., 0, 0};
-      if (pre.full) {
-        if (myHits > 0) {
-          acc.area = s_area[tid];
-          acc.spike = s_spike[tid];
-          acc.nphe = s_nphe[tid];
-        }
-      } else
-        s1_parametric(g, P, pre.nHits, acc);
-      double scint[9], scint2[9];
-      s1_epilogue(g, P, pre, acc, scint);
-      int Ne = q.electrons;
-      if (cli && pz < det.cathode) Ne = 0;  // execNEST.cpp:1107
-      get_s2(g, P, Ne, px, py, pz, sx, sy, dt, field, scint2);
-      double signal1 = 0., signal2 = 0., signalE = 0.;
-      const double keV_true = keV;
-      if (cli) {
-        select_signals(P.ana, scint, scint2, signal1, signal2);
-        signalE = reconstruct_energy(P, y, scint, scint2, signal1, signal2, field, keV);
-        if (P.do_band) {
-          bool acc_ok = false;
-          double xv = 0., yv = 0.;
-          int bin = band_bin(P, signal1, signal2, acc_ok, xv, yv);
-          if (bin >= 0) {
-            unsigned long long* B = band_smem ? s_band : P.band;
-            unsigned long long* b = B + size_t(bin) * BAND_WORDS;
-            if (acc_ok) {
-              atomicAdd(&b[0], 1ull);
-              atomicAdd(&b[2], (unsigned long long)(long long)llrint(xv * NB200_FX_S1));
-              atomicAdd(&b[3], (unsigned long long)(long long)llrint(yv * NB200_FX_Y));
-              atomicAdd(&b[4], (unsigned long long)(long long)llrint(yv * yv * NB200_FX_Y2));
-              atomicAdd(&b[5], (unsigned long long)(long long)llrint(yv * yv * yv * NB200_FX_Y3));
-              if (yv != 0. && lb > 0) {
-                int jb = int((yv - P.ana.logMin) / (P.ana.logMax - P.ana.logMin) * double(lb));
-                jb = min(max(jb, 0), lb - 1);
-                if (band_smem)
-                  atomicAdd(&s_h2[bin * lb + jb], 1u);
-                else
-                  atomicAdd(&P.band[size_t(nb) * BAND_WORDS + size_t(bin) * lb + jb], 1ull);
-              }
-            } else
-              atomicAdd(&b[1], 1ull);
-          }
-        }
-      }
-      if (P.write_soa) {
-        const SoaDev& o = P.soa;
-        if (o.energy_kev) o.energy_kev[idx] = keV_true;
-        if (o.x_mm) o.x_mm[idx] = px;
-        if (o.y_mm) o.y_mm[idx] = py;
-        if (o.z_mm) o.z_mm[idx] = pz;
-        if (o.field) o.field[idx] = field;
-        if (o.driftTime) o.driftTime[idx] = dt;
-        if (o.smear_x) o.smear_x[idx] = sx;
-        if (o.smear_y) o.smear_y[idx] = sy;
-        if (o.photons) o.photons[idx] = q.photons;
-        if (o.electrons) o.electrons[idx] = Ne;
-        if (o.ions) o.ions[idx] = q.ions;
-        if (o.excitons) o.excitons[idx] = q.excitons;
+    if (P.write_soa) {
+      const SoaDev& o = P.soa;
+      if (o.energy_kev) o.energy_kev[gidx] = keV_true;
+      if (o.x_mm) o.x_mm[gidx] = px;
+      if (o.y_mm) o.y_mm[gidx] = py;
+      if (o.z_mm) o.z_mm[gidx] = pz;
+      if (o.field) o.field[gidx] = field;
+      if (o.driftTime) o.driftTime[gidx] = dt;
+      if (o.smear_x) o.smear_x[gidx] = sx;
+      if (o.smear_y) o.smear_y[gidx] = sy;
+      if (o.photons) o.photons[gidx] = W.photons[idx];
+      if (o.electrons) o.electrons[gidx] = Ne;
+      if (o.ions) o.ions[gidx] = W.ions[idx];
+      if (o.excitons) o.excitons[gidx] = W.excitons[idx];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) {
-          if (o.s1[k]) o.s1[k][idx] = scint[k];
-          if (o.s2[k]) o.s2[k][idx] = scint2[k];
-        }
-        if (o.signal1) o.signal1[idx] = signal1;
-        if (o.signal2) o.signal2[idx] = signal2;
-        if (o.signalE) o.signalE[idx] = cli ? signalE : keV;
-        if (o.Nph_mean) o.Nph_mean[idx] = y.Nph;
-        if (o.Ne_mean) o.Ne_mean[idx] = y.Ne;
+      for (int k = 0; k < 9; ++k) {
+        if (o.s1[k]) o.s1[k][gidx] = scint[k];
+        if (o.s2[k]) o.s2[k][gidx] = scint2[k];
       }
-      if (err) atomicOr(err_flag, err);
+      if (o.signal1) o.signal1[gidx] = signal1;
+      if (o.signal2) o.signal2[gidx] = signal2;
+      if (o.signalE) o.signalE[gidx] = cli ? signalE : keV;
+      if (o.Nph_mean) o.Nph_mean[gidx] = y.Nph;
+      if (o.Ne_mean) o.Ne_mean[gidx] = y.Ne;
     }
   }
-
   if (band_smem) {
     __syncthreads();
-    for (int i = tid; i < nb * BAND_WORDS; i += BLOCK) {
+    for (int i = tid; i < nb * BAND_WORDS; i += kPostBlock) {
       unsigned long long v = s_band[i];
       if (v) atomicAdd(&P.band[i], v);
     }
-    for (int i = tid; i < nb * lb; i += BLOCK) {
+    for (int i = tid; i < nb * lb; i += kPostBlock) {
       unsigned int v = s_h2[i];
       if (v) atomicAdd(&P.band[size_t(nb) * BAND_WORDS + i], (unsigned long long)v);
     }
@@ -387,7 +557,7 @@ __global__ void __launch_bounds__(256) k_lar(const __grid_constant__ LArParams P
       Stream g;
       g.init(P.seed, P.first_event + i, STREAM_LAR);
       double f[4];
-      lar_fluctuations(g, y, f);
+      lar_fluctuations(g, P.seed, P.first_event + i, y, f);
       P.fluct[i] = f[0];
       P.fluct[P.n + i] = f[1];
       P.fluct[2 * P.n + i] = f[2];

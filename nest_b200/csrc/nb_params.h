@@ -23,6 +23,13 @@ struct SoaDev {  // nb200_soa_out with device pointers (null = column not writte
   double *signal1, *signal2, *signalE, *Nph_mean, *Ne_mean;
 };
 
+// per-event state handed from k_pre to k_hits to k_post (device workspace, one chunk)
+struct Work {
+  double *keV, *px, *py, *pz, *sx, *sy, *field, *dt, *yNph, *yNe, *yL, *posDepSm, *fitSm, *area;
+  int32_t *photons, *electrons, *ions, *excitons, *nHits, *spike, *nphe;
+};
+enum { WORK_F64 = 14, WORK_I32 = 7 };
+
 struct RunParams {
   nb200_detector det;  // map.lut -> device memory
   nb200_model model;
@@ -47,6 +54,7 @@ struct RunParams {
   const double* vtable;
 
   uint64_t seed, first_event, n_events;
+  uint64_t chunk_off;  // index of this chunk's first event within the call (lists, SoA columns)
   int32_t species;
   int32_t vec_mode;   // 1 = runNESTvec semantics (execNEST.cpp:357-406)
   int32_t write_soa;
@@ -54,6 +62,7 @@ struct RunParams {
   int32_t band_in_smem;  // accumulate the band in shared memory (fits) or straight in global
   int32_t _pad;
   SoaDev soa;
+  Work work;
   unsigned long long* band;  // device accumulator or null
 };
 

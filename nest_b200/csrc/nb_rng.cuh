@@ -27,7 +27,12 @@ enum : uint32_t {
   STREAM_HIT2 = 2,   // S1 PMT hits: second photo-electron of a double-phe hit
   STREAM_HITX = 3,   // S1 PMT hits: rare redraws of the zero-truncated Gaussian
   STREAM_HIT3 = 4,   // S1 PMT hits: single-phe efficiency decisions (sPEeff < 1 only)
+  STREAM_POST = 5,   // per-event scalar draws after the S1 hit loop (k_post)
   STREAM_LAR = 8,
+  // each binomial draw owns a stream (the sampler is an out-of-line subroutine)
+  STREAM_BIN_NI = 32, STREAM_BIN_S1 = 33, STREAM_BIN_NEE = 34, STREAM_BIN_S2HIT = 35,
+  STREAM_BIN_S2DPE = 36, STREAM_BIN_PAR0 = 37, STREAM_BIN_PAR1 = 38, STREAM_BIN_PAR2 = 39,
+  STREAM_BIN_LAR = 40,
   STREAM_HOST = 16   // host-side draws (Poisson event count, WIMP table)
 };
 
@@ -36,14 +41,9 @@ struct u128 {
 };
 
 NB_HD void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
-#ifdef __CUDA_ARCH__
-  lo = a * b;
-  hi = __umulhi(a, b);
-#else
-  uint64_t p = uint64_t(a) * uint64_t(b);
+  uint64_t p = uint64_t(a) * uint64_t(b);  // one IMAD.WIDE.U32
   lo = uint32_t(p);
   hi = uint32_t(p >> 32);
-#endif
 }
 
 // Philox4x32-10 (Salmon et al., SC'11); constants of the Random123 reference implementation.
@@ -65,6 +65,16 @@ NB_HD u128 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uin
   }
   return u128{c0, c1, c2, c3};
 }
+
+#ifdef __CUDACC__
+// Out-of-line copy for the per-event scalar streams: those stages are long straight-line code
+// whose cost is instruction fetch, so the ~60-instruction block function is shared, not inlined.
+// (The S1 hit loop inlines philox4x32_10 directly.)
+__device__ __noinline__ u128 philox_block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                          uint32_t k1) {
+  return philox4x32_10(c0, c1, c2, c3, k0, k1);
+}
+#endif
 
 // 53-bit uniform on the OPEN interval (0,1).  The reference's rand_uniform is
 // u64/(2^64-1) on the closed interval (RandomGen.cpp:39-42); the end points have
@@ -99,7 +109,11 @@ struct Stream {
       b = s1;
       return;
     }
+#ifdef __CUDA_ARCH__
+    u128 r = philox_block(e0, e1, blk, sid, k0, k1);
+#else
     u128 r = philox4x32_10(e0, e1, blk, sid, k0, k1);
+#endif
     ++blk;
     s0 = r.z;
     s1 = r.w;
@@ -121,23 +135,25 @@ struct Stream {
 // rand_gauss (RandomGen.cpp:44-53) evaluates mean + sigma*sqrt2*sqrt(-ln u)*cos(2 pi v)
 // and throws the sine partner away; the partner is an independent N(0,1), so using it
 // halves the log/sqrt work without changing any distribution.
+__device__ __noinline__ double2 box_muller(double u, double v) {
+  double r = sqrt(-2.0 * log(u));
+  double s, co;
+  sincospi(2.0 * v, &s, &co);
+  return make_double2(r * co, r * s);
+}
 NB_D void normal_pair(Stream& g, double& z0, double& z1) {
   uint32_t a, b, c, d;
   g.next2(a, b);
   g.next2(c, d);
-  double u = u53(a, b);
-  double v = u53(c, d);
-  double r = sqrt(-2.0 * log(u));
-  double s, co;
-  sincospi(2.0 * v, &s, &co);
-  z0 = r * co;
-  z1 = r * s;
+  double2 z = box_muller(u53(a, b), u53(c, d));
+  z0 = z.x;
+  z1 = z.y;
 }
 NB_D double normal(Stream& g) {
   uint32_t a, b, c, d;
   g.next2(a, b);
   g.next2(c, d);
-  return sqrt(-2.0 * log(u53(a, b))) * cospi(2.0 * u53(c, d));
+  return box_muller(u53(a, b), u53(c, d)).x;
 }
 // rand_gauss(mean, sigma, zero_min) RandomGen.cpp:44-53
 NB_D double gauss(Stream& g, double mean, double sigma, bool zero_min) {
@@ -207,10 +223,14 @@ NB_D double stirling_tail(double k) {
 
 // binom_draw RandomGen.cpp:132-134 = std::binomial_distribution<int64_t>(n,p).  Exact
 // binomial sampler: sequential CDF inversion while n*min(p,1-p) < 10, Hormann's BTRS
-// transformed rejection (J. Stat. Comput. Simul. 46 (1993) 101) above.
-NB_D long long binomial(Stream& g, long long n, double p) {
+// transformed rejection (J. Stat. Comput. Simul. 46 (1993) 101) above.  Draws from its own
+// counter stream (seed; event, stream) so that it can live out of line.
+__device__ __noinline__ long long binomial(uint64_t seed, uint64_t event, uint32_t stream, long long n,
+                                           double p) {
   if (!(n > 0) || !(p > 0.)) return 0;
   if (p >= 1.) return n;
+  Stream g;
+  g.init(seed, event, stream);
   bool flip = p > 0.5;
   double pp = flip ? 1. - p : p;
   double q = 1. - pp;
