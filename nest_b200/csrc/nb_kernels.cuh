@@ -126,6 +126,7 @@ NB_D double drift_velocity_dev(const RunParams& P, double eField) {
   return speed;
 }
 
+#define NB_LOCKSTEP() __syncthreads()
 constexpr int kPreBlock = 256;
 constexpr int kPostBlock = 256;
 constexpr int kHitGroup = 1024;  // events per k_hits group
@@ -137,8 +138,14 @@ __global__ void __launch_bounds__(kPreBlock, 2)
   const nb200_detector& det = P.det;
   const Work& W = P.work;
   const bool cli = !P.vec_mode;
-  for (uint64_t idx = blockIdx.x * uint64_t(kPreBlock) + threadIdx.x; idx < P.n_events;
-       idx += uint64_t(gridDim.x) * kPreBlock) {
+  // The per-event code is long and straight-line: its cost is instruction fetch, not arithmetic.
+  // NB_LOCKSTEP() barriers keep the warps of a block inside the same few KB of code, so that one
+  // warp's instruction-cache fill serves the others (all threads reach every barrier: the loop
+  // bound is block-uniform and inactive lanes only skip the stores).
+  for (uint64_t base = blockIdx.x * uint64_t(kPreBlock); base < P.n_events;
+       base += uint64_t(gridDim.x) * kPreBlock) {
+    const bool active = base + threadIdx.x < P.n_events;
+    const uint64_t idx = active ? base + threadIdx.x : P.n_events - 1;
     const uint64_t gidx = P.chunk_off + idx;
     const uint64_t ev = P.first_event + gidx;
     Stream g;
@@ -148,6 +155,7 @@ __global__ void __launch_bounds__(kPreBlock, 2)
     Quanta q{0, 0, 0, 0, 0., 0.};
     int err = 0;
     double keV = sample_energy(g, P, gidx);
+    NB_LOCKSTEP();
     const nb200_source& S = P.src;
     const bool nonuni = (S.inField == -1.);
     const bool listed = (S.kind == NB200_SRC_LIST && S.x != nullptr);
@@ -190,6 +198,7 @@ __global__ void __launch_bounds__(kPreBlock, 2)
         pz = det.TopDrift - P.ana.z_step;
       }
     }
+    NB_LOCKSTEP();
     // yields + quanta: execNEST.cpp:1031-1077 / FullCalculation NEST.cpp:22-42
     const int sp = P.species;
     const bool nrlike = sp <= NB200_Cf || sp == NB200_atmNu;
@@ -205,8 +214,10 @@ __global__ void __launch_bounds__(kPreBlock, 2)
         y = yield_er_weighted(keV, P.rc.rho, field, det, P.model.ERYieldsParam);
       else
         y = get_yields(sp, keV, P.rc.rho, field, P.model.massNum, P.model.atomNum, A2, det, P.model, &err);
-      q = get_quanta(g, P.seed, ev, y, P.rc.rho, det, P.model, &err);
     }
+    NB_LOCKSTEP();
+    if (!cli || keV > 0.001 * P.rc.Wq_eV) q = get_quanta(g, P.seed, ev, y, P.rc.rho, det, P.model, &err);
+    NB_LOCKSTEP();
     if (cli && (det.noiseBaseline[2] != 0. || det.noiseBaseline[3] != 0.))
       q.electrons += to_int_round(gauss(g, det.noiseBaseline[2], det.noiseBaseline[3], false));
     // position smearing execNEST.cpp:1090-1099
@@ -216,7 +227,10 @@ __global__ void __launch_bounds__(kPreBlock, 2)
       double Nphd_S2 = fabs(P.rc.g2_params[3]) * q.electrons * exp(-dt / det.eLife_us);
       if (!P.ana.MCtruthPos && Nphd_S2 > NB_PHE_MIN) xy_resolution(g, det, px, py, Nphd_S2, sx, sy);
     }
+    NB_LOCKSTEP();
     S1Pre pre = s1_prelude(ev, P, q.photons, px, py, pz, sx, sy, pz, keV);
+    NB_LOCKSTEP();
+    if (!active) continue;
 
     W.keV[idx] = keV;
     W.px[idx] = px;
@@ -426,8 +440,10 @@ __global__ void __launch_bounds__(kPostBlock, 2)
     __syncthreads();
   }
   const bool cli = !P.vec_mode;
-  for (uint64_t idx = blockIdx.x * uint64_t(kPostBlock) + tid; idx < P.n_events;
-       idx += uint64_t(gridDim.x) * kPostBlock) {
+  for (uint64_t base = blockIdx.x * uint64_t(kPostBlock); base < P.n_events;
+       base += uint64_t(gridDim.x) * kPostBlock) {
+    const bool active = base + tid < P.n_events;
+    const uint64_t idx = active ? base + tid : P.n_events - 1;
     const uint64_t gidx = P.chunk_off + idx;
     const uint64_t ev = P.first_event + gidx;
     Stream g;
@@ -453,15 +469,22 @@ __global__ void __launch_bounds__(kPostBlock, 2)
     } else
       s1_parametric(g, ev, P, pre.nHits, acc);
     double scint[9], scint2[9];
+    NB_LOCKSTEP();
     s1_epilogue(g, P, pre, acc, scint);
     int Ne = W.electrons[idx];
     if (cli && pz < det.cathode) Ne = 0;  // execNEST.cpp:1107
+    NB_LOCKSTEP();
     get_s2(g, ev, P, Ne, px, py, pz, sx, sy, dt, field, scint2);
+    NB_LOCKSTEP();
     double signal1 = 0., signal2 = 0., signalE = 0.;
     const double keV_true = keV;
     if (cli) {
       select_signals(P.ana, scint, scint2, signal1, signal2);
       signalE = reconstruct_energy(P, y, scint, scint2, signal1, signal2, field, keV);
+    }
+    NB_LOCKSTEP();
+    if (!active) continue;
+    if (cli) {
       if (P.do_band) {
         bool acc_ok = false;
         double xv = 0., yv = 0.;
