@@ -314,6 +314,12 @@ int nb200_lar(nb200_ctx* ctx, int species, size_t n, const double* E, const doub
  * CUDA events (the roofline denominator of the chain kernel). */
 int nb200_fp64_peak(nb200_ctx* ctx, double* tflops);
 
+/* Test hook: the S1 hit loop builds -ln(u) and (sin, cos) straight from random bits with
+ * short polynomials instead of libm's generic log/sincospi.  bits3 = n triples {hi, lo, z}
+ * (u = (hi:lo)/2^64, angle = 2 pi (z+1/2)/2^32), out3 = n triples {-ln u, sin, cos}; host
+ * pointers.  Used by tests/test_gpu_hitmath.py to hold them to 1e-15 against libm. */
+int nb200_debug_hitmath(nb200_ctx* ctx, size_t n, const uint32_t* bits3, double* out3);
+
 /* counters for the bench: kernels launched by this context since creation */
 uint64_t nb200_launch_count(const nb200_ctx* ctx);
 

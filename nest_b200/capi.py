@@ -103,7 +103,8 @@ EXPORTS = [
     "nb200_synchronize", "nb200_detector_builtin", "nb200_model_default", "nb200_analysis_default",
     "nb200_prepare", "nb200_wimp_prep", "nb200_poisson", "nb200_yields", "nb200_run", "nb200_run_async",
     "nb200_band_reset", "nb200_band_attach", "nb200_fp64_peak", "nb200_band_fetch", "nb200_band_device_buffer", "nb200_allreduce_hist",
-    "nb200_band_hist_bytes", "nb200_band_finalize", "nb200_lar", "nb200_launch_count"]
+    "nb200_band_hist_bytes", "nb200_band_finalize", "nb200_lar", "nb200_launch_count",
+    "nb200_debug_hitmath"]
 
 _lib = None
 
@@ -162,6 +163,7 @@ def lib():
     L.nb200_band_finalize.argtypes = [C.POINTER(Analysis), C.POINTER(BandHist), c_dp]
     L.nb200_lar.argtypes = [vp, C.c_int, C.c_size_t, vp, vp, C.c_double, C.c_uint64, C.c_uint64, C.c_int,
                             vp, vp]
+    L.nb200_debug_hitmath.argtypes = [vp, C.c_size_t, vp, vp]
     L.nb200_launch_count.argtypes = [vp]
     L.nb200_launch_count.restype = C.c_uint64
     _lib = L
@@ -333,6 +335,12 @@ class Context:
         n = C.c_size_t()
         self._check(lib().nb200_band_device_buffer(self.h, C.byref(p), C.byref(n)))
         return p.value, n.value
+
+    def debug_hitmath(self, bits3):
+        b = np.ascontiguousarray(bits3, np.uint32).reshape(-1, 3)
+        out = np.empty((b.shape[0], 3))
+        self._check(lib().nb200_debug_hitmath(self.h, b.shape[0], _dptr(b), _dptr(out)))
+        return out
 
     def lar(self, species, E, field, density, seed=0, first_event=0, want_fluct=True):
         E = np.ascontiguousarray(E, np.float64)

@@ -177,6 +177,10 @@ int build_params(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo,
   P->s2_center = fit_s2(det->FitS2, 0., 0.);
   P->coin_u_min = exp(-det->coinWind / 20.);
   {
+    double t = ceil(det->P_dphe * 4294967296.0 - 0.5);  // (w + 1/2)/2^32 < P_dphe  <=>  w < t
+    P->dphe_thr = t <= 0. ? 0ull : (t >= 4294967296.0 ? 4294967296ull : (unsigned long long)t);
+  }
+  {
     const double sq2 = sqrt(2.);
     double a_spe = 0.5 * (1. + erf(-1. / det->sPEres / sq2));
     double x_spe = 0.5 * (1. + erf((det->sPEthr - 1.) / det->sPEres / sq2));
@@ -233,6 +237,7 @@ int build_params(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo,
     }
   }
   P->seed = seed;
+  philox_round_keys(seed, P->rk);
   P->first_event = first;
   P->n_events = n;
   P->species = src->species;
@@ -1001,6 +1006,26 @@ int nb200_fp64_peak(nb200_ctx* c, double* tflops) {
   cudaFree(d);
   NB_CUDA(c, cudaGetLastError());
   *tflops = 2.0 * 8.0 * double(iters) * 256.0 * double(blocks) / (double(best) * 1e-3) / 1e12;
+  return 0;
+}
+
+// test hook (tests/test_gpu_hitmath.py): {-ln u, sin, cos} of the hit loop's bit-built math
+int nb200_debug_hitmath(nb200_ctx* c, size_t n, const uint32_t* bits3, double* out3) {
+  if (!c || !bits3 || !out3) return NB200_EINVAL;
+  if (n == 0) return 0;
+  NB_CUDA(c, cudaSetDevice(c->device));
+  uint32_t* db = nullptr;
+  double* dout = nullptr;
+  NB_CUDA(c, cudaMalloc(&db, n * 12));
+  NB_CUDA(c, cudaMalloc(&dout, n * 24));
+  cudaMemcpyAsync(db, bits3, n * 12, cudaMemcpyHostToDevice, c->stream);
+  k_hitmath<<<unsigned(std::min<size_t>((n + 255) / 256, 4096)), 256, 0, c->stream>>>(n, db, dout);
+  ++c->launches;
+  cudaMemcpyAsync(out3, dout, n * 24, cudaMemcpyDeviceToHost, c->stream);
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  cudaFree(db);
+  cudaFree(dout);
+  if (e != cudaSuccess) return fail(c, NB200_ECUDA, cudaGetErrorString(e));
   return 0;
 }
 

@@ -289,44 +289,44 @@ NB_D double s1_ztg_redraw(uint64_t seed, uint64_t event, uint32_t blk, double me
 // First photo-electron of hit k: returns phe1 (zeroed when the single-phe efficiency draw loses
 // it, :1381-1386) and whether the photon makes a second one (:1390).
 NB_D double s1_hit_first(const RunParams& P, uint32_t k0, uint32_t k1, uint32_t e0, uint32_t e1,
-                         uint32_t k, double eff, double spe_mean, bool& dphe) {
+                         uint32_t k, double eff, double spe_mean, const double* lntab, bool& dphe) {
   const nb200_detector& det = P.det;
-  // block 1: radius (53 bits), angle (32 bits), double-phe decision (32 bits)
-  u128 r = philox4x32_10(e0, e1, k, STREAM_HIT, k0, k1);
-  double rad = sqrt(-2.0 * log(u53(r.x, r.y)));
+  // block 1: radius (64 bits), angle (32 bits), double-phe decision (32 bits)
+  u128 r = philox4x32_10_rk(e0, e1, k, STREAM_HIT, P.rk);
+  double rad = sqrt(2.0 * neg_log_bits(r.x, r.y, lntab));
   double s, c;
-  sincospi(2.0 * u32d(r.z), &s, &c);
+  sincos_bits(r.z, s, c);
   double tg = fma(det.sPEres, rad * c, spe_mean);
   if (tg <= 0.)  // redraw the truncated Gaussian (P ~ 0.4 % at sPEres 0.37)
     tg = s1_ztg_redraw((uint64_t(k1) << 32) | k0, (uint64_t(e1) << 32) | e0, k * 64u, spe_mean, det.sPEres);
   double phe1 = tg + fma(det.noiseBaseline[1], rad * s, det.noiseBaseline[0]);
-  dphe = u32d(r.w) < det.P_dphe;
+  dphe = (unsigned long long)r.w < P.dphe_thr;  // (w + 1/2) 2^-32 < P_dphe
   if (eff < 1.) {  // block 3: the single-phe efficiency decisions (:1381-1386, :1403)
-    u128 t = philox4x32_10(e0, e1, k, STREAM_HIT3, k0, k1);
+    u128 t = philox4x32_10_rk(e0, e1, k, STREAM_HIT3, P.rk);
     if (u32d(t.x) > eff) phe1 = 0.;
   }
   return phe1;
 }
 // coincidence-window draw of hit k (block 2, word w): only events with nHits <= coinLevel need it
-NB_D double s1_hit_ucoin(uint32_t k0, uint32_t k1, uint32_t e0, uint32_t e1, uint32_t k) {
-  u128 q = philox4x32_10(e0, e1, k, STREAM_HIT2, k0, k1);
+NB_D double s1_hit_ucoin(const RunParams& P, uint32_t e0, uint32_t e1, uint32_t k) {
+  u128 q = philox4x32_10_rk(e0, e1, k, STREAM_HIT2, P.rk);
   return u32d(q.w);
 }
 // Second photo-electron of a double-phe hit (:1390-1409): returns phe2 and the coincidence draw
 NB_D double s1_hit_second(const RunParams& P, uint32_t k0, uint32_t k1, uint32_t e0, uint32_t e1,
-                          uint32_t k, double eff, double spe_mean, double& ucoin) {
+                          uint32_t k, double eff, double spe_mean, const double* lntab, double& ucoin) {
   const nb200_detector& det = P.det;
-  u128 q = philox4x32_10(e0, e1, k, STREAM_HIT2, k0, k1);
+  u128 q = philox4x32_10_rk(e0, e1, k, STREAM_HIT2, P.rk);
   ucoin = u32d(q.w);
-  double rad2 = sqrt(-2.0 * log(u53(q.x, q.y)));
+  double rad2 = sqrt(2.0 * neg_log_bits(q.x, q.y, lntab));
   double s2, c2;
-  sincospi(2.0 * u32d(q.z), &s2, &c2);
+  sincos_bits(q.z, s2, c2);
   double tg2 = fma(det.sPEres, rad2 * c2, spe_mean);
   if (tg2 <= 0.)
     tg2 = s1_ztg_redraw((uint64_t(k1) << 32) | k0, (uint64_t(e1) << 32) | e0, k * 64u + 32u, spe_mean, det.sPEres);
   double phe2 = tg2 + fma(det.noiseBaseline[1], rad2 * s2, det.noiseBaseline[0]);
   if (eff < 1.) {
-    u128 t = philox4x32_10(e0, e1, k, STREAM_HIT3, k0, k1);
+    u128 t = philox4x32_10_rk(e0, e1, k, STREAM_HIT3, P.rk);
     if (u32d(t.y) > eff && u32d(t.x) > eff) phe2 = 0.;
   }
   return phe2;

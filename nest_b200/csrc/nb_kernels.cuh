@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(kPreBlock, 2)
 // threshold / coincidence test (NEST.cpp:1421-1427) and add to the owning event's accumulators
 NB_D void hit_finish_dphe(const RunParams& P, const int* s_pref, unsigned long long* s_area,
                           unsigned int* s_spike, uint64_t ev0, int slot, uint32_t k, double phe1,
-                          double spe_mean) {
+                          double spe_mean, const double* lntab) {
   const nb200_detector& det = P.det;
   const int ne = s_pref[slot + 1] - s_pref[slot];
   const double eff = s1_eff(det, ne);
@@ -266,7 +266,7 @@ NB_D void hit_finish_dphe(const RunParams& P, const int* s_pref, unsigned long l
   const uint64_t ev = ev0 + slot;
   double ucoin;
   double phe2 = s1_hit_second(P, uint32_t(P.seed), uint32_t(P.seed >> 32), uint32_t(ev), uint32_t(ev >> 32), k,
-                              eff, spe_mean, ucoin);
+                              eff, spe_mean, lntab, ucoin);
   double a = phe1 + phe2;
   if (a > det.sPEthr && (!need_coin || ucoin > P.coin_u_min)) {
     atomicAdd(&s_area[slot], (unsigned long long)__double2ll_rn(a * NB_AREA_FX));
@@ -285,6 +285,8 @@ __global__ void __launch_bounds__(kHitBlock, 4)
   __shared__ double s_qphe[kHitBlock / 32][64];
   __shared__ uint32_t s_qk[kHitBlock / 32][64];
   __shared__ uint16_t s_qslot[kHitBlock / 32][64];
+  __shared__ __align__(16) double s_lntab[64];
+  if (threadIdx.x < 64) s_lntab[threadIdx.x] = c_lntab[threadIdx.x];
   constexpr int PER = kHitGroup / kHitBlock;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const nb200_detector& det = P.det;
@@ -372,12 +374,12 @@ __global__ void __launch_bounds__(kHitBlock, 4)
           need_coin = !(ne > det.coinLevel);
           hev = ev0 + e;
         }
-        phe1 = s1_hit_first(P, k0, k1, uint32_t(hev), uint32_t(hev >> 32), uint32_t(k), eff, spe_mean, dphe);
+        phe1 = s1_hit_first(P, k0, k1, uint32_t(hev), uint32_t(hev >> 32), uint32_t(k), eff, spe_mean, s_lntab, dphe);
         a_nphe += dphe ? 2u : 1u;
         if (!dphe) {
           bool pass = phe1 > det.sPEthr;
           if (pass && need_coin)
-            pass = s1_hit_ucoin(k0, k1, uint32_t(hev), uint32_t(hev >> 32), uint32_t(k)) > P.coin_u_min;
+            pass = s1_hit_ucoin(P, uint32_t(hev), uint32_t(hev >> 32), uint32_t(k)) > P.coin_u_min;
           if (pass) {
             a_spike += 1u;
             a_fx += (unsigned long long)__double2ll_rn(phe1 * NB_AREA_FX);
@@ -396,7 +398,7 @@ __global__ void __launch_bounds__(kHitBlock, 4)
         __syncwarp();
         if (qcount >= 32) {
           const int j = qcount - 32 + lane;
-          hit_finish_dphe(P, s_pref, s_area, s_spike, ev0, int(qslot[j]), qk[j], qphe[j], spe_mean);
+          hit_finish_dphe(P, s_pref, s_area, s_spike, ev0, int(qslot[j]), qk[j], qphe[j], spe_mean, s_lntab);
           qcount -= 32;
           __syncwarp();
         }
@@ -404,7 +406,7 @@ __global__ void __launch_bounds__(kHitBlock, 4)
       ++k;
     }
     if (lane < qcount)
-      hit_finish_dphe(P, s_pref, s_area, s_spike, ev0, int(qslot[lane]), qk[lane], qphe[lane], spe_mean);
+      hit_finish_dphe(P, s_pref, s_area, s_spike, ev0, int(qslot[lane]), qk[lane], qphe[lane], spe_mean, s_lntab);
     if (len > 0) {
       atomicAdd(&s_area[e], a_fx);
       atomicAdd(&s_spike[e], a_spike);
@@ -547,6 +549,20 @@ __global__ void __launch_bounds__(kPostBlock, 2)
       unsigned int v = s_h2[i];
       if (v) atomicAdd(&P.band[size_t(nb) * BAND_WORDS + i], (unsigned long long)v);
     }
+  }
+}
+
+// test hook: the hit loop's specialised math on caller-supplied bits; out = {-ln u, sin, cos}
+__global__ void k_hitmath(size_t n, const uint32_t* __restrict__ bits, double* __restrict__ out) {
+  __shared__ __align__(16) double s_lntab[64];
+  if (threadIdx.x < 64) s_lntab[threadIdx.x] = c_lntab[threadIdx.x];
+  __syncthreads();
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+    double s, c;
+    sincos_bits(bits[3 * i + 2], s, c);
+    out[3 * i] = neg_log_bits(bits[3 * i], bits[3 * i + 1], s_lntab);
+    out[3 * i + 1] = s;
+    out[3 * i + 2] = c;
   }
 }
 

@@ -40,6 +40,7 @@ struct RunParams {
   // hoisted per-run constants
   double s1_center;      // FitS1(0,0,TopDrift - vD_middle*dtCntr)   NEST.cpp:1317-1321
   double s2_center;      // FitS2(0,0)                               NEST.cpp:1762-1763
+  unsigned long long dphe_thr;  // double-phe decision on a 32-bit word w: w < dphe_thr
   double coin_u_min;     // exp(-coinWind/20): -20 ln u < coinWind <=> u > this  NEST.cpp:1422
   double below_thr_pct;  // Parametric S1 threshold percentile       NEST.cpp:1437-1457
   double recon_mult;     // MultFact prefactor, execNEST.cpp:1179-1182
@@ -54,6 +55,7 @@ struct RunParams {
   const double* vtable;
 
   uint64_t seed, first_event, n_events;
+  uint32_t rk[20];     // Philox round keys of `seed` (nb_rng.cuh: philox_round_keys)
   uint64_t chunk_off;  // index of this chunk's first event within the call (lists, SoA columns)
   int32_t species;
   int32_t vec_mode;   // 1 = runNESTvec semantics (execNEST.cpp:357-406)

@@ -76,6 +76,34 @@ __device__ __noinline__ u128 philox_block(uint32_t c0, uint32_t c1, uint32_t c2,
 }
 #endif
 
+// Same function with the 10 round keys taken from a precomputed table (rk[2r], rk[2r+1]); in the
+// hit loop the table sits in the kernel's constant bank, so each round is two IMAD.WIDE and two
+// three-input LOP3 with a constant operand -- no key-schedule adds.
+NB_HD void philox_round_keys(uint64_t seed, uint32_t* rk) {
+  uint32_t k0 = uint32_t(seed), k1 = uint32_t(seed >> 32);
+  for (int r = 0; r < 10; ++r) {
+    rk[2 * r] = k0;
+    rk[2 * r + 1] = k1;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+NB_HD u128 philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const uint32_t* rk) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0, lo0, hi1, lo1;
+    mulhilo(0xD2511F53u, c0, hi0, lo0);
+    mulhilo(0xCD9E8D57u, c2, hi1, lo1);
+    uint32_t n0 = hi1 ^ c1 ^ rk[2 * r];
+    uint32_t n2 = hi0 ^ c3 ^ rk[2 * r + 1];
+    c0 = n0;
+    c1 = lo1;
+    c2 = n2;
+    c3 = lo0;
+  }
+  return u128{c0, c1, c2, c3};
+}
+
 // 53-bit uniform on the OPEN interval (0,1).  The reference's rand_uniform is
 // u64/(2^64-1) on the closed interval (RandomGen.cpp:39-42); the end points have
 // probability 2^-64 each and only matter as log(0) hazards, which the open interval removes.
@@ -129,6 +157,93 @@ struct Stream {
 };
 
 #ifdef __CUDACC__
+// ---- specialised FP64 math for the S1 hit loop -------------------------------------------
+// The hit loop spends its time in -ln(u), sqrt and sincos of RANDOM BITS.  libm's log and
+// sincospi pay for generic arguments (frexp, special values, large-argument reduction); here
+// the argument is built from the bits, so the reduction is free and the remaining polynomials
+// are short.  Both are accurate to ~1e-16 (tests/test_gpu_hitmath.py compares with libm).
+
+// {1/c_j, ln c_j} for c_j = 1 + (j + 1/2)/32, j = 0..31
+static __constant__ double c_lntab[64] = {
+    0.98461538461538461538, 0.015504186535965254151, 0.95522388059701492537, 0.045809536031294203167,
+    0.92753623188405797101, 0.075223421237587525699, 0.90140845070422535211, 0.10379679368164356483,
+    0.87671232876712328767, 0.13157635778871927259,  0.85333333333333333333, 0.15860503017663858409,
+    0.83116883116883116883, 0.18492233849401199266,  0.81012658227848101266, 0.21056476910734963767,
+    0.79012345679012345679, 0.23556607131276690908,  0.77108433734939759036, 0.25995752443692606697,
+    0.75294117647058823529, 0.28376817313064459835,  0.73563218390804597701, 0.30702503529491186208,
+    0.71910112359550561798, 0.32975328637246798181,  0.7032967032967032967,  0.35197642315717818466,
+    0.68817204301075268817, 0.37371640979358408082,  0.67368421052631578947, 0.39499380824086897811,
+    0.65979381443298969072, 0.41582789514371096561,  0.64646464646464646465, 0.43623676677491807035,
+    0.63366336633663366337, 0.45623743348158759438,  0.62135922330097087379, 0.47584590486996391427,
+    0.60952380952380952381, 0.4950772667978515146,   0.5981308411214953271,  0.5139457511022343168,
+    0.58715596330275229358, 0.53246479886947184387,  0.57657657657657657658, 0.55064711795266227926,
+    0.56637168141592920354, 0.56850473535266871208,  0.55652173913043478261, 0.5860490450035782089,
+    0.54700854700854700855, 0.60329085143808426234,  0.53781512605042016807, 0.62024040975185752885,
+    0.5289256198347107438,  0.63690746223706923162,  0.52032520325203252033, 0.65330127201274563876,
+    0.512,                  0.6694306539426292673,   0.50393700787401574803, 0.68530400309891941654};
+
+// -ln(u) for u = x / 2^64 built from 64 random bits (x = 0 is mapped to x = 1).  With e leading
+// zeros, u = m 2^-(e+1), m in [1,2) from the next 53 bits; ln m = ln c_j + ln(1 + d) with c_j the
+// centre of m's 1/32-wide cell and d = m/c_j - 1, |d| <= 2^-6 (Taylor through d^9: 9e-20).
+// tab: c_lntab staged in shared memory by the caller.
+NB_D double neg_log_bits(uint32_t hi, uint32_t lo, const double* tab) {
+  unsigned long long x = ((unsigned long long)hi << 32) | lo;
+  x |= 1ull;
+  const int e = __clzll((long long)x);
+  const unsigned long long y = x << e;
+  const double m = __longlong_as_double((long long)(0x3FF0000000000000ull | ((y << 1) >> 12)));
+  const int j = int((y >> 58) & 31ull);
+  const double2 t = *reinterpret_cast<const double2*>(tab + 2 * j);
+  const double d = fma(m, t.x, -1.0);
+  double q = 1.0 / 9.0;
+  q = fma(q, d, -1.0 / 8.0);
+  q = fma(q, d, 1.0 / 7.0);
+  q = fma(q, d, -1.0 / 6.0);
+  q = fma(q, d, 1.0 / 5.0);
+  q = fma(q, d, -1.0 / 4.0);
+  q = fma(q, d, 1.0 / 3.0);
+  q = fma(q, d, -0.5);
+  const double ln1pd = fma(d * d, q, d);
+  return fma(double(e + 1), 0.69314718055994530942, -t.y) - ln1pd;
+}
+
+// (sin, cos) of the angle 2 pi (z + 1/2) / 2^32: quadrant from the top two bits, the remaining
+// 30 bits folded onto [0, pi/4] (Taylor through x^15 / x^16: 5e-17).
+NB_D void sincos_bits(uint32_t z, double& s, double& c) {
+  const uint32_t quad = z >> 30;
+  double f = double(z & 0x3FFFFFFFu) + 0.5;  // in (0, 2^30)
+  const bool fold = f > 536870912.0;          // beyond pi/4: use the complementary angle
+  if (fold) f = 1073741824.0 - f;
+  const double x = f * 1.4629180792671596e-9;  // (pi/2) / 2^30
+  const double x2 = x * x;
+  double ps = -1.0 / 1307674368000.0;
+  ps = fma(ps, x2, 1.0 / 6227020800.0);
+  ps = fma(ps, x2, -1.0 / 39916800.0);
+  ps = fma(ps, x2, 1.0 / 362880.0);
+  ps = fma(ps, x2, -1.0 / 5040.0);
+  ps = fma(ps, x2, 1.0 / 120.0);
+  ps = fma(ps, x2, -1.0 / 6.0);
+  double sn = fma(x * x2, ps, x);
+  double pc = 1.0 / 20922789888000.0;
+  pc = fma(pc, x2, -1.0 / 87178291200.0);
+  pc = fma(pc, x2, 1.0 / 479001600.0);
+  pc = fma(pc, x2, -1.0 / 3628800.0);
+  pc = fma(pc, x2, 1.0 / 40320.0);
+  pc = fma(pc, x2, -1.0 / 720.0);
+  pc = fma(pc, x2, 1.0 / 24.0);
+  pc = fma(pc, x2, -0.5);
+  double cs = fma(x2, pc, 1.0);
+  if (fold) {
+    const double t = sn;
+    sn = cs;
+    cs = t;
+  }
+  // rotate by quadrant * pi/2
+  const double a = (quad & 1u) ? sn : cs, b = (quad & 1u) ? cs : sn;
+  c = (quad == 1u || quad == 2u) ? -a : a;
+  s = (quad >= 2u) ? -b : b;
+}
+
 // ---- samplers (device) -------------------------------------------------------------
 
 // two independent standard normals from one Box-Muller transform.  The reference's
