@@ -332,8 +332,9 @@ static __constant__ double c_stirling[10] = {
     0.009255462182712733, 0.008330563433362871};
 NB_D double stirling_tail(double k) {
   if (k < 10.) return c_stirling[int(k)];
-  double kp1sq = (k + 1.) * (k + 1.);
-  return (1.0 / 12. - (1.0 / 360. - 1.0 / 1260. / kp1sq) / kp1sq) / (k + 1.);
+  const double rk = 1.0 / (k + 1.);
+  const double rk2 = rk * rk;
+  return (1.0 / 12. - (1.0 / 360. - (1.0 / 1260.) * rk2) * rk2) * rk;
 }
 
 // binom_draw RandomGen.cpp:132-134 = std::binomial_distribution<int64_t>(n,p).  Exact
@@ -382,26 +383,24 @@ __device__ __noinline__ long long binomial(uint64_t seed, uint64_t event, uint32
     double r = pp / q;
     double alpha = (2.83 + 5.1 / b) * spq;
     double m = floor((dn + 1.) * pp);
+    // terms of the acceptance bound that do not depend on the candidate (computed once, by all lanes)
+    const double nm1 = dn - m + 1.;
+    const double hm = (m + 0.5) * log((m + 1.) / (r * nm1)) + stirling_tail(m) + stirling_tail(dn - m);
+    double kk;
     for (;;) {
       double u = g.uniform() - 0.5;
       double v = g.uniform();
       double us = 0.5 - fabs(u);
-      double kk = floor((2. * a / us + b) * u + c);
-      if (us >= 0.07 && v <= vr) {
-        k = (long long)kk;
-        break;
-      }
+      kk = floor((2. * a / us + b) * u + c);
+      if (us >= 0.07 && v <= vr) break;
       if (kk < 0. || kk > dn) continue;
+      const double nk1 = dn - kk + 1.;
       v = log(v * alpha / (a / (us * us) + b));
-      double ub = (m + 0.5) * log((m + 1.) / (r * (dn - m + 1.))) +
-                  (dn + 1.) * log((dn - m + 1.) / (dn - kk + 1.)) +
-                  (kk + 0.5) * log(r * (dn - kk + 1.) / (kk + 1.)) + stirling_tail(m) +
-                  stirling_tail(dn - m) - stirling_tail(kk) - stirling_tail(dn - kk);
-      if (v <= ub) {
-        k = (long long)kk;
-        break;
-      }
+      double ub = hm + (dn + 1.) * log(nm1 / nk1) + (kk + 0.5) * log(r * nk1 / (kk + 1.)) -
+                  stirling_tail(kk) - stirling_tail(dn - kk);
+      if (v <= ub) break;
     }
+    k = (long long)kk;
   }
   return flip ? n - k : k;
 }
