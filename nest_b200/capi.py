@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libnest_b200.so")
+LIB_PATH = os.environ.get("NB200_LIB", os.path.join(HERE, "csrc", "libnest_b200.so"))
 
 # error codes
 OK, EINVAL, ENODEV, ECUDA, EPHYSICS, ENOMEM = 0, -1, -2, -3, -4, -5

@@ -127,13 +127,31 @@ NB_D double drift_velocity_dev(const RunParams& P, double eField) {
 }
 
 #define NB_LOCKSTEP() __syncthreads()
-constexpr int kPreBlock = 256;
-constexpr int kPostBlock = 256;
+// launch geometry, measured on B200 (tools/sweep_variants.sh): k_post is fastest as ONE 512-thread
+// block per SM (16 warps in lockstep share instruction-cache fills; 128-thread blocks are 35 %
+// slower), k_pre as two 256-thread blocks, k_hits at 64 registers (4 blocks of 256 per SM)
+#ifndef NB_PRE_BLOCK
+#define NB_PRE_BLOCK 256
+#endif
+#ifndef NB_PRE_MINB
+#define NB_PRE_MINB 2
+#endif
+#ifndef NB_POST_BLOCK
+#define NB_POST_BLOCK 512
+#endif
+#ifndef NB_POST_MINB
+#define NB_POST_MINB 1
+#endif
+#ifndef NB_HIT_MINB
+#define NB_HIT_MINB 4
+#endif
+constexpr int kPreBlock = NB_PRE_BLOCK;
+constexpr int kPostBlock = NB_POST_BLOCK;
 constexpr int kHitGroup = 1024;  // events per k_hits group
 constexpr int kHitBlock = 256;   // threads per k_hits block
 #define NB_AREA_FX 4294967296.0  // 2^32: S1 hit areas are summed in units of 2^-32 phe
 
-__global__ void __launch_bounds__(kPreBlock, 2)
+__global__ void __launch_bounds__(kPreBlock, NB_PRE_MINB)
     k_pre(const __grid_constant__ RunParams P, int* __restrict__ err_flag) {
   const nb200_detector& det = P.det;
   const Work& W = P.work;
@@ -274,7 +292,7 @@ NB_D void hit_finish_dphe(const RunParams& P, const int* s_pref, unsigned long l
   }
 }
 
-__global__ void __launch_bounds__(kHitBlock, 4)
+__global__ void __launch_bounds__(kHitBlock, NB_HIT_MINB)
     k_hits(const __grid_constant__ RunParams P) {
   __shared__ int s_pref[kHitGroup + 1];
   __shared__ unsigned long long s_area[kHitGroup];
@@ -427,7 +445,7 @@ __global__ void __launch_bounds__(kHitBlock, 4)
   }
 }
 
-__global__ void __launch_bounds__(kPostBlock, 2)
+__global__ void __launch_bounds__(kPostBlock, NB_POST_MINB)
     k_post(const __grid_constant__ RunParams P, int* __restrict__ err_flag) {
   extern __shared__ __align__(16) unsigned long long s_band[];  // [numBins*6] then u32 hist2d
   const int tid = threadIdx.x;

@@ -71,6 +71,24 @@ NB_HD Yields validity(Yields r, double energy, double Wq_eV) {
 NB_HD int imin_(int a, int b) { return a < b ? a : b; }
 NB_HD int imax_(int a, int b) { return a > b ? a : b; }
 
+// integer powers: on the host exactly the reference's pow(x, n.) calls (the per-run constants are
+// bit-identical to the reference's), on the device plain products (<= 1 ulp apart)
+#ifdef __CUDA_ARCH__
+#define NB_POW2(x) ((x) * (x))
+#define NB_POW3(x) ((x) * (x) * (x))
+#define NB_POW4(x) (((x) * (x)) * ((x) * (x)))
+#define NB_POW5(x) (((x) * (x)) * ((x) * (x)) * (x))
+#define NB_POW6(x) (((x) * (x) * (x)) * ((x) * (x) * (x)))
+#define NB_POW7(x) ((((x) * (x)) * ((x) * (x))) * ((x) * (x) * (x)))
+#else
+#define NB_POW2(x) pow((x), 2.)
+#define NB_POW3(x) pow((x), 3.)
+#define NB_POW4(x) pow((x), 4.)
+#define NB_POW5(x) pow((x), 5.)
+#define NB_POW6(x) pow((x), 6.)
+#define NB_POW7(x) pow((x), 7.)
+#endif
+
 // ---- position maps: VDetector::FitS1/FitS2/FitEF/FitTBA (VDetector.hh:131-148) -------
 NB_HD double map_lut_rz(const nb200_map& m, double r, double z) {
   double fr = (m.n0 > 1) ? (r - m.c[0]) / (m.c[1] - m.c[0]) * double(m.n0 - 1) : 0.;
@@ -90,11 +108,11 @@ NB_HD double map_lut_rz(const nb200_map& m, double r, double z) {
 // FitS1: LUX_Run03.hh:90-105.  c = {307.9, 0.3071, 0.0002257, 1.1525e-7, 318.84, 307.9, radmax}
 NB_HD double fit_s1(const nb200_map& m, double x, double y, double z) {
   if (m.kind == NB200_MAP_CONST) return m.c[0];
-  double radius = sqrt(x * x + y * y);
+  double radius = sqrt(NB_POW2(x) + NB_POW2(y));
   if (m.kind == NB200_MAP_LUX_RUN03) {
-    double amplitude = m.c[0] - m.c[1] * z + m.c[2] * (z * z);
+    double amplitude = m.c[0] - m.c[1] * z + m.c[2] * NB_POW2(z);
     double shape = m.c[3] * sqrt(fabs(z - m.c[4]));
-    double corr = -shape * (radius * radius * radius) + amplitude;
+    double corr = -shape * NB_POW3(radius) + amplitude;
     corr /= m.c[5];
     if ((corr < 0.5 || corr > 1.5 || (corr != corr)) && radius < m.c[6]) return 1.;
     return corr;
@@ -104,11 +122,10 @@ NB_HD double fit_s1(const nb200_map& m, double x, double y, double z) {
 // FitS2: LUX_Run03.hh:129-146.  c[0..7] polynomial in r, c[8] normalisation, c[9] radmax
 NB_HD double fit_s2(const nb200_map& m, double x, double y) {
   if (m.kind == NB200_MAP_CONST) return m.c[0];
-  double r = sqrt(x * x + y * y);
+  double r = sqrt(NB_POW2(x) + NB_POW2(y));
   if (m.kind == NB200_MAP_LUX_RUN03) {
-    double r2 = r * r, r3 = r2 * r, r4 = r2 * r2;
-    double corr = m.c[0] + m.c[1] * r + m.c[2] * r2 - m.c[3] * r3 + m.c[4] * r4 -
-                  m.c[5] * (r4 * r) + m.c[6] * (r3 * r3) - m.c[7] * (r4 * r3);
+    double corr = m.c[0] + m.c[1] * r + m.c[2] * NB_POW2(r) - m.c[3] * NB_POW3(r) + m.c[4] * NB_POW4(r) -
+                  m.c[5] * NB_POW5(r) + m.c[6] * NB_POW6(r) - m.c[7] * NB_POW7(r);
     corr /= m.c[8];
     if ((corr < 0.5 || corr > 1.5 || (corr != corr)) && r < m.c[9]) return 1.;
     return corr;
@@ -119,9 +136,8 @@ NB_HD double fit_s2(const nb200_map& m, double x, double y) {
 NB_HD double fit_ef(const nb200_map& m, double x, double y, double z) {
   if (m.kind == NB200_MAP_CONST) return m.c[0];
   if (m.kind == NB200_MAP_LUX_RUN03) {
-    double z2 = z * z;
-    double ef = m.c[0] - m.c[1] * z + m.c[2] * z2 - m.c[3] * (z2 * z) + m.c[4] * (z2 * z2) -
-                m.c[5] * (z2 * z2 * z);
+    double ef = m.c[0] - m.c[1] * z + m.c[2] * NB_POW2(z) - m.c[3] * NB_POW3(z) + m.c[4] * NB_POW4(z) -
+                m.c[5] * NB_POW5(z);
     if (ef <= NB_FIELD_MIN || ef > 1e5 || (ef != ef)) return NB_FIELD_MIN;
     return ef;
   }

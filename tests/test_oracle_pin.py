@@ -1,0 +1,139 @@
+"""The oracle is pinned before it is trusted: the CPU restatement (oracle/liboracle.so) must
+reproduce the UNMODIFIED reference bit for bit -- against the committed golden fixtures
+(tests/golden/reference_lux_run03.npz, outputs of the compiled reference) everywhere, and against
+the reference library / binary themselves wherever oracle/_ref has been built."""
+import ast
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import refprobe
+from helpers import RHO_LUX, ref_chain
+from nest_b200 import capi
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_lux_run03.npz")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLD)
+
+
+def test_yields_bitwise(orc, gold):
+    mo = capi.model(1)
+    nr, er = list(mo.NRYieldsParam), list(mo.ERYieldsParam)
+    E, F = gold["y_E"], gold["y_F"]
+    for name, which, sp, mult in [("NR", 0, capi.NR, 1.0), ("beta", 0, capi.beta, 1.0), ("betaGR09", 1, capi.beta, 0.9),
+                                  ("gamma", 0, capi.gammaRay, 1.0), ("gamma13", 2, capi.beta, 1.3),
+                                  ("weighted", 3, capi.beta, 1.0)]:
+        got = orc.yields(which, sp, E, F, RHO_LUX, 131.293, 54.0, nr, er, mult)
+        assert np.array_equal(got, gold["y_" + name]), name
+    got = orc.yields(0, capi.ion, gold["y_alpha_E"], 180.0, RHO_LUX, 4.0, 2.0, nr, er)
+    assert np.array_equal(got, gold["y_alpha"])
+
+
+def test_run_constants_and_maps_bitwise(orc, gold):
+    import ctypes as C
+    det = capi.detector("LUX_Run03")
+    rc = capi.RunConsts()
+    assert orc.L.orc_prepare(C.byref(det), C.c_double(180.0), C.byref(rc)) == 0
+    c = gold["consts_180"]
+    got = [rc.rho, rc.Wq_eV, rc.alpha, rc.vD] + list(rc.g2_params) + [rc.NewMean]
+    assert got == list(c)
+    x, y, z = gold["maps_xyz"]
+    assert np.array_equal(np.stack(orc.maps(x, y, z)), gold["maps"])
+
+
+def test_chain_bitwise(orc, gold):
+    cases = ast.literal_eval(str(gold["chain_cases"]))
+    for name, (seed, n, sp, kind, e0, e1, fld, fp, xyz, erm) in cases.items():
+        got = ref_chain(orc, seed, n, sp, kind, e0, e1, fld, fp, xyz, erm)
+        assert np.array_equal(got, gold[name]), name
+
+
+def test_band_samplers_spectra_lar_vec_bitwise(orc, gold):
+    ana = capi.analysis(0)
+    s1, s2 = gold["band_sig"]
+    assert np.array_equal(orc.getband(s1, s2, ana=ana), gold["band"], equal_nan=True)
+    for key in gold.files:
+        if key.startswith("sampler_"):
+            _, kind, p0, p1 = key.split("_")
+            p2 = {1: 1.0, 3: 2.25, 5: 1000.0}.get(int(kind), 0.0)
+            assert np.array_equal(orc.sampler(int(kind), 5, 400, float(p0), float(p1), p2), gold[key]), key
+    for k, nme in [(capi.SRC_CH3T, "CH3T"), (capi.SRC_DD, "DD"), (capi.SRC_B8, "B8")]:
+        assert np.array_equal(orc.spectrum(k, 9, 400, 0.0, 80.0), gold["spectrum_" + nme])
+    for sp in (0, 1, 2):
+        for fld in (1.0, 500.0, 1000.0):
+            y, f = orc.lar(4, sp, gold["lar_E"], fld, 1.393)
+            assert np.array_equal(y, gold["lar_y_%d_%g" % (sp, fld)])
+            assert np.array_equal(f, gold["lar_f_%d_%g" % (sp, fld)])
+    m0 = capi.model(0)
+    args = (list(m0.ERYieldsParam), list(m0.NRYieldsParam), list(m0.NRERWidthsParam)[:13])
+    assert np.array_equal(orc.runvec(capi.beta, gold["vec_E"], gold["vec_xyz"], 180.0, 3, *args), gold["vec_beta_180"])
+    assert np.array_equal(orc.runvec(capi.NR, gold["vec_E"], gold["vec_xyz"], -1.0, 3, *args), gold["vec_NR_fitEF"])
+
+
+def test_survey_pinned_values(orc):
+    """values captured from the compiled reference in SURVEY.md 8(c)"""
+    mo = capi.model(1)
+    nr, er = list(mo.NRYieldsParam), list(mo.ERYieldsParam)
+    b = orc.yields(1, capi.beta, [5.0, 0.5, 20.0, 100.0], [180.0, 180.0, 50.0, 1000.0], RHO_LUX, 131.293, 54., nr, er)
+    assert list(b[0][:3]) == [205.88604645954106, 165.20770456738973, 0.050298182684348262]
+    assert list(b[3][:3]) == [2806.3962674277627, 4615.4787531108532, 0.18202453502051572]
+    n = orc.yields(0, capi.NR, [1.0, 10.0], [180.0, 180.0], RHO_LUX, 131.293, 54., nr, er)
+    assert list(n[0][:4]) == [3.8175326853690859, 6.8511840288214803, 0.50923264205705066, 0.14374691954077559]
+    g = orc.yields(0, capi.gammaRay, [41.5], [180.0], RHO_LUX, 131.293, 54., nr, er)
+    assert list(g[0][:3]) == [2255.6704922630879, 824.40764126043757, 0.18141640390708169]
+    y, _ = orc.lar(1, 0, [10.0], 500.0, 1.393)
+    assert (y[0][3], y[0][4]) == (86.11970082647197, 49.498412045124624)
+
+
+# ---- live reference (this container; oracle/_ref travels to the GPU box as prebuilt files) ------
+
+def test_oracle_equals_live_reference(orc, ref):
+    rng = np.random.default_rng(0)
+    for seed in (17, 18):
+        for sp, kind, e0, e1, erm in [(capi.beta, capi.SRC_FLAT, 0.1, 20.0, 0), (capi.NR, capi.SRC_FLAT, 0.0, 100.0, -1),
+                                      (capi.beta, capi.SRC_GAUSS, 10.0, 2.0, 1), (capi.beta, capi.SRC_FLAT, 0.5, 60.0, 2)]:
+            a = ref_chain(ref, seed, 1500, sp, kind, e0, e1, 180.0, 0, (0, 0, 0), erm, 1.2)
+            b = ref_chain(orc, seed, 1500, sp, kind, e0, e1, 180.0, 0, (0, 0, 0), erm, 1.2)
+            assert np.array_equal(a, b), (seed, sp, kind)
+    E = rng.uniform(0.01, 300.0, 3000)
+    F = rng.uniform(1.0, 3000.0, 3000)
+    mo = capi.model(0)
+    for which, sp in [(0, capi.NR), (1, capi.beta), (2, capi.beta), (3, capi.beta)]:
+        assert np.array_equal(ref.yields(which, sp, E, F, 2.95, 131.293, 54., list(mo.NRYieldsParam),
+                                         list(mo.ERYieldsParam), 0.8),
+                              orc.yields(which, sp, E, F, 2.95, 131.293, 54., list(mo.NRYieldsParam),
+                                         list(mo.ERYieldsParam), 0.8))
+
+
+def test_oracle_reproduces_reference_binary_stdout(orc):
+    """`execNEST 300 ER 0.1 20 180 -1 1` of the unmodified LUX_Run03 reference binary, row by row
+    (verbosity 1: CalculateG2's 10 000-sample Monte Carlo consumes the stream before event 0)"""
+    if not os.path.exists(refprobe.REF_BIN_LUX):
+        pytest.skip("oracle/_ref/execNEST_ref_lux not built")
+    n = 300
+    r = subprocess.run([refprobe.REF_BIN_LUX, str(n), "ER", "0.1", "20", "180", "-1", "1"], stdout=subprocess.PIPE,
+                       stderr=subprocess.DEVNULL, text=True, check=True)
+    rows = [ln for ln in r.stdout.splitlines() if ln[:1].isdigit() or ln[:1] == "-"]
+    rows = [ln for ln in rows if ln.count("\t") >= 11]
+    assert len(rows) == n
+    mo = capi.model(1)
+    o = orc.chain(1, n, capi.beta, capi.SRC_FLAT, 0.1, 20.0, 180.0, 0, [0., 0., 0.], 0, 1.0, list(mo.NRYieldsParam),
+                  list(mo.ERYieldsParam), list(mo.NRERWidthsParam)[:13], 0.0, 1, ana=capi.analysis(0))
+    C = refprobe.COL
+    ana = capi.analysis(0)
+    for j, ln in enumerate(rows):
+        s1, s2 = o[j, refprobe.S1_0:refprobe.S1_0 + 9], o[j, refprobe.S2_0:refprobe.S2_0 + 9]
+        exp = "%.6f\t%.6f\t%.6f\t%.0f, %.0f, %.0f\t%d\t%d\t" % (
+            o[j, C["keV_out"]], o[j, C["field"]], o[j, C["dt"]], o[j, C["sx"]], o[j, C["sy"]], o[j, C["z"]],
+            o[j, C["Nph"]], o[j, C["Ne"]])
+        # execNEST.cpp:1390-1408: engineering notation once a pulse leaves the analysis window
+        if o[j, C["keV_out"]] > 1000. or s1[5] > ana.maxS1 or s2[7] > ana.maxS2:
+            exp += "%e\t%e\t%e\t%d\t%e\t%e" % (s1[2], s1[5], s1[7], int(s2[0]), s2[4], s2[7])
+        else:
+            exp += "%.6f\t%.6f\t%.6f\t%i\t%.6f\t%.6f" % (s1[2], s1[5], s1[7], int(s2[0]), s2[4], s2[7])
+        assert ln.strip() == exp, (j, ln, exp)
