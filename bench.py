@@ -186,38 +186,28 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    launches0 = ctx.launch_count()
     for i in range(a.warmup):
         step(i)
     barrier()
+    ctx.timing_enable(True)
+    ctx.timing_read()
     sampler = ClockSampler(local)
     sampler.start()
     launches1 = ctx.launch_count()
-    kev0, kev1 = [], []
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(a.steps):
-        k0 = torch.cuda.Event(enable_timing=True)
-        k1 = torch.cuda.Event(enable_timing=True)
-        band_t.zero_()
-        first = ((a.warmup + i) * world + rank) * n
-        k0.record()
-        ctx.run_async(det, mo, ana, src, rc, seed, first, n)
-        k1.record()
-        if world > 1:
-            dist.all_reduce(band_t)
-        flush.fill_(i & 0xff)
-        kev0.append(k0)
-        kev1.append(k1)
+        step(a.warmup + i)
     e1.record()
     barrier()
     sampler.stop_flag = True
+    stage_ms, stage_launches = ctx.timing_read()
+    ctx.timing_enable(False)
     ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
-    kernel_ms = sum(x.elapsed_time(y) for x, y in zip(kev0, kev1)) / a.steps
     gpu_launches = ctx.launch_count() - launches1
     value = float(n) * world * a.steps / (ms_total * 1e-3)
 
@@ -292,18 +282,31 @@ def main():
 
     if rank == 0:
         peak = ctx.fp64_peak()
-        achieved = (float(n) * flops_per_event / (kernel_ms * 1e-3)) / 1e12
+        # dominant kernel: k_hits, the per-hit S1 loop.  Algorithmic work per launch = SURVEY 8(d)'s
+        # F_hit = 192 DFMA-equivalent flop per PMT hit x the hits one launch processes.
+        n_hit_launches = max(stage_launches[1], 1)
+        hits_ms = stage_ms["k_hits"] / n_hit_launches
+        events_per_launch = float(n) * a.steps / n_hit_launches
+        achieved = events_per_launch * mean_hits * F_HIT / (hits_ms * 1e-3) / 1e12
+        chain_ms = sum(stage_ms.values()) / a.steps
         out["roofline"] = {
             "bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "traffic": None, "kernel": "k_event<512>", "kernel_ms": kernel_ms,
-            "flops_per_event": flops_per_event, "mean_s1_hits": mean_hits,
-            "peak_source": "measured on this device by nb200_fp64_peak (DFMA chain, CUDA events); "
-                           "MEASURED_PEAKS.json carries no FP64 figure (nominal 37.2 TFLOP/s)",
-            "note": "FP64 CUDA-core pipe bound (no contraction, no HBM stream in band-only mode): algorithmic "
-                    "flops = SURVEY 8(d) nominal 3600 + 192 x mean S1 hits per event"}
+            "traffic": None, "kernel": "k_hits", "kernel_ms_per_launch": hits_ms,
+            "kernel_launches": int(n_hit_launches), "hits_per_launch": events_per_launch * mean_hits,
+            "flops_per_hit": F_HIT, "mean_s1_hits": mean_hits,
+            "stage_ms_per_step": {k: v / a.steps for k, v in stage_ms.items()},
+            "kernel_share_of_step": stage_ms["k_hits"] / max(sum(stage_ms.values()), 1e-9),
+            "chain_flops_per_event": flops_per_event,
+            "chain_achieved_tflops": float(n) * flops_per_event / (chain_ms * 1e-3) / 1e12,
+            "peak_source": "measured on this device by nb200_fp64_peak (register-resident DFMA chain, CUDA "
+                           "events); MEASURED_PEAKS.json carries HBM and bf16 figures only (nominal FP64 37.2)",
+            "note": "FP64 CUDA-core pipe bound, not HBM or tensor: no contraction, and in band-only mode the "
+                    "only HBM stream is the 140 B/event stage workspace (see hbm_workspace_frac)",
+            "hbm_workspace_frac": None}
         try:
             with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
                 mp = json.load(f)
+            out["roofline"]["hbm_workspace_frac"] = (value / world) * 140.0 * 2 / 1e9 / mp["hbm_gbs"]
             out["roofline"]["hbm_output_stream_frac_e2e"] = (e2e_value / world) * (d2h / ne) / 1e9 / mp["hbm_gbs"]
         except Exception:
             pass

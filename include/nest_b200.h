@@ -310,6 +310,13 @@ int nb200_lar(nb200_ctx* ctx, int species, size_t n, const double* E, const doub
               double density, uint64_t seed, uint64_t first_event, int mem_kind,
               double* yields, double* fluct);
 
+/* Per-stage device time of the chain kernels (k_pre, k_hits, k_post): with timing enabled each
+ * launch is bracketed by CUDA events on the context's stream; nb200_timing_read synchronises
+ * the stream, returns the milliseconds and launch counts accumulated since the last read and
+ * clears them.  ms[3], launches[3]. */
+int nb200_timing_enable(nb200_ctx* ctx, int on);
+int nb200_timing_read(nb200_ctx* ctx, double* ms, uint64_t* launches);
+
 /* Measured FP64 pipe peak of this device: a register-resident DFMA chain kernel timed with
  * CUDA events (the roofline denominator of the chain kernel). */
 int nb200_fp64_peak(nb200_ctx* ctx, double* tflops);

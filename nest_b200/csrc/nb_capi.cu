@@ -40,6 +40,9 @@ struct nb200_ctx {
     void* dev;
   };
   std::vector<Blob> blobs;
+  // optional per-stage timing
+  bool timing = false;
+  std::vector<cudaEvent_t> tev;   // 4 events per chunk launched since the last read
   // k_pre -> k_hits -> k_post workspace (one chunk)
   void* d_work = nullptr;
   uint64_t work_cap = 0;
@@ -302,9 +305,19 @@ int launch_event(nb200_ctx* c, RunParams& P) {
     unsigned g_pre = unsigned(std::min<uint64_t>((m + kPreBlock - 1) / kPreBlock, sm * c->occ_pre * 8));
     unsigned g_hits = unsigned(std::min<uint64_t>((m + kHitGroup - 1) / kHitGroup, sm * c->occ_hits * 4));
     unsigned g_post = unsigned(std::min<uint64_t>((m + kPostBlock - 1) / kPostBlock, sm * c->occ_post));
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (c->timing)
+      for (auto& e : ev) cudaEventCreate(&e);
+    if (c->timing) cudaEventRecord(ev[0], c->stream);
     k_pre<<<g_pre, kPreBlock, 0, c->stream>>>(Q, c->d_err);
+    if (c->timing) cudaEventRecord(ev[1], c->stream);
     k_hits<<<g_hits, kHitBlock, 0, c->stream>>>(Q);
+    if (c->timing) cudaEventRecord(ev[2], c->stream);
     k_post<<<g_post, kPostBlock, smem, c->stream>>>(Q, c->d_err);
+    if (c->timing) {
+      cudaEventRecord(ev[3], c->stream);
+      for (auto& e : ev) c->tev.push_back(e);
+    }
     NB_CUDA(c, cudaGetLastError());
     c->launches += 3;
   }
@@ -386,6 +399,7 @@ void nb200_destroy(nb200_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  for (auto e : c->tev) cudaEventDestroy(e);
   for (auto& b : c->blobs) cudaFree(b.dev);
   if (c->d_band && !c->band_external) cudaFree(c->d_band);
   if (c->d_band_tmp) cudaFree(c->d_band_tmp);
@@ -981,6 +995,32 @@ __global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, doubl
 }
 }  // namespace
 extern "C" {
+int nb200_timing_enable(nb200_ctx* c, int on) {
+  if (!c) return NB200_EINVAL;
+  c->timing = on != 0;
+  return 0;
+}
+
+int nb200_timing_read(nb200_ctx* c, double* ms, uint64_t* launches) {
+  if (!c || !ms || !launches) return NB200_EINVAL;
+  NB_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int k = 0; k < 3; ++k) {
+    ms[k] = 0.;
+    launches[k] = 0;
+  }
+  for (size_t i = 0; i + 3 < c->tev.size(); i += 4) {
+    for (int k = 0; k < 3; ++k) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, c->tev[i + k], c->tev[i + k + 1]);
+      ms[k] += t;
+      ++launches[k];
+    }
+  }
+  for (auto e : c->tev) cudaEventDestroy(e);
+  c->tev.clear();
+  return 0;
+}
+
 int nb200_fp64_peak(nb200_ctx* c, double* tflops) {
   if (!c || !tflops) return NB200_EINVAL;
   NB_CUDA(c, cudaSetDevice(c->device));

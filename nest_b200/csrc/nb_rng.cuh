@@ -186,6 +186,19 @@ static __constant__ double c_lntab[64] = {
 // zeros, u = m 2^-(e+1), m in [1,2) from the next 53 bits; ln m = ln c_j + ln(1 + d) with c_j the
 // centre of m's 1/32-wide cell and d = m/c_j - 1, |d| <= 2^-6 (Taylor through d^9: 9e-20).
 // tab: c_lntab staged in shared memory by the caller.
+// polynomial coefficients live in constant memory so that each DFMA takes its coefficient as a
+// constant-bank operand (64-bit literals would cost two UMOV each, every iteration)
+static __constant__ double c_lnp[8] = {1.0 / 9.0,  -1.0 / 8.0, 1.0 / 7.0, -1.0 / 6.0,
+                                       1.0 / 5.0,  -1.0 / 4.0, 1.0 / 3.0, -0.5};
+static __constant__ double c_sinp[7] = {-1.0 / 1307674368000.0, 1.0 / 6227020800.0, -1.0 / 39916800.0,
+                                        1.0 / 362880.0,         -1.0 / 5040.0,      1.0 / 120.0,
+                                        -1.0 / 6.0};
+static __constant__ double c_cosp[8] = {1.0 / 20922789888000.0, -1.0 / 87178291200.0, 1.0 / 479001600.0,
+                                        -1.0 / 3628800.0,       1.0 / 40320.0,        -1.0 / 720.0,
+                                        1.0 / 24.0,             -0.5};
+static __constant__ double c_hitk[4] = {0.69314718055994530942, 1.4629180792671596e-9, 536870912.0,
+                                        1073741824.0};
+
 NB_D double neg_log_bits(uint32_t hi, uint32_t lo, const double* tab) {
   unsigned long long x = ((unsigned long long)hi << 32) | lo;
   x |= 1ull;
@@ -195,53 +208,39 @@ NB_D double neg_log_bits(uint32_t hi, uint32_t lo, const double* tab) {
   const int j = int((y >> 58) & 31ull);
   const double2 t = *reinterpret_cast<const double2*>(tab + 2 * j);
   const double d = fma(m, t.x, -1.0);
-  double q = 1.0 / 9.0;
-  q = fma(q, d, -1.0 / 8.0);
-  q = fma(q, d, 1.0 / 7.0);
-  q = fma(q, d, -1.0 / 6.0);
-  q = fma(q, d, 1.0 / 5.0);
-  q = fma(q, d, -1.0 / 4.0);
-  q = fma(q, d, 1.0 / 3.0);
-  q = fma(q, d, -0.5);
+  double q = c_lnp[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) q = fma(q, d, c_lnp[i]);
   const double ln1pd = fma(d * d, q, d);
-  return fma(double(e + 1), 0.69314718055994530942, -t.y) - ln1pd;
+  return fma(double(e + 1), c_hitk[0], -t.y) - ln1pd;
 }
 
 // (sin, cos) of the angle 2 pi (z + 1/2) / 2^32: quadrant from the top two bits, the remaining
 // 30 bits folded onto [0, pi/4] (Taylor through x^15 / x^16: 5e-17).
 NB_D void sincos_bits(uint32_t z, double& s, double& c) {
-  const uint32_t quad = z >> 30;
   double f = double(z & 0x3FFFFFFFu) + 0.5;  // in (0, 2^30)
-  const bool fold = f > 536870912.0;          // beyond pi/4: use the complementary angle
-  if (fold) f = 1073741824.0 - f;
-  const double x = f * 1.4629180792671596e-9;  // (pi/2) / 2^30
+  const bool fold = f > c_hitk[2];            // beyond pi/4: use the complementary angle
+  if (fold) f = c_hitk[3] - f;
+  const double x = f * c_hitk[1];  // (pi/2) / 2^30
   const double x2 = x * x;
-  double ps = -1.0 / 1307674368000.0;
-  ps = fma(ps, x2, 1.0 / 6227020800.0);
-  ps = fma(ps, x2, -1.0 / 39916800.0);
-  ps = fma(ps, x2, 1.0 / 362880.0);
-  ps = fma(ps, x2, -1.0 / 5040.0);
-  ps = fma(ps, x2, 1.0 / 120.0);
-  ps = fma(ps, x2, -1.0 / 6.0);
-  double sn = fma(x * x2, ps, x);
-  double pc = 1.0 / 20922789888000.0;
-  pc = fma(pc, x2, -1.0 / 87178291200.0);
-  pc = fma(pc, x2, 1.0 / 479001600.0);
-  pc = fma(pc, x2, -1.0 / 3628800.0);
-  pc = fma(pc, x2, 1.0 / 40320.0);
-  pc = fma(pc, x2, -1.0 / 720.0);
-  pc = fma(pc, x2, 1.0 / 24.0);
-  pc = fma(pc, x2, -0.5);
-  double cs = fma(x2, pc, 1.0);
-  if (fold) {
-    const double t = sn;
-    sn = cs;
-    cs = t;
-  }
-  // rotate by quadrant * pi/2
-  const double a = (quad & 1u) ? sn : cs, b = (quad & 1u) ? cs : sn;
-  c = (quad == 1u || quad == 2u) ? -a : a;
-  s = (quad >= 2u) ? -b : b;
+  double ps = c_sinp[0];
+#pragma unroll
+  for (int i = 1; i < 7; ++i) ps = fma(ps, x2, c_sinp[i]);
+  const double sn = fma(x * x2, ps, x);
+  double pc = c_cosp[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) pc = fma(pc, x2, c_cosp[i]);
+  const double cs = fma(x2, pc, 1.0);
+  // quadrant q (top two bits): (cos, sin) of q pi/2 + a with a = x or pi/2 - x (fold).  The values
+  // swap when exactly one of (q odd, fold) holds; the signs are cos < 0 for q in {1,2}, sin < 0
+  // for q in {2,3}: applied to the sign bit of the high word.
+  const bool swap = (((z >> 30) & 1u) != 0u) != fold;
+  const double a = swap ? sn : cs, b = swap ? cs : sn;
+  const uint32_t q = z >> 30;
+  const uint32_t sc = ((q ^ (q >> 1)) & 1u) << 31;  // q = 1, 2
+  const uint32_t ss = (q >> 1) << 31;               // q = 2, 3
+  c = __hiloint2double(__double2hiint(a) ^ int(sc), __double2loint(a));
+  s = __hiloint2double(__double2hiint(b) ^ int(ss), __double2loint(b));
 }
 
 // ---- samplers (device) -------------------------------------------------------------
