@@ -317,6 +317,12 @@ int nb200_lar(nb200_ctx* ctx, int species, size_t n, const double* E, const doub
 int nb200_timing_enable(nb200_ctx* ctx, int on);
 int nb200_timing_read(nb200_ctx* ctx, double* ms, uint64_t* launches);
 
+/* Single-electron size Monte Carlo of CalculateG2(verbosity > 0) (NEST.cpp:2169-2225): n single
+ * electrons at random (r, phi); returns the mean and the width about the analytic SE the banner
+ * "g1 = ... SE_mean,width = ..." prints. */
+int nb200_se_stats(nb200_ctx* ctx, const nb200_detector* det, const nb200_run_consts* rc, int n, uint64_t seed,
+                   double* se_mean, double* se_width);
+
 /* Measured FP64 pipe peak of this device: a register-resident DFMA chain kernel timed with
  * CUDA events (the roofline denominator of the chain kernel). */
 int nb200_fp64_peak(nb200_ctx* ctx, double* tflops);

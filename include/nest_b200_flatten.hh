@@ -83,12 +83,9 @@ inline void tabulate(nb200_map* m, std::vector<double>* store, int nr, int nz, d
 
 }  // namespace nb200_detail
 
-// Det: any class with the VDetector public interface.  fold: Det::fold (the LCE enum
-// value passed by GetS1/GetS2; the shipped detectors ignore it).
+// scalars and noise arrays only (VDetector.hh:25-126 getters); maps untouched
 template <class Det>
-inline void nb200_flatten(Det& det, nb200_detector* out, nb200_flatten_storage* st,
-                          int nr = 257, int nz = 513, bool force_lut = false) {
-  std::memset(out, 0, sizeof *out);
+inline void nb200_flatten_scalars(Det& det, nb200_detector* out) {
   out->g1 = det.get_g1();
   out->sPEres = det.get_sPEres();
   out->sPEthr = det.get_sPEthr();
@@ -123,6 +120,15 @@ inline void nb200_flatten(Det& det, nb200_detector* out, nb200_flatten_storage* 
   out->PosResFlat = det.get_PosResFlat();
   out->PosResBase = det.get_PosResBase();
   out->molarMass = det.get_molarMass();
+}
+
+// Det: any class with the VDetector public interface.  fold: Det::fold (the LCE enum
+// value passed by GetS1/GetS2; the shipped detectors ignore it).
+template <class Det>
+inline void nb200_flatten(Det& det, nb200_detector* out, nb200_flatten_storage* st,
+                          int nr = 257, int nz = 513, bool force_lut = false) {
+  std::memset(out, 0, sizeof *out);
+  nb200_flatten_scalars(det, out);
 
   if (!force_lut && det.getName() == std::string("LUX Run03")) {
     nb200_detail::lux_run03_maps(out);

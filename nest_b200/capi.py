@@ -102,7 +102,7 @@ EXPORTS = [
     "nb200_abi_version", "nb200_sizeof", "nb200_create", "nb200_destroy", "nb200_last_error", "nb200_set_stream",
     "nb200_synchronize", "nb200_detector_builtin", "nb200_model_default", "nb200_analysis_default",
     "nb200_prepare", "nb200_wimp_prep", "nb200_poisson", "nb200_yields", "nb200_run", "nb200_run_async",
-    "nb200_band_reset", "nb200_band_attach", "nb200_fp64_peak", "nb200_timing_enable", "nb200_timing_read", "nb200_band_fetch", "nb200_band_device_buffer", "nb200_allreduce_hist",
+    "nb200_band_reset", "nb200_band_attach", "nb200_fp64_peak", "nb200_timing_enable", "nb200_timing_read", "nb200_se_stats", "nb200_band_fetch", "nb200_band_device_buffer", "nb200_allreduce_hist",
     "nb200_band_hist_bytes", "nb200_band_finalize", "nb200_lar", "nb200_launch_count",
     "nb200_debug_hitmath"]
 
@@ -156,6 +156,7 @@ def lib():
     L.nb200_band_fetch.argtypes = [vp, C.POINTER(BandHist)]
     L.nb200_band_attach.argtypes = [vp, C.POINTER(Analysis), vp]
     L.nb200_fp64_peak.argtypes = [vp, c_dp]
+    L.nb200_se_stats.argtypes = [vp, C.POINTER(Detector), C.POINTER(RunConsts), C.c_int, C.c_uint64, c_dp, c_dp]
     L.nb200_timing_enable.argtypes = [vp, C.c_int]
     L.nb200_timing_read.argtypes = [vp, c_dp, c_u64p]
     L.nb200_band_device_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]

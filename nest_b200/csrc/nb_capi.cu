@@ -40,6 +40,13 @@ struct nb200_ctx {
     void* dev;
   };
   std::vector<Blob> blobs;
+  // double-buffered device staging + copy stream for nb200_run's host outputs (kept across calls)
+  void* d_stage[2] = {nullptr, nullptr};
+  size_t stage_bytes = 0;
+  void* d_list = nullptr;
+  size_t list_bytes = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
   // optional per-stage timing
   bool timing = false;
   std::vector<cudaEvent_t> tev;   // 4 events per chunk launched since the last read
@@ -405,6 +412,13 @@ void nb200_destroy(nb200_ctx* c) {
   if (c->d_band_tmp) cudaFree(c->d_band_tmp);
   if (c->d_vtable) cudaFree(c->d_vtable);
   if (c->d_work) cudaFree(c->d_work);
+  for (int b = 0; b < 2; ++b) {
+    if (c->d_stage[b]) cudaFree(c->d_stage[b]);
+    if (c->ev_done[b]) cudaEventDestroy(c->ev_done[b]);
+    if (c->ev_copied[b]) cudaEventDestroy(c->ev_copied[b]);
+  }
+  if (c->d_list) cudaFree(c->d_list);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->d_err) cudaFree(c->d_err);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
@@ -802,54 +816,61 @@ int nb200_run(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo, co
   Trace tr("nb200_run");
   const bool host_soa = soa && soa->mem_kind == NB200_MEM_HOST;
   const bool host_list = src->kind == NB200_SRC_LIST && src->list_mem_kind == NB200_MEM_HOST;
-  const uint64_t chunk_max = 1ull << 22;
-  // device staging for host SoA columns
+  // Host outputs: the kernels of chunk i write into device staging buffer i%2 while the copy
+  // stream drains buffer (i-1)%2 to the caller's arrays, so PCIe and compute overlap.
+  const uint64_t chunk_max = host_soa ? (1ull << 21) : (1ull << 22);
+  const uint64_t cap = std::min<uint64_t>(n_events, chunk_max);
+  const size_t ncol = (sizeof(nb200_soa_out) - 8) / sizeof(void*);
   struct Col {
-    void** host_slot;
+    size_t k, elt, off;
     void* host;
-    void* dev;
-    size_t elt;
   };
   std::vector<Col> cols;
-  nb200_soa_out dsoa;
-  std::vector<void*> to_free;
-  auto cleanup = [&]() {
-    for (void* p : to_free) cudaFree(p);
-  };
-  const uint64_t cap = std::min<uint64_t>(n_events, chunk_max);
-  if (soa) {
-    dsoa = *soa;
-    dsoa.mem_kind = NB200_MEM_DEVICE;
-    if (host_soa) {
-      void** hp = reinterpret_cast<void**>(reinterpret_cast<char*>(soa) + 8);
-      void** dp = reinterpret_cast<void**>(reinterpret_cast<char*>(&dsoa) + 8);
-      const size_t ncol = (sizeof(nb200_soa_out) - 8) / sizeof(void*);
-      for (size_t k = 0; k < ncol; ++k) {
-        if (!hp[k]) continue;
-        const bool is_int = (k >= 8 && k < 12);
-        size_t elt = is_int ? 4 : 8;
-        void* d = nullptr;
-        cudaError_t e = cudaMalloc(&d, elt * cap);
-        if (e != cudaSuccess) {
-          cleanup();
-          return fail(c, NB200_ENOMEM, cudaGetErrorString(e));
-        }
-        to_free.push_back(d);
-        dp[k] = d;
-        cols.push_back({&dp[k], hp[k], d, elt});
+  size_t per_chunk = 0;
+  if (host_soa) {
+    void** hp = reinterpret_cast<void**>(reinterpret_cast<char*>(soa) + 8);
+    for (size_t k = 0; k < ncol; ++k) {
+      if (!hp[k]) continue;
+      const size_t elt = (k >= 8 && k < 12) ? 4 : 8;
+      cols.push_back({k, elt, per_chunk, hp[k]});
+      per_chunk += ((elt * cap + 255) / 256) * 256;
+    }
+    if (per_chunk > c->stage_bytes) {
+      for (int b = 0; b < 2; ++b) {
+        if (c->d_stage[b]) cudaFree(c->d_stage[b]);
+        c->d_stage[b] = nullptr;
+      }
+      c->stage_bytes = 0;
+      for (int b = 0; b < 2; ++b) {
+        cudaError_t e = cudaMalloc(&c->d_stage[b], per_chunk);
+        if (e != cudaSuccess) return fail(c, NB200_ENOMEM, cudaGetErrorString(e));
+      }
+      c->stage_bytes = per_chunk;
+    }
+    if (!c->copy_stream) {
+      NB_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+      for (int b = 0; b < 2; ++b) {
+        NB_CUDA(c, cudaEventCreateWithFlags(&c->ev_done[b], cudaEventDisableTiming));
+        NB_CUDA(c, cudaEventCreateWithFlags(&c->ev_copied[b], cudaEventDisableTiming));
       }
     }
   }
   double *dE = nullptr, *dx = nullptr, *dy = nullptr, *dz = nullptr;
   if (host_list) {
-    auto mk = [&](double** d) {
-      cudaError_t e = cudaMalloc(d, 8 * cap);
-      if (e == cudaSuccess) to_free.push_back(*d);
-      return e;
-    };
-    if (mk(&dE) != cudaSuccess || (src->x && (mk(&dx) != cudaSuccess || mk(&dy) != cudaSuccess || mk(&dz) != cudaSuccess))) {
-      cleanup();
-      return fail(c, NB200_ENOMEM, "device staging for the energy list");
+    const size_t need = 8 * cap * (src->x ? 4 : 1);
+    if (need > c->list_bytes) {
+      if (c->d_list) cudaFree(c->d_list);
+      c->d_list = nullptr;
+      c->list_bytes = 0;
+      cudaError_t e = cudaMalloc(&c->d_list, need);
+      if (e != cudaSuccess) return fail(c, NB200_ENOMEM, "device staging for the energy list");
+      c->list_bytes = need;
+    }
+    dE = static_cast<double*>(c->d_list);
+    if (src->x) {
+      dx = dE + cap;
+      dy = dx + cap;
+      dz = dy + cap;
     }
   }
   if (hist) {
@@ -858,19 +879,18 @@ int nb200_run(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo, co
       if (c->d_band_tmp) cudaFree(c->d_band_tmp);
       c->d_band_tmp = nullptr;
       cudaError_t e = cudaMalloc(&c->d_band_tmp, w * 8);
-      if (e != cudaSuccess) {
-        cleanup();
-        return fail(c, NB200_ENOMEM, cudaGetErrorString(e));
-      }
+      if (e != cudaSuccess) return fail(c, NB200_ENOMEM, cudaGetErrorString(e));
       c->band_tmp_words = w;
     }
     cudaMemsetAsync(c->d_band_tmp, 0, w * 8, c->stream);
   }
 
-  tr.mark("staging alloc");
+  tr.mark("staging");
   int rcode = 0;
-  for (uint64_t done = 0; done < n_events && !rcode; done += chunk_max) {
+  uint64_t ichunk = 0;
+  for (uint64_t done = 0; done < n_events && !rcode; done += chunk_max, ++ichunk) {
     const uint64_t m = std::min<uint64_t>(chunk_max, n_events - done);
+    const int buf = int(ichunk & 1);
     nb200_source s = *src;
     if (src->kind == NB200_SRC_LIST) {
       if (host_list) {
@@ -898,10 +918,13 @@ int nb200_run(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo, co
     if (rcode) break;
     if (soa) {
       P.write_soa = 1;
-      nb200_soa_out tmp = dsoa;
-      if (!host_soa) {  // advance caller's device columns
-        void** dp = reinterpret_cast<void**>(reinterpret_cast<char*>(&tmp) + 8);
-        const size_t ncol = (sizeof(nb200_soa_out) - 8) / sizeof(void*);
+      nb200_soa_out tmp = *soa;
+      void** dp = reinterpret_cast<void**>(reinterpret_cast<char*>(&tmp) + 8);
+      if (host_soa) {
+        for (size_t k = 0; k < ncol; ++k) dp[k] = nullptr;
+        for (auto& col : cols) dp[col.k] = static_cast<char*>(c->d_stage[buf]) + col.off;
+        if (ichunk >= 2) cudaStreamWaitEvent(c->stream, c->ev_copied[buf], 0);  // buffer drained?
+      } else {  // caller's device columns, advanced to this chunk
         for (size_t k = 0; k < ncol; ++k)
           if (dp[k]) dp[k] = static_cast<char*>(dp[k]) + ((k >= 8 && k < 12) ? 4 : 8) * done;
       }
@@ -913,13 +936,22 @@ int nb200_run(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo, co
     }
     rcode = launch_event(c, P);
     if (rcode) break;
-    if (host_soa)
+    if (host_soa) {
+      cudaEventRecord(c->ev_done[buf], c->stream);
+      cudaStreamWaitEvent(c->copy_stream, c->ev_done[buf], 0);
       for (auto& col : cols)
-        cudaMemcpyAsync(static_cast<char*>(col.host) + col.elt * done, col.dev, col.elt * m, cudaMemcpyDeviceToHost,
-                        c->stream);
-    rcode = check_device_error(c);
-    tr.mark("chunk kernel + copies");
+        cudaMemcpyAsync(static_cast<char*>(col.host) + col.elt * done, static_cast<char*>(c->d_stage[buf]) + col.off,
+                        col.elt * m, cudaMemcpyDeviceToHost, c->copy_stream);
+      cudaEventRecord(c->ev_copied[buf], c->copy_stream);
+    }
+    tr.mark("chunk enqueued");
   }
+  if (host_soa && c->copy_stream) {
+    cudaError_t e = cudaStreamSynchronize(c->copy_stream);
+    if (e != cudaSuccess && !rcode) rcode = fail(c, NB200_ECUDA, cudaGetErrorString(e));
+  }
+  if (!rcode) rcode = check_device_error(c);
+  tr.mark("kernels + copies done");
   if (!rcode && hist) {
     std::vector<unsigned long long> w(c->band_tmp_words);
     cudaError_t e = cudaMemcpyAsync(w.data(), c->d_band_tmp, c->band_tmp_words * 8, cudaMemcpyDeviceToHost, c->stream);
@@ -944,8 +976,6 @@ int nb200_run(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo, co
   }
   cudaStreamSynchronize(c->stream);
   tr.mark("band fetch");
-  cleanup();
-  tr.mark("staging free");
   return rcode;
 }
 
@@ -995,6 +1025,42 @@ __global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, doubl
 }
 }  // namespace
 extern "C" {
+int nb200_se_stats(nb200_ctx* c, const nb200_detector* det, const nb200_run_consts* rc, int n, uint64_t seed,
+                   double* se_mean, double* se_width) {
+  if (!c || !det || !rc || !se_mean || !se_width || n < 2) return c ? fail(c, NB200_EINVAL, "bad argument") : NB200_EINVAL;
+  NB_CUDA(c, cudaSetDevice(c->device));
+  RunParams P;
+  std::memset(&P, 0, sizeof P);
+  P.det = *det;
+  P.rc = *rc;
+  int r;
+  if ((r = upload_map(c, &P.det.FitS2))) return r;
+  if ((r = upload_map(c, &P.det.FitTBA))) return r;
+  P.det.FitS1.lut = nullptr;
+  P.det.FitEF.lut = nullptr;
+  P.s2_center = fit_s2(det->FitS2, 0., 0.);
+  P.seed = seed;
+  double* d = nullptr;
+  NB_CUDA(c, cudaMalloc(&d, sizeof(double) * n));
+  k_se<<<(n + 127) / 128, 128, 0, c->stream>>>(P, n, d);
+  ++c->launches;
+  std::vector<double> h(n);
+  cudaMemcpyAsync(h.data(), d, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream);
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(c, NB200_ECUDA, cudaGetErrorString(e));
+  const double SE = rc->g2_params[0] * det->g1_gas *
+                    (det->s2_thr < 0 ? fit_tba(det->FitTBA, 0., 0., det->TopDrift / 2.) : 1.);
+  double mu = 0., sd = 0.;
+  for (double v : h) {
+    sd += (SE - v) * (SE - v);
+    mu += v;
+  }
+  *se_mean = mu / double(n);
+  *se_width = sqrt(sd) / sqrt(double(n) - 1.);
+  return 0;
+}
+
 int nb200_timing_enable(nb200_ctx* c, int on) {
   if (!c) return NB200_EINVAL;
   c->timing = on != 0;

@@ -570,6 +570,36 @@ __global__ void __launch_bounds__(kPostBlock, NB_POST_MINB)
   }
 }
 
+// CalculateG2's single-electron Monte Carlo (NEST.cpp:2169-2215): one thread = one electron
+__global__ void k_se(const __grid_constant__ RunParams P, int n, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const nb200_detector& d = P.det;
+  const double elYield = P.rc.g2_params[0];
+  Stream g;
+  g.init(P.seed, uint64_t(i), STREAM_SE);
+  long long Nph = (long long)floor(gauss(g, elYield, sqrt(d.s2Fano * elYield), true) + 0.5);
+  double sn, cs;
+  sincospi(2. * g.uniform(), &sn, &cs);
+  const double r = d.radius * sqrt(g.uniform());
+  const double posDep = fit_s2(d.FitS2, r * cs, r * sn) / P.s2_center;
+  long long nHits = binomial(P.seed, uint64_t(i), STREAM_BIN_S2HIT, Nph, d.g1_gas * posDep);
+  double Nphe = double(nHits + binomial(P.seed, uint64_t(i), STREAM_BIN_S2DPE, nHits, d.P_dphe));
+  double area = gauss(g, Nphe, d.sPEres * sqrt(Nphe), true);
+  double sig;
+  if (d.noiseQuadratic[1] != 0) {
+    double a = d.noiseQuadratic[1] * (area * area), b = d.noiseLinear[1] * area;
+    sig = sqrt(a * a + b * b);
+  } else
+    sig = d.noiseLinear[1] * area;
+  area = gauss(g, area, sig, true);
+  if (d.s2_thr < 0.) {
+    const double t = fit_tba(d.FitTBA, 0., 0., d.TopDrift / 2.);
+    area = gauss(g, t * area, sqrt(t * area * (1. - t)), true);
+  }
+  out[i] = (area / posDep) / (1. + d.P_dphe);
+}
+
 // test hook: the hit loop's specialised math on caller-supplied bits; out = {-ln u, sin, cos}
 __global__ void k_hitmath(size_t n, const uint32_t* __restrict__ bits, double* __restrict__ out) {
   __shared__ __align__(16) double s_lntab[64];

@@ -29,6 +29,7 @@ enum : uint32_t {
   STREAM_HIT3 = 4,   // S1 PMT hits: single-phe efficiency decisions (sPEeff < 1 only)
   STREAM_POST = 5,   // per-event scalar draws after the S1 hit loop (k_post)
   STREAM_LAR = 8,
+  STREAM_SE = 9,     // CalculateG2's single-electron Monte Carlo
   // each binomial draw owns a stream (the sampler is an out-of-line subroutine)
   STREAM_BIN_NI = 32, STREAM_BIN_S1 = 33, STREAM_BIN_NEE = 34, STREAM_BIN_S2HIT = 35,
   STREAM_BIN_S2DPE = 36, STREAM_BIN_PAR0 = 37, STREAM_BIN_PAR1 = 38, STREAM_BIN_PAR2 = 39,

@@ -1,0 +1,640 @@
+// NEST_b200.cpp -- host side of the drop-in: the reference's driver logic (argument checks,
+// messages, output formats) around the GPU chain.  No physics is computed here: every number comes
+// from libnest_b200.so; reference lines are cited where behaviour is mirrored.
+#include "NEST_b200.hh"
+
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <stdexcept>
+
+#include "nest_b200_flatten.hh"
+
+using namespace std;
+using namespace NEST;
+
+namespace {
+const double kHiEregime = 1E+2;  // execNEST.hh:25
+const double kPHE_MIN = 1e-6;
+
+bool nearlyEqual(double a, double b, double eps = 1e-9) {  // ValidityTests.cpp:6-21
+  if (a == b) return true;
+  double A = fabs(a), B = fabs(b), d = fabs(a - b);
+  if (a == 0 || b == 0 || (A + B < DBL_MIN)) return d < eps * DBL_MIN;
+  return d / fmin(A + B, DBL_MAX) < eps;
+}
+void fill_model(nb200_model* m, const vector<double>& nr, const vector<double>& er, const vector<double>& w) {
+  nb200_model_default(0, m);
+  if (nr.size() < 12) throw runtime_error("ERROR: You need a minimum of 12 nuisance parameters for the mean yields.");
+  if (er.size() < 10) throw runtime_error("ERROR: You need a minimum of 10 nuisance parameters for the mean yields.");
+  if (w.size() < 13) throw runtime_error("ERROR: You need a minimum of 13 free parameters for the resolution model.");
+  for (int i = 0; i < 12; ++i) m->NRYieldsParam[i] = nr[i];
+  for (int i = 0; i < 10; ++i) m->ERYieldsParam[i] = er[i];
+  m->n_widths = int(min<size_t>(w.size(), 17));
+  for (int i = 0; i < m->n_widths; ++i) m->NRERWidthsParam[i] = w[i];
+}
+}  // namespace
+
+// ---- Analysis ---------------------------------------------------------------------------------
+Analysis Analysis::G2() {  // include/NEST/analysis_G2.hh
+  Analysis a;
+  a.verbosity = 1; a.PrintSubThr = 0; a.MCtruthE = true; a.usePD = 1; a.useS2 = 1;
+  a.minS1 = 2.5; a.maxS1 = 120.5; a.numBins = 118; a.minS2 = 200.; a.maxS2 = 9e4;
+  a.logMax = 5.; a.logMin = 2.; a.z_step = 1.;
+  return a;
+}
+nb200_analysis Analysis::flat() const {
+  nb200_analysis f;
+  nb200_analysis_default(0, &f);
+  f.usePD = usePD; f.useS2 = useS2; f.numBins = numBins; f.logBins = logBins;
+  f.minS1 = minS1; f.maxS1 = maxS1; f.minS2 = minS2; f.maxS2 = maxS2; f.logMin = logMin; f.logMax = logMax;
+  f.MCtruthE = MCtruthE; f.MCtruthPos = MCtruthPos; f.z_step = z_step;
+  switch (s1CalculationMode) {
+    case S1CalculationMode::Full: f.s1mode = NB200_S1_FULL; break;
+    case S1CalculationMode::Parametric: f.s1mode = NB200_S1_PARAMETRIC; break;
+    case S1CalculationMode::Hybrid: f.s1mode = NB200_S1_HYBRID; break;
+    default: f.s1mode = -1; break;  // Waveform: refused by the library
+  }
+  f.s2mode = (s2CalculationMode == S2CalculationMode::Full) ? NB200_S2_FULL : -1;
+  return f;
+}
+
+// ---- Device -------------------------------------------------------------------------------------
+nb200_ctx* Device::get() {
+  static nb200_ctx* ctx = nullptr;
+  if (!ctx) {
+    int dev = 0;
+    if (const char* e = getenv("NB200_DEVICE")) dev = atoi(e);
+    int rc = nb200_create(dev, &ctx);
+    if (rc) throw runtime_error(string("nest_b200: ") + nb200_last_error(nullptr) + " (there is no CPU fallback)");
+  }
+  return ctx;
+}
+void Device::check(int rc) {
+  if (rc) {
+    const char* m = nb200_last_error(rc == NB200_OK ? nullptr : Device::get());
+    throw runtime_error(m && *m ? m : "nest_b200 error");
+  }
+}
+
+// ---- NESTcalc -----------------------------------------------------------------------------------
+NESTcalc::NESTcalc(VDetector* detector) : fdetector(detector) {
+  if (!detector) throw runtime_error("NESTcalc needs a detector");
+}
+const nb200_detector& NESTcalc::flat() {
+  if (!flattened) {
+    static nb200_flatten_storage store;  // LUT backing store (one detector per process, as the reference)
+    nb200_flatten(*fdetector, &fdet, &store);
+    flattened = true;
+  } else {  // scalars may have been changed through the setters since
+    nb200_detector keep = fdet;
+    nb200_flatten_storage dummy;
+    nb200_map s1 = keep.FitS1, s2 = keep.FitS2, ef = keep.FitEF, tba = keep.FitTBA;
+    nb200_flatten_scalars(*fdetector, &fdet);
+    fdet.FitS1 = s1; fdet.FitS2 = s2; fdet.FitEF = ef; fdet.FitTBA = tba;
+  }
+  return fdet;
+}
+const nb200_run_consts& NESTcalc::prepared(double inField, double z_step) {
+  nb200_detector d = flat();
+  int rc_ = nb200_prepare(&d, inField, z_step, &rc);
+  if (rc_) throw runtime_error(nb200_last_error(nullptr));
+  fdet.inGas = d.inGas;
+  fdetector->set_inGas(d.inGas != 0);
+  rc_field = inField;
+  return rc;
+}
+double NESTcalc::SetDensity(double Kelvin, double bara) {
+  nb200_detector d = flat();
+  d.T_Kelvin = Kelvin;
+  d.p_bar = bara;
+  nb200_run_consts c;
+  int r = nb200_prepare(&d, 180., 0., &c);
+  fdetector->set_inGas(d.inGas != 0);
+  if (r) throw runtime_error(nb200_last_error(nullptr));
+  return c.rho;
+}
+double NESTcalc::SetDriftVelocity(double Kelvin, double, double eField, double) {
+  nb200_detector d = flat();
+  d.T_Kelvin = Kelvin;
+  d.dt_min = 0.;
+  nb200_run_consts c;
+  if (nb200_prepare(&d, eField, 0., &c)) throw runtime_error(nb200_last_error(nullptr));
+  return c.vD;
+}
+NESTcalc::Wvalue NESTcalc::WorkFunction(double rho, double MolarMass, bool OldW13eV) {
+  double alpha = 0.067366 + rho * 0.039693;
+  double eDensity = (rho / MolarMass) * 6.0221409e+23 * 54.;
+  double Wq = 18.7263 - 1.01e-23 * eDensity;
+  if (OldW13eV) Wq *= 1.1716263232;
+  return Wvalue{Wq, alpha};
+}
+vector<double> NESTcalc::CalculateG2(int verbosity) {
+  const nb200_run_consts& c = prepared(rc_field > -12345. ? rc_field : 180.);
+  vector<double> g(c.g2_params, c.g2_params + 5);
+  if (verbosity > 0) {  // banner NEST.cpp:2220-2224; SE mean/width from a 10 000-event single-electron run
+    double se_mean = g[2], se_width = 0.;
+    nb200_se_stats(Device::get(), &fdet, &c, 10000, 1, &se_mean, &se_width);
+    cout << endl << "g1 = " << fdetector->get_g1() << " phd per photon\tg2 = " << g[3] << " phd per electron (e-EE = ";
+    cout << g[1] * 100. << "%, SE_mean,width = " << se_mean << "," << se_width << ")\t";
+  }
+  return g;
+}
+vector<YieldResult> NESTcalc::GetYields(INTERACTION_TYPE species, const vector<double>& energy, double density,
+                                        const vector<double>& dfield, double massNum, double atomNum,
+                                        const vector<double>& NRYieldsParam, const vector<double>& ERYieldsParam) {
+  if (energy.size() != dfield.size()) throw runtime_error("GetYields: energy and field lists differ in length");
+  nb200_model m;
+  fill_model(&m, NRYieldsParam, ERYieldsParam, default_NRERWidthsParam);
+  m.er_model = -1;
+  m.massNum = massNum;
+  m.atomNum = atomNum;
+  const size_t n = energy.size();
+  vector<double> out(6 * n);
+  Device::check(nb200_yields(Device::get(), &flat(), &m, int(species), n, energy.data(), dfield.data(), density,
+                             NB200_MEM_HOST, out.data()));
+  vector<YieldResult> r(n);
+  for (size_t i = 0; i < n; ++i)
+    r[i] = YieldResult{out[i], out[n + i], out[2 * n + i], out[3 * n + i], out[4 * n + i], out[5 * n + i]};
+  return r;
+}
+YieldResult NESTcalc::GetYields(INTERACTION_TYPE species, double energy, double density, double dfield,
+                                double massNum, double atomNum, const vector<double>& NRYieldsParam,
+                                const vector<double>& ERYieldsParam) {
+  return GetYields(species, vector<double>{energy}, density, vector<double>{dfield}, massNum, atomNum,
+                   NRYieldsParam, ERYieldsParam)[0];
+}
+
+// ---- runNESTvec: execNEST.cpp:329-409 ----------------------------------------------------------------
+NESTObservableArray runNESTvec(VDetector* detector, INTERACTION_TYPE particleType, vector<double> eList,
+                               vector<vector<double>> pos3dxyz, double inField, int seed,
+                               vector<double> ERYieldsParam, vector<double> NRYieldsParam,
+                               vector<double> NRERWidthsParam, S1CalculationMode s1mode, S2CalculationMode s2mode,
+                               bool calculate_times) {
+  if (calculate_times) throw runtime_error("runNESTvec: photon times are outside the GPU path (calculate_times=false)");
+  if (eList.size() != pos3dxyz.size()) throw runtime_error("runNESTvec: eList and pos3dxyz differ in length");
+  NESTcalc calc(detector);
+  const size_t n = eList.size();
+  NESTObservableArray r;
+  if (n == 0) return r;
+  const nb200_run_consts rc = calc.prepared(inField < 0. ? 180. : inField);
+  nb200_model m;
+  fill_model(&m, NRYieldsParam, ERYieldsParam, NRERWidthsParam);
+  m.er_model = -1;
+  m.SkewnessER = -999.;                  // FullCalculation NEST.cpp:33-34
+  m.massNum = detector->get_molarMass();  // execNEST.cpp:378-379
+  m.atomNum = 54.;
+  Analysis a;
+  a.s1CalculationMode = s1mode;
+  a.s2CalculationMode = s2mode;
+  nb200_analysis ana = a.flat();
+  vector<double> x(n), y(n), z(n);
+  for (size_t i = 0; i < n; ++i) {
+    if (pos3dxyz[i].size() < 3) throw runtime_error("runNESTvec: a position needs x, y, z");
+    x[i] = pos3dxyz[i][0];
+    y[i] = pos3dxyz[i][1];
+    z[i] = pos3dxyz[i][2];
+  }
+  nb200_source s;
+  memset(&s, 0, sizeof s);
+  s.kind = NB200_SRC_LIST;
+  s.species = int(particleType);
+  s.fixed_pos = 1;
+  s.vec_mode = 1;
+  s.inField = inField;
+  s.list_mem_kind = NB200_MEM_HOST;
+  s.E = eList.data();
+  s.x = x.data();
+  s.y = y.data();
+  s.z = z.data();
+  vector<int32_t> nph(n), ne(n);
+  vector<vector<double>> s1(9, vector<double>(n)), s2(9, vector<double>(n));
+  nb200_soa_out o;
+  memset(&o, 0, sizeof o);
+  o.mem_kind = NB200_MEM_HOST;
+  o.photons = nph.data();
+  o.electrons = ne.data();
+  for (int k = 0; k < 9; ++k) {
+    o.s1[k] = s1[k].data();
+    o.s2[k] = s2[k].data();
+  }
+  Device::check(nb200_run(Device::get(), &calc.flat(), &m, &ana, &s, &rc, uint64_t(seed), 0, n, &o, nullptr));
+  r.energy_kev = eList;
+  r.x_mm = x; r.y_mm = y; r.z_mm = z;
+  r.n_photons.assign(nph.begin(), nph.end());
+  r.n_electrons.assign(ne.begin(), ne.end());
+  auto iabs = [&](const vector<double>& v) {  // store_signals: std::abs(int(.)) execNEST.cpp:284-311
+    vector<int> q(n);
+    for (size_t i = 0; i < n; ++i) q[i] = abs(int(v[i]));
+    return q;
+  };
+  auto dabs = [&](const vector<double>& v) {
+    vector<double> q(n);
+    for (size_t i = 0; i < n; ++i) q[i] = fabs(v[i]);
+    return q;
+  };
+  r.s1_nhits = iabs(s1[0]); r.s1_nhits_dpe = iabs(s1[1]); r.s1_nhits_thr = iabs(s1[8]);
+  r.s1r_phe = dabs(s1[2]); r.s1c_phe = dabs(s1[3]); r.s1r_phd = dabs(s1[4]); r.s1c_phd = dabs(s1[5]);
+  r.s1r_spike = dabs(s1[6]); r.s1c_spike = dabs(s1[7]);
+  r.s2_Nee = iabs(s2[0]); r.s2_Nph = iabs(s2[1]); r.s2_nhits = iabs(s2[2]); r.s2_nhits_dpe = iabs(s2[3]);
+  r.s2r_phe = dabs(s2[4]); r.s2c_phe = dabs(s2[5]); r.s2r_phd = dabs(s2[6]); r.s2c_phd = dabs(s2[7]);
+  return r;
+}
+
+// ---- execNEST(): execNEST.cpp:412-1506 ---------------------------------------------------------------
+namespace nest_b200_cli {
+Analysis analysis;
+vector<double> NRYieldsParam = default_NRYieldsParam, NRERWidthsParam = default_NRERWidthsParam,
+               ERYieldsParam = default_ERYieldsParam;
+double multFact = 1.;
+}  // namespace nest_b200_cli
+
+int execNEST(VDetector* detector, double numEvts, const string& type, double eMin, double eMax, double inField,
+             string position, const string& posiMuon, double fPos, int seed, bool no_seed, double dayNumber) {
+  using namespace nest_b200_cli;
+  (void)posiMuon;
+  (void)no_seed;
+  Analysis& A = analysis;
+  const int verbosity = A.verbosity;
+  try {
+    NESTcalc n(detector);
+    if (detector->get_TopDrift() <= 0. || detector->get_anode() <= 0. || detector->get_gate() <= 0.) {  // :419-426
+      if (verbosity > 0) cerr << "ERROR, unphysical value(s) of position within the detector geometry.";
+      return 1;
+    }
+    const bool muon = (type == "muon" || type == "MIP" || type == "LIP" || type == "mu" || type == "mu-");
+    if (nearlyEqual(eMin, -1.) && !muon) eMin = 0.;  // :452-466
+    if (nearlyEqual(eMax, -1.) && nearlyEqual(eMin, 0.)) eMax = kHiEregime;
+    if (nearlyEqual(eMax, 0.) && !muon) {
+      if (verbosity > 0) cerr << "ERROR: The maximum energy (or Kr time sep) cannot be 0 keV (or 0 ns)!" << endl;
+      return 1;
+    }
+    uint64_t useed = (seed == -1) ? uint64_t(time(nullptr)) : uint64_t(int64_t(seed));  // :442-450
+
+    nb200_source S;
+    memset(&S, 0, sizeof S);
+    nb200_model M;
+    fill_model(&M, NRYieldsParam, ERYieldsParam, NRERWidthsParam);
+    M.SkewnessER = 0.;  // execNEST.cpp:1065
+    M.er_model = -1;
+    M.massNum = detector->get_molarMass();
+    M.atomNum = 0.;
+    vector<double> wbase(100), wexp(100);
+    INTERACTION_TYPE type_num;
+    // type aliases :468-576
+    if (type == "NR" || type == "neutron" || type == "-1") type_num = NR;
+    else if (type == "WIMP") {
+      if (eMin < 0.44) {
+        if (verbosity > 0) cerr << "WIMP mass too low, you're crazy!" << endl;
+        return 1;
+      }
+      type_num = WIMP;
+      double integral = 0.;
+      int rc_ = nb200_wimp_prep(eMin, A.E_step, dayNumber, useed, wbase.data(), wexp.data(), &integral, &S.wimp_xMax,
+                                &S.wimp_divisor);
+      if (rc_) throw runtime_error(nb200_last_error(nullptr));
+      S.wimp_base = wbase.data();
+      S.wimp_exponent = wexp.data();
+      S.wimp_mass = eMin;
+      S.wimp_day = dayNumber;
+      numEvts = double(nb200_poisson(integral * 1.0 * numEvts * eMax / 1e-36, useed));
+    } else if (type == "B8" || type == "Boron8" || type == "8Boron" || type == "8B" || type == "Boron-8") {
+      type_num = B8;
+      numEvts = double(nb200_poisson(0.0026 * numEvts, useed));
+    } else if (type == "DD" || type == "D-D") type_num = DD;
+    else if (type == "AmBe") type_num = AmBe;
+    else if (type == "alpha") {
+      type_num = ion;
+      M.atomNum = 2;
+      M.massNum = 4;
+    } else if (type == "gamma" || type == "gammaRay" || type == "x-ray" || type == "xray" || type == "xRay" ||
+               type == "X-ray" || type == "Xray" || type == "XRay")
+      type_num = gammaRay;
+    else if (type == "CH3T" || type == "tritium") type_num = CH3T;
+    else if (type == "beta" || type == "ER" || type == "Compton" || type == "compton" || type == "electron" ||
+             type == "e-")
+      type_num = NEST::beta;
+    else if (muon || type == "Kr83m" || type == "83mKr" || type == "Kr83" || type == "C14" || type == "Carbon14" ||
+             type == "14C" || type == "C-14" || type == "Carbon-14" || type == "Cf" || type == "Cf252" ||
+             type == "252Cf" || type == "Cf-252" || type == "pp" || type == "ppsolar" || type == "ppSolar" ||
+             type == "atmNu" || type == "fullGamma" || type == "ion" || type == "nucleus") {
+      if (verbosity > 0)
+        cerr << "ERROR: particle type " << type << " is not part of the GPU path (nest-b200 DESIGN.md section 8); "
+             << "use the reference execNEST for it." << endl;
+      return 1;
+    } else {
+      if (verbosity > 0)
+        cerr << "UNRECOGNIZED PARTICLE TYPE!! VALID OPTIONS ARE:\nNR or neutron,\nWIMP,\nB8 or Boron8 or 8Boron or "
+                "8B or Boron-8,\nDD or D-D,\nAmBe,\nalpha,\ngamma or gammaRay,\nx-ray or xray or xRay or X-ray or "
+                "Xray or XRay,\nCH3T or tritium,\nbeta or ER or Compton or compton or electron or e-\n";
+      return 1;
+    }
+    if (numEvts < 1. && type_num != WIMP && type_num != B8) {  // :578-581
+      if (verbosity > 0) cerr << "ERROR, you must simulate at least one event, or non-zero kg*days" << endl;
+      return 1;
+    }
+    if ((eMin < 10. || eMax < 10.) && type_num == gammaRay && verbosity > 0) {  // :603-610
+      cerr << "WARNING: Typically beta model works better for ER BG at low energies as in a WS." << endl;
+      cerr << "ER data is often best matched by a weighted average of the beta & gamma models." << endl;
+    }
+
+    // per-run constants :612-631, 878-890
+    nb200_run_consts rc;
+    try {
+      rc = n.prepared(inField, A.z_step);
+    } catch (exception& e) {
+      if (verbosity > 0) cerr << e.what() << endl;
+      return 1;
+    }
+    const double rho = rc.rho, Wq_eV = rc.Wq_eV;
+    n.CalculateG2(verbosity);
+    const double g2 = fabs(rc.g2_params[3]), g1 = detector->get_g1();
+    (void)g1;
+    (void)g2;
+    if (type_num < 6) M.massNum = 0;  // :670
+
+    // source kind :681-790
+    const bool mono = (nearlyEqual(eMin, eMax) && eMin >= 0. && eMax > 0.);
+    S.species = int(type_num);
+    S.eMin = eMin;
+    S.eMax = eMax;
+    S.inField = inField;
+    if (mono) S.kind = NB200_SRC_MONO;
+    else if (type_num == CH3T) {
+      S.kind = NB200_SRC_CH3T;
+      if ((min(eMax, 18.5898) != 18.5898 || max(eMin, 0.) != 0.) && verbosity > 0)
+        cerr << "WARNING: Recommended energy range is 0 to " << 18.5898 << " keV" << endl;  // TestSpectra.cpp:37-41
+    } else if (type_num == B8) S.kind = NB200_SRC_B8;
+    else if (type_num == AmBe) {
+      S.kind = NB200_SRC_AMBE;
+      S.par[0] = -0.95351;
+    } else if (type_num == DD) {
+      S.kind = NB200_SRC_DD;
+      const double p[5] = {13., 0.12, 71.2, 20., -20.5};  // :705
+      memcpy(S.par, p, sizeof p);
+    } else if (type_num == WIMP) S.kind = NB200_SRC_WIMP;
+    else {
+      if (eMin < 0.) return 1;
+      if (eMax > 0.) S.kind = (eMax > eMin) ? NB200_SRC_FLAT : NB200_SRC_GAUSS;
+      else {
+        if (nearlyEqual(eMin, 0.)) return 1;
+        S.kind = NB200_SRC_EXP;
+      }
+    }
+    if (type == "ER") {  // :1032-1048
+      if (verbosity > 0)
+        cerr << "CAUTION: Are you sure you don't want beta model instead of ER? This is a recomb-enhanced "
+                "(Qy-reduced) version of it for non-betas e.g. EC, DEC. Seed is now Q reduction."
+             << endl
+             << ">1 means increase, and negative number means gamma model; use 0 for a weighted average of the "
+                "gamma, beta models"
+             << endl;
+      if (multFact > 0.) { M.er_model = 0; M.multFact = multFact; }
+      else if (multFact < 0.) { M.er_model = 1; M.multFact = -multFact; }
+      else M.er_model = 2;
+    } else if (seed < 0 && seed != -1 && type_num <= 5)
+      M.massNum = detector->get_molarMass();  // :1050-1051
+
+    // position :806-855
+    if (nearlyEqual(fPos, -1.)) S.fixed_pos = 0;
+    else {
+      double px = 0., py = 0., pz = 0.;
+      size_t c1 = position.find(','), c2 = position.rfind(',');
+      if (c1 == string::npos || c1 == c2) {
+        if (verbosity > 0) cerr << "ERROR: position must be -1 or x,y,z" << endl;
+        return 1;
+      }
+      px = stof(position.substr(0, c1));
+      py = stof(position.substr(c1 + 1, c2 - c1 - 1));
+      pz = stof(position.substr(c2 + 1));
+      const bool ranXY = nearlyEqual(py, -999.), ranZ = nearlyEqual(pz, -1.);
+      if (!ranXY) {
+        if ((px * px + py * py) > detector->get_radius() * detector->get_radius() && verbosity > 0)
+          cerr << "WARNING: outside fiducial radius." << endl;
+        if ((px * px + py * py) > detector->get_radmax() * detector->get_radmax()) {
+          if (verbosity > 0) cerr << "\nERROR: outside physical radius!!!" << endl;
+          return EXIT_FAILURE;
+        }
+      }
+      S.fixed_pos = ranXY ? (ranZ ? 0 : 3) : (ranZ ? 2 : 1);
+      S.xyz[0] = px;
+      S.xyz[1] = py;
+      S.xyz[2] = pz;
+    }
+    if ((inField < 0. && inField != -1.) || detector->get_E_gas() < 0.) {  // :863-868
+      if (verbosity > 0)
+        cerr << "\nERROR: Neg field is not permitted. We don't simulate field dir (yet). Put in magnitude.\n";
+      return 1;
+    }
+    if (inField > 12e3 && verbosity > 0)
+      cerr << "\nWARNING: Your field is >12,000 V/cm. No data out here. Are you sure about this?\n";
+
+    if (mono && A.numBins == 1 && A.MCtruthE) {  // :903-909
+      A.MCtruthE = false;
+      if (verbosity > 0) fprintf(stderr, "Simulating a mono-E peak; setting MCtruthE false.\n");
+    }
+    // header :891-947
+    if (verbosity > 0) {
+      cout << "Density = " << rho << " g/mL" << "\t";
+      cout << "central vDrift = " << rc.vD_middle << " mm/us\n";
+      cout << "\t\t\tPRO TIP: neg s2_thr in detector->S2bot!\tW = " << Wq_eV
+           << " eV\tNegative numbers are flagging things below threshold!   phe=(1+P_dphe)*phd & "
+              "phd=phe/(1+P_dphe)\n";
+      if (eMax > kHiEregime) fprintf(stdout, "Energy [keV]");
+      else fprintf(stdout, A.MCtruthE ? "E_truth [keV]" : "E_recon [keV]");
+      if (verbosity >= 2)
+        printf("\tfield [V/cm]\ttDrift [us]\tZ [mm]\tNph\tNe-\tS1 [PE or phe]\tS1_3Dcor [phd]\tspikeC(NON-INT)\tNe-Extr"
+               "\tS2_rawArea [PE]\tS2_3Dcorr [phd]\n");
+      else
+        printf("\tfield [V/cm]\ttDrift [us]\tX,Y,Z [mm]\tNph\tNe-\tS1 [PE or phe]\tS1_3Dcor [phd]\tspikeC(NON-INT)\tNe-"
+               "Extr\tS2_rawArea [PE]\tS2_3Dcorr [phd]\n");
+    }
+
+    // the event loop :676-1414 on the device, in chunks; rows printed as the reference does :1346-1409
+    nb200_analysis ana = A.flat();
+    const uint64_t N = uint64_t(numEvts);
+    const uint64_t chunk = 1u << 20;
+    const uint64_t cap = min<uint64_t>(N, chunk);
+    vector<double> cE(cap), cEtrue(cap), cF(cap), cDt(cap), cSx(cap), cSy(cap), cZ(cap), sig1(cap), sig2(cap);
+    vector<int32_t> cNph(cap), cNe(cap);
+    vector<vector<double>> s1(9, vector<double>(cap)), s2(9, vector<double>(cap));
+    vector<double> all1, all2, allE;  // mono-energetic summaries need every event (GetBand resol, GetEnergyRes)
+    nb200_soa_out o;
+    memset(&o, 0, sizeof o);
+    o.mem_kind = NB200_MEM_HOST;
+    o.signalE = cE.data(); o.energy_kev = cEtrue.data(); o.field = cF.data(); o.driftTime = cDt.data();
+    o.smear_x = cSx.data(); o.smear_y = cSy.data(); o.z_mm = cZ.data(); o.photons = cNph.data();
+    o.electrons = cNe.data(); o.signal1 = sig1.data(); o.signal2 = sig2.data();
+    for (int k = 0; k < 9; ++k) {
+      o.s1[k] = s1[k].data();
+      o.s2[k] = s2[k].data();
+    }
+    vector<uint64_t> acc(ana.numBins), rej(ana.numBins), h2(size_t(ana.numBins) * ana.logBins);
+    vector<int64_t> sS1(ana.numBins), sY(ana.numBins), sY2(ana.numBins), sY3(ana.numBins);
+    nb200_band_hist H;
+    memset(&H, 0, sizeof H);
+    H.numBins = ana.numBins; H.logBins = ana.logBins;
+    H.accepted = acc.data(); H.rejected = rej.data(); H.sumS1 = sS1.data(); H.sumY = sY.data();
+    H.sumY2 = sY2.data(); H.sumY3 = sY3.data(); H.hist2d = h2.data();
+    bool warnedCathode = false;
+    for (uint64_t done = 0; done < N; done += chunk) {
+      const uint64_t m = min<uint64_t>(chunk, N - done);
+      int rc_ = nb200_run(Device::get(), &n.flat(), &M, &ana, &S, &rc, useed, done, m, &o, mono ? nullptr : &H);
+      if (rc_) {  // :1410-1413
+        if (verbosity > 0) cerr << nb200_last_error(Device::get()) << endl;
+        return 1;
+      }
+      for (uint64_t j = 0; j < m; ++j) {
+        if (mono) {
+          all1.push_back(sig1[j]);
+          all2.push_back(sig2[j]);
+          allE.push_back(cE[j]);
+        }
+        if (cZ[j] < detector->get_cathode() && verbosity > 0 && !warnedCathode) {  // :1326-1334
+          warnedCathode = true;
+          fprintf(stderr, "gamma-X i.e. MSSI may be happening. This may be why even high-E eff is <100%%. Check your "
+                          "cathode position definition.\n\n");
+        }
+        bool print = (A.PrintSubThr == 1);
+        if (!print) {  // :1336-1358
+          double s1min[3] = {kPHE_MIN, kPHE_MIN, kPHE_MIN}, s1max[3] = {DBL_MAX, DBL_MAX, DBL_MAX};
+          double s2min = kPHE_MIN, s2max = DBL_MAX;
+          if (A.PrintSubThr == -1) {
+            if (A.usePD >= 0 && A.usePD <= 2) {
+              s1min[A.usePD] = A.minS1;
+              s1max[A.usePD] = A.maxS1;
+            }
+            s2max = A.maxS2;
+            s2min = detector->get_s2_thr();
+          }
+          print = true;
+          const double lo1[9] = {kPHE_MIN, kPHE_MIN, kPHE_MIN, s1min[0], kPHE_MIN, s1min[1], kPHE_MIN, s1min[2], kPHE_MIN};
+          const double hi1[9] = {DBL_MAX, DBL_MAX, DBL_MAX, s1max[0], DBL_MAX, s1max[1], DBL_MAX, s1max[2], DBL_MAX};
+          for (int k = 0; k < 9 && print; ++k) {
+            print = s1[k][j] > lo1[k] && s1[k][j] < hi1[k];
+            double lo2 = (k == 4) ? s2min : kPHE_MIN, hi2 = (k == 7) ? s2max : DBL_MAX;
+            print = print && s2[k][j] > lo2 && s2[k][j] < hi2;
+          }
+        }
+        if (!print) continue;
+        const double keV = A.MCtruthE ? cEtrue[j] : cE[j];
+        if (verbosity >= 2)
+          printf("%.6f\t%.6f\t%.6f\t%.0f\t%d\t%d\t", keV, cF[j], cDt[j], cZ[j], cNph[j], cNe[j]);
+        else
+          printf("%.6f\t%.6f\t%.6f\t%.0f, %.0f, %.0f\t%d\t%d\t", keV, cF[j], cDt[j], cSx[j], cSy[j], cZ[j], cNph[j],
+                 cNe[j]);
+        if (keV > 10. * kHiEregime || s1[5][j] > A.maxS1 || s2[7][j] > A.maxS2) {  // :1390-1396
+          printf("%e\t%e\t%e\t", s1[2][j], s1[5][j], s1[7][j]);
+          printf("%lli\t%e\t%e\n", (long long int)s2[0][j], s2[4][j], s2[7][j]);
+        } else {
+          printf("%.6f\t%.6f\t%.6f\t", s1[2][j], s1[5][j], s1[7][j]);
+          printf("%i\t%.6f\t%.6f\n", (int)s2[0][j], s2[4][j], s2[7][j]);
+        }
+      }
+    }
+
+    if (verbosity >= 0) {  // :1422-1504
+      if (!mono) {
+        vector<double> band(size_t(ana.numBins) * 7);
+        nb200_band_finalize(&ana, &H, band.data());
+        fprintf(stderr, "Bin Center\tBin Actual\tHist Mean\tMean Error\tHist Sigma\tSkewness\t\tEff[%%>thr]\n");
+        bool warned = false;
+        for (int j = 0; j < ana.numBins; ++j) {
+          const double* b = &band[7 * size_t(j)];
+          fprintf(stderr, "%lf\t%lf\t%lf\t%lf\t%lf\t%lf\t\t%lf\n", b[0], b[1], b[2], b[4], b[3], b[6], b[5] * 100.);
+          bool bad = false;
+          for (int k = 0; k < 6; ++k) bad = bad || b[k] <= 0.0 || std::isnan(b[k]);
+          if (bad && !warned && verbosity > 0) {
+            cerr << "WARNING: Insufficient number of events to populate some bins. Adjust minS1/maxS1/minS2/maxS2, up "
+                    "the stats, change E range\n";
+            warned = true;
+          }
+        }
+      } else {  // GetBand(resol=true) + GetEnergyRes :1456-1503, 1582-1644
+        double nPts = 0, m1 = 0, m2 = 0;
+        for (size_t i = 0; i < all1.size(); ++i)
+          if (all1[i] >= 0. && all2[i] >= 0.) {
+            m1 += all1[i];
+            m2 += all2[i];
+            ++nPts;
+          }
+        double total = double(all1.size());
+        double eff = nPts / total;
+        m1 /= nPts;
+        m2 /= nPts;
+        double v1 = 0, v2 = 0;
+        for (size_t i = 0; i < all1.size(); ++i) {
+          if (all1[i] > 0. && all2[i] > 0.0) v1 += pow(all1[i] - m1, 2.);
+          if (all1[i] >= 0. && all2[i] >= 0.) v2 += pow(all2[i] - m2, 2.);
+        }
+        v1 = sqrt(v1 / (nPts - 1.));
+        v2 = sqrt(v2 / (nPts - 1.));
+        double eN = 0, eM = 0, eV = 0;
+        for (double e : allE)
+          if (e > 0.) {
+            eM += e;
+            ++eN;
+          }
+        eM /= eN;
+        for (double e : allE)
+          if (e > 0.) eV += pow(eM - e, 2.);
+        eV = sqrt(eV / (eN - 1.));
+        const bool nrlike = type_num < 7;
+        if (verbosity > 0)
+          fprintf(stderr, nrlike ? "S1 Mean\t\tS1 Res [%%]\tS2 Mean\t\tS2 Res [%%]\tEc [keVnr]\tEc Res[%%]\tEff[%%>thr]\tEc "
+                                   "[keVee]\n"
+                                 : "S1 Mean\t\tS1 Res [%%]\tS2 Mean\t\tS2 Res [%%]\tEc Mean\t\tEc Res[%%]\tEff[%%>thr]\n");
+        fprintf(stderr, "%lf\t%lf\t%lf\t%lf\t%lf\t%lf\t%lf\t", m1, v1 / m1 * 100., m2, v2 / m2 * 100., eM, eV / eM * 100.,
+                (eN / total) * 100.);
+        (void)eff;
+        fprintf(stderr, "\n");
+      }
+    }
+    return 0;
+  } catch (exception& e) {
+    if (analysis.verbosity > 0) cerr << e.what() << endl;
+    return 1;
+  }
+}
+
+// ---- main(): execNEST.cpp:40-256 (the non-loopNEST branch) ------------------------------------------
+int nest_b200_cli::main_like(VDetector* detector, int argc, char** argv) {
+  Analysis& A = analysis;
+  if (A.verbosity > 0) cerr << "*** Detector definition message ***" << endl;
+  if (A.verbosity > 0) cerr << "You are currently using the " << detector->getName() << " detector." << endl << endl;
+  if (argc < 7) {
+    cout << "This program takes 6 (or 7) inputs, with Z position in mm from bottom of detector:" << endl;
+    cout << "\t./execNEST numEvts type_interaction E_min[keV] E_max[keV] field_drift[V/cm] x,y,z-position[mm] "
+            "{optional:seed}"
+         << endl << endl;
+    cout << "For 8B, numEvts is kg-days of exposure with everything else same. For WIMPs:" << endl;
+    cout << "\t./execNEST exposure[kg-days] {WIMP} m[GeV] x-sect[cm^2] field_drift[V/cm] x,y,z-position[mm] "
+            "{optional:seed}"
+         << endl << endl;
+    return 1;
+  }
+  double numEvts = atof(argv[1]);
+  if (numEvts <= 0.) {
+    if (A.verbosity > 0) cerr << "ERROR, you must simulate at least one event, or non-zero kg*days" << endl;
+    return 1;
+  }
+  string type = argv[2];
+  double eMin = atof(argv[3]), eMax = atof(argv[4]), inField = atof(argv[5]);
+  string position = argv[6], posiMuon = argv[4];
+  double fPos = atof(argv[6]);
+  int seed = 1;
+  bool no_seed = false;
+  if (argc == 8) {  // the 7th argument is both seed and multFact (:177-180)
+    multFact = atof(argv[7]);
+    seed = atoi(argv[7]);
+  } else
+    no_seed = true;
+  // the CLI's own model vectors (:185-249), not the NEST.hh defaults
+  NRERWidthsParam = {0.4, 0.4, 0.04, 0.50, 0.19, 2.25, -0.00050, 0.03290, 2.629, 0.2964, -.3343, 0.0000, 0.0000};
+  NRYieldsParam = {11., 1.1, 0.0480, -0.0533, 12.6, 0.3, 2., 0.3, 2., 0.5, 1.0, 1.0};
+  ERYieldsParam = default_ERYieldsParam;
+  return execNEST(detector, numEvts, type, eMin, eMax, inField, position, posiMuon, fPos, seed, no_seed, 0.00);
+}

@@ -1,0 +1,202 @@
+// NEST_b200.hh -- host-side mirror of the reference's operator API for the accelerated path.
+//
+// Same names, argument meaning and error behaviour as the reference (NESTCollaboration/nest):
+//   VDetector              include/Detectors/VDetector.hh:18-225  (getters/setters + Fit* virtuals)
+//   INTERACTION_TYPE, YieldResult, S1/S2CalculationMode   include/NEST/NEST.hh:133-178
+//   NESTObservableArray, runNESTvec(), execNEST()          include/NEST/execNEST.hh:10-87
+//   NESTcalc::{SetDensity, SetDriftVelocity, CalculateG2, WorkFunction, GetYields}  NEST.hh:214-457
+// so that a program written against the reference recompiles against this header and runs the
+// event loop on the GPU through the C-ABI (include/nest_b200.h).  User detectors subclass VDetector
+// exactly as before; their virtual position maps are tabulated once (nest_b200_flatten.hh).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "nest_b200.h"
+
+#define NB_DET_SCALAR(T, name, dflt)       \
+ protected:                                \
+  T name = dflt;                           \
+                                           \
+ public:                                   \
+  T get_##name() const { return name; }    \
+  void set_##name(T v) { name = v; }
+
+class VDetector {
+ public:
+  VDetector() = default;
+  virtual ~VDetector() = default;
+  virtual void Initialization() {}
+  std::string getName() const { return name; }
+
+  typedef enum { fold = 0, unfold = 1 } LCE;
+  virtual double FitS1(double, double, double, LCE) { return 1.; }
+  virtual double FitEF(double, double, double) { return 730.; }
+  virtual std::vector<double> FitDirEF(double, double, double) { return {0, 0, 1}; }
+  virtual double FitS2(double, double, LCE) { return 1.; }
+  virtual std::vector<double> FitTBA(double, double, double) { return {0.5, 0.5}; }
+
+  const double* get_noiseBaseline() const { return noiseBaseline; }
+  const double* get_noiseLinear() const { return noiseLinear; }
+  const double* get_noiseQuadratic() const { return noiseQuadratic; }
+  void set_noiseBaseline(double a, double b, double c, double d) {
+    noiseBaseline[0] = a; noiseBaseline[1] = b; noiseBaseline[2] = c; noiseBaseline[3] = d;
+  }
+  void set_noiseLinear(double a, double b) { noiseLinear[0] = a; noiseLinear[1] = b; }
+  void set_noiseQuadratic(double a, double b) { noiseQuadratic[0] = a; noiseQuadratic[1] = b; }
+
+  // defaults: VDetector.hh:157-224
+  NB_DET_SCALAR(double, g1, 0.0760)
+  NB_DET_SCALAR(double, sPEres, 0.58)
+  NB_DET_SCALAR(double, sPEthr, 0.35)
+  NB_DET_SCALAR(double, sPEeff, 1.00)
+  NB_DET_SCALAR(double, P_dphe, 0.2)
+  NB_DET_SCALAR(double, coinWind, 100)
+  NB_DET_SCALAR(int, coinLevel, 2)
+  NB_DET_SCALAR(int, numPMTs, 89)
+  NB_DET_SCALAR(bool, OldW13eV, true)
+  NB_DET_SCALAR(double, g1_gas, 0.06)
+  NB_DET_SCALAR(double, s2Fano, 3.61)
+  NB_DET_SCALAR(double, s2_thr, 300.)
+  NB_DET_SCALAR(double, E_gas, 12.)
+  NB_DET_SCALAR(double, eLife_us, 2200.)
+  NB_DET_SCALAR(bool, inGas, false)
+  NB_DET_SCALAR(double, T_Kelvin, 177.)
+  NB_DET_SCALAR(double, p_bar, 2.14)
+  NB_DET_SCALAR(double, dtCntr, 40.)
+  NB_DET_SCALAR(double, dt_min, 20.)
+  NB_DET_SCALAR(double, dt_max, 60.)
+  NB_DET_SCALAR(double, radius, 50.)
+  NB_DET_SCALAR(double, radmax, 50.)
+  NB_DET_SCALAR(double, TopDrift, 150.)
+  NB_DET_SCALAR(double, anode, 152.5)
+  NB_DET_SCALAR(double, gate, 147.5)
+  NB_DET_SCALAR(double, cathode, 1.00)
+  NB_DET_SCALAR(double, PosResFlat, 3.00)
+  NB_DET_SCALAR(double, PosResBase, 70.8364)
+  NB_DET_SCALAR(double, molarMass, 131.293)
+
+ protected:
+  std::string name = "VDetector";
+  double noiseBaseline[4] = {0., 0., 0., 0.};
+  double noiseLinear[2] = {3e-2, 3e-2};
+  double noiseQuadratic[2] = {0., 0.};
+};
+
+namespace NEST {
+
+typedef enum {
+  NR = 0, WIMP = 1, B8 = 2, DD = 3, AmBe = 4, Cf = 5, ion = 6, gammaRay = 7, beta = 8, CH3T = 9, C14 = 10,
+  Kr83m = 11, ppSolar = 12, atmNu = 13, fullGamma = 14, fullGamma_PE = 15, fullGamma_Compton_PP = 16,
+  NoneType = 17
+} INTERACTION_TYPE;
+
+enum class S1CalculationMode { Full, Parametric, Hybrid, Waveform };
+enum class S2CalculationMode { Full, Waveform, WaveformWithEtrain };
+
+struct YieldResult {
+  double PhotonYield, ElectronYield, ExcitonRatio, Lindhard, ElectricField, DeltaT_Scint;
+};
+
+// analysis.hh's compile-time globals as a runtime object (include/NEST/analysis.hh:7-77)
+struct Analysis {
+  int verbosity = 1;
+  short PrintSubThr = 1;
+  bool MCtruthE = false, MCtruthPos = false;
+  S1CalculationMode s1CalculationMode = S1CalculationMode::Hybrid;
+  S2CalculationMode s2CalculationMode = S2CalculationMode::Full;
+  int usePD = 2, useS2 = 0;
+  double minS1 = 1.5, maxS1 = 99.5;
+  int numBins = 98;
+  double minS2 = 42., maxS2 = 1e4, logMax = 3.6, logMin = 0.6;
+  int logBins = 30;
+  double z_step = 0.1, E_step = 5.0;
+  static Analysis G2();  // analysis_G2.hh values
+  nb200_analysis flat() const;
+};
+
+const std::vector<double> default_NRYieldsParam = {11., 1.1, 0.0480, -0.0533, 12.6, 0.3, 2., 0.3, 2., 0.5, 1., 1.};
+const std::vector<double> default_NRERWidthsParam = {0.4, 0.4, 0.04, 0.5, 0.19, 2.25, -0.001,
+                                                     0.046452, 0.45, 0.205, -0.2, 0., 0.};
+const std::vector<double> default_ERYieldsParam = {-1., -1., -1., -1., -1., -1., -1., -1., -1., -1.};
+
+// one GPU context per process (the reference's RandomGen / NESTcalc are process-wide state too)
+class Device {
+ public:
+  static nb200_ctx* get();        // throws std::runtime_error without a CUDA device: no CPU fallback
+  static void check(int rc);      // nonzero -> throw std::runtime_error(nb200_last_error)
+};
+
+class NESTcalc {
+ public:
+  struct Wvalue {
+    double Wq_eV, alpha;
+  };
+  explicit NESTcalc(VDetector* detector);
+  NESTcalc(const NESTcalc&) = delete;
+  NESTcalc& operator=(const NESTcalc&) = delete;
+
+  double SetDensity(double Kelvin, double bara);                                // NEST.cpp:2270
+  double SetDriftVelocity(double Kelvin, double Density, double eField, double Bar = 1.5);  // :2352
+  std::vector<double> CalculateG2(int verbosity = 1);                           // :2065 (prints the banner)
+  static Wvalue WorkFunction(double rho, double MolarMass, bool OldW13eV = true);  // :2829
+
+  // NEST.cpp:1211-1252 on the device; the vector form evaluates n (energy, field) pairs in one launch
+  YieldResult GetYields(INTERACTION_TYPE species, double energy, double density, double dfield, double massNum,
+                        double atomNum, const std::vector<double>& NRYieldsParam = default_NRYieldsParam,
+                        const std::vector<double>& ERYieldsParam = default_ERYieldsParam);
+  std::vector<YieldResult> GetYields(INTERACTION_TYPE species, const std::vector<double>& energy, double density,
+                                     const std::vector<double>& dfield, double massNum, double atomNum,
+                                     const std::vector<double>& NRYieldsParam = default_NRYieldsParam,
+                                     const std::vector<double>& ERYieldsParam = default_ERYieldsParam);
+
+  const nb200_detector& flat();   // the detector flattened for the device (maps tabulated on first use)
+  const nb200_run_consts& prepared(double inField, double z_step = 0.);
+  VDetector* detector() const { return fdetector; }
+
+ protected:
+  VDetector* fdetector;
+
+ private:
+  nb200_detector fdet{};
+  std::vector<double> lut[4];
+  bool flattened = false;
+  nb200_run_consts rc{};
+  double rc_field = -12345.;
+};
+
+}  // namespace NEST
+
+// include/NEST/execNEST.hh:10-65 (vectors filled by store_signals, :259-326)
+class NESTObservableArray {
+ public:
+  std::vector<double> energy_kev, x_mm, y_mm, z_mm;
+  std::vector<int> n_electrons, n_photons;
+  std::vector<int> s1_nhits, s1_nhits_dpe, s1_nhits_thr;
+  std::vector<double> s1r_phe, s1c_phe, s1r_phd, s1c_phd, s1r_spike, s1c_spike;
+  std::vector<int> s2_Nee, s2_Nph, s2_nhits, s2_nhits_dpe;
+  std::vector<double> s2r_phe, s2c_phe, s2r_phd, s2c_phd;
+};
+
+// execNEST.hh:72-87, unchanged signatures (the Waveform modes and calculate_times=true are refused)
+NESTObservableArray runNESTvec(VDetector* detector, NEST::INTERACTION_TYPE particleType, std::vector<double> eList,
+                               std::vector<std::vector<double>> pos3dxyz, double inField = -1.0, int seed = 0,
+                               std::vector<double> ERYieldsParam = NEST::default_ERYieldsParam,
+                               std::vector<double> NRYieldsParam = NEST::default_NRYieldsParam,
+                               std::vector<double> NRERWidthsParam = NEST::default_NRERWidthsParam,
+                               NEST::S1CalculationMode s1mode = NEST::S1CalculationMode::Hybrid,
+                               NEST::S2CalculationMode s2mode = NEST::S2CalculationMode::Full,
+                               bool calculate_times = false);
+
+int execNEST(VDetector* detector, double numEvts, const std::string& type, double eMin, double eMax, double inField,
+             std::string position, const std::string& posiMuon, double fPos, int seed, bool no_seed,
+             double dayNumber);
+
+// state the reference keeps in file-scope globals of execNEST.cpp (:30-38, :185-249)
+namespace nest_b200_cli {
+extern NEST::Analysis analysis;
+extern std::vector<double> NRYieldsParam, NRERWidthsParam, ERYieldsParam;
+extern double multFact;
+int main_like(VDetector* detector, int argc, char** argv);  // execNEST.cpp:40-256
+}  // namespace nest_b200_cli

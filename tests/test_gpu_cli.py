@@ -1,0 +1,120 @@
+"""The execNEST command line on the GPU chain (nest_b200/host/execNEST_b200) against the unmodified
+reference binary: same argv, same stdout/stderr layout, statistically the same numbers."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+from scipy import stats
+
+import refprobe
+from helpers import band_chi2
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "nest_b200", "host", "execNEST_b200")
+
+
+def run(binary, args):
+    r = subprocess.run([binary] + [str(a) for a in args], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    return r.returncode, r.stdout, r.stderr
+
+
+def rows_of(out):
+    rows = []
+    for ln in out.splitlines():
+        f = ln.split("\t")
+        if len(f) == 12 and re.match(r"^-?[0-9]", f[0]):
+            xyz = [float(v) for v in f[3].split(",")]
+            rows.append([float(f[0]), float(f[1]), float(f[2])] + xyz + [float(v) for v in f[4:]])
+    return np.array(rows)
+
+
+def band_of(err):
+    b = []
+    for ln in err.splitlines():
+        f = ln.split()
+        if len(f) == 7 and re.match(r"^[0-9.]+$", f[0]):
+            try:
+                v = [float(x) for x in f]
+            except ValueError:
+                continue
+            # columns: centre, actual, mean, mean error, sigma, skew, eff -> GetBand order
+            b.append([v[0], v[1], v[2], v[4], v[3], v[6] / 100., v[5]])
+    return np.array(b)
+
+
+@pytest.fixture(scope="module")
+def cli():
+    if not os.path.exists(CLI):
+        pytest.skip("nest_b200/host/execNEST_b200 not built (python -c 'import __graft_entry__ as g; g.build()')")
+    if not os.path.exists(refprobe.REF_BIN_LUX):
+        pytest.skip("oracle/_ref/execNEST_ref_lux not built")
+    return CLI
+
+
+@pytest.mark.parametrize("args", [("30000", "ER", "0.1", "20", "180", "-1", "1"),
+                                  ("30000", "NR", "0", "100", "180", "-1", "3"),
+                                  ("20000", "CH3T", "0", "18.5898", "180", "-1", "2")])
+def test_cli_matches_reference_binary(cli, args):
+    rc_g, out_g, err_g = run(cli, args)
+    rc_r, out_r, err_r = run(refprobe.REF_BIN_LUX, args)
+    assert rc_g == 0 and rc_r == 0, (err_g[-400:], err_r[-400:])
+    # same header lines (the g1/g2 banner carries a Monte-Carlo SE mean/width: compare its fixed part)
+    hg = [ln for ln in out_g.splitlines() if not re.match(r"^-?[0-9]", ln)]
+    hr = [ln for ln in out_r.splitlines() if not re.match(r"^-?[0-9]", ln)]
+    assert len(hg) == len(hr)
+    for a, b in zip(hg, hr):
+        if a.startswith("g1 = "):
+            assert a.split("SE_mean")[0] == b.split("SE_mean")[0]
+            se_g = [float(x) for x in re.findall(r"SE_mean,width = ([0-9.]+),([0-9.]+)", a)[0]]
+            se_r = [float(x) for x in re.findall(r"SE_mean,width = ([0-9.]+),([0-9.]+)", b)[0]]
+            assert abs(se_g[0] - se_r[0]) < 0.3 and abs(se_g[1] - se_r[1]) < 0.4
+        else:
+            assert a == b
+    g, r = rows_of(out_g), rows_of(out_r)
+    assert g.shape == r.shape == (int(args[0]), 14)
+    names = ["keV", "field", "dt", "x", "y", "z", "Nph", "Ne", "S1", "S1c", "spikeC", "Nee", "S2", "S2c"]
+    for j, nme in enumerate(names):
+        if np.all(g[:, j] == g[0, j]):
+            assert np.all(r[:, j] == g[0, j]), nme
+            continue
+        p = stats.ks_2samp(g[:, j], r[:, j]).pvalue
+        assert p > 1e-4, (nme, p, g[:, j].mean(), r[:, j].mean())
+    bg, br = band_of(err_g), band_of(err_r)
+    assert bg.shape == br.shape == (98, 7)
+    assert np.array_equal(bg[:, 0], br[:, 0])
+    cm, cw, dof = band_chi2(bg, br)
+    assert cm < 2.5 and cw < 2.5, (cm, cw, dof)
+
+
+def test_cli_errors_like_the_reference(cli):
+    for args in [("0", "NR", "0", "100", "180", "-1"), ("100", "bogus", "0", "100", "180", "-1"),
+                 ("100", "NR", "0", "0", "180", "-1"), ("100", "NR", "0", "100", "-5", "-1"), ("100",)]:
+        rc_g, _, _ = run(cli, args)
+        rc_r, _, _ = run(refprobe.REF_BIN_LUX, args)
+        assert rc_g == rc_r == 1, args
+    rc_g, _, err = run(cli, ("100", "Kr83m", "41.5", "400", "180", "-1"))
+    assert rc_g == 1 and "not part of the GPU path" in err
+
+
+def test_cli_mono_energy_summary(cli):
+    rc_g, out_g, err_g = run(cli, ("20000", "gamma", "10", "10", "180", "-1", "1"))
+    rc_r, out_r, err_r = run(refprobe.REF_BIN_LUX, ("20000", "gamma", "10", "10", "180", "-1", "1"))
+    assert rc_g == 0 and rc_r == 0
+
+    def summary(err):
+        for ln in err.splitlines():
+            f = ln.split()
+            if len(f) >= 7 and re.match(r"^[0-9.]+$", f[0]):
+                try:
+                    return [float(x) for x in f[:7]]
+                except ValueError:
+                    pass
+        return None
+    sg, sr = summary(err_g), summary(err_r)
+    assert sg is not None and sr is not None
+    # S1 mean, S1 res, S2 mean, S2 res, Ec mean, Ec res, eff: statistical agreement at 2e4 events
+    for a, b, tol in zip(sg, sr, [0.01, 0.05, 0.01, 0.05, 0.01, 0.05, 0.02]):
+        assert abs(a - b) <= tol * abs(b), (sg, sr)
