@@ -127,17 +127,19 @@ NB_D double drift_velocity_dev(const RunParams& P, double eField) {
 }
 
 #define NB_LOCKSTEP() __syncthreads()
-// launch geometry, measured on B200 (tools/sweep_variants.sh): k_post is fastest as ONE 512-thread
-// block per SM (16 warps in lockstep share instruction-cache fills; 128-thread blocks are 35 %
-// slower), k_pre as two 256-thread blocks, k_hits at 64 registers (4 blocks of 256 per SM)
+// launch geometry, measured on B200 (tools/sweep_variants.sh): k_pre and k_post are fastest at 64
+// registers with 32 warps per SM in large lockstep blocks (k_post one 1024-thread block, k_pre two
+// 512-thread blocks: the spills cost less than the FP64 dependency stalls the extra warps hide, and
+// 128-thread blocks are 35 % slower for lack of instruction-cache sharing); k_hits at 64 registers
+// (4 blocks of 256 per SM)
 #ifndef NB_PRE_BLOCK
-#define NB_PRE_BLOCK 256
+#define NB_PRE_BLOCK 512
 #endif
 #ifndef NB_PRE_MINB
 #define NB_PRE_MINB 2
 #endif
 #ifndef NB_POST_BLOCK
-#define NB_POST_BLOCK 512
+#define NB_POST_BLOCK 1024
 #endif
 #ifndef NB_POST_MINB
 #define NB_POST_MINB 1
