@@ -5,6 +5,7 @@
 #include <dlfcn.h>
 
 #include <chrono>
+#include <cfloat>
 #include <cstdio>
 #include <cstdlib>
 #include <random>
@@ -189,6 +190,21 @@ int build_params(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo,
   {
     double t = ceil(det->P_dphe * 4294967296.0 - 0.5);  // (w + 1/2)/2^32 < P_dphe  <=>  w < t
     P->dphe_thr = t <= 0. ? 0ull : (t >= 4294967296.0 ? 4294967296ull : (unsigned long long)t);
+  }
+  {
+    // S = T + N decomposition of the single-phe area (nb_params.h)
+    const double mu = 1. / rc->NewMean, sg = det->sPEres, nb0 = det->noiseBaseline[0], nu = det->noiseBaseline[1];
+    const double var = sg * sg + nu * nu;
+    P->pe_mu = mu + nb0;
+    P->pe_sig = sqrt(var);
+    P->pe_rho = var > 0. ? sg * sg / var : 0.;
+    P->pe_m0 = mu - P->pe_rho * (mu + nb0);
+    P->pe_tau = var > 0. ? sg * fabs(nu) / sqrt(var) : 0.;
+    // P(T <= 0 | S = s) = Phi(-(m0 + rho s)/tau) < 2^-64  <=>  m0 + rho s > 9.1 tau
+    P->pe_cut = P->pe_rho > 0. ? (9.1 * P->pe_tau - P->pe_m0) / P->pe_rho : -DBL_MAX;
+    P->pe_fast = 1.5341205443525465 * P->pe_tau;  // Phi(1.5341205...) = 15/16
+    double t = ceil(det->P_dphe * 16777216.0 - 0.5);
+    P->dphe_thr24 = t <= 0. ? 0u : (t >= 16777216.0 ? 16777216u : uint32_t(t));
   }
   {
     const double sq2 = sqrt(2.);

@@ -265,71 +265,58 @@ struct S1Acc {
   int spike, nphe;
 };
 
-// One PMT hit of the Full S1 loop, NEST.cpp:1367-1429, on its own counter block
-// (seed; event, hit index).  Same distribution as the reference per hit:
-//   * phe = zero-truncated Gaussian(1/NewMean, sPEres) + Gaussian baseline noise; the two
-//     normals are the two outputs of ONE Box-Muller transform (independent N(0,1));
-//   * u > eff kills the area only when eff < 1 (u <= 1 always);
-//   * the double-phe decision uses a 32-bit uniform, and the second photo-electron (17 % of
-//     hits) is computed by s1_hit_second from its own counter block so that the caller can
-//     defer it and run 32 of them together instead of one lane in six;
-//   * -20 ln u < coinWind is tested as u > exp(-coinWind/20) and the draw is skipped when
-//     nHits > coinLevel makes the test irrelevant.
-NB_D double s1_ztg_redraw(uint64_t seed, uint64_t event, uint32_t blk, double mean, double sigma) {
+// ---- the per-hit S1 loop, NEST.cpp:1367-1429 -------------------------------------------------
+// Per PMT hit the reference draws phe = T + N with T a zero-truncated Gaussian(1/NewMean, sPEres)
+// and N the Gaussian baseline noise, kills it with probability 1 - eff, adds a second such
+// photo-electron with probability P_dphe, and counts the hit (spike + area) when the summed area
+// clears sPEthr and, for events with nHits <= coinLevel, a coincidence-window draw.
+//
+// Same distributions, drawn differently (all exact to within the 2^-64 resolution of the
+// reference's own generator):
+//   * a photo-electron area is sampled through its SUM S = T + N ~ N(pe_mu, pe_sig^2), accepted
+//     with probability P(T > 0 | S): one normal per photo-electron instead of two.  Above pe_cut
+//     that probability is 1 - 2^-64 and nothing else is drawn; below it (22 % of LUX hits) T | S is
+//     drawn and the pair redrawn when T <= 0 (0.36 %);
+//     The accept test itself never needs T: it is a Bernoulli(Phi(m/tau)) draw, tried first
+//     against a 4-bit uniform (u4 < 15 accepts when Phi >= 15/16) with the exact residual
+//     probability evaluated (erfc) only when that fails -- 2 % of hits;
+//   * one Box-Muller transform therefore serves TWO hits of an event (cos and sin outputs), and
+//     one Philox block the pair: 48 bits of radius, 24 of angle, 2 x 24 for the double-phe draws,
+//     2 x 4 for the truncation pre-tests;
+//   * hits needing anything more (exact truncation test, second photo-electron, efficiency or
+//     coincidence draws) are queued per warp and finished 32 at a time (k_hits);
+//   * -20 ln u < coinWind is tested as u > exp(-coinWind/20) and only when nHits <= coinLevel.
+enum : uint32_t { HIT_CHK1 = 1u, HIT_DP = 2u, HIT_SPECIAL = 8u };
+
+// exact residual acceptance of a photo-electron sum s that failed the 4-bit pre-test:
+// P(accept) = Phi(m/tau) overall, of which 15/16 was already granted when m >= pe_fast
+NB_D bool pe_accept_exact(const RunParams& P, double sv, double u) {
+  const double m = fma(P.pe_rho, sv, P.pe_m0);
+  double phi;
+  if (P.pe_tau > 0.)
+    phi = 0.5 * erfc(-(m / P.pe_tau) * 0.70710678118654752440);
+  else
+    phi = (m > 0.) ? 1. : 0.;
+  const double p = (m >= P.pe_fast) ? fma(16., phi, -15.) : phi;
+  return u < p;
+}
+
+// joint redraw of (S, T) after a failed truncation check: sequential stream, rare
+__device__ __noinline__ double pe_redraw(uint64_t seed, uint64_t event, uint32_t blk, double pe_mu, double pe_sig,
+                                         double pe_cut, double pe_tau, double pe_rho, double pe_m0) {
   Stream x;
   x.init(seed, event, STREAM_HITX);
   x.blk = blk;
-  double t;
-  int guard = 0;
-  do {
-    t = mean + sigma * normal(x);
-  } while (t <= 0. && ++guard < 60);
-  return t;
-}
-// First photo-electron of hit k: returns phe1 (zeroed when the single-phe efficiency draw loses
-// it, :1381-1386) and whether the photon makes a second one (:1390).
-NB_D double s1_hit_first(const RunParams& P, uint32_t k0, uint32_t k1, uint32_t e0, uint32_t e1,
-                         uint32_t k, double eff, double spe_mean, const double* lntab, bool& dphe) {
-  const nb200_detector& det = P.det;
-  // block 1: radius (64 bits), angle (32 bits), double-phe decision (32 bits)
-  u128 r = philox4x32_10_rk(e0, e1, k, STREAM_HIT, P.rk);
-  double rad = sqrt(2.0 * neg_log_bits(r.x, r.y, lntab));
-  double s, c;
-  sincos_bits(r.z, s, c);
-  double tg = fma(det.sPEres, rad * c, spe_mean);
-  if (tg <= 0.)  // redraw the truncated Gaussian (P ~ 0.4 % at sPEres 0.37)
-    tg = s1_ztg_redraw((uint64_t(k1) << 32) | k0, (uint64_t(e1) << 32) | e0, k * 64u, spe_mean, det.sPEres);
-  double phe1 = tg + fma(det.noiseBaseline[1], rad * s, det.noiseBaseline[0]);
-  dphe = (unsigned long long)r.w < P.dphe_thr;  // (w + 1/2) 2^-32 < P_dphe
-  if (eff < 1.) {  // block 3: the single-phe efficiency decisions (:1381-1386, :1403)
-    u128 t = philox4x32_10_rk(e0, e1, k, STREAM_HIT3, P.rk);
-    if (u32d(t.x) > eff) phe1 = 0.;
+  double sv = pe_mu;
+#pragma unroll 1
+  for (int guard = 0; guard < 60; ++guard) {
+    double zs, zt;
+    normal_pair(x, zs, zt);
+    sv = fma(pe_sig, zs, pe_mu);
+    if (sv > pe_cut) break;
+    if (fma(pe_tau, zt, fma(pe_rho, sv, pe_m0)) > 0.) break;
   }
-  return phe1;
-}
-// coincidence-window draw of hit k (block 2, word w): only events with nHits <= coinLevel need it
-NB_D double s1_hit_ucoin(const RunParams& P, uint32_t e0, uint32_t e1, uint32_t k) {
-  u128 q = philox4x32_10_rk(e0, e1, k, STREAM_HIT2, P.rk);
-  return u32d(q.w);
-}
-// Second photo-electron of a double-phe hit (:1390-1409): returns phe2 and the coincidence draw
-NB_D double s1_hit_second(const RunParams& P, uint32_t k0, uint32_t k1, uint32_t e0, uint32_t e1,
-                          uint32_t k, double eff, double spe_mean, const double* lntab, double& ucoin) {
-  const nb200_detector& det = P.det;
-  u128 q = philox4x32_10_rk(e0, e1, k, STREAM_HIT2, P.rk);
-  ucoin = u32d(q.w);
-  double rad2 = sqrt(2.0 * neg_log_bits(q.x, q.y, lntab));
-  double s2, c2;
-  sincos_bits(q.z, s2, c2);
-  double tg2 = fma(det.sPEres, rad2 * c2, spe_mean);
-  if (tg2 <= 0.)
-    tg2 = s1_ztg_redraw((uint64_t(k1) << 32) | k0, (uint64_t(e1) << 32) | e0, k * 64u + 32u, spe_mean, det.sPEres);
-  double phe2 = tg2 + fma(det.noiseBaseline[1], rad2 * s2, det.noiseBaseline[0]);
-  if (eff < 1.) {
-    u128 t = philox4x32_10_rk(e0, e1, k, STREAM_HIT3, P.rk);
-    if (u32d(t.y) > eff && u32d(t.x) > eff) phe2 = 0.;
-  }
-  return phe2;
+  return sv;
 }
 
 // Parametric S1, NEST.cpp:1432-1481

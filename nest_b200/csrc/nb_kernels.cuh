@@ -274,99 +274,143 @@ __global__ void __launch_bounds__(kPreBlock, NB_PRE_MINB)
   }
 }
 
-// finish one double-phe hit taken from the warp queue: add the second photo-electron, apply the
-// threshold / coincidence test (NEST.cpp:1421-1427) and add to the owning event's accumulators
-NB_D void hit_finish_dphe(const RunParams& P, const int* s_pref, unsigned long long* s_area,
-                          unsigned int* s_spike, uint64_t ev0, int slot, uint32_t k, double phe1,
-                          double spe_mean, const double* lntab) {
+// Per-warp queue of hits that need more than the one normal of the main loop.
+struct HitEntry {  // 16 bytes: one STS.128 / LDS.128 per queued hit
+  double s1;
+  uint32_t k;
+  uint32_t slot_flags;  // slot << 8 | flags
+};
+constexpr int kHitQueueCap = 96;  // <= 31 left over + 64 pushed per pair iteration
+
+// Finish up to 32 queued hits (one per lane): exact truncation tests, second photo-electrons,
+// efficiency and coincidence draws, then the threshold test of NEST.cpp:1421-1427 and the owning
+// event's sums.
+NB_D void hits_finish(const RunParams& P, const int* s_pref, unsigned long long* s_area, unsigned int* s_spike,
+                      uint64_t ev0, const HitEntry* q, int first, int count, int lane, const double* lntab) {
   const nb200_detector& det = P.det;
-  const int ne = s_pref[slot + 1] - s_pref[slot];
-  const double eff = s1_eff(det, ne);
-  const bool need_coin = !(ne > det.coinLevel);
-  const uint64_t ev = ev0 + slot;
-  double ucoin;
-  double phe2 = s1_hit_second(P, uint32_t(P.seed), uint32_t(P.seed >> 32), uint32_t(ev), uint32_t(ev >> 32), k,
-                              eff, spe_mean, lntab, ucoin);
-  double a = phe1 + phe2;
-  if (a > det.sPEthr && (!need_coin || ucoin > P.coin_u_min)) {
-    atomicAdd(&s_area[slot], (unsigned long long)__double2ll_rn(a * NB_AREA_FX));
-    atomicAdd(&s_spike[slot], 1u);
+  if (lane < count) {
+    const HitEntry en = q[first + lane];
+    double s1 = en.s1;
+    const uint32_t k = en.k, flags = en.slot_flags & 0xFFu;
+    const int slot = int(en.slot_flags >> 8);
+    const uint64_t ev = ev0 + slot;
+    const uint32_t e0 = uint32_t(ev), e1 = uint32_t(ev >> 32);
+    // block 2: second photo-electron (radius 64 bits, angle 32) + 20-bit uniform + 4-bit pre-test
+    const u128 r = philox4x32_10_rk(e0, e1, k, STREAM_HIT2, P.rk);
+    if (flags & HIT_CHK1) {
+      if (!pe_accept_exact(P, s1, (double(r.w >> 12) + 0.5) * (1.0 / 1048576.0)))
+        s1 = pe_redraw(P.seed, ev, k * 64u, P.pe_mu, P.pe_sig, P.pe_cut, P.pe_tau, P.pe_rho, P.pe_m0);
+    }
+    double s2 = 0.;
+    if (flags & HIT_DP) {
+      const double rad = sqrt(2.0 * neg_log_bits(r.x, r.y, lntab));
+      double sn, cs;
+      sincos_bits(r.z, sn, cs);
+      s2 = fma(P.pe_sig, rad * cs, P.pe_mu);
+      if (s2 <= P.pe_cut) {
+        const double m2 = fma(P.pe_rho, s2, P.pe_m0);
+        if (m2 < P.pe_fast || ((r.w >> 8) & 0xFu) == 15u) {  // exact test from a block of its own (0.4 % of hits)
+          const u128 t = philox4x32_10_rk(e0, e1, k, STREAM_HIT4, P.rk);
+          if (!pe_accept_exact(P, s2, u53(t.x, t.y)))
+            s2 = pe_redraw(P.seed, ev, k * 64u + 32u, P.pe_mu, P.pe_sig, P.pe_cut, P.pe_tau, P.pe_rho, P.pe_m0);
+        }
+      }
+    }
+    bool pass_coin = true;
+    if (flags & HIT_SPECIAL) {  // sPEeff < 1 and/or nHits <= coinLevel: block 3
+      const int ne = s_pref[slot + 1] - s_pref[slot];
+      const double eff = s1_eff(det, ne);
+      const u128 t = philox4x32_10_rk(e0, e1, k, STREAM_HIT3, P.rk);
+      if (eff < 1.) {  // NEST.cpp:1381-1386, 1403
+        const bool lost1 = u32d(t.x) > eff, lost2 = u32d(t.y) > eff;
+        if (lost1) s1 = 0.;
+        if (lost1 && lost2) s2 = 0.;
+      }
+      if (!(ne > det.coinLevel)) pass_coin = u32d(t.z) > P.coin_u_min;  // :1422-1424
+    }
+    const double a = s1 + s2;
+    if (a > det.sPEthr && pass_coin) {
+      atomicAdd(&s_area[slot], (unsigned long long)__double2ll_rn(a * NB_AREA_FX));
+      atomicAdd(&s_spike[slot], 1u);
+    }
   }
+  __syncwarp();
 }
 
 __global__ void __launch_bounds__(kHitBlock, NB_HIT_MINB)
     k_hits(const __grid_constant__ RunParams P) {
-  __shared__ int s_pref[kHitGroup + 1];
+  __shared__ int s_pref[kHitGroup + 1];   // hit-count prefix (events)
+  __shared__ int s_ppref[kHitGroup + 1];  // pair-count prefix: the flattened work items
   __shared__ unsigned long long s_area[kHitGroup];
   __shared__ unsigned int s_spike[kHitGroup];
   __shared__ unsigned int s_nphe[kHitGroup];
   __shared__ int s_warp[32];
-  // per-warp queue of double-phe hits waiting for their second photo-electron
-  __shared__ double s_qphe[kHitBlock / 32][64];
-  __shared__ uint32_t s_qk[kHitBlock / 32][64];
-  __shared__ uint16_t s_qslot[kHitBlock / 32][64];
+  __shared__ __align__(16) HitEntry s_qe[kHitBlock / 32][kHitQueueCap];
   __shared__ __align__(16) double s_lntab[64];
   if (threadIdx.x < 64) s_lntab[threadIdx.x] = c_lntab[threadIdx.x];
   constexpr int PER = kHitGroup / kHitBlock;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const nb200_detector& det = P.det;
   const Work& W = P.work;
-  const double spe_mean = 1. / P.rc.NewMean;
-  const uint32_t k0 = uint32_t(P.seed), k1 = uint32_t(P.seed >> 32);
   const uint64_t n_groups = (P.n_events + kHitGroup - 1) / kHitGroup;
-  double* qphe = s_qphe[wid];
-  uint32_t* qk = s_qk[wid];
-  uint16_t* qslot = s_qslot[wid];
+  HitEntry* const q = s_qe[wid];
+  const bool all_special = det.sPEeff < 1.;  // efficiency draws: every hit goes through the queue
 
   for (uint64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
     const uint64_t gbase = grp * kHitGroup;
     const uint64_t ev0 = P.first_event + P.chunk_off + gbase;
-    // hit counts of my PER consecutive events -> exclusive prefix over the group
+    // hit counts of my PER consecutive events -> exclusive prefixes (hits and pairs) over the group
     int cnt[PER];
-    int mine = 0;
+    int mine = 0, minep = 0;
 #pragma unroll
     for (int j = 0; j < PER; ++j) {
       const uint64_t idx = gbase + uint64_t(tid) * PER + j;
       int n = (idx < P.n_events) ? W.nHits[idx] : 0;
       cnt[j] = n > 0 ? n : 0;
       mine += cnt[j];
+      minep += (cnt[j] + 1) >> 1;
       s_area[tid * PER + j] = 0ull;
       s_spike[tid * PER + j] = 0u;
       s_nphe[tid * PER + j] = 0u;
     }
     int off = block_exclusive_scan<kHitBlock>(mine, s_warp);
+    __syncthreads();
+    int offp = block_exclusive_scan<kHitBlock>(minep, s_warp);
 #pragma unroll
     for (int j = 0; j < PER; ++j) {
       s_pref[tid * PER + j] = off;
+      s_ppref[tid * PER + j] = offp;
       off += cnt[j];
+      offp += (cnt[j] + 1) >> 1;
     }
-    if (tid == kHitBlock - 1) s_pref[kHitGroup] = off;
+    if (tid == kHitBlock - 1) {
+      s_pref[kHitGroup] = off;
+      s_ppref[kHitGroup] = offp;
+    }
     __syncthreads();
-    const int H = s_pref[kHitGroup];
+    const int H = s_ppref[kHitGroup];  // pairs in this group
     const int h0 = int((long long)H * tid / kHitBlock);
     const int h1 = int((long long)H * (tid + 1) / kHitBlock);
     const int len = h1 - h0;
     const int maxlen = __reduce_max_sync(0xffffffffu, len);
-    int e = 0, e_end = 0, ne = 0, k = 0;
-    double eff = 1.;
-    bool need_coin = false;
+    int e = 0, e_end = 0, ne = 0, j = 0;
+    bool special = false;
     uint64_t hev = ev0;
     if (len > 0) {
-      // event owning hit h0: largest e with s_pref[e] <= h0
+      // event owning pair h0: largest e with s_ppref[e] <= h0
       int lo = 0, hi = kHitGroup;
       while (hi - lo > 1) {
         int mid = (lo + hi) >> 1;
-        if (s_pref[mid] <= h0)
+        if (s_ppref[mid] <= h0)
           lo = mid;
         else
           hi = mid;
       }
       e = lo;
-      e_end = s_pref[e + 1];
-      ne = e_end - s_pref[e];
-      k = h0 - s_pref[e];
-      eff = s1_eff(det, ne);
-      need_coin = !(ne > det.coinLevel);
+      e_end = s_ppref[e + 1];
+      ne = s_pref[e + 1] - s_pref[e];
+      j = h0 - s_ppref[e];
+      special = all_special || !(ne > det.coinLevel);
       hev = ev0 + e;
     }
     unsigned long long a_fx = 0ull;
@@ -375,8 +419,9 @@ __global__ void __launch_bounds__(kHitBlock, NB_HIT_MINB)
     for (int i = 0; i < maxlen; ++i) {
       const int h = h0 + i;
       const bool act = i < len;
-      bool dphe = false;
-      double phe1 = 0.;
+      uint32_t fa = 0u, fb = 0u;  // queue flags of the pair's two hits (0 = finished here)
+      double sa = 0., sb = 0.;
+      bool pusha = false, pushb = false;
       if (act) {
         if (h == e_end) {  // crossed into the next event with hits: flush, then advance
           atomicAdd(&s_area[e], a_fx);
@@ -386,47 +431,65 @@ __global__ void __launch_bounds__(kHitBlock, NB_HIT_MINB)
           a_spike = a_nphe = 0u;
           do {
             ++e;
-            e_end = s_pref[e + 1];
+            e_end = s_ppref[e + 1];
           } while (e_end == h);
-          ne = e_end - s_pref[e];
-          k = 0;
-          eff = s1_eff(det, ne);
-          need_coin = !(ne > det.coinLevel);
+          ne = s_pref[e + 1] - s_pref[e];
+          j = 0;
+          special = all_special || !(ne > det.coinLevel);
           hev = ev0 + e;
         }
-        phe1 = s1_hit_first(P, k0, k1, uint32_t(hev), uint32_t(hev >> 32), uint32_t(k), eff, spe_mean, s_lntab, dphe);
-        a_nphe += dphe ? 2u : 1u;
-        if (!dphe) {
-          bool pass = phe1 > det.sPEthr;
-          if (pass && need_coin)
-            pass = s1_hit_ucoin(P, uint32_t(hev), uint32_t(hev >> 32), uint32_t(k)) > P.coin_u_min;
-          if (pass) {
+        // one Philox block and one Box-Muller transform for hits 2j and 2j+1 of this event
+        u128 r = philox4x32_10_rk(uint32_t(hev), uint32_t(hev >> 32), uint32_t(j), STREAM_HIT, P.rk);
+        const double rad = sqrt(2.0 * neg_log_bits(r.x, r.y & 0xFFFF0000u, s_lntab));
+        double sn, cs;
+        sincos_bits(r.z & 0xFFFFFF00u, sn, cs);
+        sa = fma(P.pe_sig, rad * cs, P.pe_mu);
+        sb = fma(P.pe_sig, rad * sn, P.pe_mu);
+        const uint32_t da = ((r.z & 0xFFu) << 16) | (r.w >> 16);
+        const uint32_t db = ((r.w & 0xFFFFu) << 8) | ((r.y >> 8) & 0xFFu);
+        const bool hasb = (2 * j + 1) < ne;
+        const bool dpa = da < P.dphe_thr24, dpb = db < P.dphe_thr24;
+        // truncation pre-test (nb_params.h): above pe_cut nothing to do; below it a 4-bit uniform
+        // settles it unless it is 15 or the acceptance is under 15/16
+        const bool ca = sa <= P.pe_cut && (fma(P.pe_rho, sa, P.pe_m0) < P.pe_fast || ((r.y >> 4) & 0xFu) == 15u);
+        const bool cb = sb <= P.pe_cut && (fma(P.pe_rho, sb, P.pe_m0) < P.pe_fast || (r.y & 0xFu) == 15u);
+        fa = (ca ? HIT_CHK1 : 0u) | (dpa ? HIT_DP : 0u) | (special ? HIT_SPECIAL : 0u);
+        fb = (cb ? HIT_CHK1 : 0u) | (dpb ? HIT_DP : 0u) | (special ? HIT_SPECIAL : 0u);
+        a_nphe += dpa ? 2u : 1u;
+        if (fa == 0u) {
+          if (sa > det.sPEthr) {
             a_spike += 1u;
-            a_fx += (unsigned long long)__double2ll_rn(phe1 * NB_AREA_FX);
+            a_fx += (unsigned long long)__double2ll_rn(sa * NB_AREA_FX);
           }
+        } else
+          pusha = true;
+        if (hasb) {
+          a_nphe += dpb ? 2u : 1u;
+          if (fb == 0u) {
+            if (sb > det.sPEthr) {
+              a_spike += 1u;
+              a_fx += (unsigned long long)__double2ll_rn(sb * NB_AREA_FX);
+            }
+          } else
+            pushb = true;
         }
       }
-      const unsigned m = __ballot_sync(0xffffffffu, dphe);
-      if (m) {
-        if (dphe) {
-          const int pos = qcount + __popc(m & ((1u << lane) - 1u));
-          qphe[pos] = phe1;
-          qk[pos] = uint32_t(k);
-          qslot[pos] = uint16_t(e);
-        }
-        qcount += __popc(m);
+      const unsigned ma = __ballot_sync(0xffffffffu, pusha);
+      const unsigned mb = __ballot_sync(0xffffffffu, pushb);
+      if (ma | mb) {
+        const unsigned lt = (1u << lane) - 1u;
+        if (pusha) q[qcount + __popc(ma & lt)] = HitEntry{sa, uint32_t(2 * j), (uint32_t(e) << 8) | fa};
+        if (pushb) q[qcount + __popc(ma) + __popc(mb & lt)] = HitEntry{sb, uint32_t(2 * j + 1), (uint32_t(e) << 8) | fb};
+        qcount += __popc(ma) + __popc(mb);
         __syncwarp();
-        if (qcount >= 32) {
-          const int j = qcount - 32 + lane;
-          hit_finish_dphe(P, s_pref, s_area, s_spike, ev0, int(qslot[j]), qk[j], qphe[j], spe_mean, s_lntab);
+        while (qcount >= 32) {
           qcount -= 32;
-          __syncwarp();
+          hits_finish(P, s_pref, s_area, s_spike, ev0, q, qcount, 32, lane, s_lntab);
         }
       }
-      ++k;
+      ++j;
     }
-    if (lane < qcount)
-      hit_finish_dphe(P, s_pref, s_area, s_spike, ev0, int(qslot[lane]), qk[lane], qphe[lane], spe_mean, s_lntab);
+    if (qcount > 0) hits_finish(P, s_pref, s_area, s_spike, ev0, q, 0, qcount, lane, s_lntab);  // drain (< 32)
     if (len > 0) {
       atomicAdd(&s_area[e], a_fx);
       atomicAdd(&s_spike[e], a_spike);
@@ -434,8 +497,8 @@ __global__ void __launch_bounds__(kHitBlock, NB_HIT_MINB)
     }
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < PER; ++j) {
-      const int i = j * kHitBlock + tid;  // coalesced
+    for (int jj = 0; jj < PER; ++jj) {
+      const int i = jj * kHitBlock + tid;  // coalesced
       const uint64_t idx = gbase + i;
       if (idx < P.n_events) {
         W.area[idx] = double(s_area[i]) * (1. / NB_AREA_FX);

@@ -41,6 +41,17 @@ struct RunParams {
   double s1_center;      // FitS1(0,0,TopDrift - vD_middle*dtCntr)   NEST.cpp:1317-1321
   double s2_center;      // FitS2(0,0)                               NEST.cpp:1762-1763
   unsigned long long dphe_thr;  // double-phe decision on a 32-bit word w: w < dphe_thr
+  // single photo-electron area phe = T + N, T ~ N(1/NewMean, sPEres^2) truncated to T > 0 and
+  // N ~ N(noiseBaseline[0], noiseBaseline[1]^2) (NEST.cpp:1370-1376), sampled through its sum:
+  // S ~ N(pe_mu, pe_sig^2) accepted with P(T > 0 | S) where T | S ~ N(pe_m0 + pe_rho S, pe_tau^2);
+  // above pe_cut that probability is 1 to within 2^-64 and no second normal is drawn
+  double pe_mu, pe_sig, pe_rho, pe_m0, pe_tau, pe_cut;
+  // below pe_cut the acceptance P(T > 0 | S) = Phi(m/tau), m = pe_m0 + pe_rho S, is first tried
+  // against a 4-bit uniform: for m >= pe_fast = 1.5342 tau (Phi >= 15/16) the draw u4 < 15 accepts
+  // outright; only u4 == 15 or m < pe_fast needs Phi itself (exact residual test in the queue)
+  double pe_fast;
+  uint32_t dphe_thr24;          // double-phe decision on a 24-bit word
+  uint32_t _pad_pe;
   double coin_u_min;     // exp(-coinWind/20): -20 ln u < coinWind <=> u > this  NEST.cpp:1422
   double below_thr_pct;  // Parametric S1 threshold percentile       NEST.cpp:1437-1457
   double recon_mult;     // MultFact prefactor, execNEST.cpp:1179-1182

@@ -27,7 +27,8 @@ enum : uint32_t {
   STREAM_HIT2 = 2,   // S1 PMT hits: second photo-electron of a double-phe hit
   STREAM_HITX = 3,   // S1 PMT hits: rare redraws of the zero-truncated Gaussian
   STREAM_HIT3 = 4,   // S1 PMT hits: single-phe efficiency decisions (sPEeff < 1 only)
-  STREAM_POST = 5,   // per-event scalar draws after the S1 hit loop (k_post)
+  STREAM_POST = 5,
+  STREAM_HIT4 = 6,   // S1 PMT hits: truncation check of a second photo-electron   // per-event scalar draws after the S1 hit loop (k_post)
   STREAM_LAR = 8,
   STREAM_SE = 9,     // CalculateG2's single-electron Monte Carlo
   // each binomial draw owns a stream (the sampler is an out-of-line subroutine)

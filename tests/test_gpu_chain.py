@@ -140,3 +140,61 @@ def test_edge_cases(ctx):
     ana2.numBins = 5000
     with pytest.raises(capi.NestB200Error):
         ctx.run(det, mo, ana2, src, rc, 1, 10)
+
+
+def test_few_hit_s1_area_shape(ctx, ref):
+    """the hit loop draws a photo-electron through its sum S = T + N with an exact accept test
+    instead of the reference's two normals: compare the S1 area of 1-, 2- and 3-hit events at high
+    statistics, where the single-phe shape (truncation, noise, double-phe, threshold) is exposed"""
+    n = 400000
+    xyz = (20.0, 30.0, 280.0)
+    g, _ = gpu_chain(ctx, 21, n, capi.beta, capi.SRC_MONO, 1.5, 1.5, 180.0, 1, xyz, 0, 1.0, 1)
+    r = ref_chain(ref, 22, n, capi.beta, capi.SRC_MONO, 1.5, 1.5, 180.0, 1, xyz, 0, 1.0, 1)
+    S1 = refprobe.S1_0
+    from scipy import stats
+    for hits in (1, 2, 3):
+        a = g[np.abs(g[:, S1 + 0]) == hits]
+        b = r[np.abs(r[:, S1 + 0]) == hits]
+        assert len(a) > 3000 and len(b) > 3000, (hits, len(a), len(b))
+        assert abs(len(a) - len(b)) < 6 * np.sqrt(len(a))
+        for col in (1, 2, 6):      # Nphe, pulse area, spike
+            p = stats.ks_2samp(np.abs(a[:, S1 + col]), np.abs(b[:, S1 + col])).pvalue
+            assert p > P_MIN, (hits, col, p)
+        # fraction of hits below the sPE threshold / lost to the coincidence window
+        fa, fb = (a[:, S1 + 2] == 0).mean(), (b[:, S1 + 2] == 0).mean()
+        assert abs(fa - fb) < 5 * np.sqrt(fb * (1 - fb) / len(b) * 2 + 1e-12), (hits, fa, fb)
+
+
+def _variant_detectors():
+    a = capi.detector("LUX_Run03")        # efficiency draws, 3-fold coincidence, S1 linear noise
+    a.sPEeff, a.coinLevel, a.numPMTs = 0.85, 3, 61
+    a.noiseLinear[0] = 0.03
+    b = capi.detector("LUX_Run03")        # no baseline noise (tau = 0), S2 bottom array, quadratic noise
+    b.noiseBaseline[1] = 0.0
+    b.sPEres, b.P_dphe, b.s2_thr = 0.58, 0.2, -150.0
+    b.noiseQuadratic[0], b.noiseQuadratic[1] = 1e-4, 1e-6
+    c = capi.detector("LUX_Run03")        # large baseline noise with an offset, 1-fold, noise electrons
+    # (a noise-electron draw that drives Ne negative sends the reference's std::binomial_distribution
+    # into undefined behaviour, so keep the added electrons positive)
+    c.noiseBaseline[0], c.noiseBaseline[1], c.noiseBaseline[2], c.noiseBaseline[3] = 0.05, 0.3, 30.0, 2.0
+    c.coinLevel, c.sPEthr, c.coinWind = 1, 0.5, 30.0
+    return {"eff85_3fold": a, "nonoise_s2bottom": b, "bignoise_1fold": c}
+
+
+@pytest.mark.parametrize("which", ["eff85_3fold", "nonoise_s2bottom", "bignoise_1fold"])
+def test_other_detector_parameters_against_oracle(ctx, orc, which):
+    """detector settings that exercise the rarely-taken branches (sPEeff < 1, nCr coincidence,
+    S2-bottom, quadratic noise, zero / large baseline noise): the oracle port takes any flattened
+    detector (it is pinned bit-for-bit to the reference on LUX_Run03)"""
+    det = _variant_detectors()[which]
+    capi.prepare(det, 180.0)
+    n = 80000
+    saved = orc.det
+    try:
+        orc.det = det
+        for species, kind, e0, e1, erm in [(capi.beta, capi.SRC_FLAT, 0.1, 12.0, 0), (capi.NR, capi.SRC_FLAT, 0.0, 60.0, -1)]:
+            g, _ = gpu_chain(ctx, 31, n, species, kind, e0, e1, er_model=erm, det=det)
+            r = ref_chain(orc, 32, n, species, kind, e0, e1, er_model=erm)
+            check(g, r, label="%s species %d" % (which, species))
+    finally:
+        orc.det = saved
