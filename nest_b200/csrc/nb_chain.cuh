@@ -286,7 +286,7 @@ struct S1Acc {
 //   * hits needing anything more (exact truncation test, second photo-electron, efficiency or
 //     coincidence draws) are queued per warp and finished 32 at a time (k_hits);
 //   * -20 ln u < coinWind is tested as u > exp(-coinWind/20) and only when nHits <= coinLevel.
-enum : uint32_t { HIT_CHK1 = 1u, HIT_DP = 2u, HIT_SPECIAL = 8u };
+enum : uint32_t { HIT_CHK1 = 1u, HIT_DP = 2u, HIT_CHK2 = 4u, HIT_SPECIAL = 8u };
 
 // exact residual acceptance of a photo-electron sum s that failed the 4-bit pre-test:
 // P(accept) = Phi(m/tau) overall, of which 15/16 was already granted when m >= pe_fast

@@ -149,7 +149,7 @@ NB_D double drift_velocity_dev(const RunParams& P, double eField) {
 #endif
 constexpr int kPreBlock = NB_PRE_BLOCK;
 constexpr int kPostBlock = NB_POST_BLOCK;
-constexpr int kHitGroup = 1024;  // events per k_hits group
+constexpr int kHitGroup = 512;   // events per k_hits group
 constexpr int kHitBlock = 256;   // threads per k_hits block
 #define NB_AREA_FX 4294967296.0  // 2^32: S1 hit areas are summed in units of 2^-32 phe
 
@@ -280,36 +280,60 @@ struct HitEntry {  // 16 bytes: one STS.128 / LDS.128 per queued hit
   uint32_t k;
   uint32_t slot_flags;  // slot << 8 | flags
 };
-constexpr int kHitQueueCap = 96;  // <= 31 left over + 64 pushed per pair iteration
+// Two queues per warp.  "fast": hits that only need their second photo-electron (17 % of hits) --
+// branch-free finisher.  "slow": everything rare (exact truncation tests, redraws, efficiency and
+// coincidence draws; 2-3 % of hits): rare per lane but frequent per warp, so they are also
+// collected and run 32 at a time instead of one lane at a time inside the fast path.
+constexpr int kFastCap = 96;  // <= 31 left over + 64 pushed per pair iteration
+constexpr int kSlowCap = 64;  // <= 31 left over + 32 handed on by one fast pass
+struct HitQueues {
+  HitEntry* fast;
+  HitEntry* slow;
+  double* slow_s2;
+};
 
-// Finish up to 32 queued hits (one per lane): exact truncation tests, second photo-electrons,
-// efficiency and coincidence draws, then the threshold test of NEST.cpp:1421-1427 and the owning
-// event's sums.
-NB_D void hits_finish(const RunParams& P, const int* s_pref, unsigned long long* s_area, unsigned int* s_spike,
-                      uint64_t ev0, const HitEntry* q, int first, int count, int lane, const double* lntab) {
+NB_D void hit_commit(const RunParams& P, unsigned long long* s_area, unsigned int* s_spike, int slot, double a,
+                     bool pass_coin) {
+  if (a > P.det.sPEthr && pass_coin) {
+    atomicAdd(&s_area[slot], (unsigned long long)__double2ll_rn(a * NB_AREA_FX));
+    atomicAdd(&s_spike[slot], 1u);
+  }
+}
+
+// slow path, up to 32 queued hits: everything the reference does for a hit beyond one normal
+#if 1  // out of line: its register needs must not shape the main loop (3.75 -> 3.28 ms)
+__device__ __noinline__ void hits_finish_slow(
+#else
+NB_D void hits_finish_slow(
+#endif
+const RunParams& P, const int* s_pref, unsigned long long* s_area, unsigned int* s_spike,
+                           uint64_t ev0, const HitQueues& q, int first, int count, int lane, const double* lntab) {
   const nb200_detector& det = P.det;
   if (lane < count) {
-    const HitEntry en = q[first + lane];
+    const HitEntry en = q.slow[first + lane];
     double s1 = en.s1;
     const uint32_t k = en.k, flags = en.slot_flags & 0xFFu;
     const int slot = int(en.slot_flags >> 8);
     const uint64_t ev = ev0 + slot;
     const uint32_t e0 = uint32_t(ev), e1 = uint32_t(ev >> 32);
-    // block 2: second photo-electron (radius 64 bits, angle 32) + 20-bit uniform + 4-bit pre-test
     const u128 r = philox4x32_10_rk(e0, e1, k, STREAM_HIT2, P.rk);
-    if (flags & HIT_CHK1) {
-      if (!pe_accept_exact(P, s1, (double(r.w >> 12) + 0.5) * (1.0 / 1048576.0)))
-        s1 = pe_redraw(P.seed, ev, k * 64u, P.pe_mu, P.pe_sig, P.pe_cut, P.pe_tau, P.pe_rho, P.pe_m0);
-    }
     double s2 = 0.;
-    if (flags & HIT_DP) {
-      const double rad = sqrt(2.0 * neg_log_bits(r.x, r.y, lntab));
-      double sn, cs;
-      sincos_bits(r.z, sn, cs);
-      s2 = fma(P.pe_sig, rad * cs, P.pe_mu);
-      if (s2 <= P.pe_cut) {
-        const double m2 = fma(P.pe_rho, s2, P.pe_m0);
-        if (m2 < P.pe_fast || ((r.w >> 8) & 0xFu) == 15u) {  // exact test from a block of its own (0.4 % of hits)
+    if (flags & HIT_CHK2) {  // came back from the fast finisher: s1 final, s2 drawn, exact test pending
+      s2 = q.slow_s2[first + lane];
+      const u128 t = philox4x32_10_rk(e0, e1, k, STREAM_HIT4, P.rk);
+      if (!pe_accept_exact(P, s2, u53(t.x, t.y)))
+        s2 = pe_redraw(P.seed, ev, k * 64u + 32u, P.pe_mu, P.pe_sig, P.pe_cut, P.pe_tau, P.pe_rho, P.pe_m0);
+    } else {
+      if (flags & HIT_CHK1) {
+        if (!pe_accept_exact(P, s1, (double(r.w >> 12) + 0.5) * (1.0 / 1048576.0)))
+          s1 = pe_redraw(P.seed, ev, k * 64u, P.pe_mu, P.pe_sig, P.pe_cut, P.pe_tau, P.pe_rho, P.pe_m0);
+      }
+      if (flags & HIT_DP) {
+        const double rad = sqrt(2.0 * neg_log_bits(r.x, r.y, lntab));
+        double sn, cs;
+        sincos_bits(r.z, sn, cs);
+        s2 = fma(P.pe_sig, rad * cs, P.pe_mu);
+        if (s2 <= P.pe_cut && (fma(P.pe_rho, s2, P.pe_m0) < P.pe_fast || ((r.w >> 8) & 0xFu) == 15u)) {
           const u128 t = philox4x32_10_rk(e0, e1, k, STREAM_HIT4, P.rk);
           if (!pe_accept_exact(P, s2, u53(t.x, t.y)))
             s2 = pe_redraw(P.seed, ev, k * 64u + 32u, P.pe_mu, P.pe_sig, P.pe_cut, P.pe_tau, P.pe_rho, P.pe_m0);
@@ -328,11 +352,50 @@ NB_D void hits_finish(const RunParams& P, const int* s_pref, unsigned long long*
       }
       if (!(ne > det.coinLevel)) pass_coin = u32d(t.z) > P.coin_u_min;  // :1422-1424
     }
-    const double a = s1 + s2;
-    if (a > det.sPEthr && pass_coin) {
-      atomicAdd(&s_area[slot], (unsigned long long)__double2ll_rn(a * NB_AREA_FX));
-      atomicAdd(&s_spike[slot], 1u);
+    hit_commit(P, s_area, s_spike, slot, s1 + s2, pass_coin);
+  }
+  __syncwarp();
+}
+
+// fast path, up to 32 queued double-phe hits: draw the second photo-electron from the hit's own
+// block; the 0.4 % whose second draw needs the exact truncation test move on to the slow queue
+#ifdef NB_FAST_NOINLINE
+__device__ __noinline__ void hits_finish_fast(
+#else
+NB_D void hits_finish_fast(
+#endif
+const RunParams& P, unsigned long long* s_area, unsigned int* s_spike, uint64_t ev0,
+                           const HitQueues& q, int first, int count, int& scount, int lane, const double* lntab) {
+  bool defer = false;
+  HitEntry en{0., 0u, 0u};
+  double s2 = 0.;
+  if (lane < count) {
+    en = q.fast[first + lane];
+    if ((en.slot_flags & 0xFFu) != HIT_DP) {
+      defer = true;  // rare kinds (exact truncation test, efficiency / coincidence draws): slow queue
+    } else {
+      const int slot = int(en.slot_flags >> 8);
+      const uint64_t ev = ev0 + slot;
+      const u128 r = philox4x32_10_rk(uint32_t(ev), uint32_t(ev >> 32), en.k, STREAM_HIT2, P.rk);
+      const double rad = sqrt(2.0 * neg_log_bits(r.x, r.y, lntab));
+      double sn, cs;
+      sincos_bits(r.z, sn, cs);
+      s2 = fma(P.pe_sig, rad * cs, P.pe_mu);
+      defer = s2 <= P.pe_cut && (fma(P.pe_rho, s2, P.pe_m0) < P.pe_fast || ((r.w >> 8) & 0xFu) == 15u);
+      if (defer)
+        en.slot_flags = (en.slot_flags & 0xFFFFFF00u) | HIT_CHK2;
+      else
+        hit_commit(P, s_area, s_spike, slot, en.s1 + s2, true);
     }
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, defer);
+  if (m) {
+    if (defer) {
+      const int pos = scount + __popc(m & ((1u << lane) - 1u));
+      q.slow[pos] = en;
+      q.slow_s2[pos] = s2;
+    }
+    scount += __popc(m);
   }
   __syncwarp();
 }
@@ -345,7 +408,9 @@ __global__ void __launch_bounds__(kHitBlock, NB_HIT_MINB)
   __shared__ unsigned int s_spike[kHitGroup];
   __shared__ unsigned int s_nphe[kHitGroup];
   __shared__ int s_warp[32];
-  __shared__ __align__(16) HitEntry s_qe[kHitBlock / 32][kHitQueueCap];
+  __shared__ __align__(16) HitEntry s_qf[kHitBlock / 32][kFastCap];
+  __shared__ __align__(16) HitEntry s_qs[kHitBlock / 32][kSlowCap];
+  __shared__ double s_qs2[kHitBlock / 32][kSlowCap];
   __shared__ __align__(16) double s_lntab[64];
   if (threadIdx.x < 64) s_lntab[threadIdx.x] = c_lntab[threadIdx.x];
   constexpr int PER = kHitGroup / kHitBlock;
@@ -353,8 +418,8 @@ __global__ void __launch_bounds__(kHitBlock, NB_HIT_MINB)
   const nb200_detector& det = P.det;
   const Work& W = P.work;
   const uint64_t n_groups = (P.n_events + kHitGroup - 1) / kHitGroup;
-  HitEntry* const q = s_qe[wid];
-  const bool all_special = det.sPEeff < 1.;  // efficiency draws: every hit goes through the queue
+  const HitQueues q{s_qf[wid], s_qs[wid], s_qs2[wid]};
+  const bool all_special = det.sPEeff < 1.;  // efficiency draws: every hit goes through the slow queue
 
   for (uint64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
     const uint64_t gbase = grp * kHitGroup;
@@ -394,8 +459,6 @@ __global__ void __launch_bounds__(kHitBlock, NB_HIT_MINB)
     const int len = h1 - h0;
     const int maxlen = __reduce_max_sync(0xffffffffu, len);
     int e = 0, e_end = 0, ne = 0, j = 0;
-    bool special = false;
-    uint64_t hev = ev0;
     if (len > 0) {
       // event owning pair h0: largest e with s_ppref[e] <= h0
       int lo = 0, hi = kHitGroup;
@@ -410,19 +473,15 @@ __global__ void __launch_bounds__(kHitBlock, NB_HIT_MINB)
       e_end = s_ppref[e + 1];
       ne = s_pref[e + 1] - s_pref[e];
       j = h0 - s_ppref[e];
-      special = all_special || !(ne > det.coinLevel);
-      hev = ev0 + e;
     }
     unsigned long long a_fx = 0ull;
     unsigned int a_spike = 0u, a_nphe = 0u;
-    int qcount = 0;  // warp-uniform
+    int fcount = 0, scount = 0;  // warp-uniform queue fills
     for (int i = 0; i < maxlen; ++i) {
       const int h = h0 + i;
-      const bool act = i < len;
       uint32_t fa = 0u, fb = 0u;  // queue flags of the pair's two hits (0 = finished here)
       double sa = 0., sb = 0.;
-      bool pusha = false, pushb = false;
-      if (act) {
+      if (i < len) {
         if (h == e_end) {  // crossed into the next event with hits: flush, then advance
           atomicAdd(&s_area[e], a_fx);
           atomicAdd(&s_spike[e], a_spike);
@@ -435,11 +494,10 @@ __global__ void __launch_bounds__(kHitBlock, NB_HIT_MINB)
           } while (e_end == h);
           ne = s_pref[e + 1] - s_pref[e];
           j = 0;
-          special = all_special || !(ne > det.coinLevel);
-          hev = ev0 + e;
         }
         // one Philox block and one Box-Muller transform for hits 2j and 2j+1 of this event
-        u128 r = philox4x32_10_rk(uint32_t(hev), uint32_t(hev >> 32), uint32_t(j), STREAM_HIT, P.rk);
+        const uint64_t hev = ev0 + e;
+        const u128 r = philox4x32_10_rk(uint32_t(hev), uint32_t(hev >> 32), uint32_t(j), STREAM_HIT, P.rk);
         const double rad = sqrt(2.0 * neg_log_bits(r.x, r.y & 0xFFFF0000u, s_lntab));
         double sn, cs;
         sincos_bits(r.z & 0xFFFFFF00u, sn, cs);
@@ -448,48 +506,49 @@ __global__ void __launch_bounds__(kHitBlock, NB_HIT_MINB)
         const uint32_t da = ((r.z & 0xFFu) << 16) | (r.w >> 16);
         const uint32_t db = ((r.w & 0xFFFFu) << 8) | ((r.y >> 8) & 0xFFu);
         const bool hasb = (2 * j + 1) < ne;
-        const bool dpa = da < P.dphe_thr24, dpb = db < P.dphe_thr24;
+        const uint32_t sp = (all_special || !(ne > det.coinLevel)) ? HIT_SPECIAL : 0u;
         // truncation pre-test (nb_params.h): above pe_cut nothing to do; below it a 4-bit uniform
         // settles it unless it is 15 or the acceptance is under 15/16
         const bool ca = sa <= P.pe_cut && (fma(P.pe_rho, sa, P.pe_m0) < P.pe_fast || ((r.y >> 4) & 0xFu) == 15u);
         const bool cb = sb <= P.pe_cut && (fma(P.pe_rho, sb, P.pe_m0) < P.pe_fast || (r.y & 0xFu) == 15u);
-        fa = (ca ? HIT_CHK1 : 0u) | (dpa ? HIT_DP : 0u) | (special ? HIT_SPECIAL : 0u);
-        fb = (cb ? HIT_CHK1 : 0u) | (dpb ? HIT_DP : 0u) | (special ? HIT_SPECIAL : 0u);
-        a_nphe += dpa ? 2u : 1u;
-        if (fa == 0u) {
-          if (sa > det.sPEthr) {
-            a_spike += 1u;
-            a_fx += (unsigned long long)__double2ll_rn(sa * NB_AREA_FX);
-          }
-        } else
-          pusha = true;
-        if (hasb) {
-          a_nphe += dpb ? 2u : 1u;
-          if (fb == 0u) {
-            if (sb > det.sPEthr) {
-              a_spike += 1u;
-              a_fx += (unsigned long long)__double2ll_rn(sb * NB_AREA_FX);
-            }
-          } else
-            pushb = true;
+        fa = (ca ? HIT_CHK1 : 0u) | (da < P.dphe_thr24 ? HIT_DP : 0u) | sp;
+        fb = hasb ? ((cb ? HIT_CHK1 : 0u) | (db < P.dphe_thr24 ? HIT_DP : 0u) | sp) : 0u;
+        a_nphe += 1u + ((fa >> 1) & 1u) + (hasb ? 1u + ((fb >> 1) & 1u) : 0u);
+        if (fa == 0u && sa > det.sPEthr) {
+          a_spike += 1u;
+          a_fx += (unsigned long long)__double2ll_rn(sa * NB_AREA_FX);
+        }
+        if (hasb && fb == 0u && sb > det.sPEthr) {
+          a_spike += 1u;
+          a_fx += (unsigned long long)__double2ll_rn(sb * NB_AREA_FX);
         }
       }
-      const unsigned ma = __ballot_sync(0xffffffffu, pusha);
-      const unsigned mb = __ballot_sync(0xffffffffu, pushb);
+      // queue the unfinished hits (the fast finisher passes the rare kinds on to the slow queue)
+      const unsigned ma = __ballot_sync(0xffffffffu, fa != 0u), mb = __ballot_sync(0xffffffffu, fb != 0u);
       if (ma | mb) {
         const unsigned lt = (1u << lane) - 1u;
-        if (pusha) q[qcount + __popc(ma & lt)] = HitEntry{sa, uint32_t(2 * j), (uint32_t(e) << 8) | fa};
-        if (pushb) q[qcount + __popc(ma) + __popc(mb & lt)] = HitEntry{sb, uint32_t(2 * j + 1), (uint32_t(e) << 8) | fb};
-        qcount += __popc(ma) + __popc(mb);
+        if (fa) q.fast[fcount + __popc(ma & lt)] = HitEntry{sa, uint32_t(2 * j), (uint32_t(e) << 8) | fa};
+        if (fb) q.fast[fcount + __popc(ma) + __popc(mb & lt)] = HitEntry{sb, uint32_t(2 * j + 1), (uint32_t(e) << 8) | fb};
+        fcount += __popc(ma) + __popc(mb);
         __syncwarp();
-        while (qcount >= 32) {
-          qcount -= 32;
-          hits_finish(P, s_pref, s_area, s_spike, ev0, q, qcount, 32, lane, s_lntab);
+        while (fcount >= 32) {
+          fcount -= 32;
+          hits_finish_fast(P, s_area, s_spike, ev0, q, fcount, 32, scount, lane, s_lntab);
+          while (scount >= 32) {
+            scount -= 32;
+            hits_finish_slow(P, s_pref, s_area, s_spike, ev0, q, scount, 32, lane, s_lntab);
+          }
         }
       }
       ++j;
     }
-    if (qcount > 0) hits_finish(P, s_pref, s_area, s_spike, ev0, q, 0, qcount, lane, s_lntab);  // drain (< 32)
+    // drain (the fast drain may add to the slow queue)
+    if (fcount > 0) hits_finish_fast(P, s_area, s_spike, ev0, q, 0, fcount, scount, lane, s_lntab);
+    while (scount > 0) {
+      const int c = min(scount, 32);
+      scount -= c;
+      hits_finish_slow(P, s_pref, s_area, s_spike, ev0, q, scount, c, lane, s_lntab);
+    }
     if (len > 0) {
       atomicAdd(&s_area[e], a_fx);
       atomicAdd(&s_spike[e], a_spike);
