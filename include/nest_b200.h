@@ -333,6 +333,13 @@ int nb200_fp64_peak(nb200_ctx* ctx, double* tflops);
  * pointers.  Used by tests/test_gpu_hitmath.py to hold them to 1e-15 against libm. */
 int nb200_debug_hitmath(nb200_ctx* ctx, size_t n, const uint32_t* bits3, double* out3);
 
+/* Test hook: `count` draws of the chain's binomial sampler (the device replacement of
+ * RandomGen::binom_draw, src/RandomGen.cpp:132-134) with n trials of probability p, draw i on
+ * the stream of event first_event + i; out = count int64 on the host.
+ * tests/test_gpu_samplers.py compares the histogram with the exact pmf. */
+int nb200_debug_binomial(nb200_ctx* ctx, uint64_t seed, uint64_t first_event, size_t count, int64_t n,
+                         double p, int64_t* out);
+
 /* counters for the bench: kernels launched by this context since creation */
 uint64_t nb200_launch_count(const nb200_ctx* ctx);
 

@@ -1151,6 +1151,23 @@ int nb200_debug_hitmath(nb200_ctx* c, size_t n, const uint32_t* bits3, double* o
   return 0;
 }
 
+int nb200_debug_binomial(nb200_ctx* c, uint64_t seed, uint64_t first_event, size_t count, int64_t n, double p,
+                         int64_t* out) {
+  if (!c || !out) return NB200_EINVAL;
+  if (count == 0) return 0;
+  NB_CUDA(c, cudaSetDevice(c->device));
+  long long* dout = nullptr;
+  NB_CUDA(c, cudaMalloc(&dout, count * 8));
+  k_binomial<<<unsigned(std::min<size_t>((count + 255) / 256, 148 * 8)), 256, 0, c->stream>>>(
+      seed, first_event, count, (long long)n, p, dout);
+  ++c->launches;
+  cudaMemcpyAsync(out, dout, count * 8, cudaMemcpyDeviceToHost, c->stream);
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  cudaFree(dout);
+  if (e != cudaSuccess) return fail(c, NB200_ECUDA, cudaGetErrorString(e));
+  return 0;
+}
+
 // ---- liquid argon ---------------------------------------------------------------------------
 
 int nb200_lar(nb200_ctx* c, int species, size_t n, const double* E, const double* field, double density,

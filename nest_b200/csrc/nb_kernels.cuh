@@ -738,6 +738,13 @@ __global__ void k_hitmath(size_t n, const uint32_t* __restrict__ bits, double* _
   }
 }
 
+// k_binomial: the binomial sampler alone (test hook, nb200_debug_binomial)
+__global__ void __launch_bounds__(256) k_binomial(uint64_t seed, uint64_t first, size_t count, long long n, double p,
+                                                  long long* __restrict__ out) {
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < count; i += size_t(gridDim.x) * blockDim.x)
+    out[i] = binomial(seed, first + i, STREAM_BIN_S1, n, p);
+}
+
 // -------------------------------------------------------------------------------------------
 // k_lar: LArNEST::FullCalculation (src/LArNEST.cpp:17-33) for species NR/ER/Alpha
 // -------------------------------------------------------------------------------------------

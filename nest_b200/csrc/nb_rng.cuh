@@ -342,6 +342,9 @@ NB_D double stirling_tail(double k) {
 // binomial sampler: sequential CDF inversion while n*min(p,1-p) < 10, Hormann's BTRS
 // transformed rejection (J. Stat. Comput. Simul. 46 (1993) 101) above.  Draws from its own
 // counter stream (seed; event, stream) so that it can live out of line.
+// (The paper's BTRD refinement -- one-uniform centre, quadratic squeeze, lazy h -- was measured
+// and is SLOWER here: a warp nearly always has some lane in the exact test, so squeezes only add
+// serial latency; the four independent logarithms of the plain test overlap instead.)
 __device__ __noinline__ long long binomial(uint64_t seed, uint64_t event, uint32_t stream, long long n,
                                            double p) {
   if (!(n > 0) || !(p > 0.)) return 0;

@@ -1,0 +1,56 @@
+"""The binomial sampler of the chain (device replacement of RandomGen::binom_draw,
+src/RandomGen.cpp:132-134 = std::binomial_distribution) against the exact pmf.
+
+Every regime of the sampler is covered: CDF inversion (n p < 10), the recursive f(k)/f(m)
+branch of BTRD (small n p q), the squeeze / exact log-pmf branch (large n p q), p > 1/2
+(reflected), and the sizes the chain really draws (S2 photons: n ~ 1e5..1e6)."""
+import numpy as np
+import pytest
+from scipy import stats
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    (5, 0.3), (40, 0.2), (1000, 0.005),            # inversion
+    (60, 0.2), (100, 0.5), (200, 0.07), (150, 0.9),  # BTRD, |k-m| <= 15 almost always
+    (2000, 0.12), (5000, 0.47), (30000, 0.83),      # BTRD, squeeze
+    (250000, 0.094), (1200000, 0.173),              # S2-sized draws
+]
+
+
+@pytest.mark.parametrize("n,p", CASES)
+def test_binomial_matches_pmf(ctx, n, p):
+    count = 4_000_000
+    k = ctx.debug_binomial(n, p, count, seed=12345 + n)
+    assert k.min() >= 0 and k.max() <= n
+    lo, hi = int(k.min()), int(k.max())
+    obs = np.bincount(k - lo, minlength=hi - lo + 1).astype(float)
+    ks = np.arange(lo, hi + 1)
+    exp = stats.binom.pmf(ks, n, p) * count
+    # pool the tails so that every cell expects >= 20 draws
+    keep = exp >= 20
+    i0, i1 = np.argmax(keep), len(keep) - np.argmax(keep[::-1])
+    o = np.concatenate([[obs[:i0].sum()], obs[i0:i1], [obs[i1:].sum()]])
+    e = np.concatenate([[stats.binom.cdf(lo + i0 - 1, n, p) * count], exp[i0:i1],
+                        [stats.binom.sf(lo + i1 - 1, n, p) * count]])
+    m = e > 0
+    chi2 = ((o[m] - e[m]) ** 2 / e[m]).sum()
+    dof = m.sum() - 1
+    pval = stats.chi2.sf(chi2, dof)
+    # moments to ~5 sigma of their sampling error
+    mu, var = n * p, n * p * (1 - p)
+    assert abs(k.mean() - mu) < 5 * np.sqrt(var / count)
+    assert abs(k.var() - var) < 5 * var * np.sqrt(2.0 / count) + 5 * np.sqrt(var / count)
+    assert pval > 1e-4, (n, p, chi2, dof, pval)
+
+
+def test_binomial_edges(ctx):
+    assert (ctx.debug_binomial(0, 0.3, 1000) == 0).all()
+    assert (ctx.debug_binomial(100, 0.0, 1000) == 0).all()
+    assert (ctx.debug_binomial(100, 1.0, 1000) == 100).all()
+    assert (ctx.debug_binomial(-5, 0.5, 1000) == 0).all()
+    # disjoint event ranges give disjoint streams; the same range reproduces
+    a = ctx.debug_binomial(5000, 0.3, 10000, seed=7, first_event=0)
+    b = ctx.debug_binomial(5000, 0.3, 10000, seed=7, first_event=0)
+    c = ctx.debug_binomial(5000, 0.3, 5000, seed=7, first_event=5000)
+    assert (a == b).all() and (a[5000:] == c).all()
