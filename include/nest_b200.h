@@ -146,7 +146,9 @@ int nb200_analysis_default(int which, nb200_analysis* out);
 enum {
   NB200_SRC_MONO = 0, NB200_SRC_FLAT = 1, NB200_SRC_GAUSS = 2, NB200_SRC_EXP = 3,
   NB200_SRC_CH3T = 4, NB200_SRC_DD = 5, NB200_SRC_B8 = 6, NB200_SRC_LIST = 7,
-  NB200_SRC_WIMP = 8, NB200_SRC_AMBE = 9
+  NB200_SRC_WIMP = 8, NB200_SRC_AMBE = 9,
+  /* C14_spectrum :60-108, Cf_spectrum :169-190, ppSolar_spectrum :213-227, atmNu_spectrum :229-245 */
+  NB200_SRC_C14 = 10, NB200_SRC_CF = 11, NB200_SRC_PPSOLAR = 12, NB200_SRC_ATMNU = 13
 };
 
 typedef struct nb200_source {
@@ -207,6 +209,8 @@ typedef struct nb200_soa_out {
   double *s2[9];
   double *signal1, *signal2, *signalE; /* band inputs; keV_recon */
   double *Nph_mean, *Ne_mean;          /* yields.PhotonYield / ElectronYield */
+  double *deltaT_ns;                   /* yields.DeltaT_Scint: Kr83m decay separation (-999 otherwise) */
+  double *keVee;                       /* this event's term of the keVee sum, execNEST.cpp:1239-1240 */
 } nb200_soa_out;
 
 /* Band accumulator = what GetBand (execNEST.cpp:1508-1621) reduces, kept as exact

@@ -20,7 +20,7 @@ NoneType = 17
 S1_FULL, S1_PARAMETRIC, S1_HYBRID = 0, 1, 2
 MAP_CONST, MAP_LUX_RUN03, MAP_LUT_RZ = 0, 1, 2
 (SRC_MONO, SRC_FLAT, SRC_GAUSS, SRC_EXP, SRC_CH3T, SRC_DD, SRC_B8, SRC_LIST, SRC_WIMP,
- SRC_AMBE) = range(10)
+ SRC_AMBE, SRC_C14, SRC_CF, SRC_PPSOLAR, SRC_ATMNU) = range(14)
 MEM_HOST, MEM_DEVICE = 0, 1
 FX_S1, FX_Y, FX_Y2, FX_Y3 = 2.0 ** 20, 2.0 ** 30, 2.0 ** 26, 2.0 ** 22
 
@@ -83,7 +83,7 @@ class RunConsts(C.Structure):
 
 SOA_F64 = ["energy_kev", "x_mm", "y_mm", "z_mm", "field", "driftTime", "smear_x", "smear_y"]
 SOA_I32 = ["photons", "electrons", "ions", "excitons"]
-SOA_TAIL = ["signal1", "signal2", "signalE", "Nph_mean", "Ne_mean"]
+SOA_TAIL = ["signal1", "signal2", "signalE", "Nph_mean", "Ne_mean", "deltaT_ns", "keVee"]
 
 
 class SoaOut(C.Structure):

@@ -141,7 +141,7 @@ int validate(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo, con
     return fail(c, NB200_EINVAL, "ERROR: Too many bins. Decrease numBins (analysis.hh) or increase NUMBINS_MAX");
   if (ana->s1mode < NB200_S1_FULL || ana->s1mode > NB200_S1_HYBRID || ana->s2mode != NB200_S2_FULL)
     return fail(c, NB200_EINVAL, "Waveform S1/S2 calculation modes are not part of this path");
-  if (src->species == NB200_Kr83m || src->species > NB200_atmNu)
+  if (src->species < 0 || src->species > NB200_atmNu)
     return fail(c, NB200_EINVAL, "species not supported by the GPU chain");
   if (src->inField < 0. && src->inField != -1. && !src->vec_mode)  // execNEST.cpp:863-868
     return fail(c, NB200_EINVAL, "ERROR: Neg field is not permitted. We don't simulate field dir (yet). Put in magnitude.");
@@ -354,6 +354,7 @@ int check_device_error(nb200_ctx* c) {
   if (h) {
     NB_CUDA(c, cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream));
     if (h & 2) return fail(c, NB200_EINVAL, "species not supported by the GPU chain");
+    if (h & 4) return fail(c, NB200_EPHYSICS, "ERROR: min greater than max");  // NEST.cpp:957-959
     return fail(c, NB200_EPHYSICS, "ERROR: Quanta not conserved. Tell Matthew Immediately!");
   }
   return 0;
@@ -665,7 +666,7 @@ int nb200_yields(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo,
   if (!c) return NB200_EINVAL;
   if (!det || !mo || !E || !field || !out) return fail(c, NB200_EINVAL, "null argument");
   if (n == 0) return 0;
-  if (species == NB200_Kr83m || species > NB200_NoneType) return fail(c, NB200_EINVAL, "species not supported");
+  if (species < 0 || species > NB200_NoneType) return fail(c, NB200_EINVAL, "species not supported");
   NB_CUDA(c, cudaSetDevice(c->device));
   YieldsParams P;
   std::memset(&P, 0, sizeof P);

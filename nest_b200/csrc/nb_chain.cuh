@@ -550,6 +550,64 @@ NB_D double powlaw_spectrum(Stream& g, double xMin, double xMax, double expo) {
   if (xTry > xMax) xTry = xMax;
   return xTry;
 }
+// The less common spectra, one out-of-line subroutine (the chain kernels are instruction-fetch
+// sensitive): C14_spectrum TestSpectra.cpp:60-108, Cf_spectrum :169-190, ppSolar_spectrum
+// :213-227, atmNu_spectrum :229-245.  Each is the reference's box rejection
+// (RandomGen::VonNeumann RandomGen.cpp:140-157): x ~ U(xMin,xMax), y ~ U(0,yMax), keep if y <= f(x).
+__device__ __noinline__ double rare_spectrum(Stream& g, int kind, double xMin, double xMax) {
+  double yMax = 1.;
+  if (kind == NB200_SRC_C14) {
+    if (xMax > 156.) xMax = 156.;
+    if (xMin < 0.) xMin = 0.;
+    yMax = 2.5e9;
+  } else if (kind == NB200_SRC_CF) {
+    if (xMax > 200.) xMax = 200.;
+    if (xMin < DBL_MIN) xMin = DBL_MIN;
+    yMax = 2. * pow(10., 3.7488);
+  } else if (kind == NB200_SRC_PPSOLAR) {
+    if (xMax > 250.) xMax = 250.;
+    if (xMin < 0.00) xMin = 0.00;
+    yMax = 0.000594;
+  } else {
+    if (xMax > 85.) xMax = 85.;
+    if (xMin < 0.0) xMin = 0.0;
+  }
+  for (int it = 0; it < 1000000; ++it) {
+    const double x0 = xMin + (xMax - xMin) * g.uniform();
+    const double y0 = yMax * g.uniform();
+    double f;
+    if (kind == NB200_SRC_C14) {
+      const double m_e = 510.9989461, aa = 0.0072973525664, ZZ = 7., V0 = 0.495, qValue = 156.;
+      double Ee = x0 + m_e;
+      double pe = sqrt(Ee * Ee - m_e * m_e);
+      double dNdE_phasespace = pe * Ee * (qValue - x0) * (qValue - x0);
+      double Ee_screen = Ee - V0;
+      double W_screen = (Ee_screen) / m_e;
+      double p_screen = sqrt(W_screen * W_screen - 1);
+      double WW = (Ee) / m_e;
+      double pp = sqrt(WW * WW - 1);
+      double G_screen = (Ee_screen) / (m_e);
+      double B_screen = sqrt((G_screen * G_screen - 1) / (G_screen * G_screen));
+      double x_screen = (2 * NB_PI * ZZ * aa) / B_screen;
+      double F_nr_screen = W_screen * p_screen / (WW * pp) * x_screen * (1 / (1 - exp(-x_screen)));
+      double F_bb_screen = F_nr_screen * pow(W_screen * W_screen * (1 + 4 * (aa * ZZ) * (aa * ZZ)) - 1,
+                                             sqrt(1 - aa * aa * ZZ * ZZ) - 1);
+      f = dNdE_phasespace * F_bb_screen;
+    } else if (kind == NB200_SRC_CF) {
+      const double l = log10(x0);
+      f = 3.7488 - 0.77942 * l + 1.30300 * (l * l) - 2.75280 * (l * l * l) + 1.57310 * ((l * l) * (l * l)) -
+          0.30072 * ((l * l) * (l * l) * l);
+      f = pow(10., f);
+      f *= 1.9929 - .033214 * x0 + .00032857 * (x0 * x0) - 1.000e-6 * (x0 * x0 * x0);
+    } else if (kind == NB200_SRC_PPSOLAR) {
+      f = 9.2759e-6 - 3.5556e-8 * x0 - 5.4608e-12 * x0 * x0;
+    } else {
+      f = (1. + 0.0041482 * x0 + 0.00079972 * x0 * x0 - 1.0201e-5 * x0 * x0 * x0) * exp(-x0 / 12.355);
+    }
+    if (!(y0 > f)) return x0;
+  }
+  return xMin;
+}
 NB_D int xe_isotope_index(int A) {
   switch (A) {
     case 124: return 0;
@@ -612,6 +670,10 @@ NB_D double sample_energy(Stream& g, const RunParams& P, uint64_t idx) {
       break;
     case NB200_SRC_AMBE: keV = powlaw_spectrum(g, S.eMin, S.eMax, S.par[0]); break;
     case NB200_SRC_WIMP: return wimp_spectrum(g, P);
+    case NB200_SRC_C14:
+    case NB200_SRC_CF: keV = rare_spectrum(g, S.kind, S.eMin, S.eMax); break;
+    case NB200_SRC_PPSOLAR:
+    case NB200_SRC_ATMNU: return rare_spectrum(g, S.kind, S.eMin, S.eMax);  // not clamped (:786-787)
     case NB200_SRC_GAUSS: keV = zero_trunc_gauss(g, S.eMin, S.eMax); break;
     case NB200_SRC_EXP: keV = exponential(g, -S.eMax * log(2.), 0., S.eMin); break;
     default: keV = S.eMin + (S.eMax - S.eMin) * g.uniform(); break;
@@ -653,8 +715,9 @@ NB_D double pow_small(double x, double y) {
 // energy reconstruction execNEST.cpp:1170-1250; returns signalE, keV updated in place
 NB_D double reconstruct_energy(const RunParams& P, const Yields& y, const double* scint,
                                const double* scint2, double signal1, double signal2, double field,
-                               double& keV) {
+                               double& keV, double& keVee) {
   const nb200_detector& det = P.det;
+  keVee = 0.;  // this event's term of the CLI's electron-equivalent energy sum, execNEST.cpp:1239-1240
   const nb200_analysis& A = P.ana;
   const double g1 = det.g1, g2 = fabs(P.rc.g2_params[3]);
   if (!A.MCtruthE) {
@@ -704,6 +767,7 @@ NB_D double reconstruct_energy(const RunParams& P, const Yields& y, const double
             2.2352 * pow(logden, 7.);
         keV = (Nph + Ne) * Wq_eV_alpha * 1e-3 / y.L;
       }
+      keVee = (Nph + Ne) * P.rc.Wq_eV * 1e-3;
     } else
       keV = 0.;
   }

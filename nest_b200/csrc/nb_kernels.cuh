@@ -37,14 +37,19 @@ __global__ void __launch_bounds__(256) k_yields(const __grid_constant__ YieldsPa
       y = yield_er_weighted(E, P.density, F, P.det, P.model.ERYieldsParam);
     else {
       int A2 = 131;
+      double u01 = 0.5;
       const bool nrlike = P.species <= NB200_Cf || P.species == NB200_atmNu;
       if ((nrlike && nearly_equal(P.model.massNum, 0.)) || P.species == NB200_ion) {
         Stream g;
         g.init(P.seed, i, STREAM_MAIN);
         A2 = select_xe_atom(g);
+      } else if (P.species == NB200_Kr83m) {
+        Stream g;
+        g.init(P.seed, i, STREAM_MAIN);
+        u01 = g.uniform();
       }
       y = get_yields(P.species, E, P.density, F, P.model.massNum, P.model.atomNum, A2, P.det, P.model,
-                     &err);
+                     &err, u01);
     }
     if (err) atomicOr(err_flag, err);
     P.out[i] = y.Nph;
@@ -232,8 +237,11 @@ __global__ void __launch_bounds__(kPreBlock, NB_PRE_MINB)
         y = yield_gamma(keV, P.rc.rho, field, det, P.model.multFact);
       else if (P.model.er_model == 2)
         y = yield_er_weighted(keV, P.rc.rho, field, det, P.model.ERYieldsParam);
-      else
-        y = get_yields(sp, keV, P.rc.rho, field, P.model.massNum, P.model.atomNum, A2, det, P.model, &err);
+      else {
+        double u01 = 0.5;
+        if (sp == NB200_Kr83m && !nearly_equal(P.model.massNum, P.model.atomNum)) u01 = g.uniform();
+        y = get_yields(sp, keV, P.rc.rho, field, P.model.massNum, P.model.atomNum, A2, det, P.model, &err, u01);
+      }
     }
     NB_LOCKSTEP();
     if (!cli || keV > 0.001 * P.rc.Wq_eV) q = get_quanta(g, P.seed, ev, y, P.rc.rho, det, P.model, &err);
@@ -252,6 +260,7 @@ __global__ void __launch_bounds__(kPreBlock, NB_PRE_MINB)
     NB_LOCKSTEP();
     if (!active) continue;
 
+    if (P.write_soa && P.soa.deltaT_ns) P.soa.deltaT_ns[gidx] = y.dT;
     W.keV[idx] = keV;
     W.px[idx] = px;
     W.py[idx] = py;
@@ -620,11 +629,11 @@ __global__ void __launch_bounds__(kPostBlock, NB_POST_MINB)
     NB_LOCKSTEP();
     get_s2(g, ev, P, Ne, px, py, pz, sx, sy, dt, field, scint2);
     NB_LOCKSTEP();
-    double signal1 = 0., signal2 = 0., signalE = 0.;
+    double signal1 = 0., signal2 = 0., signalE = 0., keVee = 0.;
     const double keV_true = keV;
     if (cli) {
       select_signals(P.ana, scint, scint2, signal1, signal2);
-      signalE = reconstruct_energy(P, y, scint, scint2, signal1, signal2, field, keV);
+      signalE = reconstruct_energy(P, y, scint, scint2, signal1, signal2, field, keV, keVee);
     }
     NB_LOCKSTEP();
     if (!active) continue;
@@ -679,6 +688,7 @@ __global__ void __launch_bounds__(kPostBlock, NB_POST_MINB)
       if (o.signalE) o.signalE[gidx] = cli ? signalE : keV;
       if (o.Nph_mean) o.Nph_mean[gidx] = y.Nph;
       if (o.Ne_mean) o.Ne_mean[gidx] = y.Ne;
+      if (o.keVee) o.keVee[gidx] = keVee;
     }
   }
   if (band_smem) {

@@ -20,7 +20,7 @@ struct SoaDev {  // nb200_soa_out with device pointers (null = column not writte
   int32_t *photons, *electrons, *ions, *excitons;
   double* s1[9];
   double* s2[9];
-  double *signal1, *signal2, *signalE, *Nph_mean, *Ne_mean;
+  double *signal1, *signal2, *signalE, *Nph_mean, *Ne_mean, *deltaT_ns, *keVee;
 };
 
 // per-event state handed from k_pre to k_hits to k_post (device workspace, one chunk)

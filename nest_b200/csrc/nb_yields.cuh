@@ -340,11 +340,78 @@ NB_D Yields yield_ion(double energy, double density, double dfield, double massN
   return validity(r, energy, Wq_eV);
 }
 
+// NESTcalc::GetYieldKr83m NEST.cpp:954-1044: the 9.4 keV, 32.1 keV or merged 41.5 keV line of
+// 83mKr as a function of the time between the two decays.  That separation is
+// rand_exponential(154.4 ns, minTimeSeparation, maxTimeSeparation) (RandomGen.cpp:72-85) from
+// the uniform u01, or maxTimeSeparation itself when the two are nearly equal.  The 32.1 keV
+// yields are the weighted sum of five GetYieldGamma calls (2, 10, 12, 18, 30 keV).  A rare
+// species: out of line and looped, so that it costs the chain kernels no code they execute.
+__device__ __noinline__ Yields yield_kr83m(double energy, double density, double dfield, double maxT,
+                                           double minT, double u01, const nb200_detector& det, int* err) {
+  if (minT > maxT && (energy < 32.0 || energy >= 32.2)) {  // throws "min greater than max" (:957-959)
+    *err = 4;
+    return Yields{0., 0., 0., 0., 0., 0.};
+  }
+  Wvalue w = work_function(density, det.molarMass, det.OldW13eV != 0);
+  const double Wq_eV = w.Wq_eV;
+  const double halflife = 154.4, ln2 = 0.69314718055994530942;
+  double deltaT_ns;
+  if (nearly_equal(minT, maxT))
+    deltaT_ns = maxT;
+  else {
+    double r_min = 0., r_max = 1.;
+    if (minT >= 0.) r_min = 1. - exp(-minT * ln2 / halflife);
+    if (maxT >= 0.) r_max = 1. - exp(-maxT * ln2 / halflife);
+    double r = (r_max - r_min) * u01 + r_min;
+    deltaT_ns = -log(1. - r) * halflife / ln2;
+  }
+  double Nq_9 = 9.4e3 / Wq_eV;
+  double a1 = -19.575;
+  if (a1 > 0.) a1 = 0.;
+  double a2 = 5.823e-4;
+  double a3 = 69.986 + 3e5 / pow(deltaT_ns, 2.);
+  if (a3 > 87.) a3 = 87.;
+  double Nph_9 = 9.4 * (a1 * a2 * dfield * log(1. + 1. / (a2 * dfield)) + a3);
+  double Ne_9 = Nq_9 - Nph_9;
+  if (Ne_9 < 0.) Ne_9 = 0.;
+  double NphG[5];
+  const double eG[5] = {2., 10., 12., 18., 30.};
+#pragma unroll 1
+  for (int k = 0; k < 5; ++k) NphG[k] = yield_gamma(eG[k], density, dfield, det, 1.).Nph;
+  const double Nph_2 = NphG[0], Nph_10 = NphG[1], Nph_12 = NphG[2], Nph_18 = NphG[3], Nph_30 = NphG[4];
+  double Nph_76 = Nph_30 + Nph_2;
+  double Nph_09 = Nph_18 + Nph_10 + Nph_2 + Nph_2;
+  double Nph_15 = Nph_18 + Nph_12 + Nph_2;
+  double Nph_32 = 0.76 * Nph_76 + 0.15 * Nph_15 + 0.09 * Nph_09;
+  double Ne_32 = 32e3 / Wq_eV - Nph_32;
+  double Nph, Ne;
+  if (energy > 9.35 && energy < 9.45) {
+    Nph = Nph_9;
+    Ne = Ne_9;
+  } else if (energy >= 32.0 && energy < 32.2) {
+    Nph = Nph_32;
+    Ne = Ne_32;
+  } else {  // merged 41.5 keV decay
+    Ne = Ne_9 + Ne_32;
+    Nph = Nph_9 + Nph_32;
+  }
+  Yields r{Nph, Ne, 0., 1., dfield, deltaT_ns};
+  if (!det.OldW13eV) {
+    Ne *= NB_ZurichEXOQ;
+    Nph = (r.Nph + r.Ne) - Ne;
+    r.Nph = Nph;
+    r.Ne = Ne;
+  }
+  r.NexONi = nex_o_ni(energy, w.alpha);
+  return validity(r, energy, Wq_eV);
+}
+
 // NESTcalc::GetYields dispatch NEST.cpp:1211-1252.  A2iso: random Xe isotope, used by NR when
-// massNum ~ 0 (:789-790) and by ion (:864).  unsupported species raise err = 2.
+// massNum ~ 0 (:789-790) and by ion (:864).  u01: uniform for Kr83m's decay-time separation
+// (massNum / atomNum carry max / min separation there, :1238-1239).
 NB_D Yields get_yields(int species, double energy, double density, double dfield, double massNum,
                        double atomNum, int A2iso, const nb200_detector& det, const nb200_model& mo,
-                       int* err) {
+                       int* err, double u01 = 0.5) {
   switch (species) {
     case NB200_NR:
     case NB200_WIMP:
@@ -361,8 +428,7 @@ NB_D Yields get_yields(int species, double energy, double density, double dfield
     case NB200_gammaRay:
       return yield_gamma(energy, density, dfield, det, 1.);
     case NB200_Kr83m:
-      *err = 2;
-      return Yields{0., 0., 0., 0., 0., 0.};
+      return yield_kr83m(energy, density, dfield, massNum, atomNum, u01, det, err);
     default:
       return yield_beta(energy, density, dfield, det, mo.ERYieldsParam, 1.);
   }

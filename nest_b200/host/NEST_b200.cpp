@@ -306,35 +306,72 @@ int execNEST(VDetector* detector, double numEvts, const string& type, double eMi
       numEvts = double(nb200_poisson(0.0026 * numEvts, useed));
     } else if (type == "DD" || type == "D-D") type_num = DD;
     else if (type == "AmBe") type_num = AmBe;
-    else if (type == "alpha") {
+    else if (type == "Cf" || type == "Cf252" || type == "252Cf" || type == "Cf-252") type_num = Cf;
+    else if (type == "ion" || type == "nucleus" || type == "alpha") {
       type_num = ion;
-      M.atomNum = 2;
-      M.massNum = 4;
+      if (type == "alpha") {
+        M.atomNum = 2;
+        M.massNum = 4;
+      } else {  // :500-505
+        cerr << "Atomic Number: ";
+        cin >> M.atomNum;
+        cerr << "Mass Number: ";
+        cin >> M.massNum;
+      }
+      if (M.atomNum == 54.) type_num = NR;  // ATOM_NUM :506
     } else if (type == "gamma" || type == "gammaRay" || type == "x-ray" || type == "xray" || type == "xRay" ||
                type == "X-ray" || type == "Xray" || type == "XRay")
       type_num = gammaRay;
+    else if (type == "Kr83m" || type == "83mKr" || type == "Kr83") type_num = Kr83m;
     else if (type == "CH3T" || type == "tritium") type_num = CH3T;
+    else if (type == "C14" || type == "Carbon14" || type == "14C" || type == "C-14" || type == "Carbon-14")
+      type_num = C14;
     else if (type == "beta" || type == "ER" || type == "Compton" || type == "compton" || type == "electron" ||
              type == "e-")
       type_num = NEST::beta;
-    else if (muon || type == "Kr83m" || type == "83mKr" || type == "Kr83" || type == "C14" || type == "Carbon14" ||
-             type == "14C" || type == "C-14" || type == "Carbon-14" || type == "Cf" || type == "Cf252" ||
-             type == "252Cf" || type == "Cf-252" || type == "pp" || type == "ppsolar" || type == "ppSolar" ||
-             type == "atmNu" || type == "fullGamma" || type == "ion" || type == "nucleus") {
+    else if (type == "pp" || type == "ppsolar" || type == "ppSolar" || type == "pp_Solar" || type == "pp_solar" ||
+             type == "pp-Solar" || type == "pp-solar") {
+      type_num = ppSolar;
+      numEvts = double(nb200_poisson(0.0011794 * numEvts, useed));  // counts per kg-day, 0-250 keVee :535-537
+    } else if (type == "atmNu" || type == "AtmNu" || type == "atm_Nu" || type == "Atm_Nu" || type == "atm-Nu" ||
+               type == "Atm-Nu" || type == "atm_nu" || type == "atm-nu") {
+      type_num = atmNu;
+      numEvts = double(nb200_poisson(1.5764e-7 * numEvts, useed));  // :541-542
+    } else if (muon || type == "fullGamma") {
       if (verbosity > 0)
-        cerr << "ERROR: particle type " << type << " is not part of the GPU path (nest-b200 DESIGN.md section 8); "
+        cerr << "ERROR: particle type " << type << " is not part of the GPU path (nest-b200 DESIGN.md, scope); "
              << "use the reference execNEST for it." << endl;
       return 1;
     } else {
       if (verbosity > 0)
         cerr << "UNRECOGNIZED PARTICLE TYPE!! VALID OPTIONS ARE:\nNR or neutron,\nWIMP,\nB8 or Boron8 or 8Boron or "
-                "8B or Boron-8,\nDD or D-D,\nAmBe,\nalpha,\ngamma or gammaRay,\nx-ray or xray or xRay or X-ray or "
-                "Xray or XRay,\nCH3T or tritium,\nbeta or ER or Compton or compton or electron or e-\n";
+                "8B or Boron-8,\nDD or D-D,\nAmBe,\nCf or Cf252 or 252Cf or Cf-252,\nion or nucleus,\nalpha,\ngamma or "
+                "gammaRay,\nx-ray or xray or xRay or X-ray or Xray or XRay,\nKr83m or 83mKr or Kr83,\nCH3T or "
+                "tritium,\nCarbon14 or 14C or C14 or C-14 or Carbon-14,\nbeta or ER or Compton or compton or "
+                "electron or e-,\npp or ppsolar with many various underscore, hyphen and capitalization "
+                "permutations permitted,\natmNu\n";
       return 1;
     }
-    if (numEvts < 1. && type_num != WIMP && type_num != B8) {  // :578-581
+    if (numEvts < 1. && type_num != WIMP && type_num != B8 && type_num != ppSolar && type_num != atmNu) {  // :578-581
       if (verbosity > 0) cerr << "ERROR, you must simulate at least one event, or non-zero kg*days" << endl;
       return 1;
+    }
+    double maxTimeSep = DBL_MAX;
+    if (type_num == Kr83m) {  // :583-601
+      if (((eMin > 9.35 && eMin < 9.45) || (eMin >= 32. && eMin < 32.2) || (eMin > 41. && eMin <= 41.6)) &&
+          eMin != eMax) {
+        maxTimeSep = eMax;
+        if (eMax <= 0.) {
+          if (verbosity > 0) cerr << "Max t sep must be +." << endl;
+          return 1;
+        }
+      } else {
+        if (verbosity > 0)
+          cerr << "ERROR: For Kr83m, put E_min as 9.4, 32.1, or 41.5 keV and E_max as the max time-separation [ns] "
+                  "between the two decays please."
+               << endl;
+        return 1;
+      }
     }
     if ((eMin < 10. || eMax < 10.) && type_num == gammaRay && verbosity > 0) {  // :603-610
       cerr << "WARNING: Typically beta model works better for ER BG at low energies as in a WS." << endl;
@@ -355,9 +392,13 @@ int execNEST(VDetector* detector, double numEvts, const string& type, double eMi
     (void)g1;
     (void)g2;
     if (type_num < 6) M.massNum = 0;  // :670
+    if (type_num == Kr83m) {           // :671, 1052: max / min time separation ride in massNum / atomNum
+      M.massNum = maxTimeSep;
+      M.atomNum = 0.;  // minTimeSeparation :38
+    }
 
     // source kind :681-790
-    const bool mono = (nearlyEqual(eMin, eMax) && eMin >= 0. && eMax > 0.);
+    const bool mono = (nearlyEqual(eMin, eMax) && eMin >= 0. && eMax > 0.) || type_num == Kr83m;
     S.species = int(type_num);
     S.eMin = eMin;
     S.eMax = eMax;
@@ -368,6 +409,13 @@ int execNEST(VDetector* detector, double numEvts, const string& type, double eMi
       if ((min(eMax, 18.5898) != 18.5898 || max(eMin, 0.) != 0.) && verbosity > 0)
         cerr << "WARNING: Recommended energy range is 0 to " << 18.5898 << " keV" << endl;  // TestSpectra.cpp:37-41
     } else if (type_num == B8) S.kind = NB200_SRC_B8;
+    else if (type_num == C14) {
+      S.kind = NB200_SRC_C14;
+      if ((min(eMax, 156.) != 156. || max(eMin, 0.) != 0.) && verbosity > 0)
+        cerr << "WARNING: Recommended energy range is 0 to " << 156. << " keV" << endl;  // TestSpectra.cpp:70-72
+    } else if (type_num == Cf) S.kind = NB200_SRC_CF;
+    else if (type_num == ppSolar) S.kind = NB200_SRC_PPSOLAR;
+    else if (type_num == atmNu) S.kind = NB200_SRC_ATMNU;
     else if (type_num == AmBe) {
       S.kind = NB200_SRC_AMBE;
       S.par[0] = -0.95351;
@@ -443,6 +491,7 @@ int execNEST(VDetector* detector, double numEvts, const string& type, double eMi
       cout << "\t\t\tPRO TIP: neg s2_thr in detector->S2bot!\tW = " << Wq_eV
            << " eV\tNegative numbers are flagging things below threshold!   phe=(1+P_dphe)*phd & "
               "phd=phe/(1+P_dphe)\n";
+      if (type_num == Kr83m && (eMin < 10. || eMin > 40.)) fprintf(stdout, "t [ns]\t\t");  // :900-901
       if (eMax > kHiEregime) fprintf(stdout, "Energy [keV]");
       else fprintf(stdout, A.MCtruthE ? "E_truth [keV]" : "E_recon [keV]");
       if (verbosity >= 2)
@@ -461,6 +510,8 @@ int execNEST(VDetector* detector, double numEvts, const string& type, double eMi
     vector<double> cE(cap), cEtrue(cap), cF(cap), cDt(cap), cSx(cap), cSy(cap), cZ(cap), sig1(cap), sig2(cap);
     vector<int32_t> cNph(cap), cNe(cap);
     vector<vector<double>> s1(9, vector<double>(cap)), s2(9, vector<double>(cap));
+    vector<double> cDeltaT(cap), cKeVee(cap);
+    double keVee = 0.;
     vector<double> all1, all2, allE;  // mono-energetic summaries need every event (GetBand resol, GetEnergyRes)
     nb200_soa_out o;
     memset(&o, 0, sizeof o);
@@ -468,6 +519,7 @@ int execNEST(VDetector* detector, double numEvts, const string& type, double eMi
     o.signalE = cE.data(); o.energy_kev = cEtrue.data(); o.field = cF.data(); o.driftTime = cDt.data();
     o.smear_x = cSx.data(); o.smear_y = cSy.data(); o.z_mm = cZ.data(); o.photons = cNph.data();
     o.electrons = cNe.data(); o.signal1 = sig1.data(); o.signal2 = sig2.data();
+    o.deltaT_ns = cDeltaT.data(); o.keVee = cKeVee.data();
     for (int k = 0; k < 9; ++k) {
       o.s1[k] = s1[k].data();
       o.s2[k] = s2[k].data();
@@ -488,6 +540,13 @@ int execNEST(VDetector* detector, double numEvts, const string& type, double eMi
         return 1;
       }
       for (uint64_t j = 0; j < m; ++j) {
+        keVee += cKeVee[j];
+        if (mono && done + j < 10 && verbosity > 0) {  // :1160-1168
+          if (s1[3][j] > A.maxS1 || s1[5][j] > A.maxS1 || s1[7][j] > A.maxS1)
+            cerr << "WARNING: Some S1 pulse areas are greater than maxS1" << endl;
+          if (s2[5][j] > A.maxS2 || s2[7][j] > A.maxS2)
+            cerr << "WARNING: Some S2 pulse areas are greater than maxS2" << endl;
+        }
         if (mono) {
           all1.push_back(sig1[j]);
           all2.push_back(sig2[j]);
@@ -521,6 +580,7 @@ int execNEST(VDetector* detector, double numEvts, const string& type, double eMi
         }
         if (!print) continue;
         const double keV = A.MCtruthE ? cEtrue[j] : cE[j];
+        if (type_num == Kr83m && verbosity > 0 && (eMin < 10. || eMin > 40.)) printf("%.6f\t", cDeltaT[j]);  // :1360-1361
         if (verbosity >= 2)
           printf("%.6f\t%.6f\t%.6f\t%.0f\t%d\t%d\t", keV, cF[j], cDt[j], cZ[j], cNph[j], cNe[j]);
         else
@@ -554,24 +614,39 @@ int execNEST(VDetector* detector, double numEvts, const string& type, double eMi
           }
         }
       } else {  // GetBand(resol=true) + GetEnergyRes :1456-1503, 1582-1644
-        double nPts = 0, m1 = 0, m2 = 0;
-        for (size_t i = 0; i < all1.size(); ++i)
-          if (all1[i] >= 0. && all2[i] >= 0.) {
-            m1 += all1[i];
-            m2 += all2[i];
-            ++nPts;
-          }
-        double total = double(all1.size());
-        double eff = nPts / total;
-        m1 /= nPts;
-        m2 /= nPts;
-        double v1 = 0, v2 = 0;
+        // GetBand(S1s, S2s, resol = true, nFold): one bin of infinite width (:1533-1536)
+        const int nFold = detector->get_coinLevel();
+        const double border = (ana.useS2 == 2) ? ana.minS2 : ana.minS1, binWidth = DBL_MAX;
+        const double s1c = border + binWidth / 2.;
+        const double ReqS1 = nFold == 0 ? -DBL_MAX : 0.;
+        double b0 = 0., b1 = 0., b2 = 0., b3 = 0.;
+        vector<double> sel;
         for (size_t i = 0; i < all1.size(); ++i) {
-          if (all1[i] > 0. && all2[i] > 0.0) v1 += pow(all1[i] - m1, 2.);
-          if (all1[i] >= 0. && all2[i] >= 0.) v2 += pow(all2[i] - m2, 2.);
+          if ((fabs(all1[i]) > (s1c - binWidth / 2.) && fabs(all1[i]) <= (s1c + binWidth / 2.)) || !nFold) {
+            if (all1[i] >= ReqS1 && all2[i] >= 0.) {
+              sel.push_back(all2[i]);
+              b2 += all2[i];
+              b0 += all1[i];
+            }
+          }
         }
-        v1 = sqrt(v1 / (nPts - 1.));
-        v2 = sqrt(v2 / (nPts - 1.));
+        const double total = double(all1.size());
+        double numPts = double(sel.size());
+        if (numPts <= 0) {  // :1585-1588
+          for (size_t i = 0; i < all1.size(); ++i) b0 += fabs(all1[i]);
+          numPts = total;
+        }
+        b0 /= numPts;
+        b1 /= numPts;
+        b2 /= numPts;
+        if (numPts > double(sel.size())) numPts = double(sel.size());
+        for (size_t i = 0; i < sel.size(); ++i) b3 += pow(sel[i] - b2, 2.);
+        for (size_t i = 0; i < all1.size(); ++i)
+          if (all1[i] > ReqS1 && all2[i] > 0.0) b1 += pow(all1[i] - b0, 2.);
+        b3 = sqrt(b3 / (numPts - 1.));
+        b1 = sqrt(b1 / (numPts - 1.));
+        const double m1 = b0, v1 = b1, m2 = b2, v2 = b3;
+        // GetEnergyRes :1623-1644
         double eN = 0, eM = 0, eV = 0;
         for (double e : allE)
           if (e > 0.) {
@@ -589,8 +664,23 @@ int execNEST(VDetector* detector, double numEvts, const string& type, double eMi
                                  : "S1 Mean\t\tS1 Res [%%]\tS2 Mean\t\tS2 Res [%%]\tEc Mean\t\tEc Res[%%]\tEff[%%>thr]\n");
         fprintf(stderr, "%lf\t%lf\t%lf\t%lf\t%lf\t%lf\t%lf\t", m1, v1 / m1 * 100., m2, v2 / m2 * 100., eM, eV / eM * 100.,
                 (eN / total) * 100.);
-        (void)eff;
-        fprintf(stderr, "\n");
+        if (nrlike)  // :1465, 1477-1478
+          fprintf(stderr, "%lf\n", (keVee / numEvts) / (eN / total));
+        else
+          fprintf(stderr, "\n");
+        if ((m1 <= 0.0 || v1 <= 0.0 || m2 <= 0.0 || v2 <= 0.0 || std::isnan(m1) || std::isnan(v1) || std::isnan(m2) ||
+             std::isnan(v2)) &&
+            rc.field >= 1.) {  // :1481-1495
+          if (verbosity > 0) {
+            if (numEvts > 1)
+              cerr << "CAUTION: YOUR S1 and/or S2 MIN and/or MAX may be set to be too restrictive, please check.\n";
+            else
+              cerr << "CAUTION: Poor stats. You must have at least 2 events to calculate S1 and S2 and E "
+                      "resolutions.\n";
+          }
+        } else if ((nearlyEqual(eM, eMin) || nearlyEqual(eM, eMax) || eV <= 1E-6) && rc.field >= 1.)
+          if (verbosity > 0)
+            cerr << "If your energy resolution is 0% then you probably still have MC truth energy on." << endl;
       }
     }
     return 0;

@@ -459,6 +459,57 @@ Y GetYieldIon(const nb200_detector& d, double energy, double density, double dfi
   Y r{Nph, Ne, NexONi_, L, dfield, -999};
   return YieldResultValidity(r, energy, Wq_eV);
 }
+Y GetYieldKr83m(const nb200_detector& d, double energy, double density, double dfield, double maxTimeSeparation,
+                double minTimeSeparation) {  // :954-1044
+  if (minTimeSeparation > maxTimeSeparation && (energy < 32.0 || energy >= 32.2))
+    throw std::runtime_error("ERROR: min greater than max");
+  double Wq_eV, alpha;
+  WorkFunction(density, d.molarMass, d.OldW13eV, Wq_eV, alpha);
+  const double deltaT_ns_halflife = 154.4;
+  double deltaT_ns = -999.;
+  if (nearlyEqual(minTimeSeparation, maxTimeSeparation)) deltaT_ns = maxTimeSeparation;
+  if (!nearlyEqual(minTimeSeparation, maxTimeSeparation))
+    deltaT_ns = rand_exponential(deltaT_ns_halflife, minTimeSeparation, maxTimeSeparation);
+  double Nq_9 = 9.4e3 / Wq_eV;
+  double a1 = -19.575;
+  if (a1 > 0.) a1 = 0.;
+  double a2 = 5.823e-4;
+  double a3 = 69.986 + 3e5 / pow(deltaT_ns, 2.);
+  if (a3 > 87.) a3 = 87.;
+  double Nph_9 = 9.4 * (a1 * a2 * dfield * log(1. + 1. / (a2 * dfield)) + a3);
+  double Ne_9 = Nq_9 - Nph_9;
+  if (Ne_9 < 0.) Ne_9 = 0.;
+  double Nph_2 = GetYieldGamma(d, 2., density, dfield).Nph;
+  double Nph_10 = GetYieldGamma(d, 10., density, dfield).Nph;
+  double Nph_12 = GetYieldGamma(d, 12., density, dfield).Nph;
+  double Nph_18 = GetYieldGamma(d, 18., density, dfield).Nph;
+  double Nph_30 = GetYieldGamma(d, 30., density, dfield).Nph;
+  double Nph_76 = Nph_30 + Nph_2;
+  double Nph_09 = Nph_18 + Nph_10 + Nph_2 + Nph_2;
+  double Nph_15 = Nph_18 + Nph_12 + Nph_2;
+  double Nph_32 = 0.76 * Nph_76 + 0.15 * Nph_15 + 0.09 * Nph_09;
+  double Ne_32 = 32e3 / Wq_eV - Nph_32;
+  double Nph, Ne;
+  if (energy > 9.35 && energy < 9.45) {
+    Nph = Nph_9;
+    Ne = Ne_9;
+  } else if (energy >= 32.0 && energy < 32.2) {
+    Nph = Nph_32;
+    Ne = Ne_32;
+  } else {
+    Ne = Ne_9 + Ne_32;
+    Nph = Nph_9 + Nph_32;
+  }
+  Y r{Nph, Ne, 0., 1, dfield, deltaT_ns};
+  if (!d.OldW13eV) {
+    Ne *= kZurichEXOQ;
+    Nph = (r.Nph + r.Ne) - Ne;
+    r.Nph = Nph;
+    r.Ne = Ne;
+  }
+  r.NexONi = NexONi(d, energy, density);
+  return YieldResultValidity(r, energy, Wq_eV);
+}
 Y GetYields(const nb200_detector& d, int species, double energy, double density, double dfield, double massNum,
             double atomNum, const double* NR, const double* ER) {  // :1211-1252
   switch (species) {
@@ -469,7 +520,7 @@ Y GetYields(const nb200_detector& d, int species, double energy, double density,
     case NB200_gammaRay:
       return GetYieldGamma(d, energy, density, dfield);
     case NB200_Kr83m:
-      throw std::runtime_error("Kr83m is outside the restated path");
+      return GetYieldKr83m(d, energy, density, dfield, massNum, atomNum);  // :1238-1239
     default:
       return GetYieldBetaGR(d, energy, density, dfield, ER);
   }
@@ -924,6 +975,76 @@ double DD_spectrum(double xMin, double xMax, double expFall, double peakFrac, do
   }
   return x0;
 }
+double C14_spectrum(double xMin, double xMax) {  // TestSpectra.cpp:60-108
+  double m_e = 510.9989461, aa = 0.0072973525664, ZZ = 7., V0 = 0.495, qValue = 156.;
+  if (xMax > qValue) xMax = qValue;
+  if (xMin < 0.) xMin = 0.;
+  double yMax = 2.5e9;
+  double x0 = xMin + (xMax - xMin) * rand_uniform();
+  double y0 = yMax * rand_uniform();
+  bool again = true;
+  while (again) {
+    double Ee = x0 + m_e;
+    double pe = sqrt(Ee * Ee - m_e * m_e);
+    double dNdE_phasespace = pe * Ee * (qValue - x0) * (qValue - x0);
+    double Ee_screen = Ee - V0;
+    double W_screen = (Ee_screen) / m_e;
+    double p_screen = sqrt(W_screen * W_screen - 1);
+    double WW = (Ee) / m_e;
+    double pp = sqrt(WW * WW - 1);
+    double G_screen = (Ee_screen) / (m_e);
+    double B_screen = sqrt((G_screen * G_screen - 1) / (G_screen * G_screen));
+    double x_screen = (2 * M_PI * ZZ * aa) / B_screen;
+    double F_nr_screen = W_screen * p_screen / (WW * pp) * x_screen * (1 / (1 - exp(-x_screen)));
+    double F_bb_screen =
+        F_nr_screen * pow(W_screen * W_screen * (1 + 4 * (aa * ZZ) * (aa * ZZ)) - 1, sqrt(1 - aa * aa * ZZ * ZZ) - 1);
+    again = VonNeumann(xMin, xMax, 0., yMax, x0, y0, dNdE_phasespace * F_bb_screen);
+  }
+  return x0;
+}
+double Cf_spectrum(double xMin, double xMax) {  // TestSpectra.cpp:169-190, `power` :20-21
+  const double power = 3.7488;
+  if (xMax > 200.) xMax = 200.;
+  if (xMin < DBL_MIN) xMin = DBL_MIN;
+  double yMax = 2. * pow(10., power), yMin = 0.0;
+  double x0 = xMin + (xMax - xMin) * rand_uniform();
+  double y0 = yMax * rand_uniform();
+  bool again = true;
+  while (again) {
+    double l = log10(x0);
+    double FuncValue = power * pow(l, 0.) - 0.77942 * pow(l, 1.) + 1.30300 * pow(l, 2.) - 2.75280 * pow(l, 3.) +
+                       1.57310 * pow(l, 4.) - 0.30072 * pow(l, 5.);
+    FuncValue = pow(10., FuncValue);
+    FuncValue *= 1.9929 - .033214 * pow(x0, 1.) + .00032857 * pow(x0, 2.) - 1.000e-6 * pow(x0, 3.);
+    again = VonNeumann(xMin, xMax, yMin, yMax, x0, y0, FuncValue);
+  }
+  return x0;
+}
+double ppSolar_spectrum(double xMin, double xMax) {  // TestSpectra.cpp:213-227
+  if (xMax > 250.) xMax = 250.;
+  if (xMin < 0.00) xMin = 0.00;
+  double yMax = 0.000594;
+  double x0 = xMin + (xMax - xMin) * rand_uniform();
+  double y0 = yMax * rand_uniform();
+  bool again = true;
+  while (again) {
+    double FuncValue = 9.2759e-6 - 3.5556e-8 * x0 - 5.4608e-12 * x0 * x0;
+    again = VonNeumann(xMin, xMax, 0., yMax, x0, y0, FuncValue);
+  }
+  return x0;
+}
+double atmNu_spectrum(double xMin, double xMax) {  // TestSpectra.cpp:229-245
+  if (xMax > 85.) xMax = 85.;
+  if (xMin < 0.0) xMin = 0.0;
+  double x0 = xMin + (xMax - xMin) * rand_uniform();
+  double y0 = rand_uniform();
+  bool again = true;
+  while (again) {
+    double FuncValue = (1. + 0.0041482 * x0 + 0.00079972 * x0 * x0 - 1.0201e-5 * x0 * x0 * x0) * exp(-x0 / 12.355);
+    again = VonNeumann(xMin, xMax, 0., 1., x0, y0, FuncValue);
+  }
+  return x0;
+}
 double PowLawFit_spectrum(double xMin, double xMax, double expo) {
   double yMax, yMin;
   ++expo;
@@ -1072,6 +1193,10 @@ void orc_spectrum(int kind, uint64_t seed, int n, double eMin, double eMax, doub
     if (kind == NB200_SRC_CH3T) out[i] = CH3T_spectrum(eMin, eMax);
     else if (kind == NB200_SRC_DD) out[i] = DD_spectrum(eMin, eMax, 13., 0.12, 71.2, 20., -20.5);
     else if (kind == NB200_SRC_AMBE) out[i] = PowLawFit_spectrum(eMin, eMax, -0.95351);
+    else if (kind == NB200_SRC_C14) out[i] = C14_spectrum(eMin, eMax);
+    else if (kind == NB200_SRC_CF) out[i] = Cf_spectrum(eMin, eMax);
+    else if (kind == NB200_SRC_PPSOLAR) out[i] = ppSolar_spectrum(eMin, eMax);
+    else if (kind == NB200_SRC_ATMNU) out[i] = atmNu_spectrum(eMin, eMax);
     else out[i] = B8_spectrum(eMin, eMax);
   }
 }
@@ -1123,6 +1248,7 @@ int orc_chain(const nb200_detector* det, const nb200_analysis* ana, uint64_t see
   double massNum = d.molarMass, atomNum = 0;
   if (species == NB200_ion) { massNum = 4; atomNum = 2; }  // "alpha" :498-500
   if (species < 6) massNum = 0;  // :670
+  if (species == NB200_Kr83m) { massNum = eMax; atomNum = 0.; }  // maxTimeSep :583-588,671; minTimeSeparation :38,1052
   std::vector<double> W(widths, widths + nw);
   if (species == NB200_ion) W = {1.00, 1.00, 0., 0.50, 0.19, 0., 1., 0.046452, 0.45, 0.205, -0.2, 0., 0.};  // :1056-1063
   double vD = 0, vD_middle = 0, pos_x = 0, pos_y = 0, pos_z = 0, field, driftTime;
@@ -1130,15 +1256,20 @@ int orc_chain(const nb200_detector* det, const nb200_analysis* ana, uint64_t see
   try {
     for (int j = 0; j < n; ++j) {
       double keV;
-      if (src_kind == NB200_SRC_MONO) keV = eMin;
+      if (src_kind == NB200_SRC_MONO || species == NB200_Kr83m) keV = eMin;  // :681-684
       else if (src_kind == NB200_SRC_CH3T) keV = CH3T_spectrum(eMin, eMax);
       else if (src_kind == NB200_SRC_B8) keV = B8_spectrum(eMin, eMax);
       else if (src_kind == NB200_SRC_DD) keV = DD_spectrum(eMin, eMax, 13., 0.12, 71.2, 20., -20.5);
       else if (src_kind == NB200_SRC_AMBE) keV = PowLawFit_spectrum(eMin, eMax, -0.95351);
+      else if (src_kind == NB200_SRC_C14) keV = C14_spectrum(eMin, eMax);
+      else if (src_kind == NB200_SRC_CF) keV = Cf_spectrum(eMin, eMax);
+      else if (src_kind == NB200_SRC_PPSOLAR) keV = ppSolar_spectrum(eMin, eMax);
+      else if (src_kind == NB200_SRC_ATMNU) keV = atmNu_spectrum(eMin, eMax);
       else if (src_kind == NB200_SRC_GAUSS) keV = rand_zero_trunc_gauss(eMin, eMax);
       else if (src_kind == NB200_SRC_EXP) keV = rand_exponential(-eMax * log(2.), 0., eMin);
       else keV = eMin + (eMax - eMin) * rand_uniform();
-      if (species != NB200_B8 && eMax > 0. && eMin < eMax) {  // :786-790
+      if (species != NB200_B8 && species != NB200_Kr83m && species != NB200_ppSolar && species != NB200_atmNu &&
+          eMax > 0. && eMin < eMax) {  // :786-790
         if (keV > eMax) keV = eMax;
         if (keV < eMin) keV = eMin;
       }

@@ -27,6 +27,7 @@ using namespace NEST;
 extern int verbosity, usePD, useS2, numBins;
 extern bool MCtruthE, MCtruthPos;
 extern double minS1, maxS1, minS2, maxS2, logMin, logMax, z_step;
+extern double minTimeSeparation;  // execNEST.cpp:38
 extern double band[NUMBINS_MAX][7];
 extern NEST::S1CalculationMode s1CalculationMode;
 extern NEST::S2CalculationMode s2CalculationMode;
@@ -160,6 +161,11 @@ void ref_spectrum(int kind, uint64_t seed, int n, double eMin, double eMax, doub
   for (int i = 0; i < n; ++i) {
     if (kind == NB200_SRC_CH3T) out[i] = TestSpectra::CH3T_spectrum(eMin, eMax);
     else if (kind == NB200_SRC_DD) out[i] = TestSpectra::DD_spectrum(eMin, eMax, 13., 0.12, 71.2, 20., -20.5);
+    else if (kind == NB200_SRC_AMBE) out[i] = TestSpectra::PowLawFit_spectrum(eMin, eMax, -0.95351);
+    else if (kind == NB200_SRC_C14) out[i] = TestSpectra::C14_spectrum(eMin, eMax);
+    else if (kind == NB200_SRC_CF) out[i] = TestSpectra::Cf_spectrum(eMin, eMax);
+    else if (kind == NB200_SRC_PPSOLAR) out[i] = TestSpectra::ppSolar_spectrum(eMin, eMax);
+    else if (kind == NB200_SRC_ATMNU) out[i] = TestSpectra::atmNu_spectrum(eMin, eMax);
     else out[i] = TestSpectra::B8_spectrum(eMin, eMax);
   }
 }
@@ -235,19 +241,26 @@ int ref_chain(uint64_t seed, int n, int species, int src_kind, double eMin, doub
   double massNum = detector->get_molarMass(), atomNum = 0;
   if (type_num == ion) { atomNum = 2; massNum = 4; }  // the CLI's "alpha" (execNEST.cpp:496-500)
   if (type_num < 6) massNum = 0;
+  if (type_num == Kr83m) { massNum = eMax; atomNum = minTimeSeparation; }  // execNEST.cpp:671, 1052
   double vD = 0, vD_middle = 0, pos_x = 0, pos_y = 0, pos_z = 0, field, driftTime;
   std::vector<double> vTable;
   try {
     for (int j = 0; j < n; ++j) {
       double keV;
-      if (src_kind == NB200_SRC_MONO) keV = eMin;
+      if (src_kind == NB200_SRC_MONO || type_num == Kr83m) keV = eMin;
       else if (src_kind == NB200_SRC_CH3T) keV = TestSpectra::CH3T_spectrum(eMin, eMax);
       else if (src_kind == NB200_SRC_B8) keV = TestSpectra::B8_spectrum(eMin, eMax);
       else if (src_kind == NB200_SRC_DD) keV = TestSpectra::DD_spectrum(eMin, eMax, 13., 0.12, 71.2, 20., -20.5);
+      else if (src_kind == NB200_SRC_AMBE) keV = TestSpectra::PowLawFit_spectrum(eMin, eMax, -0.95351);
+      else if (src_kind == NB200_SRC_C14) keV = TestSpectra::C14_spectrum(eMin, eMax);
+      else if (src_kind == NB200_SRC_CF) keV = TestSpectra::Cf_spectrum(eMin, eMax);
+      else if (src_kind == NB200_SRC_PPSOLAR) keV = TestSpectra::ppSolar_spectrum(eMin, eMax);
+      else if (src_kind == NB200_SRC_ATMNU) keV = TestSpectra::atmNu_spectrum(eMin, eMax);
       else if (src_kind == NB200_SRC_GAUSS) keV = RandomGen::rndm()->rand_zero_trunc_gauss(eMin, eMax);
       else if (src_kind == NB200_SRC_EXP) keV = RandomGen::rndm()->rand_exponential(-eMax * log(2.), 0., eMin);
       else keV = eMin + (eMax - eMin) * RandomGen::rndm()->rand_uniform();
-      if (type_num != B8 && eMax > 0. && eMin < eMax) {
+      if (type_num != B8 && type_num != Kr83m && type_num != ppSolar && type_num != atmNu && eMax > 0. &&
+          eMin < eMax) {
         if (keV > eMax) keV = eMax;
         if (keV < eMin) keV = eMin;
       }

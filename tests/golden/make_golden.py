@@ -35,6 +35,12 @@ def main():
                                   ("gamma", 0, capi.gammaRay, 1.0), ("gamma13", 2, capi.beta, 1.3),
                                   ("weighted", 3, capi.beta, 1.0)]:
         out["y_" + name] = r.yields(which, sp, EE, FF, RHO_LUX, 131.293, 54.0, nr, er, mult)
+    # Kr83m: the three lines x decay separations (min == max => no random draw) x fields
+    Fk = np.array([1.0, 50.0, 180.0, 400.0, 1000.0, 4000.0])
+    out["y_kr_F"] = Fk
+    for e in (9.4, 32.1, 41.5):
+        for dT in (50.0, 154.4, 400.0, 1000.0):
+            out["y_kr_%g_%g" % (e, dT)] = r.yields(0, capi.Kr83m, np.full(Fk.size, e), Fk, RHO_LUX, dT, dT, nr, er)
     Ea = np.linspace(500.0, 9000.0, 60)
     out["y_alpha_E"] = Ea
     out["y_alpha"] = r.yields(0, capi.ion, Ea, 180.0, RHO_LUX, 4.0, 2.0, nr, er)
@@ -59,6 +65,15 @@ def main():
         "chain_gamma_mono": (7, 200, capi.gammaRay, capi.SRC_MONO, 41.5, 41.5, 180.0, 1, (10., 20., 300.), -1),
         "chain_NR_250_parametric": (8, 200, capi.NR, capi.SRC_MONO, 250.0, 250.0, 180.0, 1, (10., 20., 300.), -1),
         "chain_alpha": (9, 100, capi.ion, capi.SRC_MONO, 5300.0, 5300.0, 180.0, 1, (10., 20., 300.), -1),
+        # Kr83m: eMin = the line, eMax = max time separation [ns] (execNEST.cpp:583-588)
+        "chain_Kr83m_41": (10, 200, capi.Kr83m, capi.SRC_MONO, 41.5, 1000.0, 180.0, 0, (0, 0, 0), -1),
+        "chain_Kr83m_9": (11, 200, capi.Kr83m, capi.SRC_MONO, 9.4, 400.0, 180.0, 0, (0, 0, 0), -1),
+        "chain_Kr83m_32": (12, 200, capi.Kr83m, capi.SRC_MONO, 32.1, 400.0, 180.0, 0, (0, 0, 0), -1),
+        "chain_C14": (13, 200, capi.C14, capi.SRC_C14, 0.0, 156.0, 180.0, 0, (0, 0, 0), -1),
+        "chain_Cf": (14, 200, capi.Cf, capi.SRC_CF, 0.0, 200.0, 180.0, 0, (0, 0, 0), -1),
+        "chain_ppSolar": (15, 200, capi.ppSolar, capi.SRC_PPSOLAR, 0.0, 250.0, 180.0, 0, (0, 0, 0), -1),
+        "chain_atmNu": (16, 200, capi.atmNu, capi.SRC_ATMNU, 0.0, 85.0, 180.0, 0, (0, 0, 0), -1),
+        "chain_AmBe": (17, 200, capi.AmBe, capi.SRC_AMBE, 0.5, 300.0, 180.0, 0, (0, 0, 0), -1),
     }
     for name, (seed, n, sp, kind, e0, e1, fld, fp, xyz, erm) in cases.items():
         out[name] = ref_chain(r, seed, n, sp, kind, e0, e1, fld, fp, xyz, erm)
@@ -73,6 +88,9 @@ def main():
         out["sampler_%d_%g_%g" % (kind, p[0], p[1])] = r.sampler(kind, 5, 400, *p)
     for k, nme in [(capi.SRC_CH3T, "CH3T"), (capi.SRC_DD, "DD"), (capi.SRC_B8, "B8")]:
         out["spectrum_" + nme] = r.spectrum(k, 9, 400, 0.0, 80.0)
+    for k, nme, hi in [(capi.SRC_C14, "C14", 156.0), (capi.SRC_CF, "Cf", 200.0), (capi.SRC_PPSOLAR, "ppSolar", 250.0),
+                       (capi.SRC_ATMNU, "atmNu", 85.0), (capi.SRC_AMBE, "AmBe", 300.0)]:
+        out["spectrum_" + nme] = r.spectrum(k, 9, 400, 0.5, hi)
     # LAr
     El = np.exp(np.linspace(np.log(0.1), np.log(1000.0), 300))
     out["lar_E"] = El

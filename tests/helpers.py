@@ -19,6 +19,13 @@ def gpu_chain(ctx, seed, n, species, src_kind, eMin, eMax, inField=180.0, fixed_
     mo.multFact = multFact
     if skewER is not None:
         mo.SkewnessER = skewER
+    # massNum / atomNum as the CLI sets them (execNEST.cpp:438-439, 496-500, 670-671, 1052)
+    if species == capi.ion:
+        mo.massNum, mo.atomNum = 4.0, 2.0
+    elif species == capi.Kr83m:
+        mo.massNum, mo.atomNum = eMax, 0.0
+    elif species >= 6:
+        mo.massNum, mo.atomNum = det.molarMass, 0.0
     ana = ana or capi.analysis(0)
     src = capi.source(src_kind, species, eMin, eMax, inField, fixed_pos, xyz, par)
     cols = ctx.run(det, mo, ana, src, rc, seed, n, first_event=first_event, band=band)

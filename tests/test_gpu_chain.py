@@ -30,6 +30,7 @@ MONO = [
     ("NR_3keV", capi.NR, 3.0, -1, 1.0, 1),
     ("NR_30keV", capi.NR, 30.0, -1, 1.0, 1),
     ("NR_250keV_parametric", capi.NR, 250.0, -1, 1.0, 1),
+    ("alpha_5300keV", capi.ion, 5300.0, -1, 1.0, 1),
 ]
 
 
@@ -49,10 +50,15 @@ def test_mono_fixed_position(ctx, ref, label, species, E, er_model, mult, which)
     ("CH3T", capi.CH3T, capi.SRC_CH3T, 0.0, 18.5898, -1),
     ("DD", capi.DD, capi.SRC_DD, 0.0, 80.0, -1),
     ("B8", capi.B8, capi.SRC_B8, 0.0, 5.0, -1),
+    ("AmBe", capi.AmBe, capi.SRC_AMBE, 0.5, 300.0, -1),
+    ("Cf", capi.Cf, capi.SRC_CF, 0.0, 200.0, -1),
+    ("C14", capi.C14, capi.SRC_C14, 0.0, 156.0, -1),
+    ("ppSolar", capi.ppSolar, capi.SRC_PPSOLAR, 0.0, 250.0, -1),
+    ("atmNu", capi.atmNu, capi.SRC_ATMNU, 0.0, 85.0, -1),
 ])
 def test_random_vertex_chain_and_band(ctx, ref, label, species, kind, emin, emax, er_model):
     n = 100000
-    par = (13., 0.12, 71.2, 20., -20.5) if kind == capi.SRC_DD else ()
+    par = (13., 0.12, 71.2, 20., -20.5) if kind == capi.SRC_DD else (-0.95351,) if kind == capi.SRC_AMBE else ()
     ana = capi.analysis(0)
     band = capi.Band(ana)
     g, cols = gpu_chain(ctx, 3, n, species, kind, emin, emax, 180.0, 0, (0, 0, 0), er_model, 1.0, 1, ana=ana,
@@ -69,6 +75,21 @@ def test_random_vertex_chain_and_band(ctx, ref, label, species, kind, emin, emax
     bs = ref.getband(cols["signal1"], cols["signal2"])
     ok = np.isfinite(bs).all(axis=1) & np.isfinite(bg).all(axis=1)
     assert np.allclose(bg[ok][:, [0, 1, 2, 3, 4, 5]], bs[ok][:, [0, 1, 2, 3, 4, 5]], rtol=2e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("line,maxT", [(41.5, 1000.0), (9.4, 400.0), (32.1, 400.0)])
+def test_kr83m_chain(ctx, ref, line, maxT):
+    """83mKr: eMin = the line, eMax = max time between the two decays (execNEST.cpp:583-588);
+    the separation is drawn per event and shapes the 9.4 keV yields (NEST.cpp:954-1044)"""
+    n = 60000
+    g, cols = gpu_chain(ctx, 31, n, capi.Kr83m, capi.SRC_MONO, line, maxT)
+    r = ref_chain(ref, 32, n, capi.Kr83m, capi.SRC_MONO, line, maxT)
+    check(g, r, label="Kr83m %g keV" % line)
+    dT = cols["deltaT_ns"]
+    assert dT.min() >= 0.0 and dT.max() <= maxT
+    from scipy import stats
+    exp = ref.sampler(5, 77, n, 154.4, 0.0, maxT)   # rand_exponential(half-life, min, max)
+    assert stats.ks_2samp(dT, exp).pvalue > P_MIN
 
 
 def test_nonuniform_field(ctx, ref):

@@ -65,6 +65,28 @@ def test_alpha_yields(ctx, ref):
         assert relerr(got[k], exp[k]).max() <= TOL
 
 
+@pytest.mark.parametrize("line", [9.4, 32.1, 41.5])
+def test_kr83m_yields(ctx, ref, line):
+    """GetYieldKr83m (NEST.cpp:954-1044) at fixed decay separation: deterministic, 1e-12"""
+    det = capi.detector("LUX_Run03")
+    capi.prepare(det, 180.0)
+    mo = capi.model(1)
+    F = np.array(FIELDS, float)
+    E = np.full(F.size, line)
+    for dT in (20.0, 50.0, 154.4, 400.0, 1000.0, 5000.0):
+        mo.massNum, mo.atomNum = dT, dT
+        for rho in (RHO_LUX, 2.7):
+            got = ctx.yields(det, mo, capi.Kr83m, E, F, rho)
+            exp = ref.yields(0, capi.Kr83m, E, F, rho, dT, dT, list(mo.NRYieldsParam), list(mo.ERYieldsParam)).T
+            for k in range(6):
+                assert relerr(got[k], exp[k]).max() <= TOL, (line, dT, rho, k, got[k], exp[k])
+    # min > max is the reference's "ERROR: min greater than max" (:957-959), except on the 32.1 keV line
+    mo.massNum, mo.atomNum = 100.0, 300.0
+    if line != 32.1:
+        with pytest.raises(capi.NestB200Error, match="min greater than max"):
+            ctx.yields(det, mo, capi.Kr83m, E, F, RHO_LUX)
+
+
 def test_survey_pinned_values(ctx):
     """values captured from the compiled reference in SURVEY.md 8(c)"""
     det = capi.detector("LUX_Run03")

@@ -32,6 +32,11 @@ def test_yields_bitwise(orc, gold):
         assert np.array_equal(got, gold["y_" + name]), name
     got = orc.yields(0, capi.ion, gold["y_alpha_E"], 180.0, RHO_LUX, 4.0, 2.0, nr, er)
     assert np.array_equal(got, gold["y_alpha"])
+    Fk = gold["y_kr_F"]
+    for e in (9.4, 32.1, 41.5):  # GetYieldKr83m, fixed decay separation (NEST.cpp:954-1044)
+        for dT in (50.0, 154.4, 400.0, 1000.0):
+            got = orc.yields(0, capi.Kr83m, np.full(Fk.size, e), Fk, RHO_LUX, dT, dT, nr, er)
+            assert np.array_equal(got, gold["y_kr_%g_%g" % (e, dT)]), (e, dT)
 
 
 def test_run_constants_and_maps_bitwise(orc, gold):
@@ -64,6 +69,9 @@ def test_band_samplers_spectra_lar_vec_bitwise(orc, gold):
             assert np.array_equal(orc.sampler(int(kind), 5, 400, float(p0), float(p1), p2), gold[key]), key
     for k, nme in [(capi.SRC_CH3T, "CH3T"), (capi.SRC_DD, "DD"), (capi.SRC_B8, "B8")]:
         assert np.array_equal(orc.spectrum(k, 9, 400, 0.0, 80.0), gold["spectrum_" + nme])
+    for k, nme, hi in [(capi.SRC_C14, "C14", 156.0), (capi.SRC_CF, "Cf", 200.0), (capi.SRC_PPSOLAR, "ppSolar", 250.0),
+                       (capi.SRC_ATMNU, "atmNu", 85.0), (capi.SRC_AMBE, "AmBe", 300.0)]:
+        assert np.array_equal(orc.spectrum(k, 9, 400, 0.5, hi), gold["spectrum_" + nme]), nme
     for sp in (0, 1, 2):
         for fld in (1.0, 500.0, 1000.0):
             y, f = orc.lar(4, sp, gold["lar_E"], fld, 1.393)
@@ -96,7 +104,9 @@ def test_oracle_equals_live_reference(orc, ref):
     rng = np.random.default_rng(0)
     for seed in (17, 18):
         for sp, kind, e0, e1, erm in [(capi.beta, capi.SRC_FLAT, 0.1, 20.0, 0), (capi.NR, capi.SRC_FLAT, 0.0, 100.0, -1),
-                                      (capi.beta, capi.SRC_GAUSS, 10.0, 2.0, 1), (capi.beta, capi.SRC_FLAT, 0.5, 60.0, 2)]:
+                                      (capi.beta, capi.SRC_GAUSS, 10.0, 2.0, 1), (capi.beta, capi.SRC_FLAT, 0.5, 60.0, 2),
+                                      (capi.Kr83m, capi.SRC_MONO, 41.5, 600.0, -1), (capi.C14, capi.SRC_C14, 0., 156., -1),
+                                      (capi.atmNu, capi.SRC_ATMNU, 0.0, 85.0, -1)]:
             a = ref_chain(ref, seed, 1500, sp, kind, e0, e1, 180.0, 0, (0, 0, 0), erm, 1.2)
             b = ref_chain(orc, seed, 1500, sp, kind, e0, e1, 180.0, 0, (0, 0, 0), erm, 1.2)
             assert np.array_equal(a, b), (seed, sp, kind)
