@@ -182,6 +182,15 @@ int build_params(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo,
     std::memcpy(P->model.NRERWidthsParam, w, sizeof w);
     P->model.n_widths = 13;
   }
+  // yield-model factors of the uniform drift field (an event with another field evaluates its own)
+  P->hoist.field = -1.;
+  if (src->inField >= 0.) {
+    P->hoist.field = src->inField;
+    P->hoist.density = rc->rho;
+    P->hoist.nr_ti = nr_thomas_imel(src->inField, rc->rho, mo->NRYieldsParam);
+    beta_field_terms(src->inField, rc->rho, mo->ERYieldsParam, P->hoist.b);
+    gamma_field_terms(src->inField, rc->rho, P->hoist.g);
+  }
   // per-run hoists (host maps evaluate the caller's LUT, not the device copy)
   const double zc = det->TopDrift - rc->vD_middle * det->dtCntr;
   P->s1_center = fit_s1(det->FitS1, 0., 0., zc);

@@ -704,14 +704,6 @@ NB_D void select_signals(const nb200_analysis& A, const double* scint, const dou
     signal2 = -999.;
 }
 
-// pow with the exponents 1 and 2 taken exactly (x, x*x are the correctly rounded results, what
-// glibc's pow returns); the default NR model has n[6] = n[8] = 2 and n[10] = n[11] = 1.
-NB_D double pow_small(double x, double y) {
-  if (y == 1.) return x;
-  if (y == 2.) return x * x;
-  return pow(x, y);
-}
-
 // energy reconstruction execNEST.cpp:1170-1250; returns signalE, keV updated in place
 NB_D double reconstruct_energy(const RunParams& P, const Yields& y, const double* scint,
                                const double* scint2, double signal1, double signal2, double field,

@@ -232,15 +232,16 @@ __global__ void __launch_bounds__(kPreBlock, NB_PRE_MINB)
       if (P.model.er_model < 0 && ((nrlike && nearly_equal(P.model.massNum, 0.)) || sp == NB200_ion))
         A2 = select_xe_atom(g);
       if (P.model.er_model == 0)
-        y = yield_beta(keV, P.rc.rho, field, det, P.model.ERYieldsParam, P.model.multFact);
+        y = yield_beta(keV, P.rc.rho, field, det, P.model.ERYieldsParam, P.model.multFact, &P.hoist);
       else if (P.model.er_model == 1)
-        y = yield_gamma(keV, P.rc.rho, field, det, P.model.multFact);
+        y = yield_gamma(keV, P.rc.rho, field, det, P.model.multFact, &P.hoist);
       else if (P.model.er_model == 2)
-        y = yield_er_weighted(keV, P.rc.rho, field, det, P.model.ERYieldsParam);
+        y = yield_er_weighted(keV, P.rc.rho, field, det, P.model.ERYieldsParam, &P.hoist);
       else {
         double u01 = 0.5;
         if (sp == NB200_Kr83m && !nearly_equal(P.model.massNum, P.model.atomNum)) u01 = g.uniform();
-        y = get_yields(sp, keV, P.rc.rho, field, P.model.massNum, P.model.atomNum, A2, det, P.model, &err, u01);
+        y = get_yields(sp, keV, P.rc.rho, field, P.model.massNum, P.model.atomNum, A2, det, P.model, &err, u01,
+                       &P.hoist);
       }
     }
     NB_LOCKSTEP();

@@ -30,6 +30,14 @@ struct Work {
 };
 enum { WORK_F64 = 14, WORK_I32 = 7 };
 
+// field/density-only factors of the mean-yield models, see nb_yields.cuh
+struct YieldHoist {
+  double field, density;  // what the factors were evaluated for (field < 0: none)
+  double nr_ti;           // NR: ThomasImel
+  double b[6];            // beta: m01, m03, m04, m07, m10, density correction of Qy
+  double g[3];            // gamma: m1, m5, m7
+};
+
 struct RunParams {
   nb200_detector det;  // map.lut -> device memory
   nb200_model model;
@@ -56,6 +64,7 @@ struct RunParams {
   double below_thr_pct;  // Parametric S1 threshold percentile       NEST.cpp:1437-1457
   double recon_mult;     // MultFact prefactor, execNEST.cpp:1179-1182
   double wimp_dr0[9];    // WIMP_dRate(0) per Xe isotope             TestSpectra.cpp:459,466
+  YieldHoist hoist;      // yield-model factors of (inField, rho), uniform field only
   double band_width, band_border;  // GetBand bin geometry           execNEST.cpp:1521-1527
   // GetDriftVelocity_Liquid rows bracketing T_Kelvin (NEST.cpp:2429-2502); dv_mode 0 blend,
   // 1 = T on the lower node, 2 = T on the upper node

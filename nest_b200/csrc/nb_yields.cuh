@@ -155,23 +155,71 @@ NB_HD double fit_tba(const nb200_map& m, double x, double y, double z) {
 // NESTcalc::NexONi NEST.cpp:2850-2857
 NB_D double nex_o_ni(double energy, double alpha) { return alpha * erf(0.05 * energy); }
 
+// pow with the exponents 1, 2 and 1/2 taken exactly: x, x*x and sqrt(x) are the correctly rounded
+// results (what glibc's pow returns to within its last bit) and cost a few instructions instead
+// of ~150.  The default model vectors use exactly these (NR: [6] = [8] = 2, [9] = 0.5,
+// [10] = [11] = 1; gamma: m4 = m8 = 2).
+NB_HD double pow_small(double x, double y) {
+  if (y == 1.) return x;
+  if (y == 2.) return x * x;
+  if (y == 0.5) return sqrt(x);
+  return pow(x, y);
+}
+
+// Factors of the mean-yield models that depend on the drift field and the density only
+// (GetYieldNR NEST.cpp:778-780, GetYieldBetaGR :1135-1193, GetYieldGamma :441-447).  With a
+// uniform field they are the same for every event of a run: the host evaluates them once
+// (build_params) and the kernels reuse them; an event whose field or density differs (FitEF
+// maps, nb200_yields on arbitrary lists) evaluates them itself with the same functions.
+// (struct YieldHoist: nb_params.h)
+NB_HD double nr_thomas_imel(double dfield, double density, const double* p) {
+  return p[2] * pow(dfield, p[3]) * pow(density / NB_DENSITY, 0.3);
+}
+NB_HD void beta_field_terms(double dfield, double density, const double* ep, double* t) {
+  t[0] = (ep[0] < 0.) ? 30.66 + (6.1978 - 30.66) / pow(1. + pow(dfield / 73.855, 2.0318), 0.41883) : ep[0];
+  t[1] = (ep[2] < 0.) ? log10(dfield) * 0.13946236 + 0.52561312 : ep[2];
+  t[2] = (ep[3] < 0.) ? 1.82217496 + (2.82528809 - 1.82217496) / (1. + pow(dfield / 144.65029656, -2.80532006))
+                      : ep[3];
+  t[3] = (ep[6] < 0.) ? 7.02921301 + (98.27936794 - 7.02921301) / (1. + pow(dfield / 256.48156448, 1.29119251))
+                      : ep[6];
+  t[4] = (ep[9] < 0.)
+             ? 0.0508273937 + (0.1166087199 - 0.0508273937) / (1. + pow(dfield / 1.39260460e+02, -0.65763592))
+             : ep[9];
+  t[5] = 1.;
+  if (ep[5] < 0.) {
+    double coeff_TI = pow(1. / NB_DENSITY, 0.3);
+    double coeff_Ni = pow(1. / NB_DENSITY, 1.4);
+    double coeff_OL = pow(1. / NB_DENSITY, -1.7) / log(1. + coeff_TI * coeff_Ni * pow(NB_DENSITY, 1.7));
+    t[5] = coeff_OL * log(1. + coeff_TI * coeff_Ni * pow(density, 1.7)) * pow(density, -1.7);
+  }
+}
+NB_HD void gamma_field_terms(double dfield, double density, double* t) {
+  t[0] = 33.951 + (3.3284 - 33.951) / (1. + pow(dfield / 165.34, .72665));
+  t[1] = 23.156 + (10.737 - 23.156) / (1. + pow(dfield / 34.195, .87459));
+  double densCorr = 240720. / pow(density, 8.2076);
+  t[2] = 66.825 + (829.25 - 66.825) / (1. + pow(dfield / densCorr, .83344));
+}
+NB_HD bool hoisted(const YieldHoist* h, double dfield, double density) {
+  return h && h->field == dfield && h->density == density;
+}
+
 // NESTcalc::GetYieldNR NEST.cpp:773-854.  massNumber: int(massNum) or the random isotope.
 // err is raised where the reference throws "Quanta not conserved" (:837-840).
 NB_D Yields yield_nr(double energy, double density, double dfield, int massNumber,
-                     const nb200_detector& det, const double* p, int* err) {
+                     const nb200_detector& det, const double* p, int* err, const YieldHoist* h = nullptr) {
   double scale = sqrt(det.molarMass / double(massNumber));
   double Nq = p[0] * pow(energy, p[1]) + 0.0;  // McMConst = 0 (NEST.cpp:19)
   if (!det.OldW13eV) Nq *= NB_ZurichEXOW;
-  double ThomasImel = p[2] * pow(dfield, p[3]) * pow(density / NB_DENSITY, 0.3);
-  double Qy = 1. / (ThomasImel * pow(energy + p[4], p[9]));
-  Qy *= 1. - 1. / pow(1. + pow((energy / p[5]), p[6]), p[10]);
+  double ThomasImel = hoisted(h, dfield, density) ? h->nr_ti : nr_thomas_imel(dfield, density, p);
+  double Qy = 1. / (ThomasImel * pow_small(energy + p[4], p[9]));
+  Qy *= 1. - 1. / pow_small(1. + pow_small((energy / p[5]), p[6]), p[10]);
   if (!det.OldW13eV) Qy *= NB_ZurichEXOQ;
   double Ly = Nq / energy - Qy;
   if (Qy < 0.0) Qy = 0.0;
   if (Ly < 0.0) Ly = 0.0;
   double Ne = Qy * energy * scale;
   double Nph = Ly * energy * scale;
-  Nph *= (1. - 1. / pow(1. + pow((energy / p[7]), p[8]), p[11]));
+  Nph *= (1. - 1. / pow_small(1. + pow_small((energy / p[7]), p[8]), p[11]));
   Nq = Nph + Ne;
   double ex = exp(Ne * ThomasImel / 4.);
   double Ni = (4. / ThomasImel) * (ex - 1.);
@@ -196,46 +244,32 @@ NB_D Yields yield_nr(double energy, double density, double dfield, int massNumbe
 
 // NESTcalc::GetYieldBetaGR NEST.cpp:1089-1209 (xenon branch)
 NB_D Yields yield_beta(double energy, double density, double dfield, const nb200_detector& det,
-                       const double* ep, double multFact) {
+                       const double* ep, double multFact, const YieldHoist* h = nullptr) {
   Wvalue w = work_function(density, det.molarMass, det.OldW13eV != 0);
   double Wq_eV = w.Wq_eV, alpha = w.alpha;
   double Nq = energy * 1e3 / Wq_eV, m01, m02, m03, m04, m05, m07, m08, m09, m10;
-  if (ep[0] < 0.)
-    m01 = 30.66 + (6.1978 - 30.66) / pow(1. + pow(dfield / 73.855, 2.0318), 0.41883);
+  double tl[6];
+  const double* t = tl;
+  if (hoisted(h, dfield, density))
+    t = h->b;
   else
-    m01 = ep[0];
+    beta_field_terms(dfield, density, ep, tl);
+  m01 = t[0];
   m02 = (ep[1] < 0.) ? 77.2931084 : ep[1];
-  if (ep[2] < 0.)
-    m03 = log10(dfield) * 0.13946236 + 0.52561312;
-  else
-    m03 = ep[2];
-  if (ep[3] < 0.)
-    m04 = 1.82217496 + (2.82528809 - 1.82217496) / (1. + pow(dfield / 144.65029656, -2.80532006));
-  else
-    m04 = ep[3];
+  m03 = t[1];
+  m04 = t[2];
   if (ep[4] < 0.)
     m05 = Nq / energy / (1. + alpha * erf(0.05 * energy)) - m01;
   else
     m05 = ep[4];
-  if (ep[6] < 0.)
-    m07 = 7.02921301 + (98.27936794 - 7.02921301) / (1. + pow(dfield / 256.48156448, 1.29119251));
-  else
-    m07 = ep[6];
+  m07 = t[3];
   m08 = (ep[7] < 0.) ? 4.285781736 : ep[7];
   m09 = (ep[8] < 0.) ? 0.3344049589 : ep[8];
-  if (ep[9] < 0.)
-    m10 = 0.0508273937 +
-          (0.1166087199 - 0.0508273937) / (1. + pow(dfield / 1.39260460e+02, -0.65763592));
-  else
-    m10 = ep[9];
+  m10 = t[4];
   double Qy = m01 + (m02 - m01) / pow((1. + pow(energy / m03, m04)), m09) + m05 +
               (0.0 - m05) / pow((1. + pow(energy / m07, m08)), m10);
   if (ep[5] < 0.) {
-    double coeff_TI = pow(1. / NB_DENSITY, 0.3);
-    double coeff_Ni = pow(1. / NB_DENSITY, 1.4);
-    double coeff_OL =
-        pow(1. / NB_DENSITY, -1.7) / log(1. + coeff_TI * coeff_Ni * pow(NB_DENSITY, 1.7));
-    Qy *= coeff_OL * log(1. + coeff_TI * coeff_Ni * pow(density, 1.7)) * pow(density, -1.7);
+    Qy *= t[5];
     if (!det.OldW13eV) Qy *= NB_ZurichEXOQ;
   }
   Qy *= multFact;
@@ -248,20 +282,25 @@ NB_D Yields yield_beta(double energy, double density, double dfield, const nb200
 
 // NESTcalc::GetYieldGamma NEST.cpp:434-467
 NB_D Yields yield_gamma(double energy, double density, double dfield, const nb200_detector& det,
-                        double multFact) {
+                        double multFact, const YieldHoist* h = nullptr) {
   Wvalue w = work_function(density, det.molarMass, det.OldW13eV != 0);
   double Wq_eV = w.Wq_eV;
   const double m3 = 2., m4 = 2., m6 = 0.;
-  const double m1 = 33.951 + (3.3284 - 33.951) / (1. + pow(dfield / 165.34, .72665));
+  double tl[3];
+  const double* t = tl;
+  if (hoisted(h, dfield, density))
+    t = h->g;
+  else
+    gamma_field_terms(dfield, density, tl);
+  const double m1 = t[0];
   double m2 = 1000 / Wq_eV;
-  double m5 = 23.156 + (10.737 - 23.156) / (1. + pow(dfield / 34.195, .87459));
-  double densCorr = 240720. / pow(density, 8.2076);
-  double m7 = 66.825 + (829.25 - 66.825) / (1. + pow(dfield / densCorr, .83344));
+  double m5 = t[1];
+  double m7 = t[2];
   double Nq = energy * 1000. / Wq_eV;
   double m8 = 2.;
   if (det.inGas) m8 = -2.;
-  double Qy = m1 + (m2 - m1) / (1. + pow(energy / m3, m4)) + m5 +
-              (m6 - m5) / (1. + pow(energy / m7, m8));
+  double Qy = m1 + (m2 - m1) / (1. + pow_small(energy / m3, m4)) + m5 +
+              (m6 - m5) / (1. + (det.inGas ? pow(energy / m7, m8) : pow_small(energy / m7, m8)));
   if (!det.OldW13eV) Qy *= NB_ZurichEXOQ;
   Qy *= multFact;
   double Ly = Nq / energy - Qy;
@@ -272,10 +311,10 @@ NB_D Yields yield_gamma(double energy, double density, double dfield, const nb20
 // NESTcalc::GetYieldERWeighted NEST.cpp:469-501 with default_EnergyParams /
 // default_FieldParams (NEST.hh:128-129), as execNEST.cpp:1047-1048 calls it
 NB_D Yields yield_er_weighted(double energy, double density, double dfield,
-                              const nb200_detector& det, const double* ep) {
+                              const nb200_detector& det, const double* ep, const YieldHoist* h = nullptr) {
   Wvalue w = work_function(density, det.molarMass, det.OldW13eV != 0);
-  Yields yB = yield_beta(energy, density, dfield, det, ep, 1.);
-  Yields yG = yield_gamma(energy, density, dfield, det, 1.);
+  Yields yB = yield_beta(energy, density, dfield, det, ep, 1., h);
+  Yields yG = yield_gamma(energy, density, dfield, det, 1., h);
   const double E0 = 0.23, E1 = 0.77, E2 = 2.95, E3 = -1.44, F0 = 421.15, F1 = 3.27;
   double weightG =
       E0 + E1 * erf(E2 * (log(energy) + E3)) * (1. - (1. / (1. + pow(dfield / F0, F1))));
@@ -411,7 +450,7 @@ __device__ __noinline__ Yields yield_kr83m(double energy, double density, double
 // (massNum / atomNum carry max / min separation there, :1238-1239).
 NB_D Yields get_yields(int species, double energy, double density, double dfield, double massNum,
                        double atomNum, int A2iso, const nb200_detector& det, const nb200_model& mo,
-                       int* err, double u01 = 0.5) {
+                       int* err, double u01 = 0.5, const YieldHoist* h = nullptr) {
   switch (species) {
     case NB200_NR:
     case NB200_WIMP:
@@ -421,16 +460,16 @@ NB_D Yields get_yields(int species, double energy, double density, double dfield
     case NB200_AmBe:
     case NB200_Cf: {
       int massNumber = nearly_equal(massNum, 0.) ? A2iso : int(massNum);
-      return yield_nr(energy, density, dfield, massNumber, det, mo.NRYieldsParam, err);
+      return yield_nr(energy, density, dfield, massNumber, det, mo.NRYieldsParam, err, h);
     }
     case NB200_ion:
       return yield_ion(energy, density, dfield, massNum, atomNum, double(A2iso), det);
     case NB200_gammaRay:
-      return yield_gamma(energy, density, dfield, det, 1.);
+      return yield_gamma(energy, density, dfield, det, 1., h);
     case NB200_Kr83m:
       return yield_kr83m(energy, density, dfield, massNum, atomNum, u01, det, err);
     default:
-      return yield_beta(energy, density, dfield, det, mo.ERYieldsParam, 1.);
+      return yield_beta(energy, density, dfield, det, mo.ERYieldsParam, 1., h);
   }
 }
 
