@@ -338,25 +338,85 @@ NB_D double stirling_tail(double k) {
   return (1.0 / 12. - (1.0 / 360. - (1.0 / 1260.) * rk2) * rk2) * rk;
 }
 
+// position of the n-th (0-based) set bit of m; n < popc(m)
+NB_D int nth_set_bit(unsigned m, int n) {
+  int pos = 0, t;
+  t = __popc(m & 0xFFFFu);
+  if (n >= t) { n -= t; pos += 16; m >>= 16; }
+  t = __popc(m & 0xFFu);
+  if (n >= t) { n -= t; pos += 8; m >>= 8; }
+  t = __popc(m & 0xFu);
+  if (n >= t) { n -= t; pos += 4; m >>= 4; }
+  t = __popc(m & 0x3u);
+  if (n >= t) { n -= t; pos += 2; m >>= 2; }
+  if (n >= int(m & 1u)) pos += 1;
+  return pos;
+}
+
+// One of the four terms of BTRS's exact acceptance test for candidate k of Binomial(n, p), r = p/q,
+// m = floor((n+1)p), X/Y = v alpha/(a/us^2 + b):
+//   accept  <=>  log(X/Y) <= h(m) + (n+1) log(nm1/nk1) + (k+1/2) log(r nk1/(k+1)) - fc(k) - fc(n-k)
+//   term 0: (m+1/2) log((m+1)/(r nm1)) + fc(m)       term 1: (n+1) log(nm1/nk1) + fc(n-m)
+//   term 2: (k+1/2) log(r nk1/(k+1)) - fc(k)         term 3: -log(X/Y) - fc(n-k)
+// accept <=> (t0 + t1) + (t2 + t3) >= 0.  Both the warp-cooperative and the per-lane evaluation
+// go through this function and this summation order, so a draw does not depend on which is used.
+NB_D double btrs_term(int t, double dn, double m, double r, double kk, double X, double Y) {
+  const double nm1 = dn - m + 1., nk1 = dn - kk + 1.;
+  double w, num, den, sarg, sg;
+  if (t == 0) {
+    w = m + 0.5; num = m + 1.; den = r * nm1; sarg = m; sg = 1.;
+  } else if (t == 1) {
+    w = dn + 1.; num = nm1; den = nk1; sarg = dn - m; sg = 1.;
+  } else if (t == 2) {
+    w = kk + 0.5; num = r * nk1; den = kk + 1.; sarg = kk; sg = -1.;
+  } else {
+    w = -1.; num = X; den = Y; sarg = dn - kk; sg = -1.;
+  }
+  return fma(w, log(num / den), sg * stirling_tail(sarg));
+}
+
 // binom_draw RandomGen.cpp:132-134 = std::binomial_distribution<int64_t>(n,p).  Exact
 // binomial sampler: sequential CDF inversion while n*min(p,1-p) < 10, Hormann's BTRS
 // transformed rejection (J. Stat. Comput. Simul. 46 (1993) 101) above.  Draws from its own
 // counter stream (seed; event, stream) so that it can live out of line.
-// (The paper's BTRD refinement -- one-uniform centre, quadratic squeeze, lazy h -- was measured
-// and is SLOWER here: a warp nearly always has some lane in the exact test, so squeezes only add
-// serial latency; the four independent logarithms of the plain test overlap instead.)
+//
+// BTRS accepts 86 % of its candidates on a cheap test; the others need the exact log-pmf
+// bound: four logarithms and four Stirling tails.  Per lane that is ~330 instructions which a
+// warp executes for the ~5 lanes that need it in an iteration -- the single most expensive
+// piece of k_post.  When a full warp is inside the sampler (the chain kernels) the bound is
+// evaluated by the WARP instead: lane 4c+t takes term t of pending candidate c (eight
+// candidates per pass), the four terms are summed by two shuffles, and the owner of the
+// candidate reads the sum back.  One division, one logarithm and one Stirling tail per lane per
+// pass, at full lane occupancy.  (The paper's BTRD squeeze was measured too and is slower: some
+// lane of a warp nearly always needs the exact test anyway.)  A partial warp runs the plain loop.
+#ifndef NB_BINOM_COOP
+#define NB_BINOM_COOP 1
+#endif
 __device__ __noinline__ long long binomial(uint64_t seed, uint64_t event, uint32_t stream, long long n,
                                            double p) {
-  if (!(n > 0) || !(p > 0.)) return 0;
-  if (p >= 1.) return n;
+#if NB_BINOM_COOP
+  const unsigned grp = __activemask();
+  const bool trivial = !(n > 0) || !(p > 0.) || p >= 1.;
+  if (grp != 0xffffffffu || __all_sync(grp, trivial)) {
+#else
+  {
+#endif
+    if (!(n > 0) || !(p > 0.)) return 0;
+    if (p >= 1.) return n;
+  }
   Stream g;
   g.init(seed, event, stream);
-  bool flip = p > 0.5;
-  double pp = flip ? 1. - p : p;
-  double q = 1. - pp;
-  double dn = double(n);
-  long long k;
-  if (dn * pp < 10.) {
+  const bool flip = p > 0.5;
+  const double pp = flip ? 1. - p : p;
+  const double q = 1. - pp;
+  const double dn = double(n);
+  long long k = 0;
+#if NB_BINOM_COOP
+  const bool inversion = !trivial && dn * pp < 10.;
+#else
+  const bool inversion = dn * pp < 10.;
+#endif
+  if (inversion) {
     double r0 = exp(dn * log1p(-pp));
     double s = pp / q;
     for (;;) {
@@ -378,31 +438,94 @@ __device__ __noinline__ long long binomial(uint64_t seed, uint64_t event, uint32
         break;
       }
     }
-  } else {
-    double spq = sqrt(dn * pp * q);
-    double b = 1.15 + 2.53 * spq;
-    double a = -0.0873 + 0.0248 * b + 0.01 * pp;
-    double c = dn * pp + 0.5;
-    double vr = 0.92 - 4.2 / b;
-    double r = pp / q;
-    double alpha = (2.83 + 5.1 / b) * spq;
-    double m = floor((dn + 1.) * pp);
-    // terms of the acceptance bound that do not depend on the candidate (computed once, by all lanes)
-    const double nm1 = dn - m + 1.;
-    const double hm = (m + 0.5) * log((m + 1.) / (r * nm1)) + stirling_tail(m) + stirling_tail(dn - m);
+  }
+#if NB_BINOM_COOP
+  if (grp == 0xffffffffu) {
+    const bool need = !trivial && !inversion;
+    if (__any_sync(grp, need)) {
+      const int lane = int(threadIdx.x & 31u);
+      const unsigned lt = (1u << lane) - 1u;
+      // setup (harmless numbers in the lanes that do not draw)
+      const double npq = need ? dn * pp * q : 100.;
+      const double spq = sqrt(npq);
+      const double b = 1.15 + 2.53 * spq;
+      const double rb = 1. / b;
+      const double a = -0.0873 + 0.0248 * b + 0.01 * pp;
+      const double c = dn * pp + 0.5;
+      const double vr = 0.92 - 4.2 * rb;
+      const double r = pp / q;
+      const double alpha = (2.83 + 5.1 * rb) * spq;
+      const double m = floor((dn + 1.) * pp);
+      bool done = !need;
+      double kk = 0.;
+      const int role_c = lane >> 2, role_t = lane & 3;
+      for (;;) {
+        bool pend = false;
+        double X = 1., Y = 1.;
+        if (!done) {
+          const double u = g.uniform() - 0.5;
+          const double v = g.uniform();
+          const double us = 0.5 - fabs(u);
+          kk = floor((2. * a / us + b) * u + c);
+          if (us >= 0.07 && v <= vr)
+            done = true;
+          else if (!(kk < 0. || kk > dn)) {
+            pend = true;
+            const double us2 = us * us;
+            X = v * alpha * us2;  // v alpha / (a/us^2 + b) = X / Y
+            Y = a + b * us2;
+          }
+        }
+        unsigned pm = __ballot_sync(grp, pend);
+        while (pm) {  // warp-uniform
+          const int np = __popc(pm);
+          const int rank = __popc(pm & lt);  // of a pending lane among the pending
+          const bool have = role_c < np;
+          const int src = have ? nth_set_bit(pm, role_c) : lane;
+          const double c_dn = __shfl_sync(grp, dn, src), c_m = __shfl_sync(grp, m, src);
+          const double c_r = __shfl_sync(grp, r, src), c_kk = __shfl_sync(grp, kk, src);
+          const double c_X = __shfl_sync(grp, X, src), c_Y = __shfl_sync(grp, Y, src);
+          double val = have ? btrs_term(role_t, c_dn, c_m, c_r, c_kk, c_X, c_Y) : 0.;
+          val += __shfl_xor_sync(grp, val, 1);
+          val += __shfl_xor_sync(grp, val, 2);
+          const double mine = __shfl_sync(grp, val, (rank & 7) << 2);
+          if (pend && rank < 8) {
+            pend = false;
+            if (mine >= 0.) done = true;
+          }
+          pm = (np > 8) ? (pm & ~((2u << nth_set_bit(pm, 7)) - 1u)) : 0u;
+        }
+        if (__all_sync(grp, done)) break;
+      }
+      if (need) k = (long long)kk;
+    }
+    if (trivial) return (p >= 1. && n > 0) ? n : 0;
+    return flip ? n - k : k;
+  }
+#endif
+  if (!inversion) {
+    const double spq = sqrt(dn * pp * q);
+    const double b = 1.15 + 2.53 * spq;
+    const double rb = 1. / b;
+    const double a = -0.0873 + 0.0248 * b + 0.01 * pp;
+    const double c = dn * pp + 0.5;
+    const double vr = 0.92 - 4.2 * rb;
+    const double r = pp / q;
+    const double alpha = (2.83 + 5.1 * rb) * spq;
+    const double m = floor((dn + 1.) * pp);
     double kk;
     for (;;) {
-      double u = g.uniform() - 0.5;
-      double v = g.uniform();
-      double us = 0.5 - fabs(u);
+      const double u = g.uniform() - 0.5;
+      const double v = g.uniform();
+      const double us = 0.5 - fabs(u);
       kk = floor((2. * a / us + b) * u + c);
       if (us >= 0.07 && v <= vr) break;
       if (kk < 0. || kk > dn) continue;
-      const double nk1 = dn - kk + 1.;
-      v = log(v * alpha / (a / (us * us) + b));
-      double ub = hm + (dn + 1.) * log(nm1 / nk1) + (kk + 0.5) * log(r * nk1 / (kk + 1.)) -
-                  stirling_tail(kk) - stirling_tail(dn - kk);
-      if (v <= ub) break;
+      const double us2 = us * us;
+      const double X = v * alpha * us2, Y = a + b * us2;
+      const double t01 = btrs_term(0, dn, m, r, kk, X, Y) + btrs_term(1, dn, m, r, kk, X, Y);
+      const double t23 = btrs_term(2, dn, m, r, kk, X, Y) + btrs_term(3, dn, m, r, kk, X, Y);
+      if (t01 + t23 >= 0.) break;
     }
     k = (long long)kk;
   }
