@@ -131,7 +131,11 @@ NB_D double drift_velocity_dev(const RunParams& P, double eField) {
   return speed;
 }
 
+#ifndef NB_NO_LOCKSTEP
 #define NB_LOCKSTEP() __syncthreads()
+#else
+#define NB_LOCKSTEP() ((void)0)
+#endif
 // launch geometry, measured on B200 (tools/sweep_variants.sh): k_pre and k_post are fastest at 64
 // registers with 32 warps per SM in large lockstep blocks (k_post one 1024-thread block, k_pre two
 // 512-thread blocks: the spills cost less than the FP64 dependency stalls the extra warps hide, and
