@@ -245,23 +245,75 @@ NB_D void sincos_bits(uint32_t z, double& s, double& c) {
   s = __hiloint2double(__double2hiint(b) ^ int(ss), __double2loint(b));
 }
 
+// The same table in global memory for the per-event stages (k_pre / k_post and the samplers they
+// call out of line), which have no shared-memory staging: a random index into constant memory
+// would serialise, a read-only global load is one instruction and stays in L1.
+static __device__ const double g_lntab[64] = {
+    0.98461538461538461538, 0.015504186535965254151, 0.95522388059701492537, 0.045809536031294203167,
+    0.92753623188405797101, 0.075223421237587525699, 0.90140845070422535211, 0.10379679368164356483,
+    0.87671232876712328767, 0.13157635778871927259,  0.85333333333333333333, 0.15860503017663858409,
+    0.83116883116883116883, 0.18492233849401199266,  0.81012658227848101266, 0.21056476910734963767,
+    0.79012345679012345679, 0.23556607131276690908,  0.77108433734939759036, 0.25995752443692606697,
+    0.75294117647058823529, 0.28376817313064459835,  0.73563218390804597701, 0.30702503529491186208,
+    0.71910112359550561798, 0.32975328637246798181,  0.7032967032967032967,  0.35197642315717818466,
+    0.68817204301075268817, 0.37371640979358408082,  0.67368421052631578947, 0.39499380824086897811,
+    0.65979381443298969072, 0.41582789514371096561,  0.64646464646464646465, 0.43623676677491807035,
+    0.63366336633663366337, 0.45623743348158759438,  0.62135922330097087379, 0.47584590486996391427,
+    0.60952380952380952381, 0.4950772667978515146,   0.5981308411214953271,  0.5139457511022343168,
+    0.58715596330275229358, 0.53246479886947184387,  0.57657657657657657658, 0.55064711795266227926,
+    0.56637168141592920354, 0.56850473535266871208,  0.55652173913043478261, 0.5860490450035782089,
+    0.54700854700854700855, 0.60329085143808426234,  0.53781512605042016807, 0.62024040975185752885,
+    0.5289256198347107438,  0.63690746223706923162,  0.52032520325203252033, 0.65330127201274563876,
+    0.512,                  0.6694306539426292673,   0.50393700787401574803, 0.68530400309891941654};
+
+// ln(1 + d) for |d| <= 2^-6, Taylor through d^9 (as in neg_log_bits)
+NB_D double ln1p_small(double d) {
+  double q = c_lnp[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) q = fma(q, d, c_lnp[i]);
+  return fma(d * d, q, d);
+}
+// -ln(u), u = (hi:lo)/2^64, with the global table (per-event stages)
+NB_D double neg_log_bits_g(uint32_t hi, uint32_t lo) {
+  unsigned long long x = ((unsigned long long)hi << 32) | lo;
+  x |= 1ull;
+  const int e = __clzll((long long)x);
+  const unsigned long long y = x << e;
+  const double m = __longlong_as_double((long long)(0x3FF0000000000000ull | ((y << 1) >> 12)));
+  const int j = int((y >> 58) & 31ull);
+  const double2 t = __ldg(reinterpret_cast<const double2*>(g_lntab) + j);
+  return fma(double(e + 1), c_hitk[0], -t.y) - ln1p_small(fma(m, t.x, -1.0));
+}
+// ln(x) for a positive, finite, normal x: exponent and mantissa taken from the bits, the same table
+// and polynomial (absolute error ~1e-16; no special cases -- callers guarantee the domain)
+NB_D double log_pos(double x) {
+  const long long b = __double_as_longlong(x);
+  const int e = int(b >> 52) - 1023;
+  const double m = __longlong_as_double((b & 0x000FFFFFFFFFFFFFll) | 0x3FF0000000000000ll);
+  const int j = int(b >> 47) & 31;
+  const double2 t = __ldg(reinterpret_cast<const double2*>(g_lntab) + j);
+  return fma(double(e), c_hitk[0], t.y) + ln1p_small(fma(m, t.x, -1.0));
+}
+
 // ---- samplers (device) -------------------------------------------------------------
 
 // two independent standard normals from one Box-Muller transform.  The reference's
 // rand_gauss (RandomGen.cpp:44-53) evaluates mean + sigma*sqrt2*sqrt(-ln u)*cos(2 pi v)
 // and throws the sine partner away; the partner is an independent N(0,1), so using it
 // halves the log/sqrt work without changing any distribution.
-__device__ __noinline__ double2 box_muller(double u, double v) {
-  double r = sqrt(-2.0 * log(u));
+// Out of line (shared by the many call sites of the per-event stages), and built from the random
+// bits like the hit loop's: radius from 64 bits, angle from 32.
+__device__ __noinline__ double2 box_muller(uint32_t a, uint32_t b, uint32_t c) {
+  const double r = sqrt(2.0 * neg_log_bits_g(a, b));
   double s, co;
-  sincospi(2.0 * v, &s, &co);
+  sincos_bits(c, s, co);
   return make_double2(r * co, r * s);
 }
 NB_D void normal_pair(Stream& g, double& z0, double& z1) {
   uint32_t a, b, c, d;
   g.next2(a, b);
   g.next2(c, d);
-  double2 z = box_muller(u53(a, b), u53(c, d));
+  double2 z = box_muller(a, b, c);
   z0 = z.x;
   z1 = z.y;
 }
@@ -269,7 +321,7 @@ NB_D double normal(Stream& g) {
   uint32_t a, b, c, d;
   g.next2(a, b);
   g.next2(c, d);
-  return box_muller(u53(a, b), u53(c, d)).x;
+  return box_muller(a, b, c).x;
 }
 // rand_gauss(mean, sigma, zero_min) RandomGen.cpp:44-53
 NB_D double gauss(Stream& g, double mean, double sigma, bool zero_min) {
@@ -372,7 +424,7 @@ NB_D double btrs_term(int t, double dn, double m, double r, double kk, double X,
   } else {
     w = -1.; num = X; den = Y; sarg = dn - kk; sg = -1.;
   }
-  return fma(w, log(num / den), sg * stirling_tail(sarg));
+  return fma(w, log_pos(num / den), sg * stirling_tail(sarg));
 }
 
 // binom_draw RandomGen.cpp:132-134 = std::binomial_distribution<int64_t>(n,p).  Exact

@@ -48,26 +48,11 @@ def main():
     json.dump(b, open(os.path.join(out, "%s_bench_n1.json" % tag), "w"), indent=1)
     if refarm:
         json.dump(json.load(open(refarm)), open(os.path.join(out, "%s_bench_reference_arm.json" % tag), "w"), indent=1)
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
-    rr = list(csv.reader(raw.splitlines()))
-    hdr, units, vals = rr[0], rr[1], rr[2]
-    want = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
-            "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
-            "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
-            "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
-            "sm__inst_executed_pipe_fp64.sum.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.sum.pct_of_peak_sustained_active",
-            "sm__inst_executed_pipe_alu.sum.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.sum.pct_of_peak_sustained_active",
-            "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio", "dram__bytes_read.sum",
-            "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
-            "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__cycles_elapsed.avg", "sm__cycles_elapsed.avg.per_second"]
-    with open(os.path.join(out, "%s_k_hits_ncu_full.txt" % tag), "w") as f:
-        f.write("ncu --set full --clock-control none --import-source on -k regex:k_hits -s 30 -c 1 python bench.py --steps 2 --warmup 1   (B200)\n")
-        f.write("one launch of k_hits inside the bench command: 2^22 NR events (0-100 keV flat, LUX_Run03), ~3.3e8 S1 PMT hits\n\n")
-        for h, u, v in zip(hdr, units, vals):
-            if h in want or ("issue_stalled" in h and "per_issue_active" in h):
-                f.write("%-92s %-16s %s\n" % (h, u, v))
-    src = os.path.join(ROOT, "gpurun_out", "_src_%s.csv" % tag)
-    open(src, "w").write(subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], stdout=subprocess.PIPE, text=True).stdout)
+    kernels = [("k_hits", "_ZN2nb6k_hitsENS_9RunParamsE", rep)]
+    for short, mangled in (("k_pre", "_ZN2nb5k_preENS_9RunParamsEPi"), ("k_post", "_ZN2nb6k_postENS_9RunParamsEPi")):
+        cand = rep.replace("k_hits", short)
+        if cand != rep and os.path.exists(cand):
+            kernels.append((short, mangled, cand))
     sassd = os.path.join(ROOT, "gpurun_out", "sass")
     os.makedirs(sassd, exist_ok=True)
     for fn in os.listdir(sassd):
@@ -78,9 +63,31 @@ def main():
     cub = [fn for fn in os.listdir(sassd) if fn.endswith(".cubin")][0]
     open(os.path.join(sassd, "all.sass"), "w").write(
         subprocess.run(["nvdisasm", "-g", cub], cwd=sassd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout)
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_by_line.py"), src, os.path.join(sassd, "all.sass"),
-                        KERNEL, "24"], stdout=subprocess.PIPE, text=True).stdout
-    open(os.path.join(out, "%s_k_hits_by_function.txt" % tag), "w").write(r)
+    want = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+            "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+            "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+            "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+            "sm__inst_executed_pipe_fp64.sum.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.sum.pct_of_peak_sustained_active",
+            "sm__inst_executed_pipe_alu.sum.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.sum.pct_of_peak_sustained_active",
+            "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio", "dram__bytes_read.sum",
+            "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+            "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__cycles_elapsed.avg", "sm__cycles_elapsed.avg.per_second",
+            "launch__shared_mem_per_block_static", "launch__shared_mem_per_block_dynamic", "local_load_store__"]
+    for short, mangled, krep in kernels:
+        raw = subprocess.run(["ncu", "-i", krep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
+        rr = list(csv.reader(raw.splitlines()))
+        hdr, units, vals = rr[0], rr[1], rr[2]
+        with open(os.path.join(out, "%s_%s_ncu_full.txt" % (tag, short)), "w") as f:
+            f.write("ncu --set full --clock-control none --import-source on -k regex:%s -s 30 -c 1 python bench.py --steps 2 --warmup 1 --no-cpu-baseline   (B200)\n" % short)
+            f.write("one launch of %s inside the bench command: 2^22 NR events (0-100 keV flat, LUX_Run03), ~3.3e8 S1 PMT hits\n\n" % short)
+            for h, u, v in zip(hdr, units, vals):
+                if h in want or ("issue_stalled" in h and "per_issue_active" in h) or h.startswith("smsp__inst_executed_op_local") or h.startswith("l1tex__t_bytes_pipe_lsu_mem_local"):
+                    f.write("%-92s %-16s %s\n" % (h, u, v))
+        src = os.path.join(ROOT, "gpurun_out", "_src_%s_%s.csv" % (tag, short))
+        open(src, "w").write(subprocess.run(["ncu", "-i", krep, "--page", "source", "--csv"], stdout=subprocess.PIPE, text=True).stdout)
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_by_line.py"), src, os.path.join(sassd, "all.sass"),
+                            mangled, "24"], stdout=subprocess.PIPE, text=True).stdout
+        open(os.path.join(out, "%s_%s_by_function.txt" % (tag, short)), "w").write(r)
     print(open(os.path.join(out, "%s_bench_launch_list.txt" % tag)).read()[:900])
 
 
