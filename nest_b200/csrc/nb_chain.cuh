@@ -204,10 +204,11 @@ NB_D void xy_resolution(Stream& g, const nb200_detector& det, double x, double y
   double kappa = det.PosResBase;
   double sigmaR = kappa / sqrt(A_top);
   sigmaR = sqrt(sigmaR * sigmaR + det.PosResFlat * det.PosResFlat);
-  double phi2 = 2. * g.uniform();  // phi = 2 pi u
+  uint32_t pa, pb;
+  g.next2(pa, pb);  // phi = 2 pi u, u from 32 bits
   sigmaR = fabs(gauss(g, 0.0, sigmaR, false));
   double s, c;
-  sincospi(phi2, &s, &c);
+  sincos_bits(pa, s, c);
   double sigmaX = sigmaR * c, sigmaY = sigmaR * s;
   if (sigmaR > 1e2 || isnan(sigmaR) || sigmaR < 0. || fabs(sigmaX) > 1e2 || fabs(sigmaY) > 1e2) {
     if (A_top > 40.) {
@@ -747,10 +748,13 @@ NB_D double reconstruct_energy(const RunParams& P, const Yields& y, const double
         keV = (Nph + Ne) * P.rc.Wq_eV * 1e-3;
       else if (P.species <= NB200_Cf) {
         const double* n = P.model.NRYieldsParam;
-        keV = pow((Ne + Nph) / n[0], 1. / n[1]);
+        // x^y = exp(y ln x) with the bit-built logarithm: a reconstructed (smeared) energy, not one of
+        // the deterministic yields held to 1e-12 -- its error (~|y ln x| 1e-16) is far below either
+        const double inv = 1. / n[1];
+        keV = exp(inv * log_pos((Ne + Nph) / n[0]));
         Ne *= 1. - 1. / pow_small(1. + pow_small((keV / n[5]), n[6]), n[10]);
         Nph *= 1. - 1. / pow_small(1. + pow_small((keV / n[7]), n[8]), n[11]);
-        keV = pow((Ne + Nph) / n[0], 1. / n[1]);
+        keV = exp(inv * log_pos((Ne + Nph) / n[0]));
       } else {
         const double logden = log10(P.rc.rho);
         const double Wq_eV_alpha =

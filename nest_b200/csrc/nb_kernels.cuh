@@ -204,7 +204,9 @@ __global__ void __launch_bounds__(kPreBlock, NB_PRE_MINB)
       if (ranXY && (guard == 0 || S.fixed_pos == 0)) {
         double r = det.radius * sqrt(g.uniform());
         double sn, cs;
-        sincospi(2. * g.uniform(), &sn, &cs);
+        uint32_t pa, pb;
+        g.next2(pa, pb);  // phi = 2 pi u, u from 32 bits
+        sincos_bits(pa, sn, cs);
         px = r * cs;
         py = r * sn;
       }
