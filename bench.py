@@ -34,6 +34,23 @@ F_HIT = 192.0
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "execNEST_ref_lux")
 
 
+
+def ncu_traffic():
+    """DRAM bytes of one k_hits launch from the committed `ncu --set full` capture (profiles/): the kernel
+    has no HBM stream of its own -- it reads hit counts and writes three words per event."""
+    import glob
+    import re
+    best = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_k_hits_ncu_full.txt")))
+    if not best:
+        return {"traffic": None}
+    tot = 0.0
+    for ln in open(best[-1]):
+        m = re.match(r"dram__bytes_(read|write)\.sum\s+(\S+)\s+([0-9.]+)", ln)
+        if m:
+            tot += float(m.group(3)) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[m.group(2)]
+    return {"traffic": tot, "traffic_unit": "bytes per launch (dram read + write)",
+            "traffic_source": os.path.relpath(best[-1], ROOT)}
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -291,7 +308,7 @@ def main():
         chain_ms = sum(stage_ms.values()) / a.steps
         out["roofline"] = {
             "bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "traffic": None, "kernel": "k_hits", "kernel_ms_per_launch": hits_ms,
+            **ncu_traffic(), "kernel": "k_hits", "kernel_ms_per_launch": hits_ms,
             "kernel_launches": int(n_hit_launches), "hits_per_launch": events_per_launch * mean_hits,
             "flops_per_hit": F_HIT, "mean_s1_hits": mean_hits,
             "stage_ms_per_step": {k: v / a.steps for k, v in stage_ms.items()},
