@@ -35,6 +35,24 @@ REF_BIN = os.path.join(ROOT, "oracle", "_ref", "execNEST_ref_lux")
 
 
 
+
+def bind_to_gpu_cpus(local):
+    """Multi-rank runs: keep this rank (and the pinned buffers it first-touches) on the CPUs NVML reports as
+    closest to its GPU -- what `numactl --cpunodebind` would do for a user.  Best effort; returns the set."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        near = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        mine = near & os.sched_getaffinity(0)
+        if mine:
+            os.sched_setaffinity(0, mine)
+            return sorted(mine)
+    except Exception:
+        pass
+    return None
+
 def ncu_traffic():
     """DRAM bytes of one k_hits launch from the committed `ncu --set full` capture (profiles/): the kernel
     has no HBM stream of its own -- it reads hit counts and writes three words per event."""
@@ -166,6 +184,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the chain has no CPU fallback")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_cpus(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -293,7 +312,8 @@ def main():
         "gpu_launches": int(gpu_launches),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "events_per_step_per_gpu": ne, "steps": e2e_steps,
-                "api": "nb200_run (C-ABI), pinned host SoA of the 14 CLI columns + band"},
+                "api": "nb200_run (C-ABI), pinned host SoA of the 14 CLI columns + band",
+                "cpu_affinity": numa},
         "clocks": sampler.summary(),
     }
 
