@@ -9,11 +9,68 @@
 // event loop on the GPU through the C-ABI (include/nest_b200.h).  User detectors subclass VDetector
 // exactly as before; their virtual position maps are tabulated once (nest_b200_flatten.hh).
 #pragma once
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
 #include <cstdint>
+#include <numeric>
 #include <string>
 #include <vector>
 
 #include "nest_b200.h"
+
+// What detector headers written for the reference take from NEST.hh, which the reference's translation
+// units include ahead of them (include/NEST/NEST.hh:105-111): the waveform constants ...
+#ifndef SAMPLE_SIZE
+#define SAMPLE_SIZE 10  // ns
+#define PULSE_WIDTH 10  // ns
+#define PULSEHEIGHT 0.005
+#define SPIKES_MAXM 120
+#define PHE_MAX 140
+#endif
+
+// ... and the RandomGen singleton (include/NEST/RandomGen.hh:16-36).  The event loop never draws from
+// it -- the GPU chain owns its counter-based streams -- but user hooks such as OptTrans /
+// SinglePEWaveForm call it, so the interface is kept (host SplitMix64; same distributions as
+// src/RandomGen.cpp:39-85).
+class RandomGen {
+ public:
+  static RandomGen* rndm() {
+    static RandomGen r;
+    return &r;
+  }
+  void SetSeed(uint64_t s) { state_ = s; }
+  void LockSeed() {}
+  void UnlockSeed() {}
+  double rand_uniform() {
+    uint64_t z = (state_ += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (double(z >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+  }
+  double rand_gauss(double mean, double sigma, bool zero_min = false) {
+    double u = rand_uniform(), v = rand_uniform();
+    double d = mean + sigma * std::sqrt(2.) * std::sqrt(-std::log(u)) * std::cos(2. * M_PI * v);
+    return zero_min ? std::max(d, 0.) : d;
+  }
+  double rand_zero_trunc_gauss(double mean, double sigma) {
+    double r = rand_gauss(mean, sigma);
+    while (r <= 0.) r = rand_gauss(mean, sigma);
+    return r;
+  }
+  double rand_exponential(double half_life, double t_min = -1, double t_max = -1) {
+    double r = rand_uniform(), r_min = 0, r_max = 1;
+    if (t_min >= 0) r_min = 1 - std::exp(-t_min * std::log(2.) / half_life);
+    if (t_max >= 0) r_max = 1 - std::exp(-t_max * std::log(2.) / half_life);
+    r = (r_max - r_min) * r + r_min;
+    return -std::log(1 - r) * half_life / std::log(2.);
+  }
+
+ private:
+  RandomGen() = default;
+  uint64_t state_ = 0x853C49E6748FEA9Bull;
+};
 
 #define NB_DET_SCALAR(T, name, dflt)       \
  protected:                                \
@@ -36,6 +93,10 @@ class VDetector {
   virtual std::vector<double> FitDirEF(double, double, double) { return {0, 0, 1}; }
   virtual double FitS2(double, double, LCE) { return 1.; }
   virtual std::vector<double> FitTBA(double, double, double) { return {0.5, 0.5}; }
+  // photon-timing hooks (VDetector.hh:150-154): declared so that detector headers overriding them
+  // compile unchanged; the waveform modes that call them are outside this path
+  virtual double OptTrans(double, double, double) { return 0.; }
+  virtual std::vector<double> SinglePEWaveForm(double, double) { return {0.}; }
 
   const double* get_noiseBaseline() const { return noiseBaseline; }
   const double* get_noiseLinear() const { return noiseLinear; }

@@ -140,3 +140,38 @@ def test_cli_mono_energy_summary(cli, args, ncol):
     for a, b, tol in zip(sg, sr, [0.01, 0.05, 0.01, 0.05, 0.01, 0.05, 0.02, 0.01]):
         # (41.5 keV sits above maxS1 of analysis.hh: the reference prints 999 / -0 / nan there, and so must we)
         assert (np.isnan(a) and np.isnan(b)) or abs(a - b) <= tol * abs(b), (sg, sr)
+
+
+LZ_CLI = os.path.join(ROOT, "oracle", "_ref", "execNEST_b200_lz")
+
+
+@pytest.mark.parametrize("args", [("30000", "NR", "0", "70", "-1", "-1", "1"),
+                                  ("30000", "beta", "0.1", "20", "96.5", "-1", "2")])
+def test_unmodified_lz_detector_header_matches_the_shipped_reference(args):
+    """The reference as shipped instantiates LZ_Detector_2024 (include/Detectors/LZ_WS2024.hh) with the
+    analysis_G2.hh settings.  oracle/_ref/execNEST_b200_lz is nest-b200's command line compiled with that
+    same, unmodified detector header against the VDetector mirror (maps -> (r,z) lookup tables):
+    statistically the same rows and band as oracle/_ref/execNEST_ref."""
+    if not (os.path.exists(LZ_CLI) and os.path.exists(refprobe.REF_BIN)):
+        pytest.skip("oracle/_ref/execNEST_b200_lz or execNEST_ref not built (needs the reference tree at build time)")
+    rc_g, out_g, err_g = run(LZ_CLI, args)
+    rc_r, out_r, err_r = run(refprobe.REF_BIN, args)
+    assert rc_g == 0 and rc_r == 0, (err_g[-400:], err_r[-400:])
+    g, r = rows_of(out_g), rows_of(out_r)
+    # analysis_G2.hh prints only the events above threshold (PrintSubThr): the row COUNT is itself a
+    # binomial variable -- equal within 5 sigma, not identical
+    n = int(args[0])
+    assert g.shape[1] == r.shape[1] == 14 and 0 < r.shape[0] <= n
+    assert abs(g.shape[0] - r.shape[0]) < 5 * np.sqrt(2 * max(n - r.shape[0], 25)), (g.shape, r.shape)
+    names = ["keV", "field", "dt", "x", "y", "z", "Nph", "Ne", "S1", "S1c", "spikeC", "Nee", "S2", "S2c"]
+    for j, nme in enumerate(names):
+        if np.all(g[:, j] == g[0, j]):
+            assert np.all(r[:, j] == g[0, j]), nme
+            continue
+        p = stats.ks_2samp(g[:, j], r[:, j]).pvalue
+        assert p > 1e-4, (nme, p, g[:, j].mean(), r[:, j].mean())
+    bg, br = band_of(err_g), band_of(err_r)
+    assert bg.shape == br.shape and bg.shape[0] > 10
+    assert np.array_equal(bg[:, 0], br[:, 0])
+    cm, cw, dof = band_chi2(bg, br)
+    assert cm < 2.5 and cw < 2.5, (cm, cw, dof)
