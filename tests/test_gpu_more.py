@@ -136,3 +136,27 @@ def test_chunked_launch_equals_single_and_properties_at_size(ctx):
     assert np.all(np.diff(b[ok][:, 1]) > 0)                    # mean S1 rises bin by bin
     assert np.all((b[ok][:, 2] > ana.logMin) & (b[ok][:, 2] < ana.logMax))
     assert np.all((b[ok][:, 5] > 0) & (b[ok][:, 5] <= 1))
+
+
+def test_full_size_config2_is_the_sum_of_its_eight_shards(ctx):
+    """BASELINE config 2 at its full size (1e8 NR events): the band of one run equals, word for word,
+    the sum of the eight contiguous id ranges an 8-GPU job would simulate (nest_b200/shard.py)"""
+    from nest_b200 import shard
+    ana = capi.analysis(0)
+    det = capi.detector("LUX_Run03")
+    rc = capi.prepare(det, 180.0)
+    mo = capi.model(1)
+    src = capi.source(capi.SRC_FLAT, capi.NR, 0.0, 100.0, 180.0)
+    n = 100_000_000
+    full = capi.Band(ana)
+    ctx.run(det, mo, ana, src, rc, 1, n, columns=[], band=full)
+    parts = capi.Band(ana)
+    for r in range(8):
+        lo, hi = shard.event_range(r, 8, n)
+        ctx.run(det, mo, ana, src, rc, 1, hi - lo, first_event=lo, columns=[], band=parts)
+    assert np.array_equal(full.words(), parts.words())
+    assert full.c.n_events == n == parts.c.n_events
+    acc = int(full.accepted.sum())
+    assert abs(acc / n - 0.619) < 0.005        # fraction of 0-100 keV NR events inside the S1/S2 window
+    b = full.finalize()
+    assert np.all(np.diff(b[:, 1]) > 0) and np.all(b[:, 4] < 2e-3)   # every bin populated: mean error < 0.002 dex
