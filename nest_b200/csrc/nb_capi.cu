@@ -212,6 +212,7 @@ int build_params(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo,
     // P(T <= 0 | S = s) = Phi(-(m0 + rho s)/tau) < 2^-64  <=>  m0 + rho s > 9.1 tau
     P->pe_cut = P->pe_rho > 0. ? (9.1 * P->pe_tau - P->pe_m0) / P->pe_rho : -DBL_MAX;
     P->pe_fast = 1.5341205443525465 * P->pe_tau;  // Phi(1.5341205...) = 15/16
+    P->pe_inv_tau16 = P->pe_tau > 0. ? 16. / P->pe_tau : 0.;
     double t = ceil(det->P_dphe * 16777216.0 - 0.5);
     P->dphe_thr24 = t <= 0. ? 0u : (t >= 16777216.0 ? 16777216u : uint32_t(t));
   }
@@ -424,6 +425,15 @@ int nb200_create(int device, nb200_ctx** out) {
     return NB200_ECUDA;
   }
   c->stream = c->own_stream;
+  {  // Phi table of the photo-electron acceptance bounds (nb_chain.cuh)
+    double tab[NB_PHI_N];
+    for (int k = 0; k < NB_PHI_N; ++k) tab[k] = 0.5 * erfc(-(-8. + double(k) / 16.) * 0.70710678118654752440);
+    if (cudaMemcpyToSymbol(g_phitab, tab, sizeof tab) != cudaSuccess) {
+      g_err_noctx = std::string("context setup: ") + cudaGetErrorString(cudaGetLastError());
+      nb200_destroy(c);
+      return NB200_ECUDA;
+    }
+  }
   *out = c;
   return 0;
 }
