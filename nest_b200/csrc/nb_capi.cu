@@ -283,10 +283,16 @@ int build_params(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo,
 
 // events per internal chunk: the workspace holds one chunk (140 B/event); large enough that the
 // ragged last wave of each kernel is a few per cent of its run time
-constexpr uint64_t kChunk = 1ull << 22;
+// ~2^22, rounded to a whole number of waves of the one-block-per-SM lockstep kernel (k_post: sm_count blocks
+// of 1024 events per sweep; 28 sweeps of 148 x 1024 on B200), which also makes it a whole number of k_hits
+// groups per resident block
+uint64_t chunk_events(const nb200_ctx* c) {
+  const uint64_t wave = uint64_t(c->sm_count > 0 ? c->sm_count : 148) * 1024u;
+  return std::max<uint64_t>(1, ((1ull << 22) + wave / 2) / wave) * wave;
+}
 
 int ensure_workspace(nb200_ctx* c, uint64_t n, Work* w) {
-  const uint64_t need = std::min<uint64_t>(kChunk, std::max<uint64_t>(n, 1024));
+  const uint64_t need = std::min<uint64_t>(chunk_events(c), std::max<uint64_t>(n, 1024));
   if (need > c->work_cap) {
     if (c->d_work) cudaFree(c->d_work);
     c->d_work = nullptr;
@@ -858,7 +864,7 @@ int nb200_run(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo, co
   // copies); NB200_HOST_CHUNK_LOG2 overrides for tuning
   int host_log2 = 20;  // measured on B200: 2^20 gives 5.06e8 events/s end to end, 2^21 4.93e8, 2^18 4.82e8
   if (const char* e = std::getenv("NB200_HOST_CHUNK_LOG2")) host_log2 = std::min(22, std::max(16, atoi(e)));
-  const uint64_t chunk_max = host_soa ? (1ull << host_log2) : (1ull << 22);
+  const uint64_t chunk_max = host_soa ? (1ull << host_log2) : chunk_events(c);
   const uint64_t cap = std::min<uint64_t>(n_events, chunk_max);
   const size_t ncol = (sizeof(nb200_soa_out) - 8) / sizeof(void*);
   struct Col {

@@ -113,14 +113,14 @@ def test_wimp_source(ctx, ref):
 
 
 def test_chunked_launch_equals_single_and_properties_at_size(ctx):
-    """N beyond one internal chunk (2^22 events): same integers as the sum of its parts, and the
+    """N beyond one internal chunk (~2^22 events): same integers as the sum of its parts, and the
     size-independent invariants of the band accumulator"""
     ana = capi.analysis(0)
     det = capi.detector("LUX_Run03")
     rc = capi.prepare(det, 180.0)
     mo = capi.model(1)
     src = capi.source(capi.SRC_FLAT, capi.NR, 0.0, 100.0, 180.0)
-    n = (1 << 22) + 12345
+    n = (1 << 22) + 312345     # the internal chunk is 28 x 148 x 1024 = 4 243 456 events on a B200
     full = capi.Band(ana)
     ctx.run(det, mo, ana, src, rc, 1, n, columns=[], band=full)
     parts = capi.Band(ana)
