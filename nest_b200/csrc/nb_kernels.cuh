@@ -317,13 +317,10 @@ NB_D void hit_commit(const RunParams& P, unsigned long long* s_area, unsigned in
 }
 
 // slow path, up to 32 queued hits: everything the reference does for a hit beyond one normal
-#if 1  // out of line: its register needs must not shape the main loop (3.75 -> 3.28 ms)
-__device__ __noinline__ void hits_finish_slow(
-#else
-NB_D void hits_finish_slow(
-#endif
-const RunParams& P, const int* s_pref, unsigned long long* s_area, unsigned int* s_spike,
-                           uint64_t ev0, const HitQueues& q, int first, int count, int lane, const double* lntab) {
+// (out of line: its register needs must not shape the main loop, 3.75 -> 3.28 ms)
+__device__ __noinline__ void hits_finish_slow(const RunParams& P, const int* s_pref, unsigned long long* s_area,
+                                             unsigned int* s_spike, uint64_t ev0, const HitQueues& q, int first,
+                                             int count, int lane, const double* lntab) {
   const nb200_detector& det = P.det;
   if (lane < count) {
     const HitEntry en = q.slow[first + lane];
@@ -375,12 +372,8 @@ const RunParams& P, const int* s_pref, unsigned long long* s_area, unsigned int*
 
 // fast path, up to 32 queued double-phe hits: draw the second photo-electron from the hit's own
 // block; the 0.4 % whose second draw needs the exact truncation test move on to the slow queue
-#ifdef NB_FAST_NOINLINE
-__device__ __noinline__ void hits_finish_fast(
-#else
-NB_D void hits_finish_fast(
-#endif
-const RunParams& P, unsigned long long* s_area, unsigned int* s_spike, uint64_t ev0,
+// (inlined: an out-of-line copy was measured slower)
+NB_D void hits_finish_fast(const RunParams& P, unsigned long long* s_area, unsigned int* s_spike, uint64_t ev0,
                            const HitQueues& q, int first, int count, int& scount, int lane, const double* lntab) {
   bool defer = false;
   HitEntry en{0., 0u, 0u};
