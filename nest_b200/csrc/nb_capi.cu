@@ -191,6 +191,17 @@ int build_params(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo,
     beta_field_terms(src->inField, rc->rho, mo->ERYieldsParam, P->hoist.b);
     gamma_field_terms(src->inField, rc->rho, P->hoist.g);
   }
+  P->z_direct = 0;
+  if (!src->vec_mode && src->inField >= 1. /* FIELD_MIN */ && rc->vD > 0. && (src->fixed_pos == 0 || src->fixed_pos == 2) &&
+      !(src->kind == NB200_SRC_LIST && src->x)) {
+    const double lo = std::max(0., det->TopDrift - rc->vD * det->dt_max);
+    const double hi = std::min(det->TopDrift, det->TopDrift - rc->vD * det->dt_min);
+    if (hi > lo) {
+      P->z_lo = lo;
+      P->z_hi = hi;
+      P->z_direct = 1;
+    }
+  }
   // per-run hoists (host maps evaluate the caller's LUT, not the device copy)
   const double zc = det->TopDrift - rc->vD_middle * det->dtCntr;
   P->s1_center = fit_s1(det->FitS1, 0., 0., zc);

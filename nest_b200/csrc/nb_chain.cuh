@@ -379,11 +379,17 @@ NB_D void s1_epilogue(Stream& g, const RunParams& P, const S1Pre& pre, const S1A
     sig = sqrt(a * a + b * b);
   } else
     sig = det.noiseLinear[0] * pulseArea;
-  // gauss(mu, 0, true) == max(mu, 0): skip the draw when the width is exactly zero
-  if (sig != 0.)
-    pulseArea = gauss(g, pulseArea, sig, true);
-  else
-    pulseArea = (pulseArea < 0.) ? 0. : pulseArea;
+  // gauss(mu, 0, true) == max(mu, 0): skip the draw when the width is exactly zero.  The Box-Muller
+  // partner of this draw serves the spike smearing below (independent normals)
+  double zB = 0.;
+  bool haveB = false;
+  if (sig != 0.) {
+    double zA;
+    normal_pair(g, zA, zB);
+    haveB = true;
+    pulseArea = pulseArea + sig * zA;
+  }
+  pulseArea = (pulseArea < 0.) ? 0. : pulseArea;
   if (pulseArea < det.sPEthr) pulseArea = 0.;
   if (spike < 0) spike = 0;
   double pulseAreaC = pulseArea / pre.posDepSm;
@@ -426,7 +432,10 @@ NB_D void s1_epilogue(Stream& g, const RunParams& P, const S1Pre& pre, const S1A
       out[6] = Nphd;
       out[7] = NphdC;
     } else {
-      double ns = zero_trunc_gauss(g, spike, (det.sPEres / 4.) * sqrt(fabs(spike)));
+      // rand_zero_trunc_gauss RandomGen.cpp:55-61 (redraw while <= 0)
+      const double sw = (det.sPEres / 4.) * sqrt(fabs(spike));
+      double ns = spike + sw * (haveB ? zB : normal(g));
+      for (int guard = 0; ns <= 0. && guard < 100000; ++guard) ns = spike + sw * normal(g);
       out[6] = ns;
       out[7] = ns / pre.fitSm * P.s1_center;
     }
@@ -466,12 +475,16 @@ NB_D void get_s2(Stream& g, uint64_t ev, const RunParams& P, int Ne, double tx, 
   const double life = exp(-dt / det.eLife_us);
   long long Nee = binomial(P.seed, ev, STREAM_BIN_NEE, Ne, ExtEff * life);
   double mu = elYield * double(Nee);
-  double nphd = floor(gauss(g, mu, sqrt(det.s2Fano * elYield * double(Nee)), true) + 0.5);
+  double z0, z1;  // one Box-Muller pair: photon number here, pulse area below
+  normal_pair(g, z0, z1);
+  double nraw = mu + sqrt(det.s2Fano * elYield * double(Nee)) * z0;
+  double nphd = floor(((nraw < 0.) ? 0. : nraw) + 0.5);
   long long Nph = (long long)nphd;
   long long nHits = binomial(P.seed, ev, STREAM_BIN_S2HIT, Nph, det.g1_gas * posDep);
   long long Nphe = nHits + binomial(P.seed, ev, STREAM_BIN_S2DPE, nHits, det.P_dphe);
   double m = double(Nphe) / P.rc.NewMean;
-  double pulseArea = gauss(g, m, det.sPEres * sqrt(m), true);
+  double pulseArea = m + det.sPEres * sqrt(m) * z1;
+  pulseArea = (pulseArea < 0.) ? 0. : pulseArea;
   double sig;
   if (det.noiseQuadratic[1] != 0) {
     double a = det.noiseQuadratic[1] * (pulseArea * pulseArea), b = det.noiseLinear[1] * pulseArea;

@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(kPreBlock, NB_PRE_MINB)
     const bool ranXY = (S.fixed_pos == 0 || S.fixed_pos == 3) && !listed;
     const bool ranZ = (S.fixed_pos == 0 || S.fixed_pos == 2) && !listed;
     for (int guard = 0; guard < 10000; ++guard) {  // Z_NEW loop execNEST.cpp:806-967
-      if (ranZ) pz = 0. + (det.TopDrift - 0.) * g.uniform();
+      if (ranZ) pz = P.z_direct ? fma(P.z_hi - P.z_lo, g.uniform(), P.z_lo) : 0. + (det.TopDrift - 0.) * g.uniform();
       if (ranXY && (guard == 0 || S.fixed_pos == 0)) {
         double r = det.radius * sqrt(g.uniform());
         double sn, cs;

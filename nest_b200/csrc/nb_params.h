@@ -66,6 +66,11 @@ struct RunParams {
   double recon_mult;     // MultFact prefactor, execNEST.cpp:1179-1182
   double wimp_dr0[9];    // WIMP_dRate(0) per Xe isotope             TestSpectra.cpp:459,466
   YieldHoist hoist;      // yield-model factors of (inField, rho), uniform field only
+  // uniform field + random z: the drift-window retry (execNEST.cpp:962-967) keeps exactly the z with
+  // dt = (TopDrift - z)/vD in [dt_min, dt_max], so z is drawn uniformly on that interval instead of
+  // redrawing 26 % of the LUX vertices (z_direct = 0: keep the retry loop)
+  double z_lo, z_hi;
+  int32_t z_direct, _pad_z;
   double band_width, band_border;  // GetBand bin geometry           execNEST.cpp:1521-1527
   // GetDriftVelocity_Liquid rows bracketing T_Kelvin (NEST.cpp:2429-2502); dv_mode 0 blend,
   // 1 = T on the lower node, 2 = T on the upper node
