@@ -190,6 +190,9 @@ int build_params(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo,
     P->hoist.nr_ti = nr_thomas_imel(src->inField, rc->rho, mo->NRYieldsParam);
     beta_field_terms(src->inField, rc->rho, mo->ERYieldsParam, P->hoist.b);
     gamma_field_terms(src->inField, rc->rho, P->hoist.g);
+    const double* wv = P->model.NRERWidthsParam;  // after the ion swap above
+    if (!(wv[9] > wv[8])) omega_er_consts(src->inField, wv, P->model.n_widths, P->hoist.w);
+    else P->hoist.w[0] = P->hoist.w[1] = P->hoist.w[2] = 0.;
   }
   P->z_direct = 0;
   if (!src->vec_mode && src->inField >= 1. /* FIELD_MIN */ && rc->vD > 0. && (src->fixed_pos == 0 || src->fixed_pos == 2) &&

@@ -24,16 +24,38 @@ NB_D double recomb_omega_nr(double elecFrac, const double* w) {
   return omega;
 }
 
-// NESTcalc::RecombOmegaER NEST.cpp:173-225 (the wide > cntr throw is checked on the host)
-NB_D double recomb_omega_er(double efield, double elecFrac, double numQuanta, const double* w,
-                            int nw) {
+// NESTcalc::RecombOmegaER NEST.cpp:173-225 (the wide > cntr throw is checked on the host).
+// omega_er_consts: the factors that depend on the field and the width vector only -- amplitude
+// (two pow) and the normalisations of the two skew-Gaussians (exp, erf, sqrt each); hoisted to the
+// host for a uniform field like the yield factors (YieldHoist::w).
+NB_HD void omega_er_consts(double efield, const double* w, int nw, double* o) {
   double ampl = 0.07 + (w[7] - 0.07) / pow(1. + pow(efield / 295.2, 251.6), 0.0069114);
   if (ampl < 0.) ampl = 0.;
-  double cntr = w[8], wide = w[9], skew = w[10];
-  double mode = cntr + 2. * NB_INV_SQRT2PI * skew * wide / sqrt(1. + skew * skew);
-  double dm = mode - cntr;
-  double norm =
-      1. / (exp(-0.5 * (dm * dm) / (wide * wide)) * (1. + erf(skew * (mode - cntr) / (wide * NB_SQRT2))));
+  const double cntr = w[8], wide = w[9], skew = w[10];
+  const double mode = cntr + 2. * NB_INV_SQRT2PI * skew * wide / sqrt(1. + skew * skew);
+  const double dm = mode - cntr;
+  o[0] = ampl;
+  o[1] = 1. / (exp(-0.5 * (dm * dm) / (wide * wide)) * (1. + erf(skew * (mode - cntr) / (wide * NB_SQRT2))));
+  double cntr2 = 5.207, wide2 = 1.361, skew2 = -2.495;
+  if (nw > 15) {
+    cntr2 = w[14];
+    wide2 = w[15];
+  }
+  if (nw > 16) skew2 = w[16];
+  const double mode2 = cntr2 + 2. * NB_INV_SQRT2PI * skew2 * wide2 / sqrt(1. + skew2 * skew2);
+  const double dm2 = mode2 - cntr2;
+  o[2] = 1. / (exp(-0.5 * (dm2 * dm2) / (wide2 * wide2)) * (1. + erf(skew2 * (mode2 - cntr2) / (wide2 * NB_SQRT2))));
+}
+NB_D double recomb_omega_er(double efield, double elecFrac, double numQuanta, const double* w, int nw,
+                            const YieldHoist* h) {
+  double cl[3];
+  const double* c = cl;
+  if (h && h->field == efield)
+    c = h->w;
+  else
+    omega_er_consts(efield, w, nw, cl);
+  const double ampl = c[0], norm = c[1];
+  const double cntr = w[8], wide = w[9], skew = w[10];
   double omega;
   if (cntr < 1.) {
     double d = elecFrac - cntr;
@@ -47,11 +69,8 @@ NB_D double recomb_omega_er(double efield, double elecFrac, double numQuanta, co
       wide2 = w[15];
     }
     if (nw > 16) skew2 = w[16];
-    double mode2 = cntr2 + 2. * NB_INV_SQRT2PI * skew2 * wide2 / sqrt(1. + skew2 * skew2);
+    const double norm2 = c[2];
     double logNQ = log10(numQuanta);
-    double dm2 = mode2 - cntr2;
-    double norm2 = 1. / (exp(-0.5 * (dm2 * dm2) / (wide2 * wide2)) *
-                         (1. + erf(skew2 * (mode2 - cntr2) / (wide2 * NB_SQRT2))));
     double d1 = logNQ - cntr, d2 = logNQ - cntr2;
     omega = 0.00 +
             norm * ampl * exp(-0.5 * (d1 * d1) / (wide * wide)) *
@@ -80,7 +99,7 @@ NB_D int to_int_round(double x) { return int(floor(x + 0.5)); }
 
 // NESTcalc::GetQuanta NEST.cpp:248-432
 NB_D Quanta get_quanta(Stream& g, uint64_t seed, uint64_t ev, const Yields& y, double density,
-                       const nb200_detector& det, const nb200_model& mo, int* err) {
+                       const nb200_detector& det, const nb200_model& mo, int* err, const YieldHoist* h = nullptr) {
   const double* w = mo.NRERWidthsParam;
   Quanta q{0, 0, 0, 0, 0., 0.};
   bool HighE;
@@ -143,7 +162,7 @@ NB_D Quanta get_quanta(Stream& g, uint64_t seed, uint64_t ev, const Yields& y, d
   }
 
   double omega = y.L < 1 ? recomb_omega_nr(elecFrac, w)
-                         : recomb_omega_er(y.field, elecFrac, Nq_mean, w, mo.n_widths);
+                         : recomb_omega_er(y.field, elecFrac, Nq_mean, w, mo.n_widths, h);
   double lambdaChen;
   if (w[2] < 0. && y.L < 1)
     lambdaChen = 1.0 + w[2];
@@ -529,51 +548,129 @@ NB_D void get_s2(Stream& g, uint64_t ev, const RunParams& P, int Ne, double tx, 
 
 // ---- energy sources: src/TestSpectra.cpp, execNEST.cpp:681-790 -----------------------------
 
-// TestSpectra::CH3T_spectrum TestSpectra.cpp:31-58 (Von Neumann rejection, yMax 1.1e7)
-NB_D double ch3t_spectrum(Stream& g, double xMin, double xMax) {
-  const double m_e = 510.9989461, aa = 0.0072973525664, ZZ = 2., qValue = 18.5898, yMax = 1.1e7;
-  if (xMax > qValue) xMax = qValue;
-  if (xMin < 0.) xMin = 0.;
+// The reference's spectra are box rejections (RandomGen::VonNeumann RandomGen.cpp:140-157):
+// x ~ U(xMin, xMax), y ~ U(0, yMax), keep the first pair with y <= f(x).  Candidate k of an event is
+// Philox block k of its stream, so WHICH candidate an event ends up with does not depend on who
+// evaluates it: when a full warp is sampling (the chain kernels), the lanes that already hold an
+// accepted energy evaluate further candidates of the lanes that do not -- floor(32 / needy) candidates
+// per needy lane and pass, the first accepted one (in stream order) wins.  A warp then finishes in
+// ~3 passes instead of the ~5 sequential tries of its unluckiest lane, and every event gets
+// bit for bit the energy the sequential loop gives (NB_COOP_REJECT=0 builds that loop;
+// tools/cmp_variants.py compares the two).
+#ifndef NB_COOP_REJECT
+#define NB_COOP_REJECT 1
+#endif
+template <class F>
+NB_D double box_reject(Stream& g, double xMin, double xMax, double yMax, const F& f) {
+#if NB_COOP_REJECT
+  const unsigned grp = __activemask();
+  if (grp == 0xffffffffu && __all_sync(grp, !g.have)) {
+    const int lane = int(threadIdx.x & 31u);
+    const unsigned lt = (1u << lane) - 1u;
+    uint32_t kdone = g.blk;  // next untried block of this lane's stream
+    double x = xMin;
+    bool need = true;
+    {
+      const u128 r = philox_block(g.e0, g.e1, kdone, g.sid, g.k0, g.k1);
+      const double x0 = xMin + (xMax - xMin) * u53(r.x, r.y);
+      const double y0 = yMax * u53(r.z, r.w);
+      ++kdone;
+      if (!(y0 > f(x0))) {
+        x = x0;
+        need = false;
+      }
+    }
+    unsigned nm = __ballot_sync(grp, need);
+    for (int pass = 0; nm && pass < 100000; ++pass) {
+      const int nneed = __popc(nm);
+      const int per = 32 / nneed;
+      const int j = lane / per, t = lane - j * per;
+      const bool serve = j < nneed;
+      const int target = serve ? nth_set_bit(nm, j) : lane;
+      const uint32_t te0 = __shfl_sync(grp, g.e0, target), te1 = __shfl_sync(grp, g.e1, target);
+      const uint32_t tk = __shfl_sync(grp, kdone, target);
+      bool ok = false;
+      double xc = 0.;
+      if (serve) {
+        const u128 r = philox_block(te0, te1, tk + uint32_t(t), g.sid, g.k0, g.k1);
+        xc = xMin + (xMax - xMin) * u53(r.x, r.y);
+        const double y0 = yMax * u53(r.z, r.w);
+        ok = !(y0 > f(xc));
+      }
+      const unsigned okm = __ballot_sync(grp, ok);
+      int src = lane;
+      bool got = false;
+      if (need) {
+        const int myj = __popc(nm & lt);
+        const unsigned seg = (per == 32) ? okm : ((okm >> (myj * per)) & ((1u << per) - 1u));
+        if (seg) {
+          const int tt = __ffs(int(seg)) - 1;
+          src = myj * per + tt;
+          got = true;
+          kdone += uint32_t(tt + 1);
+        } else
+          kdone += uint32_t(per);
+      }
+      const double xs = __shfl_sync(grp, xc, src);
+      if (got) {
+        x = xs;
+        need = false;
+      }
+      nm = __ballot_sync(grp, need);
+    }
+    g.blk = kdone;
+    g.have = false;
+    return x;
+  }
+#endif
   for (int it = 0; it < 100000; ++it) {
-    double x0 = xMin + (xMax - xMin) * g.uniform();
-    double y0 = yMax * g.uniform();
+    const double x0 = xMin + (xMax - xMin) * g.uniform();
+    const double y0 = yMax * g.uniform();
+    if (!(y0 > f(x0))) return x0;
+  }
+  return xMin;
+}
+
+// TestSpectra::CH3T_spectrum TestSpectra.cpp:31-58 (yMax 1.1e7)
+struct Ch3tShape {
+  NB_D double operator()(double x0) const {
+    const double m_e = 510.9989461, aa = 0.0072973525664, ZZ = 2., qValue = 18.5898;
     double B = sqrt(x0 * x0 + 2. * x0 * m_e) / (x0 + m_e);
     double x = (2. * NB_PI * ZZ * aa) * (x0 + m_e) / sqrt(x0 * x0 + 2. * x0 * m_e);
-    double f = (sqrt(2. * x0 * m_e) * (x0 + m_e) * (qValue - x0) * (qValue - x0) * x *
-                (1. / (1. - exp(-x))) * (1.002037 - 0.001427 * (B)));
-    if (!(y0 > f)) return x0;
+    return (sqrt(2. * x0 * m_e) * (x0 + m_e) * (qValue - x0) * (qValue - x0) * x * (1. / (1. - exp(-x))) *
+            (1.002037 - 0.001427 * (B)));
   }
-  return xMin;
+};
+NB_D double ch3t_spectrum(Stream& g, double xMin, double xMax) {
+  const double qValue = 18.5898, yMax = 1.1e7;
+  if (xMax > qValue) xMax = qValue;
+  if (xMin < 0.) xMin = 0.;
+  return box_reject(g, xMin, xMax, yMax, Ch3tShape());
 }
 // TestSpectra::B8_spectrum TestSpectra.cpp:110-128 (range forced to [0,5] keV)
-NB_D double b8_spectrum(Stream& g) {
-  const double m1 = -2.6455e-10, m2 = 5.0843;
-  const double xMin = 0., xMax = 5.;
-  const double yMax = pow(10., 3.4155);
-  for (int it = 0; it < 100000; ++it) {
-    double x0 = xMin + (xMax - xMin) * g.uniform();
-    double y0 = yMax * g.uniform();
+struct B8Shape {
+  NB_D double operator()(double x0) const {
+    const double m1 = -2.6455e-10, m2 = 5.0843;
     double f = 3.4155 - 1.2184 * x0 + 0.32849 * (x0 * x0) - 0.12441 * (x0 * x0 * x0) + m1 * exp(m2 * x0);
-    f = pow(10., f);
-    if (!(y0 > f)) return x0;
+    return pow(10., f);
   }
-  return xMin;
-}
+};
+NB_D double b8_spectrum(Stream& g) { return box_reject(g, 0., 5., pow(10., 3.4155), B8Shape()); }
 // TestSpectra::DD_spectrum TestSpectra.cpp:192-211
+struct DdShape {
+  double expFall, peakFrac, peakMu, peakSig, peakSkew;
+  NB_D double operator()(double x0) const {
+    double d = (x0 - peakMu) / peakSig;
+    return exp(-x0 / expFall) + peakFrac * exp(-(d * d)) * (erf(peakSkew * (x0 - peakMu) / peakSig) + 1);
+  }
+};
 NB_D double dd_spectrum(Stream& g, double xMin, double xMax, double expFall, double peakFrac,
                         double peakMu, double peakSig, double peakSkew) {
   if (xMax > 80.) xMax = 80.;
   if (xMin < 0.000) xMin = 0.000;
   double yMax = 1.;
   if (peakMu < xMax) yMax += peakFrac;
-  for (int it = 0; it < 100000; ++it) {
-    double x0 = xMin + (xMax - xMin) * g.uniform();
-    double y0 = yMax * g.uniform();
-    double d = (x0 - peakMu) / peakSig;
-    double f = exp(-x0 / expFall) + peakFrac * exp(-(d * d)) * (erf(peakSkew * (x0 - peakMu) / peakSig) + 1);
-    if (!(y0 > f)) return x0;
-  }
-  return xMin;
+  return box_reject(g, xMin, xMax, yMax, DdShape{expFall, peakFrac, peakMu, peakSig, peakSkew});
 }
 // TestSpectra::PowLawFit_spectrum TestSpectra.cpp:151-167 (AmBe, expo -0.95351)
 NB_D double powlaw_spectrum(Stream& g, double xMin, double xMax, double expo) {
@@ -596,27 +693,9 @@ NB_D double powlaw_spectrum(Stream& g, double xMin, double xMax, double expo) {
 // sensitive): C14_spectrum TestSpectra.cpp:60-108, Cf_spectrum :169-190, ppSolar_spectrum
 // :213-227, atmNu_spectrum :229-245.  Each is the reference's box rejection
 // (RandomGen::VonNeumann RandomGen.cpp:140-157): x ~ U(xMin,xMax), y ~ U(0,yMax), keep if y <= f(x).
-__device__ __noinline__ double rare_spectrum(Stream& g, int kind, double xMin, double xMax) {
-  double yMax = 1.;
-  if (kind == NB200_SRC_C14) {
-    if (xMax > 156.) xMax = 156.;
-    if (xMin < 0.) xMin = 0.;
-    yMax = 2.5e9;
-  } else if (kind == NB200_SRC_CF) {
-    if (xMax > 200.) xMax = 200.;
-    if (xMin < DBL_MIN) xMin = DBL_MIN;
-    yMax = 2. * pow(10., 3.7488);
-  } else if (kind == NB200_SRC_PPSOLAR) {
-    if (xMax > 250.) xMax = 250.;
-    if (xMin < 0.00) xMin = 0.00;
-    yMax = 0.000594;
-  } else {
-    if (xMax > 85.) xMax = 85.;
-    if (xMin < 0.0) xMin = 0.0;
-  }
-  for (int it = 0; it < 1000000; ++it) {
-    const double x0 = xMin + (xMax - xMin) * g.uniform();
-    const double y0 = yMax * g.uniform();
+struct RareShape {
+  int kind;
+  NB_D double operator()(double x0) const {
     double f;
     if (kind == NB200_SRC_C14) {
       const double m_e = 510.9989461, aa = 0.0072973525664, ZZ = 7., V0 = 0.495, qValue = 156.;
@@ -646,9 +725,28 @@ __device__ __noinline__ double rare_spectrum(Stream& g, int kind, double xMin, d
     } else {
       f = (1. + 0.0041482 * x0 + 0.00079972 * x0 * x0 - 1.0201e-5 * x0 * x0 * x0) * exp(-x0 / 12.355);
     }
-    if (!(y0 > f)) return x0;
+    return f;
   }
-  return xMin;
+};
+__device__ __noinline__ double rare_spectrum(Stream& g, int kind, double xMin, double xMax) {
+  double yMax = 1.;
+  if (kind == NB200_SRC_C14) {
+    if (xMax > 156.) xMax = 156.;
+    if (xMin < 0.) xMin = 0.;
+    yMax = 2.5e9;
+  } else if (kind == NB200_SRC_CF) {
+    if (xMax > 200.) xMax = 200.;
+    if (xMin < DBL_MIN) xMin = DBL_MIN;
+    yMax = 2. * pow(10., 3.7488);
+  } else if (kind == NB200_SRC_PPSOLAR) {
+    if (xMax > 250.) xMax = 250.;
+    if (xMin < 0.00) xMin = 0.00;
+    yMax = 0.000594;
+  } else {
+    if (xMax > 85.) xMax = 85.;
+    if (xMin < 0.0) xMin = 0.0;
+  }
+  return box_reject(g, xMin, xMax, yMax, RareShape{kind});
 }
 NB_D int xe_isotope_index(int A) {
   switch (A) {

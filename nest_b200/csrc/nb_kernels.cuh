@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(kPreBlock, NB_PRE_MINB)
       }
     }
     NB_LOCKSTEP();
-    if (!cli || keV > 0.001 * P.rc.Wq_eV) q = get_quanta(g, P.seed, ev, y, P.rc.rho, det, P.model, &err);
+    if (!cli || keV > 0.001 * P.rc.Wq_eV) q = get_quanta(g, P.seed, ev, y, P.rc.rho, det, P.model, &err, &P.hoist);
     NB_LOCKSTEP();
     if (cli && (det.noiseBaseline[2] != 0. || det.noiseBaseline[3] != 0.))
       q.electrons += to_int_round(gauss(g, det.noiseBaseline[2], det.noiseBaseline[3], false));

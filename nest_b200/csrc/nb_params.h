@@ -36,6 +36,7 @@ struct YieldHoist {
   double nr_ti;           // NR: ThomasImel
   double b[6];            // beta: m01, m03, m04, m07, m10, density correction of Qy
   double g[3];            // gamma: m1, m5, m7
+  double w[3];            // RecombOmegaER: amplitude(field), the two skew-Gaussian normalisations
 };
 
 struct RunParams {
