@@ -454,6 +454,16 @@ int nb200_create(int device, nb200_ctx** out) {
       return NB200_ECUDA;
     }
   }
+  {
+    double rcp[NB_RCP_N];
+    rcp[0] = 0.;
+    for (int k = 1; k < NB_RCP_N; ++k) rcp[k] = 1. / double(k);
+    if (cudaMemcpyToSymbol(g_rcptab, rcp, sizeof rcp) != cudaSuccess) {
+      g_err_noctx = std::string("context setup: ") + cudaGetErrorString(cudaGetLastError());
+      nb200_destroy(c);
+      return NB200_ECUDA;
+    }
+  }
   *out = c;
   return 0;
 }

@@ -390,6 +390,11 @@ NB_D double stirling_tail(double k) {
   return (1.0 / 12. - (1.0 / 360. - (1.0 / 1260.) * rk2) * rk2) * rk;
 }
 
+// 1/x for x = 0..255 (filled by nb200_create): the CDF-inversion recurrence of the binomial sampler
+// multiplies instead of dividing
+#define NB_RCP_N 256
+__device__ double g_rcptab[NB_RCP_N];
+
 // position of the n-th (0-based) set bit of m; n < popc(m)
 NB_D int nth_set_bit(unsigned m, int n) {
   int pos = 0, t;
@@ -483,7 +488,7 @@ __device__ __noinline__ long long binomial(uint64_t seed, uint64_t event, uint32
           ok = false;
           break;
         }
-        r *= s * (double(n - x + 1) / double(x));
+        r *= s * (double(n - x + 1) * __ldg(&g_rcptab[x]));  // x <= 200
       }
       if (ok) {
         k = x;
