@@ -19,25 +19,38 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared", "-ldl"]
 
 
-def needs_build():
-    if not os.path.exists(LIB):
+# TEST AID: the same library with the warp-cooperative evaluation of the BTRS bound, the cooperative box
+# rejection of the spectra and the table bounds of the photo-electron test switched off -- the plain per-lane
+# algorithms.  tests/test_gpu_variants.py requires the product library to reproduce it bit for bit.
+LIB_PLAIN = os.path.join(CSRC, "libnest_b200_plain.so")
+PLAIN_FLAGS = ["-DNB_BINOM_COOP=0", "-DNB_COOP_REJECT=0", "-DNB_PE_NO_BOUNDS"]
+
+
+def needs_build(lib=LIB):
+    if not os.path.exists(lib):
         return True
-    t = os.path.getmtime(LIB)
+    t = os.path.getmtime(lib)
     deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
-        return LIB
+def build(force=False, verbose=False, plain=True):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
-    r = subprocess.run(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if r.returncode != 0:
-        sys.stderr.write(r.stdout)
-        raise RuntimeError("nvcc failed building %s" % LIB)
-    if verbose:
-        sys.stderr.write(r.stdout)
+    jobs = []
+    for lib, extra in ((LIB, []), (LIB_PLAIN, PLAIN_FLAGS)):
+        if lib == LIB_PLAIN and not plain:
+            continue
+        if not force and not needs_build(lib):
+            continue
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", lib] + SOURCES
+        jobs.append((lib, subprocess.Popen(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for lib, p in jobs:  # the two compilations run side by side
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            sys.stderr.write(out)
+            raise RuntimeError("nvcc failed building %s" % lib)
+        if verbose:
+            sys.stderr.write(out)
     return LIB
 
 
