@@ -85,9 +85,14 @@ def main():
                     f.write("%-92s %-16s %s\n" % (h, u, v))
         src = os.path.join(ROOT, "gpurun_out", "_src_%s_%s.csv" % (tag, short))
         open(src, "w").write(subprocess.run(["ncu", "-i", krep, "--page", "source", "--csv"], stdout=subprocess.PIPE, text=True).stdout)
-        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_by_line.py"), src, os.path.join(sassd, "all.sass"),
-                            mangled, "24"], stdout=subprocess.PIPE, text=True).stdout
-        open(os.path.join(out, "%s_%s_by_function.txt" % (tag, short)), "w").write(r)
+        if short == "k_hits":  # everything inlined: attribute by inlined function and source line
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_by_line.py"), src,
+                                os.path.join(sassd, "all.sass"), mangled, "24"], stdout=subprocess.PIPE, text=True).stdout
+            open(os.path.join(out, "%s_%s_by_function.txt" % (tag, short)), "w").write(r)
+        # out-of-line subroutines (binomial, philox_block, box_muller, libm helpers) kept apart
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_by_label.py"), krep, mangled, "30"],
+                           stdout=subprocess.PIPE, text=True).stdout
+        open(os.path.join(out, "%s_%s_by_subroutine.txt" % (tag, short)), "w").write(r)
     print(open(os.path.join(out, "%s_bench_launch_list.txt" % tag)).read()[:900])
 
 
