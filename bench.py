@@ -317,6 +317,28 @@ def main():
         "clocks": sampler.summary(),
     }
 
+    if rank == 0 and world == 1:
+        # the other BASELINE configurations on the same device (band-only, device resident), for information:
+        # config 1 (ER flat 0.1-20 keV, the reference's own CPU-runnable case) and config 3 (CH3T, DD)
+        others = {}
+        for name, s_, er_model in [
+                ("config1_ER_flat_0.1-20keV", capi.source(capi.SRC_FLAT, capi.beta, 0.1, 20.0, 180.0), 0),
+                ("config3_CH3T", capi.source(capi.SRC_CH3T, capi.CH3T, 0.0, 18.5898, 180.0), -1),
+                ("config3_DD", capi.source(capi.SRC_DD, capi.DD, 0.0, 80.0, 180.0, par=(13., 0.12, 71.2, 20., -20.5)), -1)]:
+            m_ = capi.model(1)
+            m_.er_model = er_model
+            if s_.species >= 6:
+                m_.massNum = det.molarMass
+            n_ = 20_000_000
+            for rep in range(2):  # first pass warms up
+                band_t.zero_()
+                t0_, t1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0_.record()
+                ctx.run_async(det, m_, ana, s_, rc, seed, 0, n_)
+                t1_.record()
+                torch.cuda.synchronize()
+            others[name] = n_ / (t0_.elapsed_time(t1_) * 1e-3)
+        out["other_workloads_events_per_s"] = others
     if rank == 0:
         peak = ctx.fp64_peak()
         # dominant kernel: k_hits, the per-hit S1 loop.  Algorithmic work per launch = SURVEY 8(d)'s
