@@ -652,7 +652,7 @@ struct B8Shape {
   NB_D double operator()(double x0) const {
     const double m1 = -2.6455e-10, m2 = 5.0843;
     double f = 3.4155 - 1.2184 * x0 + 0.32849 * (x0 * x0) - 0.12441 * (x0 * x0 * x0) + m1 * exp(m2 * x0);
-    return pow(10., f);
+    return exp(2.302585092994045684 * f);  // 10^f; a rejection bound, 1e-15 is ample
   }
 };
 NB_D double b8_spectrum(Stream& g) { return box_reject(g, 0., 5., pow(10., 3.4155), B8Shape()); }
@@ -718,7 +718,7 @@ struct RareShape {
       const double l = log10(x0);
       f = 3.7488 - 0.77942 * l + 1.30300 * (l * l) - 2.75280 * (l * l * l) + 1.57310 * ((l * l) * (l * l)) -
           0.30072 * ((l * l) * (l * l) * l);
-      f = pow(10., f);
+      f = exp(2.302585092994045684 * f);  // 10^f
       f *= 1.9929 - .033214 * x0 + .00032857 * (x0 * x0) - 1.000e-6 * (x0 * x0 * x0);
     } else if (kind == NB200_SRC_PPSOLAR) {
       f = 9.2759e-6 - 3.5556e-8 * x0 - 5.4608e-12 * x0 * x0;
