@@ -764,36 +764,158 @@ NB_D int xe_isotope_index(int A) {
 // TestSpectra::WIMP_spectrum TestSpectra.cpp:456-499.  WIMP_dRate(0, m, day) depends only on
 // the random isotope it draws (:278), so its 9 possible values are tabulated on the host
 // (P.wimp_dr0) and every call of the reference becomes an isotope draw + lookup.
-NB_D double wimp_spectrum(Stream& g, const RunParams& P) {
+//
+// The reference's nested loops are one flat sequence of ATTEMPTS: a point (x, y), two fresh
+// isotope draws a, b for the triangle pre-cut y <= -a/xMax x + b (:465-475), and -- only if the
+// point survives it -- the table lookup, the Von Neumann test y <= f(x) and one tick of the
+// 100-try counter (:476-495).  Stream layout: block 0 = the isotope of yMax; attempt k = blocks
+// 1+2k (x, y) and 2+2k (a, b).  With that layout an attempt can be evaluated by any lane, and a
+// full warp shares the work as box_reject does: the spectrum is steep (a few per cent of the box), a
+// lane needs ~10 attempts and a warp would wait for its unluckiest lane's ~30.
+NB_D int xe_isotope_of(double u01) {
+  double iso = u01 * 100.;
+  if (iso <= 0.090) return 124;
+  if (iso <= 0.180) return 126;
+  if (iso <= 2.100) return 128;
+  if (iso <= 28.54) return 129;
+  if (iso <= 32.62) return 130;
+  if (iso <= 53.80) return 131;
+  if (iso <= 80.69) return 132;
+  if (iso <= 91.13) return 134;
+  return 136;
+}
+struct WimpAttempt {
+  double x0;
+  bool passed;  // survived the triangle pre-cut: the Von Neumann test ran (one tick of the counter)
+  bool acc;     // ... and accepted
+  bool odd;     // no table interval holds x0: the reference would reuse the previous f (:458) -- replay
+};
+NB_D WimpAttempt wimp_attempt(const RunParams& P, uint32_t e0, uint32_t e1, uint32_t sid, uint32_t k0, uint32_t k1,
+                              uint32_t k, double yMax) {
   const nb200_source& S = P.src;
-  const double xMax = S.wimp_xMax, xMin = 0.;
-  const double step = 1. / S.wimp_divisor;
+  const double xMax = S.wimp_xMax, step = 1. / S.wimp_divisor;
+  const u128 r = philox_block(e0, e1, 1u + 2u * k, sid, k0, k1);
+  const u128 q = philox_block(e0, e1, 2u + 2u * k, sid, k0, k1);
+  WimpAttempt w;
+  w.x0 = xMax * u53(r.x, r.y);
+  const double y0 = yMax * u53(r.z, r.w);
+  const double a = P.wimp_dr0[xe_isotope_index(xe_isotope_of(u53(q.x, q.y)))];
+  const double b = P.wimp_dr0[xe_isotope_index(xe_isotope_of(u53(q.z, q.w)))];
+  w.passed = !(y0 > (-a / xMax * w.x0 + b));
+  w.acc = false;
+  w.odd = false;
+  if (w.passed) {
+    const int idx = int(w.x0 * S.wimp_divisor);
+    const double xl = double(idx) * step;
+    if (idx >= 0 && idx < 100 && xl < xMax && w.x0 > xl && w.x0 < xl + step)
+      w.acc = !(y0 > S.wimp_base[idx] * exp(-S.wimp_exponent[idx] * w.x0));
+    else
+      w.odd = true;
+  }
+  return w;
+}
+// the literal sequential algorithm (persisting f), from attempt 0
+NB_D double wimp_sequential(const RunParams& P, const Stream& g, double yMax, uint32_t& attempts) {
+  const nb200_source& S = P.src;
+  const double xMax = S.wimp_xMax, step = 1. / S.wimp_divisor;
   int count = 0;
   double f = 0.00;  // FuncValue persists across tries (:458)
-  double yMax = P.wimp_dr0[xe_isotope_index(select_xe_atom(g))];
-  double x0 = xMin + (xMax - xMin) * g.uniform();
-  double y0 = yMax * g.uniform();
-  for (;;) {
-    for (int guard = 0; guard < 100000; ++guard) {  // triangle pre-cut (:465-475)
-      double a = P.wimp_dr0[xe_isotope_index(select_xe_atom(g))];
-      double b = P.wimp_dr0[xe_isotope_index(select_xe_atom(g))];
-      if (!(y0 > (-a / xMax * x0 + b))) break;
-      x0 = (xMax - xMin) * g.uniform();
-      y0 = yMax * g.uniform();
-    }
-    // table interval lookup (:476-487): open interval (x, x + 1/divisor), x < xMax
-    int idx = int(x0 * S.wimp_divisor);
-    double xl = double(idx) * step;
+  for (uint32_t k = 0; k < 1000000u; ++k) {
+    const u128 r = philox_block(g.e0, g.e1, 1u + 2u * k, g.sid, g.k0, g.k1);
+    const u128 q = philox_block(g.e0, g.e1, 2u + 2u * k, g.sid, g.k0, g.k1);
+    const double x0 = xMax * u53(r.x, r.y), y0 = yMax * u53(r.z, r.w);
+    const double a = P.wimp_dr0[xe_isotope_index(xe_isotope_of(u53(q.x, q.y)))];
+    const double b = P.wimp_dr0[xe_isotope_index(xe_isotope_of(u53(q.z, q.w)))];
+    attempts = k + 1u;
+    if (y0 > (-a / xMax * x0 + b)) continue;  // triangle pre-cut (:465-475)
+    const int idx = int(x0 * S.wimp_divisor);  // open interval (x, x + 1/divisor), x < xMax (:476-487)
+    const double xl = double(idx) * step;
     if (idx >= 0 && idx < 100 && xl < xMax && x0 > xl && x0 < xl + step)
       f = S.wimp_base[idx] * exp(-S.wimp_exponent[idx] * x0);
-    const bool rejected = y0 > f;  // RandomGen::VonNeumann RandomGen.cpp:140-157
-    if (rejected) {
-      x0 = xMin + (xMax - xMin) * g.uniform();
-      y0 = 0. + (yMax - 0.) * g.uniform();
-    }
-    if (++count >= 100) return 0.;  // :491-495, taken even when the 100th try was accepted
+    const bool rejected = y0 > f;           // RandomGen::VonNeumann RandomGen.cpp:140-157
+    if (++count >= 100) return 0.;           // :491-495, taken even when the 100th try was accepted
     if (!rejected) return x0;
   }
+  return 0.;
+}
+NB_D double wimp_spectrum(Stream& g, const RunParams& P) {
+  // requires a fresh stream (the first draw of the event)
+  const u128 r0 = philox_block(g.e0, g.e1, 0u, g.sid, g.k0, g.k1);
+  const double yMax = P.wimp_dr0[xe_isotope_index(xe_isotope_of(u53(r0.x, r0.y)))];
+  uint32_t attempts = 0;
+  double x = 0.;
+#if NB_COOP_REJECT
+  const unsigned grp = __activemask();
+  if (grp == 0xffffffffu) {
+    const int lane = int(threadIdx.x & 31u);
+    const unsigned lt = (1u << lane) - 1u;
+    int count = 0;
+    bool need = true, replay = false;
+    {
+      const WimpAttempt w = wimp_attempt(P, g.e0, g.e1, g.sid, g.k0, g.k1, 0u, yMax);
+      attempts = 1u;
+      if (w.odd)
+        replay = true, need = false;
+      else if (w.passed) {
+        count = 1;
+        if (w.acc) x = w.x0, need = false;
+      }
+    }
+    unsigned nm = __ballot_sync(grp, need);
+    for (int pass = 0; nm && pass < 100000; ++pass) {
+      const int nneed = __popc(nm);
+      const int per = 32 / nneed;
+      const int j = lane / per, t = lane - j * per;
+      const bool serve = j < nneed;
+      const int target = serve ? nth_set_bit(nm, j) : lane;
+      const uint32_t te0 = __shfl_sync(grp, g.e0, target), te1 = __shfl_sync(grp, g.e1, target);
+      const uint32_t tk = __shfl_sync(grp, attempts, target);
+      const double tyMax = __shfl_sync(grp, yMax, target);
+      WimpAttempt w{0., false, false, false};
+      if (serve) w = wimp_attempt(P, te0, te1, g.sid, g.k0, g.k1, tk + uint32_t(t), tyMax);
+      const unsigned pm = __ballot_sync(grp, w.passed), am = __ballot_sync(grp, w.acc), om = __ballot_sync(grp, w.odd);
+      int src = lane;
+      bool got = false;
+      if (need) {
+        const int myj = __popc(nm & lt);
+        const unsigned segmask = (per == 32) ? 0xffffffffu : ((1u << per) - 1u);
+        const unsigned ps = (pm >> (myj * per)) & segmask, as = (am >> (myj * per)) & segmask,
+                       os = (om >> (myj * per)) & segmask;
+        const int t_acc = as ? __ffs(int(as)) - 1 : 64;
+        const int t_odd = os ? __ffs(int(os)) - 1 : 64;
+        const int to100 = 100 - count;  // >= 1
+        const int t_bail = (__popc(ps) >= to100) ? nth_set_bit(ps, to100 - 1) : 64;
+        const int t_first = min(t_acc, min(t_odd, t_bail));
+        if (t_first == 64) {  // nothing decisive in this batch
+          count += __popc(ps);
+          attempts += uint32_t(per);
+        } else if (t_odd == t_first) {
+          replay = true;
+          need = false;
+        } else if (t_bail == t_first) {  // the counter runs out first (bail-out wins over acceptance)
+          x = 0.;
+          attempts += uint32_t(t_bail + 1);
+          need = false;
+        } else {
+          src = myj * per + t_acc;
+          got = true;
+          attempts += uint32_t(t_acc + 1);
+        }
+      }
+      const double xs = __shfl_sync(grp, w.x0, src);
+      if (got) {
+        x = xs;
+        need = false;
+      }
+      nm = __ballot_sync(grp, need);
+    }
+    if (replay) x = wimp_sequential(P, g, yMax, attempts);
+  } else
+#endif
+    x = wimp_sequential(P, g, yMax, attempts);
+  g.blk = 1u + 2u * attempts;
+  g.have = false;
+  return x;
 }
 
 // energy per event: execNEST.cpp:681-790

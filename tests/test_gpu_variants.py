@@ -27,6 +27,6 @@ def test_cooperative_paths_are_bit_identical_to_the_plain_algorithms():
         pytest.skip("libnest_b200_plain.so not built (python -c 'import __graft_entry__ as g; g.build()')")
     n = 2_000_000
     a, b = hashes(nb_build.LIB, n), hashes(nb_build.LIB_PLAIN, n)
-    assert a.keys() == b.keys() and len(a) == 8
+    assert a.keys() == b.keys() and len(a) == 9
     for k in a:
         assert a[k] == b[k], "configuration %s differs between the product and the plain build" % k
