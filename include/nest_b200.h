@@ -337,6 +337,15 @@ int nb200_fp64_peak(nb200_ctx* ctx, double* tflops);
  * pointers.  Used by tests/test_gpu_hitmath.py to hold them to 1e-15 against libm. */
 int nb200_debug_hitmath(nb200_ctx* ctx, size_t n, const uint32_t* bits3, double* out3);
 
+/* Test hook: the standard normals of the S1 hit loop (256-layer ziggurat, replacing the
+ * Box-Muller of RandomGen::rand_gauss, src/RandomGen.cpp:44-53, for the per-hit draws of
+ * NEST.cpp:1367-1429), drawn exactly as the hit kernel draws them: pair p = hits 2(p%1024),
+ * 2(p%1024)+1 of event first_event + p/1024.  out = 2*pairs doubles, kind = 2*pairs bytes or
+ * NULL (0: layer core, 1: wedge / tail completion); host pointers.
+ * tests/test_gpu_samplers.py holds them to N(0,1) (KS, moments, tail mass). */
+int nb200_debug_normal(nb200_ctx* ctx, uint64_t seed, uint64_t first_event, size_t pairs, double* out,
+                       unsigned char* kind);
+
 /* Test hook: `count` draws of the chain's binomial sampler (the device replacement of
  * RandomGen::binom_draw, src/RandomGen.cpp:132-134) with n trials of probability p, draw i on
  * the stream of event first_event + i; out = count int64 on the host.

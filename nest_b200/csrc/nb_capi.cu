@@ -24,7 +24,7 @@ struct nb200_ctx {
   cudaStream_t stream = nullptr;
   std::string err;
   uint64_t launches = 0;
-  int* d_err = nullptr;
+  int* d_err = nullptr;  // [0] error flags of the kernels, [1] k_hits group counter
   // device-resident band accumulator (async API)
   unsigned long long* d_band = nullptr;
   bool band_external = false;
@@ -227,8 +227,8 @@ int build_params(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo,
     P->pe_cut = P->pe_rho > 0. ? (9.1 * P->pe_tau - P->pe_m0) / P->pe_rho : -DBL_MAX;
     P->pe_fast = 1.5341205443525465 * P->pe_tau;  // Phi(1.5341205...) = 15/16
     P->pe_inv_tau16 = P->pe_tau > 0. ? 16. / P->pe_tau : 0.;
-    double t = ceil(det->P_dphe * 16777216.0 - 0.5);
-    P->dphe_thr24 = t <= 0. ? 0u : (t >= 16777216.0 ? 16777216u : uint32_t(t));
+    double t = ceil(det->P_dphe * 4194304.0 - 0.5);
+    P->dphe_thr22 = t <= 0. ? 0u : (t >= 4194304.0 ? 4194304u : uint32_t(t));
   }
   {
     const double sq2 = sqrt(2.);
@@ -339,8 +339,9 @@ int launch_event(nb200_ctx* c, RunParams& P) {
   }
   if (!c->occ_pre) {
     NB_CUDA(c, cudaFuncSetAttribute(k_post, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    NB_CUDA(c, cudaFuncSetAttribute(k_hits, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kHitDynSmem)));
     NB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_pre, k_pre, kPreBlock, 0));
-    NB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_hits, k_hits, kHitBlock, 0));
+    NB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_hits, k_hits, kHitBlock, kHitDynSmem));
     if (c->occ_pre < 1) c->occ_pre = 1;
     if (c->occ_hits < 1) c->occ_hits = 1;
   }
@@ -356,7 +357,7 @@ int launch_event(nb200_ctx* c, RunParams& P) {
     Q.chunk_off = P.chunk_off + off;
     const uint64_t sm = uint64_t(c->sm_count);
     unsigned g_pre = unsigned(std::min<uint64_t>((m + kPreBlock - 1) / kPreBlock, sm * c->occ_pre * 8));
-    unsigned g_hits = unsigned(std::min<uint64_t>((m + kHitGroup - 1) / kHitGroup, sm * c->occ_hits * 4));
+    unsigned g_hits = unsigned(std::min<uint64_t>((m + kHitGroup - 1) / kHitGroup, sm * c->occ_hits));  // persistent
     unsigned g_post = unsigned(std::min<uint64_t>((m + kPostBlock - 1) / kPostBlock, sm * c->occ_post));
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     if (c->timing)
@@ -364,7 +365,8 @@ int launch_event(nb200_ctx* c, RunParams& P) {
     if (c->timing) cudaEventRecord(ev[0], c->stream);
     k_pre<<<g_pre, kPreBlock, 0, c->stream>>>(Q, c->d_err);
     if (c->timing) cudaEventRecord(ev[1], c->stream);
-    k_hits<<<g_hits, kHitBlock, 0, c->stream>>>(Q);
+    cudaMemsetAsync(c->d_err + 1, 0, sizeof(int), c->stream);
+    k_hits<<<g_hits, kHitBlock, kHitDynSmem, c->stream>>>(Q, reinterpret_cast<unsigned int*>(c->d_err + 1));
     if (c->timing) cudaEventRecord(ev[2], c->stream);
     k_post<<<g_post, kPostBlock, smem, c->stream>>>(Q, c->d_err);
     if (c->timing) {
@@ -439,7 +441,7 @@ int nb200_create(int device, nb200_ctx** out) {
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaMalloc(&c->d_err, sizeof(int)) != cudaSuccess || cudaMemset(c->d_err, 0, sizeof(int)) != cudaSuccess) {
+      cudaMalloc(&c->d_err, 2 * sizeof(int)) != cudaSuccess || cudaMemset(c->d_err, 0, 2 * sizeof(int)) != cudaSuccess) {
     g_err_noctx = std::string("context setup: ") + cudaGetErrorString(cudaGetLastError());
     delete c;
     return NB200_ECUDA;
@@ -449,6 +451,45 @@ int nb200_create(int device, nb200_ctx** out) {
     double tab[NB_PHI_N];
     for (int k = 0; k < NB_PHI_N; ++k) tab[k] = 0.5 * erfc(-(-8. + double(k) / 16.) * 0.70710678118654752440);
     if (cudaMemcpyToSymbol(g_phitab, tab, sizeof tab) != cudaSuccess) {
+      g_err_noctx = std::string("context setup: ") + cudaGetErrorString(cudaGetLastError());
+      nb200_destroy(c);
+      return NB200_ECUDA;
+    }
+  }
+  {  // ziggurat layers of the hit loop's normal sampler (nb_rng.cuh): solve R so that the layers of
+     // equal area V = R f(R) + tail(R) close exactly at f = 1
+    double zx[NB_ZIG_N + 1], zf[NB_ZIG_N + 1], zw[NB_ZIG_N];
+    uint32_t zk[NB_ZIG_N];
+    auto f = [](double x) { return std::exp(-0.5 * x * x); };
+    auto fill = [&](double R) -> double {  // returns f at the top minus 1 (> 0: R too small)
+      const double V = R * f(R) + 1.2533141373155002512 * std::erfc(R * 0.70710678118654752440);
+      zx[0] = V / f(R);
+      zx[1] = R;
+      for (int i = 1; i < NB_ZIG_N; ++i) {
+        const double fi = f(zx[i]) + V / zx[i];
+        if (i == NB_ZIG_N - 1) return fi - 1.;
+        if (fi >= 1.) return double(NB_ZIG_N - i);
+        zx[i + 1] = std::sqrt(-2. * std::log(fi));
+      }
+      return 0.;
+    };
+    double lo = 3.0, hi = 5.0;
+    for (int it = 0; it < 200; ++it) {
+      const double mid = 0.5 * (lo + hi);
+      (fill(mid) > 0. ? lo : hi) = mid;
+    }
+    fill(hi);
+    zx[NB_ZIG_N] = 0.;
+    for (int i = 1; i <= NB_ZIG_N; ++i) zf[i] = f(zx[i]);
+    zf[0] = 0.;
+    zf[NB_ZIG_N] = 1.;
+    for (int i = 0; i < NB_ZIG_N; ++i) {
+      zk[i] = uint32_t(std::floor(268435456.0 * (zx[i + 1] / zx[i])));
+      zw[i] = zx[i] / 268435456.0;
+    }
+    const double R = zx[1];
+    if (cudaMemcpyToSymbol(g_zig_k, zk, sizeof zk) != cudaSuccess || cudaMemcpyToSymbol(g_zig_w, zw, sizeof zw) != cudaSuccess ||
+        cudaMemcpyToSymbol(g_zig_f, zf, sizeof zf) != cudaSuccess || cudaMemcpyToSymbol(g_zig_R, &R, sizeof R) != cudaSuccess) {
       g_err_noctx = std::string("context setup: ") + cudaGetErrorString(cudaGetLastError());
       nb200_destroy(c);
       return NB200_ECUDA;
@@ -1201,6 +1242,30 @@ int nb200_debug_hitmath(nb200_ctx* c, size_t n, const uint32_t* bits3, double* o
   cudaError_t e = cudaStreamSynchronize(c->stream);
   cudaFree(db);
   cudaFree(dout);
+  if (e != cudaSuccess) return fail(c, NB200_ECUDA, cudaGetErrorString(e));
+  return 0;
+}
+
+int nb200_debug_normal(nb200_ctx* c, uint64_t seed, uint64_t first_event, size_t pairs, double* out,
+                       unsigned char* kind) {
+  if (!c || !out) return NB200_EINVAL;
+  if (pairs == 0) return 0;
+  NB_CUDA(c, cudaSetDevice(c->device));
+  double* dout = nullptr;
+  unsigned char* dk = nullptr;
+  NB_CUDA(c, cudaMalloc(&dout, pairs * 16));
+  if (kind && cudaMalloc(&dk, pairs * 2) != cudaSuccess) {
+    cudaFree(dout);
+    return fail(c, NB200_ENOMEM, "cudaMalloc");
+  }
+  k_zignormal<<<unsigned(std::min<size_t>((pairs + 255) / 256, 148 * 8)), 256, 0, c->stream>>>(seed, first_event, pairs,
+                                                                                             dout, dk);
+  ++c->launches;
+  cudaMemcpyAsync(out, dout, pairs * 16, cudaMemcpyDeviceToHost, c->stream);
+  if (kind) cudaMemcpyAsync(kind, dk, pairs * 2, cudaMemcpyDeviceToHost, c->stream);
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  cudaFree(dout);
+  cudaFree(dk);
   if (e != cudaSuccess) return fail(c, NB200_ECUDA, cudaGetErrorString(e));
   return 0;
 }

@@ -306,7 +306,7 @@ struct S1Acc {
 //   * hits needing anything more (exact truncation test, second photo-electron, efficiency or
 //     coincidence draws) are queued per warp and finished 32 at a time (k_hits);
 //   * -20 ln u < coinWind is tested as u > exp(-coinWind/20) and only when nHits <= coinLevel.
-enum : uint32_t { HIT_CHK1 = 1u, HIT_DP = 2u, HIT_CHK2 = 4u, HIT_SPECIAL = 8u };
+enum : uint32_t { HIT_CHK1 = 1u, HIT_DP = 2u, HIT_CHK2 = 4u, HIT_SPECIAL = 8u, HIT_ZIG = 16u };
 
 // Phi(z) at z = -8 + k/16, k = 0..272, filled by nb200_create (host erfc).  Linear interpolation
 // between neighbours is within 1.18e-4 of Phi (h^2/8 max|Phi''| = (1/16)^2/8 * 0.242).
@@ -349,19 +349,25 @@ NB_D bool pe_accept_exact(const RunParams& P, double sv, double u) {
   return u < p;
 }
 
-// joint redraw of (S, T) after a failed truncation check: sequential stream, rare
+// joint redraw of (S, T) after a failed truncation check (0.35 % of photo-electrons): one block per
+// attempt, both normals from the hit loop's ziggurat (tables read from global memory here)
+NB_D double zig_normal_g(uint32_t w0, uint32_t w1, uint32_t e0, uint32_t e1, uint32_t k, uint32_t stream, uint32_t k0,
+                         uint32_t k1) {
+  const int32_t t = zig_t(w0);
+  const uint32_t i = w1 >> (32 - NB_ZIG_BITS);
+  if (uint32_t(abs(t)) < __ldg(&g_zig_k[i])) return zig_td(t) * __ldg(&g_zig_w[i]);
+  return zig_finish(w0, w1, 0u, false, e0, e1, k, stream, k0, k1);
+}
 __device__ __noinline__ double pe_redraw(uint64_t seed, uint64_t event, uint32_t blk, double pe_mu, double pe_sig,
                                          double pe_cut, double pe_tau, double pe_rho, double pe_m0) {
-  Stream x;
-  x.init(seed, event, STREAM_HITX);
-  x.blk = blk;
+  const uint32_t k0 = uint32_t(seed), k1 = uint32_t(seed >> 32), e0 = uint32_t(event), e1 = uint32_t(event >> 32);
   double sv = pe_mu;
 #pragma unroll 1
-  for (int guard = 0; guard < 60; ++guard) {
-    double zs, zt;
-    normal_pair(x, zs, zt);
-    sv = fma(pe_sig, zs, pe_mu);
+  for (uint32_t a = 0; a < 32u; ++a) {  // callers space blk by 32
+    const u128 b = philox_block(e0, e1, blk + a, STREAM_HITX, k0, k1);
+    sv = fma(pe_sig, zig_normal_g(b.x, b.y, e0, e1, blk + a, STREAM_ZIGX, k0, k1), pe_mu);
     if (sv > pe_cut) break;
+    const double zt = zig_normal_g(b.z, b.w, e0, e1, blk + a, STREAM_ZIGX + 1u, k0, k1);
     if (fma(pe_tau, zt, fma(pe_rho, sv, pe_m0)) > 0.) break;
   }
   return sv;

@@ -154,7 +154,7 @@ NB_D double drift_velocity_dev(const RunParams& P, double eField) {
 #define NB_POST_MINB 1
 #endif
 #ifndef NB_HIT_MINB
-#define NB_HIT_MINB 4
+#define NB_HIT_MINB 3  // 80 registers: at 64 (4 blocks/SM) the hit loop reloads spilled loop state every iteration (2.65 vs 2.56 ms)
 #endif
 constexpr int kPreBlock = NB_PRE_BLOCK;
 constexpr int kPostBlock = NB_POST_BLOCK;
@@ -302,11 +302,20 @@ struct HitEntry {  // 16 bytes: one STS.128 / LDS.128 per queued hit
 // collected and run 32 at a time instead of one lane at a time inside the fast path.
 constexpr int kFastCap = 96;  // <= 31 left over + 64 pushed per pair iteration
 constexpr int kSlowCap = 64;  // <= 31 left over + 32 handed on by one fast pass
+constexpr size_t kHitDynSmem = NB_ZIG_N * (sizeof(double) + sizeof(uint32_t));  // ziggurat tables (opt-in: > 48 KB total)
 struct HitQueues {
   HitEntry* fast;
   HitEntry* slow;
   double* slow_s2;
+  const uint32_t* zk;  // ziggurat tables staged in shared memory (nb_rng.cuh)
+  const double* zw;
 };
+
+NB_D void sts_entry(uint32_t shared_addr, double s1, uint32_t k, uint32_t slot_flags) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(shared_addr), "r"(__double2loint(s1)),
+               "r"(__double2hiint(s1)), "r"(k), "r"(slot_flags)
+               : "memory");
+}
 
 NB_D void hit_commit(const RunParams& P, unsigned long long* s_area, unsigned int* s_spike, int slot, double a,
                      bool pass_coin) {
@@ -320,12 +329,13 @@ NB_D void hit_commit(const RunParams& P, unsigned long long* s_area, unsigned in
 // (out of line: its register needs must not shape the main loop, 3.75 -> 3.28 ms)
 __device__ __noinline__ void hits_finish_slow(const RunParams& P, const int* s_pref, unsigned long long* s_area,
                                              unsigned int* s_spike, uint64_t ev0, const HitQueues& q, int first,
-                                             int count, int lane, const double* lntab) {
+                                             int count, int lane) {
   const nb200_detector& det = P.det;
   if (lane < count) {
     const HitEntry en = q.slow[first + lane];
     double s1 = en.s1;
-    const uint32_t k = en.k, flags = en.slot_flags & 0xFFu;
+    const uint32_t k = en.k;
+    uint32_t flags = en.slot_flags & 0xFFu;
     const int slot = int(en.slot_flags >> 8);
     const uint64_t ev = ev0 + slot;
     const uint32_t e0 = uint32_t(ev), e1 = uint32_t(ev >> 32);
@@ -337,15 +347,23 @@ __device__ __noinline__ void hits_finish_slow(const RunParams& P, const int* s_p
       if (!pe_accept_exact(P, s2, u53(t.x, t.y)))
         s2 = pe_redraw(P.seed, ev, k * 64u + 32u, P.pe_mu, P.pe_sig, P.pe_cut, P.pe_tau, P.pe_rho, P.pe_m0);
     } else {
+      if (flags & HIT_ZIG) {  // the hit's own normal fell outside its ziggurat layer's core
+        const u128 m = philox4x32_10_rk(e0, e1, k >> 1, STREAM_HIT, P.rk);
+        const uint32_t w0 = (k & 1u) ? m.z : m.x, w1 = (k & 1u) ? m.w : m.y;
+        s1 = fma(P.pe_sig,
+                 zig_finish(w0, w1, r.z, true, e0, e1, k, STREAM_ZIG, uint32_t(P.seed), uint32_t(P.seed >> 32)), P.pe_mu);
+        if (s1 <= P.pe_cut && (fma(P.pe_rho, s1, P.pe_m0) < P.pe_fast || (w0 & 0xFu) == 15u)) flags |= HIT_CHK1;
+      }
       if (flags & HIT_CHK1) {
         if (!pe_accept_exact(P, s1, (double(r.w >> 12) + 0.5) * (1.0 / 1048576.0)))
           s1 = pe_redraw(P.seed, ev, k * 64u, P.pe_mu, P.pe_sig, P.pe_cut, P.pe_tau, P.pe_rho, P.pe_m0);
       }
       if (flags & HIT_DP) {
-        const double rad = sqrt(2.0 * neg_log_bits(r.x, r.y, lntab));
-        double sn, cs;
-        sincos_bits(r.z, sn, cs);
-        s2 = fma(P.pe_sig, rad * cs, P.pe_mu);
+        double z2;
+        if (!zig_fast(r.x, r.y, q.zk, q.zw, z2))
+          z2 = zig_finish(r.x, r.y, r.z, !(flags & HIT_ZIG), e0, e1, k, STREAM_ZIG2, uint32_t(P.seed),
+                          uint32_t(P.seed >> 32));
+        s2 = fma(P.pe_sig, z2, P.pe_mu);
         if (s2 <= P.pe_cut && (fma(P.pe_rho, s2, P.pe_m0) < P.pe_fast || ((r.w >> 8) & 0xFu) == 15u)) {
           const u128 t = philox4x32_10_rk(e0, e1, k, STREAM_HIT4, P.rk);
           if (!pe_accept_exact(P, s2, u53(t.x, t.y)))
@@ -374,7 +392,7 @@ __device__ __noinline__ void hits_finish_slow(const RunParams& P, const int* s_p
 // block; the 0.4 % whose second draw needs the exact truncation test move on to the slow queue
 // (inlined: an out-of-line copy was measured slower)
 NB_D void hits_finish_fast(const RunParams& P, unsigned long long* s_area, unsigned int* s_spike, uint64_t ev0,
-                           const HitQueues& q, int first, int count, int& scount, int lane, const double* lntab) {
+                           const HitQueues& q, int first, int count, int& scount, int lane) {
   bool defer = false;
   HitEntry en{0., 0u, 0u};
   double s2 = 0.;
@@ -386,12 +404,14 @@ NB_D void hits_finish_fast(const RunParams& P, unsigned long long* s_area, unsig
       const int slot = int(en.slot_flags >> 8);
       const uint64_t ev = ev0 + slot;
       const u128 r = philox4x32_10_rk(uint32_t(ev), uint32_t(ev >> 32), en.k, STREAM_HIT2, P.rk);
-      const double rad = sqrt(2.0 * neg_log_bits(r.x, r.y, lntab));
-      double sn, cs;
-      sincos_bits(r.z, sn, cs);
-      s2 = fma(P.pe_sig, rad * cs, P.pe_mu);
-      defer = s2 <= P.pe_cut && (fma(P.pe_rho, s2, P.pe_m0) < P.pe_fast || ((r.w >> 8) & 0xFu) == 15u);
-      if (defer)
+      double z2;
+      const bool core = zig_fast(r.x, r.y, q.zk, q.zw, z2);
+      s2 = fma(P.pe_sig, z2, P.pe_mu);
+      const bool chk = s2 <= P.pe_cut && (fma(P.pe_rho, s2, P.pe_m0) < P.pe_fast || ((r.w >> 8) & 0xFu) == 15u);
+      defer = !core || chk;
+      if (!core)
+        ;  // wedge or tail: the slow finisher redoes this draw in full (flags stay HIT_DP)
+      else if (chk)
         en.slot_flags = (en.slot_flags & 0xFFFFFF00u) | HIT_CHK2;
       else
         hit_commit(P, s_area, s_spike, slot, en.s1 + s2, true);
@@ -410,7 +430,7 @@ NB_D void hits_finish_fast(const RunParams& P, unsigned long long* s_area, unsig
 }
 
 __global__ void __launch_bounds__(kHitBlock, NB_HIT_MINB)
-    k_hits(const __grid_constant__ RunParams P) {
+    k_hits(const __grid_constant__ RunParams P, unsigned int* __restrict__ next_group) {
   __shared__ int s_pref[kHitGroup + 1];   // hit-count prefix (events)
   __shared__ int s_ppref[kHitGroup + 1];  // pair-count prefix: the flattened work items
   __shared__ unsigned long long s_area[kHitGroup];
@@ -420,17 +440,29 @@ __global__ void __launch_bounds__(kHitBlock, NB_HIT_MINB)
   __shared__ __align__(16) HitEntry s_qf[kHitBlock / 32][kFastCap];
   __shared__ __align__(16) HitEntry s_qs[kHitBlock / 32][kSlowCap];
   __shared__ double s_qs2[kHitBlock / 32][kSlowCap];
-  __shared__ __align__(16) double s_lntab[64];
-  if (threadIdx.x < 64) s_lntab[threadIdx.x] = c_lntab[threadIdx.x];
+  extern __shared__ __align__(16) double s_zw[];  // kHitDynSmem: zw[NB_ZIG_N] then zk[NB_ZIG_N]
+  uint32_t* const s_zk = reinterpret_cast<uint32_t*>(s_zw + NB_ZIG_N);
+  for (int i = threadIdx.x; i < NB_ZIG_N; i += kHitBlock) {
+    s_zw[i] = g_zig_w[i];
+    s_zk[i] = g_zig_k[i];
+  }
   constexpr int PER = kHitGroup / kHitBlock;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const nb200_detector& det = P.det;
   const Work& W = P.work;
   const uint64_t n_groups = (P.n_events + kHitGroup - 1) / kHitGroup;
-  const HitQueues q{s_qf[wid], s_qs[wid], s_qs2[wid]};
+  const HitQueues q{s_qf[wid], s_qs[wid], s_qs2[wid], s_zk, s_zw};
+  const uint32_t qf_addr = uint32_t(__cvta_generic_to_shared(&s_qf[wid][0]));
   const bool all_special = det.sPEeff < 1.;  // efficiency draws: every hit goes through the slow queue
 
-  for (uint64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+  // groups are handed out by a device counter (zeroed before the launch): their cost follows their hit
+  // counts, so a static stride leaves the last wave ragged
+  __shared__ unsigned int s_grp;
+  for (;;) {
+    if (tid == 0) s_grp = atomicAdd(next_group, 1u);
+    __syncthreads();
+    const uint64_t grp = s_grp;
+    if (grp >= n_groups) break;
     const uint64_t gbase = grp * kHitGroup;
     const uint64_t ev0 = P.first_event + P.chunk_off + gbase;
     // hit counts of my PER consecutive events -> exclusive prefixes (hits and pairs) over the group
@@ -465,10 +497,10 @@ __global__ void __launch_bounds__(kHitBlock, NB_HIT_MINB)
     const int H = s_ppref[kHitGroup];  // pairs in this group
     const int h0 = int((long long)H * tid / kHitBlock);
     const int h1 = int((long long)H * (tid + 1) / kHitBlock);
-    const int len = h1 - h0;
-    const int maxlen = __reduce_max_sync(0xffffffffu, len);
+    const int maxlen = __reduce_max_sync(0xffffffffu, h1 - h0);
     int e = 0, e_end = 0, ne = 0, j = 0;
-    if (len > 0) {
+    int h = h0;  // running pair index; this thread owns [h0, h1)
+    if (h1 > h0) {
       // event owning pair h0: largest e with s_ppref[e] <= h0
       int lo = 0, hi = kHitGroup;
       while (hi - lo > 1) {
@@ -486,11 +518,10 @@ __global__ void __launch_bounds__(kHitBlock, NB_HIT_MINB)
     unsigned long long a_fx = 0ull;
     unsigned int a_spike = 0u, a_nphe = 0u;
     int fcount = 0, scount = 0;  // warp-uniform queue fills
-    for (int i = 0; i < maxlen; ++i) {
-      const int h = h0 + i;
+    for (int it = maxlen; it > 0; --it) {
       uint32_t fa = 0u, fb = 0u;  // queue flags of the pair's two hits (0 = finished here)
       double sa = 0., sb = 0.;
-      if (i < len) {
+      if (h < h1) {
         if (h == e_end) {  // crossed into the next event with hits: flush, then advance
           atomicAdd(&s_area[e], a_fx);
           atomicAdd(&s_spike[e], a_spike);
@@ -504,24 +535,24 @@ __global__ void __launch_bounds__(kHitBlock, NB_HIT_MINB)
           ne = s_pref[e + 1] - s_pref[e];
           j = 0;
         }
-        // one Philox block and one Box-Muller transform for hits 2j and 2j+1 of this event
+        // one Philox block for hits 2j and 2j+1 of this event: 64 bits each -- 28 (abscissa) + 10
+        // (layer) for the ziggurat normal, 22 for the double-phe draw, 4 for the truncation pre-test
         const uint64_t hev = ev0 + e;
         const u128 r = philox4x32_10_rk(uint32_t(hev), uint32_t(hev >> 32), uint32_t(j), STREAM_HIT, P.rk);
-        const double rad = sqrt(2.0 * neg_log_bits(r.x, r.y & 0xFFFF0000u, s_lntab));
-        double sn, cs;
-        sincos_bits(r.z & 0xFFFFFF00u, sn, cs);
-        sa = fma(P.pe_sig, rad * cs, P.pe_mu);
-        sb = fma(P.pe_sig, rad * sn, P.pe_mu);
-        const uint32_t da = ((r.z & 0xFFu) << 16) | (r.w >> 16);
-        const uint32_t db = ((r.w & 0xFFFFu) << 8) | ((r.y >> 8) & 0xFFu);
+        double za, zb;
+        const bool ka = zig_fast(r.x, r.y, s_zk, s_zw, za), kb = zig_fast(r.z, r.w, s_zk, s_zw, zb);
+        sa = fma(P.pe_sig, za, P.pe_mu);
+        sb = fma(P.pe_sig, zb, P.pe_mu);
+        const uint32_t da = r.y & 0x3FFFFFu, db = r.w & 0x3FFFFFu;
         const bool hasb = (2 * j + 1) < ne;
         const uint32_t sp = (all_special || !(ne > det.coinLevel)) ? HIT_SPECIAL : 0u;
         // truncation pre-test (nb_params.h): above pe_cut nothing to do; below it a 4-bit uniform
-        // settles it unless it is 15 or the acceptance is under 15/16
-        const bool ca = sa <= P.pe_cut && (fma(P.pe_rho, sa, P.pe_m0) < P.pe_fast || ((r.y >> 4) & 0xFu) == 15u);
-        const bool cb = sb <= P.pe_cut && (fma(P.pe_rho, sb, P.pe_m0) < P.pe_fast || (r.y & 0xFu) == 15u);
-        fa = (ca ? HIT_CHK1 : 0u) | (da < P.dphe_thr24 ? HIT_DP : 0u) | sp;
-        fb = hasb ? ((cb ? HIT_CHK1 : 0u) | (db < P.dphe_thr24 ? HIT_DP : 0u) | sp) : 0u;
+        // settles it unless it is 15 or the acceptance is under 15/16.  A normal outside its
+        // layer's core (0.45 %) is completed, and then pre-tested, by the slow finisher.
+        const bool ca = sa <= P.pe_cut && (fma(P.pe_rho, sa, P.pe_m0) < P.pe_fast || (r.x & 0xFu) == 15u);
+        const bool cb = sb <= P.pe_cut && (fma(P.pe_rho, sb, P.pe_m0) < P.pe_fast || (r.z & 0xFu) == 15u);
+        fa = (ka ? (ca ? HIT_CHK1 : 0u) : HIT_ZIG) | (da < P.dphe_thr22 ? HIT_DP : 0u) | sp;
+        fb = hasb ? ((kb ? (cb ? HIT_CHK1 : 0u) : HIT_ZIG) | (db < P.dphe_thr22 ? HIT_DP : 0u) | sp) : 0u;
         a_nphe += 1u + ((fa >> 1) & 1u) + (hasb ? 1u + ((fb >> 1) & 1u) : 0u);
         if (fa == 0u && sa > det.sPEthr) {
           a_spike += 1u;
@@ -535,30 +566,36 @@ __global__ void __launch_bounds__(kHitBlock, NB_HIT_MINB)
       // queue the unfinished hits (the fast finisher passes the rare kinds on to the slow queue)
       const unsigned ma = __ballot_sync(0xffffffffu, fa != 0u), mb = __ballot_sync(0xffffffffu, fb != 0u);
       if (ma | mb) {
+        // lane-major order, one address computation, one 16-byte store per entry
         const unsigned lt = (1u << lane) - 1u;
-        if (fa) q.fast[fcount + __popc(ma & lt)] = HitEntry{sa, uint32_t(2 * j), (uint32_t(e) << 8) | fa};
-        if (fb) q.fast[fcount + __popc(ma) + __popc(mb & lt)] = HitEntry{sb, uint32_t(2 * j + 1), (uint32_t(e) << 8) | fb};
+        uint32_t at = qf_addr + uint32_t(fcount + __popc(ma & lt) + __popc(mb & lt)) * uint32_t(sizeof(HitEntry));
+        if (fa) {
+          sts_entry(at, sa, uint32_t(2 * j), (uint32_t(e) << 8) | fa);
+          at += uint32_t(sizeof(HitEntry));
+        }
+        if (fb) sts_entry(at, sb, uint32_t(2 * j + 1), (uint32_t(e) << 8) | fb);
         fcount += __popc(ma) + __popc(mb);
         __syncwarp();
         while (fcount >= 32) {
           fcount -= 32;
-          hits_finish_fast(P, s_area, s_spike, ev0, q, fcount, 32, scount, lane, s_lntab);
+          hits_finish_fast(P, s_area, s_spike, ev0, q, fcount, 32, scount, lane);
           while (scount >= 32) {
             scount -= 32;
-            hits_finish_slow(P, s_pref, s_area, s_spike, ev0, q, scount, 32, lane, s_lntab);
+            hits_finish_slow(P, s_pref, s_area, s_spike, ev0, q, scount, 32, lane);
           }
         }
       }
       ++j;
+      ++h;
     }
     // drain (the fast drain may add to the slow queue)
-    if (fcount > 0) hits_finish_fast(P, s_area, s_spike, ev0, q, 0, fcount, scount, lane, s_lntab);
+    if (fcount > 0) hits_finish_fast(P, s_area, s_spike, ev0, q, 0, fcount, scount, lane);
     while (scount > 0) {
       const int c = min(scount, 32);
       scount -= c;
-      hits_finish_slow(P, s_pref, s_area, s_spike, ev0, q, scount, c, lane, s_lntab);
+      hits_finish_slow(P, s_pref, s_area, s_spike, ev0, q, scount, c, lane);
     }
-    if (len > 0) {
+    if (h1 > h0) {
       atomicAdd(&s_area[e], a_fx);
       atomicAdd(&s_spike[e], a_spike);
       atomicAdd(&s_nphe[e], a_nphe);
@@ -745,6 +782,41 @@ __global__ void k_hitmath(size_t n, const uint32_t* __restrict__ bits, double* _
     out[3 * i] = neg_log_bits(bits[3 * i], bits[3 * i + 1], s_lntab);
     out[3 * i + 1] = s;
     out[3 * i + 2] = c;
+  }
+}
+
+// test hook (nb200_debug_normal): the hit loop's ziggurat normal exactly as k_hits and its slow
+// finisher draw it -- pair j of event `first + i`, both hits; kind[.] = 0 core, 1 wedge / tail
+__global__ void __launch_bounds__(256) k_zignormal(uint64_t seed, uint64_t first, size_t pairs,
+                                                   double* __restrict__ out, unsigned char* __restrict__ kind) {
+  __shared__ double s_zw[NB_ZIG_N];
+  __shared__ uint32_t s_zk[NB_ZIG_N];
+  for (int i = threadIdx.x; i < NB_ZIG_N; i += blockDim.x) {
+    s_zw[i] = g_zig_w[i];
+    s_zk[i] = g_zig_k[i];
+  }
+  __syncthreads();
+  uint32_t rk[20];
+  philox_round_keys(seed, rk);
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < pairs; i += size_t(gridDim.x) * blockDim.x) {
+    const uint64_t ev = first + (i >> 10);
+    const uint32_t j = uint32_t(i & 1023u), e0 = uint32_t(ev), e1 = uint32_t(ev >> 32);
+    const u128 r = philox4x32_10_rk(e0, e1, j, STREAM_HIT, rk);
+    double za, zb;
+    const bool ka = zig_fast(r.x, r.y, s_zk, s_zw, za), kb = zig_fast(r.z, r.w, s_zk, s_zw, zb);
+    // as hits_finish_slow: the spare word of the hit's STREAM_HIT2 block decides the first wedge test
+    if (!ka)
+      za = zig_finish(r.x, r.y, philox4x32_10_rk(e0, e1, 2 * j, STREAM_HIT2, rk).z, true, e0, e1, 2 * j, STREAM_ZIG,
+                      uint32_t(seed), uint32_t(seed >> 32));
+    if (!kb)
+      zb = zig_finish(r.z, r.w, philox4x32_10_rk(e0, e1, 2 * j + 1, STREAM_HIT2, rk).z, (j & 1u) != 0u, e0, e1, 2 * j + 1,
+                      STREAM_ZIG, uint32_t(seed), uint32_t(seed >> 32));
+    out[2 * i] = za;
+    out[2 * i + 1] = zb;
+    if (kind) {
+      kind[2 * i] = ka ? 0 : 1;
+      kind[2 * i + 1] = kb ? 0 : 1;
+    }
   }
 }
 

@@ -60,7 +60,7 @@ struct RunParams {
   // outright; only u4 == 15 or m < pe_fast needs Phi itself (exact residual test in the queue)
   double pe_fast;
   double pe_inv_tau16;   // 16 / pe_tau: index scale of the Phi bounds table (pe_accept_exact)
-  uint32_t dphe_thr24;          // double-phe decision on a 24-bit word
+  uint32_t dphe_thr22;          // double-phe decision on a 22-bit word
   uint32_t _pad_pe;
   double coin_u_min;     // exp(-coinWind/20): -20 ln u < coinWind <=> u > this  NEST.cpp:1422
   double below_thr_pct;  // Parametric S1 threshold percentile       NEST.cpp:1437-1457

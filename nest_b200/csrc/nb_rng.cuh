@@ -27,8 +27,11 @@ enum : uint32_t {
   STREAM_HIT2 = 2,   // S1 PMT hits: second photo-electron of a double-phe hit
   STREAM_HITX = 3,   // S1 PMT hits: rare redraws of the zero-truncated Gaussian
   STREAM_HIT3 = 4,   // S1 PMT hits: single-phe efficiency decisions (sPEeff < 1 only)
-  STREAM_POST = 5,
-  STREAM_HIT4 = 6,   // S1 PMT hits: truncation check of a second photo-electron   // per-event scalar draws after the S1 hit loop (k_post)
+  STREAM_POST = 5,   // per-event scalar draws after the S1 hit loop (k_post)
+  STREAM_HIT4 = 6,   // S1 PMT hits: truncation check of a second photo-electron
+  STREAM_ZIG = 7,    // S1 PMT hits: ziggurat wedge / tail completion of a hit's normal (| attempt << 8)
+  STREAM_ZIG2 = 10,  // ... of its second photo-electron's normal
+  STREAM_ZIGX = 11,  // ... of a joint (S, T) redraw (11: S, 12: T)
   STREAM_LAR = 8,
   STREAM_SE = 9,     // CalculateG2's single-electron Monte Carlo
   // each binomial draw owns a stream (the sampler is an out-of-line subroutine)
@@ -293,6 +296,83 @@ NB_D double log_pos(double x) {
   const int j = int(b >> 47) & 31;
   const double2 t = __ldg(reinterpret_cast<const double2*>(g_lntab) + j);
   return fma(double(e), c_hitk[0], t.y) + ln1p_small(fma(m, t.x, -1.0));
+}
+
+// ---- ziggurat normal for the S1 hit loop ---------------------------------------------------
+// Marsaglia & Tsang's ziggurat (J. Stat. Soft. 5(8), 2000) with 1024 layers of equal area, layer
+// index and abscissa taken from DISJOINT bits as Doornik (2005) requires: an exact sampler of
+// N(0,1) -- 99.55 % of the draws are one table look-up, one integer compare and one multiply;
+// the rest (wedges, tail) are finished out of line with exact exp / log tests (zig_finish).
+// (256 layers leave 1.5 % for the out-of-line path, which then costs as much as the core: measured.)
+// Layer i covers |x| < x_i at heights f(x_i)..f(x_{i+1}), x_0 = V/f(R) (base strip + tail),
+// x_1 = R, x_1024 = 0.  Tables are built by nb200_create (host, double) and staged in shared
+// memory by k_hits:  zk[i] = floor(2^28 x_{i+1}/x_i), zw[i] = x_i / 2^28.
+// Abscissa: t = 2 s + 1 with s the signed 28-bit field of the word (odd t: symmetric, no atom
+// at zero), x = t zw[i]; it lies inside the next layer (certain accept) iff |t| < zk[i].
+#define NB_ZIG_BITS 10
+#define NB_ZIG_N (1 << NB_ZIG_BITS)
+__device__ uint32_t g_zig_k[NB_ZIG_N];
+__device__ double g_zig_w[NB_ZIG_N];
+__device__ double g_zig_f[NB_ZIG_N + 1];  // f(x_i) = exp(-x_i^2/2), f[N] = 1
+__device__ double g_zig_R;
+
+static __constant__ double c_zigk[1] = {4503601774854144.0};  // 2^52 + 2^31 (constant-bank operand)
+NB_D int32_t zig_t(uint32_t w0) { return (int32_t(w0) >> 3) | 1; }
+// double(t) without the conversion unit: 2^52 + 2^31 + t has t in its low mantissa bits
+NB_D double zig_td(int32_t t) {
+  return __hiloint2double(0x43300000, t ^ int32_t(0x80000000)) - c_zigk[0];
+}
+// fast path: z is the normal iff the return value is true
+NB_D bool zig_fast(uint32_t w0, uint32_t w1, const uint32_t* zk, const double* zw, double& z) {
+  const int32_t t = zig_t(w0);
+  const uint32_t i = w1 >> (32 - NB_ZIG_BITS);
+  z = zig_td(t) * zw[i];
+  return uint32_t(abs(t)) < zk[i];
+}
+// everything else: wedge test of (i, t); on rejection a fresh layer and abscissa; layer 0 beyond
+// R is the tail (Marsaglia 1964: x = -ln(u1)/R, y = -ln(u2), accept when 2y > x^2).  The first
+// wedge test takes its uniform from `spare` (an unused word of the caller's block) when has_spare;
+// further bits come from blocks (event, k, stream | attempt << 8): words x,y decide a pending
+// (i, t), words z,w are the next (i, t).
+NB_D bool zig_wedge(uint32_t i, int32_t t, double u, double& x) {
+  x = zig_td(t) * g_zig_w[i];
+  const double f0 = g_zig_f[i], f1 = g_zig_f[i + 1];
+  return fma(u, f1 - f0, f0) < exp(-0.5 * x * x);
+}
+__device__ __noinline__ double zig_finish(uint32_t w0, uint32_t w1, uint32_t spare, bool has_spare, uint32_t e0,
+                                          uint32_t e1, uint32_t k, uint32_t stream, uint32_t k0, uint32_t k1) {
+  int32_t t = zig_t(w0);
+  uint32_t i = w1 >> (32 - NB_ZIG_BITS);
+  bool have = true;  // (i, t) awaits its wedge / tail decision
+  double x;
+  if (has_spare && i != 0u) {
+    if (zig_wedge(i, t, u32d(spare), x)) return x;
+    have = false;
+  }
+#pragma unroll 1
+  for (uint32_t att = 0; att < 4096u; ++att) {
+    const u128 b = philox_block(e0, e1, k, stream | (att << 8), k0, k1);
+    if (have) {
+      if (i == 0u) {
+        const double R = g_zig_R;
+        x = neg_log_bits_g(b.x, b.y) / R;
+        const double y = neg_log_bits_g(b.z, b.w);
+        if (y + y > x * x) return t < 0 ? -(R + x) : (R + x);
+        continue;  // not a tail sample yet: draw the tail again
+      }
+      if (zig_wedge(i, t, u53(b.x, b.y), x)) return x;
+    }
+    t = zig_t(b.z);
+    i = b.w >> (32 - NB_ZIG_BITS);
+    if (uint32_t(abs(t)) < g_zig_k[i]) return zig_td(t) * g_zig_w[i];
+    const bool decided = !have && i != 0u;  // words x,y of this block are still unused
+    have = true;
+    if (decided) {
+      if (zig_wedge(i, t, u53(b.x, b.y), x)) return x;
+      have = false;
+    }
+  }
+  return 0.;
 }
 
 // ---- samplers (device) -------------------------------------------------------------

@@ -54,3 +54,40 @@ def test_binomial_edges(ctx):
     b = ctx.debug_binomial(5000, 0.3, 10000, seed=7, first_event=0)
     c = ctx.debug_binomial(5000, 0.3, 5000, seed=7, first_event=5000)
     assert (a == b).all() and (a[5000:] == c).all()
+
+
+def test_hit_loop_normal_is_standard_normal(ctx):
+    """The S1 hit loop's ziggurat normal (core + wedge + tail, drawn exactly as k_hits and its slow
+    finisher draw it) against N(0,1): KS, chi2 over 200 equiprobable cells, moments to 5 sigma,
+    the mass beyond the ziggurat's R (tail algorithm) and the wedge/tail share."""
+    pairs = 10_000_000
+    z, kind = ctx.debug_normal(pairs, seed=2024)
+    n = z.size
+    assert np.isfinite(z).all()
+    # the rare completions are 0.43 % of the draws (1 - mean of x_{i+1}/x_i over the 1024 layers)
+    assert abs(kind.mean() - 0.0042766) < 5 * np.sqrt(0.0042766 / n)
+    assert stats.kstest(z[:4_000_000], "norm").pvalue > 1e-4
+    edges = stats.norm.ppf(np.linspace(0, 1, 201)[1:-1])
+    obs = np.bincount(np.searchsorted(edges, z), minlength=200).astype(float)
+    chi2 = ((obs - n / 200) ** 2 / (n / 200)).sum()
+    assert stats.chi2.sf(chi2, 199) > 1e-4, chi2
+    # the wedge / tail completions on their own: |z| of those draws against the exact law of a completion
+    # is covered by the cells above only through their 0.4 % weight, so test where they dominate --
+    # the outermost cells, where every draw beyond x_2 of the ziggurat is a completion or a base-strip core
+    # the completions alone, weighted back in, must not distort anything: chi2 of |z| in the tail region
+    R = 4.038849846109505
+    for cut in (3.0, 3.6, R, 4.5):
+        exp = 2 * stats.norm.sf(cut) * n
+        got = (np.abs(z) > cut).sum()
+        assert abs(got - exp) < 5 * np.sqrt(exp) + 1, (cut, got, exp)
+    assert abs(z.mean()) < 5 / np.sqrt(n)
+    assert abs(z.var() - 1) < 5 * np.sqrt(2 / n)
+    assert abs(stats.skew(z)) < 5 * np.sqrt(6 / n)
+    assert abs(stats.kurtosis(z)) < 5 * np.sqrt(24 / n)
+    assert abs((z ** 6).mean() - 15) < 5 * np.sqrt((10395 - 225) / n)
+    # the two normals of a pair, and neighbouring pairs, are uncorrelated
+    assert abs(np.corrcoef(z[0::2], z[1::2])[0, 1]) < 5 / np.sqrt(pairs)
+    assert abs(np.corrcoef(z[:-2:2], z[2::2])[0, 1]) < 5 / np.sqrt(pairs)
+    # reproducible, and a function of (seed, event, pair) only
+    z2, _ = ctx.debug_normal(2048, seed=2024, first_event=1)
+    assert (z2 == z[2048:2048 + 4096]).all()
