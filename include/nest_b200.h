@@ -353,6 +353,12 @@ int nb200_debug_normal(nb200_ctx* ctx, uint64_t seed, uint64_t first_event, size
 int nb200_debug_binomial(nb200_ctx* ctx, uint64_t seed, uint64_t first_event, size_t count, int64_t n,
                          double p, int64_t* out);
 
+/* Test hook: the same for the alias-table sampler that draws an event's number of double-phe hits,
+ * Binomial(nHits, P_dphe) (the hit-by-hit decision of NEST.cpp:1391, taken once per event): 0 < p < 1,
+ * 0 <= n < 2048. */
+int nb200_debug_binomial_fixed(nb200_ctx* ctx, uint64_t seed, uint64_t first_event, size_t count, int n,
+                               double p, int64_t* out);
+
 /* counters for the bench: kernels launched by this context since creation */
 uint64_t nb200_launch_count(const nb200_ctx* ctx);
 

@@ -104,7 +104,7 @@ EXPORTS = [
     "nb200_prepare", "nb200_wimp_prep", "nb200_poisson", "nb200_yields", "nb200_run", "nb200_run_async",
     "nb200_band_reset", "nb200_band_attach", "nb200_fp64_peak", "nb200_timing_enable", "nb200_timing_read", "nb200_se_stats", "nb200_band_fetch", "nb200_band_device_buffer", "nb200_allreduce_hist",
     "nb200_band_hist_bytes", "nb200_band_finalize", "nb200_lar", "nb200_launch_count",
-    "nb200_debug_hitmath", "nb200_debug_binomial", "nb200_debug_normal"]
+    "nb200_debug_hitmath", "nb200_debug_binomial", "nb200_debug_normal", "nb200_debug_binomial_fixed"]
 
 _lib = None
 
@@ -168,6 +168,7 @@ def lib():
                             vp, vp]
     L.nb200_debug_hitmath.argtypes = [vp, C.c_size_t, vp, vp]
     L.nb200_debug_binomial.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_size_t, C.c_int64, C.c_double, vp]
+    L.nb200_debug_binomial_fixed.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_size_t, C.c_int, C.c_double, vp]
     L.nb200_debug_normal.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_size_t, vp, vp]
     L.nb200_launch_count.argtypes = [vp]
     L.nb200_launch_count.restype = C.c_uint64
@@ -360,6 +361,11 @@ class Context:
     def debug_binomial(self, n, p, count, seed=1, first_event=0):
         out = np.empty(int(count), np.int64)
         self._check(lib().nb200_debug_binomial(self.h, seed, first_event, out.size, int(n), float(p), _dptr(out)))
+        return out
+
+    def debug_binomial_fixed(self, n, p, count, seed=1, first_event=0):
+        out = np.empty(int(count), np.int64)
+        self._check(lib().nb200_debug_binomial_fixed(self.h, seed, first_event, out.size, int(n), float(p), _dptr(out)))
         return out
 
     def debug_normal(self, pairs, seed=1, first_event=0):

@@ -59,6 +59,8 @@ struct nb200_ctx {
   nb200_detector vtable_det;
   double vtable_zstep = 0.;
   double* d_vtable = nullptr;
+  void* d_dpe = nullptr;  // alias tables of Binomial(2^b, P_dphe)
+  double dpe_p = -1.;
 };
 
 namespace {
@@ -226,9 +228,9 @@ int build_params(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo,
     // P(T <= 0 | S = s) = Phi(-(m0 + rho s)/tau) < 2^-64  <=>  m0 + rho s > 9.1 tau
     P->pe_cut = P->pe_rho > 0. ? (9.1 * P->pe_tau - P->pe_m0) / P->pe_rho : -DBL_MAX;
     P->pe_fast = 1.5341205443525465 * P->pe_tau;  // Phi(1.5341205...) = 15/16
+    // m = pe_m0 + pe_rho S < pe_fast as a threshold on S itself (pe_rho = 0: m is constant)
+    P->pe_sfast = P->pe_rho > 0. ? (P->pe_fast - P->pe_m0) / P->pe_rho : (P->pe_m0 < P->pe_fast ? DBL_MAX : -DBL_MAX);
     P->pe_inv_tau16 = P->pe_tau > 0. ? 16. / P->pe_tau : 0.;
-    double t = ceil(det->P_dphe * 4194304.0 - 0.5);
-    P->dphe_thr22 = t <= 0. ? 0u : (t >= 4194304.0 ? 4194304u : uint32_t(t));
   }
   {
     const double sq2 = sqrt(2.);
@@ -273,6 +275,18 @@ int build_params(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo,
     }
     P->vtable = c->d_vtable;
     P->vtable_n = int(c->vtable_host.size());
+  }
+  P->dpe_alias = nullptr;
+  if (det->P_dphe > 0. && det->P_dphe < 1.) {  // alias tables of Binomial(2^b, P_dphe) for k_pre's double-phe count
+    if (!c->d_dpe || c->dpe_p != det->P_dphe) {
+      AliasEntry tab[NB_ALIAS_ENTRIES];
+      build_binomial_alias(det->P_dphe, tab);
+      if (!c->d_dpe) NB_CUDA(c, cudaMalloc(&c->d_dpe, sizeof tab));
+      NB_CUDA(c, cudaMemcpyAsync(c->d_dpe, tab, sizeof tab, cudaMemcpyHostToDevice, c->stream));
+      NB_CUDA(c, cudaStreamSynchronize(c->stream));  // tab is a stack array
+      c->dpe_p = det->P_dphe;
+    }
+    P->dpe_alias = static_cast<const uint2*>(c->d_dpe);
   }
   if (src->kind == NB200_SRC_WIMP) {
     void* d = nullptr;
@@ -518,6 +532,7 @@ void nb200_destroy(nb200_ctx* c) {
   if (c->d_band && !c->band_external) cudaFree(c->d_band);
   if (c->d_band_tmp) cudaFree(c->d_band_tmp);
   if (c->d_vtable) cudaFree(c->d_vtable);
+  if (c->d_dpe) cudaFree(c->d_dpe);
   if (c->d_work) cudaFree(c->d_work);
   for (int b = 0; b < 2; ++b) {
     if (c->d_stage[b]) cudaFree(c->d_stage[b]);
@@ -1283,6 +1298,32 @@ int nb200_debug_binomial(nb200_ctx* c, uint64_t seed, uint64_t first_event, size
   cudaMemcpyAsync(out, dout, count * 8, cudaMemcpyDeviceToHost, c->stream);
   cudaError_t e = cudaStreamSynchronize(c->stream);
   cudaFree(dout);
+  if (e != cudaSuccess) return fail(c, NB200_ECUDA, cudaGetErrorString(e));
+  return 0;
+}
+
+int nb200_debug_binomial_fixed(nb200_ctx* c, uint64_t seed, uint64_t first_event, size_t count, int n, double p,
+                               int64_t* out) {
+  if (!c || !out || !(p > 0. && p < 1.) || n < 0 || n >= NB_ALIAS_MAXN) return NB200_EINVAL;
+  if (count == 0) return 0;
+  NB_CUDA(c, cudaSetDevice(c->device));
+  AliasEntry tab[NB_ALIAS_ENTRIES];
+  build_binomial_alias(p, tab);
+  long long* dout = nullptr;
+  void* dtab = nullptr;
+  NB_CUDA(c, cudaMalloc(&dout, count * 8));
+  if (cudaMalloc(&dtab, sizeof tab) != cudaSuccess) {
+    cudaFree(dout);
+    return fail(c, NB200_ENOMEM, "cudaMalloc");
+  }
+  cudaMemcpyAsync(dtab, tab, sizeof tab, cudaMemcpyHostToDevice, c->stream);
+  k_binomial_fixed<<<unsigned(std::min<size_t>((count + 255) / 256, 148 * 8)), 256, 0, c->stream>>>(
+      seed, first_event, count, n, static_cast<const uint2*>(dtab), dout);
+  ++c->launches;
+  cudaMemcpyAsync(out, dout, count * 8, cudaMemcpyDeviceToHost, c->stream);
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  cudaFree(dout);
+  cudaFree(dtab);
   if (e != cudaSuccess) return fail(c, NB200_ECUDA, cudaGetErrorString(e));
   return 0;
 }

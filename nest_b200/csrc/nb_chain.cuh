@@ -244,6 +244,7 @@ struct S1Pre {
   double posDepSm, fitSm;  // FitS1(smear)/centre, and FitS1(smear) itself (GetSpike)
   double eff;
   int nHits;
+  int nDP;    // Full mode: how many of the hits carry a second photo-electron (see k_hits)
   bool full;  // Full per-hit loop (true) or Parametric
 };
 
@@ -277,6 +278,14 @@ NB_D S1Pre s1_prelude(uint64_t ev, const RunParams& P, int Nph, double tx, doubl
   int mode = P.ana.s1mode;
   if (mode == NB200_S1_HYBRID) mode = energy < 100. ? NB200_S1_FULL : NB200_S1_PARAMETRIC;
   r.full = (mode == NB200_S1_FULL);
+  // NEST.cpp:1391 decides hit by hit, with probability P_dphe, whether a second photo-electron
+  // follows; the hits are exchangeable, so only their number matters: one binomial here, and k_hits
+  // makes the first nDP hits the double ones
+  const int nh = r.full ? r.nHits : 0;
+  const bool tab = P.dpe_alias != nullptr && nh < NB_ALIAS_MAXN;  // P_dphe in (0,1) and a moderate hit count
+  r.nDP = tab ? binomial_fixed_p(P.seed, ev, STREAM_BIN_S1DPE, nh, P.dpe_alias) : 0;
+  if (__any_sync(__activemask(), !tab))  // large events (or P_dphe of 0 / 1): the general sampler
+    r.nDP += int(binomial(P.seed, ev, STREAM_BIN_S1DPE + 1u, tab ? 0 : nh, det.P_dphe));
   return r;
 }
 
@@ -306,11 +315,13 @@ struct S1Acc {
 //   * hits needing anything more (exact truncation test, second photo-electron, efficiency or
 //     coincidence draws) are queued per warp and finished 32 at a time (k_hits);
 //   * -20 ln u < coinWind is tested as u > exp(-coinWind/20) and only when nHits <= coinLevel.
-enum : uint32_t { HIT_CHK1 = 1u, HIT_DP = 2u, HIT_CHK2 = 4u, HIT_SPECIAL = 8u, HIT_ZIG = 16u };
 
-// Phi(z) at z = -8 + k/16, k = 0..272, filled by nb200_create (host erfc).  Linear interpolation
+// Phi(z) at z = -8 + k/16, k = 0..304, filled by nb200_create (host erfc).  Linear interpolation
 // between neighbours is within 1.18e-4 of Phi (h^2/8 max|Phi''| = (1/16)^2/8 * 0.242).
-#define NB_PHI_N 273
+// (up to z = 11: the pre-test sends everything below m/tau = 9.1 here, and arguments past the table
+// end evaluate erfc -- with a table ending at 9 that was 1 % of the tests, and the reason erfc ran
+// in nearly every finisher pass)
+#define NB_PHI_N 305
 #define NB_PHI_EPS 1.25e-4
 __device__ double g_phitab[NB_PHI_N];
 
@@ -321,7 +332,7 @@ __device__ double g_phitab[NB_PHI_N];
 // evaluates erfc.  The outcome is that of the erfc test in every case.
 NB_D bool pe_accept_exact(const RunParams& P, double sv, double u) {
   const double m = fma(P.pe_rho, sv, P.pe_m0);
-  const bool scaled = m >= P.pe_fast;
+  const bool scaled = !(sv < P.pe_sfast);  // the pre-test's own comparison (m >= pe_fast)
 #ifndef NB_PE_NO_BOUNDS
   if (P.pe_tau > 0.) {
     const double t = fma(m, P.pe_inv_tau16, 128.);  // (z + 8) * 16

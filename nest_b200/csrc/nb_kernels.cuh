@@ -154,13 +154,21 @@ NB_D double drift_velocity_dev(const RunParams& P, double eField) {
 #define NB_POST_MINB 1
 #endif
 #ifndef NB_HIT_MINB
-#define NB_HIT_MINB 3  // 80 registers: at 64 (4 blocks/SM) the hit loop reloads spilled loop state every iteration (2.65 vs 2.56 ms)
+#define NB_HIT_MINB 5  // 128-thread blocks at 96 registers (20 warps/SM): measured best of {256x4@64, 256x3@80, 256x2@128, 128x6@80, 128x5@96, 128x4@128}
 #endif
 constexpr int kPreBlock = NB_PRE_BLOCK;
 constexpr int kPostBlock = NB_POST_BLOCK;
-constexpr int kHitGroup = 512;   // events per k_hits group
-constexpr int kHitBlock = 256;   // threads per k_hits block
+#ifndef NB_HIT_GROUP
+#define NB_HIT_GROUP 512
+#endif
+#ifndef NB_HIT_BLOCK
+#define NB_HIT_BLOCK 128
+#endif
+constexpr int kHitGroup = NB_HIT_GROUP;   // events per k_hits group
+constexpr int kHitBlock = NB_HIT_BLOCK;   // threads per k_hits block
 #define NB_AREA_FX 4294967296.0  // 2^32: S1 hit areas are summed in units of 2^-32 phe
+#define NB_AREA_MAGIC 6755399441055744.0           // 1.5 * 2^52: ulp = 1 for |a 2^32| < 2^51
+#define NB_AREA_MAGIC_BITS 0x4338000000000000ull  // its bit pattern
 
 __global__ void __launch_bounds__(kPreBlock, NB_PRE_MINB)
     k_pre(const __grid_constant__ RunParams P, int* __restrict__ err_flag) {
@@ -286,36 +294,32 @@ __global__ void __launch_bounds__(kPreBlock, NB_PRE_MINB)
     W.ions[idx] = q.ions;
     W.excitons[idx] = q.excitons;
     W.nHits[idx] = pre.full ? pre.nHits : -(pre.nHits + 1);  // negative: Parametric S1 in k_post
+    W.nphe[idx] = pre.nDP;  // in: double-phe hits; k_hits replaces it by Nphe = nHits + nDP
     if (err) atomicOr(err_flag, err);
   }
 }
 
-// Per-warp queue of hits that need more than the one normal of the main loop.
-struct HitEntry {  // 16 bytes: one STS.128 / LDS.128 per queued hit
-  double s1;
-  uint32_t k;
-  uint32_t slot_flags;  // slot << 8 | flags
+// -------------------------------------------------------------------------------------------
+// k_hits: the per-PMT-hit loop of GetS1, NEST.cpp:1367-1429
+//
+// Work item = SLOT = one Philox block = two photo-electrons.  The hits of an event are
+// exchangeable (iid draws, and the event observables -- spike count, summed area, Nphe -- are
+// symmetric in them), so instead of deciding hit by hit whether it carries a second
+// photo-electron (NEST.cpp:1391), k_pre draws their number nDP ~ Binomial(nHits, P_dphe) once and
+// the first nDP hits are the double ones: slot j < nDP is one double-phe hit (both photo-electrons
+// in the same lane, summed before the sPEthr test), a later slot is two single-phe hits.
+// Nphe = nHits + nDP.  No second-photo-electron queue, no per-hit Bernoulli.
+//
+// A slot whose photo-electrons all land in their ziggurat layer's core above the truncation
+// pre-test (95 % of slots for LUX) is finished in the main loop.  Any other slot -- wedge / tail
+// of the ziggurat, exact truncation test, and every slot of an event that needs efficiency or
+// coincidence-window draws -- is queued per warp as (event, slot) and redone in full, 32 at a
+// time, by the out-of-line finisher: rare per lane but frequent per warp.
+struct SlotEntry {
+  uint32_t j, e;
 };
-// Two queues per warp.  "fast": hits that only need their second photo-electron (17 % of hits) --
-// branch-free finisher.  "slow": everything rare (exact truncation tests, redraws, efficiency and
-// coincidence draws; 2-3 % of hits): rare per lane but frequent per warp, so they are also
-// collected and run 32 at a time instead of one lane at a time inside the fast path.
-constexpr int kFastCap = 96;  // <= 31 left over + 64 pushed per pair iteration
-constexpr int kSlowCap = 64;  // <= 31 left over + 32 handed on by one fast pass
+constexpr int kSlotCap = 64;  // <= 31 left over + 32 pushed per iteration
 constexpr size_t kHitDynSmem = NB_ZIG_N * (sizeof(double) + sizeof(uint32_t));  // ziggurat tables (opt-in: > 48 KB total)
-struct HitQueues {
-  HitEntry* fast;
-  HitEntry* slow;
-  double* slow_s2;
-  const uint32_t* zk;  // ziggurat tables staged in shared memory (nb_rng.cuh)
-  const double* zw;
-};
-
-NB_D void sts_entry(uint32_t shared_addr, double s1, uint32_t k, uint32_t slot_flags) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(shared_addr), "r"(__double2loint(s1)),
-               "r"(__double2hiint(s1)), "r"(k), "r"(slot_flags)
-               : "memory");
-}
 
 NB_D void hit_commit(const RunParams& P, unsigned long long* s_area, unsigned int* s_spike, int slot, double a,
                      bool pass_coin) {
@@ -325,121 +329,77 @@ NB_D void hit_commit(const RunParams& P, unsigned long long* s_area, unsigned in
   }
 }
 
-// slow path, up to 32 queued hits: everything the reference does for a hit beyond one normal
-// (out of line: its register needs must not shape the main loop, 3.75 -> 3.28 ms)
-__device__ __noinline__ void hits_finish_slow(const RunParams& P, const int* s_pref, unsigned long long* s_area,
-                                             unsigned int* s_spike, uint64_t ev0, const HitQueues& q, int first,
-                                             int count, int lane) {
-  const nb200_detector& det = P.det;
-  if (lane < count) {
-    const HitEntry en = q.slow[first + lane];
-    double s1 = en.s1;
-    const uint32_t k = en.k;
-    uint32_t flags = en.slot_flags & 0xFFu;
-    const int slot = int(en.slot_flags >> 8);
-    const uint64_t ev = ev0 + slot;
-    const uint32_t e0 = uint32_t(ev), e1 = uint32_t(ev >> 32);
-    const u128 r = philox4x32_10_rk(e0, e1, k, STREAM_HIT2, P.rk);
-    double s2 = 0.;
-    if (flags & HIT_CHK2) {  // came back from the fast finisher: s1 final, s2 drawn, exact test pending
-      s2 = q.slow_s2[first + lane];
-      const u128 t = philox4x32_10_rk(e0, e1, k, STREAM_HIT4, P.rk);
-      if (!pe_accept_exact(P, s2, u53(t.x, t.y)))
-        s2 = pe_redraw(P.seed, ev, k * 64u + 32u, P.pe_mu, P.pe_sig, P.pe_cut, P.pe_tau, P.pe_rho, P.pe_m0);
-    } else {
-      if (flags & HIT_ZIG) {  // the hit's own normal fell outside its ziggurat layer's core
-        const u128 m = philox4x32_10_rk(e0, e1, k >> 1, STREAM_HIT, P.rk);
-        const uint32_t w0 = (k & 1u) ? m.z : m.x, w1 = (k & 1u) ? m.w : m.y;
-        s1 = fma(P.pe_sig,
-                 zig_finish(w0, w1, r.z, true, e0, e1, k, STREAM_ZIG, uint32_t(P.seed), uint32_t(P.seed >> 32)), P.pe_mu);
-        if (s1 <= P.pe_cut && (fma(P.pe_rho, s1, P.pe_m0) < P.pe_fast || (w0 & 0xFu) == 15u)) flags |= HIT_CHK1;
-      }
-      if (flags & HIT_CHK1) {
-        if (!pe_accept_exact(P, s1, (double(r.w >> 12) + 0.5) * (1.0 / 1048576.0)))
-          s1 = pe_redraw(P.seed, ev, k * 64u, P.pe_mu, P.pe_sig, P.pe_cut, P.pe_tau, P.pe_rho, P.pe_m0);
-      }
-      if (flags & HIT_DP) {
-        double z2;
-        if (!zig_fast(r.x, r.y, q.zk, q.zw, z2))
-          z2 = zig_finish(r.x, r.y, r.z, !(flags & HIT_ZIG), e0, e1, k, STREAM_ZIG2, uint32_t(P.seed),
-                          uint32_t(P.seed >> 32));
-        s2 = fma(P.pe_sig, z2, P.pe_mu);
-        if (s2 <= P.pe_cut && (fma(P.pe_rho, s2, P.pe_m0) < P.pe_fast || ((r.w >> 8) & 0xFu) == 15u)) {
-          const u128 t = philox4x32_10_rk(e0, e1, k, STREAM_HIT4, P.rk);
-          if (!pe_accept_exact(P, s2, u53(t.x, t.y)))
-            s2 = pe_redraw(P.seed, ev, k * 64u + 32u, P.pe_mu, P.pe_sig, P.pe_cut, P.pe_tau, P.pe_rho, P.pe_m0);
-        }
-      }
-    }
-    bool pass_coin = true;
-    if (flags & HIT_SPECIAL) {  // sPEeff < 1 and/or nHits <= coinLevel: block 3
-      const int ne = s_pref[slot + 1] - s_pref[slot];
-      const double eff = s1_eff(det, ne);
-      const u128 t = philox4x32_10_rk(e0, e1, k, STREAM_HIT3, P.rk);
-      if (eff < 1.) {  // NEST.cpp:1381-1386, 1403
-        const bool lost1 = u32d(t.x) > eff, lost2 = u32d(t.y) > eff;
-        if (lost1) s1 = 0.;
-        if (lost1 && lost2) s2 = 0.;
-      }
-      if (!(ne > det.coinLevel)) pass_coin = u32d(t.z) > P.coin_u_min;  // :1422-1424
-    }
-    hit_commit(P, s_area, s_spike, slot, s1 + s2, pass_coin);
+// one photo-electron in full: ziggurat normal (core, wedge or tail), truncation pre-test, exact
+// residual test, joint redraw.  which = 0 / 1: words (x,y) / (z,w) of the slot's block r; the
+// spare uniforms come from the slot's STREAM_HIT2 block t (x,y: first wedge test, z,w: exact test).
+NB_D double pe_full(const RunParams& P, const u128& r, const u128& t, int which, uint64_t ev, uint32_t j,
+                    const uint32_t* zk, const double* zw) {
+  const uint32_t w0 = which ? r.z : r.x, w1 = which ? r.w : r.y;
+  const uint32_t e0 = uint32_t(ev), e1 = uint32_t(ev >> 32);
+  double z;
+  if (!zig_fast(w0, w1, zk, zw, z))
+    z = zig_finish(w0, w1, which ? t.y : t.x, true, e0, e1, 2u * j + uint32_t(which), STREAM_ZIG, uint32_t(P.seed),
+                   uint32_t(P.seed >> 32));
+  double sv = fma(P.pe_sig, z, P.pe_mu);
+  if (sv <= P.pe_cut && (sv < P.pe_sfast || (w0 & 0xFu) == 15u)) {
+    if (!pe_accept_exact(P, sv, u32d(which ? t.w : t.z)))
+      sv = pe_redraw(P.seed, ev, j * 64u + (which ? 32u : 0u), P.pe_mu, P.pe_sig, P.pe_cut, P.pe_tau, P.pe_rho, P.pe_m0);
   }
-  __syncwarp();
+  return sv;
 }
 
-// fast path, up to 32 queued double-phe hits: draw the second photo-electron from the hit's own
-// block; the 0.4 % whose second draw needs the exact truncation test move on to the slow queue
-// (inlined: an out-of-line copy was measured slower)
-NB_D void hits_finish_fast(const RunParams& P, unsigned long long* s_area, unsigned int* s_spike, uint64_t ev0,
-                           const HitQueues& q, int first, int count, int& scount, int lane) {
-  bool defer = false;
-  HitEntry en{0., 0u, 0u};
-  double s2 = 0.;
+// up to 32 queued slots, everything the reference does for their hits
+// (out of line: its register needs must not shape the main loop)
+__device__ __noinline__ void hits_finish_slow(const RunParams& P, const int* s_nh, const int* s_nd,
+                                             unsigned long long* s_area, unsigned int* s_spike, uint64_t ev0,
+                                             const SlotEntry* q, int count, int lane, const uint32_t* zk,
+                                             const double* zw) {
+  const nb200_detector& det = P.det;
   if (lane < count) {
-    en = q.fast[first + lane];
-    if ((en.slot_flags & 0xFFu) != HIT_DP) {
-      defer = true;  // rare kinds (exact truncation test, efficiency / coincidence draws): slow queue
+    const SlotEntry en = q[lane];
+    const int e = int(en.e), nh = s_nh[e], nd = s_nd[e];
+    const uint32_t j = en.j;
+    const bool dp = int(j) < nd;
+    const bool hasb = dp || (2 * (int(j) - nd) + 1 < nh - nd);
+    const uint64_t ev = ev0 + uint64_t(e);
+    const uint32_t e0 = uint32_t(ev), e1 = uint32_t(ev >> 32);
+    const u128 r = philox4x32_10_rk(e0, e1, j, STREAM_HIT, P.rk);
+    const u128 t = philox4x32_10_rk(e0, e1, j, STREAM_HIT2, P.rk);
+    double s1 = pe_full(P, r, t, 0, ev, j, zk, zw);
+    double s2 = hasb ? pe_full(P, r, t, 1, ev, j, zk, zw) : 0.;
+    bool coin1 = true, coin2 = true;
+    if (det.sPEeff < 1. || !(nh > det.coinLevel)) {  // efficiency and coincidence-window draws
+      const double eff = s1_eff(det, nh);
+      const u128 c = philox4x32_10_rk(e0, e1, j, STREAM_HIT3, P.rk);
+      if (eff < 1.) {  // NEST.cpp:1381-1386, 1403: a second photo-electron is lost only with the first
+        const bool lost1 = u32d(c.x) > eff, lost2 = u32d(c.y) > eff;
+        if (lost1) s1 = 0.;
+        if (dp ? (lost1 && lost2) : lost2) s2 = 0.;
+      }
+      if (!(nh > det.coinLevel)) {  // :1422-1424
+        coin1 = u32d(c.z) > P.coin_u_min;
+        coin2 = u32d(c.w) > P.coin_u_min;
+      }
+    }
+    if (dp) {
+      hit_commit(P, s_area, s_spike, e, s1 + s2, coin1);
     } else {
-      const int slot = int(en.slot_flags >> 8);
-      const uint64_t ev = ev0 + slot;
-      const u128 r = philox4x32_10_rk(uint32_t(ev), uint32_t(ev >> 32), en.k, STREAM_HIT2, P.rk);
-      double z2;
-      const bool core = zig_fast(r.x, r.y, q.zk, q.zw, z2);
-      s2 = fma(P.pe_sig, z2, P.pe_mu);
-      const bool chk = s2 <= P.pe_cut && (fma(P.pe_rho, s2, P.pe_m0) < P.pe_fast || ((r.w >> 8) & 0xFu) == 15u);
-      defer = !core || chk;
-      if (!core)
-        ;  // wedge or tail: the slow finisher redoes this draw in full (flags stay HIT_DP)
-      else if (chk)
-        en.slot_flags = (en.slot_flags & 0xFFFFFF00u) | HIT_CHK2;
-      else
-        hit_commit(P, s_area, s_spike, slot, en.s1 + s2, true);
+      hit_commit(P, s_area, s_spike, e, s1, coin1);
+      if (hasb) hit_commit(P, s_area, s_spike, e, s2, coin2);
     }
-  }
-  const unsigned m = __ballot_sync(0xffffffffu, defer);
-  if (m) {
-    if (defer) {
-      const int pos = scount + __popc(m & ((1u << lane) - 1u));
-      q.slow[pos] = en;
-      q.slow_s2[pos] = s2;
-    }
-    scount += __popc(m);
   }
   __syncwarp();
 }
 
 __global__ void __launch_bounds__(kHitBlock, NB_HIT_MINB)
     k_hits(const __grid_constant__ RunParams P, unsigned int* __restrict__ next_group) {
-  __shared__ int s_pref[kHitGroup + 1];   // hit-count prefix (events)
-  __shared__ int s_ppref[kHitGroup + 1];  // pair-count prefix: the flattened work items
+  __shared__ int s_ppref[kHitGroup + 1];  // slot-count prefix: the flattened work items
+  __shared__ int s_nh[kHitGroup];         // hits of the event
+  __shared__ int s_nd[kHitGroup];         // of which double-phe
   __shared__ unsigned long long s_area[kHitGroup];
   __shared__ unsigned int s_spike[kHitGroup];
-  __shared__ unsigned int s_nphe[kHitGroup];
   __shared__ int s_warp[32];
-  __shared__ __align__(16) HitEntry s_qf[kHitBlock / 32][kFastCap];
-  __shared__ __align__(16) HitEntry s_qs[kHitBlock / 32][kSlowCap];
-  __shared__ double s_qs2[kHitBlock / 32][kSlowCap];
+  __shared__ __align__(8) SlotEntry s_q[kHitBlock / 32][kSlotCap];
   extern __shared__ __align__(16) double s_zw[];  // kHitDynSmem: zw[NB_ZIG_N] then zk[NB_ZIG_N]
   uint32_t* const s_zk = reinterpret_cast<uint32_t*>(s_zw + NB_ZIG_N);
   for (int i = threadIdx.x; i < NB_ZIG_N; i += kHitBlock) {
@@ -451,9 +411,8 @@ __global__ void __launch_bounds__(kHitBlock, NB_HIT_MINB)
   const nb200_detector& det = P.det;
   const Work& W = P.work;
   const uint64_t n_groups = (P.n_events + kHitGroup - 1) / kHitGroup;
-  const HitQueues q{s_qf[wid], s_qs[wid], s_qs2[wid], s_zk, s_zw};
-  const uint32_t qf_addr = uint32_t(__cvta_generic_to_shared(&s_qf[wid][0]));
-  const bool all_special = det.sPEeff < 1.;  // efficiency draws: every hit goes through the slow queue
+  const uint32_t q_addr = uint32_t(__cvta_generic_to_shared(&s_q[wid][0]));
+  const bool all_special = det.sPEeff < 1.;  // efficiency draws: every slot goes through the finisher
 
   // groups are handed out by a device counter (zeroed before the launch): their cost follows their hit
   // counts, so a static stride leaves the last wave ragged
@@ -465,43 +424,40 @@ __global__ void __launch_bounds__(kHitBlock, NB_HIT_MINB)
     if (grp >= n_groups) break;
     const uint64_t gbase = grp * kHitGroup;
     const uint64_t ev0 = P.first_event + P.chunk_off + gbase;
-    // hit counts of my PER consecutive events -> exclusive prefixes (hits and pairs) over the group
+    // slot counts of my PER consecutive events -> exclusive prefix over the group
     int cnt[PER];
-    int mine = 0, minep = 0;
+    int mine = 0;
 #pragma unroll
-    for (int j = 0; j < PER; ++j) {
-      const uint64_t idx = gbase + uint64_t(tid) * PER + j;
-      int n = (idx < P.n_events) ? W.nHits[idx] : 0;
-      cnt[j] = n > 0 ? n : 0;
-      mine += cnt[j];
-      minep += (cnt[j] + 1) >> 1;
-      s_area[tid * PER + j] = 0ull;
-      s_spike[tid * PER + j] = 0u;
-      s_nphe[tid * PER + j] = 0u;
+    for (int k = 0; k < PER; ++k) {
+      const uint64_t idx = gbase + uint64_t(tid) * PER + k;
+      int nh = (idx < P.n_events) ? W.nHits[idx] : 0;  // negative: Parametric S1 (k_post)
+      nh = nh > 0 ? nh : 0;
+      int nd = (idx < P.n_events) ? W.nphe[idx] : 0;  // k_pre left the double-phe count here
+      nd = nd < 0 ? 0 : (nd > nh ? nh : nd);
+      cnt[k] = nd + ((nh - nd + 1) >> 1);
+      mine += cnt[k];
+      s_nh[tid * PER + k] = nh;
+      s_nd[tid * PER + k] = nd;
+      s_area[tid * PER + k] = 0ull;
+      s_spike[tid * PER + k] = 0u;
     }
     int off = block_exclusive_scan<kHitBlock>(mine, s_warp);
-    __syncthreads();
-    int offp = block_exclusive_scan<kHitBlock>(minep, s_warp);
 #pragma unroll
-    for (int j = 0; j < PER; ++j) {
-      s_pref[tid * PER + j] = off;
-      s_ppref[tid * PER + j] = offp;
-      off += cnt[j];
-      offp += (cnt[j] + 1) >> 1;
+    for (int k = 0; k < PER; ++k) {
+      s_ppref[tid * PER + k] = off;
+      off += cnt[k];
     }
-    if (tid == kHitBlock - 1) {
-      s_pref[kHitGroup] = off;
-      s_ppref[kHitGroup] = offp;
-    }
+    if (tid == kHitBlock - 1) s_ppref[kHitGroup] = off;
     __syncthreads();
-    const int H = s_ppref[kHitGroup];  // pairs in this group
+    const int H = s_ppref[kHitGroup];  // slots in this group
     const int h0 = int((long long)H * tid / kHitBlock);
     const int h1 = int((long long)H * (tid + 1) / kHitBlock);
     const int maxlen = __reduce_max_sync(0xffffffffu, h1 - h0);
-    int e = 0, e_end = 0, ne = 0, j = 0;
-    int h = h0;  // running pair index; this thread owns [h0, h1)
+    int e = 0, e_end = 0, nd = 0, jlast = -1, j = 0;  // jlast: the slot holding a lone single hit, if any
+    bool sp = false;
+    int h = h0;  // running slot index; this thread owns [h0, h1)
     if (h1 > h0) {
-      // event owning pair h0: largest e with s_ppref[e] <= h0
+      // event owning slot h0: largest e with s_ppref[e] <= h0
       int lo = 0, hi = kHitGroup;
       while (hi - lo > 1) {
         int mid = (lo + hi) >> 1;
@@ -512,93 +468,83 @@ __global__ void __launch_bounds__(kHitBlock, NB_HIT_MINB)
       }
       e = lo;
       e_end = s_ppref[e + 1];
-      ne = s_pref[e + 1] - s_pref[e];
+      nd = s_nd[e];
+      const int ns = s_nh[e] - nd;
+      jlast = (ns & 1) ? nd + (ns >> 1) : -1;
+      sp = all_special || !(nd + ns > det.coinLevel);
       j = h0 - s_ppref[e];
     }
     unsigned long long a_fx = 0ull;
-    unsigned int a_spike = 0u, a_nphe = 0u;
-    int fcount = 0, scount = 0;  // warp-uniform queue fills
+    unsigned int a_spike = 0u;
+    int qcount = 0;  // warp-uniform queue fill
     for (int it = maxlen; it > 0; --it) {
-      uint32_t fa = 0u, fb = 0u;  // queue flags of the pair's two hits (0 = finished here)
-      double sa = 0., sb = 0.;
+      bool queue = false;
       if (h < h1) {
         if (h == e_end) {  // crossed into the next event with hits: flush, then advance
-          atomicAdd(&s_area[e], a_fx);
+          atomicAdd(&s_area[e], a_fx - (unsigned long long)a_spike * NB_AREA_MAGIC_BITS);
           atomicAdd(&s_spike[e], a_spike);
-          atomicAdd(&s_nphe[e], a_nphe);
           a_fx = 0ull;
-          a_spike = a_nphe = 0u;
+          a_spike = 0u;
           do {
             ++e;
             e_end = s_ppref[e + 1];
           } while (e_end == h);
-          ne = s_pref[e + 1] - s_pref[e];
+          nd = s_nd[e];
+          const int ns = s_nh[e] - nd;
+          jlast = (ns & 1) ? nd + (ns >> 1) : -1;
+          sp = all_special || !(nd + ns > det.coinLevel);
           j = 0;
         }
-        // one Philox block for hits 2j and 2j+1 of this event: 64 bits each -- 28 (abscissa) + 10
-        // (layer) for the ziggurat normal, 22 for the double-phe draw, 4 for the truncation pre-test
+        // one Philox block per slot, 64 bits per photo-electron: 28 (abscissa) + 10 (layer) for the
+        // ziggurat normal, 4 for the truncation pre-test (22 spare)
         const uint64_t hev = ev0 + e;
         const u128 r = philox4x32_10_rk(uint32_t(hev), uint32_t(hev >> 32), uint32_t(j), STREAM_HIT, P.rk);
         double za, zb;
         const bool ka = zig_fast(r.x, r.y, s_zk, s_zw, za), kb = zig_fast(r.z, r.w, s_zk, s_zw, zb);
-        sa = fma(P.pe_sig, za, P.pe_mu);
-        sb = fma(P.pe_sig, zb, P.pe_mu);
-        const uint32_t da = r.y & 0x3FFFFFu, db = r.w & 0x3FFFFFu;
-        const bool hasb = (2 * j + 1) < ne;
-        const uint32_t sp = (all_special || !(ne > det.coinLevel)) ? HIT_SPECIAL : 0u;
+        const double sa = fma(P.pe_sig, za, P.pe_mu), sb = fma(P.pe_sig, zb, P.pe_mu);
+        const bool dp = j < nd;
+        const bool hasb = j != jlast;
         // truncation pre-test (nb_params.h): above pe_cut nothing to do; below it a 4-bit uniform
-        // settles it unless it is 15 or the acceptance is under 15/16.  A normal outside its
-        // layer's core (0.45 %) is completed, and then pre-tested, by the slow finisher.
-        const bool ca = sa <= P.pe_cut && (fma(P.pe_rho, sa, P.pe_m0) < P.pe_fast || (r.x & 0xFu) == 15u);
-        const bool cb = sb <= P.pe_cut && (fma(P.pe_rho, sb, P.pe_m0) < P.pe_fast || (r.z & 0xFu) == 15u);
-        fa = (ka ? (ca ? HIT_CHK1 : 0u) : HIT_ZIG) | (da < P.dphe_thr22 ? HIT_DP : 0u) | sp;
-        fb = hasb ? ((kb ? (cb ? HIT_CHK1 : 0u) : HIT_ZIG) | (db < P.dphe_thr22 ? HIT_DP : 0u) | sp) : 0u;
-        a_nphe += 1u + ((fa >> 1) & 1u) + (hasb ? 1u + ((fb >> 1) & 1u) : 0u);
-        if (fa == 0u && sa > det.sPEthr) {
-          a_spike += 1u;
-          a_fx += (unsigned long long)__double2ll_rn(sa * NB_AREA_FX);
-        }
-        if (hasb && fb == 0u && sb > det.sPEthr) {
-          a_spike += 1u;
-          a_fx += (unsigned long long)__double2ll_rn(sb * NB_AREA_FX);
+        // settles it unless it is 15 or the acceptance is under 15/16 (S below pe_sfast)
+        const bool ca = sa <= P.pe_cut && (sa < P.pe_sfast || (r.x & 0xFu) == 15u);
+        const bool cb = sb <= P.pe_cut && (sb < P.pe_sfast || (r.z & 0xFu) == 15u);
+        queue = sp || !ka || ca || (hasb && (!kb || cb));
+        if (!queue) {
+          // areas are summed as integers in units of 2^-32 phe: fma(a, 2^32, 1.5 * 2^52) rounds a 2^32 to the
+          // nearest integer (ties to even, as __double2ll_rn) and leaves it in the low mantissa bits; the raw
+          // words are added up and the offsets taken out at the flush (a_spike of them)
+          const double a1 = dp ? sa + sb : sa;
+          const double a2 = (hasb && !dp) ? sb : -DBL_MAX;
+          if (a1 > det.sPEthr) {
+            a_spike += 1u;
+            a_fx += (unsigned long long)__double_as_longlong(fma(a1, NB_AREA_FX, NB_AREA_MAGIC));
+          }
+          if (a2 > det.sPEthr) {
+            a_spike += 1u;
+            a_fx += (unsigned long long)__double_as_longlong(fma(a2, NB_AREA_FX, NB_AREA_MAGIC));
+          }
         }
       }
-      // queue the unfinished hits (the fast finisher passes the rare kinds on to the slow queue)
-      const unsigned ma = __ballot_sync(0xffffffffu, fa != 0u), mb = __ballot_sync(0xffffffffu, fb != 0u);
-      if (ma | mb) {
-        // lane-major order, one address computation, one 16-byte store per entry
-        const unsigned lt = (1u << lane) - 1u;
-        uint32_t at = qf_addr + uint32_t(fcount + __popc(ma & lt) + __popc(mb & lt)) * uint32_t(sizeof(HitEntry));
-        if (fa) {
-          sts_entry(at, sa, uint32_t(2 * j), (uint32_t(e) << 8) | fa);
-          at += uint32_t(sizeof(HitEntry));
+      const unsigned m = __ballot_sync(0xffffffffu, queue);
+      if (m) {
+        if (queue) {
+          const uint32_t at = q_addr + uint32_t(qcount + __popc(m & ((1u << lane) - 1u))) * uint32_t(sizeof(SlotEntry));
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(at), "r"(uint32_t(j)), "r"(uint32_t(e)) : "memory");
         }
-        if (fb) sts_entry(at, sb, uint32_t(2 * j + 1), (uint32_t(e) << 8) | fb);
-        fcount += __popc(ma) + __popc(mb);
+        qcount += __popc(m);
         __syncwarp();
-        while (fcount >= 32) {
-          fcount -= 32;
-          hits_finish_fast(P, s_area, s_spike, ev0, q, fcount, 32, scount, lane);
-          while (scount >= 32) {
-            scount -= 32;
-            hits_finish_slow(P, s_pref, s_area, s_spike, ev0, q, scount, 32, lane);
-          }
+        if (qcount >= 32) {
+          qcount -= 32;
+          hits_finish_slow(P, s_nh, s_nd, s_area, s_spike, ev0, &s_q[wid][qcount], 32, lane, s_zk, s_zw);
         }
       }
       ++j;
       ++h;
     }
-    // drain (the fast drain may add to the slow queue)
-    if (fcount > 0) hits_finish_fast(P, s_area, s_spike, ev0, q, 0, fcount, scount, lane);
-    while (scount > 0) {
-      const int c = min(scount, 32);
-      scount -= c;
-      hits_finish_slow(P, s_pref, s_area, s_spike, ev0, q, scount, c, lane);
-    }
+    if (qcount > 0) hits_finish_slow(P, s_nh, s_nd, s_area, s_spike, ev0, &s_q[wid][0], qcount, lane, s_zk, s_zw);
     if (h1 > h0) {
-      atomicAdd(&s_area[e], a_fx);
+      atomicAdd(&s_area[e], a_fx - (unsigned long long)a_spike * NB_AREA_MAGIC_BITS);
       atomicAdd(&s_spike[e], a_spike);
-      atomicAdd(&s_nphe[e], a_nphe);
     }
     __syncthreads();
 #pragma unroll
@@ -608,7 +554,7 @@ __global__ void __launch_bounds__(kHitBlock, NB_HIT_MINB)
       if (idx < P.n_events) {
         W.area[idx] = double(s_area[i]) * (1. / NB_AREA_FX);
         W.spike[idx] = int(s_spike[i]);
-        W.nphe[idx] = int(s_nphe[i]);
+        W.nphe[idx] = s_nh[i] + s_nd[i];
       }
     }
     __syncthreads();
@@ -825,6 +771,13 @@ __global__ void __launch_bounds__(256) k_binomial(uint64_t seed, uint64_t first,
                                                   long long* __restrict__ out) {
   for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < count; i += size_t(gridDim.x) * blockDim.x)
     out[i] = binomial(seed, first + i, STREAM_BIN_S1, n, p);
+}
+
+// test hook (nb200_debug_binomial_fixed): the alias-table sampler of k_pre's double-phe count
+__global__ void __launch_bounds__(256) k_binomial_fixed(uint64_t seed, uint64_t first, size_t count, int n,
+                                                        const uint2* __restrict__ tab, long long* __restrict__ out) {
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < count; i += size_t(gridDim.x) * blockDim.x)
+    out[i] = binomial_fixed_p(seed, first + i, STREAM_BIN_S1DPE, n, tab);
 }
 
 // -------------------------------------------------------------------------------------------

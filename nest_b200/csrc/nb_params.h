@@ -59,9 +59,9 @@ struct RunParams {
   // against a 4-bit uniform: for m >= pe_fast = 1.5342 tau (Phi >= 15/16) the draw u4 < 15 accepts
   // outright; only u4 == 15 or m < pe_fast needs Phi itself (exact residual test in the queue)
   double pe_fast;
+  double pe_sfast;       // the same threshold on S: m < pe_fast <=> S < pe_sfast (pe_rho > 0)
   double pe_inv_tau16;   // 16 / pe_tau: index scale of the Phi bounds table (pe_accept_exact)
-  uint32_t dphe_thr22;          // double-phe decision on a 22-bit word
-  uint32_t _pad_pe;
+  const uint2* dpe_alias;  // alias tables of Binomial(2^b, P_dphe) (nb_rng.cuh: binomial_fixed_p), or null
   double coin_u_min;     // exp(-coinWind/20): -20 ln u < coinWind <=> u > this  NEST.cpp:1422
   double below_thr_pct;  // Parametric S1 threshold percentile       NEST.cpp:1437-1457
   double recon_mult;     // MultFact prefactor, execNEST.cpp:1179-1182

@@ -91,3 +91,22 @@ def test_hit_loop_normal_is_standard_normal(ctx):
     # reproducible, and a function of (seed, event, pair) only
     z2, _ = ctx.debug_normal(2048, seed=2024, first_event=1)
     assert (z2 == z[2048:2048 + 4096]).all()
+
+
+@pytest.mark.parametrize("n,p", [(1, 0.173), (7, 0.173), (64, 0.173), (79, 0.173), (350, 0.2), (2047, 0.05), (1000, 0.9)])
+def test_fixed_p_binomial_matches_pmf(ctx, n, p):
+    """The alias-table sampler of the per-event double-phe count against the exact pmf."""
+    count = 4_000_000
+    k = ctx.debug_binomial_fixed(n, p, count, seed=99 + n)
+    assert k.min() >= 0 and k.max() <= n
+    obs = np.bincount(k, minlength=n + 1).astype(float)
+    exp = stats.binom.pmf(np.arange(n + 1), n, p) * count
+    keep = exp >= 20
+    o = np.concatenate([obs[keep], [obs[~keep].sum()]])
+    e = np.concatenate([exp[keep], [exp[~keep].sum()]])
+    m = e > 0
+    chi2 = ((o[m] - e[m]) ** 2 / e[m]).sum()
+    assert stats.chi2.sf(chi2, max(m.sum() - 1, 1)) > 1e-4, (n, p, chi2)
+    mu, var = n * p, n * p * (1 - p)
+    assert abs(k.mean() - mu) < 5 * np.sqrt(var / count)
+    assert (ctx.debug_binomial_fixed(0, p, 100) == 0).all()
