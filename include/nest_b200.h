@@ -354,8 +354,8 @@ int nb200_debug_binomial(nb200_ctx* ctx, uint64_t seed, uint64_t first_event, si
                          double p, int64_t* out);
 
 /* Test hook: the same for the alias-table sampler that draws an event's number of double-phe hits,
- * Binomial(nHits, P_dphe) (the hit-by-hit decision of NEST.cpp:1391, taken once per event): 0 < p < 1,
- * 0 <= n < 2048. */
+ * Binomial(nHits, P_dphe) (the hit-by-hit decision of NEST.cpp:1391, taken once per event; also the
+ * second photo-electrons of S2, NEST.cpp:1984): 0 < p < 1, 0 <= n < 65536. */
 int nb200_debug_binomial_fixed(nb200_ctx* ctx, uint64_t seed, uint64_t first_event, size_t count, int n,
                                double p, int64_t* out);
 

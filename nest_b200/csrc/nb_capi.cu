@@ -279,11 +279,11 @@ int build_params(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo,
   P->dpe_alias = nullptr;
   if (det->P_dphe > 0. && det->P_dphe < 1.) {  // alias tables of Binomial(2^b, P_dphe) for k_pre's double-phe count
     if (!c->d_dpe || c->dpe_p != det->P_dphe) {
-      AliasEntry tab[NB_ALIAS_ENTRIES];
-      build_binomial_alias(det->P_dphe, tab);
-      if (!c->d_dpe) NB_CUDA(c, cudaMalloc(&c->d_dpe, sizeof tab));
-      NB_CUDA(c, cudaMemcpyAsync(c->d_dpe, tab, sizeof tab, cudaMemcpyHostToDevice, c->stream));
-      NB_CUDA(c, cudaStreamSynchronize(c->stream));  // tab is a stack array
+      std::vector<AliasEntry> tab(NB_ALIAS_ENTRIES);
+      build_binomial_alias(det->P_dphe, tab.data());
+      if (!c->d_dpe) NB_CUDA(c, cudaMalloc(&c->d_dpe, sizeof(AliasEntry) * tab.size()));
+      NB_CUDA(c, cudaMemcpyAsync(c->d_dpe, tab.data(), sizeof(AliasEntry) * tab.size(), cudaMemcpyHostToDevice, c->stream));
+      NB_CUDA(c, cudaStreamSynchronize(c->stream));  // tab goes out of scope
       c->dpe_p = det->P_dphe;
     }
     P->dpe_alias = static_cast<const uint2*>(c->d_dpe);
@@ -1307,16 +1307,16 @@ int nb200_debug_binomial_fixed(nb200_ctx* c, uint64_t seed, uint64_t first_event
   if (!c || !out || !(p > 0. && p < 1.) || n < 0 || n >= NB_ALIAS_MAXN) return NB200_EINVAL;
   if (count == 0) return 0;
   NB_CUDA(c, cudaSetDevice(c->device));
-  AliasEntry tab[NB_ALIAS_ENTRIES];
-  build_binomial_alias(p, tab);
+  std::vector<AliasEntry> tab(NB_ALIAS_ENTRIES);
+  build_binomial_alias(p, tab.data());
   long long* dout = nullptr;
   void* dtab = nullptr;
   NB_CUDA(c, cudaMalloc(&dout, count * 8));
-  if (cudaMalloc(&dtab, sizeof tab) != cudaSuccess) {
+  if (cudaMalloc(&dtab, sizeof(AliasEntry) * tab.size()) != cudaSuccess) {
     cudaFree(dout);
     return fail(c, NB200_ENOMEM, "cudaMalloc");
   }
-  cudaMemcpyAsync(dtab, tab, sizeof tab, cudaMemcpyHostToDevice, c->stream);
+  cudaMemcpyAsync(dtab, tab.data(), sizeof(AliasEntry) * tab.size(), cudaMemcpyHostToDevice, c->stream);
   k_binomial_fixed<<<unsigned(std::min<size_t>((count + 255) / 256, 148 * 8)), 256, 0, c->stream>>>(
       seed, first_event, count, n, static_cast<const uint2*>(dtab), dout);
   ++c->launches;

@@ -517,7 +517,11 @@ NB_D void get_s2(Stream& g, uint64_t ev, const RunParams& P, int Ne, double tx, 
   double nphd = floor(((nraw < 0.) ? 0. : nraw) + 0.5);
   long long Nph = (long long)nphd;
   long long nHits = binomial(P.seed, ev, STREAM_BIN_S2HIT, Nph, det.g1_gas * posDep);
-  long long Nphe = nHits + binomial(P.seed, ev, STREAM_BIN_S2DPE, nHits, det.P_dphe);
+  // second photo-electrons: Binomial(nHits, P_dphe), fixed probability -> alias tables (nb_rng.cuh)
+  const bool tab = P.dpe_alias != nullptr && nHits < NB_ALIAS_MAXN;
+  long long Nphe = nHits + (tab ? binomial_fixed_p(P.seed, ev, STREAM_BIN_S2DPE, int(nHits), P.dpe_alias) : 0);
+  if (__any_sync(__activemask(), !tab))  // very large S2 (or P_dphe of 0 / 1): the general sampler
+    Nphe += binomial(P.seed, ev, STREAM_BIN_S2DPE + 8u, tab ? 0 : nHits, det.P_dphe);
   double m = double(Nphe) / P.rc.NewMean;
   double pulseArea = m + det.sPEres * sqrt(m) * z1;
   pulseArea = (pulseArea < 0.) ? 0. : pulseArea;

@@ -9,6 +9,7 @@
 #pragma once
 #include <cstdint>
 #include <cfloat>
+#include <cmath>
 
 #ifdef __CUDACC__
 #define NB_HD __host__ __device__ __forceinline__
@@ -670,13 +671,15 @@ __device__ __noinline__ long long binomial(uint64_t seed, uint64_t event, uint32
 }
 
 // Binomial(n, p) for a probability that is fixed for the whole run (P_dphe): n is split into its binary
-// digits, n = 64 q + sum of 2^b, and Binomial(2^b, p) is drawn from an alias table (Walker / Vose) built on
-// the host for that p -- one 32-bit word, one multiply, one 8-byte load and one compare per digit, q + <= 6
-// draws in all (a 79-hit event: 5), against the ~1500 warp-instructions of a divergent BTRS call.
-// Table b (b = 0..6) holds 2^b + 1 entries {threshold on the 32-bit fraction, alias} at offset 2^b - 1 + b.
-// Outcome probabilities are exact to 2^-32 (the resolution of the other yes/no draws of the chain).
-#define NB_ALIAS_ENTRIES 134
-#define NB_ALIAS_MAXN 2048  // beyond: BTRS
+// digits, n = 4096 q + sum of 2^b, and Binomial(2^b, p) is drawn from an alias table (Walker / Vose) built
+// on the host for that p -- one 32-bit word, one multiply, one 8-byte load and one compare per digit,
+// q + <= 12 draws in all (a 79-hit S1: 5; a 2300-hit S2: 6), against the ~1500 warp-instructions of a
+// divergent BTRS call.  Table b (b = 0..12) holds 2^b + 1 entries {threshold on the 32-bit fraction,
+// alias} at offset 2^b - 1 + b.  Outcome probabilities are exact to 2^-32 (the resolution of the other
+// yes/no draws of the chain).
+#define NB_ALIAS_BITS 12
+#define NB_ALIAS_ENTRIES ((2 << NB_ALIAS_BITS) - 1 + NB_ALIAS_BITS + 1)  // 8204
+#define NB_ALIAS_MAXN (16 << NB_ALIAS_BITS)  // 65536; beyond: BTRS
 NB_D int alias_draw(const uint2* __restrict__ t, uint32_t K, uint32_t w) {
   const uint64_t pr = uint64_t(w) * K;
   const uint32_t idx = uint32_t(pr >> 32);
@@ -690,18 +693,17 @@ NB_D int binomial_fixed_p(uint64_t seed, uint64_t event, uint32_t stream, int n,
   bool have = false;
   int k = 0;
 #pragma unroll 1
-  for (int q = n >> 6; q > 0; --q) {
+  for (int q = n >> NB_ALIAS_BITS; q > 0; --q) {
     if (!have) g.next2(a, b);
-    k += alias_draw(tab + 69, 65u, have ? b : a);
+    k += alias_draw(tab + ((1 << NB_ALIAS_BITS) - 1 + NB_ALIAS_BITS), (1u << NB_ALIAS_BITS) + 1u, have ? b : a);
     have = !have;
   }
-#pragma unroll
-  for (int bit = 0; bit < 6; ++bit) {
-    if ((n >> bit) & 1) {
-      if (!have) g.next2(a, b);
-      k += alias_draw(tab + ((1 << bit) - 1 + bit), (1u << bit) + 1u, have ? b : a);
-      have = !have;
-    }
+#pragma unroll 1
+  for (int rest = n & ((1 << NB_ALIAS_BITS) - 1); rest != 0; rest &= rest - 1) {  // its set bits, lowest first
+    const int bit = __ffs(rest) - 1;
+    if (!have) g.next2(a, b);
+    k += alias_draw(tab + ((1 << bit) - 1 + bit), (1u << bit) + 1u, have ? b : a);
+    have = !have;
   }
   return k;
 }
@@ -712,30 +714,38 @@ struct AliasEntry {
   uint32_t thr, alias;
 };
 inline void build_binomial_alias(double p, AliasEntry* out /* NB_ALIAS_ENTRIES */) {
-  for (int b = 0; b <= 6; ++b) {
+  const int KMAX = (1 << NB_ALIAS_BITS) + 1;
+  double* pmf = new double[KMAX];
+  int* small = new int[KMAX];
+  int* large = new int[KMAX];
+  const double lp = std::log(p), lq = std::log1p(-p);
+  for (int b = 0; b <= NB_ALIAS_BITS; ++b) {
     const int m = 1 << b, K = m + 1;
     AliasEntry* t = out + (m - 1 + b);
-    double pmf[65], sc[65];
-    pmf[0] = 1.;
-    for (int i = 0; i < m; ++i) pmf[0] *= (1. - p);
-    for (int k = 0; k < m; ++k) pmf[k + 1] = pmf[k] * (double(m - k) / double(k + 1)) * (p / (1. - p));
     double tot = 0.;
-    for (int k = 0; k < K; ++k) tot += pmf[k];
-    int small[65], large[65], ns = 0, nl = 0;
+    for (int k = 0; k < K; ++k) {  // log space: (1-p)^4096 underflows
+      pmf[k] = std::exp(std::lgamma(double(m) + 1.) - std::lgamma(double(k) + 1.) - std::lgamma(double(m - k) + 1.) +
+                        double(k) * lp + double(m - k) * lq);
+      tot += pmf[k];
+    }
+    int ns = 0, nl = 0;
     for (int k = 0; k < K; ++k) {
-      sc[k] = pmf[k] / tot * K;
-      (sc[k] < 1. ? small[ns++] : large[nl++]) = k;
+      pmf[k] = pmf[k] / tot * K;
+      (pmf[k] < 1. ? small[ns++] : large[nl++]) = k;
     }
     for (int k = 0; k < K; ++k) t[k] = AliasEntry{0xFFFFFFFFu, uint32_t(k)};
     while (ns > 0 && nl > 0) {
       const int s_ = small[--ns], l_ = large[--nl];
-      const double v = sc[s_] * 4294967296.0;
+      const double v = pmf[s_] * 4294967296.0;
       t[s_].thr = v >= 4294967295.0 ? 0xFFFFFFFFu : uint32_t(v);
       t[s_].alias = uint32_t(l_);
-      sc[l_] = (sc[l_] + sc[s_]) - 1.;
-      (sc[l_] < 1. ? small[ns++] : large[nl++]) = l_;
+      pmf[l_] = (pmf[l_] + pmf[s_]) - 1.;
+      (pmf[l_] < 1. ? small[ns++] : large[nl++]) = l_;
     }
   }
+  delete[] pmf;
+  delete[] small;
+  delete[] large;
 }
 
 }  // namespace nb

@@ -93,7 +93,8 @@ def test_hit_loop_normal_is_standard_normal(ctx):
     assert (z2 == z[2048:2048 + 4096]).all()
 
 
-@pytest.mark.parametrize("n,p", [(1, 0.173), (7, 0.173), (64, 0.173), (79, 0.173), (350, 0.2), (2047, 0.05), (1000, 0.9)])
+@pytest.mark.parametrize("n,p", [(1, 0.173), (7, 0.173), (64, 0.173), (79, 0.173), (350, 0.2), (2047, 0.05), (1000, 0.9),
+                                  (4096, 0.173), (5000, 0.173), (65535, 0.173)])
 def test_fixed_p_binomial_matches_pmf(ctx, n, p):
     """The alias-table sampler of the per-event double-phe count against the exact pmf."""
     count = 4_000_000
