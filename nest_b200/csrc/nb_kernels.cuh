@@ -321,10 +321,22 @@ struct SlotEntry {
 constexpr int kSlotCap = 64;  // <= 31 left over + 32 pushed per iteration
 constexpr size_t kHitDynSmem = NB_ZIG_N * (sizeof(double) + sizeof(uint32_t));  // ziggurat tables (opt-in: > 48 KB total)
 
+// 64-bit add to shared memory as two 32-bit atomics with the carry passed on by whoever wraps the low word
+// (the native shared-memory atomic is 32 bits wide; a 64-bit atomicAdd compiles to a compare-and-swap loop,
+// 6 % of the kernel's stall samples).  The adds to a word are totally ordered, so every wrap of the low
+// word is seen by exactly one adder and the pair ends up holding the exact 64-bit sum.
+NB_D void smem_add64(unsigned long long* p, unsigned long long v) {
+  unsigned int* w = reinterpret_cast<unsigned int*>(p);
+  const unsigned int lo = (unsigned int)v;
+  const unsigned int old = atomicAdd(w, lo);
+  const unsigned int hi = (unsigned int)(v >> 32) + ((old + lo) < old ? 1u : 0u);
+  if (hi) atomicAdd(w + 1, hi);
+}
+
 NB_D void hit_commit(const RunParams& P, unsigned long long* s_area, unsigned int* s_spike, int slot, double a,
                      bool pass_coin) {
   if (a > P.det.sPEthr && pass_coin) {
-    atomicAdd(&s_area[slot], (unsigned long long)__double2ll_rn(a * NB_AREA_FX));
+    smem_add64(&s_area[slot], (unsigned long long)__double2ll_rn(a * NB_AREA_FX));
     atomicAdd(&s_spike[slot], 1u);
   }
 }
@@ -411,7 +423,8 @@ __global__ void __launch_bounds__(kHitBlock, NB_HIT_MINB)
   const nb200_detector& det = P.det;
   const Work& W = P.work;
   const uint64_t n_groups = (P.n_events + kHitGroup - 1) / kHitGroup;
-  const uint32_t q_addr = uint32_t(__cvta_generic_to_shared(&s_q[wid][0]));
+  uint32_t q_addr = uint32_t(__cvta_generic_to_shared(&s_q[wid][0]));
+  asm volatile("" : "+r"(q_addr));  // opaque: keep it in a register instead of recomputing it at every push
   const bool all_special = det.sPEeff < 1.;  // efficiency draws: every slot goes through the finisher
 
   // groups are handed out by a device counter (zeroed before the launch): their cost follows their hit
@@ -481,7 +494,7 @@ __global__ void __launch_bounds__(kHitBlock, NB_HIT_MINB)
       bool queue = false;
       if (h < h1) {
         if (h == e_end) {  // crossed into the next event with hits: flush, then advance
-          atomicAdd(&s_area[e], a_fx - (unsigned long long)a_spike * NB_AREA_MAGIC_BITS);
+          smem_add64(&s_area[e], a_fx - (unsigned long long)a_spike * NB_AREA_MAGIC_BITS);
           atomicAdd(&s_spike[e], a_spike);
           a_fx = 0ull;
           a_spike = 0u;
@@ -543,7 +556,7 @@ __global__ void __launch_bounds__(kHitBlock, NB_HIT_MINB)
     }
     if (qcount > 0) hits_finish_slow(P, s_nh, s_nd, s_area, s_spike, ev0, &s_q[wid][0], qcount, lane, s_zk, s_zw);
     if (h1 > h0) {
-      atomicAdd(&s_area[e], a_fx - (unsigned long long)a_spike * NB_AREA_MAGIC_BITS);
+      smem_add64(&s_area[e], a_fx - (unsigned long long)a_spike * NB_AREA_MAGIC_BITS);
       atomicAdd(&s_spike[e], a_spike);
     }
     __syncthreads();

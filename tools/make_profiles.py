@@ -12,7 +12,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
-KERNEL = "_ZN2nb6k_hitsENS_9RunParamsE"
+KERNEL = "_ZN2nb6k_hitsENS_9RunParamsEPj"
 
 
 def nm(s):
@@ -48,7 +48,7 @@ def main():
     json.dump(b, open(os.path.join(out, "%s_bench_n1.json" % tag), "w"), indent=1)
     if refarm:
         json.dump(json.load(open(refarm)), open(os.path.join(out, "%s_bench_reference_arm.json" % tag), "w"), indent=1)
-    kernels = [("k_hits", "_ZN2nb6k_hitsENS_9RunParamsE", rep)]
+    kernels = [("k_hits", "_ZN2nb6k_hitsENS_9RunParamsEPj", rep)]
     for short, mangled in (("k_pre", "_ZN2nb5k_preENS_9RunParamsEPi"), ("k_post", "_ZN2nb6k_postENS_9RunParamsEPi")):
         cand = rep.replace("k_hits", short)
         if cand != rep and os.path.exists(cand):
