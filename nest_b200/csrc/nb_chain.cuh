@@ -309,11 +309,13 @@ struct S1Acc {
 //     The accept test itself never needs T: it is a Bernoulli(Phi(m/tau)) draw, tried first
 //     against a 4-bit uniform (u4 < 15 accepts when Phi >= 15/16) with the exact residual
 //     probability evaluated (erfc) only when that fails -- 2 % of hits;
-//   * one Box-Muller transform therefore serves TWO hits of an event (cos and sin outputs), and
-//     one Philox block the pair: 48 bits of radius, 24 of angle, 2 x 24 for the double-phe draws,
-//     2 x 4 for the truncation pre-tests;
-//   * hits needing anything more (exact truncation test, second photo-electron, efficiency or
-//     coincidence draws) are queued per warp and finished 32 at a time (k_hits);
+//   * that normal comes from a 1024-layer ziggurat (nb_rng.cuh) instead of Box-Muller;
+//   * the hits of an event are exchangeable, so the number of double-phe hits is drawn once per
+//     event (k_pre: Binomial(nHits, P_dphe) from alias tables) instead of a Bernoulli per hit, and one
+//     Philox block serves a SLOT of two photo-electrons -- one double hit or two single hits:
+//     2 x (28 bits of abscissa, 10 of layer, 4 for the truncation pre-test);
+//   * slots needing anything more (wedge / tail of the ziggurat, exact truncation test, redraw,
+//     efficiency or coincidence draws) are queued per warp and redone in full 32 at a time (k_hits);
 //   * -20 ln u < coinWind is tested as u > exp(-coinWind/20) and only when nHits <= coinLevel.
 
 // Phi(z) at z = -8 + k/16, k = 0..304, filled by nb200_create (host erfc).  Linear interpolation

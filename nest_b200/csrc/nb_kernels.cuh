@@ -70,12 +70,12 @@ __global__ void __launch_bounds__(256) k_yields(const __grid_constant__ YieldsPa
 //           smearing and the S1 prelude up to nHits = binomial(Nph, g1(x,y,z)).
 //   k_hits  the per-hit S1 loop (NEST.cpp:1367-1429), the dominant cost.  Hit counts differ by
 //           orders of magnitude between events, so a block takes a GROUP of events, prefix-sums
-//           their hit counts in shared memory and deals the flattened hit range out evenly:
-//           every thread runs the same number of hits (+-1) whatever events they belong to.
-//           Each hit draws from its own Philox block keyed (seed; event, hit index) and the
-//           areas are accumulated as 2^-32 phe integers, so the result for an event does not
-//           depend on how the range was cut (bit-identical for any batch split / GPU count).
-//           The kernel carries no event state: few registers, high occupancy, small code.
+//           their work items (slots of two photo-electrons, see the kernel) in shared memory and
+//           deals the flattened range out evenly: every thread runs the same number of slots
+//           (+-1) whatever events they belong to.  Each slot draws from its own Philox block keyed
+//           (seed; event, slot index) and the areas are accumulated as 2^-32 phe integers, so the
+//           result for an event does not depend on how the range was cut (bit-identical for any
+//           batch split / GPU count).
 //   k_post  one thread = one event: S1 epilogue (noise, thresholds, coincidence, spike smearing),
 //           S2, signal selection, energy reconstruction, band accumulation (shared-memory
 //           integer accumulators flushed once per block) and the optional SoA record.
@@ -139,8 +139,8 @@ NB_D double drift_velocity_dev(const RunParams& P, double eField) {
 // launch geometry, measured on B200 (tools/sweep_variants.sh): k_pre and k_post are fastest at 64
 // registers with 32 warps per SM in large lockstep blocks (k_post one 1024-thread block, k_pre two
 // 512-thread blocks: the spills cost less than the FP64 dependency stalls the extra warps hide, and
-// 128-thread blocks are 35 % slower for lack of instruction-cache sharing); k_hits at 64 registers
-// (4 blocks of 256 per SM)
+// 128-thread blocks are 35 % slower for lack of instruction-cache sharing); k_hits in 128-thread
+// blocks at 96 registers (5 per SM)
 #ifndef NB_PRE_BLOCK
 #define NB_PRE_BLOCK 512
 #endif
