@@ -186,6 +186,55 @@ def test_few_hit_s1_area_shape(ctx, ref):
         assert abs(fa - fb) < 5 * np.sqrt(fb * (1 - fb) / len(b) * 2 + 1e-12), (hits, fa, fb)
 
 
+def test_double_phe_count_per_event_keeps_the_joint_law(ctx, ref):
+    """the hit loop draws the NUMBER of double-phe hits once per event (the hits are exchangeable) instead of
+    the reference's Bernoulli per hit (NEST.cpp:1391): the joint law of (nHits, Nphe, area, spike) must not
+    move.  Conditional on nHits, compare Nphe - nHits ~ Binomial(nHits, P_dphe) exactly, and against the
+    reference the covariance of the extra photo-electrons with the pulse area and the spike count."""
+    from scipy import stats
+    n = 300000
+    xyz = (20.0, 30.0, 280.0)
+    g, _ = gpu_chain(ctx, 31, n, capi.beta, capi.SRC_MONO, 6.0, 6.0, 180.0, 1, xyz, 0, 1.0, 1)
+    r = ref_chain(ref, 32, n, capi.beta, capi.SRC_MONO, 6.0, 6.0, 180.0, 1, xyz, 0, 1.0, 1)
+    S1 = refprobe.S1_0
+    p_dphe = capi.detector("LUX_Run03").P_dphe
+
+    def cols(a):
+        a = a[np.abs(a[:, S1 + 0]) > 3]   # above the coincidence level: every hit is counted
+        return np.abs(a[:, S1 + 0]), np.abs(a[:, S1 + 1]), np.abs(a[:, S1 + 2]), np.abs(a[:, S1 + 6])
+
+    hg, pg, ag, sg = cols(g)
+    hr, pr, ar, sr = cols(r)
+    # exact conditional law of the extra photo-electrons, pooled over nHits through their z-scores
+    for h, pe in ((hg, pg), (hr, pr)):
+        extra = pe - h
+        assert abs(extra.sum() - p_dphe * h.sum()) < 5 * np.sqrt(p_dphe * (1 - p_dphe) * h.sum())
+        z = (extra - p_dphe * h) / np.sqrt(p_dphe * (1 - p_dphe) * h)
+        assert abs(z.var() - 1) < 5 * np.sqrt(2 / z.size) + 0.01
+    for hits in (20, 30, 40):
+        a, b = (pg - hg)[hg == hits], (pr - hr)[hr == hits]
+        assert len(a) > 2000 and len(b) > 2000
+        obs = np.bincount(a.astype(int), minlength=hits + 1).astype(float)
+        exp = stats.binom.pmf(np.arange(hits + 1), hits, p_dphe) * len(a)
+        keep = exp >= 10
+        o = np.concatenate([obs[keep], [obs[~keep].sum()]])
+        e = np.concatenate([exp[keep], [exp[~keep].sum()]])
+        assert stats.chisquare(o[e > 0], e[e > 0] * o.sum() / e[e > 0].sum()).pvalue > P_MIN, hits
+    # joint moments against the reference: residuals after removing the dependence on nHits
+    def resid(h, y):
+        k = np.polyfit(h, y, 1)
+        return y - np.polyval(k, h)
+    for name, yg, yr in (("area", ag, ar), ("spike", sg, sr)):
+        cg = np.mean(resid(hg, pg - hg) * resid(hg, yg))
+        cr = np.mean(resid(hr, pr - hr) * resid(hr, yr))
+        vg = np.var(resid(hg, pg - hg) * resid(hg, yg)) / hg.size
+        vr = np.var(resid(hr, pr - hr) * resid(hr, yr)) / hr.size
+        assert abs(cg - cr) < 5 * np.sqrt(vg + vr), (name, cg, cr)
+        # a second photo-electron adds ~1 phe of area to its hit: the covariance is not zero
+        if name == "area":
+            assert cg > 10 * np.sqrt(vg)
+
+
 def _variant_detectors():
     a = capi.detector("LUX_Run03")        # efficiency draws, 3-fold coincidence, S1 linear noise
     a.sPEeff, a.coinLevel, a.numPMTs = 0.85, 3, 61
