@@ -338,7 +338,24 @@ def main():
                 t1_.record()
                 torch.cuda.synchronize()
             others[name] = n_ / (t0_.elapsed_time(t1_) * 1e-3)
+        # config 5: LArNEST NR mean yields + default fluctuations, device-resident in and out (120 B/event:
+        # E and field in, 9 yield columns and 4 fluctuation columns out) -- the HBM-bound member of the family
+        n_ = 20_000_000
+        E_ = torch.rand(n_, dtype=torch.float64, device="cuda") * 999.9 + 0.1
+        F_ = torch.rand(n_, dtype=torch.float64, device="cuda") * 999.0 + 1.0
+        Y_ = torch.empty((9, n_), dtype=torch.float64, device="cuda")
+        Fl_ = torch.empty((4, n_), dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        for rep in range(2):
+            ctx.synchronize()
+            t0w = time.perf_counter()
+            ctx.lar_device(0, n_, E_.data_ptr(), F_.data_ptr(), 1.393, Y_.data_ptr(), Fl_.data_ptr(), seed=seed)
+            ctx.synchronize()
+            dtw = time.perf_counter() - t0w
+        others["config5_LAr_NR_yields+fluctuations"] = n_ / dtw
         out["other_workloads_events_per_s"] = others
+        out["lar_hbm_gbs"] = 120.0 * n_ / dtw / 1e9
+        del E_, F_, Y_, Fl_
     if rank == 0:
         peak = ctx.fp64_peak()
         # dominant kernel: k_hits, the per-hit S1 loop.  Algorithmic work per launch = SURVEY 8(d)'s

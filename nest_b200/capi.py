@@ -374,6 +374,11 @@ class Context:
         self._check(lib().nb200_debug_normal(self.h, seed, first_event, int(pairs), _dptr(out), _dptr(kind)))
         return out, kind
 
+    def lar_device(self, species, n, dE, dF, density, dY, dFl, seed=0, first_event=0):
+        """LArNEST on device-resident arrays (raw pointers: E[n], field[n] in; yields[9][n], fluct[4][n] out or 0)."""
+        self._check(lib().nb200_lar(self.h, species, int(n), C.c_void_p(dE), C.c_void_p(dF), density, seed, first_event,
+                                    MEM_DEVICE, C.c_void_p(dY) if dY else None, C.c_void_p(dFl) if dFl else None))
+
     def lar(self, species, E, field, density, seed=0, first_event=0, want_fluct=True):
         E = np.ascontiguousarray(E, np.float64)
         F = np.ascontiguousarray(np.broadcast_to(field, E.shape), np.float64)
