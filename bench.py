@@ -376,8 +376,13 @@ def main():
             "chain_achieved_tflops": float(n) * flops_per_event / (chain_ms * 1e-3) / 1e12,
             "peak_source": "measured on this device by nb200_fp64_peak (register-resident DFMA chain, CUDA "
                            "events); MEASURED_PEAKS.json carries HBM and bf16 figures only (nominal FP64 37.2)",
-            "note": "FP64 CUDA-core pipe bound, not HBM or tensor: no contraction, and in band-only mode the "
-                    "only HBM stream is the 140 B/event stage workspace (see hbm_workspace_frac)",
+            "note": "FP64 CUDA-core roofline, not HBM or tensor: no contraction, and in band-only mode the only HBM "
+                    "stream is the 140 B/event stage workspace (see hbm_workspace_frac).  `achieved` counts the "
+                    "REFERENCE algorithm's per-hit work (SURVEY 8d: 192 DFMA-equivalent flop per PMT hit: two "
+                    "Box-Muller normals, a Bernoulli, ...) delivered per second; the kernel itself executes far "
+                    "fewer FP64 instructions per hit (ziggurat normal, one normal per photo-electron, per-event "
+                    "double-phe count): ncu shows its FP64 pipe ~11 % busy and 65 % of issue slots used "
+                    "(profiles/r01_k_hits_ncu_full.txt, DESIGN.md section 5)",
             "hbm_workspace_frac": None}
         try:
             with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
