@@ -309,11 +309,11 @@ struct S1Acc {
 //     The accept test itself never needs T: it is a Bernoulli(Phi(m/tau)) draw, tried first
 //     against a 4-bit uniform (u4 < 15 accepts when Phi >= 15/16) with the exact residual
 //     probability evaluated (erfc) only when that fails -- 2 % of hits;
-//   * that normal comes from a 1024-layer ziggurat (nb_rng.cuh) instead of Box-Muller;
+//   * that normal comes from a 2048-layer ziggurat (nb_rng.cuh) instead of Box-Muller;
 //   * the hits of an event are exchangeable, so the number of double-phe hits is drawn once per
 //     event (k_pre: Binomial(nHits, P_dphe) from alias tables) instead of a Bernoulli per hit, and one
 //     Philox block serves a SLOT of two photo-electrons -- one double hit or two single hits:
-//     2 x (28 bits of abscissa, 10 of layer, 4 for the truncation pre-test);
+//     2 x (28 bits of abscissa, 11 of layer, 4 for the truncation pre-test);
 //   * slots needing anything more (wedge / tail of the ziggurat, exact truncation test, redraw,
 //     efficiency or coincidence draws) are queued per warp and redone in full 32 at a time (k_hits);
 //   * -20 ln u < coinWind is tested as u > exp(-coinWind/20) and only when nHits <= coinLevel.

@@ -140,7 +140,7 @@ NB_D double drift_velocity_dev(const RunParams& P, double eField) {
 // registers with 32 warps per SM in large lockstep blocks (k_post one 1024-thread block, k_pre two
 // 512-thread blocks: the spills cost less than the FP64 dependency stalls the extra warps hide, and
 // 128-thread blocks are 35 % slower for lack of instruction-cache sharing); k_hits in 128-thread
-// blocks at 96 registers (5 per SM)
+// blocks at 128 registers (4 per SM)
 #ifndef NB_PRE_BLOCK
 #define NB_PRE_BLOCK 512
 #endif
@@ -154,7 +154,8 @@ NB_D double drift_velocity_dev(const RunParams& P, double eField) {
 #define NB_POST_MINB 1
 #endif
 #ifndef NB_HIT_MINB
-#define NB_HIT_MINB 5  // 128-thread blocks at 96 registers (20 warps/SM): measured best of {256x4@64, 256x3@80, 256x2@128, 128x6@80, 128x5@96, 128x4@128}
+#define NB_HIT_MINB 4  // 128-thread blocks at 128 registers (no spills, 16 warps/SM) with the 24 KB ziggurat tables: measured best of
+                       // {256x4@64, 256x3@80, 256x2@128, 128x6@80, 128x5@96, 128x4@128} x {1024, 2048 layers}
 #endif
 constexpr int kPreBlock = NB_PRE_BLOCK;
 constexpr int kPostBlock = NB_POST_BLOCK;
@@ -508,8 +509,8 @@ __global__ void __launch_bounds__(kHitBlock, NB_HIT_MINB)
           sp = all_special || !(nd + ns > det.coinLevel);
           j = 0;
         }
-        // one Philox block per slot, 64 bits per photo-electron: 28 (abscissa) + 10 (layer) for the
-        // ziggurat normal, 4 for the truncation pre-test (22 spare)
+        // one Philox block per slot, 64 bits per photo-electron: 28 (abscissa) + 11 (layer) for the
+        // ziggurat normal, 4 for the truncation pre-test (21 spare)
         const uint64_t hev = ev0 + e;
         const u128 r = philox4x32_10_rk(uint32_t(hev), uint32_t(hev >> 32), uint32_t(j), STREAM_HIT, P.rk);
         double za, zb;

@@ -300,17 +300,20 @@ NB_D double log_pos(double x) {
 }
 
 // ---- ziggurat normal for the S1 hit loop ---------------------------------------------------
-// Marsaglia & Tsang's ziggurat (J. Stat. Soft. 5(8), 2000) with 1024 layers of equal area, layer
+// Marsaglia & Tsang's ziggurat (J. Stat. Soft. 5(8), 2000) with 2048 layers of equal area, layer
 // index and abscissa taken from DISJOINT bits as Doornik (2005) requires: an exact sampler of
-// N(0,1) -- 99.55 % of the draws are one table look-up, one integer compare and one multiply;
+// N(0,1) -- 99.77 % of the draws are one table look-up, one integer compare and one multiply;
 // the rest (wedges, tail) are finished out of line with exact exp / log tests (zig_finish).
-// (256 layers leave 1.5 % for the out-of-line path, which then costs as much as the core: measured.)
+// (256 layers leave 1.5 % for the out-of-line path, which then costs as much as the core, 1024 leave
+// 0.43 %, 2048 0.23 % at 24 KB of shared memory per block: see DESIGN.md section 5 for the measurements.)
 // Layer i covers |x| < x_i at heights f(x_i)..f(x_{i+1}), x_0 = V/f(R) (base strip + tail),
-// x_1 = R, x_1024 = 0.  Tables are built by nb200_create (host, double) and staged in shared
+// x_1 = R, x_2048 = 0.  Tables are built by nb200_create (host, double) and staged in shared
 // memory by k_hits:  zk[i] = floor(2^28 x_{i+1}/x_i), zw[i] = x_i / 2^28.
 // Abscissa: t = 2 s + 1 with s the signed 28-bit field of the word (odd t: symmetric, no atom
 // at zero), x = t zw[i]; it lies inside the next layer (certain accept) iff |t| < zk[i].
-#define NB_ZIG_BITS 10
+#ifndef NB_ZIG_BITS
+#define NB_ZIG_BITS 11
+#endif
 #define NB_ZIG_N (1 << NB_ZIG_BITS)
 __device__ uint32_t g_zig_k[NB_ZIG_N];
 __device__ double g_zig_w[NB_ZIG_N];
