@@ -488,6 +488,11 @@ __global__ void __launch_bounds__(kHitBlock, NB_HIT_MINB)
       sp = all_special || !(nd + ns > det.coinLevel);
       j = h0 - s_ppref[e];
     }
+    PhiloxEvent pev;  // the per-event part of the slot blocks' first Philox round
+    {
+      const uint64_t hev = ev0 + e;
+      pev = philox_event_prep(uint32_t(hev), uint32_t(hev >> 32), STREAM_HIT, P.rk);
+    }
     unsigned long long a_fx = 0ull;
     unsigned int a_spike = 0u;
     int qcount = 0;  // warp-uniform queue fill
@@ -508,11 +513,12 @@ __global__ void __launch_bounds__(kHitBlock, NB_HIT_MINB)
           jlast = (ns & 1) ? nd + (ns >> 1) : -1;
           sp = all_special || !(nd + ns > det.coinLevel);
           j = 0;
+          const uint64_t hev = ev0 + e;
+          pev = philox_event_prep(uint32_t(hev), uint32_t(hev >> 32), STREAM_HIT, P.rk);
         }
         // one Philox block per slot, 64 bits per photo-electron: 28 (abscissa) + 11 (layer) for the
         // ziggurat normal, 4 for the truncation pre-test (21 spare)
-        const uint64_t hev = ev0 + e;
-        const u128 r = philox4x32_10_rk(uint32_t(hev), uint32_t(hev >> 32), uint32_t(j), STREAM_HIT, P.rk);
+        const u128 r = philox4x32_10_rk_event(pev, uint32_t(j), P.rk);
         double za, zb;
         const bool ka = zig_fast(r.x, r.y, s_zk, s_zw, za), kb = zig_fast(r.z, r.w, s_zk, s_zw, zb);
         const double sa = fma(P.pe_sig, za, P.pe_mu), sb = fma(P.pe_sig, zb, P.pe_mu);

@@ -19,6 +19,11 @@
 #define NB_D inline
 #endif
 
+// alias tables of the fixed-probability binomial sampler (binomial_fixed_p below)
+#define NB_ALIAS_BITS 12
+#define NB_ALIAS_ENTRIES ((2 << NB_ALIAS_BITS) - 1 + NB_ALIAS_BITS + 1)  // 8204
+#define NB_ALIAS_MAXN (16 << NB_ALIAS_BITS)  // 65536; beyond: BTRS
+
 namespace nb {
 
 // stream ids (counter word 3)
@@ -98,6 +103,38 @@ NB_HD u128 philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, 
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
     uint32_t hi0, lo0, hi1, lo1;
+    mulhilo(0xD2511F53u, c0, hi0, lo0);
+    mulhilo(0xCD9E8D57u, c2, hi1, lo1);
+    uint32_t n0 = hi1 ^ c1 ^ rk[2 * r];
+    uint32_t n2 = hi0 ^ c3 ^ rk[2 * r + 1];
+    c0 = n0;
+    c1 = lo1;
+    c2 = n2;
+    c3 = lo0;
+  }
+  return u128{c0, c1, c2, c3};
+}
+
+// The same block with the first round split off for a loop that walks blocks (c0, c1, *, c3) of one event:
+// of round 1 only the product with c2 changes from block to block; the c0 product, n2 and the key/counter
+// mix of n0 are per-event constants (philox_event_prep).  Bit-identical to philox4x32_10_rk.
+struct PhiloxEvent {
+  uint32_t x;    // c1 ^ rk[0]
+  uint32_t n2;   // hi(M0 c0) ^ c3 ^ rk[1]
+  uint32_t lo0;  // lo(M0 c0)
+};
+NB_HD PhiloxEvent philox_event_prep(uint32_t c0, uint32_t c1, uint32_t c3, const uint32_t* rk) {
+  uint32_t hi0, lo0;
+  mulhilo(0xD2511F53u, c0, hi0, lo0);
+  return PhiloxEvent{c1 ^ rk[0], hi0 ^ c3 ^ rk[1], lo0};
+}
+NB_HD u128 philox4x32_10_rk_event(const PhiloxEvent& ev, uint32_t blk, const uint32_t* rk) {
+  uint32_t hi1, lo1;
+  mulhilo(0xCD9E8D57u, blk, hi1, lo1);
+  uint32_t c0 = hi1 ^ ev.x, c1 = lo1, c2 = ev.n2, c3 = ev.lo0;
+#pragma unroll
+  for (int r = 1; r < 10; ++r) {
+    uint32_t hi0, lo0;
     mulhilo(0xD2511F53u, c0, hi0, lo0);
     mulhilo(0xCD9E8D57u, c2, hi1, lo1);
     uint32_t n0 = hi1 ^ c1 ^ rk[2 * r];
@@ -680,9 +717,6 @@ __device__ __noinline__ long long binomial(uint64_t seed, uint64_t event, uint32
 // divergent BTRS call.  Table b (b = 0..12) holds 2^b + 1 entries {threshold on the 32-bit fraction,
 // alias} at offset 2^b - 1 + b.  Outcome probabilities are exact to 2^-32 (the resolution of the other
 // yes/no draws of the chain).
-#define NB_ALIAS_BITS 12
-#define NB_ALIAS_ENTRIES ((2 << NB_ALIAS_BITS) - 1 + NB_ALIAS_BITS + 1)  // 8204
-#define NB_ALIAS_MAXN (16 << NB_ALIAS_BITS)  // 65536; beyond: BTRS
 NB_D int alias_draw(const uint2* __restrict__ t, uint32_t K, uint32_t w) {
   const uint64_t pr = uint64_t(w) * K;
   const uint32_t idx = uint32_t(pr >> 32);
