@@ -359,6 +359,12 @@ int nb200_debug_binomial(nb200_ctx* ctx, uint64_t seed, uint64_t first_event, si
 int nb200_debug_binomial_fixed(nb200_ctx* ctx, uint64_t seed, uint64_t first_event, size_t count, int n,
                                double p, int64_t* out);
 
+/* Host-only test hooks (no device needed; tests/test_capi_cpu.py): the ziggurat layers
+ * (x[n+1], f[n+1], k[n], w[n], n_layers must equal the library's 2048) and the alias tables of
+ * Binomial(2^b, p), b = 0..12 (8204 entries: table b at offset 2^b - 1 + b). */
+int nb200_debug_zig_tables(int n_layers, double* x, double* f, uint32_t* k, double* w);
+int nb200_debug_alias_tables(double p, int n_entries, uint32_t* thr, uint32_t* alias);
+
 /* counters for the bench: kernels launched by this context since creation */
 uint64_t nb200_launch_count(const nb200_ctx* ctx);
 

@@ -104,7 +104,8 @@ EXPORTS = [
     "nb200_prepare", "nb200_wimp_prep", "nb200_poisson", "nb200_yields", "nb200_run", "nb200_run_async",
     "nb200_band_reset", "nb200_band_attach", "nb200_fp64_peak", "nb200_timing_enable", "nb200_timing_read", "nb200_se_stats", "nb200_band_fetch", "nb200_band_device_buffer", "nb200_allreduce_hist",
     "nb200_band_hist_bytes", "nb200_band_finalize", "nb200_lar", "nb200_launch_count",
-    "nb200_debug_hitmath", "nb200_debug_binomial", "nb200_debug_normal", "nb200_debug_binomial_fixed"]
+    "nb200_debug_hitmath", "nb200_debug_binomial", "nb200_debug_normal", "nb200_debug_binomial_fixed",
+    "nb200_debug_zig_tables", "nb200_debug_alias_tables"]
 
 _lib = None
 
@@ -169,6 +170,8 @@ def lib():
     L.nb200_debug_hitmath.argtypes = [vp, C.c_size_t, vp, vp]
     L.nb200_debug_binomial.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_size_t, C.c_int64, C.c_double, vp]
     L.nb200_debug_binomial_fixed.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_size_t, C.c_int, C.c_double, vp]
+    L.nb200_debug_zig_tables.argtypes = [C.c_int, vp, vp, vp, vp]
+    L.nb200_debug_alias_tables.argtypes = [C.c_double, C.c_int, vp, vp]
     L.nb200_debug_normal.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_size_t, vp, vp]
     L.nb200_launch_count.argtypes = [vp]
     L.nb200_launch_count.restype = C.c_uint64

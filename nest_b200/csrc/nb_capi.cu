@@ -470,40 +470,15 @@ int nb200_create(int device, nb200_ctx** out) {
       return NB200_ECUDA;
     }
   }
-  {  // ziggurat layers of the hit loop's normal sampler (nb_rng.cuh): solve R so that the layers of
-     // equal area V = R f(R) + tail(R) close exactly at f = 1
-    double zx[NB_ZIG_N + 1], zf[NB_ZIG_N + 1], zw[NB_ZIG_N];
-    uint32_t zk[NB_ZIG_N];
-    auto f = [](double x) { return std::exp(-0.5 * x * x); };
-    auto fill = [&](double R) -> double {  // returns f at the top minus 1 (> 0: R too small)
-      const double V = R * f(R) + 1.2533141373155002512 * std::erfc(R * 0.70710678118654752440);
-      zx[0] = V / f(R);
-      zx[1] = R;
-      for (int i = 1; i < NB_ZIG_N; ++i) {
-        const double fi = f(zx[i]) + V / zx[i];
-        if (i == NB_ZIG_N - 1) return fi - 1.;
-        if (fi >= 1.) return double(NB_ZIG_N - i);
-        zx[i + 1] = std::sqrt(-2. * std::log(fi));
-      }
-      return 0.;
-    };
-    double lo = 3.0, hi = 5.0;
-    for (int it = 0; it < 200; ++it) {
-      const double mid = 0.5 * (lo + hi);
-      (fill(mid) > 0. ? lo : hi) = mid;
-    }
-    fill(hi);
-    zx[NB_ZIG_N] = 0.;
-    for (int i = 1; i <= NB_ZIG_N; ++i) zf[i] = f(zx[i]);
-    zf[0] = 0.;
-    zf[NB_ZIG_N] = 1.;
-    for (int i = 0; i < NB_ZIG_N; ++i) {
-      zk[i] = uint32_t(std::floor(268435456.0 * (zx[i + 1] / zx[i])));
-      zw[i] = zx[i] / 268435456.0;
-    }
+  {  // ziggurat layers of the hit loop's normal sampler (nb_rng.cuh)
+    std::vector<double> zx(NB_ZIG_N + 1), zf(NB_ZIG_N + 1), zw(NB_ZIG_N);
+    std::vector<uint32_t> zk(NB_ZIG_N);
+    build_zig_tables(zx.data(), zf.data(), zk.data(), zw.data());
     const double R = zx[1];
-    if (cudaMemcpyToSymbol(g_zig_k, zk, sizeof zk) != cudaSuccess || cudaMemcpyToSymbol(g_zig_w, zw, sizeof zw) != cudaSuccess ||
-        cudaMemcpyToSymbol(g_zig_f, zf, sizeof zf) != cudaSuccess || cudaMemcpyToSymbol(g_zig_R, &R, sizeof R) != cudaSuccess) {
+    if (cudaMemcpyToSymbol(g_zig_k, zk.data(), sizeof(uint32_t) * NB_ZIG_N) != cudaSuccess ||
+        cudaMemcpyToSymbol(g_zig_w, zw.data(), sizeof(double) * NB_ZIG_N) != cudaSuccess ||
+        cudaMemcpyToSymbol(g_zig_f, zf.data(), sizeof(double) * (NB_ZIG_N + 1)) != cudaSuccess ||
+        cudaMemcpyToSymbol(g_zig_R, &R, sizeof R) != cudaSuccess) {
       g_err_noctx = std::string("context setup: ") + cudaGetErrorString(cudaGetLastError());
       nb200_destroy(c);
       return NB200_ECUDA;
@@ -1299,6 +1274,23 @@ int nb200_debug_binomial(nb200_ctx* c, uint64_t seed, uint64_t first_event, size
   cudaError_t e = cudaStreamSynchronize(c->stream);
   cudaFree(dout);
   if (e != cudaSuccess) return fail(c, NB200_ECUDA, cudaGetErrorString(e));
+  return 0;
+}
+
+// host-only test hooks (no device needed): the tables the samplers above are built on
+int nb200_debug_zig_tables(int n_layers, double* x, double* f, uint32_t* k, double* w) {
+  if (n_layers != NB_ZIG_N || !x || !f || !k || !w) return NB200_EINVAL;
+  build_zig_tables(x, f, k, w);
+  return 0;
+}
+int nb200_debug_alias_tables(double p, int n_entries, uint32_t* thr, uint32_t* alias) {
+  if (n_entries != NB_ALIAS_ENTRIES || !(p > 0. && p < 1.) || !thr || !alias) return NB200_EINVAL;
+  std::vector<AliasEntry> tab(NB_ALIAS_ENTRIES);
+  build_binomial_alias(p, tab.data());
+  for (int i = 0; i < NB_ALIAS_ENTRIES; ++i) {
+    thr[i] = tab[i].thr;
+    alias[i] = tab[i].alias;
+  }
   return 0;
 }
 

@@ -19,6 +19,10 @@
 #define NB_D inline
 #endif
 
+// layers of the hit loop's ziggurat normal: 2^NB_ZIG_BITS
+#ifndef NB_ZIG_BITS
+#define NB_ZIG_BITS 11
+#endif
 // alias tables of the fixed-probability binomial sampler (binomial_fixed_p below)
 #define NB_ALIAS_BITS 12
 #define NB_ALIAS_ENTRIES ((2 << NB_ALIAS_BITS) - 1 + NB_ALIAS_BITS + 1)  // 8204
@@ -348,9 +352,6 @@ NB_D double log_pos(double x) {
 // memory by k_hits:  zk[i] = floor(2^28 x_{i+1}/x_i), zw[i] = x_i / 2^28.
 // Abscissa: t = 2 s + 1 with s the signed 28-bit field of the word (odd t: symmetric, no atom
 // at zero), x = t zw[i]; it lies inside the next layer (certain accept) iff |t| < zk[i].
-#ifndef NB_ZIG_BITS
-#define NB_ZIG_BITS 11
-#endif
 #define NB_ZIG_N (1 << NB_ZIG_BITS)
 __device__ uint32_t g_zig_k[NB_ZIG_N];
 __device__ double g_zig_w[NB_ZIG_N];
@@ -746,7 +747,42 @@ NB_D int binomial_fixed_p(uint64_t seed, uint64_t event, uint32_t stream, int n,
 }
 #endif  // __CUDACC__
 
-// host: alias tables of Binomial(2^b, p), b = 0..6, for binomial_fixed_p (0 < p < 1)
+// host: the ziggurat of the hit loop's normal sampler.  x[0..N]: x_0 = V/f(R) (base strip incl. tail),
+// x_1 = R, ..., x_N = 0; f[i] = exp(-x_i^2/2) (f[0] unused, f[N] = 1); k[i] = floor(2^28 x_{i+1}/x_i),
+// w[i] = x_i / 2^28.  R is solved by bisection so that N layers of equal area V = R f(R) + tail(R)
+// close exactly at f = 1.
+inline void build_zig_tables(double* zx, double* zf, uint32_t* zk, double* zw) {
+  const int N = 1 << NB_ZIG_BITS;
+  auto f = [](double x) { return std::exp(-0.5 * x * x); };
+  auto fill = [&](double R) -> double {  // returns f at the top minus 1 (> 0: R too small)
+    const double V = R * f(R) + 1.2533141373155002512 * std::erfc(R * 0.70710678118654752440);
+    zx[0] = V / f(R);
+    zx[1] = R;
+    for (int i = 1; i < N; ++i) {
+      const double fi = f(zx[i]) + V / zx[i];
+      if (i == N - 1) return fi - 1.;
+      if (fi >= 1.) return double(N - i);
+      zx[i + 1] = std::sqrt(-2. * std::log(fi));
+    }
+    return 0.;
+  };
+  double lo = 3.0, hi = 5.0;
+  for (int it = 0; it < 200; ++it) {
+    const double mid = 0.5 * (lo + hi);
+    (fill(mid) > 0. ? lo : hi) = mid;
+  }
+  fill(hi);
+  zx[N] = 0.;
+  for (int i = 1; i <= N; ++i) zf[i] = f(zx[i]);
+  zf[0] = 0.;
+  zf[N] = 1.;
+  for (int i = 0; i < N; ++i) {
+    zk[i] = uint32_t(std::floor(268435456.0 * (zx[i + 1] / zx[i])));
+    zw[i] = zx[i] / 268435456.0;
+  }
+}
+
+// host: alias tables of Binomial(2^b, p), b = 0..12, for binomial_fixed_p (0 < p < 1)
 struct AliasEntry {
   uint32_t thr, alias;
 };

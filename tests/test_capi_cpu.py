@@ -156,3 +156,55 @@ def test_event_range_partitions():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         shard.event_range(2, 2, 10)
+
+
+def test_ziggurat_tables_close_with_equal_areas(built):
+    """host side of the hit loop's normal sampler (nb_rng.cuh: build_zig_tables): 2048 layers of equal
+    area under exp(-x^2/2) including the base strip + tail, closing exactly at f = 1."""
+    from scipy.special import erfc
+    L = built.lib()
+    n = 2048
+    x, f, w = np.zeros(n + 1), np.zeros(n + 1), np.zeros(n)
+    k = np.zeros(n, np.uint32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert L.nb200_debug_zig_tables(n, p(x), p(f), p(k), p(w)) == 0
+    assert L.nb200_debug_zig_tables(1024, p(x), p(f), p(k), p(w)) != 0
+    R = x[1]
+    assert abs(R - 4.216370409511897) < 1e-12 and x[n] == 0.0 and f[n] == 1.0
+    assert (np.diff(x) < 0).all() and (np.diff(f[1:]) > 0).all()
+    assert np.allclose(f[1:], np.exp(-0.5 * x[1:] ** 2), rtol=0, atol=1e-15)
+    V = R * np.exp(-0.5 * R * R) + np.sqrt(np.pi / 2) * erfc(R / np.sqrt(2))
+    assert abs(x[0] * f[1] - V) < 1e-15 * 10                      # base strip: x_0 f(R) = V
+    area = x[1:n] * (f[2:n + 1] - f[1:n])                         # layers 1..n-1
+    assert np.abs(area / V - 1).max() < 1e-9
+    # the rectangles cover the density; what sticks out of it is what the wedge tests reject (0.10 %)
+    assert 0 < 2 * n * V / np.sqrt(2 * np.pi) - 1 < 1.1e-3
+    assert (k == np.floor(2.0 ** 28 * (x[1:] / x[:-1])).astype(np.uint32)).all() and k[n - 1] == 0
+    assert np.array_equal(w, x[:-1] / 2.0 ** 28)
+    # share of draws that leave the layer core (what tests/test_gpu_samplers.py expects of the device)
+    assert abs((1 - (k / 2.0 ** 28).mean()) - 0.0022711) < 1e-6
+
+
+@pytest.mark.parametrize("prob", [0.173, 0.2, 0.01, 0.9])
+def test_alias_tables_reproduce_the_binomial_pmf(built, prob):
+    """host side of the fixed-probability binomial sampler (nb_rng.cuh: build_binomial_alias): the alias
+    tables of Binomial(2^b, p), b = 0..12, give back the pmf to the 2^-32 resolution of their thresholds."""
+    from scipy import stats
+    L = built.lib()
+    ne = 8204
+    thr, alias = np.zeros(ne, np.uint32), np.zeros(ne, np.uint32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert L.nb200_debug_alias_tables(C.c_double(prob), ne, p(thr), p(alias)) == 0
+    assert L.nb200_debug_alias_tables(C.c_double(0.0), ne, p(thr), p(alias)) != 0
+    for b in range(13):
+        m = 1 << b
+        K = m + 1
+        off = m - 1 + b
+        t, a = thr[off:off + K].astype(np.float64), alias[off:off + K].astype(np.int64)
+        assert (a >= 0).all() and (a <= m).all()
+        keep = (t + (t == 2.0 ** 32 - 1)) / 2.0 ** 32        # a saturated threshold means "always keep"
+        pmf = keep / K
+        np.add.at(pmf, a, (1 - keep) / K)
+        exact = stats.binom.pmf(np.arange(K), m, prob)
+        assert abs(pmf.sum() - 1) < 1e-12
+        assert np.abs(pmf - exact).max() < 2.0 ** -31, (b, np.abs(pmf - exact).max())
