@@ -156,7 +156,9 @@ NB_HD u128 philox4x32_10_rk_event(const PhiloxEvent& ev, uint32_t blk, const uin
 // probability 2^-64 each and only matter as log(0) hazards, which the open interval removes.
 NB_HD double u53(uint32_t hi, uint32_t lo) {
   uint64_t v = (uint64_t(hi) << 21) | (uint64_t(lo) >> 11);
-  return (double(v) + 0.5) * 1.1102230246251565404e-16;  // 2^-53
+  const double u = (double(v) + 0.5) * 1.1102230246251565404e-16;  // 2^-53
+  // v = 2^53 - 1 alone rounds up to 1.0 (2^53 - 1/2 is not a double): keep the interval open
+  return u < 1. ? u : 0.99999999999999988898;  // 1 - 2^-53
 }
 // 32-bit uniform on (0,1) for yes/no decisions and angles
 NB_HD double u32d(uint32_t a) { return (double(a) + 0.5) * 2.3283064365386962891e-10; }
