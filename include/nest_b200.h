@@ -306,6 +306,26 @@ size_t nb200_band_hist_bytes(const nb200_analysis* ana);
 int nb200_band_finalize(const nb200_analysis* ana, const nb200_band_hist* hist,
                         double* band /* [numBins][7] */);
 
+/* Band post-processing on the host, the two uses rootNEST makes of a band without ROOT fits:
+ *
+ * nb200_band_chi2 -- goodness of fit between two bands (examples/rootNEST.cpp:600-643): a = the simulated
+ * band, b = the band compared against, both [numBins][7] as nb200_band_finalize writes them.  Bins with
+ * |mean| >= 5 are ignored for useS2 == 0 as in the reference; the error of a width, which rootNEST reads
+ * from its Gaussian fits, is sigma/sqrt(2N) = band[.][4]/sqrt(2); empty bins are skipped.
+ * DoF = numBins - |free_param|.  out[6] = reduced chi^2 of the means, of the widths, their arithmetic and
+ * geometric means, and the mean %-differences (a - b)/b of means and widths.  NB200_EINVAL when the bin
+ * centres differ by more than 0.05 (the reference's "Binning doesn't match for GoF calculation").
+ *
+ * nb200_band_leakage -- fraction of the accumulator's events below a centroid, by counting
+ * (examples/rootNEST.cpp:880-915 with the per-bin centroid, NRbandCenter = 1): centroid[numBins] in the
+ * band's y units; counted on the 2-D histogram (the log bin holding the centroid is split linearly, so the
+ * resolution is (logMax - logMin)/logBins); events the reference would have pushed as y = 0 count as
+ * below.  leak[numBins]; err_hi / err_lo[numBins] = the reference's Poisson error bars (:898-903) or NULL;
+ * total[3] = {events below, all events, ratio} or NULL. */
+int nb200_band_chi2(int numBins, int useS2, const double* a, const double* b, int free_param, double* out);
+int nb200_band_leakage(const nb200_analysis* ana, const nb200_band_hist* hist, const double* centroid,
+                       double* leak, double* err_hi, double* err_lo, double* total);
+
 /* LAr: replaces LArNEST::FullCalculation (src/LArNEST.cpp:17-33) for species
  * NR=0, ER=1, Alpha=2 (LArParameters.hh:27-34).  yields [9][n] in the field order
  * of LArYieldResult (LArNEST.hh:19-29), fluct [4][n] LArYieldFluctuationResult

@@ -103,7 +103,7 @@ EXPORTS = [
     "nb200_synchronize", "nb200_detector_builtin", "nb200_model_default", "nb200_analysis_default",
     "nb200_prepare", "nb200_wimp_prep", "nb200_poisson", "nb200_yields", "nb200_run", "nb200_run_async",
     "nb200_band_reset", "nb200_band_attach", "nb200_fp64_peak", "nb200_timing_enable", "nb200_timing_read", "nb200_se_stats", "nb200_band_fetch", "nb200_band_device_buffer", "nb200_allreduce_hist",
-    "nb200_band_hist_bytes", "nb200_band_finalize", "nb200_lar", "nb200_launch_count",
+    "nb200_band_hist_bytes", "nb200_band_finalize", "nb200_band_chi2", "nb200_band_leakage", "nb200_lar", "nb200_launch_count",
     "nb200_debug_hitmath", "nb200_debug_binomial", "nb200_debug_normal", "nb200_debug_binomial_fixed",
     "nb200_debug_zig_tables", "nb200_debug_alias_tables"]
 
@@ -165,6 +165,8 @@ def lib():
     L.nb200_band_hist_bytes.argtypes = [C.POINTER(Analysis)]
     L.nb200_band_hist_bytes.restype = C.c_size_t
     L.nb200_band_finalize.argtypes = [C.POINTER(Analysis), C.POINTER(BandHist), c_dp]
+    L.nb200_band_chi2.argtypes = [C.c_int, C.c_int, c_dp, c_dp, C.c_int, c_dp]
+    L.nb200_band_leakage.argtypes = [C.POINTER(Analysis), C.POINTER(BandHist), c_dp, c_dp, c_dp, c_dp, c_dp]
     L.nb200_lar.argtypes = [vp, C.c_int, C.c_size_t, vp, vp, C.c_double, C.c_uint64, C.c_uint64, C.c_int,
                             vp, vp]
     L.nb200_debug_hitmath.argtypes = [vp, C.c_size_t, vp, vp]
@@ -181,6 +183,18 @@ def lib():
 
 def _dptr(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+def band_chi2(a, b, useS2=0, free_param=2):
+    """rootNEST's band goodness of fit (examples/rootNEST.cpp:600-643): a simulated, b compared against"""
+    a = np.ascontiguousarray(a, np.float64)
+    b = np.ascontiguousarray(b, np.float64)
+    out = np.zeros(6)
+    rc = lib().nb200_band_chi2(a.shape[0], useS2, a.ctypes.data_as(c_dp), b.ctypes.data_as(c_dp), free_param,
+                               out.ctypes.data_as(c_dp))
+    if rc:
+        raise NestB200Error(rc, "nb200_band_chi2: binning does not match")
+    return out
 
 
 class Band:
@@ -207,6 +221,17 @@ class Band:
         if rc:
             raise NestB200Error(rc, "nb200_band_finalize")
         return out
+
+    def leakage(self, centroid):
+        """fraction of events below `centroid[numBins]` per S1 bin, Poisson error bars, totals (rootNEST.cpp:880-915)"""
+        nb = self.ana.numBins
+        cen = np.ascontiguousarray(centroid, np.float64)
+        leak, hi, lo, tot = np.zeros(nb), np.zeros(nb), np.zeros(nb), np.zeros(3)
+        dp = lambda a: a.ctypes.data_as(c_dp)
+        rc = lib().nb200_band_leakage(C.byref(self.ana), C.byref(self.c), dp(cen), dp(leak), dp(hi), dp(lo), dp(tot))
+        if rc:
+            raise NestB200Error(rc, "nb200_band_leakage")
+        return leak, hi, lo, tot
 
     def words(self):
         """all integer words, for exact comparisons"""

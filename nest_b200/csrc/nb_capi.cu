@@ -1111,6 +1111,78 @@ int nb200_band_finalize(const nb200_analysis* ana, const nb200_band_hist* h, dou
   return 0;
 }
 
+// ---- band post-processing on the host (no device needed) ----------------------------------
+// examples/rootNEST.cpp:600-643: goodness of fit between two bands
+int nb200_band_chi2(int numBins, int useS2, const double* a, const double* b, int free_param, double* out) {
+  if (!a || !b || !out || numBins < 1) return NB200_EINVAL;
+  double chi2[4] = {0., 0., 0., 0.};
+  const int DoF = numBins - std::abs(free_param);
+  for (int i = 0; i < numBins; ++i) {
+    const double* x = a + 7 * size_t(i);  // NEST ("band")
+    const double* y = b + 7 * size_t(i);  // data ("band2")
+    if (std::fabs(x[0] - y[0]) > 0.05) return NB200_EINVAL;  // "Binning doesn't match for GoF calculation"
+    if (!(std::isfinite(x[2]) && std::isfinite(y[2]) && std::isfinite(x[3]) && std::isfinite(y[3]) && x[4] > 0. && y[4] > 0.))
+      continue;  // empty bin on either side
+    if ((useS2 == 0 && std::fabs(x[2]) < 5.) || useS2 != 0) {
+      double error = std::sqrt(x[4] * x[4] + y[4] * y[4]);
+      chi2[0] += (y[2] - x[2]) / error * ((y[2] - x[2]) / error);
+      error = std::sqrt(0.5 * (x[4] * x[4] + y[4] * y[4]));  // sigma/sqrt(2N) on each side
+      chi2[1] += (y[3] - x[3]) / error * ((y[3] - x[3]) / error);
+      chi2[2] += 100. * (y[2] - x[2]) / y[2];
+      chi2[3] += 100. * (y[3] - x[3]) / y[3];
+    }
+  }
+  chi2[0] /= double(DoF - 1);
+  chi2[1] /= double(DoF - 1);
+  chi2[2] /= double(numBins);
+  chi2[3] /= double(numBins);
+  out[0] = chi2[0];
+  out[1] = chi2[1];
+  out[2] = 0.5 * (chi2[0] + chi2[1]);
+  out[3] = std::sqrt(chi2[0] * chi2[1]);
+  out[4] = -chi2[2];
+  out[5] = -chi2[3];
+  return 0;
+}
+
+// examples/rootNEST.cpp:880-915 (counting, per-bin centroid): leakage of the accumulator's events below a centroid
+int nb200_band_leakage(const nb200_analysis* ana, const nb200_band_hist* h, const double* centroid, double* leak,
+                       double* err_hi, double* err_lo, double* total) {
+  if (!ana || !h || !centroid || !leak || !h->accepted || !h->hist2d || h->logBins < 1) return NB200_EINVAL;
+  const int nb = h->numBins, lb = h->logBins;
+  const double w = (ana->logMax - ana->logMin) / double(lb);
+  double sum_below = 0., sum_all = 0.;
+  for (int i = 0; i < nb; ++i) {
+    const uint64_t* row = h->hist2d + size_t(i) * lb;
+    double in_hist = 0., below = 0.;
+    const double pos = (centroid[i] - ana->logMin) / w;  // in units of log bins
+    for (int j = 0; j < lb; ++j) {
+      const double c = double(row[j]);
+      in_hist += c;
+      if (double(j + 1) <= pos)
+        below += c;
+      else if (double(j) < pos)
+        below += c * (pos - double(j));  // the bin holding the centroid, split linearly
+    }
+    const double N = double(h->accepted[i]);
+    // events whose y fell outside (logMin, logMax) entered the reference's vectors as 0 (execNEST.cpp:1551-1555)
+    if (centroid[i] > 0.) below += N - in_hist;
+    leak[i] = below / N;
+    if (err_hi) err_hi[i] = (below + std::sqrt(below)) / (N - std::sqrt(N)) - leak[i];
+    if (err_lo) err_lo[i] = leak[i] - (below - std::sqrt(below)) / (N + std::sqrt(N));
+    if (N > 0.) {
+      sum_below += below;
+      sum_all += N;
+    }
+  }
+  if (total) {
+    total[0] = sum_below;
+    total[1] = sum_all;
+    total[2] = sum_below / sum_all;
+  }
+  return 0;
+}
+
 // ---- FP64 pipe peak ---------------------------------------------------------------------
 }  // extern "C"
 namespace {

@@ -1,0 +1,165 @@
+"""Band post-processing on the host (nb200_band_chi2, nb200_band_leakage) without a GPU: the two
+uses rootNEST makes of a band that need no ROOT fit, checked against numpy restatements of
+reference examples/rootNEST.cpp:600-643 (goodness of fit) and :880-915 (leakage by counting)."""
+import numpy as np
+import pytest
+
+from nest_b200 import capi, shard
+
+
+def synthetic_signals(seed, n, mu0, slope, sigma):
+    """(S1, S2) pairs whose log10(S2/S1) is N(mu0 + slope*S1, sigma) -- a band-shaped cloud"""
+    rng = np.random.default_rng(seed)
+    s1 = rng.uniform(1.5, 60.0, n)
+    y = rng.normal(mu0 + slope * s1, sigma)
+    return s1, s1 * 10.0 ** y
+
+
+def band_of(ana, s1, s2):
+    return shard.band_from_words(ana, shard.band_words_from_signals(ana, 2, s1, s2))
+
+
+def chi2_restated(band, band2, useS2, free_param):
+    """examples/rootNEST.cpp:619-643 with the error columns this library's bands carry:
+    [4] = sigma/sqrt(N) for the mean, [4]/sqrt(2) for the width"""
+    nb = len(band)
+    chi = np.zeros(4)
+    for i in range(nb):
+        if not (band[i][4] > 0 and band2[i][4] > 0):
+            continue
+        if (useS2 == 0 and abs(band[i][2]) < 5.) or useS2 != 0:
+            err = np.sqrt(band[i][4] ** 2 + band2[i][4] ** 2)
+            chi[0] += ((band2[i][2] - band[i][2]) / err) ** 2
+            err = np.sqrt(band[i][4] ** 2 / 2 + band2[i][4] ** 2 / 2)
+            chi[1] += ((band2[i][3] - band[i][3]) / err) ** 2
+            chi[2] += 100. * (band2[i][2] - band[i][2]) / band2[i][2]
+            chi[3] += 100. * (band2[i][3] - band[i][3]) / band2[i][3]
+    dof = nb - abs(free_param)
+    chi[0] /= dof - 1
+    chi[1] /= dof - 1
+    chi[2] /= nb
+    chi[3] /= nb
+    return np.array([chi[0], chi[1], 0.5 * (chi[0] + chi[1]), np.sqrt(chi[0] * chi[1]), -chi[2], -chi[3]])
+
+
+def test_band_chi2_follows_rootnest(built):
+    ana = capi.analysis(0)
+    a = band_of(ana, *synthetic_signals(1, 200000, 2.6, -0.006, 0.11)).finalize()
+    b = band_of(ana, *synthetic_signals(2, 150000, 2.6, -0.006, 0.11)).finalize()
+    c = band_of(ana, *synthetic_signals(3, 150000, 2.63, -0.006, 0.13)).finalize()
+    # bins above S1 = 60 are empty on both sides (N = 0: NaN statistics) and must be skipped, not propagated
+    assert np.isnan(a[-1, 2]) and np.isfinite(a[10, 2])
+    for other in (b, c):
+        got = capi.band_chi2(a, other, useS2=0, free_param=2)
+        np.testing.assert_allclose(got, chi2_restated(a, other, 0, 2), rtol=1e-12, atol=0)
+    same = capi.band_chi2(a, b)
+    diff = capi.band_chi2(a, c)
+    assert same[0] < 2.0 and same[1] < 2.0, same        # two samples of one band agree
+    assert diff[0] > 20.0 and diff[1] > 20.0, diff      # a shifted, wider band does not
+    assert diff[4] < 0 and diff[5] < 0                  # a - b < 0 in both mean and width
+    # the reference's own argument order: band2 is the one compared against
+    swapped = capi.band_chi2(c, a)
+    assert swapped[0] == pytest.approx(diff[0], rel=1e-12) and swapped[4] > 0
+    # free parameters only change the divisor
+    fp5 = capi.band_chi2(a, c, free_param=-5)
+    assert fp5[0] == pytest.approx(diff[0] * (ana.numBins - 3) / (ana.numBins - 6), rel=1e-12)
+
+
+def test_band_chi2_outlier_and_binning_rules(built):
+    ana = capi.analysis(0)
+    a = band_of(ana, *synthetic_signals(4, 50000, 2.6, -0.006, 0.11)).finalize()
+    b = band_of(ana, *synthetic_signals(5, 50000, 2.6, -0.006, 0.11)).finalize()
+    base = capi.band_chi2(a, b)
+    # useS2 == 0 ignores bins whose simulated mean is >= 5 in magnitude (rootNEST.cpp:629); other modes do not
+    a2 = a.copy()
+    a2[7, 2] = 6.0
+    assert capi.band_chi2(a2, b, useS2=0)[0] < base[0] + 1e-9
+    assert capi.band_chi2(a2, b, useS2=1)[0] > 100.0
+    # bin centres further apart than 0.05: the reference's "Binning doesn't match for GoF calculation", return 1
+    b2 = b.copy()
+    b2[:, 0] += 0.06
+    with pytest.raises(capi.NestB200Error) as e:
+        capi.band_chi2(a, b2)
+    assert e.value.code == capi.EINVAL
+    b2[:, 0] = b[:, 0] + 0.04
+    assert capi.band_chi2(a, b2)[0] == pytest.approx(base[0], rel=1e-12)
+
+
+def leakage_restated(ana, s1, s2, centroid):
+    """examples/rootNEST.cpp:880-915 with NRbandCenter = 1: per S1 bin, the events GetBand kept
+    (execNEST.cpp:1540-1570; out-of-range y enter as 0) counted below that bin's centroid"""
+    nb = ana.numBins
+    w = (ana.maxS1 - ana.minS1) / nb
+    below, size = np.zeros(nb), np.zeros(nb)
+    for i in range(nb):
+        lo = ana.minS1 + i * w
+        m = (s1 > lo) & (s1 <= lo + w) & (s2 >= 0)
+        y = np.log10(s2[m] / s1[m])
+        y = np.where((y > ana.logMin) & (y < ana.logMax), y, 0.0)
+        below[i] = (y < centroid[i]).sum()
+        size[i] = m.sum()
+    return below, size
+
+
+def test_band_leakage_counts_like_rootnest(built):
+    ana = capi.analysis(0)
+    assert ana.logBins == 30
+    ana.logBins = 300                                    # 0.01 in log10(S2/S1): the caller chooses the resolution
+    res = (ana.logMax - ana.logMin) / ana.logBins
+    er1, er2 = synthetic_signals(6, 400000, 2.6, -0.006, 0.11)
+    nr1, nr2 = synthetic_signals(7, 100000, 2.25, -0.002, 0.12)
+    er, nr = band_of(ana, er1, er2), band_of(ana, nr1, nr2)
+    centroid = nr.finalize()[:, 2]                      # the NR band's mean per S1 bin
+    filled = er.accepted > 0
+    cen = np.where(np.isfinite(centroid), centroid, 0.0)
+    leak, hi, lo, tot = er.leakage(cen)
+    below, size = leakage_restated(ana, er1, er2, cen)
+    np.testing.assert_array_equal(size, er.accepted.astype(float))
+    N = size[filled]
+    # the histogram resolves the centroid to one log bin: the count may differ by the content of the bin that
+    # holds it, never by more
+    rows = er.hist2d.reshape(ana.numBins, ana.logBins).astype(float)
+    jc = np.clip(((cen - ana.logMin) / res).astype(int), 0, ana.logBins - 1)
+    slack = rows[np.arange(ana.numBins), jc]
+    assert np.all(np.abs(leak[filled] * N - below[filled]) <= slack[filled] + 1e-9)
+    assert np.abs(leak[filled] * N - below[filled]).max() > 0 or slack[filled].max() == 0
+    # overall: some 10^-3 of this ER cloud leaks, and the histogram estimate agrees within a few per cent
+    assert tot[1] == size.sum() and tot[0] == pytest.approx((leak[filled] * N).sum(), rel=1e-12)
+    assert tot[2] == pytest.approx(below.sum() / size.sum(), rel=0.08)
+    assert 1e-4 < tot[2] < 0.05
+    # Poisson error bars exactly as rootNEST.cpp:898-903
+    k = leak[filled] * N
+    np.testing.assert_allclose(hi[filled], (k + np.sqrt(k)) / (N - np.sqrt(N)) - leak[filled], rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(lo[filled], leak[filled] - (k - np.sqrt(k)) / (N + np.sqrt(N)), rtol=1e-12, atol=1e-15)
+
+
+def test_band_leakage_edges(built):
+    ana = capi.analysis(0)
+    s1, s2 = synthetic_signals(8, 50000, 2.6, -0.006, 0.11)
+    # a tenth of the events far outside (logMin, logMax): GetBand pushes y = 0 for them (execNEST.cpp:1551-1555)
+    s2[::10] = s1[::10] * 10.0 ** 4.5
+    b = band_of(ana, s1, s2)
+    nb = ana.numBins
+    filled = b.accepted > 0
+    N = b.accepted[filled].astype(float)
+    in_hist = b.hist2d.reshape(nb, ana.logBins).sum(axis=1)[filled].astype(float)
+    assert np.all(in_hist < N)
+    # a centroid above everything: all events are below it, the y = 0 ones included
+    leak, _, _, tot = b.leakage(np.full(nb, ana.logMax))
+    np.testing.assert_allclose(leak[filled], 1.0, rtol=1e-12)
+    assert tot[0] == tot[1] == N.sum()
+    # a centroid of 0: nothing inside the histogram is below it, and y = 0 is not below 0 (`<`, rootNEST.cpp:893)
+    leak, _, _, tot = b.leakage(np.zeros(nb))
+    assert np.all(leak[filled] == 0.0) and tot[0] == 0.0
+    # a centroid at the lower edge of the log axis (0.6 > 0): only the y = 0 events are below it
+    leak, _, _, _ = b.leakage(np.full(nb, ana.logMin))
+    np.testing.assert_allclose(leak[filled] * N, N - in_hist, rtol=0, atol=1e-3)
+    # the centroid inside a log bin splits that bin linearly: monotone in the centroid
+    c = np.linspace(2.0, 2.8, 33)
+    tots = [b.leakage(np.full(nb, x))[3][2] for x in c]
+    assert np.all(np.diff(tots) >= 0) and tots[0] < 0.2 < 0.8 < tots[-1]
+    # bad arguments
+    no_hist = capi.Band(ana)
+    no_hist.c.logBins = 0
+    with pytest.raises(capi.NestB200Error):
+        no_hist.leakage(np.zeros(nb))
