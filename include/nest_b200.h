@@ -326,6 +326,21 @@ int nb200_band_chi2(int numBins, int useS2, const double* a, const double* b, in
 int nb200_band_leakage(const nb200_analysis* ana, const nb200_band_hist* hist, const double* centroid,
                        double* leak, double* err_hi, double* err_lo, double* total);
 
+/* nb200_band_fit_gauss -- GetBand_Gaussian without ROOT (examples/rootNEST.cpp:1309-1359, skewness == 0): a
+ * Gaussian A exp(-(y - mean)^2 / (2 sigma^2)) fitted to each S1 bin's row of the 2-D histogram as TH1::Fit
+ * does by default (function at the bin centres, weights 1/content, empty bins left out; Levenberg-Marquardt,
+ * errors from the inverse of J^T W J).  fit[numBins][8] = {A, mean, sigma, mean error, sigma error, chi^2 per
+ * degree of freedom of that fit, the reference's own goodness figure band[j][8] (:1346-1357, in its indexing:
+ * ROOT bin k with k = 0 the underflow, model at logMin + k w), points used}; a row of zeros where fewer than
+ * four log bins are filled.  Needs logBins >= 4; the resolution is the caller's choice of logBins.
+ *
+ * nb200_band_leakage_gauss -- the "Leak Frac Fit" columns of rootNEST's leakage table (:700-738, :848, :908-914):
+ * er, nr = [numBins][8] as nb200_band_fit_gauss writes them, num_sig_above = NUMSIGABV (:39; 0 in the reference).
+ * out[numBins][4] = {number of ER sigmas between the two means, leakage (1 - erf(n/sqrt 2))/2, + error bar,
+ * - error bar}; discrimination = 1 - leakage. */
+int nb200_band_fit_gauss(const nb200_analysis* ana, const nb200_band_hist* hist, double* fit);
+int nb200_band_leakage_gauss(int numBins, const double* er, const double* nr, double num_sig_above, double* out);
+
 /* LAr: replaces LArNEST::FullCalculation (src/LArNEST.cpp:17-33) for species
  * NR=0, ER=1, Alpha=2 (LArParameters.hh:27-34).  yields [9][n] in the field order
  * of LArYieldResult (LArNEST.hh:19-29), fluct [4][n] LArYieldFluctuationResult

@@ -103,7 +103,7 @@ EXPORTS = [
     "nb200_synchronize", "nb200_detector_builtin", "nb200_model_default", "nb200_analysis_default",
     "nb200_prepare", "nb200_wimp_prep", "nb200_poisson", "nb200_yields", "nb200_run", "nb200_run_async",
     "nb200_band_reset", "nb200_band_attach", "nb200_fp64_peak", "nb200_timing_enable", "nb200_timing_read", "nb200_se_stats", "nb200_band_fetch", "nb200_band_device_buffer", "nb200_allreduce_hist",
-    "nb200_band_hist_bytes", "nb200_band_finalize", "nb200_band_chi2", "nb200_band_leakage", "nb200_lar", "nb200_launch_count",
+    "nb200_band_hist_bytes", "nb200_band_finalize", "nb200_band_chi2", "nb200_band_leakage", "nb200_band_fit_gauss", "nb200_band_leakage_gauss", "nb200_lar", "nb200_launch_count",
     "nb200_debug_hitmath", "nb200_debug_binomial", "nb200_debug_normal", "nb200_debug_binomial_fixed",
     "nb200_debug_zig_tables", "nb200_debug_alias_tables"]
 
@@ -167,6 +167,8 @@ def lib():
     L.nb200_band_finalize.argtypes = [C.POINTER(Analysis), C.POINTER(BandHist), c_dp]
     L.nb200_band_chi2.argtypes = [C.c_int, C.c_int, c_dp, c_dp, C.c_int, c_dp]
     L.nb200_band_leakage.argtypes = [C.POINTER(Analysis), C.POINTER(BandHist), c_dp, c_dp, c_dp, c_dp, c_dp]
+    L.nb200_band_fit_gauss.argtypes = [C.POINTER(Analysis), C.POINTER(BandHist), c_dp]
+    L.nb200_band_leakage_gauss.argtypes = [C.c_int, c_dp, c_dp, C.c_double, c_dp]
     L.nb200_lar.argtypes = [vp, C.c_int, C.c_size_t, vp, vp, C.c_double, C.c_uint64, C.c_uint64, C.c_int,
                             vp, vp]
     L.nb200_debug_hitmath.argtypes = [vp, C.c_size_t, vp, vp]
@@ -194,6 +196,20 @@ def band_chi2(a, b, useS2=0, free_param=2):
                                out.ctypes.data_as(c_dp))
     if rc:
         raise NestB200Error(rc, "nb200_band_chi2: binning does not match")
+    return out
+
+
+def band_leakage_gauss(er_fit, nr_fit, num_sig_above=0.0):
+    """rootNEST's Gaussian leakage columns (examples/rootNEST.cpp:700-738): rows {numSigma, leak, +err, -err}"""
+    e = np.ascontiguousarray(er_fit, np.float64)
+    r = np.ascontiguousarray(nr_fit, np.float64)
+    if e.shape != r.shape or e.ndim != 2 or e.shape[1] != 8:
+        raise ValueError("fits must be [numBins][8] as Band.fit_gauss returns them")
+    out = np.zeros((e.shape[0], 4))
+    rc = lib().nb200_band_leakage_gauss(e.shape[0], e.ctypes.data_as(c_dp), r.ctypes.data_as(c_dp), num_sig_above,
+                                        out.ctypes.data_as(c_dp))
+    if rc:
+        raise NestB200Error(rc, "nb200_band_leakage_gauss")
     return out
 
 
@@ -232,6 +248,15 @@ class Band:
         if rc:
             raise NestB200Error(rc, "nb200_band_leakage")
         return leak, hi, lo, tot
+
+    def fit_gauss(self):
+        """Gaussian fit per S1 bin (rootNEST.cpp:1309-1359): rows {A, mean, sigma, mean err, sigma err, chi2/ndf,
+        the reference's band[j][8], points}"""
+        out = np.zeros((self.ana.numBins, 8))
+        rc = lib().nb200_band_fit_gauss(C.byref(self.ana), C.byref(self.c), out.ctypes.data_as(c_dp))
+        if rc:
+            raise NestB200Error(rc, "nb200_band_fit_gauss")
+        return out
 
     def words(self):
         """all integer words, for exact comparisons"""

@@ -1183,6 +1183,161 @@ int nb200_band_leakage(const nb200_analysis* ana, const nb200_band_hist* h, cons
   return 0;
 }
 
+}  // extern "C"
+namespace {
+// Weighted least squares of f(x) = A exp(-(x - mu)^2 / (2 s^2)) to one row of the 2-D histogram: function taken
+// at the bin centres, weights 1/content, empty bins left out -- what ROOT's TH1::Fit minimises by default and
+// so what examples/rootNEST.cpp:1336-1338 asks for.  Levenberg-Marquardt with the analytic Jacobian; the
+// parameter errors are the square roots of the diagonal of (J^T W J)^-1 at the minimum (MIGRAD's parabolic
+// errors for a chi^2).  Returns the number of points used, or 0 when there are fewer than four or no minimum.
+bool solve3(const double M[3][3], const double v[3], double x[3]) {
+  double a[3][4];
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) a[i][j] = M[i][j];
+    a[i][3] = v[i];
+  }
+  for (int c = 0; c < 3; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < 3; ++r)
+      if (std::fabs(a[r][c]) > std::fabs(a[piv][c])) piv = r;
+    if (!(std::fabs(a[piv][c]) > 0.)) return false;
+    for (int j = 0; j < 4; ++j) std::swap(a[c][j], a[piv][j]);
+    for (int r = 0; r < 3; ++r) {
+      if (r == c) continue;
+      const double f = a[r][c] / a[c][c];
+      for (int j = c; j < 4; ++j) a[r][j] -= f * a[c][j];
+    }
+  }
+  for (int i = 0; i < 3; ++i) x[i] = a[i][3] / a[i][i];
+  return true;
+}
+
+double gauss_chi2(const uint64_t* row, int lb, double x0, double w, const double p[3], double JtJ[3][3], double Jtr[3]) {
+  double chi = 0.;
+  if (JtJ)
+    for (int i = 0; i < 3; ++i) {
+      Jtr[i] = 0.;
+      for (int j = 0; j < 3; ++j) JtJ[i][j] = 0.;
+    }
+  for (int k = 0; k < lb; ++k) {
+    if (!row[k]) continue;
+    const double h = double(row[k]), x = x0 + (double(k) + 0.5) * w, d = (x - p[1]) / p[2];
+    const double e = std::exp(-0.5 * d * d), f = p[0] * e, r = h - f;
+    chi += r * r / h;
+    if (JtJ) {
+      const double g[3] = {e, f * d / p[2], f * d * d / p[2]};
+      for (int i = 0; i < 3; ++i) {
+        Jtr[i] += g[i] * r / h;
+        for (int j = 0; j < 3; ++j) JtJ[i][j] += g[i] * g[j] / h;
+      }
+    }
+  }
+  return chi;
+}
+
+int fit_gauss_row(const uint64_t* row, int lb, double x0, double w, double p[3], double err[3], double* chi2) {
+  int used = 0;
+  for (int k = 0; k < lb; ++k) used += row[k] != 0;
+  if (used < 4 || !(p[2] > 0.) || !(p[0] > 0.)) return 0;
+  double JtJ[3][3], Jtr[3], lambda = 1e-3;
+  double chi = gauss_chi2(row, lb, x0, w, p, JtJ, Jtr);
+  for (int it = 0; it < 200; ++it) {
+    double M[3][3], step[3], q[3];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) M[i][j] = JtJ[i][j] * (i == j ? 1. + lambda : 1.);
+    if (!solve3(M, Jtr, step)) return 0;
+    for (int i = 0; i < 3; ++i) q[i] = p[i] + step[i];
+    const double trial = (q[2] > 0. && q[0] > 0.) ? gauss_chi2(row, lb, x0, w, q, nullptr, nullptr) : INFINITY;
+    if (trial <= chi) {
+      const bool done = chi - trial <= 1e-13 * chi && std::fabs(step[1]) <= 1e-10 * p[2] && std::fabs(step[2]) <= 1e-10 * p[2];
+      for (int i = 0; i < 3; ++i) p[i] = q[i];
+      chi = gauss_chi2(row, lb, x0, w, p, JtJ, Jtr);
+      lambda = lambda > 1e-12 ? lambda * 0.1 : lambda;
+      if (done) break;
+    } else {
+      lambda *= 10.;
+      if (lambda > 1e12) break;  // no downhill step left: p is the minimum to rounding
+    }
+  }
+  // covariance = (J^T W J)^-1, column by column
+  for (int i = 0; i < 3; ++i) {
+    double unit[3] = {0., 0., 0.}, col[3];
+    unit[i] = 1.;
+    if (!solve3(JtJ, unit, col) || !(col[i] > 0.)) return 0;
+    err[i] = std::sqrt(col[i]);
+  }
+  *chi2 = chi;
+  return used;
+}
+}  // namespace
+extern "C" {
+
+// examples/rootNEST.cpp:1309-1359 (GetBand_Gaussian, skewness == 0): Gaussian fit of every S1 bin's histogram
+int nb200_band_fit_gauss(const nb200_analysis* ana, const nb200_band_hist* h, double* fit) {
+  if (!ana || !h || !fit || !h->accepted || !h->sumY || !h->sumY2 || !h->hist2d || h->logBins < 4) return NB200_EINVAL;
+  const int nb = h->numBins, lb = h->logBins;
+  const double w = (ana->logMax - ana->logMin) / double(lb);
+  for (int j = 0; j < nb; ++j) {
+    double* o = fit + 8 * size_t(j);
+    const uint64_t* row = h->hist2d + size_t(j) * lb;
+    for (int i = 0; i < 8; ++i) o[i] = 0.;
+    // start values from the histogram's own moments (the y = 0 entries are outside the axis: ROOT's underflow)
+    double n = 0., sx = 0., sxx = 0.;
+    for (int k = 0; k < lb; ++k) {
+      const double c = double(row[k]), x = ana->logMin + (double(k) + 0.5) * w;
+      n += c;
+      sx += c * x;
+      sxx += c * x * x;
+    }
+    if (!(n > 1.)) continue;
+    const double mu = sx / n;
+    const double var = sxx / n - mu * mu + w * w / 12.;
+    double p[3] = {n * w / std::sqrt(2. * M_PI * var), mu, std::sqrt(var)}, err[3] = {0., 0., 0.}, chi = 0.;
+    const int used = fit_gauss_row(row, lb, ana->logMin, w, p, err, &chi);
+    if (!used) continue;
+    o[0] = p[0];
+    o[1] = p[1];
+    o[2] = p[2];
+    o[3] = err[1];
+    o[4] = err[2];
+    o[5] = used > 3 ? chi / double(used - 3) : 0.;
+    // the reference's own goodness figure (:1346-1357) in its own indexing: TH1F::operator[](k) is ROOT bin k
+    // (k = 0 the underflow, which holds the events pushed as y = 0), the model taken at logMin + k w
+    double g = 0.;
+    for (int k = 0; k < lb; ++k) {
+      const double x = ana->logMin + double(k) * w;
+      const double model = p[0] * std::exp(-0.5 * (x - p[1]) * (x - p[1]) / (p[2] * p[2]));
+      const double content = k == 0 ? double(h->accepted[j]) - n : double(row[k - 1]);
+      const double denom = std::max(float(model + content), 1.f);
+      g += (content - model) * (content - model) / denom;
+    }
+    g /= double(lb) - 3. - 1.;
+    o[6] = (std::isnan(g) || g < 0. || g >= DBL_MAX) ? 0. : g;
+    o[7] = double(used);
+  }
+  return 0;
+}
+
+// examples/rootNEST.cpp:700-738, 848 (skewness == 0): leakage from the Gaussian picture of the two bands
+int nb200_band_leakage_gauss(int numBins, const double* er, const double* nr, double num_sig_above, double* out) {
+  if (!er || !nr || !out || numBins < 1) return NB200_EINVAL;
+  for (int i = 0; i < numBins; ++i) {
+    const double* e = er + 8 * size_t(i);
+    const double* r = nr + 8 * size_t(i);
+    double* o = out + 4 * size_t(i);
+    const double line = r[1] + num_sig_above * r[2];  // NUMSIGABV (:39, :718)
+    const double numSigma = (e[1] - line) / e[2];
+    const double up = (e[1] - e[3] - line - r[3]) / (e[2] + e[4]);  // more leakage
+    const double dn = (e[1] + e[3] - line + r[3]) / (e[2] - e[4]);  // less leakage
+    const double leak = (1. - std::erf(numSigma / std::sqrt(2.))) / 2.;
+    o[0] = numSigma;
+    o[1] = leak;
+    o[2] = std::fabs((1. - std::erf(up / std::sqrt(2.))) / 2. - leak);
+    o[3] = std::fabs(leak - (1. - std::erf(dn / std::sqrt(2.))) / 2.);
+  }
+  return 0;
+}
+
 // ---- FP64 pipe peak ---------------------------------------------------------------------
 }  // extern "C"
 namespace {

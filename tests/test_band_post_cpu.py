@@ -163,3 +163,81 @@ def test_band_leakage_edges(built):
     no_hist.c.logBins = 0
     with pytest.raises(capi.NestB200Error):
         no_hist.leakage(np.zeros(nb))
+
+
+def test_band_gaussian_fit_matches_least_squares(built):
+    """nb200_band_fit_gauss against scipy's Levenberg-Marquardt on the same histogram rows with the same
+    weights (1/content, empty bins left out, function at the bin centres -- TH1::Fit's default chi^2)"""
+    from scipy.optimize import curve_fit
+    ana = capi.analysis(0)
+    ana.logBins = 150
+    b = band_of(ana, *synthetic_signals(9, 600000, 2.6, -0.006, 0.11))
+    fit = b.fit_gauss()
+    mom = b.finalize()
+    nb, lb = ana.numBins, ana.logBins
+    w = (ana.logMax - ana.logMin) / lb
+    x = ana.logMin + (np.arange(lb) + 0.5) * w
+    rows = b.hist2d.reshape(nb, lb).astype(float)
+    f = lambda x, A, m, s: A * np.exp(-0.5 * ((x - m) / s) ** 2)
+    checked = 0
+    for j in range(nb):
+        if b.accepted[j] < 2000:
+            assert fit[j, 7] == 0 or fit[j, 2] > 0
+            continue
+        k = rows[j] > 0
+        popt, pcov = curve_fit(f, x[k], rows[j][k], p0=(rows[j].max(), mom[j, 2], mom[j, 3]), sigma=np.sqrt(rows[j][k]),
+                               absolute_sigma=True, xtol=1e-14, ftol=1e-14, gtol=1e-14)
+        np.testing.assert_allclose(fit[j, :3], popt, rtol=2e-6)
+        np.testing.assert_allclose(fit[j, 3:5], np.sqrt(np.diag(pcov))[1:], rtol=1e-4)
+        chi = (((rows[j][k] - f(x[k], *popt)) ** 2) / rows[j][k]).sum() / (k.sum() - 3)
+        assert fit[j, 5] == pytest.approx(chi, rel=1e-6) and fit[j, 7] == k.sum()
+        # the sample is Gaussian: fit and moments tell the same story, the fit is good, and the errors are the
+        # size of the moments' own
+        assert abs(fit[j, 1] - mom[j, 2]) < 5 * mom[j, 4] and abs(fit[j, 2] - mom[j, 3]) < 5 * mom[j, 4]
+        assert 0.2 < fit[j, 5] < 3.0
+        assert 0.5 * mom[j, 4] < fit[j, 3] < 2.0 * mom[j, 4]
+        # the reference's own figure (rootNEST.cpp:1346-1357), restated with its indexing
+        g = 0.0
+        for kk in range(lb):
+            model = fit[j, 0] * np.exp(-0.5 * (ana.logMin + kk * w - fit[j, 1]) ** 2 / fit[j, 2] ** 2)
+            content = float(b.accepted[j]) - rows[j].sum() if kk == 0 else rows[j][kk - 1]
+            g += (content - model) ** 2 / max(np.float32(model + content), np.float32(1.0))
+        assert fit[j, 6] == pytest.approx(g / (lb - 4.0), rel=1e-9)
+        checked += 1
+    assert checked > 40
+    # bins without entries: a row of zeros, no NaN anywhere
+    assert np.all(np.isfinite(fit)) and np.all(fit[b.accepted == 0] == 0)
+    # too coarse an axis is refused
+    coarse = capi.analysis(0)
+    coarse.logBins = 3
+    with pytest.raises(capi.NestB200Error):
+        band_of(coarse, *synthetic_signals(9, 1000, 2.6, -0.006, 0.11)).fit_gauss()
+
+
+def test_band_gaussian_leakage_follows_rootnest(built):
+    from scipy.special import erf
+    ana = capi.analysis(0)
+    ana.logBins = 150
+    er = band_of(ana, *synthetic_signals(10, 600000, 2.6, -0.006, 0.11)).fit_gauss()
+    nr = band_of(ana, *synthetic_signals(11, 300000, 2.25, -0.002, 0.12)).fit_gauss()
+    out = capi.band_leakage_gauss(er, nr)
+    ok = (er[:, 7] > 0) & (nr[:, 7] > 0)
+    assert ok.sum() > 40
+    e, r = er[ok], nr[ok]
+    # rootNEST.cpp:717-736 with band = ER (mean [2], sigma [3], errors [5], [6]) and band2 = NR
+    n_sig = (e[:, 1] - r[:, 1]) / e[:, 2]
+    up = (e[:, 1] - e[:, 3] - r[:, 1] - r[:, 3]) / (e[:, 2] + e[:, 4])
+    dn = (e[:, 1] + e[:, 3] - r[:, 1] + r[:, 3]) / (e[:, 2] - e[:, 4])
+    leak = (1 - erf(n_sig / np.sqrt(2))) / 2
+    np.testing.assert_allclose(out[ok, 0], n_sig, rtol=1e-13)
+    np.testing.assert_allclose(out[ok, 1], leak, rtol=1e-12)
+    np.testing.assert_allclose(out[ok, 2], np.abs((1 - erf(up / np.sqrt(2))) / 2 - leak), rtol=1e-9, atol=1e-18)
+    np.testing.assert_allclose(out[ok, 3], np.abs(leak - (1 - erf(dn / np.sqrt(2))) / 2), rtol=1e-9, atol=1e-18)
+    # the synthetic bands are (0.35 - 0.004 S1) / 0.11 sigmas apart: the Gaussian leakage says so
+    s1 = ana.minS1 + (np.arange(ana.numBins) + 0.5) * (ana.maxS1 - ana.minS1) / ana.numBins
+    np.testing.assert_allclose(out[ok, 0], ((0.35 - 0.004 * s1) / 0.11)[ok], atol=0.08)
+    # NUMSIGABV moves the NR line by that many NR sigmas
+    shifted = capi.band_leakage_gauss(er, nr, num_sig_above=-1.0)
+    np.testing.assert_allclose(shifted[ok, 0], (e[:, 1] - (r[:, 1] - r[:, 2])) / e[:, 2], rtol=1e-13)
+    with pytest.raises(ValueError):
+        capi.band_leakage_gauss(er[:, :7], nr[:, :7])
