@@ -348,7 +348,7 @@ int execNEST(VDetector* detector, double numEvts, const string& type, double eMi
                 "8B or Boron-8,\nDD or D-D,\nAmBe,\nCf or Cf252 or 252Cf or Cf-252,\nion or nucleus,\nalpha,\ngamma or "
                 "gammaRay,\nx-ray or xray or xRay or X-ray or Xray or XRay,\nKr83m or 83mKr or Kr83,\nCH3T or "
                 "tritium,\nCarbon14 or 14C or C14 or C-14 or Carbon-14,\nbeta or ER or Compton or compton or "
-                "electron or e-,\npp or ppsolar with many various underscore, hyphen and capitalization "
+                "electron or e-,\npp or ppSolar with many various underscore, hyphen and capitalization "
                 "permutations permitted,\natmNu\n";
       return 1;
     }
@@ -700,7 +700,11 @@ int nest_b200_cli::main_like(VDetector* detector, int argc, char** argv) {
     cout << "\t./execNEST numEvts type_interaction E_min[keV] E_max[keV] field_drift[V/cm] x,y,z-position[mm] "
             "{optional:seed}"
          << endl << endl;
-    cout << "For 8B, numEvts is kg-days of exposure with everything else same. For WIMPs:" << endl;
+    cout << "For Kr83m time-dependent 9.4, 32.1, or 41.5 keV yields: " << endl;
+    cout << "\t ./execNEST numEvents Kr83m Energy[keV] maxTimeDiff[ns] field_drift[V/cm] x,y,z-position[mm] "
+            "{optional:seed}"
+         << endl << endl;
+    cout << "For 8B or pp or atmNu, numEvts is kg-days of exposure with everything else same. For WIMPs:" << endl;
     cout << "\t./execNEST exposure[kg-days] {WIMP} m[GeV] x-sect[cm^2] field_drift[V/cm] x,y,z-position[mm] "
             "{optional:seed}"
          << endl << endl;
