@@ -1,0 +1,265 @@
+// rootNEST without ROOT, for the uses of examples/rootNEST.cpp that need no more than a Gaussian fit:
+//
+//   rootNEST_b200 NESTOutput.txt                 band of Gaussians (mode 0, one input; :1166-1195)
+//   rootNEST_b200 NESTOutputER.txt NESTOutputNR.txt   leakage / discrimination table (mode 0, two inputs;
+//                                                :668-950 -- examples/leakage.sh runs unchanged)
+//   NB200_MODE=1 rootNEST_b200 NESTOutput.txt dataBand.txt   goodness of fit against a data band (mode 1; :587-666)
+//
+// with the analysis.hh settings skewness = 0 (Gaussian fits) and NRbandCenter = 1 (the Gaussian mean of each
+// S1 bin is the NR centroid).  The reference's defaults -- skew-Gaussian fits and a Woods-function fit through
+// the NR means -- need ROOT's minimiser and are out of scope; modes 2 and 3 (WIMP limits)
+// likewise.  Inputs are execNEST's 12-column stdout (src/execNEST.cpp:1386-1405), read as GetFile does
+// (:955-1036); per-bin statistics, Gaussian fits and leakage come from the library's host-side band functions
+// (include/nest_b200.h: nb200_band_finalize, nb200_band_fit_gauss, nb200_band_leakage_gauss).  Nothing here
+// simulates anything: no device is needed or used.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <vector>
+
+#include "NEST_b200.hh"
+
+using namespace std;
+
+namespace {
+NEST::Analysis A;
+const int freeParam = 2;       // analysis.hh:65
+const double NUMSIGABV = -0.;  // rootNEST.cpp:39
+
+struct BandOfFile {
+  vector<vector<double>> inputs, outputs;  // per S1 bin: S1 values, y values (GetBand's two passes, :1141-1165)
+  vector<double> mom;                      // [numBins][7] nb200_band_finalize
+  vector<double> fit;                      // [numBins][8] nb200_band_fit_gauss
+  size_t events = 0;
+};
+
+// GetFile :955-1036: select S1 and S2 per usePD, flag what is outside (minS, maxS) as -999
+bool read_signals(const char* name, vector<double>& S1, vector<double>& S2) {
+  FILE* fp = fopen(name, "r");
+  if (!fp) {
+    cerr << "ERROR: cannot open " << name << endl;
+    return false;
+  }
+  char line[4096];
+  while (fgets(line, sizeof line, fp)) {
+    double a, b, c, d, e, f, g, h, i, j, k, l, m, n;
+    if (sscanf(line, "%lf\t%lf\t%lf\t%lf,%lf,%lf\t%lf\t%lf\t%lf\t%lf\t%lf\t%lf\t%lf\t%lf", &a, &b, &c, &d, &e, &f, &g, &h,
+               &i, &j, &k, &l, &m, &n) != 14)
+      continue;  // header, band table or summary lines
+    double s1 = -999., s2 = -999.;
+    if (A.usePD <= 0 && fabs(j * 1.2) > A.minS1 && (j * 1.2) < A.maxS1)
+      s1 = j * 1.2;
+    else if (A.usePD == 1 && fabs(j) > A.minS1 && j < A.maxS1)
+      s1 = j;
+    else if (A.usePD >= 2 && fabs(k) > A.minS1 && k < A.maxS1)
+      s1 = k;
+    if (A.usePD <= 0 && fabs(n * 1.2) > A.minS2 && (n * 1.2) < A.maxS2)
+      s2 = n * 1.2;
+    else if (A.usePD >= 1 && fabs(n) > A.minS2 && n < A.maxS2)
+      s2 = n;
+    S1.push_back(s1);
+    S2.push_back(s2);
+  }
+  fclose(fp);
+  return true;
+}
+
+// GetBand :1198-1306 into the library's integer accumulator (fixed-point scales of include/nest_b200.h) +
+// GetBand_Gaussian :1309-1359
+bool band_of_file(const char* name, BandOfFile& B) {
+  vector<double> S1, S2;
+  if (!read_signals(name, S1, S2)) return false;
+  B.events = S1.size();
+  const nb200_analysis ana = A.flat();
+  const int nb = ana.numBins, lb = ana.logBins;
+  double binWidth, border;
+  if (ana.useS2 == 2) {
+    binWidth = (ana.maxS2 - ana.minS2) / double(nb);
+    border = ana.minS2;
+  } else {
+    binWidth = (ana.maxS1 - ana.minS1) / double(nb);
+    border = ana.minS1;
+  }
+  vector<uint64_t> acc(nb, 0), rej(nb, 0), h2d(size_t(nb) * lb, 0);
+  vector<int64_t> sS1(nb, 0), sY(nb, 0), sY2(nb, 0), sY3(nb, 0);
+  B.inputs.assign(nb, {});
+  B.outputs.assign(nb, {});
+  for (size_t i = 0; i < S1.size(); ++i) {
+    if (S1[i] == 0. || S2[i] == 0.) ++rej[0];
+    for (int j = 0; j < nb; ++j) {
+      const double s1c = border + binWidth / 2. + double(j) * binWidth;
+      if (!(fabs(S1[i]) > (s1c - binWidth / 2.) && fabs(S1[i]) <= (s1c + binWidth / 2.))) continue;
+      if (S1[i] >= 0. && S2[i] >= 0.) {
+        double y = 0.;
+        if (S1[i] && S2[i]) y = ana.useS2 == 0 ? log10(S2[i] / S1[i]) : ana.useS2 == 1 ? log10(S2[i]) : log10(S1[i] / S2[i]);
+        B.inputs[j].push_back(S1[i]);
+        B.outputs[j].push_back(y);
+        ++acc[j];
+        sS1[j] += llrint(S1[i] * NB200_FX_S1);
+        sY[j] += llrint(y * NB200_FX_Y);
+        sY2[j] += llrint(y * y * NB200_FX_Y2);
+        sY3[j] += llrint(y * y * y * NB200_FX_Y3);
+        if (y > ana.logMin && y < ana.logMax) {  // TH1F::Fill: the rest is under- or overflow
+          int k = int((y - ana.logMin) / (ana.logMax - ana.logMin) * lb);
+          k = k < 0 ? 0 : k >= lb ? lb - 1 : k;
+          ++h2d[size_t(j) * lb + k];
+        }
+      } else
+        ++rej[j];
+      break;
+    }
+  }
+  nb200_band_hist H = {nb, lb, 0, acc.data(), rej.data(), sS1.data(), sY.data(), sY2.data(), sY3.data(), h2d.data()};
+  B.mom.assign(size_t(nb) * 7, 0.);
+  B.fit.assign(size_t(nb) * 8, 0.);
+  if (nb200_band_finalize(&ana, &H, B.mom.data()) || nb200_band_fit_gauss(&ana, &H, B.fit.data())) {
+    cerr << "ERROR: band statistics failed (numBins, logBins?)" << endl;
+    return false;
+  }
+  if (A.verbosity > 0) {  // :1180-1190
+    fprintf(stdout, "Bin Center\tBin Actual\tGaus Mean\tMean Error\tGaus Sigma\tSig Error\tGaus Skew\tSkew Error\tX^2/DOF\n");
+    for (int o = 0; o < nb; ++o) {
+      const double* m = &B.mom[7 * size_t(o)];
+      const double* f = &B.fit[8 * size_t(o)];
+      fprintf(stdout, "%lf\t%lf\t%lf\t%lf\t%lf\t%lf\t%lf\t%lf\t%lf\n", m[0], m[1], f[1], f[3], f[2], f[4], 0., 0., f[6]);
+    }
+  }
+  return true;
+}
+
+int goodness_of_fit(const char* simFile, const char* dataFile) {  // :587-666
+  const int nb = A.numBins;
+  vector<double> d(size_t(nb) * 6, 0.);
+  FILE* fp = fopen(dataFile, "r");
+  if (!fp) {
+    cerr << "ERROR: cannot open " << dataFile << endl;
+    return 1;
+  }
+  for (int i = 0; i < nb; ++i)  // centre, actual, mean, mean error, sigma, sigma error (:603-607)
+    if (fscanf(fp, "%lf %lf %lf %lf %lf %lf", &d[6 * i], &d[6 * i + 1], &d[6 * i + 2], &d[6 * i + 3], &d[6 * i + 4],
+               &d[6 * i + 5]) != 6)
+      break;
+  fclose(fp);
+  BandOfFile B;
+  if (!band_of_file(simFile, B)) return 1;
+  const int DoF = nb - abs(freeParam);
+  double chi2[4] = {0., 0., 0., 0.};
+  for (int i = 0; i < nb; ++i) {
+    const double* f = &B.fit[8 * size_t(i)];
+    const double* x = &d[6 * size_t(i)];
+    if (fabs(B.mom[7 * size_t(i)] - x[0]) > 0.05) {
+      if (A.verbosity > 0)
+        cerr << "Binning doesn't match for GoF calculation. Go to analysis.hh and adjust minS1, maxS1, numBins" << endl;
+      return 1;
+    }
+    if ((A.useS2 == 0 && fabs(f[1]) < 5.) || A.useS2 != 0) {
+      double error = sqrt(pow(f[3], 2.) + pow(x[3], 2.));
+      chi2[0] += pow((x[2] - f[1]) / error, 2.);
+      error = sqrt(pow(f[4], 2.) + pow(x[5], 2.));
+      chi2[1] += pow((x[4] - f[2]) / error, 2.);
+      chi2[2] += 100. * (x[2] - f[1]) / x[2];
+      chi2[3] += 100. * (x[4] - f[2]) / x[4];
+    } else if (A.verbosity > 0)
+      cerr << "Ignoring outliers for chi^2 calculation" << endl;
+  }
+  chi2[0] /= double(DoF - 1);
+  chi2[2] /= nb;
+  chi2[1] /= double(DoF - 1);
+  chi2[3] /= nb;
+  cout << "The reduced CHI^2 = " << chi2[0] << " for mean, and " << chi2[1] << " for width. ";
+  cout << "Arithmetic average= " << (chi2[0] + chi2[1]) / 2. << " and geo. mean " << sqrt(chi2[0] * chi2[1])
+       << " (mean+width and mean*width)" << endl;
+  cout << "%-errors of the form (1/N)*sum{(NEST-data)/data} for mean and width are " << -chi2[2] << " and " << -chi2[3]
+       << " (averages)" << endl;
+  return 0;
+}
+
+int leakage_table(const char* file1, const char* file2) {  // :668-950
+  const int nb = A.numBins;
+  BandOfFile B2, B;
+  cout << endl << "Calculating band for first dataset" << endl;
+  if (!band_of_file(file2, B2)) return 1;
+  cout << endl << "Calculating band for second dataset" << endl;
+  if (!band_of_file(file1, B)) return 1;
+  const bool ERis2nd = B2.fit[1] > B.fit[1];  // band2[0][2] > band[0][2]
+  if (ERis2nd)
+    fprintf(stderr, "\n#evts\tBinCen\tBin Actual\t#StdDev's\tLeak Frac Fit\t+ errBar\t- errBar\tDiscrim[%%]\tLower ''Half''\t+ "
+                    "errBar\t- errBar\tUpperHf[%%]\n");
+  else
+    fprintf(stderr, "\n#evts\tBinCen\tBin Actual\t#StdDev's\tLeak Frac Fit\t+ errBar\t- errBar\tDiscrim[%%]\tLeak Frac Raw\t+ "
+                    "errBar\t- errBar\tDiscrim[%%]\n");
+  // the Gaussian picture: ER band against the NR line (the library takes them in that order)
+  const vector<double>& er = ERis2nd ? B2.fit : B.fit;
+  const vector<double>& nr = ERis2nd ? B.fit : B2.fit;
+  vector<double> lk(size_t(nb) * 4, 0.);
+  if (nb200_band_leakage_gauss(nb, er.data(), nr.data(), NUMSIGABV, lk.data())) return 1;
+  double finalSums[3] = {0., 0., 0.};
+  for (int i = 0; i < nb; ++i) {
+    // counting (:880-915, NRbandCenter = 1): the second dataset's events below the NR line of this bin
+    const double centroid = nr[8 * size_t(i) + 1] + NUMSIGABV * nr[8 * size_t(i) + 2];
+    uint64_t below = 0;
+    for (double y : B.outputs[i]) below += y < centroid;
+    const double N = double(B.outputs[i].size());
+    const double leakTotal = double(below) / N;
+    const double poisHi = (double(below) + sqrt(double(below))) / (N - sqrt(N));
+    const double poisLo = (double(below) - sqrt(double(below))) / (N + sqrt(N));
+    const double* g = &lk[4 * size_t(i)];
+    cerr << B.outputs[i].size();
+    fprintf(stderr, "\t%.2f\t%f\t%f\t%e\t%e\t%e\t%f\t%e\t%e\t%e\t%f\t\n", 0.5 * (B.mom[7 * size_t(i)] + B2.mom[7 * size_t(i)]),
+            0.5 * (B.mom[7 * size_t(i) + 1] + B2.mom[7 * size_t(i) + 1]), g[0], g[1], g[2], g[3], (1. - g[1]) * 100., leakTotal,
+            poisHi - leakTotal, leakTotal - poisLo, (1. - leakTotal) * 100.);
+    finalSums[0] += double(below);
+    finalSums[1] += N;
+    finalSums[2] += g[1];
+  }
+  fprintf(stderr,
+          "\nOVERALL DISCRIMINATION (ER) or NON-ACCEPTANCE (NR) between min and maxS1 = %.12f%%, total: Gaussian & "
+          "non-Gaussian (tot=counting) Leakage Fraction = %.12e\n",
+          (1. - finalSums[0] / finalSums[1]) * 100., finalSums[0] / finalSums[1]);
+  const double LowValue = (finalSums[0] + sqrt(finalSums[0])) / (finalSums[1] - sqrt(finalSums[1]));
+  const double HighValue = (finalSums[0] - sqrt(finalSums[0])) / (finalSums[1] + sqrt(finalSums[1]));
+  fprintf(stderr, "highest possible discrimination value (plus  1-sigma) is %.12f%%, with corresponding leakage of %.12e\n",
+          (1. - HighValue) * 100., HighValue);
+  fprintf(stderr, " lowest possible discrimination value (minus 1-sigma) is %.12f%%, with corresponding leakage of %.12e\n",
+          (1. - LowValue) * 100., LowValue);
+  fprintf(stderr,
+          "OVERALL DISCRIMINATION                             between min and maxS1 = %.12f%%, Gauss, or skew-normal fits "
+          "(whatever you ran) Leakage Fraction = %.12e\n",
+          (1. - finalSums[2] / nb) * 100., finalSums[2] / nb);
+  return 0;
+}
+}  // namespace
+
+int main(int argc, char** argv) {
+  if (const char* a = getenv("NB200_ANALYSIS"))
+    if (!strcmp(a, "G2")) A = NEST::Analysis::G2();
+  if (const char* v = getenv("NB200_VERBOSITY")) A.verbosity = atoi(v);
+  if (const char* v = getenv("NB200_LOGBINS")) A.logBins = atoi(v);
+  const int mode = getenv("NB200_MODE") ? atoi(getenv("NB200_MODE")) : 0;
+  if (argc < 2) {  // :104-119
+    cout << endl << "This program takes 1 (or 2) inputs." << endl << endl;
+    cout << "One input means you are just doing a band of Gaussians." << endl << endl;
+    cout << "Two inputs means you're doing both ER and NR and calculating the leakage and discrimination." << endl;
+    cout << "If you write NR first, you're seeking characterization of the non-Gaussian asymmetry of the NR band." << endl;
+    cout << "If you write ER first, you're finding the non-Gaussian leakage of ER into the NR band." << endl << endl;
+    return 1;
+  }
+  if (mode == 1) {
+    if (argc < 3) {
+      if (A.verbosity > 0) cerr << "ERROR: mode 1 requires *2* input files. 1 is not enough" << endl;
+      return 1;
+    }
+    return goodness_of_fit(argv[1], argv[2]);
+  }
+  if (mode != 0) {
+    cerr << "ERROR: rootNEST mode " << mode << " (WIMP limits) is not part of nest-b200; use the reference rootNEST." << endl;
+    return 1;
+  }
+  if (argc == 2) {
+    BandOfFile B;
+    return band_of_file(argv[1], B) ? 0 : 1;
+  }
+  return leakage_table(argv[1], argv[2]);
+}

@@ -1,0 +1,192 @@
+"""rootNEST_b200 (nest_b200/host/rootNEST_main.cpp): rootNEST's band-of-Gaussians, leakage and goodness-of-fit
+modes without ROOT, on execNEST's 12-column stdout.  No GPU: the tool only post-processes text.  Checked
+against numpy restatements of reference examples/rootNEST.cpp (GetFile :955-1036, GetBand :1198-1306,
+leakage :668-950, GoF :587-666) on the same rows, and run on the unmodified reference binary's own output."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+from scipy.special import erf
+
+import refprobe
+from nest_b200 import capi, shard
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOOL = os.path.join(ROOT, "nest_b200", "host", "rootNEST_b200")
+
+
+@pytest.fixture(scope="module")
+def tool(built):
+    r = subprocess.run(["make", "-s", "-C", os.path.dirname(TOOL)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    return TOOL
+
+
+def run(tool, *args, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    r = subprocess.run([tool] + list(args), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=e, timeout=300)
+    return r.returncode, r.stdout, r.stderr
+
+
+def write_execnest_file(path, seed, n, mu0, slope, sigma):
+    """rows in execNEST's stdout layout (src/execNEST.cpp:1386-1405) under its two header lines; some rows carry the
+    reference's below-threshold flags (negative signals) and some lie outside the S1 / S2 windows"""
+    rng = np.random.default_rng(seed)
+    s1 = rng.uniform(0.5, 70.0, n)
+    s2 = s1 * 10.0 ** rng.normal(mu0 + slope * s1, sigma)
+    s1[::17] *= -1.0
+    s2[::23] *= -1.0
+    s1, s2 = np.round(s1, 6), np.round(s2, 6)       # what the 6-decimal text carries
+    with open(path, "w") as f:
+        f.write("E_truth [keV]\tfield [V/cm]\ttDrift [us]\tX,Y,Z [mm]\tNph\tNe-\tS1 [PE or phe]\tS1_3Dcor [phd]\t"
+                "spikeC(NON-INT)\tNe-Extr\tS2_rawArea [PE]\tS2_3Dcorr [phd]\n")
+        for a, b in zip(s1, s2):
+            f.write("%.6f\t%.6f\t%.6f\t%.0f, %.0f, %.0f\t%d\t%d\t%.6f\t%.6f\t%.6f\t%d\t%.6f\t%.6f\n" %
+                    (5.0, 180.0, 100.0, 10, -20, 250, 300, 200, a * 1.1, a * 0.97, a, 100, b * 0.8, b))
+    return s1, s2
+
+
+def windowed(ana, s1, s2):
+    """GetFile's flags (:996-1025, usePD = 2): outside (minS, maxS) -> -999"""
+    a = np.where((np.abs(s1) > ana.minS1) & (s1 < ana.maxS1), s1, -999.0)
+    b = np.where((np.abs(s2) > ana.minS2) & (s2 < ana.maxS2), s2, -999.0)
+    return a, b
+
+
+def table(out, after=None):
+    lines = out.splitlines()
+    if after is not None:
+        lines = lines[lines.index(after):]
+    k = next(i for i, ln in enumerate(lines) if ln.startswith("Bin Center\tBin Actual\tGaus Mean"))
+    rows = []
+    for ln in lines[k + 1:]:
+        f = ln.split("\t")
+        if len(f) != 9:
+            break
+        rows.append([float(v) for v in f])
+    return np.array(rows)
+
+
+def test_band_of_gaussians(tool, tmp_path):
+    ana = capi.analysis(0)
+    s1, s2 = write_execnest_file(tmp_path / "er.txt", 1, 120000, 2.6, -0.006, 0.11)
+    rc, out, err = run(tool, str(tmp_path / "er.txt"))
+    assert rc == 0, err
+    t = table(out)
+    assert t.shape == (ana.numBins, 9)
+    w1, w2 = windowed(ana, s1, s2)
+    band = shard.band_from_words(ana, shard.band_words_from_signals(ana, 2, w1, w2))
+    fit, mom = band.fit_gauss(), band.finalize()
+    np.testing.assert_allclose(t[:, 0], mom[:, 0], atol=1e-6)
+    filled = band.accepted > 100
+    assert filled.sum() > 60
+    np.testing.assert_allclose(t[filled, 1], mom[filled, 1], atol=2e-6)        # Bin Actual = mean S1 of the bin
+    for col, k in ((2, 1), (3, 3), (4, 2), (5, 4), (8, 6)):                   # mean, its error, sigma, its error, X^2/DOF
+        np.testing.assert_allclose(t[filled, col], fit[filled, k], atol=2e-6)
+    assert np.all(t[:, 6] == 0) and np.all(t[:, 7] == 0)                       # Gaussian fits: no skew columns (:1343-1345)
+    # the fitted band is the one that was written
+    low = filled & (t[:, 0] < 25)                       # above, the S2 window (maxS2 = 1e4) cuts into the band
+    assert np.abs(t[low, 2] - (2.6 - 0.006 * t[low, 0])).max() < 0.02 and np.abs(t[low, 4] - 0.11).max() < 0.02
+
+
+def test_leakage_table(tool, tmp_path):
+    ana = capi.analysis(0)
+    e1, e2 = write_execnest_file(tmp_path / "er.txt", 2, 150000, 2.6, -0.006, 0.11)
+    n1, n2 = write_execnest_file(tmp_path / "nr.txt", 3, 80000, 2.3, -0.003, 0.12)
+    rc, out, err = run(tool, str(tmp_path / "er.txt"), str(tmp_path / "nr.txt"))      # examples/leakage.sh's call
+    assert rc == 0, err
+    assert "Calculating band for first dataset" in out and "Calculating band for second dataset" in out
+    nr_t = table(out, "Calculating band for first dataset")       # argv[2] is read first (:668-676)
+    er_t = table(out, "Calculating band for second dataset")
+    lines = err.splitlines()
+    k = next(i for i, ln in enumerate(lines) if ln.startswith("#evts\tBinCen"))
+    assert "Leak Frac Raw" in lines[k]                             # ER given first: the ER-into-NR table
+    rows = np.array([[float(v) for v in ln.split("\t")[:12]] for ln in lines[k + 1:k + 1 + ana.numBins]])
+    assert rows.shape == (ana.numBins, 12)
+    # counting, restated: events of the ER file per S1 bin below the NR Gaussian mean of that bin
+    w1, w2 = windowed(ana, e1, e2)
+    width = (ana.maxS1 - ana.minS1) / ana.numBins
+    ok = (w1 >= 0) & (w2 >= 0)
+    tot_below = tot = 0
+    for i in range(ana.numBins):
+        lo = ana.minS1 + i * width
+        m = ok & (w1 > lo) & (w1 <= lo + width)
+        y = np.log10(w2[m] / w1[m])
+        assert rows[i, 0] == m.sum()
+        if m.sum() == 0:
+            continue
+        below = (y < nr_t[i, 2]).sum()                             # the table prints 6 decimals of the centroid
+        assert abs(rows[i, 8] * m.sum() - below) <= 1 + (np.abs(y - nr_t[i, 2]) < 1e-6).sum()
+        N = float(m.sum())
+        kk = rows[i, 8] * N
+        assert rows[i, 9] == pytest.approx((kk + np.sqrt(kk)) / (N - np.sqrt(N)) - rows[i, 8], rel=1e-4, abs=1e-9)
+        assert rows[i, 11] == pytest.approx((1 - rows[i, 8]) * 100, abs=1e-5)
+        tot_below += round(kk)
+        tot += m.sum()
+        if er_t[i, 4] > 0 and nr_t[i, 4] > 0:
+            n_sig = (er_t[i, 2] - nr_t[i, 2]) / er_t[i, 4]          # :719
+            assert rows[i, 3] == pytest.approx(n_sig, abs=2e-4)
+            assert rows[i, 4] == pytest.approx((1 - erf(rows[i, 3] / np.sqrt(2))) / 2, rel=1e-4)
+            assert rows[i, 7] == pytest.approx((1 - rows[i, 4]) * 100, abs=1e-5)
+    overall = [ln for ln in lines if ln.startswith("OVERALL DISCRIMINATION (ER)")][0]
+    assert float(overall.split("Leakage Fraction = ")[1]) == pytest.approx(tot_below / tot, rel=1e-9)
+    # NR first: the other header (characterising the NR band against its own centroid: about half below)
+    rc, out, err = run(tool, str(tmp_path / "nr.txt"), str(tmp_path / "er.txt"))
+    assert rc == 0 and "Lower ''Half''" in err
+    overall = [ln for ln in err.splitlines() if ln.startswith("OVERALL DISCRIMINATION (ER)")][0]
+    assert 0.45 < float(overall.split("Leakage Fraction = ")[1]) < 0.55
+
+
+def test_goodness_of_fit_mode(tool, tmp_path):
+    ana = capi.analysis(0)
+    write_execnest_file(tmp_path / "a.txt", 4, 150000, 2.6, -0.006, 0.11)
+    write_execnest_file(tmp_path / "b.txt", 5, 150000, 2.6, -0.006, 0.11)
+    rc, out, _ = run(tool, str(tmp_path / "b.txt"))
+    t = table(out)
+    # a "data band" file in the layout rootNEST reads (:603-607): centre, actual, mean, mean error, sigma, sigma error
+    sel = t[:, 4] > 0
+    with open(tmp_path / "band.txt", "w") as f:
+        for r in t:
+            if r[4] > 0:
+                f.write("%f\t%f\t%f\t%f\t%f\t%f\n" % (r[0], r[1], r[2], r[3], r[4], r[5]))
+            else:
+                f.write("%f\t%f\t%f\t%f\t%f\t%f\n" % (r[0], r[0], 2.0, 1e9, 0.1, 1e9))   # an empty bin: no weight
+    rc, out, err = run(tool, str(tmp_path / "a.txt"), str(tmp_path / "band.txt"), env={"NB200_MODE": "1"})
+    assert rc == 0, err
+    line = [ln for ln in out.splitlines() if ln.startswith("The reduced CHI^2 = ")][0]
+    chi_mean = float(line.split("= ")[1].split(" for mean")[0])
+    chi_width = float(line.split("and ")[1].split(" for width")[0])
+    assert 0.3 < chi_mean < 2.0 and 0.3 < chi_width < 2.0          # two samples of one band
+    ta = table(out)
+    both = sel & (ta[:, 4] > 0)
+    dof = ana.numBins - 2
+    exp_mean = (((t[both, 2] - ta[both, 2]) ** 2) / (t[both, 3] ** 2 + ta[both, 3] ** 2)).sum() / (dof - 1)
+    assert chi_mean == pytest.approx(exp_mean, rel=2e-3)
+    # one input is not enough for mode 1; unknown modes are refused; the binning must match
+    assert run(tool, str(tmp_path / "a.txt"), env={"NB200_MODE": "1"})[0] == 1
+    assert run(tool, str(tmp_path / "a.txt"), str(tmp_path / "band.txt"), env={"NB200_MODE": "2"})[0] == 1
+    with open(tmp_path / "shifted.txt", "w") as f:
+        for r in t:
+            f.write("%f\t%f\t%f\t%f\t%f\t%f\n" % (r[0] + 0.3, r[1], r[2], 0.01, 0.1, 0.01))
+    rc, _, err = run(tool, str(tmp_path / "a.txt"), str(tmp_path / "shifted.txt"), env={"NB200_MODE": "1"})
+    assert rc == 1 and "Binning doesn't match for GoF calculation" in err
+    assert run(tool)[0] == 1
+
+
+def test_on_the_reference_binary_output(tool, tmp_path):
+    """the unmodified reference's own stdout goes through: LUX_Run03 ER vs NR discrimination around 99.5 %"""
+    if not os.path.exists(refprobe.REF_BIN_LUX):
+        pytest.skip("oracle/_ref/execNEST_ref_lux not built")
+    for name, args in (("er.txt", ["60000", "beta", "0", "20", "180", "-1", "1"]),
+                       ("nr.txt", ["40000", "NR", "0", "60", "180", "-1", "2"])):
+        with open(tmp_path / name, "w") as f:
+            subprocess.run([refprobe.REF_BIN_LUX] + args, stdout=f, stderr=subprocess.DEVNULL, check=True, timeout=300)
+    rc, out, err = run(tool, str(tmp_path / "er.txt"), str(tmp_path / "nr.txt"))
+    assert rc == 0, err
+    overall = [ln for ln in err.splitlines() if ln.startswith("OVERALL DISCRIMINATION (ER)")][0]
+    leak = float(overall.split("Leakage Fraction = ")[1])
+    assert 1e-3 < leak < 1.5e-2
+    gauss = [ln for ln in err.splitlines() if ln.startswith("OVERALL DISCRIMINATION      ")][0]
+    assert 1e-3 < float(gauss.split("Leakage Fraction = ")[1]) < 1.5e-2
