@@ -40,6 +40,7 @@ extern "C" {
 #define NB200_ECUDA (-3)    /* CUDA runtime error, see nb200_last_error         */
 #define NB200_EPHYSICS (-4) /* reference would throw std::runtime_error         */
 #define NB200_ENOMEM (-5)
+#define NB200_EFIT (-6)     /* a histogram fit found no minimum (too few filled bins) */
 
 /* INTERACTION_TYPE, include/NEST/NEST.hh:133-156 (same numeric values) */
 enum {
@@ -339,6 +340,20 @@ int nb200_band_leakage(const nb200_analysis* ana, const nb200_band_hist* hist, c
  * out[numBins][4] = {number of ER sigmas between the two means, leakage (1 - erf(n/sqrt 2))/2, + error bar,
  * - error bar}; discrimination = 1 - leakage. */
 int nb200_band_fit_gauss(const nb200_analysis* ana, const nb200_band_hist* hist, double* fit);
+
+/* nb200_hist_fit -- one histogram, one chi^2 fit (same minimiser and conventions as nb200_band_fit_gauss), for callers
+ * that keep their own histograms: rootNEST's skew-Gaussian mode re-bins every S1 slice on mean +- 3 sigma
+ * (examples/rootNEST.cpp:1319-1330).  model 0 = A exp(-(x-mu)^2/(2 s^2)), par/err/start[3] = {A, mu, s};
+ * model 1 = rootNEST's "skewband" (:1361-1364) A/(w sqrt(2 pi)) exp(-(x-xi)^2/(2 w^2)) (1 + erf(al (x-xi)/(w sqrt 2))),
+ * par/err/start[4] = {A, xi, w, al}.  counts[bins] on (lo, hi).  NB200_EFIT when no minimum was found.
+ *
+ * nb200_band_leakage_skew -- leakage below line[i] of a skew-Gaussian band (xi, omega, alpha per S1 bin), i.e. the
+ * skew-normal CDF with Owen's T evaluated by the reference's own quadrature (:700-735, :1587-1602); err_hi / err_lo
+ * (or NULL) = the same with omega +- omega_err, the reference's "quick + dirty" error bars (:739-771). */
+int nb200_hist_fit(int model, const uint64_t* counts, int bins, double lo, double hi, const double* start, double* par,
+                   double* err, double* chi2_ndf);
+int nb200_band_leakage_skew(int numBins, const double* xi, const double* omega, const double* omega_err,
+                            const double* alpha, const double* line, double* leak, double* err_hi, double* err_lo);
 int nb200_band_leakage_gauss(int numBins, const double* er, const double* nr, double num_sig_above, double* out);
 
 /* LAr: replaces LArNEST::FullCalculation (src/LArNEST.cpp:17-33) for species

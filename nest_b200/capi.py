@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("NB200_LIB", os.path.join(HERE, "csrc", "libnest_b200.so"))
 
 # error codes
-OK, EINVAL, ENODEV, ECUDA, EPHYSICS, ENOMEM = 0, -1, -2, -3, -4, -5
+OK, EINVAL, ENODEV, ECUDA, EPHYSICS, ENOMEM, EFIT = 0, -1, -2, -3, -4, -5, -6
 # INTERACTION_TYPE (NEST.hh:133-156)
 NR, WIMP, B8, DD, AmBe, Cf, ion, gammaRay, beta, CH3T, C14, Kr83m, ppSolar, atmNu = range(14)
 NoneType = 17
@@ -103,7 +103,7 @@ EXPORTS = [
     "nb200_synchronize", "nb200_detector_builtin", "nb200_model_default", "nb200_analysis_default",
     "nb200_prepare", "nb200_wimp_prep", "nb200_poisson", "nb200_yields", "nb200_run", "nb200_run_async",
     "nb200_band_reset", "nb200_band_attach", "nb200_fp64_peak", "nb200_timing_enable", "nb200_timing_read", "nb200_se_stats", "nb200_band_fetch", "nb200_band_device_buffer", "nb200_allreduce_hist",
-    "nb200_band_hist_bytes", "nb200_band_finalize", "nb200_band_chi2", "nb200_band_leakage", "nb200_band_fit_gauss", "nb200_band_leakage_gauss", "nb200_lar", "nb200_launch_count",
+    "nb200_band_hist_bytes", "nb200_band_finalize", "nb200_band_chi2", "nb200_band_leakage", "nb200_band_fit_gauss", "nb200_band_leakage_gauss", "nb200_hist_fit", "nb200_band_leakage_skew", "nb200_lar", "nb200_launch_count",
     "nb200_debug_hitmath", "nb200_debug_binomial", "nb200_debug_normal", "nb200_debug_binomial_fixed",
     "nb200_debug_zig_tables", "nb200_debug_alias_tables"]
 
@@ -169,6 +169,8 @@ def lib():
     L.nb200_band_leakage.argtypes = [C.POINTER(Analysis), C.POINTER(BandHist), c_dp, c_dp, c_dp, c_dp, c_dp]
     L.nb200_band_fit_gauss.argtypes = [C.POINTER(Analysis), C.POINTER(BandHist), c_dp]
     L.nb200_band_leakage_gauss.argtypes = [C.c_int, c_dp, c_dp, C.c_double, c_dp]
+    L.nb200_hist_fit.argtypes = [C.c_int, c_u64p, C.c_int, C.c_double, C.c_double, c_dp, c_dp, c_dp, c_dp]
+    L.nb200_band_leakage_skew.argtypes = [C.c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]
     L.nb200_lar.argtypes = [vp, C.c_int, C.c_size_t, vp, vp, C.c_double, C.c_uint64, C.c_uint64, C.c_int,
                             vp, vp]
     L.nb200_debug_hitmath.argtypes = [vp, C.c_size_t, vp, vp]
@@ -197,6 +199,36 @@ def band_chi2(a, b, useS2=0, free_param=2):
     if rc:
         raise NestB200Error(rc, "nb200_band_chi2: binning does not match")
     return out
+
+
+def hist_fit(model, counts, lo, hi, start):
+    """chi^2 fit of a Gaussian (model 0: A, mu, s) or rootNEST's skew-Gaussian (model 1: A, xi, omega, alpha) to one
+    histogram on (lo, hi), as TH1::Fit does by default; returns (par, err, chi2/ndf)"""
+    c = np.ascontiguousarray(counts, np.uint64)
+    n = 3 if model == 0 else 4
+    st = np.ascontiguousarray(start, np.float64)
+    if st.size != n:
+        raise ValueError("model %d takes %d start values" % (model, n))
+    par, err, chi = np.zeros(n), np.zeros(n), C.c_double()
+    rc = lib().nb200_hist_fit(model, c.ctypes.data_as(c_u64p), c.size, lo, hi, st.ctypes.data_as(c_dp),
+                              par.ctypes.data_as(c_dp), err.ctypes.data_as(c_dp), C.byref(chi))
+    if rc:
+        raise NestB200Error(rc, "nb200_hist_fit: no minimum" if rc == EFIT else "nb200_hist_fit")
+    return par, err, chi.value
+
+
+def band_leakage_skew(xi, omega, omega_err, alpha, line):
+    """skew-normal leakage below `line` per S1 bin with the omega +- error variants (rootNEST.cpp:700-771)"""
+    a = [np.ascontiguousarray(v, np.float64) for v in (xi, omega, omega_err, alpha, line)]
+    n = a[0].size
+    if any(v.size != n for v in a):
+        raise ValueError("arrays of different lengths")
+    leak, hi, lo = np.zeros(n), np.zeros(n), np.zeros(n)
+    rc = lib().nb200_band_leakage_skew(n, *[v.ctypes.data_as(c_dp) for v in a], leak.ctypes.data_as(c_dp),
+                                       hi.ctypes.data_as(c_dp), lo.ctypes.data_as(c_dp))
+    if rc:
+        raise NestB200Error(rc, "nb200_band_leakage_skew")
+    return leak, hi, lo
 
 
 def band_leakage_gauss(er_fit, nr_fit, num_sig_above=0.0):

@@ -1190,68 +1190,100 @@ namespace {
 // so what examples/rootNEST.cpp:1336-1338 asks for.  Levenberg-Marquardt with the analytic Jacobian; the
 // parameter errors are the square roots of the diagonal of (J^T W J)^-1 at the minimum (MIGRAD's parabolic
 // errors for a chi^2).  Returns the number of points used, or 0 when there are fewer than four or no minimum.
-bool solve3(const double M[3][3], const double v[3], double x[3]) {
-  double a[3][4];
-  for (int i = 0; i < 3; ++i) {
-    for (int j = 0; j < 3; ++j) a[i][j] = M[i][j];
-    a[i][3] = v[i];
+constexpr int kFitMaxPar = 4;
+bool solve_n(int n, const double M[kFitMaxPar][kFitMaxPar], const double* v, double* x) {
+  double a[kFitMaxPar][kFitMaxPar + 1];
+  for (int i = 0; i < n; ++i) {
+    for (int j = 0; j < n; ++j) a[i][j] = M[i][j];
+    a[i][n] = v[i];
   }
-  for (int c = 0; c < 3; ++c) {
+  for (int c = 0; c < n; ++c) {
     int piv = c;
-    for (int r = c + 1; r < 3; ++r)
+    for (int r = c + 1; r < n; ++r)
       if (std::fabs(a[r][c]) > std::fabs(a[piv][c])) piv = r;
     if (!(std::fabs(a[piv][c]) > 0.)) return false;
-    for (int j = 0; j < 4; ++j) std::swap(a[c][j], a[piv][j]);
-    for (int r = 0; r < 3; ++r) {
+    for (int j = 0; j <= n; ++j) std::swap(a[c][j], a[piv][j]);
+    for (int r = 0; r < n; ++r) {
       if (r == c) continue;
       const double f = a[r][c] / a[c][c];
-      for (int j = c; j < 4; ++j) a[r][j] -= f * a[c][j];
+      for (int j = c; j <= n; ++j) a[r][j] -= f * a[c][j];
     }
   }
-  for (int i = 0; i < 3; ++i) x[i] = a[i][3] / a[i][i];
+  for (int i = 0; i < n; ++i) x[i] = a[i][n] / a[i][i];
   return true;
 }
 
-double gauss_chi2(const uint64_t* row, int lb, double x0, double w, const double p[3], double JtJ[3][3], double Jtr[3]) {
-  double chi = 0.;
+// model 0: A exp(-(x - mu)^2 / (2 s^2))                                          (ROOT's "gaus";   p = A, mu, s)
+// model 1: A / (w sqrt(2 pi)) exp(-(x - xi)^2 / (2 w^2)) (1 + erf(al (x - xi) / (w sqrt 2)))
+//                                                     (rootNEST.cpp:1361-1364 "skewband"; p = A, xi, w, al)
+inline int model_npar(int model) { return model == 0 ? 3 : 4; }
+inline double model_eval(int model, const double* p, double x, double* g) {
+  const double z = (x - p[1]) / p[2], e = std::exp(-0.5 * z * z);
+  if (model == 0) {
+    const double f = p[0] * e;
+    if (g) {
+      g[0] = e;
+      g[1] = f * z / p[2];
+      g[2] = f * z * z / p[2];
+    }
+    return f;
+  }
+  const double G = e / (p[2] * std::sqrt(2. * M_PI)), t = p[3] * z / std::sqrt(2.);
+  const double E = 1. + std::erf(t), dE = 2. / std::sqrt(M_PI) * std::exp(-t * t);  // d erf / dt
+  if (g) {
+    g[0] = G * E;
+    g[1] = p[0] * G * (z * E - dE * p[3] / std::sqrt(2.)) / p[2];
+    g[2] = p[0] * G * ((z * z - 1.) * E - dE * p[3] * z / std::sqrt(2.)) / p[2];
+    g[3] = p[0] * G * dE * z / std::sqrt(2.);
+  }
+  return p[0] * G * E;
+}
+
+double hist_chi2(int model, const uint64_t* row, int lb, double x0, double w, const double* p,
+                 double JtJ[kFitMaxPar][kFitMaxPar], double* Jtr) {
+  const int n = model_npar(model);
+  double chi = 0., g[kFitMaxPar];
   if (JtJ)
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < n; ++i) {
       Jtr[i] = 0.;
-      for (int j = 0; j < 3; ++j) JtJ[i][j] = 0.;
+      for (int j = 0; j < n; ++j) JtJ[i][j] = 0.;
     }
   for (int k = 0; k < lb; ++k) {
     if (!row[k]) continue;
-    const double h = double(row[k]), x = x0 + (double(k) + 0.5) * w, d = (x - p[1]) / p[2];
-    const double e = std::exp(-0.5 * d * d), f = p[0] * e, r = h - f;
+    const double h = double(row[k]), x = x0 + (double(k) + 0.5) * w;
+    const double r = h - model_eval(model, p, x, JtJ ? g : nullptr);
     chi += r * r / h;
-    if (JtJ) {
-      const double g[3] = {e, f * d / p[2], f * d * d / p[2]};
-      for (int i = 0; i < 3; ++i) {
+    if (JtJ)
+      for (int i = 0; i < n; ++i) {
         Jtr[i] += g[i] * r / h;
-        for (int j = 0; j < 3; ++j) JtJ[i][j] += g[i] * g[j] / h;
+        for (int j = 0; j < n; ++j) JtJ[i][j] += g[i] * g[j] / h;
       }
-    }
   }
   return chi;
 }
 
-int fit_gauss_row(const uint64_t* row, int lb, double x0, double w, double p[3], double err[3], double* chi2) {
+// returns the number of histogram bins used, 0 when there are too few or no minimum was found
+int fit_hist_row(int model, const uint64_t* row, int lb, double x0, double w, double* p, double* err, double* chi2) {
+  const int n = model_npar(model);
   int used = 0;
   for (int k = 0; k < lb; ++k) used += row[k] != 0;
-  if (used < 4 || !(p[2] > 0.) || !(p[0] > 0.)) return 0;
-  double JtJ[3][3], Jtr[3], lambda = 1e-3;
-  double chi = gauss_chi2(row, lb, x0, w, p, JtJ, Jtr);
-  for (int it = 0; it < 200; ++it) {
-    double M[3][3], step[3], q[3];
-    for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 3; ++j) M[i][j] = JtJ[i][j] * (i == j ? 1. + lambda : 1.);
-    if (!solve3(M, Jtr, step)) return 0;
-    for (int i = 0; i < 3; ++i) q[i] = p[i] + step[i];
-    const double trial = (q[2] > 0. && q[0] > 0.) ? gauss_chi2(row, lb, x0, w, q, nullptr, nullptr) : INFINITY;
+  if (used <= n || !(p[2] > 0.) || !(p[0] > 0.)) return 0;
+  double JtJ[kFitMaxPar][kFitMaxPar], Jtr[kFitMaxPar], lambda = 1e-3;
+  double chi = hist_chi2(model, row, lb, x0, w, p, JtJ, Jtr);
+  if (!std::isfinite(chi)) return 0;
+  for (int it = 0; it < 500; ++it) {
+    double M[kFitMaxPar][kFitMaxPar], step[kFitMaxPar], q[kFitMaxPar];
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) M[i][j] = JtJ[i][j] * (i == j ? 1. + lambda : 1.);
+    if (!solve_n(n, M, Jtr, step)) return 0;
+    for (int i = 0; i < n; ++i) q[i] = p[i] + step[i];
+    double trial = (q[2] > 0. && q[0] > 0.) ? hist_chi2(model, row, lb, x0, w, q, nullptr, nullptr) : INFINITY;
+    if (!std::isfinite(trial)) trial = INFINITY;
     if (trial <= chi) {
-      const bool done = chi - trial <= 1e-13 * chi && std::fabs(step[1]) <= 1e-10 * p[2] && std::fabs(step[2]) <= 1e-10 * p[2];
-      for (int i = 0; i < 3; ++i) p[i] = q[i];
-      chi = gauss_chi2(row, lb, x0, w, p, JtJ, Jtr);
+      bool done = chi - trial <= 1e-13 * chi;
+      for (int i = 1; i < n; ++i) done = done && std::fabs(step[i]) <= 1e-9 * (i == 3 ? 1. + std::fabs(p[3]) : p[2]);
+      for (int i = 0; i < n; ++i) p[i] = q[i];
+      chi = hist_chi2(model, row, lb, x0, w, p, JtJ, Jtr);
       lambda = lambda > 1e-12 ? lambda * 0.1 : lambda;
       if (done) break;
     } else {
@@ -1260,14 +1292,26 @@ int fit_gauss_row(const uint64_t* row, int lb, double x0, double w, double p[3],
     }
   }
   // covariance = (J^T W J)^-1, column by column
-  for (int i = 0; i < 3; ++i) {
-    double unit[3] = {0., 0., 0.}, col[3];
+  for (int i = 0; i < n; ++i) {
+    double unit[kFitMaxPar] = {0., 0., 0., 0.}, col[kFitMaxPar];
     unit[i] = 1.;
-    if (!solve3(JtJ, unit, col) || !(col[i] > 0.)) return 0;
+    if (!solve_n(n, JtJ, unit, col) || !(col[i] > 0.)) return 0;
     err[i] = std::sqrt(col[i]);
   }
   *chi2 = chi;
   return used;
+}
+
+// rootNEST.cpp:1587-1602: Owen's T by the reference's own midpoint rule (2500 steps), so that leakages agree digit for digit
+double owens_t_ref(double h, double a) {
+  const int nIntSteps = 2500;
+  const double dx = a / nIntSteps;
+  double T = 0.;
+  for (int k = 0; k < nIntSteps; ++k) {
+    const double x = (k + 0.5) * dx;
+    T += std::exp(-0.5 * h * h * (1 + x * x)) / (1 + x * x) * dx;
+  }
+  return T / (2. * M_PI);
 }
 }  // namespace
 extern "C" {
@@ -1292,8 +1336,8 @@ int nb200_band_fit_gauss(const nb200_analysis* ana, const nb200_band_hist* h, do
     if (!(n > 1.)) continue;
     const double mu = sx / n;
     const double var = sxx / n - mu * mu + w * w / 12.;
-    double p[3] = {n * w / std::sqrt(2. * M_PI * var), mu, std::sqrt(var)}, err[3] = {0., 0., 0.}, chi = 0.;
-    const int used = fit_gauss_row(row, lb, ana->logMin, w, p, err, &chi);
+    double p[4] = {n * w / std::sqrt(2. * M_PI * var), mu, std::sqrt(var), 0.}, err[4] = {0., 0., 0., 0.}, chi = 0.;
+    const int used = fit_hist_row(0, row, lb, ana->logMin, w, p, err, &chi);
     if (!used) continue;
     o[0] = p[0];
     o[1] = p[1];
@@ -1334,6 +1378,39 @@ int nb200_band_leakage_gauss(int numBins, const double* er, const double* nr, do
     o[1] = leak;
     o[2] = std::fabs((1. - std::erf(up / std::sqrt(2.))) / 2. - leak);
     o[3] = std::fabs(leak - (1. - std::erf(dn / std::sqrt(2.))) / 2.);
+  }
+  return 0;
+}
+
+// One histogram, one fit: the building block of GetBand_Gaussian for callers that keep their own histograms
+// (rootNEST's skew-Gaussian mode re-bins every S1 slice on mean +- 3 sigma, rootNEST.cpp:1319-1330)
+int nb200_hist_fit(int model, const uint64_t* counts, int bins, double lo, double hi, const double* start, double* par,
+                   double* err, double* chi2_ndf) {
+  if (!counts || !start || !par || !err || bins < 1 || !(hi > lo) || (model != 0 && model != 1)) return NB200_EINVAL;
+  const int n = model_npar(model);
+  double p[kFitMaxPar], e[kFitMaxPar] = {0., 0., 0., 0.}, chi = 0.;
+  for (int i = 0; i < n; ++i) p[i] = start[i];
+  const int used = fit_hist_row(model, counts, bins, lo, (hi - lo) / double(bins), p, e, &chi);
+  if (!used) return NB200_EFIT;
+  for (int i = 0; i < n; ++i) {
+    par[i] = p[i];
+    err[i] = e[i];
+  }
+  if (chi2_ndf) *chi2_ndf = chi / double(used - n);
+  return 0;
+}
+
+// examples/rootNEST.cpp:700-773 (skewness == 1): leakage below a line from a skew-Gaussian ER band
+int nb200_band_leakage_skew(int numBins, const double* xi, const double* omega, const double* omega_err, const double* alpha,
+                            const double* line, double* leak, double* err_hi, double* err_lo) {
+  if (!xi || !omega || !alpha || !line || !leak || numBins < 1) return NB200_EINVAL;
+  auto cdf = [](double c, double xi_, double om, double al) {
+    return 0.5 + 0.5 * std::erf((c - xi_) / om / std::sqrt(2.)) - 2. * owens_t_ref((c - xi_) / om, al);
+  };
+  for (int i = 0; i < numBins; ++i) {
+    leak[i] = cdf(line[i], xi[i], omega[i], alpha[i]);
+    if (omega_err && err_hi) err_hi[i] = cdf(line[i], xi[i], omega[i] + omega_err[i], alpha[i]);  // :741-771, "focused on omega"
+    if (omega_err && err_lo) err_lo[i] = cdf(line[i], xi[i], omega[i] - omega_err[i], alpha[i]);
   }
   return 0;
 }

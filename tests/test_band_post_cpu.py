@@ -241,3 +241,65 @@ def test_band_gaussian_leakage_follows_rootnest(built):
     np.testing.assert_allclose(shifted[ok, 0], (e[:, 1] - (r[:, 1] - r[:, 2])) / e[:, 2], rtol=1e-13)
     with pytest.raises(ValueError):
         capi.band_leakage_gauss(er[:, :7], nr[:, :7])
+
+
+def test_skew_gaussian_fit_matches_least_squares(built):
+    """nb200_hist_fit model 1 (rootNEST's "skewband", examples/rootNEST.cpp:1361-1364) against scipy's least squares
+    with the same weights on the same histogram, and back to the parameters the sample was drawn with"""
+    from scipy.optimize import curve_fit
+    from scipy.special import erf
+    from scipy.stats import skewnorm
+    f = lambda x, A, xi, w, al: A / (w * np.sqrt(2 * np.pi)) * np.exp(-0.5 * ((x - xi) / w) ** 2) * (1 + erf(al * (x - xi) / (w * np.sqrt(2))))
+    for seed, (xi, om, al, n) in enumerate([(2.45, 0.16, 1.8, 200000), (2.3, 0.12, -1.2, 80000), (2.0, 0.1, 1.0, 150000)]):
+        y = skewnorm.rvs(al, loc=xi, scale=om, size=n, random_state=seed)
+        mu, sd = y.mean(), y.std()
+        lo, hi, bins = mu - 3 * sd, mu + 3 * sd, 60                      # rootNEST's per-slice axis (:1319-1323)
+        h, edges = np.histogram(y, bins=bins, range=(lo, hi))
+        x = 0.5 * (edges[1:] + edges[:-1])
+        start = (n * (hi - lo) / bins, mu - 0.5 * sd, 1.2 * sd, 0.5)
+        par, err, chi = capi.hist_fit(1, h, lo, hi, start)
+        k = h > 0
+        popt, pcov = curve_fit(f, x[k], h[k].astype(float), p0=start, sigma=np.sqrt(h[k]), absolute_sigma=True,
+                               xtol=1e-14, ftol=1e-14, gtol=1e-14)
+        np.testing.assert_allclose(par, popt, rtol=5e-5, atol=1e-6)
+        np.testing.assert_allclose(err, np.sqrt(np.diag(pcov)), rtol=2e-3)
+        c = (((h[k] - f(x[k], *par)) ** 2) / h[k]).sum() / (k.sum() - 4)
+        assert chi == pytest.approx(c, rel=1e-9) and 0.3 < chi < 2.5
+        # the sample's own parameters, within the fit's errors (bin-centre evaluation biases omega by ~w^2/24 omega)
+        assert abs(par[1] - xi) < 6 * err[1] + 2e-3 and abs(par[2] - om) < 6 * err[2] + 2e-3 and abs(par[3] - al) < 6 * err[3] + 0.05
+        assert par[0] == pytest.approx(h.sum() * (hi - lo) / bins, rel=0.02)   # the function integrates to A: N * bin width
+    # model 0 through the same entry point equals the band fit's rows
+    ana = capi.analysis(0)
+    ana.logBins = 100
+    b = band_of(ana, *synthetic_signals(12, 200000, 2.6, -0.006, 0.11))
+    fit, mom = b.fit_gauss(), b.finalize()
+    row = b.hist2d.reshape(ana.numBins, ana.logBins)[10]
+    par, err, chi = capi.hist_fit(0, row, ana.logMin, ana.logMax, (row.max(), mom[10, 2], mom[10, 3]))
+    np.testing.assert_allclose(par, fit[10, :3], rtol=1e-7)
+    np.testing.assert_allclose(err[1:], fit[10, 3:5], rtol=1e-6)
+    assert chi == pytest.approx(fit[10, 5], rel=1e-7)
+    # too few filled bins: an error code, not a made-up answer
+    with pytest.raises(capi.NestB200Error) as e:
+        capi.hist_fit(1, np.array([0, 5, 9, 4, 0, 0], np.uint64), 0.0, 1.0, (10.0, 0.4, 0.2, 0.1))
+    assert e.value.code == capi.EFIT
+    with pytest.raises(ValueError):
+        capi.hist_fit(0, row, 0.0, 1.0, (1.0, 2.0))
+
+
+def test_skew_leakage_is_the_skew_normal_cdf(built):
+    from scipy.stats import skewnorm
+    rng = np.random.default_rng(5)
+    n = 40
+    xi, om, al = rng.uniform(2.2, 2.7, n), rng.uniform(0.08, 0.2, n), rng.uniform(-2.5, 2.5, n)
+    om_err = om * 0.03
+    line = xi - rng.uniform(0.5, 3.0, n) * om
+    leak, hi, lo = capi.band_leakage_skew(xi, om, om_err, al, line)
+    # the reference integrates Owen's T by a 2500-step midpoint rule (rootNEST.cpp:1587-1602): exact to ~1e-8
+    np.testing.assert_allclose(leak, skewnorm.cdf(line, al, loc=xi, scale=om), atol=2e-7)
+    np.testing.assert_allclose(hi, skewnorm.cdf(line, al, loc=xi, scale=om + om_err), atol=2e-7)
+    np.testing.assert_allclose(lo, skewnorm.cdf(line, al, loc=xi, scale=om - om_err), atol=2e-7)
+    assert np.all(hi >= leak - 1e-12) and np.all(lo <= leak + 1e-12)      # the line is below xi: wider = more leakage
+    # alpha = 0 is the Gaussian leakage
+    g, _, _ = capi.band_leakage_skew(xi, om, om_err, np.zeros(n), line)
+    from scipy.special import erf
+    np.testing.assert_allclose(g, 0.5 * (1 + erf((line - xi) / om / np.sqrt(2))), atol=1e-15)
