@@ -5,13 +5,14 @@
 //                                                :668-950 -- examples/leakage.sh runs unchanged)
 //   NB200_MODE=1 rootNEST_b200 NESTOutput.txt dataBand.txt   goodness of fit against a data band (mode 1; :587-666)
 //
-// with the analysis.hh settings skewness = 0 (Gaussian fits) and NRbandCenter = 1 (the Gaussian mean of each
-// S1 bin is the NR centroid).  The reference's defaults -- skew-Gaussian fits and a Woods-function fit through
-// the NR means -- need ROOT's minimiser and are out of scope; modes 2 and 3 (WIMP limits)
-// likewise.  Inputs are execNEST's 12-column stdout (src/execNEST.cpp:1386-1405), read as GetFile does
+// with the analysis.hh settings skewness = 1 (skew-Gaussian fits, the reference's default; NB200_SKEWNESS=0 for
+// Gaussian fits) and NRbandCenter = 1 (the fitted mean of each S1 bin is the NR centroid; the reference's default,
+// a Woods-function fit through the NR means, is not included, nor are skewness = 2's MINOS-style covariances or
+// modes 2 and 3, the WIMP limits).  Inputs are execNEST's 12-column stdout (src/execNEST.cpp:1386-1405), read as GetFile does
 // (:955-1036); per-bin statistics, Gaussian fits and leakage come from the library's host-side band functions
-// (include/nest_b200.h: nb200_band_finalize, nb200_band_fit_gauss, nb200_band_leakage_gauss).  Nothing here
+// (include/nest_b200.h: nb200_band_finalize, nb200_band_fit_gauss, nb200_hist_fit, nb200_band_leakage_gauss / _skew).  Nothing here
 // simulates anything: no device is needed or used.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -26,12 +27,14 @@ using namespace std;
 namespace {
 NEST::Analysis A;
 const int freeParam = 2;       // analysis.hh:65
+int skewness = 1;              // analysis.hh:67
 const double NUMSIGABV = -0.;  // rootNEST.cpp:39
 
 struct BandOfFile {
   vector<vector<double>> inputs, outputs;  // per S1 bin: S1 values, y values (GetBand's two passes, :1141-1165)
   vector<double> mom;                      // [numBins][7] nb200_band_finalize
-  vector<double> fit;                      // [numBins][8] nb200_band_fit_gauss
+  vector<double> fit;                      // [numBins][8] nb200_band_fit_gauss; skew fits: [1] mean, [2] sigma, [3] xi error, [4] omega error
+  vector<double> xi, omega, omega_err, alpha, alpha_err;  // skew fits only (band[j][9], [11], [12], [4], [7])
   size_t events = 0;
 };
 
@@ -118,12 +121,75 @@ bool band_of_file(const char* name, BandOfFile& B) {
     cerr << "ERROR: band statistics failed (numBins, logBins?)" << endl;
     return false;
   }
+  if (B.events < 20000 && nb > 1 && skewness != 0) {  // :1037-1042
+    skewness = 0;
+    cerr << "WARNING: Not enough stats (at least 10^5 events) for skew fits so doing Gaussian" << endl;
+  }
+  B.xi.assign(nb, 0.);
+  B.omega.assign(nb, 0.);
+  B.omega_err.assign(nb, 0.);
+  B.alpha.assign(nb, 0.);
+  B.alpha_err.assign(nb, 0.);
+  bool wings = false;
+  for (int j = 0; skewness && j < nb; ++j) {  // :1319-1330, :1360-1507
+    double* f = &B.fit[8 * size_t(j)];
+    const double mean = B.mom[7 * size_t(j) + 2], sd = B.mom[7 * size_t(j) + 3];
+    for (int i = 0; i < 8; ++i) f[i] = 0.;
+    const vector<double>& ys = B.outputs[j];
+    if (ys.size() < 2 || !(sd > 0.)) continue;
+    double lo = mean - 3. * sd, hi = mean + 3. * sd;
+    if (lo > 2.) wings = true;
+    if (hi > 3.) wings = true;
+    if (wings) {
+      lo -= 0.5;
+      hi += 0.5;
+    }
+    vector<uint64_t> h(lb, 0);
+    for (double y : ys)
+      if (y >= lo && y < hi) ++h[min(lb - 1, int((y - lo) / (hi - lo) * lb))];
+    // EstimateSkew :1567-1585
+    double skew = 0.;
+    for (double y : ys) skew += pow((y - mean) / sd, 3.);
+    skew /= double(ys.size());
+    if (skew == 0.) skew = 1e-9;
+    skew = skew / fabs(skew) * min(0.7, fabs(skew));
+    const double delta0 = skew / fabs(skew) *
+                          sqrt(M_PI / 2. * pow(fabs(skew), 2. / 3.) / (pow(fabs(skew), 2. / 3.) + pow((4. - M_PI) / 2., 2. / 3.)));
+    const double alpha0 = delta0 / sqrt(1. - delta0 * delta0);
+    const double dE = alpha0 / sqrt(1. + alpha0 * alpha0);
+    const double omega0 = sd / sqrt(1. - 2. * dE * dE / M_PI);
+    // the reference starts the amplitude at the number of events (:1365); the function integrates to its amplitude, so
+    // the events times the bin width is where the minimum is -- start there
+    const double start[4] = {double(ys.size()) * (hi - lo) / double(lb), mean - omega0 * dE * sqrt(2. / M_PI), omega0, alpha0};
+    double par[4], err[4], chi = 0.;
+    if (nb200_hist_fit(1, h.data(), lb, lo, hi, start, par, err, &chi)) {
+      if (A.verbosity > 0) cerr << "Re-fitting... (stats, more? and/or logBins, fewer? might help)\n";
+      continue;
+    }
+    const double d = par[3] / sqrt(1. + par[3] * par[3]);
+    f[0] = par[0];
+    f[1] = par[1] + par[2] * d * sqrt(2. / M_PI);          // band[j][2]
+    f[2] = par[2] * sqrt(1. - 2. * d * d / M_PI);          // band[j][3]
+    f[3] = err[1];                                         // band[j][5] = GetParError(1)
+    f[4] = err[2];                                         // band[j][6] = GetParError(2)
+    f[5] = f[6] = chi;                                     // band[j][8] = chi^2 / NDF of the fit
+    f[7] = 1.;
+    B.xi[j] = par[1];
+    B.omega[j] = par[2];
+    B.omega_err[j] = err[2];
+    B.alpha[j] = par[3];
+    B.alpha_err[j] = err[3];
+    if ((chi > 10. || f[1] > 7. || f[3] > 1. || fabs(par[3]) > 3. || err[3] > 10. || f[2] > 0.5 || f[4] > 0.1 || f[1] <= 0. ||
+         f[2] <= 0.) && A.verbosity > 0)
+      cerr << "Re-fitting... (stats, more? and/or logBins, fewer? might help)\n";  // :1493-1504: mode 0 reports, does not retry
+  }
   if (A.verbosity > 0) {  // :1180-1190
     fprintf(stdout, "Bin Center\tBin Actual\tGaus Mean\tMean Error\tGaus Sigma\tSig Error\tGaus Skew\tSkew Error\tX^2/DOF\n");
     for (int o = 0; o < nb; ++o) {
       const double* m = &B.mom[7 * size_t(o)];
       const double* f = &B.fit[8 * size_t(o)];
-      fprintf(stdout, "%lf\t%lf\t%lf\t%lf\t%lf\t%lf\t%lf\t%lf\t%lf\n", m[0], m[1], f[1], f[3], f[2], f[4], 0., 0., f[6]);
+      fprintf(stdout, "%lf\t%lf\t%lf\t%lf\t%lf\t%lf\t%lf\t%lf\t%lf\n", m[0], m[1], f[1], f[3], f[2], f[4], B.alpha[o], B.alpha_err[o],
+              f[6]);
     }
   }
   return true;
@@ -195,6 +261,20 @@ int leakage_table(const char* file1, const char* file2) {  // :668-950
   const vector<double>& nr = ERis2nd ? B.fit : B2.fit;
   vector<double> lk(size_t(nb) * 4, 0.);
   if (nb200_band_leakage_gauss(nb, er.data(), nr.data(), NUMSIGABV, lk.data())) return 1;
+  if (skewness) {  // :700-773: the leakage and its error bars from the ER band's skew-Gaussian, the number of sigmas as before
+    const BandOfFile& E = ERis2nd ? B2 : B;
+    vector<double> line(nb), leak(nb), hi(nb), lo(nb);
+    for (int i = 0; i < nb; ++i) line[i] = nr[8 * size_t(i) + 1] + NUMSIGABV * nr[8 * size_t(i) + 2];
+    if (nb200_band_leakage_skew(nb, E.xi.data(), E.omega.data(), E.omega_err.data(), E.alpha.data(), line.data(), leak.data(),
+                                hi.data(), lo.data()))
+      return 1;
+    for (int i = 0; i < nb; ++i) {
+      if (!(E.omega[i] > 0.)) continue;
+      lk[4 * size_t(i) + 1] = leak[i];
+      lk[4 * size_t(i) + 2] = fabs(hi[i] - leak[i]);
+      lk[4 * size_t(i) + 3] = fabs(leak[i] - lo[i]);
+    }
+  }
   double finalSums[3] = {0., 0., 0.};
   for (int i = 0; i < nb; ++i) {
     // counting (:880-915, NRbandCenter = 1): the second dataset's events below the NR line of this bin
@@ -237,6 +317,7 @@ int main(int argc, char** argv) {
     if (!strcmp(a, "G2")) A = NEST::Analysis::G2();
   if (const char* v = getenv("NB200_VERBOSITY")) A.verbosity = atoi(v);
   if (const char* v = getenv("NB200_LOGBINS")) A.logBins = atoi(v);
+  if (const char* v = getenv("NB200_SKEWNESS")) skewness = atoi(v) ? 1 : 0;
   const int mode = getenv("NB200_MODE") ? atoi(getenv("NB200_MODE")) : 0;
   if (argc < 2) {  // :104-119
     cout << endl << "This program takes 1 (or 2) inputs." << endl << endl;

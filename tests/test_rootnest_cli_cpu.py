@@ -25,17 +25,19 @@ def tool(built):
 
 def run(tool, *args, env=None):
     e = dict(os.environ)
+    e["NB200_SKEWNESS"] = "0"                 # Gaussian fits unless a test asks for the reference's default
     e.update(env or {})
     r = subprocess.run([tool] + list(args), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=e, timeout=300)
     return r.returncode, r.stdout, r.stderr
 
 
-def write_execnest_file(path, seed, n, mu0, slope, sigma):
+def write_execnest_file(path, seed, n, mu0, slope, sigma, alpha=0.0, s1max=70.0):
     """rows in execNEST's stdout layout (src/execNEST.cpp:1386-1405) under its two header lines; some rows carry the
     reference's below-threshold flags (negative signals) and some lie outside the S1 / S2 windows"""
+    from scipy.stats import skewnorm
     rng = np.random.default_rng(seed)
-    s1 = rng.uniform(0.5, 70.0, n)
-    s2 = s1 * 10.0 ** rng.normal(mu0 + slope * s1, sigma)
+    s1 = rng.uniform(0.5, s1max, n)
+    s2 = s1 * 10.0 ** (mu0 + slope * s1 + skewnorm.rvs(alpha, scale=sigma, size=n, random_state=rng))
     s1[::17] *= -1.0
     s2[::23] *= -1.0
     s1, s2 = np.round(s1, 6), np.round(s2, 6)       # what the 6-decimal text carries
@@ -141,9 +143,11 @@ def test_leakage_table(tool, tmp_path):
 
 def test_goodness_of_fit_mode(tool, tmp_path):
     ana = capi.analysis(0)
-    write_execnest_file(tmp_path / "a.txt", 4, 150000, 2.6, -0.006, 0.11)
-    write_execnest_file(tmp_path / "b.txt", 5, 150000, 2.6, -0.006, 0.11)
-    rc, out, _ = run(tool, str(tmp_path / "b.txt"))
+    # S1 below 25 keeps the band clear of the S2 window; 120 log bins so that a bin is a fraction of the band's sigma
+    fine = {"NB200_LOGBINS": "120"}
+    write_execnest_file(tmp_path / "a.txt", 4, 150000, 2.6, -0.006, 0.11, s1max=25.0)
+    write_execnest_file(tmp_path / "b.txt", 5, 150000, 2.6, -0.006, 0.11, s1max=25.0)
+    rc, out, _ = run(tool, str(tmp_path / "b.txt"), env=fine)
     t = table(out)
     # a "data band" file in the layout rootNEST reads (:603-607): centre, actual, mean, mean error, sigma, sigma error
     sel = t[:, 4] > 0
@@ -153,12 +157,14 @@ def test_goodness_of_fit_mode(tool, tmp_path):
                 f.write("%f\t%f\t%f\t%f\t%f\t%f\n" % (r[0], r[1], r[2], r[3], r[4], r[5]))
             else:
                 f.write("%f\t%f\t%f\t%f\t%f\t%f\n" % (r[0], r[0], 2.0, 1e9, 0.1, 1e9))   # an empty bin: no weight
-    rc, out, err = run(tool, str(tmp_path / "a.txt"), str(tmp_path / "band.txt"), env={"NB200_MODE": "1"})
+    rc, out, err = run(tool, str(tmp_path / "a.txt"), str(tmp_path / "band.txt"), env={"NB200_MODE": "1", **fine})
     assert rc == 0, err
     line = [ln for ln in out.splitlines() if ln.startswith("The reduced CHI^2 = ")][0]
     chi_mean = float(line.split("= ")[1].split(" for mean")[0])
     chi_width = float(line.split("and ")[1].split(" for width")[0])
-    assert 0.3 < chi_mean < 2.0 and 0.3 < chi_width < 2.0          # two samples of one band
+    # two samples of one band over 23 filled bins: chi^2 ~ 23 +- 7, divided by DoF - 1 = 95 as the reference does; the
+    # widths of chi^2 fits weighted by the observed contents scatter by more than their parabolic errors (as ROOT's do)
+    assert 0.08 < chi_mean < 0.5 and 0.08 < chi_width < 0.9
     ta = table(out)
     both = sel & (ta[:, 4] > 0)
     dof = ana.numBins - 2
@@ -173,6 +179,53 @@ def test_goodness_of_fit_mode(tool, tmp_path):
     rc, _, err = run(tool, str(tmp_path / "a.txt"), str(tmp_path / "shifted.txt"), env={"NB200_MODE": "1"})
     assert rc == 1 and "Binning doesn't match for GoF calculation" in err
     assert run(tool)[0] == 1
+
+
+def test_skew_gaussian_mode(tool, tmp_path):
+    """skewness = 1, the reference's default (analysis.hh:67): every S1 slice re-binned on mean +- 3 sigma and fitted with
+    rootNEST's "skewband" (:1319-1330, :1361-1440); leakage from the skew-normal CDF (:726-733)"""
+    ana = capi.analysis(0)
+    e1, e2 = write_execnest_file(tmp_path / "er.txt", 6, 400000, 2.45, -0.004, 0.16, alpha=2.0, s1max=22.0)
+    write_execnest_file(tmp_path / "nr.txt", 7, 100000, 2.2, -0.002, 0.12, s1max=22.0)
+    rc, out, err = run(tool, str(tmp_path / "er.txt"), str(tmp_path / "nr.txt"), env={"NB200_SKEWNESS": "1"})
+    assert rc == 0, err
+    nr_t = table(out, "Calculating band for first dataset")
+    er_t = table(out, "Calculating band for second dataset")
+    w1, w2 = windowed(ana, e1, e2)
+    width = (ana.maxS1 - ana.minS1) / ana.numBins
+    ok = (w1 >= 0) & (w2 >= 0)
+    lines = err.splitlines()
+    k = next(i for i, ln in enumerate(lines) if ln.startswith("#evts\tBinCen"))
+    rows = np.array([[float(v) for v in ln.split("\t")[:12]] for ln in lines[k + 1:k + 1 + ana.numBins]])
+    checked = 0
+    for i in range(2, 18):
+        lo = ana.minS1 + i * width
+        m = ok & (w1 > lo) & (w1 <= lo + width)
+        y = np.log10(w2[m] / w1[m])
+        mu, sd = y.mean(), y.std(ddof=1)
+        a, b = mu - 3 * sd, mu + 3 * sd                     # no wings: the axis stays below 2 / 3 at its ends? checked here
+        if a > 2.0 or b > 3.0:
+            a, b = a - 0.5, b + 0.5
+        h = np.histogram(y, bins=ana.logBins, range=(a, b))[0]
+        par, perr, chi = capi.hist_fit(1, h, a, b, (m.sum() * (b - a) / ana.logBins, er_t[i, 2] - 0.1, 0.17, 1.5))
+        d = par[3] / np.sqrt(1 + par[3] ** 2)
+        if perr[3] > 0.6:
+            continue                                         # a slice whose skew the fit cannot pin down: start-dependent
+        assert er_t[i, 2] == pytest.approx(par[1] + par[2] * d * np.sqrt(2 / np.pi), abs=2e-3)          # band mean
+        assert er_t[i, 4] == pytest.approx(par[2] * np.sqrt(1 - 2 * d * d / np.pi), abs=2e-3)           # band sigma
+        assert er_t[i, 6] == pytest.approx(par[3], abs=0.05) and er_t[i, 7] == pytest.approx(perr[3], rel=0.05)
+        assert er_t[i, 8] == pytest.approx(chi, rel=0.02)
+        assert 0.8 < er_t[i, 6] < 3.0                # the skew that was written (2), as 30 bins weighted by content see it
+        # leakage column = skew-normal CDF of the fitted ER slice at the NR mean
+        leak, _, _ = capi.band_leakage_skew([par[1]], [par[2]], [perr[2]], [par[3]], [nr_t[i, 2]])
+        assert rows[i, 4] == pytest.approx(leak[0], rel=0.05, abs=1e-7)
+        checked += 1
+    assert checked >= 10
+    # fewer than 20000 events: the reference's warning, and Gaussian fits (:1037-1042)
+    write_execnest_file(tmp_path / "few.txt", 8, 5000, 2.45, -0.004, 0.16)
+    rc, out, err = run(tool, str(tmp_path / "few.txt"), env={"NB200_SKEWNESS": "1"})
+    assert rc == 0 and "WARNING: Not enough stats (at least 10^5 events) for skew fits so doing Gaussian" in err
+    assert np.all(table(out)[:, 6] == 0)
 
 
 def test_on_the_reference_binary_output(tool, tmp_path):
