@@ -352,6 +352,11 @@ int nb200_band_fit_gauss(const nb200_analysis* ana, const nb200_band_hist* hist,
  * (or NULL) = the same with omega +- omega_err, the reference's "quick + dirty" error bars (:739-771). */
 int nb200_hist_fit(int model, const uint64_t* counts, int bins, double lo, double hi, const double* start, double* par,
                    double* err, double* chi2_ndf);
+/* nb200_graph_fit -- TGraph::Fit without ROOT for the two curves rootNEST puts through the NR band's means (:855-878):
+ * model 2 = the Woods function p0/(x + p1) + p2 x + p3, model 3 = its fallback p0 + (p1 - p0)/(1 + (x/p2)^p3);
+ * unweighted least squares over (x[i], y[i]), par/start[4]; *chi2_ndf = sum of squared residuals / (n - 4), the figure
+ * the reference tests against 1.5 and 2.  NB200_EFIT when no minimum was found. */
+int nb200_graph_fit(int model, int n, const double* x, const double* y, const double* start, double* par, double* chi2_ndf);
 int nb200_band_leakage_skew(int numBins, const double* xi, const double* omega, const double* omega_err,
                             const double* alpha, const double* line, double* leak, double* err_hi, double* err_lo);
 int nb200_band_leakage_gauss(int numBins, const double* er, const double* nr, double num_sig_above, double* out);

@@ -103,7 +103,7 @@ EXPORTS = [
     "nb200_synchronize", "nb200_detector_builtin", "nb200_model_default", "nb200_analysis_default",
     "nb200_prepare", "nb200_wimp_prep", "nb200_poisson", "nb200_yields", "nb200_run", "nb200_run_async",
     "nb200_band_reset", "nb200_band_attach", "nb200_fp64_peak", "nb200_timing_enable", "nb200_timing_read", "nb200_se_stats", "nb200_band_fetch", "nb200_band_device_buffer", "nb200_allreduce_hist",
-    "nb200_band_hist_bytes", "nb200_band_finalize", "nb200_band_chi2", "nb200_band_leakage", "nb200_band_fit_gauss", "nb200_band_leakage_gauss", "nb200_hist_fit", "nb200_band_leakage_skew", "nb200_lar", "nb200_launch_count",
+    "nb200_band_hist_bytes", "nb200_band_finalize", "nb200_band_chi2", "nb200_band_leakage", "nb200_band_fit_gauss", "nb200_band_leakage_gauss", "nb200_hist_fit", "nb200_graph_fit", "nb200_band_leakage_skew", "nb200_lar", "nb200_launch_count",
     "nb200_debug_hitmath", "nb200_debug_binomial", "nb200_debug_normal", "nb200_debug_binomial_fixed",
     "nb200_debug_zig_tables", "nb200_debug_alias_tables"]
 
@@ -170,6 +170,7 @@ def lib():
     L.nb200_band_fit_gauss.argtypes = [C.POINTER(Analysis), C.POINTER(BandHist), c_dp]
     L.nb200_band_leakage_gauss.argtypes = [C.c_int, c_dp, c_dp, C.c_double, c_dp]
     L.nb200_hist_fit.argtypes = [C.c_int, c_u64p, C.c_int, C.c_double, C.c_double, c_dp, c_dp, c_dp, c_dp]
+    L.nb200_graph_fit.argtypes = [C.c_int, C.c_int, c_dp, c_dp, c_dp, c_dp, c_dp]
     L.nb200_band_leakage_skew.argtypes = [C.c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]
     L.nb200_lar.argtypes = [vp, C.c_int, C.c_size_t, vp, vp, C.c_double, C.c_uint64, C.c_uint64, C.c_int,
                             vp, vp]
@@ -215,6 +216,22 @@ def hist_fit(model, counts, lo, hi, start):
     if rc:
         raise NestB200Error(rc, "nb200_hist_fit: no minimum" if rc == EFIT else "nb200_hist_fit")
     return par, err, chi.value
+
+
+def graph_fit(model, x, y, start):
+    """unweighted least squares of rootNEST's NR-centroid curves (model 2 Woods, 3 sigmoid; rootNEST.cpp:855-878);
+    returns (par[4], sum of squared residuals / (n - 4))"""
+    x = np.ascontiguousarray(x, np.float64)
+    y = np.ascontiguousarray(y, np.float64)
+    st = np.ascontiguousarray(start, np.float64)
+    if x.size != y.size or st.size != 4:
+        raise ValueError("x, y of equal length and four start values")
+    par, chi = np.zeros(4), C.c_double()
+    rc = lib().nb200_graph_fit(model, x.size, x.ctypes.data_as(c_dp), y.ctypes.data_as(c_dp), st.ctypes.data_as(c_dp),
+                               par.ctypes.data_as(c_dp), C.byref(chi))
+    if rc:
+        raise NestB200Error(rc, "nb200_graph_fit: no minimum" if rc == EFIT else "nb200_graph_fit")
+    return par, chi.value
 
 
 def band_leakage_skew(xi, omega, omega_err, alpha, line):

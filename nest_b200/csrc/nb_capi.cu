@@ -1216,8 +1216,34 @@ bool solve_n(int n, const double M[kFitMaxPar][kFitMaxPar], const double* v, dou
 // model 0: A exp(-(x - mu)^2 / (2 s^2))                                          (ROOT's "gaus";   p = A, mu, s)
 // model 1: A / (w sqrt(2 pi)) exp(-(x - xi)^2 / (2 w^2)) (1 + erf(al (x - xi) / (w sqrt 2)))
 //                                                     (rootNEST.cpp:1361-1364 "skewband"; p = A, xi, w, al)
+// model 2: p0 / (x + p1) + p2 x + p3                         (rootNEST.cpp:856-857, the Woods function through the NR means)
+// model 3: p0 + (p1 - p0) / (1 + (x / p2)^p3)                 (rootNEST.cpp:870-871, its sigmoid fallback)
 inline int model_npar(int model) { return model == 0 ? 3 : 4; }
+inline bool model_domain(int model, const double* p) {
+  if (model <= 1) return p[0] > 0. && p[2] > 0.;
+  if (model == 3) return p[2] > 0.;
+  return true;
+}
 inline double model_eval(int model, const double* p, double x, double* g) {
+  if (model == 2) {
+    if (g) {
+      g[0] = 1. / (x + p[1]);
+      g[1] = -p[0] / ((x + p[1]) * (x + p[1]));
+      g[2] = x;
+      g[3] = 1.;
+    }
+    return p[0] / (x + p[1]) + p[2] * x + p[3];
+  }
+  if (model == 3) {
+    const double u = std::pow(x / p[2], p[3]), D = 1. + u;
+    if (g) {
+      g[0] = 1. - 1. / D;
+      g[1] = 1. / D;
+      g[2] = (p[1] - p[0]) / (D * D) * u * p[3] / p[2];
+      g[3] = -(p[1] - p[0]) / (D * D) * u * std::log(x / p[2]);
+    }
+    return p[0] + (p[1] - p[0]) / D;
+  }
   const double z = (x - p[1]) / p[2], e = std::exp(-0.5 * z * z);
   if (model == 0) {
     const double f = p[0] * e;
@@ -1239,8 +1265,9 @@ inline double model_eval(int model, const double* p, double x, double* g) {
   return p[0] * G * E;
 }
 
-double hist_chi2(int model, const uint64_t* row, int lb, double x0, double w, const double* p,
-                 double JtJ[kFitMaxPar][kFitMaxPar], double* Jtr) {
+// sum of w_k (y_k - f(x_k))^2 and, on request, J^T W J and J^T W r
+double points_chi2(int model, int npts, const double* xs, const double* ys, const double* ws, const double* p,
+                   double JtJ[kFitMaxPar][kFitMaxPar], double* Jtr) {
   const int n = model_npar(model);
   double chi = 0., g[kFitMaxPar];
   if (JtJ)
@@ -1248,42 +1275,38 @@ double hist_chi2(int model, const uint64_t* row, int lb, double x0, double w, co
       Jtr[i] = 0.;
       for (int j = 0; j < n; ++j) JtJ[i][j] = 0.;
     }
-  for (int k = 0; k < lb; ++k) {
-    if (!row[k]) continue;
-    const double h = double(row[k]), x = x0 + (double(k) + 0.5) * w;
-    const double r = h - model_eval(model, p, x, JtJ ? g : nullptr);
-    chi += r * r / h;
+  for (int k = 0; k < npts; ++k) {
+    const double r = ys[k] - model_eval(model, p, xs[k], JtJ ? g : nullptr);
+    chi += ws[k] * r * r;
     if (JtJ)
       for (int i = 0; i < n; ++i) {
-        Jtr[i] += g[i] * r / h;
-        for (int j = 0; j < n; ++j) JtJ[i][j] += g[i] * g[j] / h;
+        Jtr[i] += ws[k] * g[i] * r;
+        for (int j = 0; j < n; ++j) JtJ[i][j] += ws[k] * g[i] * g[j];
       }
   }
   return chi;
 }
 
-// returns the number of histogram bins used, 0 when there are too few or no minimum was found
-int fit_hist_row(int model, const uint64_t* row, int lb, double x0, double w, double* p, double* err, double* chi2) {
+// Levenberg-Marquardt on weighted points; false when there are too few points or no minimum was found
+bool fit_points(int model, int npts, const double* xs, const double* ys, const double* ws, double* p, double* err, double* chi2) {
   const int n = model_npar(model);
-  int used = 0;
-  for (int k = 0; k < lb; ++k) used += row[k] != 0;
-  if (used <= n || !(p[2] > 0.) || !(p[0] > 0.)) return 0;
+  if (npts <= n || !model_domain(model, p)) return false;
   double JtJ[kFitMaxPar][kFitMaxPar], Jtr[kFitMaxPar], lambda = 1e-3;
-  double chi = hist_chi2(model, row, lb, x0, w, p, JtJ, Jtr);
-  if (!std::isfinite(chi)) return 0;
-  for (int it = 0; it < 500; ++it) {
+  double chi = points_chi2(model, npts, xs, ys, ws, p, JtJ, Jtr);
+  if (!std::isfinite(chi)) return false;
+  for (int it = 0; it < 1000; ++it) {
     double M[kFitMaxPar][kFitMaxPar], step[kFitMaxPar], q[kFitMaxPar];
     for (int i = 0; i < n; ++i)
       for (int j = 0; j < n; ++j) M[i][j] = JtJ[i][j] * (i == j ? 1. + lambda : 1.);
-    if (!solve_n(n, M, Jtr, step)) return 0;
+    if (!solve_n(n, M, Jtr, step)) return false;
     for (int i = 0; i < n; ++i) q[i] = p[i] + step[i];
-    double trial = (q[2] > 0. && q[0] > 0.) ? hist_chi2(model, row, lb, x0, w, q, nullptr, nullptr) : INFINITY;
+    double trial = model_domain(model, q) ? points_chi2(model, npts, xs, ys, ws, q, nullptr, nullptr) : INFINITY;
     if (!std::isfinite(trial)) trial = INFINITY;
     if (trial <= chi) {
       bool done = chi - trial <= 1e-13 * chi;
-      for (int i = 1; i < n; ++i) done = done && std::fabs(step[i]) <= 1e-9 * (i == 3 ? 1. + std::fabs(p[3]) : p[2]);
+      for (int i = 0; i < n; ++i) done = done && std::fabs(step[i]) <= 1e-9 * (std::fabs(p[i]) + (model <= 1 ? p[2] : 1e-3));
       for (int i = 0; i < n; ++i) p[i] = q[i];
-      chi = hist_chi2(model, row, lb, x0, w, p, JtJ, Jtr);
+      chi = points_chi2(model, npts, xs, ys, ws, p, JtJ, Jtr);
       lambda = lambda > 1e-12 ? lambda * 0.1 : lambda;
       if (done) break;
     } else {
@@ -1295,11 +1318,28 @@ int fit_hist_row(int model, const uint64_t* row, int lb, double x0, double w, do
   for (int i = 0; i < n; ++i) {
     double unit[kFitMaxPar] = {0., 0., 0., 0.}, col[kFitMaxPar];
     unit[i] = 1.;
-    if (!solve_n(n, JtJ, unit, col) || !(col[i] > 0.)) return 0;
+    if (!solve_n(n, JtJ, unit, col) || !(col[i] > 0.)) {
+      if (model <= 1) return false;
+      col[i] = 0.;  // a curve with a flat direction (a straight line has no Woods pole): the minimum stands, the error does not
+    }
     err[i] = std::sqrt(col[i]);
   }
   *chi2 = chi;
-  return used;
+  return true;
+}
+
+// a histogram row as weighted points: bin centres, contents, weights 1/content, empty bins left out (TH1::Fit's default
+// chi^2); returns the number of bins used, 0 when there are too few or no minimum was found
+int fit_hist_row(int model, const uint64_t* row, int lb, double x0, double w, double* p, double* err, double* chi2) {
+  std::vector<double> xs, ys, ws;
+  for (int k = 0; k < lb; ++k) {
+    if (!row[k]) continue;
+    xs.push_back(x0 + (double(k) + 0.5) * w);
+    ys.push_back(double(row[k]));
+    ws.push_back(1. / double(row[k]));
+  }
+  if (!fit_points(model, int(xs.size()), xs.data(), ys.data(), ws.data(), p, err, chi2)) return 0;
+  return int(xs.size());
 }
 
 // rootNEST.cpp:1587-1602: Owen's T by the reference's own midpoint rule (2500 steps), so that leakages agree digit for digit
@@ -1397,6 +1437,19 @@ int nb200_hist_fit(int model, const uint64_t* counts, int bins, double lo, doubl
     err[i] = e[i];
   }
   if (chi2_ndf) *chi2_ndf = chi / double(used - n);
+  return 0;
+}
+
+// TGraph::Fit without ROOT for the two curves rootNEST puts through the NR band's means (rootNEST.cpp:855-878): unweighted
+// least squares, so "chi^2 / NDF" is the mean squared residual the reference tests against 1.5 and 2
+int nb200_graph_fit(int model, int n, const double* x, const double* y, const double* start, double* par, double* chi2_ndf) {
+  if (!x || !y || !start || !par || n < 1 || (model != 2 && model != 3)) return NB200_EINVAL;
+  std::vector<double> ws(size_t(n), 1.);
+  double p[kFitMaxPar], e[kFitMaxPar], chi = 0.;
+  for (int i = 0; i < 4; ++i) p[i] = start[i];
+  if (!fit_points(model, n, x, y, ws.data(), p, e, &chi)) return NB200_EFIT;
+  for (int i = 0; i < 4; ++i) par[i] = p[i];
+  if (chi2_ndf) *chi2_ndf = chi / double(n - 4);
   return 0;
 }
 

@@ -5,10 +5,10 @@
 //                                                :668-950 -- examples/leakage.sh runs unchanged)
 //   NB200_MODE=1 rootNEST_b200 NESTOutput.txt dataBand.txt   goodness of fit against a data band (mode 1; :587-666)
 //
-// with the analysis.hh settings skewness = 1 (skew-Gaussian fits, the reference's default; NB200_SKEWNESS=0 for
-// Gaussian fits) and NRbandCenter = 1 (the fitted mean of each S1 bin is the NR centroid; the reference's default,
-// a Woods-function fit through the NR means, is not included, nor are skewness = 2's MINOS-style covariances or
-// modes 2 and 3, the WIMP limits).  Inputs are execNEST's 12-column stdout (src/execNEST.cpp:1386-1405), read as GetFile does
+// with the reference's analysis.hh defaults: skewness = 1 (skew-Gaussian fits; NB200_SKEWNESS=0 for Gaussian fits)
+// and NRbandCenter = 3 (the NR centroid is a Woods-function curve through the per-bin means, evaluated at each
+// event's S1; NB200_NRBANDCENTER=1 or 2 for the other two choices).  Not included: skewness = 2's covariance
+// propagation, medians (negative NRbandCenter), modes 2 and 3 (the WIMP limits).  Inputs are execNEST's 12-column stdout (src/execNEST.cpp:1386-1405), read as GetFile does
 // (:955-1036); per-bin statistics, Gaussian fits and leakage come from the library's host-side band functions
 // (include/nest_b200.h: nb200_band_finalize, nb200_band_fit_gauss, nb200_hist_fit, nb200_band_leakage_gauss / _skew).  Nothing here
 // simulates anything: no device is needed or used.
@@ -28,6 +28,7 @@ namespace {
 NEST::Analysis A;
 const int freeParam = 2;       // analysis.hh:65
 int skewness = 1;              // analysis.hh:67
+int NRbandCenter = 3;          // analysis.hh:76: 1 the bin's mean, 3 a curve through the means, 2 the curve at the bin centre
 const double NUMSIGABV = -0.;  // rootNEST.cpp:39
 
 struct BandOfFile {
@@ -275,12 +276,46 @@ int leakage_table(const char* file1, const char* file2) {  // :668-950
       lk[4 * size_t(i) + 3] = fabs(leak[i] - lo[i]);
     }
   }
+  // the NR line as a smooth curve through the per-bin means (:855-878): the Woods function, else a sigmoid, else the means
+  vector<double> gx, gy;
+  const vector<double>& nrMom = ERis2nd ? B.mom : B2.mom;
+  for (int i = 0; i < nb; ++i)
+    if (nr[8 * size_t(i) + 7] > 0.) {  // bins whose fit exists (the reference would feed the graph its empty bins too)
+      gx.push_back(nrMom[7 * size_t(i)]);
+      gy.push_back(nr[8 * size_t(i) + 1] + NUMSIGABV * nr[8 * size_t(i) + 2]);
+    }
+  int curve = 0;  // 0: none (bin means), 2: Woods, 3: sigmoid
+  double cp[4] = {0., 0., 0., 0.}, chi2 = 0.;
+  if (NRbandCenter != 1) {
+    const double woods0[4] = {10., 15., -1.5e-3, 2.}, sig0[4] = {0.5, 3., 1e2, 0.4};
+    if (!nb200_graph_fit(2, int(gx.size()), gx.data(), gy.data(), woods0, cp, &chi2) && !(chi2 > 1.5 || chi2 <= 0. || std::isnan(chi2)))
+      curve = 2;
+    else {
+      if (A.verbosity > 0)
+        cerr << "WARNING: Poor fit to NR Gaussian band centroids i.e. means of log(S2) or log(S2/S1) histograms in S1 bins. "
+                "Investigate please!"
+             << endl;
+      if (!nb200_graph_fit(3, int(gx.size()), gx.data(), gy.data(), sig0, cp, &chi2) && !(chi2 > 2. || chi2 < 0. || std::isnan(chi2)))
+        curve = 3;  // (the reference then evaluates the Woods formula with these parameters, :883-886; the fitted curve is used here)
+      else if (A.verbosity > 0)
+        cerr << "ERROR: Even the backup plan to use sigmoid failed as well!" << endl;
+    }
+  }
+  auto line_at = [&](double x) {
+    return curve == 2 ? cp[0] / (x + cp[1]) + cp[2] * x + cp[3] : cp[0] + (cp[1] - cp[0]) / (1. + pow(x / cp[2], cp[3]));
+  };
   double finalSums[3] = {0., 0., 0.};
   for (int i = 0; i < nb; ++i) {
-    // counting (:880-915, NRbandCenter = 1): the second dataset's events below the NR line of this bin
-    const double centroid = nr[8 * size_t(i) + 1] + NUMSIGABV * nr[8 * size_t(i) + 2];
+    // counting (:880-915): the second dataset's events below the NR line -- at the event's own S1 (NRbandCenter = 3), at
+    // the bin centre (2), or the NR mean of the bin (1, or when both curve fits failed)
+    const double binMean = nr[8 * size_t(i) + 1] + NUMSIGABV * nr[8 * size_t(i) + 2];
     uint64_t below = 0;
-    for (double y : B.outputs[i]) below += y < centroid;
+    for (size_t j = 0; j < B.outputs[i].size(); ++j) {
+      double centroid = binMean;
+      if (curve && NRbandCenter == 3) centroid = line_at(B.inputs[i][j]);
+      if (curve && NRbandCenter == 2) centroid = line_at(nrMom[7 * size_t(i)]);
+      below += B.outputs[i][j] < centroid;
+    }
     const double N = double(B.outputs[i].size());
     const double leakTotal = double(below) / N;
     const double poisHi = (double(below) + sqrt(double(below))) / (N - sqrt(N));
@@ -318,6 +353,8 @@ int main(int argc, char** argv) {
   if (const char* v = getenv("NB200_VERBOSITY")) A.verbosity = atoi(v);
   if (const char* v = getenv("NB200_LOGBINS")) A.logBins = atoi(v);
   if (const char* v = getenv("NB200_SKEWNESS")) skewness = atoi(v) ? 1 : 0;
+  if (const char* v = getenv("NB200_NRBANDCENTER")) NRbandCenter = abs(atoi(v));
+  if (NRbandCenter != 1 && NRbandCenter != 2 && NRbandCenter != 3) NRbandCenter = 3;  // :101-103
   const int mode = getenv("NB200_MODE") ? atoi(getenv("NB200_MODE")) : 0;
   if (argc < 2) {  // :104-119
     cout << endl << "This program takes 1 (or 2) inputs." << endl << endl;

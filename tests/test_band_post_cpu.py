@@ -303,3 +303,30 @@ def test_skew_leakage_is_the_skew_normal_cdf(built):
     g, _, _ = capi.band_leakage_skew(xi, om, om_err, np.zeros(n), line)
     from scipy.special import erf
     np.testing.assert_allclose(g, 0.5 * (1 + erf((line - xi) / om / np.sqrt(2))), atol=1e-15)
+
+
+def test_graph_fit_matches_least_squares(built):
+    """nb200_graph_fit (TGraph::Fit's unweighted least squares for rootNEST's NR-centroid curves, rootNEST.cpp:855-878)
+    against scipy from the reference's own start values"""
+    from scipy.optimize import curve_fit
+    rng = np.random.default_rng(3)
+    x = 2.0 + np.arange(98.0)
+    woods = lambda x, a, b, c, d: a / (x + b) + c * x + d
+    y = woods(x, 8.0, 12.0, -2.0e-3, 1.9) + rng.normal(0, 0.004, x.size)
+    par, chi = capi.graph_fit(2, x, y, (10., 15., -1.5e-3, 2.))              # SetParameters(10., 15., -1.5e-3, 2.), :858
+    popt, _ = curve_fit(woods, x, y, p0=(10., 15., -1.5e-3, 2.), xtol=1e-14, ftol=1e-14, gtol=1e-14)
+    np.testing.assert_allclose(woods(x, *par), woods(x, *popt), atol=1e-7)   # the curve; the parameters are strongly correlated
+    np.testing.assert_allclose(par, popt, rtol=2e-3)
+    assert chi == pytest.approx(((y - woods(x, *par)) ** 2).sum() / (x.size - 4), rel=1e-9)
+    assert chi < 1.5                                                         # the reference's acceptance test (:863)
+    sig = lambda x, a, b, c, d: a + (b - a) / (1 + (x / c) ** d)
+    y = sig(x, 0.6, 2.9, 90.0, 0.45) + rng.normal(0, 0.004, x.size)
+    par, chi = capi.graph_fit(3, x, y, (0.5, 3., 1e2, 0.4))                  # SetParameters(0.5, 3., 1e2, 0.4), :872
+    popt, _ = curve_fit(sig, x, y, p0=(0.5, 3., 1e2, 0.4), xtol=1e-14, ftol=1e-14, gtol=1e-14, maxfev=20000)
+    np.testing.assert_allclose(sig(x, *par), sig(x, *popt), atol=1e-6)
+    assert chi == pytest.approx(((y - sig(x, *par)) ** 2).sum() / (x.size - 4), rel=1e-9)
+    with pytest.raises(capi.NestB200Error) as e:
+        capi.graph_fit(2, x[:4], y[:4], (10., 15., -1.5e-3, 2.))             # four points, four parameters
+    assert e.value.code == capi.EFIT
+    with pytest.raises(capi.NestB200Error):
+        capi.graph_fit(0, x, y, (1., 1., 1., 1.))

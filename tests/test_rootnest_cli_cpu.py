@@ -25,7 +25,8 @@ def tool(built):
 
 def run(tool, *args, env=None):
     e = dict(os.environ)
-    e["NB200_SKEWNESS"] = "0"                 # Gaussian fits unless a test asks for the reference's default
+    e["NB200_SKEWNESS"] = "0"                 # Gaussian fits and per-bin NR means unless a test asks for the reference's defaults
+    e["NB200_NRBANDCENTER"] = "1"
     e.update(env or {})
     r = subprocess.run([tool] + list(args), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=e, timeout=300)
     return r.returncode, r.stdout, r.stderr
@@ -141,6 +142,34 @@ def test_leakage_table(tool, tmp_path):
     assert 0.45 < float(overall.split("Leakage Fraction = ")[1]) < 0.55
 
 
+def test_leakage_below_a_curve_through_the_nr_means(tool, tmp_path):
+    """NRbandCenter = 3 (the reference's default, analysis.hh:76) and 2: the Woods function fitted through the NR means
+    (rootNEST.cpp:855-862), evaluated at each event's S1 (:883-886) or at the bin centre (:890-893)"""
+    ana = capi.analysis(0)
+    e1, e2 = write_execnest_file(tmp_path / "er.txt", 12, 150000, 2.6, -0.006, 0.11, s1max=40.0)
+    write_execnest_file(tmp_path / "nr.txt", 13, 80000, 2.3, -0.003, 0.12, s1max=40.0)
+    w1, w2 = windowed(ana, e1, e2)
+    ok = (w1 >= 0) & (w2 >= 0) & (w1 > ana.minS1) & (w1 <= ana.maxS1)
+    y = np.log10(w2[ok] / w1[ok])
+    width = (ana.maxS1 - ana.minS1) / ana.numBins
+    results = {}
+    for center in ("1", "2", "3"):
+        rc, out, err = run(tool, str(tmp_path / "er.txt"), str(tmp_path / "nr.txt"), env={"NB200_NRBANDCENTER": center})
+        assert rc == 0 and "Poor fit" not in err, err
+        nr_t = table(out, "Calculating band for first dataset")
+        overall = [ln for ln in err.splitlines() if ln.startswith("OVERALL DISCRIMINATION (ER)")][0]
+        results[center] = float(overall.split("Leakage Fraction = ")[1])
+    good = nr_t[:, 4] > 0
+    par, chi = capi.graph_fit(2, nr_t[good, 0], nr_t[good, 2], (10., 15., -1.5e-3, 2.))
+    assert chi < 1.5
+    woods = lambda x: par[0] / (x + par[1]) + par[2] * x + par[3]
+    assert results["3"] == pytest.approx((y < woods(w1[ok])).mean(), rel=0.01, abs=2e-5)
+    centre = ana.minS1 + (np.floor((w1[ok] - ana.minS1) / width - 1e-12) + 0.5) * width
+    assert results["2"] == pytest.approx((y < woods(centre)).mean(), rel=0.02, abs=3e-5)
+    # the three definitions of the line agree on the overall leakage to within tens of per cent, not digit for digit
+    assert 0.5 < results["3"] / results["1"] < 1.5 and results["3"] != results["1"]
+
+
 def test_goodness_of_fit_mode(tool, tmp_path):
     ana = capi.analysis(0)
     # S1 below 25 keeps the band clear of the S2 window; 120 log bins so that a bin is a fraction of the band's sigma
@@ -236,7 +265,8 @@ def test_on_the_reference_binary_output(tool, tmp_path):
                        ("nr.txt", ["40000", "NR", "0", "60", "180", "-1", "2"])):
         with open(tmp_path / name, "w") as f:
             subprocess.run([refprobe.REF_BIN_LUX] + args, stdout=f, stderr=subprocess.DEVNULL, check=True, timeout=300)
-    rc, out, err = run(tool, str(tmp_path / "er.txt"), str(tmp_path / "nr.txt"))
+    # with the reference's defaults: skew-Gaussian fits, Woods curve through the NR means
+    rc, out, err = run(tool, str(tmp_path / "er.txt"), str(tmp_path / "nr.txt"), env={"NB200_SKEWNESS": "1", "NB200_NRBANDCENTER": "3"})
     assert rc == 0, err
     overall = [ln for ln in err.splitlines() if ln.startswith("OVERALL DISCRIMINATION (ER)")][0]
     leak = float(overall.split("Leakage Fraction = ")[1])
