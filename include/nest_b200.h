@@ -276,6 +276,16 @@ int nb200_yields(nb200_ctx* ctx, const nb200_detector* det, const nb200_model* m
                  int species, size_t n, const double* E, const double* field,
                  double density, int mem_kind, double* out);
 
+/* Fluctuated quanta on the device: replaces NESTcalc::GetQuanta (NEST.cpp:248-432) for n independent yield records --
+ * the stage call behind FullCalculation (NEST.cpp:17-40) and bareNEST.cpp:186.  yields [6][n] as nb200_yields writes
+ * them; quanta [4][n] int32 = photons, electrons, ions, excitons; prob_var [2][n] = recombProb, Variance
+ * (QuantaResult, NEST.hh:171-178).  model->NRERWidthsParam / n_widths / SkewnessER are the call's NRERWidthsParam and
+ * SkewnessER arguments.  Record i draws from Philox(seed; event first_event + i): results do not depend on how a
+ * list is split over calls.  NB200_EPHYSICS where the reference throws (fewer than 13 width parameters, quanta not
+ * conserved).  Pointers are of kind mem_kind. */
+int nb200_quanta(nb200_ctx* ctx, const nb200_detector* det, const nb200_model* model, size_t n, const double* yields,
+                 double density, uint64_t seed, uint64_t first_event, int mem_kind, int32_t* quanta, double* prob_var);
+
 /* The per-event chain: replaces the loop body of execNEST() (execNEST.cpp:676-1414)
  * and of runNESTvec() (:357-406) for event ids [first_event, first_event+n).
  * soa and hist may each be NULL.  hist is ACCUMULATED into (caller zeroes it). */

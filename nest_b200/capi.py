@@ -101,7 +101,7 @@ class BandHist(C.Structure):
 EXPORTS = [
     "nb200_abi_version", "nb200_sizeof", "nb200_create", "nb200_destroy", "nb200_last_error", "nb200_set_stream",
     "nb200_synchronize", "nb200_detector_builtin", "nb200_model_default", "nb200_analysis_default",
-    "nb200_prepare", "nb200_wimp_prep", "nb200_poisson", "nb200_yields", "nb200_run", "nb200_run_async",
+    "nb200_prepare", "nb200_wimp_prep", "nb200_poisson", "nb200_yields", "nb200_quanta", "nb200_run", "nb200_run_async",
     "nb200_band_reset", "nb200_band_attach", "nb200_fp64_peak", "nb200_timing_enable", "nb200_timing_read", "nb200_se_stats", "nb200_band_fetch", "nb200_band_device_buffer", "nb200_allreduce_hist",
     "nb200_band_hist_bytes", "nb200_band_finalize", "nb200_band_chi2", "nb200_band_leakage", "nb200_band_fit_gauss", "nb200_band_leakage_gauss", "nb200_hist_fit", "nb200_graph_fit", "nb200_band_leakage_skew", "nb200_lar", "nb200_launch_count",
     "nb200_debug_hitmath", "nb200_debug_binomial", "nb200_debug_normal", "nb200_debug_binomial_fixed",
@@ -149,6 +149,8 @@ def lib():
     L.nb200_poisson.restype = C.c_uint64
     L.nb200_yields.argtypes = [vp, C.POINTER(Detector), C.POINTER(Model), C.c_int, C.c_size_t, vp, vp,
                                C.c_double, C.c_int, vp]
+    L.nb200_quanta.argtypes = [vp, C.POINTER(Detector), C.POINTER(Model), C.c_size_t, vp, C.c_double, C.c_uint64,
+                               C.c_uint64, C.c_int, vp, vp]
     run_args = [vp, C.POINTER(Detector), C.POINTER(Model), C.POINTER(Analysis), C.POINTER(Source),
                 C.POINTER(RunConsts), C.c_uint64, C.c_uint64, C.c_uint64]
     L.nb200_run.argtypes = run_args + [C.POINTER(SoaOut), C.POINTER(BandHist)]
@@ -397,6 +399,18 @@ class Context:
         self._check(lib().nb200_yields(self.h, C.byref(det), C.byref(mo), species, E.size, _dptr(E), _dptr(F),
                                        density, MEM_HOST, _dptr(out)))
         return out
+
+    def quanta(self, det, mo, yields, density, seed, first_event=0):
+        """GetQuanta on the device for yield records [6][n] (as `yields` returns them) -> (int32 [4][n] photons,
+        electrons, ions, excitons; float64 [2][n] recombProb, Variance)"""
+        y = np.ascontiguousarray(yields, np.float64)
+        if y.ndim != 2 or y.shape[0] != 6:
+            raise ValueError("yields must be [6][n]")
+        n = y.shape[1]
+        qi, qd = np.zeros((4, n), np.int32), np.zeros((2, n))
+        self._check(lib().nb200_quanta(self.h, C.byref(det), C.byref(mo), n, _dptr(y), density, seed, first_event,
+                                       MEM_HOST, _dptr(qi), _dptr(qd)))
+        return qi, qd
 
     def run(self, det, mo, ana, src, rc, seed, n, first_event=0, columns=None, band=None):
         """nb200_run with host outputs. columns: names from SOA_COLUMNS (None = all)."""

@@ -789,6 +789,61 @@ int nb200_yields(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo,
   return rc;
 }
 
+int nb200_quanta(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo, size_t n, const double* yields,
+                 double density, uint64_t seed, uint64_t first_event, int mem_kind, int32_t* quanta, double* prob_var) {
+  if (!c) return NB200_EINVAL;
+  if (!det || !mo || !yields || !quanta || !prob_var) return fail(c, NB200_EINVAL, "null argument");
+  if (mo->n_widths < 13)  // NEST.cpp:258-262
+    return fail(c, NB200_EPHYSICS, "ERROR: You need a minimum of 13 free parameters for the resolution model.");
+  if (n == 0) return 0;
+  NB_CUDA(c, cudaSetDevice(c->device));
+  QuantaParams P;
+  std::memset(&P, 0, sizeof P);
+  P.det = *det;
+  P.model = *mo;
+  P.density = density;
+  P.n = n;
+  P.seed = seed;
+  P.first_event = first_event;
+  std::vector<void*> fr;
+  auto cleanup = [&]() {
+    for (void* q : fr) cudaFree(q);
+  };
+  double *dY = nullptr, *dD = nullptr;
+  int32_t* dI = nullptr;
+  if (mem_kind == NB200_MEM_HOST) {
+    cudaError_t e = cudaMalloc(&dY, n * 48);
+    if (e == cudaSuccess) { fr.push_back(dY); e = cudaMalloc(&dI, n * 16); }
+    if (e == cudaSuccess) { fr.push_back(dI); e = cudaMalloc(&dD, n * 16); }
+    if (e == cudaSuccess) { fr.push_back(dD); e = cudaMemcpyAsync(dY, yields, n * 48, cudaMemcpyHostToDevice, c->stream); }
+    if (e != cudaSuccess) {
+      cleanup();
+      return fail(c, NB200_ENOMEM, cudaGetErrorString(e));
+    }
+    P.y = dY;
+    P.qi = dI;
+    P.qd = dD;
+  } else {
+    P.y = yields;
+    P.qi = quanta;
+    P.qd = prob_var;
+  }
+  unsigned grid = unsigned(std::min<uint64_t>((n + 255) / 256, uint64_t(c->sm_count) * 8));
+  k_quanta<<<grid, 256, 0, c->stream>>>(P, c->d_err);
+  cudaError_t le = cudaGetLastError();
+  ++c->launches;
+  int rc = 0;
+  if (le != cudaSuccess) rc = fail(c, NB200_ECUDA, std::string("k_quanta: ") + cudaGetErrorString(le));
+  if (!rc && mem_kind == NB200_MEM_HOST) {
+    cudaError_t e = cudaMemcpyAsync(quanta, dI, n * 16, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(prob_var, dD, n * 16, cudaMemcpyDeviceToHost, c->stream);
+    if (e != cudaSuccess) rc = fail(c, NB200_ECUDA, cudaGetErrorString(e));
+  }
+  if (!rc) rc = check_device_error(c);  // synchronises; "Quanta not conserved" -> NB200_EPHYSICS
+  cleanup();
+  return rc;
+}
+
 // ---- the chain ---------------------------------------------------------------------------
 
 size_t nb200_band_hist_bytes(const nb200_analysis* a) { return a ? band_word_count(a) * 8 : 0; }

@@ -801,6 +801,45 @@ __global__ void __launch_bounds__(256) k_binomial_fixed(uint64_t seed, uint64_t 
 }
 
 // -------------------------------------------------------------------------------------------
+// k_quanta: NESTcalc::GetQuanta (NEST.cpp:248-432) for n independent yield records -- the stage call of the
+// reference's per-event API (FullCalculation NEST.cpp:17-40, bareNEST.cpp:186), one thread per record.
+// y: 6 columns of n as k_yields writes them; qi: 4 int columns (photons, electrons, ions, excitons); qd: 2
+// double columns (recombProb, Variance).  Record i draws from the Philox streams of event first_event + i.
+struct QuantaParams {
+  nb200_detector det;
+  nb200_model model;
+  double density;
+  uint64_t n, seed, first_event;
+  const double* y;
+  int32_t* qi;
+  double* qd;
+};
+
+__global__ void __launch_bounds__(256) k_quanta(const __grid_constant__ QuantaParams P, int* err_flag) {
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < P.n;
+       i += uint64_t(gridDim.x) * blockDim.x) {
+    Yields y;
+    y.Nph = P.y[i];
+    y.Ne = P.y[P.n + i];
+    y.NexONi = P.y[2 * P.n + i];
+    y.L = P.y[3 * P.n + i];
+    y.field = P.y[4 * P.n + i];
+    y.dT = P.y[5 * P.n + i];
+    const uint64_t ev = P.first_event + i;
+    Stream g;
+    g.init(P.seed, ev, STREAM_MAIN);
+    int err = 0;
+    const Quanta q = get_quanta(g, P.seed, ev, y, P.density, P.det, P.model, &err);
+    if (err) atomicOr(err_flag, err);
+    P.qi[i] = q.photons;
+    P.qi[P.n + i] = q.electrons;
+    P.qi[2 * P.n + i] = q.ions;
+    P.qi[3 * P.n + i] = q.excitons;
+    P.qd[i] = q.recombProb;
+    P.qd[P.n + i] = q.Variance;
+  }
+}
+
 // k_lar: LArNEST::FullCalculation (src/LArNEST.cpp:17-33) for species NR/ER/Alpha
 // -------------------------------------------------------------------------------------------
 struct LArParams {

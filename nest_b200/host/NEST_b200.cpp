@@ -168,6 +168,50 @@ YieldResult NESTcalc::GetYields(INTERACTION_TYPE species, double energy, double 
                    NRYieldsParam, ERYieldsParam)[0];
 }
 
+// ---- GetQuanta / FullCalculation: NEST.cpp:248-432, 17-40 ----------------------------------------------
+vector<QuantaResult> NESTcalc::GetQuanta(const vector<YieldResult>& yields, double density,
+                                         const vector<double>& NRERWidthsParam, double SkewnessER) {
+  nb200_model m;
+  fill_model(&m, default_NRYieldsParam, default_ERYieldsParam, NRERWidthsParam);  // throws below 13 widths, as NEST.cpp:258-262
+  m.er_model = -1;
+  m.SkewnessER = SkewnessER;
+  const size_t n = yields.size();
+  vector<QuantaResult> r(n);
+  if (n == 0) return r;
+  vector<double> y(6 * n), qd(2 * n);
+  vector<int32_t> qi(4 * n);
+  for (size_t i = 0; i < n; ++i) {
+    y[i] = yields[i].PhotonYield;
+    y[n + i] = yields[i].ElectronYield;
+    y[2 * n + i] = yields[i].ExcitonRatio;
+    y[3 * n + i] = yields[i].Lindhard;
+    y[4 * n + i] = yields[i].ElectricField;
+    y[5 * n + i] = yields[i].DeltaT_Scint;
+  }
+  Device::check(nb200_quanta(Device::get(), &flat(), &m, n, y.data(), density, call_seed, call_index, NB200_MEM_HOST,
+                             qi.data(), qd.data()));
+  call_index += n;
+  for (size_t i = 0; i < n; ++i)
+    r[i] = QuantaResult{qi[i], qi[n + i], qi[2 * n + i], qi[3 * n + i], qd[i], qd[n + i]};
+  return r;
+}
+QuantaResult NESTcalc::GetQuanta(const YieldResult& yields, double density, const vector<double>& NRERWidthsParam,
+                                 double SkewnessER) {
+  return GetQuanta(vector<YieldResult>{yields}, density, NRERWidthsParam, SkewnessER)[0];
+}
+NESTresult NESTcalc::FullCalculation(INTERACTION_TYPE species, double energy, double density, double dfield, double A,
+                                     double Z, const vector<double>& NRYieldsParam, const vector<double>& NRERWidthsParam,
+                                     const vector<double>& ERYieldsParam, bool do_times) {
+  if (do_times)
+    throw runtime_error("FullCalculation: photon times are outside the GPU path (nest-b200 DESIGN.md, scope); pass do_times = false");
+  if (density < 1.) fdetector->set_inGas(true);  // NEST.cpp:25
+  NESTresult result;
+  result.yields = GetYields(species, energy, density, dfield, A, Z, NRYieldsParam, ERYieldsParam);
+  result.quanta = GetQuanta(result.yields, density, NRERWidthsParam, -999.);
+  result.photon_times = photonstream(size_t(result.quanta.photons), 0.0);
+  return result;
+}
+
 // ---- runNESTvec: execNEST.cpp:329-409 ----------------------------------------------------------------
 NESTObservableArray runNESTvec(VDetector* detector, INTERACTION_TYPE particleType, vector<double> eList,
                                vector<vector<double>> pos3dxyz, double inField, int seed,

@@ -160,6 +160,17 @@ struct YieldResult {
   double PhotonYield, ElectronYield, ExcitonRatio, Lindhard, ElectricField, DeltaT_Scint;
 };
 
+struct QuantaResult {  // NEST.hh:171-178
+  int photons, electrons, ions, excitons;
+  double recombProb, Variance;
+};
+typedef std::vector<double> photonstream;
+struct NESTresult {  // NEST.hh:182-186
+  YieldResult yields;
+  QuantaResult quanta;
+  photonstream photon_times;
+};
+
 // analysis.hh's compile-time globals as a runtime object (include/NEST/analysis.hh:7-77)
 struct Analysis {
   int verbosity = 1;
@@ -212,6 +223,23 @@ class NESTcalc {
                                      const std::vector<double>& NRYieldsParam = default_NRYieldsParam,
                                      const std::vector<double>& ERYieldsParam = default_ERYieldsParam);
 
+  // NEST.cpp:248-432 on the device.  The reference draws from its process-wide RandomGen; here call number k of this
+  // object draws from the Philox streams of event k under the seed given to SetSeed (default 0), so a sequence of
+  // calls is reproducible and the vector form equals the same calls made one by one.
+  QuantaResult GetQuanta(const YieldResult& yields, double density,
+                         const std::vector<double>& NRERWidthsParam = default_NRERWidthsParam, double SkewnessER = -999.);
+  std::vector<QuantaResult> GetQuanta(const std::vector<YieldResult>& yields, double density,
+                                      const std::vector<double>& NRERWidthsParam = default_NRERWidthsParam,
+                                      double SkewnessER = -999.);
+  // NEST.cpp:17-40.  Photon times (do_times = true, the reference's default) are outside the GPU path: they are refused
+  // with std::runtime_error rather than returned as zeros; with do_times = false photon_times is photons x 0.0 as in
+  // the reference.
+  NESTresult FullCalculation(INTERACTION_TYPE species, double energy, double density, double dfield, double A, double Z,
+                             const std::vector<double>& NRYieldsParam = default_NRYieldsParam,
+                             const std::vector<double>& NRERWidthsParam = default_NRERWidthsParam,
+                             const std::vector<double>& ERYieldsParam = default_ERYieldsParam, bool do_times = true);
+  void SetSeed(uint64_t seed) { call_seed = seed; call_index = 0; }  // RandomGen::rndm()->SetSeed
+
   const nb200_detector& flat();   // the detector flattened for the device (maps tabulated on first use)
   const nb200_run_consts& prepared(double inField, double z_step = 0.);
   VDetector* detector() const { return fdetector; }
@@ -225,6 +253,7 @@ class NESTcalc {
   bool flattened = false;
   nb200_run_consts rc{};
   double rc_field = -12345.;
+  uint64_t call_seed = 0, call_index = 0;
 };
 
 }  // namespace NEST

@@ -61,6 +61,14 @@ class Probe:
         self._f("maps")(*self._d(), C.c_int(x.size), _p(x), _p(y), _p(z), *[_p(a) for a in o])
         return o
 
+    def quanta(self, seed, n, y6, rho, widths, skewER):
+        """n GetQuanta draws on one fixed YieldResult -> (int [n][4] Nph, Ne, Ni, Nex; float [n][2] recombProb, Variance)"""
+        y, w = _arr(y6), _arr(widths)
+        io, do = np.zeros((n, 4), np.int32), np.zeros((n, 2))
+        self._f("quanta")(*self._d(), C.c_uint64(seed), C.c_int(n), _p(y), C.c_double(rho), _p(w), C.c_int(w.size),
+                          C.c_double(skewER), _p(io), _p(do))
+        return io, do
+
     def sampler(self, kind, seed, n, p0=0.0, p1=0.0, p2=0.0):
         out = np.zeros(n)
         self._f("sampler")(C.c_int(kind), C.c_uint64(seed), C.c_int(n), C.c_double(p0), C.c_double(p1),

@@ -1,0 +1,96 @@
+"""The per-event stage call GetQuanta (reference src/NEST.cpp:248-432; FullCalculation :17-40, bareNEST.cpp:186)
+through the C-ABI (nb200_quanta -> k_quanta) against the unmodified reference: n draws on fixed YieldResults,
+every QuantaResult field compared -- recombProb to 1e-12 (it is deterministic given the yields), the integer
+quanta and Variance as distributions -- plus conservation, independence of how a list is split over calls,
+and the reference's error for fewer than 13 width parameters."""
+import numpy as np
+import pytest
+from scipy import stats
+
+from helpers import RHO_LUX
+from nest_b200 import capi
+
+pytestmark = pytest.mark.gpu
+
+# YieldResults of the reference at 180 V/cm: {Nph, Ne, NexONi, Lindhard, field, DeltaT_Scint}
+RECORDS = {
+    "beta 5 keV": ([205.88604645954106, 165.20770456738973, 0.050298182684348262, 1.0, 180.0, -999.0], 0.0),
+    "beta 5 keV, LUX skew model": ([205.88604645954106, 165.20770456738973, 0.050298182684348262, 1.0, 180.0, -999.0], -999.0),
+    "beta 0.5 keV": ([0.64889386770322943, 36.460481234989849, 0.0051337477773812801, 1.0, 180.0, -999.0], 0.0),
+    "gamma 41.5 keV": ([2255.6704922630879, 824.40764126043757, 0.18141640390708169, 1.0, 180.0, -999.0], 0.0),
+    "NR 10 keV": ([80.68553759012174, 57.878421270493256, 0.81936822679002697, 0.18669670194818133, 180.0, -999.0], 0.0),
+    "NR 0.3 keV": ([0.88939281415746496, 1.1501592836462304, 0.76402647275054425, 0.091600936068923555, 180.0, -999.0], 0.0),
+    "alpha 5.3 MeV": ([368873.82323330763, 5269.1361310607754, 0.0053475469399098521, 0.91499960874930175, 180.0, -999.0], 0.0),
+}
+
+
+@pytest.mark.parametrize("name", list(RECORDS))
+def test_quanta_stage_matches_reference(ctx, ref, name):
+    y6, skew = RECORDS[name]
+    n = 20000
+    det = capi.detector("LUX_Run03")
+    capi.prepare(det, 180.0)
+    mo = capi.model(1)                       # the CLI's width parameters (execNEST.cpp:188-204)
+    mo.SkewnessER = skew
+    widths = list(mo.NRERWidthsParam)[:mo.n_widths]
+    qi, qd = ctx.quanta(det, mo, np.tile(np.array(y6)[:, None], (1, n)), RHO_LUX, seed=11)
+    ri, rd = ref.quanta(12, n, y6, RHO_LUX, widths, skew)
+    # conservation (the reference throws otherwise, NEST.cpp:421-424) and the clamps
+    assert np.all(qi[0] + qi[1] == qi[2] + qi[3])
+    assert np.all(qi >= 0) and np.all(qi[1] <= qi[2]) and np.all(qi[0] >= qi[3])
+    # recombProb is a function of the yields alone wherever quanta were made
+    made = qd[0] != 0
+    rmade = rd[:, 0] != 0
+    assert abs(made.mean() - rmade.mean()) < 5 * np.sqrt(0.25 / n) + 1e-12
+    if made.any():
+        assert np.unique(qd[0][made]).size == 1 and np.unique(rd[rmade, 0]).size == 1
+        assert qd[0][made][0] == pytest.approx(rd[rmade, 0][0], rel=1e-12)
+    for k, col in enumerate(("photons", "electrons", "ions", "excitons")):
+        a, b = qi[k].astype(float), ri[:, k].astype(float)
+        if np.all(a == a[0]) and np.all(b == b[0]):
+            assert a[0] == b[0], col
+            continue
+        assert stats.ks_2samp(a, b).pvalue > 1e-4, (name, col, a.mean(), b.mean())
+        se = np.sqrt(a.var() / n + b.var() / n)
+        assert abs(a.mean() - b.mean()) < 5 * se + 1e-9, (name, col, a.mean(), b.mean())
+    a, b = qd[1], rd[:, 1]
+    if not (np.all(a == a[0]) and np.all(b == b[0])):
+        assert stats.ks_2samp(a, b).pvalue > 1e-4, (name, "Variance", a.mean(), b.mean())
+    # Variance = lambda r (1 - r) Ni + omega^2 Ni^2 (:354-355) is a function of Ni alone for fixed yields: wherever the two
+    # sides drew the same Ni they must report the same Variance
+    lut = {int(a): b for a, b in zip(ri[rmade, 2], rd[rmade, 1])}
+    pairs = [(qd[1][i], lut[int(qi[2][i])]) for i in np.nonzero(made)[0] if int(qi[2][i]) in lut]
+    assert len(pairs) > 0.5 * made.sum()
+    assert max(abs(a - b) / b for a, b in pairs) < 1e-10
+
+
+def test_quanta_stage_does_not_depend_on_batching(ctx):
+    det = capi.detector("LUX_Run03")
+    capi.prepare(det, 180.0)
+    mo = capi.model(1)
+    mo.massNum, mo.er_model = 131.293, 0
+    E = np.linspace(0.2, 60.0, 5000)
+    y = ctx.yields(det, mo, capi.beta, E, 180.0, RHO_LUX)
+    mo.er_model = -1
+    whole_i, whole_d = ctx.quanta(det, mo, y, RHO_LUX, seed=3)
+    a_i, a_d = ctx.quanta(det, mo, y[:, :1234], RHO_LUX, seed=3)
+    b_i, b_d = ctx.quanta(det, mo, y[:, 1234:], RHO_LUX, seed=3, first_event=1234)
+    assert np.array_equal(np.concatenate([a_i, b_i], axis=1), whole_i)
+    assert np.array_equal(np.concatenate([a_d, b_d], axis=1), whole_d)
+    other_i, _ = ctx.quanta(det, mo, y, RHO_LUX, seed=4)
+    assert not np.array_equal(other_i, whole_i)
+    # mean quanta follow the mean yields
+    assert abs((whole_i[0] + whole_i[1]).mean() / (y[0] + y[1]).mean() - 1) < 0.01
+
+
+def test_quanta_stage_errors(ctx):
+    det = capi.detector("LUX_Run03")
+    capi.prepare(det, 180.0)
+    mo = capi.model(1)
+    mo.n_widths = 12                          # NEST.cpp:258-262: "You need a minimum of 13 free parameters ..."
+    y = np.tile(np.array(RECORDS["beta 5 keV"][0])[:, None], (1, 4))
+    with pytest.raises(capi.NestB200Error) as e:
+        ctx.quanta(det, mo, y, RHO_LUX, seed=1)
+    assert e.value.code == capi.EPHYSICS and "13 free parameters" in str(e.value)
+    with pytest.raises(ValueError):
+        ctx.quanta(det, capi.model(1), y[:5], RHO_LUX, seed=1)
