@@ -286,6 +286,16 @@ int nb200_yields(nb200_ctx* ctx, const nb200_detector* det, const nb200_model* m
 int nb200_quanta(nb200_ctx* ctx, const nb200_detector* det, const nb200_model* model, size_t n, const double* yields,
                  double density, uint64_t seed, uint64_t first_event, int mem_kind, int32_t* quanta, double* prob_var);
 
+/* S2 on the device as a stage call: replaces NESTcalc::GetS2, S2CalculationMode::Full (NEST.cpp:1724-1776, 1975-2063;
+ * bareNEST.cpp:210) for n independent records.  Ne [n] int32 = electrons leaving the interaction site; pos [5][n] =
+ * truth x, y, z and smeared x, y [mm]; dt [n] drift time [us]; field [n] drift field [V/cm] (below 1 V/cm, or a g2
+ * parameter <= 0, gives nine zeros as in the reference, :1746-1750); rc = nb200_prepare's constants (g2_params).
+ * out [9][n] = ionization[0..8]: Nee, Nph, nHits, Nphe, area, areaC, phd, phdC (bottom-array values for s2_thr < 0;
+ * negated below |s2_thr|), g2.  Record i draws from Philox(seed; event first_event + i). */
+int nb200_s2(nb200_ctx* ctx, const nb200_detector* det, const nb200_run_consts* rc, size_t n, const int32_t* Ne,
+             const double* pos, const double* dt, const double* field, uint64_t seed, uint64_t first_event,
+             int mem_kind, double* out);
+
 /* The per-event chain: replaces the loop body of execNEST() (execNEST.cpp:676-1414)
  * and of runNESTvec() (:357-406) for event ids [first_event, first_event+n).
  * soa and hist may each be NULL.  hist is ACCUMULATED into (caller zeroes it). */

@@ -101,7 +101,7 @@ class BandHist(C.Structure):
 EXPORTS = [
     "nb200_abi_version", "nb200_sizeof", "nb200_create", "nb200_destroy", "nb200_last_error", "nb200_set_stream",
     "nb200_synchronize", "nb200_detector_builtin", "nb200_model_default", "nb200_analysis_default",
-    "nb200_prepare", "nb200_wimp_prep", "nb200_poisson", "nb200_yields", "nb200_quanta", "nb200_run", "nb200_run_async",
+    "nb200_prepare", "nb200_wimp_prep", "nb200_poisson", "nb200_yields", "nb200_quanta", "nb200_s2", "nb200_run", "nb200_run_async",
     "nb200_band_reset", "nb200_band_attach", "nb200_fp64_peak", "nb200_timing_enable", "nb200_timing_read", "nb200_se_stats", "nb200_band_fetch", "nb200_band_device_buffer", "nb200_allreduce_hist",
     "nb200_band_hist_bytes", "nb200_band_finalize", "nb200_band_chi2", "nb200_band_leakage", "nb200_band_fit_gauss", "nb200_band_leakage_gauss", "nb200_hist_fit", "nb200_graph_fit", "nb200_band_leakage_skew", "nb200_lar", "nb200_launch_count",
     "nb200_debug_hitmath", "nb200_debug_binomial", "nb200_debug_normal", "nb200_debug_binomial_fixed",
@@ -151,6 +151,8 @@ def lib():
                                C.c_double, C.c_int, vp]
     L.nb200_quanta.argtypes = [vp, C.POINTER(Detector), C.POINTER(Model), C.c_size_t, vp, C.c_double, C.c_uint64,
                                C.c_uint64, C.c_int, vp, vp]
+    L.nb200_s2.argtypes = [vp, C.POINTER(Detector), C.POINTER(RunConsts), C.c_size_t, vp, vp, vp, vp, C.c_uint64,
+                           C.c_uint64, C.c_int, vp]
     run_args = [vp, C.POINTER(Detector), C.POINTER(Model), C.POINTER(Analysis), C.POINTER(Source),
                 C.POINTER(RunConsts), C.c_uint64, C.c_uint64, C.c_uint64]
     L.nb200_run.argtypes = run_args + [C.POINTER(SoaOut), C.POINTER(BandHist)]
@@ -411,6 +413,21 @@ class Context:
         self._check(lib().nb200_quanta(self.h, C.byref(det), C.byref(mo), n, _dptr(y), density, seed, first_event,
                                        MEM_HOST, _dptr(qi), _dptr(qd)))
         return qi, qd
+
+    def s2(self, det, rc, Ne, pos, dt, field, seed, first_event=0):
+        """GetS2 (Full) on the device for n records: Ne [n], pos [5][n] (truth x, y, z, smeared x, y), dt [n], field
+        (scalar or [n]) -> ionization [9][n]"""
+        Ne = np.ascontiguousarray(Ne, np.int32)
+        n = Ne.size
+        pos = np.ascontiguousarray(pos, np.float64)
+        if pos.shape != (5, n):
+            raise ValueError("pos must be [5][n]")
+        dt = np.ascontiguousarray(np.broadcast_to(dt, (n,)), np.float64)
+        F = np.ascontiguousarray(np.broadcast_to(field, (n,)), np.float64)
+        out = np.zeros((9, n))
+        self._check(lib().nb200_s2(self.h, C.byref(det), C.byref(rc), n, _dptr(Ne), _dptr(pos), _dptr(dt), _dptr(F), seed,
+                                   first_event, MEM_HOST, _dptr(out)))
+        return out
 
     def run(self, det, mo, ana, src, rc, seed, n, first_event=0, columns=None, band=None):
         """nb200_run with host outputs. columns: names from SOA_COLUMNS (None = all)."""

@@ -844,6 +844,78 @@ int nb200_quanta(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo,
   return rc;
 }
 
+int nb200_s2(nb200_ctx* c, const nb200_detector* det, const nb200_run_consts* rc, size_t n, const int32_t* Ne,
+             const double* pos, const double* dt, const double* field, uint64_t seed, uint64_t first_event, int mem_kind,
+             double* out) {
+  if (!c) return NB200_EINVAL;
+  if (!det || !rc || !Ne || !pos || !dt || !field || !out) return fail(c, NB200_EINVAL, "null argument");
+  if (n == 0) return 0;
+  NB_CUDA(c, cudaSetDevice(c->device));
+  // the per-run constants of the chain (map centre, alias tables of the second photo-electrons, round keys): the source
+  // and the model are not used by GetS2
+  nb200_model mo;
+  nb200_model_default(1, &mo);
+  nb200_analysis ana;
+  nb200_analysis_default(0, &ana);
+  nb200_source src;
+  std::memset(&src, 0, sizeof src);
+  src.kind = NB200_SRC_FLAT;
+  src.species = NB200_NR;
+  src.eMin = 1.;
+  src.eMax = 2.;
+  src.inField = 180.;
+  RunParams P;
+  int rc_ = build_params(c, det, &mo, &ana, &src, rc, seed, first_event, n, &P);
+  if (rc_) return rc_;
+  S2Args a;
+  a.n = n;
+  std::vector<void*> fr;
+  auto cleanup = [&]() {
+    for (void* q : fr) cudaFree(q);
+  };
+  if (mem_kind == NB200_MEM_HOST) {
+    int32_t* dN = nullptr;
+    double *dP = nullptr, *dT = nullptr, *dF = nullptr, *dO = nullptr;
+    cudaError_t e = cudaMalloc(&dN, n * 4);
+    if (e == cudaSuccess) { fr.push_back(dN); e = cudaMalloc(&dP, n * 40); }
+    if (e == cudaSuccess) { fr.push_back(dP); e = cudaMalloc(&dT, n * 8); }
+    if (e == cudaSuccess) { fr.push_back(dT); e = cudaMalloc(&dF, n * 8); }
+    if (e == cudaSuccess) { fr.push_back(dF); e = cudaMalloc(&dO, n * 72); }
+    if (e == cudaSuccess) { fr.push_back(dO); e = cudaMemcpyAsync(dN, Ne, n * 4, cudaMemcpyHostToDevice, c->stream); }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dP, pos, n * 40, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dT, dt, n * 8, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dF, field, n * 8, cudaMemcpyHostToDevice, c->stream);
+    if (e != cudaSuccess) {
+      cleanup();
+      return fail(c, NB200_ENOMEM, cudaGetErrorString(e));
+    }
+    a.Ne = dN;
+    a.pos = dP;
+    a.dt = dT;
+    a.field = dF;
+    a.out = dO;
+  } else {
+    a.Ne = Ne;
+    a.pos = pos;
+    a.dt = dt;
+    a.field = field;
+    a.out = out;
+  }
+  unsigned grid = unsigned(std::min<uint64_t>((n + 255) / 256, uint64_t(c->sm_count) * 8));
+  k_s2<<<grid, 256, 0, c->stream>>>(P, a);
+  cudaError_t le = cudaGetLastError();
+  ++c->launches;
+  int r = 0;
+  if (le != cudaSuccess) r = fail(c, NB200_ECUDA, std::string("k_s2: ") + cudaGetErrorString(le));
+  if (!r && mem_kind == NB200_MEM_HOST) {
+    cudaError_t e = cudaMemcpyAsync(out, a.out, n * 72, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) r = fail(c, NB200_ECUDA, cudaGetErrorString(e));
+  }
+  cleanup();
+  return r;
+}
+
 // ---- the chain ---------------------------------------------------------------------------
 
 size_t nb200_band_hist_bytes(const nb200_analysis* a) { return a ? band_word_count(a) * 8 : 0; }

@@ -840,6 +840,29 @@ __global__ void __launch_bounds__(256) k_quanta(const __grid_constant__ QuantaPa
   }
 }
 
+// k_s2: NESTcalc::GetS2, S2CalculationMode::Full (NEST.cpp:1724-1776, 1975-2063) for n independent records -- the
+// stage call of the reference's per-event API (bareNEST.cpp:210), one thread per record, the same device function
+// k_post calls.  pos: 5 columns of n (truth x, y, z, smeared x, y); out: 9 columns of n (ionization[0..8]).
+struct S2Args {
+  uint64_t n;
+  const int32_t* Ne;
+  const double *pos, *dt, *field;
+  double* out;
+};
+
+__global__ void __launch_bounds__(256) k_s2(const __grid_constant__ RunParams P, const S2Args a) {
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < a.n; i += uint64_t(gridDim.x) * blockDim.x) {
+    const uint64_t ev = P.first_event + i;
+    Stream g;
+    g.init(P.seed, ev, STREAM_POST);
+    double o[9];
+    get_s2(g, ev, P, a.Ne[i], a.pos[i], a.pos[a.n + i], a.pos[2 * a.n + i], a.pos[3 * a.n + i], a.pos[4 * a.n + i], a.dt[i],
+           a.field[i], o);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) a.out[k * a.n + i] = o[k];
+  }
+}
+
 // k_lar: LArNEST::FullCalculation (src/LArNEST.cpp:17-33) for species NR/ER/Alpha
 // -------------------------------------------------------------------------------------------
 struct LArParams {

@@ -212,6 +212,43 @@ NESTresult NESTcalc::FullCalculation(INTERACTION_TYPE species, double energy, do
   return result;
 }
 
+// ---- GetS2: NEST.cpp:1724-2063 (Full) --------------------------------------------------------------------
+vector<vector<double>> NESTcalc::GetS2(const vector<int>& Ne, const vector<vector<double>>& truthPos,
+                                       const vector<vector<double>>& smearPos, const vector<double>& dt, uint64_t firstEvt,
+                                       double dfield, const vector<double>& g2_params) {
+  const size_t n = Ne.size();
+  if (truthPos.size() != n || smearPos.size() != n || dt.size() != n) throw runtime_error("GetS2: lists differ in length");
+  if (g2_params.size() < 5) throw runtime_error("GetS2: g2_params needs five values (CalculateG2)");
+  vector<vector<double>> r(n, vector<double>(9, 0.));
+  if (n == 0) return r;
+  nb200_run_consts c = prepared(dfield >= 1. ? dfield : 180.);
+  for (int k = 0; k < 5; ++k) c.g2_params[k] = g2_params[k];
+  vector<int32_t> ne(Ne.begin(), Ne.end());
+  vector<double> pos(5 * n), f(n, dfield), out(9 * n);
+  for (size_t i = 0; i < n; ++i) {
+    if (truthPos[i].size() < 3 || smearPos[i].size() < 2) throw runtime_error("GetS2: a position needs x, y, z");
+    pos[i] = truthPos[i][0];
+    pos[n + i] = truthPos[i][1];
+    pos[2 * n + i] = truthPos[i][2];
+    pos[3 * n + i] = smearPos[i][0];
+    pos[4 * n + i] = smearPos[i][1];
+  }
+  Device::check(nb200_s2(Device::get(), &flat(), &c, n, ne.data(), pos.data(), dt.data(), f.data(), call_seed, firstEvt,
+                         NB200_MEM_HOST, out.data()));
+  for (size_t i = 0; i < n; ++i)
+    for (int k = 0; k < 9; ++k) r[i][k] = out[size_t(k) * n + i];
+  return r;
+}
+const vector<double>& NESTcalc::GetS2(int Ne, double truthPosX, double truthPosY, double truthPosZ, double smearPosX,
+                                      double smearPosY, double smearPosZ, double dt, double, uint64_t evtNum, double dfield,
+                                      S2CalculationMode mode, int, vector<int64_t>&, vector<double>&,
+                                      const vector<double>& g2_params) {
+  if (mode != S2CalculationMode::Full) throw runtime_error("GetS2: the Waveform modes are outside the GPU path");
+  ionization = GetS2(vector<int>{Ne}, {{truthPosX, truthPosY, truthPosZ}}, {{smearPosX, smearPosY, smearPosZ}},
+                     vector<double>{dt}, evtNum, dfield, g2_params)[0];
+  return ionization;
+}
+
 // ---- runNESTvec: execNEST.cpp:329-409 ----------------------------------------------------------------
 NESTObservableArray runNESTvec(VDetector* detector, INTERACTION_TYPE particleType, vector<double> eList,
                                vector<vector<double>> pos3dxyz, double inField, int seed,

@@ -238,6 +238,16 @@ class NESTcalc {
                              const std::vector<double>& NRYieldsParam = default_NRYieldsParam,
                              const std::vector<double>& NRERWidthsParam = default_NRERWidthsParam,
                              const std::vector<double>& ERYieldsParam = default_ERYieldsParam, bool do_times = true);
+  // NEST.cpp:1724-2063, S2CalculationMode::Full, on the device (NEST.hh:351-356: the result is member scratch, valid
+  // until the next call).  evtNum selects the Philox streams (seed from SetSeed); the Waveform modes are refused.
+  const std::vector<double>& GetS2(int Ne, double truthPosX, double truthPosY, double truthPosZ, double smearPosX,
+                                   double smearPosY, double smearPosZ, double dt, double driftSpeed, uint64_t evtNum,
+                                   double dfield, S2CalculationMode mode, int outputTiming, std::vector<int64_t>& wf_time,
+                                   std::vector<double>& wf_amp, const std::vector<double>& g2_params);
+  // the same for n records at once: rows of nine (ionization[0..8]); record i uses event number firstEvt + i
+  std::vector<std::vector<double>> GetS2(const std::vector<int>& Ne, const std::vector<std::vector<double>>& truthPos,
+                                         const std::vector<std::vector<double>>& smearPos, const std::vector<double>& dt,
+                                         uint64_t firstEvt, double dfield, const std::vector<double>& g2_params);
   void SetSeed(uint64_t seed) { call_seed = seed; call_index = 0; }  // RandomGen::rndm()->SetSeed
 
   const nb200_detector& flat();   // the detector flattened for the device (maps tabulated on first use)
@@ -254,6 +264,7 @@ class NESTcalc {
   nb200_run_consts rc{};
   double rc_field = -12345.;
   uint64_t call_seed = 0, call_index = 0;
+  std::vector<double> ionization = std::vector<double>(9, 0.);
 };
 
 }  // namespace NEST

@@ -69,6 +69,14 @@ class Probe:
                           C.c_double(skewER), _p(io), _p(do))
         return io, do
 
+    def s2(self, seed, n, Ne, pos, spos, dt, vD, field):
+        """n GetS2 (Full) draws on fixed electrons / positions / drift time -> ionization [n][9]"""
+        p, sp = _arr(pos), _arr(spos)
+        out = np.zeros((n, 9))
+        self._f("s2")(*self._d(), C.c_uint64(seed), C.c_int(n), C.c_int(Ne), _p(p), _p(sp), C.c_double(dt), C.c_double(vD),
+                      C.c_double(field), _p(out))
+        return out
+
     def sampler(self, kind, seed, n, p0=0.0, p1=0.0, p2=0.0):
         out = np.zeros(n)
         self._f("sampler")(C.c_int(kind), C.c_uint64(seed), C.c_int(n), C.c_double(p0), C.c_double(p1),

@@ -94,3 +94,59 @@ def test_quanta_stage_errors(ctx):
     assert e.value.code == capi.EPHYSICS and "13 free parameters" in str(e.value)
     with pytest.raises(ValueError):
         ctx.quanta(det, capi.model(1), y[:5], RHO_LUX, seed=1)
+
+
+# GetS2 on fixed inputs: (electrons, truth xyz, smeared xyz, drift time [us], field [V/cm])
+S2_CASES = {
+    "165 e-": (165, (50., -30., 250.), (52., -28., 250.), 150.0, 180.0),
+    "5 e-": (5, (0., 0., 300.), (0., 0., 300.), 100.0, 180.0),
+    "4000 e- near the wall, long drift": (4000, (120., 80., 100.), (118., 83., 100.), 300.0, 180.0),
+    "no electrons": (0, (10., 10., 200.), (10., 10., 200.), 120.0, 180.0),
+    "no field": (300, (10., 10., 200.), (10., 10., 200.), 120.0, 0.5),
+}
+
+
+@pytest.mark.parametrize("name", list(S2_CASES))
+def test_s2_stage_matches_reference(ctx, ref, name):
+    """NESTcalc::GetS2 Full (NEST.cpp:1724-2063; bareNEST.cpp:210) through nb200_s2 -> k_s2, all nine ionization[]
+    values against the unmodified reference on the same fixed inputs"""
+    Ne, pos, spos, dt, field = S2_CASES[name]
+    n = 20000
+    det = capi.detector("LUX_Run03")
+    rc = capi.prepare(det, 180.0)
+    p5 = np.tile(np.array([pos[0], pos[1], pos[2], spos[0], spos[1]])[:, None], (1, n))
+    got = ctx.s2(det, rc, np.full(n, Ne), p5, dt, field, seed=21)
+    exp = ref.s2(22, n, Ne, pos, spos, dt, rc.vD, field).T
+    names = ["Nee", "Nph", "nHits", "Nphe", "area", "areaC", "phd", "phdC", "g2"]
+    for k, col in enumerate(names):
+        a, b = got[k], exp[k]
+        if np.all(a == a[0]) and np.all(b == b[0]):
+            assert a[0] == pytest.approx(b[0], rel=1e-12, abs=0), (name, col, a[0], b[0])
+            continue
+        assert stats.ks_2samp(a, b).pvalue > 1e-4, (name, col, a.mean(), b.mean())
+        se = np.sqrt(a.var() / n + b.var() / n)
+        assert abs(a.mean() - b.mean()) < 5 * se + 1e-9, (name, col, a.mean(), b.mean())
+    # the sign flag (below |s2_thr|: the first eight negated, NEST.cpp:2051-2057) at the same rate
+    assert abs((got[4] < 0).mean() - (exp[4] < 0).mean()) < 5 * np.sqrt(0.25 / n) + 1e-12
+
+
+def test_s2_stage_does_not_depend_on_batching(ctx):
+    det = capi.detector("LUX_Run03")
+    rc = capi.prepare(det, 180.0)
+    rng = np.random.default_rng(1)
+    n = 6000
+    Ne = rng.integers(0, 3000, n)
+    r, phi = 200 * np.sqrt(rng.uniform(0, 1, n)), rng.uniform(0, 2 * np.pi, n)
+    z = rng.uniform(50, 500, n)
+    pos = np.array([r * np.cos(phi), r * np.sin(phi), z, r * np.cos(phi) + 1.0, r * np.sin(phi) - 1.0])
+    dt = (det.TopDrift - z) / rc.vD
+    whole = ctx.s2(det, rc, Ne, pos, dt, 180.0, seed=5)
+    a = ctx.s2(det, rc, Ne[:2500], np.ascontiguousarray(pos[:, :2500]), dt[:2500], 180.0, seed=5)
+    b = ctx.s2(det, rc, Ne[2500:], np.ascontiguousarray(pos[:, 2500:]), dt[2500:], 180.0, seed=5, first_event=2500)
+    assert np.array_equal(np.concatenate([a, b], axis=1), whole)
+    assert not np.array_equal(ctx.s2(det, rc, Ne, pos, dt, 180.0, seed=6), whole)
+    # extracted electrons follow the lifetime and the extraction efficiency (NEST.cpp:1775)
+    expect = (Ne * rc.g2_params[1] * np.exp(-dt / det.eLife_us)).sum()
+    assert abs(np.abs(whole[0]).sum() / expect - 1) < 0.01
+    with pytest.raises(ValueError):
+        ctx.s2(det, rc, Ne, pos[:4], dt, 180.0, seed=5)
