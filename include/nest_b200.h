@@ -296,6 +296,16 @@ int nb200_s2(nb200_ctx* ctx, const nb200_detector* det, const nb200_run_consts* 
              const double* pos, const double* dt, const double* field, uint64_t seed, uint64_t first_event,
              int mem_kind, double* out);
 
+/* S1 on the device as a stage call: replaces NESTcalc::GetS1 (NEST.cpp:1288-1722; bareNEST.cpp:203) for n independent
+ * records in the Full, Parametric or Hybrid mode (s1mode = NB200_S1_*; Hybrid: Full below 100 keV).  Nph [n] int32 =
+ * quanta.photons; pos [6][n] = truth x, y, z and smeared x, y, z [mm]; energy [n] keV (the Hybrid switch); rc =
+ * nb200_prepare's constants (vD_middle fixes the map centre z_c).  out [9][n] = scintillation[0..8]: nHits, Nphe,
+ * area, areaC, phd, phdC, spike, spikeC, spike count (sign conventions of :1689-1716).  Three launches per 4.2e6
+ * records: prelude, the hit kernel of the chain, epilogue.  Record i draws from Philox(seed; event first_event + i). */
+int nb200_s1(nb200_ctx* ctx, const nb200_detector* det, const nb200_run_consts* rc, int s1mode, size_t n,
+             const int32_t* Nph, const double* pos, const double* energy, uint64_t seed, uint64_t first_event,
+             int mem_kind, double* out);
+
 /* The per-event chain: replaces the loop body of execNEST() (execNEST.cpp:676-1414)
  * and of runNESTvec() (:357-406) for event ids [first_event, first_event+n).
  * soa and hist may each be NULL.  hist is ACCUMULATED into (caller zeroes it). */

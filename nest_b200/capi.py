@@ -101,7 +101,7 @@ class BandHist(C.Structure):
 EXPORTS = [
     "nb200_abi_version", "nb200_sizeof", "nb200_create", "nb200_destroy", "nb200_last_error", "nb200_set_stream",
     "nb200_synchronize", "nb200_detector_builtin", "nb200_model_default", "nb200_analysis_default",
-    "nb200_prepare", "nb200_wimp_prep", "nb200_poisson", "nb200_yields", "nb200_quanta", "nb200_s2", "nb200_run", "nb200_run_async",
+    "nb200_prepare", "nb200_wimp_prep", "nb200_poisson", "nb200_yields", "nb200_quanta", "nb200_s2", "nb200_s1", "nb200_run", "nb200_run_async",
     "nb200_band_reset", "nb200_band_attach", "nb200_fp64_peak", "nb200_timing_enable", "nb200_timing_read", "nb200_se_stats", "nb200_band_fetch", "nb200_band_device_buffer", "nb200_allreduce_hist",
     "nb200_band_hist_bytes", "nb200_band_finalize", "nb200_band_chi2", "nb200_band_leakage", "nb200_band_fit_gauss", "nb200_band_leakage_gauss", "nb200_hist_fit", "nb200_graph_fit", "nb200_band_leakage_skew", "nb200_lar", "nb200_launch_count",
     "nb200_debug_hitmath", "nb200_debug_binomial", "nb200_debug_normal", "nb200_debug_binomial_fixed",
@@ -152,6 +152,8 @@ def lib():
     L.nb200_quanta.argtypes = [vp, C.POINTER(Detector), C.POINTER(Model), C.c_size_t, vp, C.c_double, C.c_uint64,
                                C.c_uint64, C.c_int, vp, vp]
     L.nb200_s2.argtypes = [vp, C.POINTER(Detector), C.POINTER(RunConsts), C.c_size_t, vp, vp, vp, vp, C.c_uint64,
+                           C.c_uint64, C.c_int, vp]
+    L.nb200_s1.argtypes = [vp, C.POINTER(Detector), C.POINTER(RunConsts), C.c_int, C.c_size_t, vp, vp, vp, C.c_uint64,
                            C.c_uint64, C.c_int, vp]
     run_args = [vp, C.POINTER(Detector), C.POINTER(Model), C.POINTER(Analysis), C.POINTER(Source),
                 C.POINTER(RunConsts), C.c_uint64, C.c_uint64, C.c_uint64]
@@ -426,6 +428,21 @@ class Context:
         F = np.ascontiguousarray(np.broadcast_to(field, (n,)), np.float64)
         out = np.zeros((9, n))
         self._check(lib().nb200_s2(self.h, C.byref(det), C.byref(rc), n, _dptr(Ne), _dptr(pos), _dptr(dt), _dptr(F), seed,
+                                   first_event, MEM_HOST, _dptr(out)))
+        return out
+
+    def s1(self, det, rc, Nph, pos, energy, seed, first_event=0, mode=None):
+        """GetS1 on the device for n records: Nph [n], pos [6][n] (truth x, y, z, smeared x, y, z), energy (scalar or
+        [n]), mode = S1 calculation mode (default Hybrid) -> scintillation [9][n]"""
+        Nph = np.ascontiguousarray(Nph, np.int32)
+        n = Nph.size
+        pos = np.ascontiguousarray(pos, np.float64)
+        if pos.shape != (6, n):
+            raise ValueError("pos must be [6][n]")
+        E = np.ascontiguousarray(np.broadcast_to(energy, (n,)), np.float64)
+        out = np.zeros((9, n))
+        m = analysis(0).s1mode if mode is None else mode
+        self._check(lib().nb200_s1(self.h, C.byref(det), C.byref(rc), m, n, _dptr(Nph), _dptr(pos), _dptr(E), seed,
                                    first_event, MEM_HOST, _dptr(out)))
         return out
 

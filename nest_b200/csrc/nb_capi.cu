@@ -339,6 +339,19 @@ int ensure_workspace(nb200_ctx* c, uint64_t n, Work* w) {
   return 0;
 }
 
+// once per context: opt-in shared-memory sizes and resident blocks per SM of the chain kernels
+int ensure_occupancy(nb200_ctx* c) {
+  if (!c->occ_pre) {
+    NB_CUDA(c, cudaFuncSetAttribute(k_post, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    NB_CUDA(c, cudaFuncSetAttribute(k_hits, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kHitDynSmem)));
+    NB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_pre, k_pre, kPreBlock, 0));
+    NB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_hits, k_hits, kHitBlock, kHitDynSmem));
+    if (c->occ_pre < 1) c->occ_pre = 1;
+    if (c->occ_hits < 1) c->occ_hits = 1;
+  }
+  return 0;
+}
+
 // k_pre -> k_hits -> k_post over the call's events in chunks of the workspace size
 int launch_event(nb200_ctx* c, RunParams& P) {
   if (P.n_events == 0) return 0;
@@ -351,14 +364,8 @@ int launch_event(nb200_ctx* c, RunParams& P) {
     else
       smem = 0;
   }
-  if (!c->occ_pre) {
-    NB_CUDA(c, cudaFuncSetAttribute(k_post, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    NB_CUDA(c, cudaFuncSetAttribute(k_hits, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kHitDynSmem)));
-    NB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_pre, k_pre, kPreBlock, 0));
-    NB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_hits, k_hits, kHitBlock, kHitDynSmem));
-    if (c->occ_pre < 1) c->occ_pre = 1;
-    if (c->occ_hits < 1) c->occ_hits = 1;
-  }
+  int ro = ensure_occupancy(c);
+  if (ro) return ro;
   NB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_post, k_post, kPostBlock, smem));
   if (c->occ_post < 1) c->occ_post = 1;
   int r = ensure_workspace(c, P.n_events, &P.work);
@@ -907,6 +914,86 @@ int nb200_s2(nb200_ctx* c, const nb200_detector* det, const nb200_run_consts* rc
   ++c->launches;
   int r = 0;
   if (le != cudaSuccess) r = fail(c, NB200_ECUDA, std::string("k_s2: ") + cudaGetErrorString(le));
+  if (!r && mem_kind == NB200_MEM_HOST) {
+    cudaError_t e = cudaMemcpyAsync(out, a.out, n * 72, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) r = fail(c, NB200_ECUDA, cudaGetErrorString(e));
+  }
+  cleanup();
+  return r;
+}
+
+int nb200_s1(nb200_ctx* c, const nb200_detector* det, const nb200_run_consts* rc, int s1mode, size_t n, const int32_t* Nph,
+             const double* pos, const double* energy, uint64_t seed, uint64_t first_event, int mem_kind, double* out) {
+  if (!c) return NB200_EINVAL;
+  if (!det || !rc || !Nph || !pos || !energy || !out) return fail(c, NB200_EINVAL, "null argument");
+  if (n == 0) return 0;
+  NB_CUDA(c, cudaSetDevice(c->device));
+  nb200_model mo;
+  nb200_model_default(1, &mo);
+  nb200_analysis ana;
+  nb200_analysis_default(0, &ana);
+  ana.s1mode = s1mode;  // validated below: Full, Parametric or Hybrid (the Waveform mode is not part of this path)
+  nb200_source src;
+  std::memset(&src, 0, sizeof src);
+  src.kind = NB200_SRC_FLAT;
+  src.species = NB200_NR;
+  src.eMin = 1.;
+  src.eMax = 2.;
+  src.inField = 180.;
+  RunParams P;
+  int r = build_params(c, det, &mo, &ana, &src, rc, seed, first_event, n, &P);
+  if (r) return r;
+  if ((r = ensure_occupancy(c))) return r;
+  if ((r = ensure_workspace(c, n, &P.work))) return r;
+  S1Args a;
+  a.stride = n;
+  a.off = 0;
+  std::vector<void*> fr;
+  auto cleanup = [&]() {
+    for (void* q : fr) cudaFree(q);
+  };
+  if (mem_kind == NB200_MEM_HOST) {
+    int32_t* dN = nullptr;
+    double *dP = nullptr, *dE = nullptr, *dO = nullptr;
+    cudaError_t e = cudaMalloc(&dN, n * 4);
+    if (e == cudaSuccess) { fr.push_back(dN); e = cudaMalloc(&dP, n * 48); }
+    if (e == cudaSuccess) { fr.push_back(dP); e = cudaMalloc(&dE, n * 8); }
+    if (e == cudaSuccess) { fr.push_back(dE); e = cudaMalloc(&dO, n * 72); }
+    if (e == cudaSuccess) { fr.push_back(dO); e = cudaMemcpyAsync(dN, Nph, n * 4, cudaMemcpyHostToDevice, c->stream); }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dP, pos, n * 48, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dE, energy, n * 8, cudaMemcpyHostToDevice, c->stream);
+    if (e != cudaSuccess) {
+      cleanup();
+      return fail(c, NB200_ENOMEM, cudaGetErrorString(e));
+    }
+    a.Nph = dN;
+    a.pos = dP;
+    a.energy = dE;
+    a.out = dO;
+  } else {
+    a.Nph = Nph;
+    a.pos = pos;
+    a.energy = energy;
+    a.out = out;
+  }
+  const uint64_t total = n, cap = c->work_cap, sm = uint64_t(c->sm_count);
+  for (uint64_t off = 0; off < total && !r; off += cap) {
+    const uint64_t m = std::min<uint64_t>(cap, total - off);
+    RunParams Q = P;
+    Q.n_events = m;
+    Q.chunk_off = off;
+    a.off = off;
+    const unsigned g1 = unsigned(std::min<uint64_t>((m + 255) / 256, sm * 8));
+    const unsigned g_hits = unsigned(std::min<uint64_t>((m + kHitGroup - 1) / kHitGroup, sm * c->occ_hits));
+    k_s1pre<<<g1, 256, 0, c->stream>>>(Q, a);
+    cudaMemsetAsync(c->d_err + 1, 0, sizeof(int), c->stream);
+    k_hits<<<g_hits, kHitBlock, kHitDynSmem, c->stream>>>(Q, reinterpret_cast<unsigned int*>(c->d_err + 1));
+    k_s1post<<<g1, 256, 0, c->stream>>>(Q, a);
+    cudaError_t le = cudaGetLastError();
+    c->launches += 3;
+    if (le != cudaSuccess) r = fail(c, NB200_ECUDA, std::string("nb200_s1: ") + cudaGetErrorString(le));
+  }
   if (!r && mem_kind == NB200_MEM_HOST) {
     cudaError_t e = cudaMemcpyAsync(out, a.out, n * 72, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);

@@ -863,6 +863,63 @@ __global__ void __launch_bounds__(256) k_s2(const __grid_constant__ RunParams P,
   }
 }
 
+// k_s1pre / k_s1post: NESTcalc::GetS1 (NEST.cpp:1288-1722; bareNEST.cpp:203) as a stage call on caller-given photons
+// and positions.  The hit loop itself is k_hits, unchanged: k_s1pre runs the prelude (binomial hit count, double-phe
+// count) into the stage workspace exactly as k_pre does, k_s1post the epilogue exactly as k_post does.
+// Nph: photons per record; pos: 6 columns (truth x, y, z, smeared x, y, z) and energy, with column stride `stride` and
+// this chunk starting at `off`; out: 9 columns (scintillation[0..8]).
+struct S1Args {
+  uint64_t stride, off;
+  const int32_t* Nph;
+  const double *pos, *energy;
+  double* out;
+};
+
+__global__ void __launch_bounds__(256) k_s1pre(const __grid_constant__ RunParams P, const S1Args a) {
+  const Work& W = P.work;
+  for (uint64_t idx = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; idx < P.n_events;
+       idx += uint64_t(gridDim.x) * blockDim.x) {
+    const uint64_t gi = a.off + idx, ev = P.first_event + P.chunk_off + idx;
+    const S1Pre pre = s1_prelude(ev, P, a.Nph[gi], a.pos[gi], a.pos[a.stride + gi], a.pos[2 * a.stride + gi],
+                                 a.pos[3 * a.stride + gi], a.pos[4 * a.stride + gi], a.pos[5 * a.stride + gi], a.energy[gi]);
+    W.posDepSm[idx] = pre.posDepSm;
+    W.fitSm[idx] = pre.fitSm;
+    W.nHits[idx] = pre.full ? pre.nHits : -(pre.nHits + 1);  // negative: Parametric S1 in k_s1post
+    W.nphe[idx] = pre.nDP;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_s1post(const __grid_constant__ RunParams P, const S1Args a) {
+  const Work& W = P.work;
+  for (uint64_t idx = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; idx < P.n_events;
+       idx += uint64_t(gridDim.x) * blockDim.x) {
+    const uint64_t gi = a.off + idx, ev = P.first_event + P.chunk_off + idx;
+    Stream g;
+    g.init(P.seed, ev, STREAM_POST);
+    S1Pre pre;
+    pre.posDepSm = W.posDepSm[idx];
+    pre.fitSm = W.fitSm[idx];
+    const int nh = W.nHits[idx];
+    pre.full = nh >= 0;
+    pre.nHits = pre.full ? nh : -(nh + 1);
+    pre.eff = 0.;
+    pre.nDP = 0;
+    S1Acc acc{0., 0, 0};
+    if (pre.full) {
+      if (nh > 0) {
+        acc.area = W.area[idx];
+        acc.spike = W.spike[idx];
+        acc.nphe = W.nphe[idx];
+      }
+    } else
+      s1_parametric(g, ev, P, pre.nHits, acc);
+    double scint[9];
+    s1_epilogue(g, P, pre, acc, scint);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) a.out[k * a.stride + gi] = scint[k];
+  }
+}
+
 // k_lar: LArNEST::FullCalculation (src/LArNEST.cpp:17-33) for species NR/ER/Alpha
 // -------------------------------------------------------------------------------------------
 struct LArParams {

@@ -212,6 +212,49 @@ NESTresult NESTcalc::FullCalculation(INTERACTION_TYPE species, double energy, do
   return result;
 }
 
+// ---- GetS1: NEST.cpp:1288-1722 ------------------------------------------------------------------------------
+vector<vector<double>> NESTcalc::GetS1(const vector<int>& photons, const vector<vector<double>>& truthPos,
+                                       const vector<vector<double>>& smearPos, double driftSpeed, double dS_mid,
+                                       uint64_t firstEvt, double dfield, const vector<double>& energy,
+                                       S1CalculationMode mode) {
+  const size_t n = photons.size();
+  if (truthPos.size() != n || smearPos.size() != n || energy.size() != n) throw runtime_error("GetS1: lists differ in length");
+  int m;
+  switch (mode) {
+    case S1CalculationMode::Full: m = NB200_S1_FULL; break;
+    case S1CalculationMode::Parametric: m = NB200_S1_PARAMETRIC; break;
+    case S1CalculationMode::Hybrid: m = NB200_S1_HYBRID; break;
+    default: throw runtime_error("GetS1: the Waveform mode is outside the GPU path");
+  }
+  vector<vector<double>> r(n, vector<double>(9, 0.));
+  if (n == 0) return r;
+  nb200_run_consts c = prepared(dfield >= 1. ? dfield : 180.);
+  c.vD = driftSpeed;
+  c.vD_middle = dS_mid;
+  vector<int32_t> nph(photons.begin(), photons.end());
+  vector<double> pos(6 * n), out(9 * n);
+  for (size_t i = 0; i < n; ++i) {
+    if (truthPos[i].size() < 3 || smearPos[i].size() < 3) throw runtime_error("GetS1: a position needs x, y, z");
+    for (int k = 0; k < 3; ++k) {
+      pos[size_t(k) * n + i] = truthPos[i][k];
+      pos[size_t(3 + k) * n + i] = smearPos[i][k];
+    }
+  }
+  Device::check(nb200_s1(Device::get(), &flat(), &c, m, n, nph.data(), pos.data(), energy.data(), call_seed, firstEvt,
+                         NB200_MEM_HOST, out.data()));
+  for (size_t i = 0; i < n; ++i)
+    for (int k = 0; k < 9; ++k) r[i][k] = out[size_t(k) * n + i];
+  return r;
+}
+const vector<double>& NESTcalc::GetS1(const QuantaResult& quanta, double truthPosX, double truthPosY, double truthPosZ,
+                                      double smearPosX, double smearPosY, double smearPosZ, double driftSpeed, double dS_mid,
+                                      INTERACTION_TYPE, uint64_t evtNum, double dfield, double energy, S1CalculationMode mode,
+                                      int, vector<int64_t>&, vector<double>&) {
+  scintillation = GetS1(vector<int>{quanta.photons}, {{truthPosX, truthPosY, truthPosZ}}, {{smearPosX, smearPosY, smearPosZ}},
+                        driftSpeed, dS_mid, evtNum, dfield, vector<double>{energy}, mode)[0];
+  return scintillation;
+}
+
 // ---- GetS2: NEST.cpp:1724-2063 (Full) --------------------------------------------------------------------
 vector<vector<double>> NESTcalc::GetS2(const vector<int>& Ne, const vector<vector<double>>& truthPos,
                                        const vector<vector<double>>& smearPos, const vector<double>& dt, uint64_t firstEvt,

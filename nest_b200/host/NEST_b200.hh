@@ -238,6 +238,19 @@ class NESTcalc {
                              const std::vector<double>& NRYieldsParam = default_NRYieldsParam,
                              const std::vector<double>& NRERWidthsParam = default_NRERWidthsParam,
                              const std::vector<double>& ERYieldsParam = default_ERYieldsParam, bool do_times = true);
+  // NEST.cpp:1288-1722 on the device (NEST.hh:335-340: the result is member scratch, valid until the next call): prelude,
+  // the chain's hit kernel, epilogue.  Full, Parametric and Hybrid modes; Waveform is refused.  driftSpeed / dS_mid
+  // replace the detector's own drift speeds for this call, as in the reference.
+  const std::vector<double>& GetS1(const QuantaResult& quanta, double truthPosX, double truthPosY, double truthPosZ,
+                                   double smearPosX, double smearPosY, double smearPosZ, double driftSpeed, double dS_mid,
+                                   INTERACTION_TYPE species, uint64_t evtNum, double dfield, double energy,
+                                   S1CalculationMode mode, int outputTiming, std::vector<int64_t>& wf_time,
+                                   std::vector<double>& wf_amp);
+  // n records at once: rows of nine (scintillation[0..8]); record i uses event number firstEvt + i
+  std::vector<std::vector<double>> GetS1(const std::vector<int>& photons, const std::vector<std::vector<double>>& truthPos,
+                                         const std::vector<std::vector<double>>& smearPos, double driftSpeed, double dS_mid,
+                                         uint64_t firstEvt, double dfield, const std::vector<double>& energy,
+                                         S1CalculationMode mode);
   // NEST.cpp:1724-2063, S2CalculationMode::Full, on the device (NEST.hh:351-356: the result is member scratch, valid
   // until the next call).  evtNum selects the Philox streams (seed from SetSeed); the Waveform modes are refused.
   const std::vector<double>& GetS2(int Ne, double truthPosX, double truthPosY, double truthPosZ, double smearPosX,
@@ -264,7 +277,7 @@ class NESTcalc {
   nb200_run_consts rc{};
   double rc_field = -12345.;
   uint64_t call_seed = 0, call_index = 0;
-  std::vector<double> ionization = std::vector<double>(9, 0.);
+  std::vector<double> ionization = std::vector<double>(9, 0.), scintillation = std::vector<double>(9, 0.);
 };
 
 }  // namespace NEST

@@ -69,6 +69,14 @@ class Probe:
                           C.c_double(skewER), _p(io), _p(do))
         return io, do
 
+    def s1(self, seed, n, Nph, pos, spos, vD, vDmid, species, field, energy, mode):
+        """n GetS1 draws on fixed photons / positions -> scintillation [n][9]"""
+        p, sp = _arr(pos), _arr(spos)
+        out = np.zeros((n, 9))
+        self._f("s1")(*self._d(), C.c_uint64(seed), C.c_int(n), C.c_int(Nph), _p(p), _p(sp), C.c_double(vD),
+                      C.c_double(vDmid), C.c_int(species), C.c_double(field), C.c_double(energy), C.c_int(mode), _p(out))
+        return out
+
     def s2(self, seed, n, Ne, pos, spos, dt, vD, field):
         """n GetS2 (Full) draws on fixed electrons / positions / drift time -> ionization [n][9]"""
         p, sp = _arr(pos), _arr(spos)

@@ -150,3 +150,60 @@ def test_s2_stage_does_not_depend_on_batching(ctx):
     assert abs(np.abs(whole[0]).sum() / expect - 1) < 0.01
     with pytest.raises(ValueError):
         ctx.s2(det, rc, Ne, pos[:4], dt, 180.0, seed=5)
+
+
+# GetS1 on fixed inputs: (photons, truth xyz, smeared xyz, energy [keV], S1 mode)
+S1_CASES = {
+    "2000 photons, Full": (2000, (50., -30., 250.), (52., -28., 250.), 10.0, 0),
+    "20 photons, Full (coincidence level matters)": (20, (0., 0., 300.), (1., 1., 300.), 0.5, 0),
+    "no photons": (0, (10., 10., 200.), (10., 10., 200.), 1.0, 0),
+    "30000 photons, Hybrid at 150 keV (Parametric)": (30000, (120., 80., 100.), (118., 83., 100.), 150.0, 2),
+    "300 photons, Parametric": (300, (100., -100., 450.), (98., -97., 450.), 5.0, 1),
+}
+
+
+@pytest.mark.parametrize("name", list(S1_CASES))
+def test_s1_stage_matches_reference(ctx, ref, name):
+    """NESTcalc::GetS1 (NEST.cpp:1288-1722; bareNEST.cpp:203) through nb200_s1 -> k_s1pre, k_hits, k_s1post: all nine
+    scintillation[] values against the unmodified reference on the same fixed inputs"""
+    Nph, pos, spos, energy, mode = S1_CASES[name]
+    n = 20000 if Nph < 5000 else 5000
+    det = capi.detector("LUX_Run03")
+    rc = capi.prepare(det, 180.0)
+    p6 = np.tile(np.array(list(pos) + list(spos))[:, None], (1, n))
+    got = ctx.s1(det, rc, np.full(n, Nph), p6, energy, seed=31, mode=mode)
+    exp = ref.s1(32, n, Nph, pos, spos, rc.vD, rc.vD_middle, capi.beta, 180.0, energy, mode).T
+    names = ["nHits", "Nphe", "area", "areaC", "phd", "phdC", "spike", "spikeC", "spike count"]
+    for k, col in enumerate(names):
+        a, b = got[k], exp[k]
+        if np.all(a == a[0]) and np.all(b == b[0]):
+            assert a[0] == pytest.approx(b[0], rel=1e-12, abs=0), (name, col, a[0], b[0])
+            continue
+        assert stats.ks_2samp(a, b).pvalue > 1e-4, (name, col, a.mean(), b.mean())
+        se = np.sqrt(a.var() / n + b.var() / n)
+        assert abs(a.mean() - b.mean()) < 5 * se + 1e-9, (name, col, a.mean(), b.mean())
+    # the coincidence flag (all eight negated, NEST.cpp:1689-1716) at the same rate
+    assert abs((got[2] < 0).mean() - (exp[2] < 0).mean()) < 5 * np.sqrt(0.25 / n) + 1e-12
+
+
+def test_s1_stage_does_not_depend_on_batching(ctx):
+    det = capi.detector("LUX_Run03")
+    rc = capi.prepare(det, 180.0)
+    rng = np.random.default_rng(2)
+    n = 6000
+    Nph = rng.integers(0, 4000, n)
+    r, phi = 200 * np.sqrt(rng.uniform(0, 1, n)), rng.uniform(0, 2 * np.pi, n)
+    z = rng.uniform(50, 500, n)
+    x, y = r * np.cos(phi), r * np.sin(phi)
+    pos = np.array([x, y, z, x + 1.0, y - 1.0, z])
+    E = rng.uniform(0.5, 200.0, n)                       # Hybrid: Full below 100 keV, Parametric above
+    whole = ctx.s1(det, rc, Nph, pos, E, seed=5)
+    a = ctx.s1(det, rc, Nph[:2500], np.ascontiguousarray(pos[:, :2500]), E[:2500], seed=5)
+    b = ctx.s1(det, rc, Nph[2500:], np.ascontiguousarray(pos[:, 2500:]), E[2500:], seed=5, first_event=2500)
+    assert np.array_equal(np.concatenate([a, b], axis=1), whole)
+    assert not np.array_equal(ctx.s1(det, rc, Nph, pos, E, seed=6), whole)
+    # hits ~ g1 x light-collection map x photons: within the map's range of the detector's g1
+    ratio = np.abs(whole[0]).sum() / Nph.sum()
+    assert 0.6 * det.g1 < ratio < 1.4 * det.g1
+    with pytest.raises(capi.NestB200Error):
+        ctx.s1(det, rc, Nph, pos, E, seed=5, mode=3)     # Waveform: not part of this path
