@@ -77,3 +77,27 @@ def test_no_device_is_an_error_not_a_fallback(cli):
     assert rc == 1
     assert any("no CUDA device" in ln and "no CPU fallback" in ln for ln in err)
     assert not any(ln[:1].isdigit() for ln in out.splitlines())       # not one event row was printed
+
+
+def test_stage_api_compiles_against_the_reference_signatures(built, tmp_path):
+    """tests/cpp/stage_calls.cpp calls GetYields -> GetQuanta -> GetS1 -> GetS2 and FullCalculation exactly as code
+    written for the reference does (examples/bareNEST.cpp:183-212, NEST.hh:218-226, 308-311, 335-356): it must compile
+    and link against the host mirror unchanged; without a device it must be refused loudly"""
+    host = os.path.join(ROOT, "nest_b200", "host")
+    r = subprocess.run(["make", "-s", "-C", host], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    exe = str(tmp_path / "stage_calls")
+    csrc = os.path.join(ROOT, "nest_b200", "csrc")
+    cmd = ["g++", "-O1", "-std=c++17", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), "-I" + host,
+           os.path.join(ROOT, "tests", "cpp", "stage_calls.cpp"), "-L" + host, "-lnest_b200_host", "-L" + csrc, "-lnest_b200",
+           "-Wl,-rpath," + host, "-Wl,-rpath," + csrc, "-o", exe]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+    import torch
+    if torch.cuda.is_available():
+        assert r.returncode == 0, r.stderr
+        assert len(r.stdout.strip().split("\t")) == 8
+    else:
+        assert r.returncode == 3 and "no CUDA device" in r.stderr and "no CPU fallback" in r.stderr
+        assert r.stdout.strip() == ""
