@@ -292,6 +292,38 @@ const vector<double>& NESTcalc::GetS2(int Ne, double truthPosX, double truthPosY
   return ionization;
 }
 
+// ---- LArNEST: src/LArNEST.cpp:17-33 ---------------------------------------------------------------------------
+vector<LArNESTResult> LArNEST::FullCalculation(LArInteraction species, const vector<double>& energy,
+                                               const vector<double>& efield, double density) {
+  if (energy.size() != efield.size()) throw runtime_error("LArNEST::FullCalculation: energy and field lists differ in length");
+  if (int(species) > int(LArInteraction::Alpha))
+    throw runtime_error("LArNEST: the dE/dx and LET models are outside the GPU path");
+  const size_t n = energy.size();
+  vector<LArNESTResult> r(n);
+  if (n == 0) return r;
+  if (density < 1.) fdetector->set_inGas(true);  // LArNEST.cpp:20
+  vector<double> y(9 * n), f(4 * n);
+  Device::check(nb200_lar(Device::get(), int(species), n, energy.data(), efield.data(), density, call_seed, call_index,
+                          NB200_MEM_HOST, y.data(), f.data()));
+  call_index += n;
+  for (size_t i = 0; i < n; ++i) {
+    r[i].yields = LArYieldResult{y[i], y[n + i], y[2 * n + i], y[3 * n + i], y[4 * n + i], y[5 * n + i], y[6 * n + i],
+                                 y[7 * n + i], y[8 * n + i]};
+    r[i].fluctuations = LArYieldFluctuationResult{f[i], f[n + i], f[2 * n + i], f[3 * n + i]};
+  }
+  return r;
+}
+LArNESTResult LArNEST::FullCalculation(LArInteraction species, double energy, double, double efield, double density, bool) {
+  return FullCalculation(species, vector<double>{energy}, vector<double>{efield}, density)[0];  // do_times: unused in the reference too (:25-32)
+}
+LArYieldResult LArNEST::GetYields(LArInteraction species, double energy, double, double efield, double density) {
+  if (int(species) > int(LArInteraction::Alpha))
+    throw runtime_error("LArNEST: the dE/dx and LET models are outside the GPU path");
+  vector<double> y(9);
+  Device::check(nb200_lar(Device::get(), int(species), 1, &energy, &efield, density, 0, 0, NB200_MEM_HOST, y.data(), nullptr));
+  return LArYieldResult{y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7], y[8]};
+}
+
 // ---- runNESTvec: execNEST.cpp:329-409 ----------------------------------------------------------------
 NESTObservableArray runNESTvec(VDetector* detector, INTERACTION_TYPE particleType, vector<double> eList,
                                vector<vector<double>> pos3dxyz, double inField, int seed,

@@ -269,6 +269,7 @@ class NESTcalc {
 
  protected:
   VDetector* fdetector;
+  uint64_t call_seed = 0, call_index = 0;  // Philox seed and next event number of the per-call stage API
 
  private:
   nb200_detector fdet{};
@@ -276,8 +277,34 @@ class NESTcalc {
   bool flattened = false;
   nb200_run_consts rc{};
   double rc_field = -12345.;
-  uint64_t call_seed = 0, call_index = 0;
   std::vector<double> ionization = std::vector<double>(9, 0.), scintillation = std::vector<double>(9, 0.);
+};
+
+// ---- liquid argon: include/NEST/LArNEST.hh:19-42, LArParameters.hh:27-34 ----
+enum class LArInteraction { NR = 0, ER = 1, Alpha = 2, dEdx = 3, LeptonLET = 4, LET = 5 };
+struct LArYieldResult {
+  double TotalYield, QuantaYield, LightYield, Nph, Ne, Nex, Nion, Lindhard, ElectricField;
+};
+struct LArYieldFluctuationResult {
+  double NphFluctuation, NeFluctuation, NexFluctuation, NionFluctuation;
+};
+struct LArNESTResult {
+  LArYieldResult yields;
+  LArYieldFluctuationResult fluctuations;
+  photonstream photon_times;
+};
+
+// LArNEST::FullCalculation / GetYields (src/LArNEST.cpp:17-33, 35-212) for the NR, ER and Alpha models with the
+// parameters of LArParameters.hh, on the device (nb200_lar -> k_lar).  The dE/dx and LET models and the parameter
+// setters of the reference class are not part of this path (std::runtime_error / absent).
+class LArNEST : public NESTcalc {
+ public:
+  explicit LArNEST(VDetector* detector) : NESTcalc(detector) {}
+  LArNESTResult FullCalculation(LArInteraction species, double energy, double dx, double efield, double density,
+                                bool do_times);
+  std::vector<LArNESTResult> FullCalculation(LArInteraction species, const std::vector<double>& energy,
+                                             const std::vector<double>& efield, double density);
+  LArYieldResult GetYields(LArInteraction species, double energy, double dx, double efield, double density);
 };
 
 }  // namespace NEST

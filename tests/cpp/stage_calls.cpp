@@ -39,6 +39,11 @@ int main() {
                                         default_NRERWidthsParam, default_ERYieldsParam, false);
     printf("%.6f\t%.6f\t%d\t%d\t%.6f\t%.6f\t%d\t%zu\n", yields.PhotonYield, yields.ElectronYield, quanta.photons,
            quanta.electrons, scint[2], scint2[4], full.quanta.photons + full.quanta.electrons, full.photon_times.size());
+    // liquid argon, as examples/LArNEST/LArNESTMeanYieldsBenchmarks.cpp:43-60 calls it
+    LArNEST larnest(detector);
+    LArNESTResult lar = larnest.FullCalculation(LArInteraction::NR, 10., 0., 500., 1.393, false);
+    LArYieldResult lary = larnest.GetYields(LArInteraction::ER, 10., 0., 500., 1.393);
+    printf("%.6f\t%.6f\t%.6f\t%.6f\n", lar.yields.Nph, lar.yields.Ne, lar.fluctuations.NphFluctuation, lary.Nph);
     if (quanta.photons + quanta.electrons != quanta.ions + quanta.excitons) status = 2;
     if (full.photon_times.size() != size_t(full.quanta.photons)) status = 2;
   } catch (const exception& e) {

@@ -97,7 +97,8 @@ def test_stage_api_compiles_against_the_reference_signatures(built, tmp_path):
     import torch
     if torch.cuda.is_available():
         assert r.returncode == 0, r.stderr
-        assert len(r.stdout.strip().split("\t")) == 8
+        lines = r.stdout.strip().splitlines()
+        assert len(lines[0].split("\t")) == 8 and len(lines[1].split("\t")) == 4
     else:
         assert r.returncode == 3 and "no CUDA device" in r.stderr and "no CPU fallback" in r.stderr
         assert r.stdout.strip() == ""
