@@ -382,6 +382,18 @@ int nb200_band_fit_gauss(const nb200_analysis* ana, const nb200_band_hist* hist,
  * (or NULL) = the same with omega +- omega_err, the reference's "quick + dirty" error bars (:739-771). */
 int nb200_hist_fit(int model, const uint64_t* counts, int bins, double lo, double hi, const double* start, double* par,
                    double* err, double* chi2_ndf);
+/* nb200_hist_fit_cov -- nb200_hist_fit returning the parameters' covariance matrix (J^T W J)^-1, row-major
+ * cov[npar][npar] (3 or 4 squared), as rootNEST's skewness = 2 reads it from TFitResult (:1399-1405).
+ *
+ * nb200_band_leakage_skew_cov -- the skewness = 2 leakage (:774-845): skew-normal CDF at line[i] and its 1-sigma error
+ * propagated from the fit (skew [numBins][9] = {xi, xi error, omega, omega error, alpha, alpha error, cov(xi, omega),
+ * cov(xi, alpha), cov(omega, alpha)}) and from the line's own error line_err[i]; the reference's error bars are
+ * leak +- err. */
+int nb200_hist_fit_cov(int model, const uint64_t* counts, int bins, double lo, double hi, const double* start,
+                       double* par, double* cov, double* chi2_ndf);
+int nb200_band_leakage_skew_cov(int numBins, const double* skew, const double* line, const double* line_err,
+                                double* leak, double* err);
+
 /* nb200_graph_fit -- TGraph::Fit without ROOT for the two curves rootNEST puts through the NR band's means (:855-878):
  * model 2 = the Woods function p0/(x + p1) + p2 x + p3, model 3 = its fallback p0 + (p1 - p0)/(1 + (x/p2)^p3);
  * unweighted least squares over (x[i], y[i]), par/start[4]; *chi2_ndf = sum of squared residuals / (n - 4), the figure

@@ -103,7 +103,7 @@ EXPORTS = [
     "nb200_synchronize", "nb200_detector_builtin", "nb200_model_default", "nb200_analysis_default",
     "nb200_prepare", "nb200_wimp_prep", "nb200_poisson", "nb200_yields", "nb200_quanta", "nb200_s2", "nb200_s1", "nb200_run", "nb200_run_async",
     "nb200_band_reset", "nb200_band_attach", "nb200_fp64_peak", "nb200_timing_enable", "nb200_timing_read", "nb200_se_stats", "nb200_band_fetch", "nb200_band_device_buffer", "nb200_allreduce_hist",
-    "nb200_band_hist_bytes", "nb200_band_finalize", "nb200_band_chi2", "nb200_band_leakage", "nb200_band_fit_gauss", "nb200_band_leakage_gauss", "nb200_hist_fit", "nb200_graph_fit", "nb200_band_leakage_skew", "nb200_lar", "nb200_launch_count",
+    "nb200_band_hist_bytes", "nb200_band_finalize", "nb200_band_chi2", "nb200_band_leakage", "nb200_band_fit_gauss", "nb200_band_leakage_gauss", "nb200_hist_fit", "nb200_hist_fit_cov", "nb200_band_leakage_skew_cov", "nb200_graph_fit", "nb200_band_leakage_skew", "nb200_lar", "nb200_launch_count",
     "nb200_debug_hitmath", "nb200_debug_binomial", "nb200_debug_normal", "nb200_debug_binomial_fixed",
     "nb200_debug_zig_tables", "nb200_debug_alias_tables"]
 
@@ -176,6 +176,8 @@ def lib():
     L.nb200_band_fit_gauss.argtypes = [C.POINTER(Analysis), C.POINTER(BandHist), c_dp]
     L.nb200_band_leakage_gauss.argtypes = [C.c_int, c_dp, c_dp, C.c_double, c_dp]
     L.nb200_hist_fit.argtypes = [C.c_int, c_u64p, C.c_int, C.c_double, C.c_double, c_dp, c_dp, c_dp, c_dp]
+    L.nb200_hist_fit_cov.argtypes = [C.c_int, c_u64p, C.c_int, C.c_double, C.c_double, c_dp, c_dp, c_dp, c_dp]
+    L.nb200_band_leakage_skew_cov.argtypes = [C.c_int, c_dp, c_dp, c_dp, c_dp, c_dp]
     L.nb200_graph_fit.argtypes = [C.c_int, C.c_int, c_dp, c_dp, c_dp, c_dp, c_dp]
     L.nb200_band_leakage_skew.argtypes = [C.c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]
     L.nb200_lar.argtypes = [vp, C.c_int, C.c_size_t, vp, vp, C.c_double, C.c_uint64, C.c_uint64, C.c_int,
@@ -222,6 +224,36 @@ def hist_fit(model, counts, lo, hi, start):
     if rc:
         raise NestB200Error(rc, "nb200_hist_fit: no minimum" if rc == EFIT else "nb200_hist_fit")
     return par, err, chi.value
+
+
+def hist_fit_cov(model, counts, lo, hi, start):
+    """hist_fit with the full covariance matrix of the parameters -> (par, cov[npar][npar], chi2/ndf)"""
+    c = np.ascontiguousarray(counts, np.uint64)
+    n = 3 if model == 0 else 4
+    st = np.ascontiguousarray(start, np.float64)
+    if st.size != n:
+        raise ValueError("model %d takes %d start values" % (model, n))
+    par, cov, chi = np.zeros(n), np.zeros((n, n)), C.c_double()
+    rc = lib().nb200_hist_fit_cov(model, c.ctypes.data_as(c_u64p), c.size, lo, hi, st.ctypes.data_as(c_dp),
+                                  par.ctypes.data_as(c_dp), cov.ctypes.data_as(c_dp), C.byref(chi))
+    if rc:
+        raise NestB200Error(rc, "nb200_hist_fit_cov: no minimum" if rc == EFIT else "nb200_hist_fit_cov")
+    return par, cov, chi.value
+
+
+def band_leakage_skew_cov(skew, line, line_err):
+    """rootNEST's skewness = 2 leakage with propagated error (rootNEST.cpp:774-845): skew [n][9] -> (leak, err)"""
+    k = np.ascontiguousarray(skew, np.float64)
+    ln = np.ascontiguousarray(line, np.float64)
+    le = np.ascontiguousarray(line_err, np.float64)
+    if k.ndim != 2 or k.shape[1] != 9 or ln.size != k.shape[0] or le.size != k.shape[0]:
+        raise ValueError("skew must be [n][9], line and line_err [n]")
+    leak, err = np.zeros(ln.size), np.zeros(ln.size)
+    rc = lib().nb200_band_leakage_skew_cov(ln.size, k.ctypes.data_as(c_dp), ln.ctypes.data_as(c_dp), le.ctypes.data_as(c_dp),
+                                           leak.ctypes.data_as(c_dp), err.ctypes.data_as(c_dp))
+    if rc:
+        raise NestB200Error(rc, "nb200_band_leakage_skew_cov")
+    return leak, err
 
 
 def graph_fit(model, x, y, start):

@@ -1502,7 +1502,8 @@ double points_chi2(int model, int npts, const double* xs, const double* ys, cons
 }
 
 // Levenberg-Marquardt on weighted points; false when there are too few points or no minimum was found
-bool fit_points(int model, int npts, const double* xs, const double* ys, const double* ws, double* p, double* err, double* chi2) {
+bool fit_points(int model, int npts, const double* xs, const double* ys, const double* ws, double* p, double* err, double* chi2,
+                double* cov = nullptr) {
   const int n = model_npar(model);
   if (npts <= n || !model_domain(model, p)) return false;
   double JtJ[kFitMaxPar][kFitMaxPar], Jtr[kFitMaxPar], lambda = 1e-3;
@@ -1537,6 +1538,8 @@ bool fit_points(int model, int npts, const double* xs, const double* ys, const d
       col[i] = 0.;  // a curve with a flat direction (a straight line has no Woods pole): the minimum stands, the error does not
     }
     err[i] = std::sqrt(col[i]);
+    if (cov)
+      for (int j = 0; j < n; ++j) cov[j * n + i] = col[j];
   }
   *chi2 = chi;
   return true;
@@ -1544,7 +1547,8 @@ bool fit_points(int model, int npts, const double* xs, const double* ys, const d
 
 // a histogram row as weighted points: bin centres, contents, weights 1/content, empty bins left out (TH1::Fit's default
 // chi^2); returns the number of bins used, 0 when there are too few or no minimum was found
-int fit_hist_row(int model, const uint64_t* row, int lb, double x0, double w, double* p, double* err, double* chi2) {
+int fit_hist_row(int model, const uint64_t* row, int lb, double x0, double w, double* p, double* err, double* chi2,
+                 double* cov = nullptr) {
   std::vector<double> xs, ys, ws;
   for (int k = 0; k < lb; ++k) {
     if (!row[k]) continue;
@@ -1552,7 +1556,7 @@ int fit_hist_row(int model, const uint64_t* row, int lb, double x0, double w, do
     ys.push_back(double(row[k]));
     ws.push_back(1. / double(row[k]));
   }
-  if (!fit_points(model, int(xs.size()), xs.data(), ys.data(), ws.data(), p, err, chi2)) return 0;
+  if (!fit_points(model, int(xs.size()), xs.data(), ys.data(), ws.data(), p, err, chi2, cov)) return 0;
   return int(xs.size());
 }
 
@@ -1651,6 +1655,41 @@ int nb200_hist_fit(int model, const uint64_t* counts, int bins, double lo, doubl
     err[i] = e[i];
   }
   if (chi2_ndf) *chi2_ndf = chi / double(used - n);
+  return 0;
+}
+
+// the same fit with the full covariance matrix (J^T W J)^-1 of the parameters, row-major [npar][npar]: what rootNEST's
+// skewness = 2 reads from TFitResult::GetCovarianceMatrix (rootNEST.cpp:1399-1405)
+int nb200_hist_fit_cov(int model, const uint64_t* counts, int bins, double lo, double hi, const double* start, double* par,
+                       double* cov, double* chi2_ndf) {
+  if (!counts || !start || !par || !cov || bins < 1 || !(hi > lo) || (model != 0 && model != 1)) return NB200_EINVAL;
+  const int n = model_npar(model);
+  double p[kFitMaxPar], e[kFitMaxPar] = {0., 0., 0., 0.}, chi = 0.;
+  for (int i = 0; i < n; ++i) p[i] = start[i];
+  const int used = fit_hist_row(model, counts, bins, lo, (hi - lo) / double(bins), p, e, &chi, cov);
+  if (!used) return NB200_EFIT;
+  for (int i = 0; i < n; ++i) par[i] = p[i];
+  if (chi2_ndf) *chi2_ndf = chi / double(used - n);
+  return 0;
+}
+
+// examples/rootNEST.cpp:774-845 (skewness == 2): the skew-normal leakage below line[i] with its error propagated from the
+// fit's parameter errors and covariances and the line's own error.  skew [numBins][9] = {xi, xi error, omega, omega
+// error, alpha, alpha error, cov(xi, omega), cov(xi, alpha), cov(omega, alpha)}
+int nb200_band_leakage_skew_cov(int numBins, const double* skew, const double* line, const double* line_err, double* leak,
+                                double* err) {
+  if (!skew || !line || !line_err || !leak || !err || numBins < 1) return NB200_EINVAL;
+  for (int i = 0; i < numBins; ++i) {
+    const double* k = skew + 9 * size_t(i);
+    const double xi = k[0], om = k[2], al = k[4], c = line[i];
+    leak[i] = 0.5 + 0.5 * std::erf((c - xi) / om / std::sqrt(2.)) - 2. * owens_t_ref((c - xi) / om, al);
+    const double pdf = (1. / (om * std::sqrt(2. * M_PI))) * std::exp(-0.5 * (c - xi) * (c - xi) / (om * om)) *
+                       (1. + std::erf(al * (c - xi) / (om * std::sqrt(2.))));
+    const double d_x = pdf, d_xi = -1. * pdf, d_om = -1. * (c - xi) / om * pdf;
+    const double d_al = -1. / M_PI / (1. + al * al) * std::exp(-1. * (1. + al * al) * (c - xi) * (c - xi) / 2. / (om * om));
+    err[i] = std::sqrt(0. + d_x * d_x * line_err[i] * line_err[i] + d_xi * d_xi * k[1] * k[1] + d_om * d_om * k[3] * k[3] +
+                       d_al * d_al * k[5] * k[5] + 2 * d_xi * d_om * k[6] + 2 * d_om * d_al * k[8] + 2 * d_xi * d_al * k[7]);
+  }
   return 0;
 }
 

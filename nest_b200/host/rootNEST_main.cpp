@@ -5,10 +5,11 @@
 //                                                :668-950 -- examples/leakage.sh runs unchanged)
 //   NB200_MODE=1 rootNEST_b200 NESTOutput.txt dataBand.txt   goodness of fit against a data band (mode 1; :587-666)
 //
-// with the reference's analysis.hh defaults: skewness = 1 (skew-Gaussian fits; NB200_SKEWNESS=0 for Gaussian fits)
+// with the reference's analysis.hh defaults: skewness = 1 (skew-Gaussian fits; NB200_SKEWNESS=0 for Gaussian fits, 2 for
+// the detailed table with covariances and propagated errors)
 // and NRbandCenter = 3 (the NR centroid is a Woods-function curve through the per-bin means, evaluated at each
-// event's S1; NB200_NRBANDCENTER=1 or 2 for the other two choices).  Not included: skewness = 2's covariance
-// propagation, medians (negative NRbandCenter), modes 2 and 3 (the WIMP limits).  Inputs are execNEST's 12-column stdout (src/execNEST.cpp:1386-1405), read as GetFile does
+// event's S1; NB200_NRBANDCENTER=1 or 2 for the other two choices).  Not included: medians (negative NRbandCenter),
+// MINUIT's IMPROVE step of skewness = 2 ("M"), modes 2 and 3 (the WIMP limits).  Inputs are execNEST's 12-column stdout (src/execNEST.cpp:1386-1405), read as GetFile does
 // (:955-1036); per-bin statistics, Gaussian fits and leakage come from the library's host-side band functions
 // (include/nest_b200.h: nb200_band_finalize, nb200_band_fit_gauss, nb200_hist_fit, nb200_band_leakage_gauss / _skew).  Nothing here
 // simulates anything: no device is needed or used.
@@ -36,6 +37,7 @@ struct BandOfFile {
   vector<double> mom;                      // [numBins][7] nb200_band_finalize
   vector<double> fit;                      // [numBins][8] nb200_band_fit_gauss; skew fits: [1] mean, [2] sigma, [3] xi error, [4] omega error
   vector<double> xi, omega, omega_err, alpha, alpha_err;  // skew fits only (band[j][9], [11], [12], [4], [7])
+  vector<double> xi_err, cov_xo, cov_xa, cov_oa;          // skewness = 2 (band[j][10], [13], [14], [15])
   size_t events = 0;
 };
 
@@ -131,6 +133,10 @@ bool band_of_file(const char* name, BandOfFile& B) {
   B.omega_err.assign(nb, 0.);
   B.alpha.assign(nb, 0.);
   B.alpha_err.assign(nb, 0.);
+  B.xi_err.assign(nb, 0.);
+  B.cov_xo.assign(nb, 0.);
+  B.cov_xa.assign(nb, 0.);
+  B.cov_oa.assign(nb, 0.);
   bool wings = false;
   for (int j = 0; skewness && j < nb; ++j) {  // :1319-1330, :1360-1507
     double* f = &B.fit[8 * size_t(j)];
@@ -162,11 +168,12 @@ bool band_of_file(const char* name, BandOfFile& B) {
     // the reference starts the amplitude at the number of events (:1365); the function integrates to its amplitude, so
     // the events times the bin width is where the minimum is -- start there
     const double start[4] = {double(ys.size()) * (hi - lo) / double(lb), mean - omega0 * dE * sqrt(2. / M_PI), omega0, alpha0};
-    double par[4], err[4], chi = 0.;
-    if (nb200_hist_fit(1, h.data(), lb, lo, hi, start, par, err, &chi)) {
+    double par[4], err[4], cov[16], chi = 0.;
+    if (nb200_hist_fit_cov(1, h.data(), lb, lo, hi, start, par, cov, &chi)) {
       if (A.verbosity > 0) cerr << "Re-fitting... (stats, more? and/or logBins, fewer? might help)\n";
       continue;
     }
+    for (int i = 0; i < 4; ++i) err[i] = sqrt(cov[5 * i]);
     const double d = par[3] / sqrt(1. + par[3] * par[3]);
     f[0] = par[0];
     f[1] = par[1] + par[2] * d * sqrt(2. / M_PI);          // band[j][2]
@@ -180,11 +187,37 @@ bool band_of_file(const char* name, BandOfFile& B) {
     B.omega_err[j] = err[2];
     B.alpha[j] = par[3];
     B.alpha_err[j] = err[3];
+    B.xi_err[j] = err[1];
+    if (skewness == 2) {  // errors of the mean and of the standard deviation through the covariance matrix, :1419-1448
+      B.cov_xo[j] = cov[1 * 4 + 2];
+      B.cov_xa[j] = cov[1 * 4 + 3];
+      B.cov_oa[j] = cov[2 * 4 + 3];
+      // (the reference's own coefficients, kept: its d mean / d xi is omega sqrt(2/pi) delta rather than 1)
+      const double dmudxi = par[2] * sqrt(2. / M_PI) * d, dmudomega = sqrt(2. / M_PI) * d,
+                   dmudalpha = par[2] * sqrt(2. / M_PI) * pow(1. + par[3] * par[3], -1.5);
+      f[3] = sqrt(dmudxi * dmudxi * err[1] * err[1] + dmudomega * dmudomega * err[2] * err[2] +
+                  dmudalpha * dmudalpha * err[3] * err[3] + 2. * dmudxi * dmudomega * B.cov_xo[j] +
+                  2. * dmudomega * dmudalpha * B.cov_oa[j] + 2. * dmudxi * dmudalpha * B.cov_xa[j]);
+      const double dvardomega = 2. * par[2] * (1. - 2. / M_PI * d * d),
+                   dvardalpha = -4. / M_PI * par[2] * par[2] * par[3] / (1. + par[3] * par[3]) / (1. + par[3] * par[3]);
+      const double var_err = sqrt(dvardomega * dvardomega * err[2] * err[2] + dvardalpha * dvardalpha * err[3] * err[3] +
+                                  2. * dvardomega * dvardalpha * B.cov_oa[j]);
+      f[4] = 0.5 / f[2] * var_err;
+    }
     if ((chi > 10. || f[1] > 7. || f[3] > 1. || fabs(par[3]) > 3. || err[3] > 10. || f[2] > 0.5 || f[4] > 0.1 || f[1] <= 0. ||
          f[2] <= 0.) && A.verbosity > 0)
       cerr << "Re-fitting... (stats, more? and/or logBins, fewer? might help)\n";  // :1493-1504: mode 0 reports, does not retry
   }
-  if (A.verbosity > 0) {  // :1180-1190
+  if (A.verbosity > 0 && skewness == 2) {  // :1168-1179
+    fprintf(stdout, "Bin Center\tBand Xi\t\tXi Err\t\tBand Omega\tOmega Err\tBand Alpha\tAlpha Err\tBand Cov Xi-Om\tBand Cov "
+                    "Xi-Al\tBand Cov Om-Al\tBand Mean\tMean Err\tBand Stddev\tStddev Err\n");
+    for (int o = 0; o < nb; ++o) {
+      const double* f = &B.fit[8 * size_t(o)];
+      fprintf(stdout, "%lf\t%lf\t%lf\t%lf\t%lf\t%lf\t%lf\t%lf\t%lf\t%lf\t%lf\t%lf\t%lf\t%lf\n", B.mom[7 * size_t(o)], B.xi[o],
+              B.xi_err[o], B.omega[o], B.omega_err[o], B.alpha[o], B.alpha_err[o], B.cov_xo[o], B.cov_xa[o], B.cov_oa[o], f[1], f[3],
+              f[2], f[4]);
+    }
+  } else if (A.verbosity > 0) {  // :1180-1190
     fprintf(stdout, "Bin Center\tBin Actual\tGaus Mean\tMean Error\tGaus Sigma\tSig Error\tGaus Skew\tSkew Error\tX^2/DOF\n");
     for (int o = 0; o < nb; ++o) {
       const double* m = &B.mom[7 * size_t(o)];
@@ -269,11 +302,22 @@ int leakage_table(const char* file1, const char* file2) {  // :668-950
     if (nb200_band_leakage_skew(nb, E.xi.data(), E.omega.data(), E.omega_err.data(), E.alpha.data(), line.data(), leak.data(),
                                 hi.data(), lo.data()))
       return 1;
+    vector<double> perr(nb, 0.);
+    if (skewness == 2) {  // :774-845: the error propagated from the fit's covariance and the NR mean's error
+      vector<double> k9(size_t(nb) * 9), lerr(nb);
+      for (int i = 0; i < nb; ++i) {
+        const double v[9] = {E.xi[i], E.xi_err[i], E.omega[i], E.omega_err[i], E.alpha[i], E.alpha_err[i], E.cov_xo[i], E.cov_xa[i],
+                             E.cov_oa[i]};
+        for (int q = 0; q < 9; ++q) k9[9 * size_t(i) + q] = v[q];
+        lerr[i] = nr[8 * size_t(i) + 3];
+      }
+      if (nb200_band_leakage_skew_cov(nb, k9.data(), line.data(), lerr.data(), leak.data(), perr.data())) return 1;
+    }
     for (int i = 0; i < nb; ++i) {
       if (!(E.omega[i] > 0.)) continue;
       lk[4 * size_t(i) + 1] = leak[i];
-      lk[4 * size_t(i) + 2] = fabs(hi[i] - leak[i]);
-      lk[4 * size_t(i) + 3] = fabs(leak[i] - lo[i]);
+      lk[4 * size_t(i) + 2] = skewness == 2 ? perr[i] : fabs(hi[i] - leak[i]);
+      lk[4 * size_t(i) + 3] = skewness == 2 ? perr[i] : fabs(leak[i] - lo[i]);
     }
   }
   // the NR line as a smooth curve through the per-bin means (:855-878): the Woods function, else a sigmoid, else the means
@@ -352,7 +396,7 @@ int main(int argc, char** argv) {
     if (!strcmp(a, "G2")) A = NEST::Analysis::G2();
   if (const char* v = getenv("NB200_VERBOSITY")) A.verbosity = atoi(v);
   if (const char* v = getenv("NB200_LOGBINS")) A.logBins = atoi(v);
-  if (const char* v = getenv("NB200_SKEWNESS")) skewness = atoi(v) ? 1 : 0;
+  if (const char* v = getenv("NB200_SKEWNESS")) skewness = max(0, min(2, atoi(v)));
   if (const char* v = getenv("NB200_NRBANDCENTER")) NRbandCenter = abs(atoi(v));
   if (NRbandCenter != 1 && NRbandCenter != 2 && NRbandCenter != 3) NRbandCenter = 3;  // :101-103
   const int mode = getenv("NB200_MODE") ? atoi(getenv("NB200_MODE")) : 0;

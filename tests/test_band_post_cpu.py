@@ -330,3 +330,43 @@ def test_graph_fit_matches_least_squares(built):
     assert e.value.code == capi.EFIT
     with pytest.raises(capi.NestB200Error):
         capi.graph_fit(0, x, y, (1., 1., 1., 1.))
+
+
+def test_fit_covariance_and_propagated_leakage_error(built):
+    """nb200_hist_fit_cov against scipy's covariance, and nb200_band_leakage_skew_cov (rootNEST.cpp:774-845) against the
+    linear error propagation done numerically on the skew-normal CDF"""
+    from scipy.optimize import curve_fit
+    from scipy.special import erf
+    from scipy.stats import skewnorm
+    f = lambda x, A, xi, w, al: A / (w * np.sqrt(2 * np.pi)) * np.exp(-0.5 * ((x - xi) / w) ** 2) * (1 + erf(al * (x - xi) / (w * np.sqrt(2))))
+    y = skewnorm.rvs(1.8, loc=2.45, scale=0.16, size=300000, random_state=3)
+    mu, sd = y.mean(), y.std()
+    lo, hi, bins = mu - 3 * sd, mu + 3 * sd, 60
+    h, edges = np.histogram(y, bins=bins, range=(lo, hi))
+    x = 0.5 * (edges[1:] + edges[:-1])
+    start = (y.size * (hi - lo) / bins, mu - 0.5 * sd, 1.2 * sd, 0.5)
+    par, cov, chi = capi.hist_fit_cov(1, h, lo, hi, start)
+    par1, err1, chi1 = capi.hist_fit(1, h, lo, hi, start)
+    assert np.array_equal(par, par1) and chi == chi1
+    np.testing.assert_allclose(np.sqrt(np.diag(cov)), err1, rtol=1e-12)
+    np.testing.assert_allclose(cov, cov.T, rtol=1e-9, atol=1e-18)
+    k = h > 0
+    popt, pcov = curve_fit(f, x[k], h[k].astype(float), p0=start, sigma=np.sqrt(h[k]), absolute_sigma=True, xtol=1e-14,
+                           ftol=1e-14, gtol=1e-14)
+    np.testing.assert_allclose(cov, pcov, rtol=5e-3, atol=1e-12)
+    # leakage below a line 2.2 omega under xi, and its error
+    line, line_err = par[1] - 2.2 * par[2] + 0.3, 0.004
+    skew = np.array([[par[1], np.sqrt(cov[1, 1]), par[2], np.sqrt(cov[2, 2]), par[3], np.sqrt(cov[3, 3]), cov[1, 2], cov[1, 3],
+                      cov[2, 3]]])
+    leak, err = capi.band_leakage_skew_cov(skew, [line], [line_err])
+    cdf = lambda xi, om, al, c: skewnorm.cdf(c, al, loc=xi, scale=om)
+    assert leak[0] == pytest.approx(cdf(par[1], par[2], par[3], line), abs=2e-7)
+    eps = 1e-6
+    g = np.array([(cdf(par[1] + eps, par[2], par[3], line) - cdf(par[1] - eps, par[2], par[3], line)) / (2 * eps),
+                  (cdf(par[1], par[2] + eps, par[3], line) - cdf(par[1], par[2] - eps, par[3], line)) / (2 * eps),
+                  (cdf(par[1], par[2], par[3] + eps, line) - cdf(par[1], par[2], par[3] - eps, line)) / (2 * eps)])
+    gc = (cdf(par[1], par[2], par[3], line + eps) - cdf(par[1], par[2], par[3], line - eps)) / (2 * eps)
+    var = g @ cov[1:, 1:] @ g + (gc * line_err) ** 2
+    assert err[0] == pytest.approx(np.sqrt(var), rel=2e-3)
+    with pytest.raises(ValueError):
+        capi.band_leakage_skew_cov(skew[:, :8], [line], [line_err])

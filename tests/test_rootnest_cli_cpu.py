@@ -257,6 +257,51 @@ def test_skew_gaussian_mode(tool, tmp_path):
     assert np.all(table(out)[:, 6] == 0)
 
 
+def test_skewness_2_table_and_propagated_errors(tool, tmp_path):
+    """skewness = 2: the 14-column table (rootNEST.cpp:1168-1179) with the fit's covariances, mean / stddev errors through
+    them (:1419-1448) and the leakage error propagated from them (:774-845)"""
+    ana = capi.analysis(0)
+    write_execnest_file(tmp_path / "er.txt", 6, 400000, 2.45, -0.004, 0.16, alpha=2.0, s1max=22.0)
+    write_execnest_file(tmp_path / "nr.txt", 7, 100000, 2.2, -0.002, 0.12, s1max=22.0)
+    files = (str(tmp_path / "er.txt"), str(tmp_path / "nr.txt"))
+    rc1, out1, err1 = run(tool, *files, env={"NB200_SKEWNESS": "1"})
+    rc2, out2, err2 = run(tool, *files, env={"NB200_SKEWNESS": "2"})
+    assert rc1 == 0 and rc2 == 0
+    t1 = table(out1, "Calculating band for second dataset")
+    lines = out2.splitlines()
+    lines = lines[lines.index("Calculating band for second dataset"):]
+    k = next(i for i, ln in enumerate(lines) if ln.startswith("Bin Center\tBand Xi"))
+    t2 = np.array([[float(v) for v in ln.split("\t")] for ln in lines[k + 1:k + 1 + ana.numBins]])
+    assert t2.shape == (ana.numBins, 14)
+    nr2 = out2.splitlines()
+    nr2 = nr2[nr2.index("Calculating band for first dataset"):]
+    k = next(i for i, ln in enumerate(nr2) if ln.startswith("Bin Center\tBand Xi"))
+    tn = np.array([[float(v) for v in ln.split("\t")] for ln in nr2[k + 1:k + 1 + ana.numBins]])
+    el = err2.splitlines()
+    k = next(i for i, ln in enumerate(el) if ln.startswith("#evts\tBinCen"))
+    rows = np.array([[float(v) for v in ln.split("\t")[:12]] for ln in el[k + 1:k + 1 + ana.numBins]])
+    checked = 0
+    for i in range(2, 18):
+        xi, xe, om, oe, al, ae, cxo, cxa, coa, mean, me, sd, se = t2[i, 1:]
+        if ae > 0.6:
+            continue
+        # the same fit as skewness = 1: mean, sigma, alpha
+        assert mean == pytest.approx(t1[i, 2], abs=2e-6) and sd == pytest.approx(t1[i, 4], abs=2e-6) and al == pytest.approx(t1[i, 6], abs=2e-6)
+        d = al / np.sqrt(1 + al * al)
+        assert mean == pytest.approx(xi + om * d * np.sqrt(2 / np.pi), abs=3e-6)
+        # :1419-1431 with the reference's own coefficients
+        a, b, c = om * np.sqrt(2 / np.pi) * d, np.sqrt(2 / np.pi) * d, om * np.sqrt(2 / np.pi) * (1 + al * al) ** -1.5
+        var = a * a * xe * xe + b * b * oe * oe + c * c * ae * ae + 2 * a * b * cxo + 2 * b * c * coa + 2 * a * c * cxa
+        assert me == pytest.approx(np.sqrt(var), rel=0.02, abs=2e-6)
+        # |cov| <= product of the errors; the leakage error bars are symmetric and equal the library's propagation
+        assert abs(cxo) <= xe * oe * 1.001 + 1e-6 and abs(cxa) <= xe * ae * 1.001 + 1e-6 and abs(coa) <= oe * ae * 1.001 + 1e-6
+        assert rows[i, 5] == rows[i, 6]
+        leak, perr = capi.band_leakage_skew_cov([[xi, xe, om, oe, al, ae, cxo, cxa, coa]], [tn[i, 10]], [tn[i, 11]])
+        assert rows[i, 4] == pytest.approx(leak[0], rel=0.02, abs=1e-7) and rows[i, 5] == pytest.approx(perr[0], rel=0.05, abs=1e-7)
+        checked += 1
+    assert checked >= 10
+
+
 def test_on_the_reference_binary_output(tool, tmp_path):
     """the unmodified reference's own stdout goes through: LUX_Run03 ER vs NR discrimination around 99.5 %"""
     if not os.path.exists(refprobe.REF_BIN_LUX):
