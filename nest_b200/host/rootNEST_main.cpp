@@ -4,6 +4,7 @@
 //   rootNEST_b200 NESTOutputER.txt NESTOutputNR.txt   leakage / discrimination table (mode 0, two inputs;
 //                                                :668-950 -- examples/leakage.sh runs unchanged)
 //   NB200_MODE=1 rootNEST_b200 NESTOutput.txt dataBand.txt   goodness of fit against a data band (mode 1; :587-666)
+//   NB200_NUMBINS=1 rootNEST_b200 NESTOutput.txt   a mono-energetic peak: S1 / S2 / energy means and resolutions (:1044-1137)
 //
 // with the reference's analysis.hh defaults: skewness = 1 (skew-Gaussian fits; NB200_SKEWNESS=0 for Gaussian fits, 2 for
 // the detailed table with covariances and propagated errors)
@@ -42,7 +43,7 @@ struct BandOfFile {
 };
 
 // GetFile :955-1036: select S1 and S2 per usePD, flag what is outside (minS, maxS) as -999
-bool read_signals(const char* name, vector<double>& S1, vector<double>& S2) {
+bool read_signals(const char* name, vector<double>& S1, vector<double>& S2, vector<double>* E_keV = nullptr) {
   FILE* fp = fopen(name, "r");
   if (!fp) {
     cerr << "ERROR: cannot open " << name << endl;
@@ -67,6 +68,7 @@ bool read_signals(const char* name, vector<double>& S1, vector<double>& S2) {
       s2 = n;
     S1.push_back(s1);
     S2.push_back(s2);
+    if (E_keV) E_keV->push_back(a);
   }
   fclose(fp);
   return true;
@@ -227,6 +229,89 @@ bool band_of_file(const char* name, BandOfFile& B) {
     }
   }
   return true;
+}
+
+// GetFile with numBins == 1 (:1044-1137): a mono-energetic peak -- Gaussian fits of the S1, S2 and energy histograms
+// (2 x NUMBINS_MAX bins around the median-ish entry), means, resolutions, their errors and chi^2 / DOF
+int peak_table(const char* name) {
+  vector<double> S1, S2, E;
+  if (!read_signals(name, S1, S2, &E)) return 1;
+  const size_t numPts = E.size();
+  if (numPts < 10) {
+    cerr << "ERROR: too few events in " << name << endl;
+    return 1;
+  }
+  double eMin = 1e100, eMax = -1e100;
+  for (double e : E) {
+    eMin = min(eMin, e);
+    eMax = max(eMax, e);
+  }
+  const int bins = 2 * 1000;  // 2 * NUMBINS_MAX (TestSpectra.hh:32)
+  double res[3][5];           // mean, resolution %, mean error, resolution error %, chi^2 / DOF
+  printf("S1 Mean\t\tS1 Res [%%]\tS2 Mean\t\tS2 Res [%%]\tEc Mean\t\tEc Res[%%]\n");
+  for (int j = 0; j < 3; ++j) {
+    const vector<double>& holder = j == 0 ? S1 : j == 1 ? S2 : E;
+    double minimum, maximum;
+    if (j == 0) {
+      if (holder[numPts / 2] > 1.0) {
+        minimum = holder[numPts / 2] / 2.;
+        maximum = holder[numPts / 2] * 2.;
+      } else {
+        minimum = A.minS1;
+        maximum = A.maxS1;
+      }
+    } else if (j == 1) {
+      if (holder[numPts / 2] > 20.) {
+        minimum = holder[numPts / 2] / 2.;
+        maximum = holder[numPts / 2] * 2.;
+      } else {
+        minimum = A.minS2;
+        maximum = A.maxS2;
+      }
+    } else {
+      minimum = eMin;
+      maximum = eMax;
+    }
+    double par[3] = {0., 0., 0.}, err[3] = {0., 0., 0.}, chi = 0.;
+    for (int attempt = 0; attempt < 50; ++attempt) {  // REFIT (:1086, 1096-1104)
+      if (!(maximum > minimum)) maximum = minimum + 1.;
+      vector<uint64_t> h(bins, 0);
+      double n = 0., sx = 0., sxx = 0.;
+      for (double v : holder)
+        if (v >= minimum && v < maximum) {
+          ++h[min(bins - 1, int((v - minimum) / (maximum - minimum) * bins))];
+          n += 1.;
+          sx += v;
+          sxx += v * v;
+        }
+      if (n < 10.) break;
+      const double mu = sx / n, sd = sqrt(max(sxx / n - mu * mu, 1e-12));
+      const double start[3] = {n * (maximum - minimum) / bins / (sd * sqrt(2. * M_PI)), mu, sd};
+      if (nb200_hist_fit(0, h.data(), bins, minimum, maximum, start, par, err, &chi)) break;
+      if (par[1] <= 0.) {
+        minimum -= 10.;
+        continue;
+      }
+      if (j == 2 && (par[1] < (eMin + eMax) / 4. || par[1] > (eMin + eMax)) && attempt == 0) {
+        minimum = (eMin + eMax) / 4.;
+        maximum = (eMin + eMax) * 1.;
+        continue;
+      }
+      break;
+    }
+    res[j][0] = par[1];
+    res[j][1] = par[2] / par[1] * 100.;
+    res[j][2] = err[1];
+    res[j][3] = err[2] / par[1] * 1e2;
+    res[j][4] = chi;
+    printf("%lf\t", res[j][0]);
+    printf("%lf\t", res[j][1]);
+  }
+  cout << endl << "+/-" << "\t\t" << "+/-" << "\t\t" << "+/-" << "\t\t" << "+/-" << "\t\t" << "+/-" << "\t\t" << "+/-";
+  printf("\n%lf\t%lf\t%lf\t%lf\t%lf\t%lf\n", res[0][2], res[0][3], res[1][2], res[1][3], res[2][2], res[2][3]);
+  cout << "X^2 / DOF" << "\t\t\t" << "X^2 / DOF" << "\t\t\t" << "X^2 / DOF";
+  printf("\n%lf\t\t\t%lf\t\t\t%lf\tEnd Table\n", res[0][4], res[1][4], res[2][4]);
+  return 0;
 }
 
 int goodness_of_fit(const char* simFile, const char* dataFile) {  // :587-666
@@ -408,17 +493,20 @@ int main(int argc, char** argv) {
     cout << "If you write ER first, you're finding the non-Gaussian leakage of ER into the NR band." << endl << endl;
     return 1;
   }
+  if (const char* v = getenv("NB200_NUMBINS")) A.numBins = atoi(v);  // analysis.hh's numBins: 1 = a mono-energetic peak
   if (mode == 1) {
     if (argc < 3) {
       if (A.verbosity > 0) cerr << "ERROR: mode 1 requires *2* input files. 1 is not enough" << endl;
       return 1;
     }
+    if (A.numBins == 1) return peak_table(argv[1]);  // :595-598
     return goodness_of_fit(argv[1], argv[2]);
   }
   if (mode != 0) {
     cerr << "ERROR: rootNEST mode " << mode << " (WIMP limits) is not part of nest-b200; use the reference rootNEST." << endl;
     return 1;
   }
+  if (A.numBins == 1) return peak_table(argv[1]);
   if (argc == 2) {
     BandOfFile B;
     return band_of_file(argv[1], B) ? 0 : 1;

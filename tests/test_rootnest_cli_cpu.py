@@ -302,6 +302,44 @@ def test_skewness_2_table_and_propagated_errors(tool, tmp_path):
     assert checked >= 10
 
 
+def test_mono_energetic_peak_table(tool, tmp_path):
+    """numBins = 1 (GetFile's peak branch, rootNEST.cpp:1044-1137): Gaussian fits of the S1, S2 and energy histograms,
+    means, resolutions in per cent, their errors, chi^2 / DOF -- in the reference's table layout"""
+    rng = np.random.default_rng(21)
+    n = 40000
+    E, s1, s2 = rng.normal(10.0, 0.9, n), rng.normal(60.0, 8.0, n), rng.normal(2600.0, 450.0, n)
+    with open(tmp_path / "mono.txt", "w") as f:
+        f.write("E_recon [keV]\tfield [V/cm]\ttDrift [us]\tX,Y,Z [mm]\tNph\tNe-\tS1 [PE or phe]\tS1_3Dcor [phd]\t"
+                "spikeC(NON-INT)\tNe-Extr\tS2_rawArea [PE]\tS2_3Dcorr [phd]\n")
+        for e, a, b in zip(E, s1, s2):
+            f.write("%.6f\t%.6f\t%.6f\t%.0f, %.0f, %.0f\t%d\t%d\t%.6f\t%.6f\t%.6f\t%d\t%.6f\t%.6f\n" %
+                    (e, 180.0, 100.0, 10, -20, 250, 500, 250, a * 1.1, a * 0.97, a, 150, b * 0.8, b))
+    rc, out, err = run(tool, str(tmp_path / "mono.txt"), env={"NB200_NUMBINS": "1"})
+    assert rc == 0, err
+    lines = out.splitlines()
+    assert lines[0] == "S1 Mean\t\tS1 Res [%]\tS2 Mean\t\tS2 Res [%]\tEc Mean\t\tEc Res[%]"
+    vals = [float(v) for v in lines[1].split("\t") if v.strip()]
+    assert lines[2].split("\t\t") == ["+/-"] * 6
+    errs = [float(v) for v in lines[3].split("\t")]
+    assert lines[4] == "X^2 / DOF\t\t\tX^2 / DOF\t\t\tX^2 / DOF" and lines[5].endswith("\tEnd Table")
+    chis = [float(v) for v in lines[5].replace("\tEnd Table", "").split("\t\t\t")]
+    for k, (mu, sg) in enumerate(((60.0, 8.0), (2600.0, 450.0), (10.0, 0.9))):
+        mean, res, emean, eres = vals[2 * k], vals[2 * k + 1], errs[2 * k], errs[2 * k + 1]
+        assert abs(mean - mu) < 5 * emean + 0.002 * mu and abs(res - sg / mu * 100) < 5 * eres + 0.1
+        assert emean == pytest.approx(sg / np.sqrt(n), rel=0.3) and eres == pytest.approx(sg / np.sqrt(2 * n) / mu * 100, rel=0.3)
+        assert 0.6 < chis[k] < 1.6
+    # mode 1 with numBins = 1 takes the same branch (:595-598)
+    rc, out1, _ = run(tool, str(tmp_path / "mono.txt"), str(tmp_path / "mono.txt"), env={"NB200_NUMBINS": "1", "NB200_MODE": "1"})
+    assert rc == 0 and out1 == out
+    if os.path.exists(refprobe.REF_BIN_LUX):       # and the reference's own mono-energetic output goes through
+        with open(tmp_path / "ref.txt", "w") as f:
+            subprocess.run([refprobe.REF_BIN_LUX, "20000", "gamma", "10", "10", "180", "-1", "1"], stdout=f,
+                           stderr=subprocess.DEVNULL, check=True, timeout=300)
+        rc, out, err = run(tool, str(tmp_path / "ref.txt"), env={"NB200_NUMBINS": "1"})
+        v = [float(x) for x in out.splitlines()[1].split("\t") if x.strip()]
+        assert rc == 0 and 9.8 < v[4] < 10.2 and 5.0 < v[5] < 15.0 and 40 < v[0] < 80 and 1500 < v[2] < 4000
+
+
 def test_on_the_reference_binary_output(tool, tmp_path):
     """the unmodified reference's own stdout goes through: LUX_Run03 ER vs NR discrimination around 99.5 %"""
     if not os.path.exists(refprobe.REF_BIN_LUX):
