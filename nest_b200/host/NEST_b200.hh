@@ -9,11 +9,19 @@
 // event loop on the GPU through the C-ABI (include/nest_b200.h).  User detectors subclass VDetector
 // exactly as before; their virtual position maps are tabulated once (nest_b200_flatten.hh).
 #pragma once
+// the standard headers NEST.hh brings in ahead of a detector header (include/NEST/NEST.hh:70-79, RandomGen.hh:10-13)
 #include <algorithm>
+#include <array>
+#include <cassert>
 #include <cfloat>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
 #include <numeric>
+#include <random>
 #include <string>
 #include <vector>
 
@@ -21,6 +29,18 @@
 
 // What detector headers written for the reference take from NEST.hh, which the reference's translation
 // units include ahead of them (include/NEST/NEST.hh:105-111): the waveform constants ...
+#ifndef FIELD_MIN  // include/NEST/NEST.hh:81-100
+#define HIGH_E_NR 330.
+#define W_DEFAULT 13.4
+#define W_SCINT 8.5e-3
+#define NEST_AVO 6.0221409e+23
+#define ATOM_NUM 54.
+#define PHE_MIN 1e-6
+#define FIELD_MIN 1.
+#define DENSITY 2.90
+#define EPS_GAS 1.00126
+#define EPS_LIQ 1.85
+#endif
 #ifndef SAMPLE_SIZE
 #define SAMPLE_SIZE 10  // ns
 #define PULSE_WIDTH 10  // ns

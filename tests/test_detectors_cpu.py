@@ -1,0 +1,102 @@
+"""Every detector header the reference ships (include/Detectors/*.hh) recompiles UNMODIFIED against the VDetector mirror
+(nest_b200/host/NEST_b200.hh), flattens to the device POD (include/nest_b200_flatten.hh), and nb200_prepare gives it the
+per-run constants -- density, work function, drift speed, the five g2 parameters, FindNewMean -- that the reference's own
+NESTcalc computes for the same header (SetDensity NEST.cpp:2270, WorkFunction :2829, SetDriftVelocity :2352, CalculateG2
+:2065), compared as printed %.17g strings.  Needs the reference tree and its compiled objects (oracle/_ref/obj): this
+container only; no GPU."""
+import glob
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+OBJ = os.path.join(ROOT, "oracle", "_ref", "obj")
+HOST = os.path.join(ROOT, "nest_b200", "host")
+CSRC = os.path.join(ROOT, "nest_b200", "csrc")
+
+HEADERS = sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(REF, "include", "Detectors", "*.hh"))
+                 if os.path.basename(p) not in ("VDetector.hh", "LArDetector.hh"))
+
+MINE = r'''
+#include <cstdio>
+#include "NEST_b200.hh"
+#define VDetector_hh 1
+#include "%(hdr)s.hh"
+#include "nest_b200_flatten.hh"
+int main() {
+  %(cls)s d;
+  nb200_detector f;
+  nb200_flatten_storage st;
+  nb200_flatten(d, &f, &st, 33, 65);
+  nb200_run_consts rc;
+  int r = nb200_prepare(&f, 180., 0., &rc);
+  if (r) { printf("refused %%d %%s\n", r, nb200_last_error(nullptr)); return 0; }
+  printf("%%s|%%.17g %%.17g %%.17g %%.17g %%.17g %%.17g %%.17g %%.17g %%.17g %%.17g\n", d.getName().c_str(), rc.rho, rc.Wq_eV,
+         rc.alpha, rc.vD, rc.g2_params[0], rc.g2_params[1], rc.g2_params[2], rc.g2_params[3], rc.g2_params[4], rc.NewMean);
+  return 0;
+}
+'''
+
+THEIRS = r'''
+#include <chrono>   // Xed_CWRU_Dahl.hh uses std::chrono without including it
+#include <cstdio>
+#include "NEST.hh"
+#include "%(hdr)s.hh"
+using namespace NEST;
+int main() {
+  %(cls)s d;
+  NESTcalc n(&d);
+  double rho = n.SetDensity(d.get_T_Kelvin(), d.get_p_bar());
+  if (d.get_inGas()) { printf("gas\n"); return 0; }
+  NESTcalc::Wvalue w = n.WorkFunction(rho, d.get_molarMass(), d.get_OldW13eV());
+  double vD = n.SetDriftVelocity(d.get_T_Kelvin(), rho, 180., d.get_p_bar());
+  std::vector<double> g2 = n.CalculateG2(0);
+  double nm = RandomGen::rndm()->FindNewMean(d.get_sPEres());
+  printf("%%s|%%.17g %%.17g %%.17g %%.17g %%.17g %%.17g %%.17g %%.17g %%.17g %%.17g\n", d.getName().c_str(), rho, w.Wq_eV, w.alpha,
+         vD, g2[0], g2[1], g2[2], g2[3], g2[4], nm);
+  return 0;
+}
+'''
+
+
+def class_of(hdr):
+    src = open(os.path.join(REF, "include", "Detectors", hdr + ".hh")).read()
+    return re.search(r"class\s+(\w+)\s*:\s*public\s+VDetector", src).group(1)
+
+
+def build_and_run(src, exe, flags, tmp_path):
+    cpp = str(tmp_path / (os.path.basename(exe) + ".cpp"))
+    open(cpp, "w").write(src)
+    r = subprocess.run(["g++", "-O1", "-std=c++17", cpp] + flags + ["-o", exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       text=True)
+    assert r.returncode == 0, r.stdout[-3000:]
+    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=300)
+    assert r.returncode == 0
+    return [ln for ln in r.stdout.splitlines() if ln.strip()][-1]
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "include", "Detectors")), reason="reference tree not present")
+@pytest.mark.parametrize("hdr", HEADERS)
+def test_shipped_detector_header_against_the_mirror(built, hdr, tmp_path):
+    if not os.path.exists(os.path.join(OBJ, "NEST.o")):
+        pytest.skip("oracle/_ref/obj not built")
+    r = subprocess.run(["make", "-s", "-C", HOST], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    cls = class_of(hdr)
+    mine = build_and_run(MINE % {"hdr": hdr, "cls": cls}, str(tmp_path / "mine"),
+                         ["-I" + os.path.join(ROOT, "include"), "-I" + HOST, "-I" + os.path.join(REF, "include", "Detectors"),
+                          "-L" + HOST, "-lnest_b200_host", "-L" + CSRC, "-lnest_b200", "-Wl,-rpath," + HOST, "-Wl,-rpath," + CSRC],
+                         tmp_path)
+    objs = [os.path.join(OBJ, o) for o in ("NEST.o", "RandomGen.o", "VDetector.o", "ValidityTests.o", "GammaHandler.o",
+                                             "TestSpectra.o")]
+    theirs = build_and_run(THEIRS % {"hdr": hdr, "cls": cls}, str(tmp_path / "theirs"),
+                           ["-I" + os.path.join(ROOT, "oracle", "shim"), "-I" + os.path.join(REF, "include"),
+                            "-I" + os.path.join(REF, "include", "NEST"), "-I" + os.path.join(REF, "include", "Detectors")] + objs,
+                           tmp_path)
+    if theirs == "gas":
+        assert mine.startswith("refused")           # gas-phase detectors are outside this path; nb200_prepare says so
+        return
+    assert mine == theirs, (hdr, mine, theirs)
