@@ -461,6 +461,11 @@ int nb200_debug_binomial_fixed(nb200_ctx* ctx, uint64_t seed, uint64_t first_eve
  * Binomial(2^b, p), b = 0..12 (8204 entries: table b at offset 2^b - 1 + b). */
 int nb200_debug_zig_tables(int n_layers, double* x, double* f, uint32_t* k, double* w);
 int nb200_debug_alias_tables(double p, int n_entries, uint32_t* thr, uint32_t* alias);
+/* Host-only test hook: the flattened position maps exactly as the kernels evaluate them (closed form or bilinear
+ * (r, z) table), at n points: s1 = FitS1(x, y, z), s2 = FitS2(x, y), ef = FitEF(x, y, z), tba = FitTBA(x, y, z)[1]
+ * (VDetector.hh:131-224); any output may be NULL.  Tables must be host-resident (as nb200_flatten leaves them). */
+int nb200_debug_maps(const nb200_detector* det, size_t n, const double* x, const double* y, const double* z, double* s1,
+                     double* s2, double* ef, double* tba);
 
 /* counters for the bench: kernels launched by this context since creation */
 uint64_t nb200_launch_count(const nb200_ctx* ctx);

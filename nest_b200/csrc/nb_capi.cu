@@ -1888,6 +1888,18 @@ int nb200_debug_binomial(nb200_ctx* c, uint64_t seed, uint64_t first_event, size
 }
 
 // host-only test hooks (no device needed): the tables the samplers above are built on
+int nb200_debug_maps(const nb200_detector* det, size_t n, const double* x, const double* y, const double* z, double* s1,
+                     double* s2, double* ef, double* tba) {
+  if (!det || !x || !y || !z) return NB200_EINVAL;
+  for (size_t i = 0; i < n; ++i) {
+    if (s1) s1[i] = fit_s1(det->FitS1, x[i], y[i], z[i]);
+    if (s2) s2[i] = fit_s2(det->FitS2, x[i], y[i]);
+    if (ef) ef[i] = fit_ef(det->FitEF, x[i], y[i], z[i]);
+    if (tba) tba[i] = fit_tba(det->FitTBA, x[i], y[i], z[i]);
+  }
+  return 0;
+}
+
 int nb200_debug_zig_tables(int n_layers, double* x, double* f, uint32_t* k, double* w) {
   if (n_layers != NB_ZIG_N || !x || !f || !k || !w) return NB200_EINVAL;
   build_zig_tables(x, f, k, w);
