@@ -766,11 +766,17 @@ int nb200_yields(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo,
   P.seed = 0;
   double *dE = nullptr, *dF = nullptr, *dO = nullptr;
   if (mem_kind == NB200_MEM_HOST) {
-    NB_CUDA(c, cudaMalloc(&dE, n * 8));
-    NB_CUDA(c, cudaMalloc(&dF, n * 8));
-    NB_CUDA(c, cudaMalloc(&dO, n * 48));
-    NB_CUDA(c, cudaMemcpyAsync(dE, E, n * 8, cudaMemcpyHostToDevice, c->stream));
-    NB_CUDA(c, cudaMemcpyAsync(dF, field, n * 8, cudaMemcpyHostToDevice, c->stream));
+    cudaError_t e = cudaMalloc(&dE, n * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&dF, n * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&dO, n * 48);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dE, E, n * 8, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dF, field, n * 8, cudaMemcpyHostToDevice, c->stream);
+    if (e != cudaSuccess) {  // nothing allocated so far may leak
+      if (dE) cudaFree(dE);
+      if (dF) cudaFree(dF);
+      if (dO) cudaFree(dO);
+      return fail(c, NB200_ENOMEM, cudaGetErrorString(e));
+    }
     P.E = dE;
     P.field = dF;
     P.out = dO;
