@@ -126,6 +126,20 @@ bool band_of_file(const char* name, BandOfFile& B) {
     cerr << "ERROR: band statistics failed (numBins, logBins?)" << endl;
     return false;
   }
+  // a slice with entries but too few filled log bins for a three-parameter fit keeps its moments (ROOT would return
+  // its start values, which are these): mean, sigma, sigma / sqrt(N), sigma / sqrt(2 N)
+  for (int j = 0; j < nb; ++j) {
+    double* f = &B.fit[8 * size_t(j)];
+    const double* m = &B.mom[7 * size_t(j)];
+    if (f[7] == 0. && acc[j] >= 2 && m[3] > 0.) {
+      f[1] = m[2];
+      f[2] = m[3];
+      f[3] = m[4];
+      f[4] = m[4] / sqrt(2.);
+      f[7] = -1.;  // flag: moments, not a fit
+      if (A.verbosity > 0) cerr << "Too few filled bins for a fit at S1 = " << m[0] << ": keeping the moments" << endl;
+    }
+  }
   if (B.events < 20000 && nb > 1 && skewness != 0) {  // :1037-1042
     skewness = 0;
     cerr << "WARNING: Not enough stats (at least 10^5 events) for skew fits so doing Gaussian" << endl;
@@ -409,7 +423,7 @@ int leakage_table(const char* file1, const char* file2) {  // :668-950
   vector<double> gx, gy;
   const vector<double>& nrMom = ERis2nd ? B.mom : B2.mom;
   for (int i = 0; i < nb; ++i)
-    if (nr[8 * size_t(i) + 7] > 0.) {  // bins whose fit exists (the reference would feed the graph its empty bins too)
+    if (nr[8 * size_t(i) + 7] != 0.) {  // bins whose fit exists (the reference would feed the graph its empty bins too)
       gx.push_back(nrMom[7 * size_t(i)]);
       gy.push_back(nr[8 * size_t(i) + 1] + NUMSIGABV * nr[8 * size_t(i) + 2]);
     }
