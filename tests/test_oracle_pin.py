@@ -147,3 +147,26 @@ def test_oracle_reproduces_reference_binary_stdout(orc):
         else:
             exp += "%.6f\t%.6f\t%.6f\t%i\t%.6f\t%.6f" % (s1[2], s1[5], s1[7], int(s2[0]), s2[4], s2[7])
         assert ln.strip() == exp, (j, ln, exp)
+
+
+def test_oracle_stage_calls_equal_live_reference(orc, ref):
+    """GetQuanta, GetS1 and GetS2 on fixed inputs -- the inputs of the GPU stage-call tests -- bit for bit (same seed,
+    same generator, same draw order)"""
+    import test_gpu_zz_stage_api as cases
+    mo = capi.model(1)
+    widths = list(mo.NRERWidthsParam)[:mo.n_widths]
+    det = capi.detector("LUX_Run03")
+    rc = capi.prepare(det, 180.0)
+    for name, (y6, skew) in cases.RECORDS.items():
+        ai, ad = ref.quanta(5, 3000, y6, RHO_LUX, widths, skew)
+        bi, bd = orc.quanta(5, 3000, y6, RHO_LUX, widths, skew)
+        assert np.array_equal(ai, bi) and np.array_equal(ad, bd), name
+    for name, (Nph, pos, spos, energy, mode) in cases.S1_CASES.items():
+        n = 3000 if Nph < 5000 else 500
+        a = ref.s1(6, n, Nph, pos, spos, rc.vD, rc.vD_middle, capi.beta, 180.0, energy, mode)
+        b = orc.s1(6, n, Nph, pos, spos, rc.vD, rc.vD_middle, capi.beta, 180.0, energy, mode)
+        assert np.array_equal(a, b), name
+    for name, (Ne, pos, spos, dt, field) in cases.S2_CASES.items():
+        a = ref.s2(7, 3000, Ne, pos, spos, dt, rc.vD, field)
+        b = orc.s2(7, 3000, Ne, pos, spos, dt, rc.vD, field)
+        assert np.array_equal(a, b), name
