@@ -461,6 +461,12 @@ int nb200_debug_binomial_fixed(nb200_ctx* ctx, uint64_t seed, uint64_t first_eve
  * Binomial(2^b, p), b = 0..12 (8204 entries: table b at offset 2^b - 1 + b). */
 int nb200_debug_zig_tables(int n_layers, double* x, double* f, uint32_t* k, double* w);
 int nb200_debug_alias_tables(double p, int n_entries, uint32_t* thr, uint32_t* alias);
+/* Host-only: NESTcalc::SetDriftVelocity_NonUniform (NEST.cpp:2664-2697, liquid): the table of effective drift speeds
+ * [mm/us] from z = k z_step (k = 0, 1, ... while z < TopDrift) to the liquid surface along the line (x, y), through the
+ * detector's FitEF map -- each entry the same sum, in the same order, as the reference's O(n^2) loop.  Call with
+ * table == NULL to get the length in *n; then with a buffer of that many doubles. */
+int nb200_drift_table(const nb200_detector* det, double z_step, double x, double y, double* table, size_t* n);
+
 /* Host-only test hook: the flattened position maps exactly as the kernels evaluate them (closed form or bilinear
  * (r, z) table), at n points: s1 = FitS1(x, y, z), s2 = FitS2(x, y), ef = FitEF(x, y, z), tba = FitTBA(x, y, z)[1]
  * (VDetector.hh:131-224); any output may be NULL.  Tables must be host-resident (as nb200_flatten leaves them). */

@@ -1894,6 +1894,21 @@ int nb200_debug_binomial(nb200_ctx* c, uint64_t seed, uint64_t first_event, size
 }
 
 // host-only test hooks (no device needed): the tables the samplers above are built on
+int nb200_drift_table(const nb200_detector* det, double z_step, double x, double y, double* table, size_t* n) {
+  if (!det || !n || !(z_step > 0.) || !(det->TopDrift > 0.)) return NB200_EINVAL;
+  if (!table) {
+    size_t k = 0;
+    for (double z = 0.0; z < det->TopDrift; z += z_step) ++k;  // the reference's own loop (:2669)
+    *n = k;
+    return 0;
+  }
+  const std::vector<double> t = host::drift_table_nonuniform(*det, z_step, x, y);
+  if (*n < t.size()) return NB200_EINVAL;
+  for (size_t i = 0; i < t.size(); ++i) table[i] = t[i];
+  *n = t.size();
+  return 0;
+}
+
 int nb200_debug_maps(const nb200_detector* det, size_t n, const double* x, const double* y, const double* z, double* s1,
                      double* s2, double* ef, double* tba) {
   if (!det || !x || !y || !z) return NB200_EINVAL;

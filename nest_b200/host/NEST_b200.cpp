@@ -117,6 +117,16 @@ double NESTcalc::SetDensity(double Kelvin, double bara) {
   if (r) throw runtime_error(nb200_last_error(nullptr));
   return c.rho;
 }
+vector<double> NESTcalc::SetDriftVelocity_NonUniform(double, double zStep, double Kelvin, double, double dx, double dy) {
+  nb200_detector d = flat();
+  d.T_Kelvin = Kelvin;
+  size_t n = 0;
+  if (nb200_drift_table(&d, zStep, dx, dy, nullptr, &n)) throw runtime_error("SetDriftVelocity_NonUniform: bad z step or geometry");
+  vector<double> t(n);
+  if (nb200_drift_table(&d, zStep, dx, dy, t.data(), &n)) throw runtime_error("SetDriftVelocity_NonUniform failed");
+  t.resize(n);
+  return t;
+}
 double NESTcalc::SetDriftVelocity(double Kelvin, double, double eField, double) {
   nb200_detector d = flat();
   d.T_Kelvin = Kelvin;

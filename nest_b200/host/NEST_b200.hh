@@ -231,6 +231,8 @@ class NESTcalc {
 
   double SetDensity(double Kelvin, double bara);                                // NEST.cpp:2270
   double SetDriftVelocity(double Kelvin, double Density, double eField, double Bar = 1.5);  // :2352
+  std::vector<double> SetDriftVelocity_NonUniform(double rho, double zStep, double Kelvin, double Bar, double dx,
+                                                  double dy);                   // :2664 (liquid; host, through FitEF)
   std::vector<double> CalculateG2(int verbosity = 1);                           // :2065 (prints the banner)
   static Wvalue WorkFunction(double rho, double MolarMass, bool OldW13eV = true);  // :2829
 

@@ -22,6 +22,8 @@ int main() {
     const double keV = 5., field = 180.;
     const double rho = n.SetDensity(detector->get_T_Kelvin(), detector->get_p_bar());
     const double vD = n.SetDriftVelocity(detector->get_T_Kelvin(), rho, field);
+    vector<double> vTable = n.SetDriftVelocity_NonUniform(rho, 0.5, detector->get_T_Kelvin(), detector->get_p_bar(), 10., -20.);
+    if (vTable.empty() || !(vTable[0] > 0.)) status = 2;
     vector<double> g2_params = n.CalculateG2(0);
     const double pos_x = 10., pos_y = -20., pos_z = 250.;
     const double driftTime = (detector->get_TopDrift() - pos_z) / vD;

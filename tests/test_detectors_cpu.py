@@ -50,6 +50,13 @@ int main() {
     for (int k = 0; k < 4; ++k) worst[k] = std::max(worst[k], fabs(a[k] - b[k]) / std::max(fabs(b[k]), 1e-300));
   }
   fprintf(stderr, "maps %%.3e %%.3e %%.3e %%.3e\n", worst[0], worst[1], worst[2], worst[3]);
+  {  // SetDriftVelocity_NonUniform with the reference's signature, through the flattened FitEF
+    NEST::NESTcalc n(&d);
+    std::vector<double> vt = n.SetDriftVelocity_NonUniform(rc.rho, 2.0, d.get_T_Kelvin(), d.get_p_bar(), 10., -20.);
+    fprintf(stderr, "vtable %%zu", vt.size());
+    for (size_t i = 0; i < vt.size(); i += 37) fprintf(stderr, " %%.17g", vt[i]);
+    fprintf(stderr, " %%.17g\n", vt.back());
+  }
   printf("%%s|%%.17g %%.17g %%.17g %%.17g %%.17g %%.17g %%.17g %%.17g %%.17g %%.17g\n", d.getName().c_str(), rc.rho, rc.Wq_eV,
          rc.alpha, rc.vD, rc.g2_params[0], rc.g2_params[1], rc.g2_params[2], rc.g2_params[3], rc.g2_params[4], rc.NewMean);
   return 0;
@@ -71,6 +78,12 @@ int main() {
   double vD = n.SetDriftVelocity(d.get_T_Kelvin(), rho, 180., d.get_p_bar());
   std::vector<double> g2 = n.CalculateG2(0);
   double nm = RandomGen::rndm()->FindNewMean(d.get_sPEres());
+  {
+    std::vector<double> vt = n.SetDriftVelocity_NonUniform(rho, 2.0, d.get_T_Kelvin(), d.get_p_bar(), 10., -20.);
+    fprintf(stderr, "vtable %%zu", vt.size());
+    for (size_t i = 0; i < vt.size(); i += 37) fprintf(stderr, " %%.17g", vt[i]);
+    fprintf(stderr, " %%.17g\n", vt.back());
+  }
   printf("%%s|%%.17g %%.17g %%.17g %%.17g %%.17g %%.17g %%.17g %%.17g %%.17g %%.17g\n", d.getName().c_str(), rho, w.Wq_eV, w.alpha,
          vD, g2[0], g2[1], g2[2], g2[3], g2[4], nm);
   return 0;
@@ -92,7 +105,9 @@ def build_and_run(src, exe, flags, tmp_path):
     r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
     assert r.returncode == 0
     maps = [ln for ln in r.stderr.splitlines() if ln.startswith("maps ")]
-    return [ln for ln in r.stdout.splitlines() if ln.strip()][-1], ([float(v) for v in maps[-1].split()[1:]] if maps else None)
+    vt = [ln for ln in r.stderr.splitlines() if ln.startswith("vtable ")]
+    return ([ln for ln in r.stdout.splitlines() if ln.strip()][-1], ([float(v) for v in maps[-1].split()[1:]] if maps else None),
+            vt[-1] if vt else None)
 
 
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "include", "Detectors")), reason="reference tree not present")
@@ -103,13 +118,13 @@ def test_shipped_detector_header_against_the_mirror(built, hdr, tmp_path):
     r = subprocess.run(["make", "-s", "-C", HOST], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0, r.stdout
     cls = class_of(hdr)
-    mine, maps = build_and_run(MINE % {"hdr": hdr, "cls": cls}, str(tmp_path / "mine"),
+    mine, maps, vt_mine = build_and_run(MINE % {"hdr": hdr, "cls": cls}, str(tmp_path / "mine"),
                          ["-I" + os.path.join(ROOT, "include"), "-I" + HOST, "-I" + os.path.join(REF, "include", "Detectors"),
                           "-L" + HOST, "-lnest_b200_host", "-L" + CSRC, "-lnest_b200", "-Wl,-rpath," + HOST, "-Wl,-rpath," + CSRC],
                          tmp_path)
     objs = [os.path.join(OBJ, o) for o in ("NEST.o", "RandomGen.o", "VDetector.o", "ValidityTests.o", "GammaHandler.o",
                                              "TestSpectra.o")]
-    theirs, _ = build_and_run(THEIRS % {"hdr": hdr, "cls": cls}, str(tmp_path / "theirs"),
+    theirs, _, vt_theirs = build_and_run(THEIRS % {"hdr": hdr, "cls": cls}, str(tmp_path / "theirs"),
                            ["-I" + os.path.join(ROOT, "oracle", "shim"), "-I" + os.path.join(REF, "include"),
                             "-I" + os.path.join(REF, "include", "NEST"), "-I" + os.path.join(REF, "include", "Detectors")] + objs,
                            tmp_path)
@@ -125,3 +140,6 @@ def test_shipped_detector_header_against_the_mirror(built, hdr, tmp_path):
         # (Xed_CWRU_Dahl.hh:91-114).  A table cannot hold that; the detector runs with a given field (inField >= 0) only.
         maps[2] = 0.0
     assert max(maps) < (1e-12 if hdr == "LUX_Run03" else 2e-4), (hdr, maps)
+    # the drift-speed table of SetDriftVelocity_NonUniform (NEST.cpp:2664-2697), sampled every 37th entry, as %.17g strings
+    if hdr != "Xed_CWRU_Dahl":
+        assert vt_mine is not None and vt_mine == vt_theirs, (hdr, vt_mine, vt_theirs)
