@@ -461,6 +461,15 @@ int nb200_debug_binomial_fixed(nb200_ctx* ctx, uint64_t seed, uint64_t first_eve
  * Binomial(2^b, p), b = 0..12 (8204 entries: table b at offset 2^b - 1 + b). */
 int nb200_debug_zig_tables(int n_layers, double* x, double* f, uint32_t* k, double* w);
 int nb200_debug_alias_tables(double p, int n_entries, uint32_t* thr, uint32_t* alias);
+/* Host-only: NESTcalc::GetDensity (NEST.cpp:2278-2350): xenon density [g/cm^3] at (Kelvin, bara); *in_gas in/out as the
+ * reference's inGas (liquid, solid below 161.4 K, or the real-gas law; the gas phase is reported here even though the
+ * event chain refuses gas-phase detectors). */
+double nb200_density(double Kelvin, double bara, double molarMass, int* in_gas);
+
+/* Host-only: NESTcalc::GetDriftVelocity_Liquid (NEST.cpp:2366-2521): electron drift speed [mm/us] in liquid xenon at
+ * (Kelvin, field [V/cm]); NaN outside the tabulated 100-230 K. */
+double nb200_drift_velocity_liquid(double Kelvin, double field);
+
 /* Host-only: NESTcalc::SetDriftVelocity_NonUniform (NEST.cpp:2664-2697, liquid): the table of effective drift speeds
  * [mm/us] from z = k z_step (k = 0, 1, ... while z < TopDrift) to the liquid surface along the line (x, y), through the
  * detector's FitEF map -- each entry the same sum, in the same order, as the reference's O(n^2) loop.  Call with

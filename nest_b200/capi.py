@@ -105,7 +105,7 @@ EXPORTS = [
     "nb200_band_reset", "nb200_band_attach", "nb200_fp64_peak", "nb200_timing_enable", "nb200_timing_read", "nb200_se_stats", "nb200_band_fetch", "nb200_band_device_buffer", "nb200_allreduce_hist",
     "nb200_band_hist_bytes", "nb200_band_finalize", "nb200_band_chi2", "nb200_band_leakage", "nb200_band_fit_gauss", "nb200_band_leakage_gauss", "nb200_hist_fit", "nb200_hist_fit_cov", "nb200_band_leakage_skew_cov", "nb200_graph_fit", "nb200_band_leakage_skew", "nb200_lar", "nb200_launch_count",
     "nb200_debug_hitmath", "nb200_debug_binomial", "nb200_debug_normal", "nb200_debug_binomial_fixed",
-    "nb200_debug_zig_tables", "nb200_debug_alias_tables", "nb200_debug_maps", "nb200_drift_table"]
+    "nb200_debug_zig_tables", "nb200_debug_alias_tables", "nb200_debug_maps", "nb200_drift_table", "nb200_density", "nb200_drift_velocity_liquid"]
 
 _lib = None
 

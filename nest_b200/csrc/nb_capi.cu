@@ -1894,6 +1894,19 @@ int nb200_debug_binomial(nb200_ctx* c, uint64_t seed, uint64_t first_event, size
 }
 
 // host-only test hooks (no device needed): the tables the samplers above are built on
+double nb200_drift_velocity_liquid(double Kelvin, double field) {
+  bool ok = true;
+  const double v = host::drift_velocity_liquid(Kelvin, field, &ok);
+  return ok ? v : std::nan("");
+}
+
+double nb200_density(double Kelvin, double bara, double molarMass, int* in_gas) {
+  bool g = in_gas && *in_gas != 0;
+  const double rho = host::density(Kelvin, bara, g, molarMass, nullptr);
+  if (in_gas) *in_gas = g ? 1 : 0;
+  return rho;
+}
+
 int nb200_drift_table(const nb200_detector* det, double z_step, double x, double y, double* table, size_t* n) {
   if (!det || !n || !(z_step > 0.) || !(det->TopDrift > 0.)) return NB200_EINVAL;
   if (!table) {

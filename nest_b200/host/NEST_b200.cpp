@@ -135,6 +135,25 @@ double NESTcalc::SetDriftVelocity(double Kelvin, double, double eField, double) 
   if (nb200_prepare(&d, eField, 0., &c)) throw runtime_error(nb200_last_error(nullptr));
   return c.vD;
 }
+double NESTcalc::GetDriftVelocity_Liquid(double Kelvin, double eField, double, double, short) {
+  const double v = nb200_drift_velocity_liquid(Kelvin, eField);
+  if (v != v) throw runtime_error("ERROR: TEMPERATURE OUT OF RANGE (100-230 K)");  // NEST.cpp:2410-2416
+  return v;
+}
+double NESTcalc::GetDriftVelocity(double Kelvin, double Density, double eField, bool inGas, double Bar) {
+  if (inGas) throw runtime_error("GetDriftVelocity: gas-phase drift (MagBoltz) is outside the GPU path");
+  return GetDriftVelocity_Liquid(Kelvin, eField, Density, Bar);
+}
+double NESTcalc::GetDensity(double Kelvin, double bara, bool& inGas, uint64_t, double molarMass) {
+  int g = inGas ? 1 : 0;
+  const double rho = nb200_density(Kelvin, bara, molarMass, &g);
+  inGas = g != 0;
+  return rho;
+}
+double NESTcalc::NexONi(double energy, double density) {
+  Wvalue w = WorkFunction(density, fdetector->get_molarMass(), fdetector->get_OldW13eV());
+  return w.alpha * erf(0.05 * energy);
+}
 NESTcalc::Wvalue NESTcalc::WorkFunction(double rho, double MolarMass, bool OldW13eV) {
   double alpha = 0.067366 + rho * 0.039693;
   double eDensity = (rho / MolarMass) * 6.0221409e+23 * 54.;

@@ -231,6 +231,12 @@ class NESTcalc {
 
   double SetDensity(double Kelvin, double bara);                                // NEST.cpp:2270
   double SetDriftVelocity(double Kelvin, double Density, double eField, double Bar = 1.5);  // :2352
+  // the static forms (NEST.hh:373-402), liquid phase; gas-phase conditions are outside this path (std::runtime_error)
+  static double GetDriftVelocity(double Kelvin, double Density, double eField, bool inGas, double Bar);
+  static double GetDriftVelocity_Liquid(double Kelvin, double eField, double Density, double Bar = 1.5, short SD = -1);
+  static double GetDensity(double Kelvin, double bara, bool& inGas, uint64_t evtNum = 0, double molarMass = 131.293);
+  double NexONi(double energy, double density);                                 // :2850
+  void SetDetector(VDetector* detector) { fdetector = detector; flattened = false; }
   std::vector<double> SetDriftVelocity_NonUniform(double rho, double zStep, double Kelvin, double Bar, double dx,
                                                   double dy);                   // :2664 (liquid; host, through FitEF)
   std::vector<double> CalculateG2(int verbosity = 1);                           // :2065 (prints the banner)

@@ -143,3 +143,55 @@ def test_shipped_detector_header_against_the_mirror(built, hdr, tmp_path):
     # the drift-speed table of SetDriftVelocity_NonUniform (NEST.cpp:2664-2697), sampled every 37th entry, as %.17g strings
     if hdr != "Xed_CWRU_Dahl":
         assert vt_mine is not None and vt_mine == vt_theirs, (hdr, vt_mine, vt_theirs)
+
+
+STATICS = r'''
+#include <chrono>
+#include <cstdio>
+#include "%(inc)s"
+%(pre)s
+using namespace NEST;
+int main() {
+  %(cls)s d;
+  NESTcalc n(&d);
+  for (double T = 162.; T < 200.; T += 3.7)
+    for (double F = 20.; F < 5000.; F *= 2.3) {
+      bool inGas = false;
+      double rho = NESTcalc::GetDensity(T, 1.8, inGas, 0, 131.293);
+      if (inGas) continue;
+      printf("%%.17g %%.17g %%.17g %%.17g\n", rho, NESTcalc::GetDriftVelocity_Liquid(T, F, rho),
+             NESTcalc::GetDriftVelocity(T, rho, F, false, 1.8), n.NexONi(F / 50., rho));
+    }
+  return 0;
+}
+'''
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "include", "Detectors")), reason="reference tree not present")
+def test_static_density_and_drift_velocity_like_the_reference(built, tmp_path):
+    """NESTcalc::GetDensity, GetDriftVelocity(_Liquid) and NexONi of the host mirror (NEST.hh:373-402, 429) against the
+    reference's own, over a grid of temperatures and fields, as %.17g strings"""
+    if not os.path.exists(os.path.join(OBJ, "NEST.o")):
+        pytest.skip("oracle/_ref/obj not built")
+    r = subprocess.run(["make", "-s", "-C", HOST], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+
+    def run(src, name, flags):
+        cpp, exe = str(tmp_path / (name + ".cpp")), str(tmp_path / name)
+        open(cpp, "w").write(src)
+        r = subprocess.run(["g++", "-O1", "-std=c++17", cpp] + flags + ["-o", exe], stdout=subprocess.PIPE,
+                           stderr=subprocess.STDOUT, text=True)
+        assert r.returncode == 0, r.stdout[-3000:]
+        r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=300)
+        assert r.returncode == 0
+        return r.stdout.splitlines()
+
+    mine = run(STATICS % {"inc": "LUX_Run03_b200.hh", "pre": "", "cls": "DetectorExample_LUX_RUN03"}, "mine",
+               ["-I" + os.path.join(ROOT, "include"), "-I" + HOST, "-L" + HOST, "-lnest_b200_host", "-L" + CSRC, "-lnest_b200",
+                "-Wl,-rpath," + HOST, "-Wl,-rpath," + CSRC])
+    objs = [os.path.join(OBJ, o) for o in ("NEST.o", "RandomGen.o", "VDetector.o", "ValidityTests.o", "GammaHandler.o",
+                                             "TestSpectra.o")]
+    theirs = run(STATICS % {"inc": "NEST.hh", "pre": '#include "LUX_Run03.hh"', "cls": "DetectorExample_LUX_RUN03"}, "theirs",
+                 ["-I" + os.path.join(ROOT, "oracle", "shim"), "-I" + os.path.join(REF, "include"),
+                  "-I" + os.path.join(REF, "include", "NEST"), "-I" + os.path.join(REF, "include", "Detectors")] + objs)
+    assert len(mine) > 20 and mine == theirs            # the liquid part of the grid (the rest is gas at 1.8 bar)
