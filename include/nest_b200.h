@@ -263,6 +263,15 @@ int nb200_prepare(nb200_detector* det, double inField, double z_step, nb200_run_
  * Philox host stream keyed by seed.  base/exponent: caller arrays of 100 doubles. */
 int nb200_wimp_prep(double mass_GeV, double eStep, double dayNum, uint64_t seed, double* base,
                     double* exponent, double* integral, double* xMax, double* divisor);
+/* The same with the isotope of every WIMP_dRate call given by the caller, in call order: the table's points first
+ * (int(100/eStep) + 1, or int(1000/eStep) + 1 below 10 GeV; fewer if the spectrum ends in 100 zeros), then the
+ * 1e6 terms of the integral.  With the reference's own draws (RandomGen::SelectRanXeAtom under the reference's seed)
+ * the table equals the reference's to rounding.  NB200_EINVAL when the list is too short. */
+int nb200_wimp_prep_iso(double mass_GeV, double eStep, double dayNum, const int32_t* isotopes, size_t n_isotopes,
+                        double* base, double* exponent, double* integral, double* xMax, double* divisor);
+/* Host-only: TestSpectra::WIMP_dRate (TestSpectra.cpp:251-390) [events/kg/day/keV] with the Xe isotope the
+ * reference draws at :278 made an argument; *ok = 0 where the reference throws ("velocity integral broke"). */
+double nb200_wimp_drate(double ER_keV, double mass_GeV, double dayNum, int isotope_A, int* ok);
 /* Poisson draw for the WIMP/8B event count (execNEST.cpp:482-488), host stream keyed by seed */
 uint64_t nb200_poisson(double mean, uint64_t seed);
 
@@ -434,13 +443,13 @@ int nb200_fp64_peak(nb200_ctx* ctx, double* tflops);
  * pointers.  Used by tests/test_gpu_hitmath.py to hold them to 1e-15 against libm. */
 int nb200_debug_hitmath(nb200_ctx* ctx, size_t n, const uint32_t* bits3, double* out3);
 
-/* Test hook: the standard normals of the S1 hit loop (256-layer ziggurat, replacing the
+/* Test hook: the standard normals of the S1 hit loop (2048-layer ziggurat, replacing the
  * Box-Muller of RandomGen::rand_gauss, src/RandomGen.cpp:44-53, for the per-hit draws of
- * NEST.cpp:1367-1429), drawn exactly as the hit kernel draws them: pair p = hits 2(p%1024),
- * 2(p%1024)+1 of event first_event + p/1024.  out = 2*pairs doubles, kind = 2*pairs bytes or
- * NULL (0: layer core, 1: wedge / tail completion); host pointers.
+ * NEST.cpp:1367-1429), drawn by the very device function the hit kernel and its finisher call: slot s =
+ * the three photo-electrons of Philox block s % 1024 of event first_event + s / 1024.  out = 3*slots doubles,
+ * kind = 3*slots bytes or NULL (0: layer core, 1: wedge / tail completion); host pointers.
  * tests/test_gpu_samplers.py holds them to N(0,1) (KS, moments, tail mass). */
-int nb200_debug_normal(nb200_ctx* ctx, uint64_t seed, uint64_t first_event, size_t pairs, double* out,
+int nb200_debug_normal(nb200_ctx* ctx, uint64_t seed, uint64_t first_event, size_t slots, double* out,
                        unsigned char* kind);
 
 /* Test hook: `count` draws of the chain's binomial sampler (the device replacement of

@@ -23,7 +23,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 # rejection of the spectra and the table bounds of the photo-electron test switched off -- the plain per-lane
 # algorithms.  tests/test_gpu_variants.py requires the product library to reproduce it bit for bit.
 LIB_PLAIN = os.path.join(CSRC, "libnest_b200_plain.so")
-PLAIN_FLAGS = ["-DNB_BINOM_COOP=0", "-DNB_COOP_REJECT=0", "-DNB_PE_NO_BOUNDS"]
+PLAIN_FLAGS = ["-DNB_COOP_REJECT=0", "-DNB_PE_NO_BOUNDS"]
 
 
 def needs_build(lib=LIB):

@@ -101,7 +101,7 @@ class BandHist(C.Structure):
 EXPORTS = [
     "nb200_abi_version", "nb200_sizeof", "nb200_create", "nb200_destroy", "nb200_last_error", "nb200_set_stream",
     "nb200_synchronize", "nb200_detector_builtin", "nb200_model_default", "nb200_analysis_default",
-    "nb200_prepare", "nb200_wimp_prep", "nb200_poisson", "nb200_yields", "nb200_quanta", "nb200_s2", "nb200_s1", "nb200_run", "nb200_run_async",
+    "nb200_prepare", "nb200_wimp_prep", "nb200_wimp_prep_iso", "nb200_wimp_drate", "nb200_poisson", "nb200_yields", "nb200_quanta", "nb200_s2", "nb200_s1", "nb200_run", "nb200_run_async",
     "nb200_band_reset", "nb200_band_attach", "nb200_fp64_peak", "nb200_timing_enable", "nb200_timing_read", "nb200_se_stats", "nb200_band_fetch", "nb200_band_device_buffer", "nb200_allreduce_hist",
     "nb200_band_hist_bytes", "nb200_band_finalize", "nb200_band_chi2", "nb200_band_leakage", "nb200_band_fit_gauss", "nb200_band_leakage_gauss", "nb200_hist_fit", "nb200_hist_fit_cov", "nb200_band_leakage_skew_cov", "nb200_graph_fit", "nb200_band_leakage_skew", "nb200_lar", "nb200_launch_count",
     "nb200_debug_hitmath", "nb200_debug_binomial", "nb200_debug_normal", "nb200_debug_binomial_fixed",
@@ -145,6 +145,9 @@ def lib():
     L.nb200_analysis_default.argtypes = [C.c_int, C.POINTER(Analysis)]
     L.nb200_prepare.argtypes = [C.POINTER(Detector), C.c_double, C.c_double, C.POINTER(RunConsts)]
     L.nb200_wimp_prep.argtypes = [C.c_double, C.c_double, C.c_double, C.c_uint64, c_dp, c_dp, c_dp, c_dp, c_dp]
+    L.nb200_wimp_prep_iso.argtypes = [C.c_double, C.c_double, C.c_double, c_ip, C.c_size_t, c_dp, c_dp, c_dp, c_dp, c_dp]
+    L.nb200_wimp_drate.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_int)]
+    L.nb200_wimp_drate.restype = C.c_double
     L.nb200_poisson.argtypes = [C.c_double, C.c_uint64]
     L.nb200_poisson.restype = C.c_uint64
     L.nb200_yields.argtypes = [vp, C.POINTER(Detector), C.POINTER(Model), C.c_int, C.c_size_t, vp, vp,
@@ -391,6 +394,33 @@ def source(kind, species, eMin=0.0, eMax=0.0, inField=180.0, fixed_pos=0, xyz=(0
     return s
 
 
+class WimpTable:
+    """TestSpectra::WIMP_spectrum_prep (TestSpectra.hh:43-49) from nb200_wimp_prep (isotopes from the Philox host
+    stream of `seed`) or nb200_wimp_prep_iso (isotopes given, e.g. the reference's own draws)."""
+
+    def __init__(self, mass, eStep=5.0, day=0.0, seed=1, isotopes=None):
+        self.mass, self.day = float(mass), float(day)
+        self.base, self.exponent = np.zeros(100), np.zeros(100)
+        integ, xmax, div = C.c_double(), C.c_double(), C.c_double()
+        dp = lambda a: a.ctypes.data_as(c_dp)
+        if isotopes is None:
+            rc = lib().nb200_wimp_prep(mass, eStep, day, seed, dp(self.base), dp(self.exponent), C.byref(integ),
+                                       C.byref(xmax), C.byref(div))
+        else:
+            iso = np.ascontiguousarray(isotopes, np.int32)
+            rc = lib().nb200_wimp_prep_iso(mass, eStep, day, iso.ctypes.data_as(c_ip), iso.size, dp(self.base),
+                                           dp(self.exponent), C.byref(integ), C.byref(xmax), C.byref(div))
+        if rc:
+            raise NestB200Error(rc, lib().nb200_last_error(None).decode())
+        self.integral, self.xMax, self.divisor = integ.value, xmax.value, div.value
+
+    def attach(self, src):
+        """point a Source at this table (keeps the arrays alive through self)"""
+        src.wimp_base, src.wimp_exponent = self.base.ctypes.data_as(c_dp), self.exponent.ctypes.data_as(c_dp)
+        src.wimp_xMax, src.wimp_divisor, src.wimp_mass, src.wimp_day = self.xMax, self.divisor, self.mass, self.day
+        return src
+
+
 SOA_COLUMNS = (SOA_F64 + SOA_I32 + ["s1_%d" % i for i in range(9)] + ["s2_%d" % i for i in range(9)] + SOA_TAIL)
 
 
@@ -550,10 +580,11 @@ class Context:
         self._check(lib().nb200_debug_binomial_fixed(self.h, seed, first_event, out.size, int(n), float(p), _dptr(out)))
         return out
 
-    def debug_normal(self, pairs, seed=1, first_event=0):
-        out = np.empty(2 * int(pairs))
-        kind = np.empty(2 * int(pairs), np.uint8)
-        self._check(lib().nb200_debug_normal(self.h, seed, first_event, int(pairs), _dptr(out), _dptr(kind)))
+    def debug_normal(self, slots, seed=1, first_event=0):
+        """the hit loop's normals: three per slot (Philox block) -> (z[3*slots], kind[3*slots])"""
+        out = np.empty(3 * int(slots))
+        kind = np.empty(3 * int(slots), np.uint8)
+        self._check(lib().nb200_debug_normal(self.h, seed, first_event, int(slots), _dptr(out), _dptr(kind)))
         return out, kind
 
     def lar_device(self, species, n, dE, dF, density, dY, dFl, seed=0, first_event=0):

@@ -212,6 +212,7 @@ int build_params(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo,
   P->s1_center = fit_s1(det->FitS1, 0., 0., zc);
   P->s2_center = fit_s2(det->FitS2, 0., 0.);
   P->coin_u_min = exp(-det->coinWind / 20.);
+  for (int k = 0; k <= 10; ++k) P->coin_pow[k] = pow(double(det->numPMTs), 1. - double(k));
   {
     double t = ceil(det->P_dphe * 4294967296.0 - 0.5);  // (w + 1/2)/2^32 < P_dphe  <=>  w < t
     P->dphe_thr = t <= 0. ? 0ull : (t >= 4294967296.0 ? 4294967296ull : (unsigned long long)t);
@@ -501,6 +502,18 @@ int nb200_create(int device, nb200_ctx** out) {
       return NB200_ECUDA;
     }
   }
+  {  // ln k! for the binomial sampler's exact acceptance test (nb_rng.cuh)
+    static std::vector<double> lf;  // once per process
+    if (lf.empty()) {
+      lf.resize(NB_LFACT_N);
+      for (int k = 0; k < NB_LFACT_N; ++k) lf[k] = double(lgammal((long double)k + 1.0L));
+    }
+    if (cudaMemcpyToSymbol(g_lfact, lf.data(), sizeof(double) * NB_LFACT_N) != cudaSuccess) {
+      g_err_noctx = std::string("context setup: ") + cudaGetErrorString(cudaGetLastError());
+      nb200_destroy(c);
+      return NB200_ECUDA;
+    }
+  }
   *out = c;
   return 0;
 }
@@ -680,11 +693,14 @@ int nb200_prepare(nb200_detector* det, double inField, double z_step, nb200_run_
   return 0;
 }
 
-int nb200_wimp_prep(double mass, double eStep, double dayNum, uint64_t seed, double* base, double* exponent,
-                    double* integral, double* xMaxOut, double* divisorOut) {
-  if (!base || !exponent || !integral || !xMaxOut || !divisorOut) return NB200_EINVAL;
-  Stream g;
-  g.init(seed, 0, STREAM_HOST);
+}  // extern "C"
+
+namespace {
+// TestSpectra::WIMP_prep_spectrum (TestSpectra.cpp:392-454); next_iso() supplies the Xe isotope of each
+// WIMP_dRate call in call order (the reference draws it inside, :278); returns false when it runs out
+template <class NextIso>
+int wimp_prep_core(double mass, double eStep, double dayNum, NextIso&& next_iso, double* base, double* exponent,
+                   double* integral, double* xMaxOut, double* divisorOut) {
   for (int i = 0; i < 100; ++i) {  // TestSpectra.hh:44-45 initialisers
     base[i] = (i == 0) ? 1. : 0.;
     exponent[i] = 0.;
@@ -701,8 +717,10 @@ int nb200_wimp_prep(double mass, double eStep, double dayNum, uint64_t seed, dou
   std::vector<double> spec;
   int nZeros = 0;
   bool ok = true;
+  int A = 0;
   for (int i = 0; i < numberPoints + 1; ++i) {
-    spec.push_back(host::wimp_drate(double(i) / divisor, mass, dayNum, double(host::select_xe_atom(g)), &ok));
+    if (!next_iso(&A)) return fail(nullptr, NB200_EINVAL, "nb200_wimp_prep_iso: isotope list too short");
+    spec.push_back(host::wimp_drate(double(i) / divisor, mass, dayNum, double(A), &ok));
     if (!ok) return fail(nullptr, NB200_EPHYSICS, "\tThe velocity integral in the WIMP generator broke!!!");
     if (nearly_equal(spec[i], 0.))
       ++nZeros;
@@ -711,8 +729,10 @@ int nb200_wimp_prep(double mass, double eStep, double dayNum, uint64_t seed, dou
     if (nZeros == 100) break;
   }
   double integ = 0.;
-  for (uint64_t i = 0; i < 1000000; ++i)
-    integ += host::wimp_drate(double(i) / 1e4, mass, dayNum, double(host::select_xe_atom(g)), &ok) / 1e4;
+  for (uint64_t i = 0; i < 1000000; ++i) {
+    if (!next_iso(&A)) return fail(nullptr, NB200_EINVAL, "nb200_wimp_prep_iso: isotope list too short");
+    integ += host::wimp_drate(double(i) / 1e4, mass, dayNum, double(A), &ok) / 1e4;
+  }
   double xMax = (double(spec.size()) - 1.) / divisor;
   for (int i = 0; i < int(spec.size()) - 1; ++i) {
     if (i >= 100) return fail(nullptr, NB200_EPHYSICS, "ERROR: WIMP E_step is too small: more than 100 table intervals");
@@ -738,6 +758,38 @@ int nb200_wimp_prep(double mass, double eStep, double dayNum, uint64_t seed, dou
   *xMaxOut = xMax;
   *divisorOut = divisor;
   return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int nb200_wimp_prep(double mass, double eStep, double dayNum, uint64_t seed, double* base, double* exponent,
+                    double* integral, double* xMaxOut, double* divisorOut) {
+  if (!base || !exponent || !integral || !xMaxOut || !divisorOut) return NB200_EINVAL;
+  Stream g;
+  g.init(seed, 0, STREAM_HOST);
+  return wimp_prep_core(mass, eStep, dayNum, [&](int* A) { *A = host::select_xe_atom(g); return true; }, base, exponent,
+                        integral, xMaxOut, divisorOut);
+}
+
+int nb200_wimp_prep_iso(double mass, double eStep, double dayNum, const int32_t* isotopes, size_t n_isotopes, double* base,
+                        double* exponent, double* integral, double* xMaxOut, double* divisorOut) {
+  if (!isotopes || !base || !exponent || !integral || !xMaxOut || !divisorOut) return NB200_EINVAL;
+  size_t at = 0;
+  return wimp_prep_core(mass, eStep, dayNum,
+                        [&](int* A) {
+                          if (at >= n_isotopes) return false;
+                          *A = int(isotopes[at++]);
+                          return true;
+                        },
+                        base, exponent, integral, xMaxOut, divisorOut);
+}
+
+double nb200_wimp_drate(double ER_keV, double mass_GeV, double dayNum, int isotope_A, int* ok_out) {
+  bool ok = true;
+  const double v = host::wimp_drate(ER_keV, mass_GeV, dayNum, double(isotope_A), &ok);
+  if (ok_out) *ok_out = ok ? 1 : 0;
+  return v;
 }
 
 uint64_t nb200_poisson(double mean, uint64_t seed) {
@@ -1852,23 +1904,23 @@ int nb200_debug_hitmath(nb200_ctx* c, size_t n, const uint32_t* bits3, double* o
   return 0;
 }
 
-int nb200_debug_normal(nb200_ctx* c, uint64_t seed, uint64_t first_event, size_t pairs, double* out,
+int nb200_debug_normal(nb200_ctx* c, uint64_t seed, uint64_t first_event, size_t slots, double* out,
                        unsigned char* kind) {
   if (!c || !out) return NB200_EINVAL;
-  if (pairs == 0) return 0;
+  if (slots == 0) return 0;
   NB_CUDA(c, cudaSetDevice(c->device));
   double* dout = nullptr;
   unsigned char* dk = nullptr;
-  NB_CUDA(c, cudaMalloc(&dout, pairs * 16));
-  if (kind && cudaMalloc(&dk, pairs * 2) != cudaSuccess) {
+  NB_CUDA(c, cudaMalloc(&dout, slots * 24));
+  if (kind && cudaMalloc(&dk, slots * 3) != cudaSuccess) {
     cudaFree(dout);
     return fail(c, NB200_ENOMEM, "cudaMalloc");
   }
-  k_zignormal<<<unsigned(std::min<size_t>((pairs + 255) / 256, 148 * 8)), 256, 0, c->stream>>>(seed, first_event, pairs,
+  k_zignormal<<<unsigned(std::min<size_t>((slots + 255) / 256, 148 * 8)), 256, 0, c->stream>>>(seed, first_event, slots,
                                                                                              dout, dk);
   ++c->launches;
-  cudaMemcpyAsync(out, dout, pairs * 16, cudaMemcpyDeviceToHost, c->stream);
-  if (kind) cudaMemcpyAsync(kind, dk, pairs * 2, cudaMemcpyDeviceToHost, c->stream);
+  cudaMemcpyAsync(out, dout, slots * 24, cudaMemcpyDeviceToHost, c->stream);
+  if (kind) cudaMemcpyAsync(kind, dk, slots * 3, cudaMemcpyDeviceToHost, c->stream);
   cudaError_t e = cudaStreamSynchronize(c->stream);
   cudaFree(dout);
   cudaFree(dk);

@@ -283,9 +283,10 @@ NB_D S1Pre s1_prelude(uint64_t ev, const RunParams& P, int Nph, double tx, doubl
   // makes the first nDP hits the double ones
   const int nh = r.full ? r.nHits : 0;
   const bool tab = P.dpe_alias != nullptr && nh < NB_ALIAS_MAXN;  // P_dphe in (0,1) and a moderate hit count
-  r.nDP = tab ? binomial_fixed_p(P.seed, ev, STREAM_BIN_S1DPE, nh, P.dpe_alias) : 0;
-  if (__any_sync(__activemask(), !tab))  // large events (or P_dphe of 0 / 1): the general sampler
-    r.nDP += int(binomial(P.seed, ev, STREAM_BIN_S1DPE + 1u, tab ? 0 : nh, det.P_dphe));
+  if (tab)
+    r.nDP = binomial_fixed_p(P.seed, ev, STREAM_BIN_S1DPE, nh, P.dpe_alias);
+  else  // large events (or P_dphe of 0 / 1): the general sampler
+    r.nDP = int(binomial(P.seed, ev, STREAM_BIN_S1DPE + 1u, nh, det.P_dphe));
   return r;
 }
 
@@ -369,7 +370,7 @@ NB_D double zig_normal_g(uint32_t w0, uint32_t w1, uint32_t e0, uint32_t e1, uin
   const int32_t t = zig_t(w0);
   const uint32_t i = w1 >> (32 - NB_ZIG_BITS);
   if (uint32_t(abs(t)) < __ldg(&g_zig_k[i])) return zig_td(t) * __ldg(&g_zig_w[i]);
-  return zig_finish(w0, w1, 0u, false, e0, e1, k, stream, k0, k1);
+  return zig_finish(w0, i, 0u, false, e0, e1, k, stream, k0, k1);
 }
 __device__ __noinline__ double pe_redraw(uint64_t seed, uint64_t event, uint32_t blk, double pe_mu, double pe_sig,
                                          double pe_cut, double pe_tau, double pe_rho, double pe_m0) {
@@ -404,9 +405,27 @@ NB_D double n_choose_r(double n, int r) {
   return c;
 }
 
+// The normals and the yes/no word that every event consumes after the hit loop, drawn together at the top of the
+// stage -- two Philox blocks at full lane occupancy instead of three to four calls from inside divergent branches
+// (ncu: philox_block was 15 % of k_post's warp instructions at 15 active lanes).  All independent:
+//   z_spike  GetSpike's smearing (NEST.cpp:2249-2256)      z_s2noise  S2 linear/quadratic noise (:1994-2003)
+//   z_s2ph   S2 photon number (:1976-1980)                 z_s2area   S2 pulse area (:1986)
+//   u_coin   the n-fold coincidence draw of GetS1 (:1689): a 32-bit uniform, like the chain's other yes/no draws
+struct PostDraws {
+  double z_spike, z_s2noise, z_s2ph, z_s2area;
+  uint32_t u_coin;
+};
+NB_D PostDraws post_draws(Stream& g) {
+  PostDraws d;
+  uint32_t spare;
+  normal_pair_spare(g, d.z_spike, d.z_s2noise, d.u_coin);
+  normal_pair_spare(g, d.z_s2ph, d.z_s2area, spare);
+  return d;
+}
+
 // GetS1 after the hit loop: noise, thresholds, corrections, n-fold coincidence, GetSpike,
 // below-threshold sign flag.  NEST.cpp:1608-1721, 2243-2268.  out[9] = scintillation.
-NB_D void s1_epilogue(Stream& g, const RunParams& P, const S1Pre& pre, const S1Acc& acc,
+NB_D void s1_epilogue(Stream& g, const RunParams& P, const S1Pre& pre, const S1Acc& acc, const PostDraws& D,
                       double* out) {
   const nb200_detector& det = P.det;
   double pulseArea = acc.area;
@@ -417,16 +436,8 @@ NB_D void s1_epilogue(Stream& g, const RunParams& P, const S1Pre& pre, const S1A
     sig = sqrt(a * a + b * b);
   } else
     sig = det.noiseLinear[0] * pulseArea;
-  // gauss(mu, 0, true) == max(mu, 0): skip the draw when the width is exactly zero.  The Box-Muller
-  // partner of this draw serves the spike smearing below (independent normals)
-  double zB = 0.;
-  bool haveB = false;
-  if (sig != 0.) {
-    double zA;
-    normal_pair(g, zA, zB);
-    haveB = true;
-    pulseArea = pulseArea + sig * zA;
-  }
+  // gauss(mu, 0, true) == max(mu, 0): skip the draw when the width is exactly zero
+  if (sig != 0.) pulseArea = pulseArea + sig * normal(g);
   pulseArea = (pulseArea < 0.) ? 0. : pulseArea;
   if (pulseArea < det.sPEthr) pulseArea = 0.;
   if (spike < 0) spike = 0;
@@ -454,7 +465,7 @@ NB_D void s1_epilogue(Stream& g, const RunParams& P, const S1Pre& pre, const S1A
   else if (det.coinLevel == 1)
     prob = (spike >= 1.) ? 1. : 0.;
   else if (det.coinLevel == 2)
-    prob = 1. - pow(double(det.numPMTs), 1. - spike);
+    prob = 1. - P.coin_pow[int(spike)];  // pow(numPMTs, 1 - spike), 2 <= spike <= 10: tabulated by the host's libm
   else {
     double numer = 0., denom = 0.;
     for (int i = int(spike); i > 0; --i) {
@@ -472,7 +483,7 @@ NB_D void s1_epilogue(Stream& g, const RunParams& P, const S1Pre& pre, const S1A
     } else {
       // rand_zero_trunc_gauss RandomGen.cpp:55-61 (redraw while <= 0)
       const double sw = (det.sPEres / 4.) * sqrt(fabs(spike));
-      double ns = spike + sw * (haveB ? zB : normal(g));
+      double ns = spike + sw * D.z_spike;
       for (int guard = 0; ns <= 0. && guard < 100000; ++guard) ns = spike + sw * normal(g);
       out[6] = ns;
       out[7] = ns / pre.fitSm * P.s1_center;
@@ -480,7 +491,7 @@ NB_D void s1_epilogue(Stream& g, const RunParams& P, const S1Pre& pre, const S1A
   }
 
   // rand_uniform() > prob && prob < 1: the draw is irrelevant when prob >= 1
-  if (prob < 1. && g.uniform() > prob) {
+  if (prob < 1. && u32d(D.u_coin) > prob) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       double v = out[i];
@@ -491,7 +502,7 @@ NB_D void s1_epilogue(Stream& g, const RunParams& P, const S1Pre& pre, const S1A
 }
 
 // NESTcalc::GetS2, S2CalculationMode::Full: NEST.cpp:1724-1776, 1975-2063.  out[9] = ionization
-NB_D void get_s2(Stream& g, uint64_t ev, const RunParams& P, int Ne, double tx, double ty, double tz,
+NB_D void get_s2(Stream& g, uint64_t ev, const RunParams& P, const PostDraws& D, int Ne, double tx, double ty, double tz,
                  double sx, double sy, double dt, double dfield, double* out) {
   const nb200_detector& det = P.det;
   const double elYield = P.rc.g2_params[0], ExtEff = P.rc.g2_params[1], SE = P.rc.g2_params[2],
@@ -513,17 +524,18 @@ NB_D void get_s2(Stream& g, uint64_t ev, const RunParams& P, int Ne, double tx, 
   const double life = exp(-dt / det.eLife_us);
   long long Nee = binomial(P.seed, ev, STREAM_BIN_NEE, Ne, ExtEff * life);
   double mu = elYield * double(Nee);
-  double z0, z1;  // one Box-Muller pair: photon number here, pulse area below
-  normal_pair(g, z0, z1);
+  const double z0 = D.z_s2ph, z1 = D.z_s2area;  // one Box-Muller pair: photon number here, pulse area below
   double nraw = mu + sqrt(det.s2Fano * elYield * double(Nee)) * z0;
   double nphd = floor(((nraw < 0.) ? 0. : nraw) + 0.5);
   long long Nph = (long long)nphd;
   long long nHits = binomial(P.seed, ev, STREAM_BIN_S2HIT, Nph, det.g1_gas * posDep);
   // second photo-electrons: Binomial(nHits, P_dphe), fixed probability -> alias tables (nb_rng.cuh)
   const bool tab = P.dpe_alias != nullptr && nHits < NB_ALIAS_MAXN;
-  long long Nphe = nHits + (tab ? binomial_fixed_p(P.seed, ev, STREAM_BIN_S2DPE, int(nHits), P.dpe_alias) : 0);
-  if (__any_sync(__activemask(), !tab))  // very large S2 (or P_dphe of 0 / 1): the general sampler
-    Nphe += binomial(P.seed, ev, STREAM_BIN_S2DPE + 8u, tab ? 0 : nHits, det.P_dphe);
+  long long Nphe = nHits;
+  if (tab)
+    Nphe += binomial_fixed_p(P.seed, ev, STREAM_BIN_S2DPE, int(nHits), P.dpe_alias);
+  else  // very large S2 (or P_dphe of 0 / 1): the general sampler
+    Nphe += binomial(P.seed, ev, STREAM_BIN_S2DPE + 8u, nHits, det.P_dphe);
   double m = double(Nphe) / P.rc.NewMean;
   double pulseArea = m + det.sPEres * sqrt(m) * z1;
   pulseArea = (pulseArea < 0.) ? 0. : pulseArea;
@@ -533,10 +545,8 @@ NB_D void get_s2(Stream& g, uint64_t ev, const RunParams& P, int Ne, double tx, 
     sig = sqrt(a * a + b * b);
   } else
     sig = det.noiseLinear[1] * pulseArea;
-  if (sig != 0.)
-    pulseArea = gauss(g, pulseArea, sig, true);
-  else
-    pulseArea = (pulseArea < 0.) ? 0. : pulseArea;
+  if (sig != 0.) pulseArea = pulseArea + sig * D.z_s2noise;  // rand_gauss(pulseArea, sig, true)
+  pulseArea = (pulseArea < 0.) ? 0. : pulseArea;
   double pulseAreaC = pulseArea / life / posDepSm;
   double Nphd = pulseArea / (1. + det.P_dphe);
   double NphdC = pulseAreaC / (1. + det.P_dphe);

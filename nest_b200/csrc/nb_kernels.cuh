@@ -171,11 +171,152 @@ constexpr int kHitBlock = NB_HIT_BLOCK;   // threads per k_hits block
 #define NB_AREA_MAGIC 6755399441055744.0           // 1.5 * 2^52: ulp = 1 for |a 2^32| < 2^51
 #define NB_AREA_MAGIC_BITS 0x4338000000000000ull  // its bit pattern
 
+// ---- batched parameter sweep (BASELINE config 4) -----------------------------------------------------------
+// n_points grid points (detector, model, run constants, source: one RunParams each, in global memory), every point
+// simulating the same event ids [first_event, first_event + n_per_point); one band per point.  The launch walks a
+// flattened range of SLOTS: slot s = point s / n_pad, event index s % n_pad (n_pad = n_per_point rounded up to a
+// multiple of 1024, so that no block tile or k_hits group straddles two points; the padding slots are idle).
+// A block copies its point's RunParams to shared memory and runs the very device code of the single-point kernels
+// on it, so a point's events are bit for bit those of nb200_run with the same parameters.
+struct SweepArgs {
+  const RunParams* params;  // [n_points], device
+  unsigned long long* bands;  // [n_points][band_words], device
+  uint64_t band_words;
+  uint64_t n_per_point, n_pad;
+  uint64_t slot0, n_slots;  // this launch: slots [slot0, slot0 + n_slots); workspace index = slot - slot0
+  uint64_t first_event;
+  Work work;
+};
+// RunParams of `point` into this block's shared copy (all threads; barriers inside)
+NB_D void sweep_load_params(RunParams* sP, const RunParams* gP, uint32_t point) {
+  __syncthreads();  // nobody still reads the previous point's copy
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(gP + point);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(sP);
+  static_assert(sizeof(RunParams) % 4 == 0, "RunParams is copied word by word");
+  for (uint32_t i = threadIdx.x; i < sizeof(RunParams) / 4; i += blockDim.x) dst[i] = src[i];
+  __syncthreads();
+}
+
+// one event of k_pre: W index idx (workspace), gidx (index within the call: lists, SoA columns), event id ev
+NB_D void pre_body(const RunParams& P, const Work& W, uint64_t idx, uint64_t gidx, uint64_t ev, bool active,
+                   int* __restrict__ err_flag) {
+  const nb200_detector& det = P.det;
+  const bool cli = !P.vec_mode;
+  Stream g;
+  g.init(P.seed, ev, STREAM_MAIN);
+  double px, py, pz, sx, sy, field = 0., dt = 0., vD = P.rc.vD;
+  Yields y{0., 0., 0., 0., 0., 0.};
+  Quanta q{0, 0, 0, 0, 0., 0.};
+  int err = 0;
+  double keV = sample_energy(g, P, gidx);
+  NB_LOCKSTEP();
+  const nb200_source& S = P.src;
+  const bool nonuni = (S.inField == -1.);
+  const bool listed = (S.kind == NB200_SRC_LIST && S.x != nullptr);
+  if (listed) {
+    px = S.x[gidx];
+    py = S.y[gidx];
+    pz = S.z[gidx];
+  } else {
+    px = S.xyz[0];
+    py = S.xyz[1];
+    pz = S.xyz[2];
+  }
+  const bool ranXY = (S.fixed_pos == 0 || S.fixed_pos == 3) && !listed;
+  const bool ranZ = (S.fixed_pos == 0 || S.fixed_pos == 2) && !listed;
+  for (int guard = 0; guard < 10000; ++guard) {  // Z_NEW loop execNEST.cpp:806-967
+    if (ranZ) pz = P.z_direct ? fma(P.z_hi - P.z_lo, g.uniform(), P.z_lo) : 0. + (det.TopDrift - 0.) * g.uniform();
+    if (ranXY && (guard == 0 || S.fixed_pos == 0)) {
+      double r = det.radius * sqrt(g.uniform());
+      double sn, cs;
+      uint32_t pa, pb;
+      g.next2(pa, pb);  // phi = 2 pi u, u from 32 bits
+      sincos_bits(pa, sn, cs);
+      px = r * cs;
+      py = r * sn;
+    }
+    if (cli)
+      field = nonuni ? fit_ef(det.FitEF, px, py, pz) : S.inField;
+    else
+      field = (S.inField < 0.0) ? fit_ef(det.FitEF, px, py, pz) : S.inField;
+    if (cli) {
+      if (nonuni) vD = P.vtable[min(max(int(floor(pz / P.ana.z_step + 0.5)), 0), P.vtable_n - 1)];
+    } else if (S.inField < 0.0)
+      vD = drift_velocity_dev(P, field);
+    dt = (det.TopDrift - pz) / vD;
+    if (cli && ranZ && (dt > det.dt_max || dt < det.dt_min) && field >= NB_FIELD_MIN) continue;
+    break;
+  }
+  if (cli) {  // execNEST.cpp:975-992
+    if (pz <= 0) pz = P.ana.z_step;
+    if ((pz > (det.TopDrift + P.ana.z_step) || dt < 0.0) && field >= NB_FIELD_MIN) {
+      dt = 0.0;
+      pz = det.TopDrift - P.ana.z_step;
+    }
+  }
+  NB_LOCKSTEP();
+  // yields + quanta: execNEST.cpp:1031-1077 / FullCalculation NEST.cpp:22-42
+  const int sp = P.species;
+  const bool nrlike = sp <= NB200_Cf || sp == NB200_atmNu;
+  if (!cli || keV > 0.001 * P.rc.Wq_eV) {
+    int A2 = 131;
+    if (P.model.er_model < 0 && ((nrlike && nearly_equal(P.model.massNum, 0.)) || sp == NB200_ion))
+      A2 = select_xe_atom(g);
+    if (P.model.er_model == 0)
+      y = yield_beta(keV, P.rc.rho, field, det, P.model.ERYieldsParam, P.model.multFact, &P.hoist);
+    else if (P.model.er_model == 1)
+      y = yield_gamma(keV, P.rc.rho, field, det, P.model.multFact, &P.hoist);
+    else if (P.model.er_model == 2)
+      y = yield_er_weighted(keV, P.rc.rho, field, det, P.model.ERYieldsParam, &P.hoist);
+    else {
+      double u01 = 0.5;
+      if (sp == NB200_Kr83m && !nearly_equal(P.model.massNum, P.model.atomNum)) u01 = g.uniform();
+      y = get_yields(sp, keV, P.rc.rho, field, P.model.massNum, P.model.atomNum, A2, det, P.model, &err, u01,
+                     &P.hoist);
+    }
+  }
+  NB_LOCKSTEP();
+  if (!cli || keV > 0.001 * P.rc.Wq_eV) q = get_quanta(g, P.seed, ev, y, P.rc.rho, det, P.model, &err, &P.hoist);
+  NB_LOCKSTEP();
+  if (cli && (det.noiseBaseline[2] != 0. || det.noiseBaseline[3] != 0.))
+    q.electrons += to_int_round(gauss(g, det.noiseBaseline[2], det.noiseBaseline[3], false));
+  // position smearing execNEST.cpp:1090-1099
+  sx = px;
+  sy = py;
+  if (cli) {
+    double Nphd_S2 = fabs(P.rc.g2_params[3]) * q.electrons * exp(-dt / det.eLife_us);
+    if (!P.ana.MCtruthPos && Nphd_S2 > NB_PHE_MIN) xy_resolution(g, det, px, py, Nphd_S2, sx, sy);
+  }
+  NB_LOCKSTEP();
+  S1Pre pre = s1_prelude(ev, P, q.photons, px, py, pz, sx, sy, pz, keV);
+  NB_LOCKSTEP();
+  if (!active) return;
+
+  if (P.write_soa && P.soa.deltaT_ns) P.soa.deltaT_ns[gidx] = y.dT;
+  W.keV[idx] = keV;
+  W.px[idx] = px;
+  W.py[idx] = py;
+  W.pz[idx] = pz;
+  W.sx[idx] = sx;
+  W.sy[idx] = sy;
+  W.field[idx] = field;
+  W.dt[idx] = dt;
+  W.yNph[idx] = y.Nph;
+  W.yNe[idx] = y.Ne;
+  W.yL[idx] = y.L;
+  W.posDepSm[idx] = pre.posDepSm;
+  W.fitSm[idx] = pre.fitSm;
+  W.photons[idx] = q.photons;
+  W.electrons[idx] = q.electrons;
+  W.ions[idx] = q.ions;
+  W.excitons[idx] = q.excitons;
+  W.nHits[idx] = pre.full ? pre.nHits : -(pre.nHits + 1);  // negative: Parametric S1 in k_post
+  W.nphe[idx] = pre.nDP;  // in: double-phe hits; k_hits replaces it by Nphe = nHits + nDP
+  if (err) atomicOr(err_flag, err);
+}
+
 __global__ void __launch_bounds__(kPreBlock, NB_PRE_MINB)
     k_pre(const __grid_constant__ RunParams P, int* __restrict__ err_flag) {
-  const nb200_detector& det = P.det;
-  const Work& W = P.work;
-  const bool cli = !P.vec_mode;
   // The per-event code is long and straight-line: its cost is instruction fetch, not arithmetic.
   // NB_LOCKSTEP() barriers keep the warps of a block inside the same few KB of code, so that one
   // warp's instruction-cache fill serves the others (all threads reach every barrier: the loop
@@ -185,134 +326,45 @@ __global__ void __launch_bounds__(kPreBlock, NB_PRE_MINB)
     const bool active = base + threadIdx.x < P.n_events;
     const uint64_t idx = active ? base + threadIdx.x : P.n_events - 1;
     const uint64_t gidx = P.chunk_off + idx;
-    const uint64_t ev = P.first_event + gidx;
-    Stream g;
-    g.init(P.seed, ev, STREAM_MAIN);
-    double px, py, pz, sx, sy, field = 0., dt = 0., vD = P.rc.vD;
-    Yields y{0., 0., 0., 0., 0., 0.};
-    Quanta q{0, 0, 0, 0, 0., 0.};
-    int err = 0;
-    double keV = sample_energy(g, P, gidx);
-    NB_LOCKSTEP();
-    const nb200_source& S = P.src;
-    const bool nonuni = (S.inField == -1.);
-    const bool listed = (S.kind == NB200_SRC_LIST && S.x != nullptr);
-    if (listed) {
-      px = S.x[gidx];
-      py = S.y[gidx];
-      pz = S.z[gidx];
-    } else {
-      px = S.xyz[0];
-      py = S.xyz[1];
-      pz = S.xyz[2];
-    }
-    const bool ranXY = (S.fixed_pos == 0 || S.fixed_pos == 3) && !listed;
-    const bool ranZ = (S.fixed_pos == 0 || S.fixed_pos == 2) && !listed;
-    for (int guard = 0; guard < 10000; ++guard) {  // Z_NEW loop execNEST.cpp:806-967
-      if (ranZ) pz = P.z_direct ? fma(P.z_hi - P.z_lo, g.uniform(), P.z_lo) : 0. + (det.TopDrift - 0.) * g.uniform();
-      if (ranXY && (guard == 0 || S.fixed_pos == 0)) {
-        double r = det.radius * sqrt(g.uniform());
-        double sn, cs;
-        uint32_t pa, pb;
-        g.next2(pa, pb);  // phi = 2 pi u, u from 32 bits
-        sincos_bits(pa, sn, cs);
-        px = r * cs;
-        py = r * sn;
-      }
-      if (cli)
-        field = nonuni ? fit_ef(det.FitEF, px, py, pz) : S.inField;
-      else
-        field = (S.inField < 0.0) ? fit_ef(det.FitEF, px, py, pz) : S.inField;
-      if (cli) {
-        if (nonuni) vD = P.vtable[min(max(int(floor(pz / P.ana.z_step + 0.5)), 0), P.vtable_n - 1)];
-      } else if (S.inField < 0.0)
-        vD = drift_velocity_dev(P, field);
-      dt = (det.TopDrift - pz) / vD;
-      if (cli && ranZ && (dt > det.dt_max || dt < det.dt_min) && field >= NB_FIELD_MIN) continue;
-      break;
-    }
-    if (cli) {  // execNEST.cpp:975-992
-      if (pz <= 0) pz = P.ana.z_step;
-      if ((pz > (det.TopDrift + P.ana.z_step) || dt < 0.0) && field >= NB_FIELD_MIN) {
-        dt = 0.0;
-        pz = det.TopDrift - P.ana.z_step;
-      }
-    }
-    NB_LOCKSTEP();
-    // yields + quanta: execNEST.cpp:1031-1077 / FullCalculation NEST.cpp:22-42
-    const int sp = P.species;
-    const bool nrlike = sp <= NB200_Cf || sp == NB200_atmNu;
-    if (!cli || keV > 0.001 * P.rc.Wq_eV) {
-      int A2 = 131;
-      if (P.model.er_model < 0 && ((nrlike && nearly_equal(P.model.massNum, 0.)) || sp == NB200_ion))
-        A2 = select_xe_atom(g);
-      if (P.model.er_model == 0)
-        y = yield_beta(keV, P.rc.rho, field, det, P.model.ERYieldsParam, P.model.multFact, &P.hoist);
-      else if (P.model.er_model == 1)
-        y = yield_gamma(keV, P.rc.rho, field, det, P.model.multFact, &P.hoist);
-      else if (P.model.er_model == 2)
-        y = yield_er_weighted(keV, P.rc.rho, field, det, P.model.ERYieldsParam, &P.hoist);
-      else {
-        double u01 = 0.5;
-        if (sp == NB200_Kr83m && !nearly_equal(P.model.massNum, P.model.atomNum)) u01 = g.uniform();
-        y = get_yields(sp, keV, P.rc.rho, field, P.model.massNum, P.model.atomNum, A2, det, P.model, &err, u01,
-                       &P.hoist);
-      }
-    }
-    NB_LOCKSTEP();
-    if (!cli || keV > 0.001 * P.rc.Wq_eV) q = get_quanta(g, P.seed, ev, y, P.rc.rho, det, P.model, &err, &P.hoist);
-    NB_LOCKSTEP();
-    if (cli && (det.noiseBaseline[2] != 0. || det.noiseBaseline[3] != 0.))
-      q.electrons += to_int_round(gauss(g, det.noiseBaseline[2], det.noiseBaseline[3], false));
-    // position smearing execNEST.cpp:1090-1099
-    sx = px;
-    sy = py;
-    if (cli) {
-      double Nphd_S2 = fabs(P.rc.g2_params[3]) * q.electrons * exp(-dt / det.eLife_us);
-      if (!P.ana.MCtruthPos && Nphd_S2 > NB_PHE_MIN) xy_resolution(g, det, px, py, Nphd_S2, sx, sy);
-    }
-    NB_LOCKSTEP();
-    S1Pre pre = s1_prelude(ev, P, q.photons, px, py, pz, sx, sy, pz, keV);
-    NB_LOCKSTEP();
-    if (!active) continue;
+    pre_body(P, P.work, idx, gidx, P.first_event + gidx, active, err_flag);
+  }
+}
 
-    if (P.write_soa && P.soa.deltaT_ns) P.soa.deltaT_ns[gidx] = y.dT;
-    W.keV[idx] = keV;
-    W.px[idx] = px;
-    W.py[idx] = py;
-    W.pz[idx] = pz;
-    W.sx[idx] = sx;
-    W.sy[idx] = sy;
-    W.field[idx] = field;
-    W.dt[idx] = dt;
-    W.yNph[idx] = y.Nph;
-    W.yNe[idx] = y.Ne;
-    W.yL[idx] = y.L;
-    W.posDepSm[idx] = pre.posDepSm;
-    W.fitSm[idx] = pre.fitSm;
-    W.photons[idx] = q.photons;
-    W.electrons[idx] = q.electrons;
-    W.ions[idx] = q.ions;
-    W.excitons[idx] = q.excitons;
-    W.nHits[idx] = pre.full ? pre.nHits : -(pre.nHits + 1);  // negative: Parametric S1 in k_post
-    W.nphe[idx] = pre.nDP;  // in: double-phe hits; k_hits replaces it by Nphe = nHits + nDP
-    if (err) atomicOr(err_flag, err);
+__global__ void __launch_bounds__(kPreBlock, NB_PRE_MINB)
+    k_pre_sweep(const __grid_constant__ SweepArgs A, int* __restrict__ err_flag) {
+  __shared__ __align__(16) RunParams sP;
+  uint32_t cur = 0xffffffffu;
+  for (uint64_t base = blockIdx.x * uint64_t(kPreBlock); base < A.n_slots; base += uint64_t(gridDim.x) * kPreBlock) {
+    const uint64_t slot = A.slot0 + base;  // first slot of this tile: multiple of kPreBlock
+    const uint32_t point = uint32_t(slot / A.n_pad);
+    if (point != cur) {
+      sweep_load_params(&sP, A.params, point);
+      cur = point;
+    }
+    const uint64_t i = slot - uint64_t(point) * A.n_pad + threadIdx.x;  // event index within the point
+    const bool active = i < A.n_per_point;
+    const uint64_t ie = active ? i : A.n_per_point - 1;
+    pre_body(sP, A.work, base + threadIdx.x, ie, A.first_event + ie, active, err_flag);
   }
 }
 
 // -------------------------------------------------------------------------------------------
 // k_hits: the per-PMT-hit loop of GetS1, NEST.cpp:1367-1429
 //
-// Work item = SLOT = one Philox block = two photo-electrons.  The hits of an event are
-// exchangeable (iid draws, and the event observables -- spike count, summed area, Nphe -- are
-// symmetric in them), so instead of deciding hit by hit whether it carries a second
-// photo-electron (NEST.cpp:1391), k_pre draws their number nDP ~ Binomial(nHits, P_dphe) once and
-// the first nDP hits are the double ones: slot j < nDP is one double-phe hit (both photo-electrons
-// in the same lane, summed before the sPEthr test), a later slot is two single-phe hits.
-// Nphe = nHits + nDP.  No second-photo-electron queue, no per-hit Bernoulli.
+// Work item = SLOT = one Philox block = THREE photo-electrons (27 bits of abscissa, 4 of truncation pre-test and
+// 11 of ziggurat layer each: nb_rng.cuh pe_fields).  The hits of an event are exchangeable (iid draws, and the
+// event observables -- spike count, summed area, Nphe -- are symmetric in them), so instead of deciding hit by
+// hit whether it carries a second photo-electron (NEST.cpp:1391), k_pre draws their number nD ~
+// Binomial(nHits, P_dphe) once, and the nD double hits and nS = nHits - nD single hits are dealt into slots:
+//   slot j < min(nD, nS)        one double hit (photo-electrons 0 + 1, summed before the sPEthr test) and one
+//                               single hit (photo-electron 2)
+//   nD > nS: slots nS .. nD-1   one double hit (photo-electron 2 unused)
+//   nD <= nS: slots from nD on  three single hits, the last slot one to three
+// Nphe = nHits + nD.  No second-photo-electron queue, no per-hit Bernoulli; 0.39 Philox blocks per hit for LUX
+// (P_dphe = 0.173) against 0.59 with two photo-electrons per block.
 //
 // A slot whose photo-electrons all land in their ziggurat layer's core above the truncation
-// pre-test (95 % of slots for LUX) is finished in the main loop.  Any other slot -- wedge / tail
+// pre-test (93 % of slots for LUX) is finished in the main loop.  Any other slot -- wedge / tail
 // of the ziggurat, exact truncation test, and every slot of an event that needs efficiency or
 // coincidence-window draws -- is queued per warp as (event, slot) and redone in full, 32 at a
 // time, by the out-of-line finisher: rare per lane but frequent per warp.
@@ -321,6 +373,16 @@ struct SlotEntry {
 };
 constexpr int kSlotCap = 64;  // <= 31 left over + 32 pushed per iteration
 constexpr size_t kHitDynSmem = NB_ZIG_N * (sizeof(double) + sizeof(uint32_t));  // ziggurat tables (opt-in: > 48 KB total)
+
+// slots of an event with nh hits of which nd carry a second photo-electron
+NB_D int hit_slots(int nh, int nd) {
+  const int ns = nh - nd;
+  return nd + (ns > nd ? (ns - nd + 2) / 3 : 0);
+}
+// valid photo-electrons of slot j: 3 = all, 2 = the first two (a double hit alone, or two single hits), 1 = one single hit
+NB_D int slot_valid(int j, int nd, int ns) {
+  return j < nd ? (j < ns ? 3 : 2) : min(3, (ns - nd) - 3 * (j - nd));
+}
 
 // 64-bit add to shared memory as two 32-bit atomics with the carry passed on by whoever wraps the low word
 // (the native shared-memory atomic is 32 bits wide; a 64-bit atomicAdd compiles to a compare-and-swap loop,
@@ -342,70 +404,96 @@ NB_D void hit_commit(const RunParams& P, unsigned long long* s_area, unsigned in
   }
 }
 
-// one photo-electron in full: ziggurat normal (core, wedge or tail), truncation pre-test, exact
-// residual test, joint redraw.  which = 0 / 1: words (x,y) / (z,w) of the slot's block r; the
-// spare uniforms come from the slot's STREAM_HIT2 block t (x,y: first wedge test, z,w: exact test).
+// the standard normal of photo-electron `which` of slot j: ziggurat core, wedge or tail.  r: the slot's
+// STREAM_HIT block, t: its STREAM_HIT2 block (word w: first wedge test of photo-electron 0).  A: the abscissa
+// word (pre-test bits); fast: the draw was a layer core (what the main loop of k_hits finishes by itself)
+NB_D double pe_normal(const u128& r, const u128& t, int which, uint32_t e0, uint32_t e1, uint32_t j, uint32_t k0,
+                      uint32_t k1, const uint32_t* zk, const double* zw, uint32_t& A, bool& fast) {
+  uint32_t L;
+  pe_fields(r, which, A, L);
+  double z;
+  fast = zig_fast(A, L, zk, zw, z);
+  if (!fast) z = zig_finish(A, L, t.w, which == 0, e0, e1, 3u * j + uint32_t(which), STREAM_ZIG, k0, k1);
+  return z;
+}
+
+// one photo-electron in full: normal, truncation pre-test, exact residual test (uniform: word `which` of t),
+// joint redraw
 NB_D double pe_full(const RunParams& P, const u128& r, const u128& t, int which, uint64_t ev, uint32_t j,
                     const uint32_t* zk, const double* zw) {
-  const uint32_t w0 = which ? r.z : r.x, w1 = which ? r.w : r.y;
-  const uint32_t e0 = uint32_t(ev), e1 = uint32_t(ev >> 32);
-  double z;
-  if (!zig_fast(w0, w1, zk, zw, z))
-    z = zig_finish(w0, w1, which ? t.y : t.x, true, e0, e1, 2u * j + uint32_t(which), STREAM_ZIG, uint32_t(P.seed),
-                   uint32_t(P.seed >> 32));
+  uint32_t A;
+  bool fast;
+  const double z = pe_normal(r, t, which, uint32_t(ev), uint32_t(ev >> 32), j, uint32_t(P.seed), uint32_t(P.seed >> 32), zk,
+                             zw, A, fast);
   double sv = fma(P.pe_sig, z, P.pe_mu);
-  if (sv <= P.pe_cut && (sv < P.pe_sfast || (w0 & 0xFu) == 15u)) {
-    if (!pe_accept_exact(P, sv, u32d(which ? t.w : t.z)))
-      sv = pe_redraw(P.seed, ev, j * 64u + (which ? 32u : 0u), P.pe_mu, P.pe_sig, P.pe_cut, P.pe_tau, P.pe_rho, P.pe_m0);
+  if (sv <= P.pe_cut && (sv < P.pe_sfast || (A & NB_PE_PRETEST_MASK) == NB_PE_PRETEST_MASK)) {
+    const uint32_t uw = which == 0 ? t.x : (which == 1 ? t.y : t.z);
+    if (!pe_accept_exact(P, sv, u32d(uw)))
+      sv = pe_redraw(P.seed, ev, j * 96u + uint32_t(which) * 32u, P.pe_mu, P.pe_sig, P.pe_cut, P.pe_tau, P.pe_rho, P.pe_m0);
   }
   return sv;
 }
 
 // up to 32 queued slots, everything the reference does for their hits
-// (out of line: its register needs must not shape the main loop)
+// (out of line: its register needs must not shape the main loop).  The photo-electrons of a slot are walked by a
+// rolled loop: one call site each for the wedge / tail completion and the joint redraw, so that the lanes of a
+// warp that need one -- a few per pass, for different photo-electrons -- go through it together.
 __device__ __noinline__ void hits_finish_slow(const RunParams& P, const int* s_nh, const int* s_nd,
                                              unsigned long long* s_area, unsigned int* s_spike, uint64_t ev0,
                                              const SlotEntry* q, int count, int lane, const uint32_t* zk,
                                              const double* zw) {
   const nb200_detector& det = P.det;
-  if (lane < count) {
-    const SlotEntry en = q[lane];
-    const int e = int(en.e), nh = s_nh[e], nd = s_nd[e];
-    const uint32_t j = en.j;
-    const bool dp = int(j) < nd;
-    const bool hasb = dp || (2 * (int(j) - nd) + 1 < nh - nd);
-    const uint64_t ev = ev0 + uint64_t(e);
-    const uint32_t e0 = uint32_t(ev), e1 = uint32_t(ev >> 32);
-    const u128 r = philox4x32_10_rk(e0, e1, j, STREAM_HIT, P.rk);
-    const u128 t = philox4x32_10_rk(e0, e1, j, STREAM_HIT2, P.rk);
-    double s1 = pe_full(P, r, t, 0, ev, j, zk, zw);
-    double s2 = hasb ? pe_full(P, r, t, 1, ev, j, zk, zw) : 0.;
-    bool coin1 = true, coin2 = true;
-    if (det.sPEeff < 1. || !(nh > det.coinLevel)) {  // efficiency and coincidence-window draws
-      const double eff = s1_eff(det, nh);
-      const u128 c = philox4x32_10_rk(e0, e1, j, STREAM_HIT3, P.rk);
-      if (eff < 1.) {  // NEST.cpp:1381-1386, 1403: a second photo-electron is lost only with the first
-        const bool lost1 = u32d(c.x) > eff, lost2 = u32d(c.y) > eff;
-        if (lost1) s1 = 0.;
-        if (dp ? (lost1 && lost2) : lost2) s2 = 0.;
+  const bool live = lane < count;
+  const SlotEntry en = live ? q[lane] : SlotEntry{0u, 0u};
+  const int e = int(en.e), nh = s_nh[e], nd = s_nd[e];
+  const uint32_t j = en.j;
+  const bool dbl = int(j) < nd;
+  const int nv = live ? slot_valid(int(j), nd, nh - nd) : 0;
+  const uint64_t ev = ev0 + uint64_t(e);
+  const uint32_t e0 = uint32_t(ev), e1 = uint32_t(ev >> 32);
+  const u128 r = philox4x32_10_rk(e0, e1, j, STREAM_HIT, P.rk);
+  const u128 t = philox4x32_10_rk(e0, e1, j, STREAM_HIT2, P.rk);
+  // efficiency and coincidence-window draws (sPEeff < 1 detectors; events of <= coinLevel hits)
+  const bool special = det.sPEeff < 1. || !(nh > det.coinLevel);
+  const double eff = s1_eff(det, nh);
+  u128 c{0u, 0u, 0u, 0u}, c2{0u, 0u, 0u, 0u};
+  if (live && special) {
+    c = philox4x32_10_rk(e0, e1, j, STREAM_HIT3, P.rk);
+    if (!(nh > det.coinLevel)) c2 = philox4x32_10_rk(e0, e1, j, STREAM_HIT4, P.rk);
+  }
+  const bool coin_draws = special && !(nh > det.coinLevel);  // NEST.cpp:1422-1424, one draw per hit
+  double first = 0.;   // first photo-electron of a double hit
+  bool lost0 = false;
+#pragma unroll 1
+  for (int which = 0; which < 3; ++which) {
+    if (which < nv) {
+      double sv = pe_full(P, r, t, which, ev, j, zk, zw);
+      if (special && eff < 1.) {  // NEST.cpp:1381-1386, 1403: a second photo-electron is lost only with the first
+        const bool lost = u32d(which == 0 ? c.x : (which == 1 ? c.y : c.z)) > eff;
+        if (which == 0) lost0 = lost;
+        if ((dbl && which == 1) ? (lost && lost0) : lost) sv = 0.;
       }
-      if (!(nh > det.coinLevel)) {  // :1422-1424
-        coin1 = u32d(c.z) > P.coin_u_min;
-        coin2 = u32d(c.w) > P.coin_u_min;
+      if (dbl && which == 0) {
+        first = sv;
+      } else {
+        // hit index of this photo-electron within the slot: the double hit is hit 0, the single after it hit 1
+        const int hit = dbl ? which - 1 : which;
+        const uint32_t cw = hit == 0 ? c.w : (hit == 1 ? c2.x : c2.y);
+        const bool coin = !coin_draws || u32d(cw) > P.coin_u_min;
+        hit_commit(P, s_area, s_spike, e, (dbl && which == 1) ? first + sv : sv, coin);
       }
-    }
-    if (dp) {
-      hit_commit(P, s_area, s_spike, e, s1 + s2, coin1);
-    } else {
-      hit_commit(P, s_area, s_spike, e, s1, coin1);
-      if (hasb) hit_commit(P, s_area, s_spike, e, s2, coin2);
     }
   }
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(kHitBlock, NB_HIT_MINB)
-    k_hits(const __grid_constant__ RunParams P, unsigned int* __restrict__ next_group) {
+// the body of k_hits / k_hits_sweep.  SWEEP = false: P0 is the launch's RunParams (kernel parameter, constant bank).
+// SWEEP = true: a group's RunParams is copied from A.params[point] into the shared sP whenever the block moves to
+// another grid point; n_events and the event ids come from the sweep's slot layout.
+template <bool SWEEP>
+NB_D void hits_body(const RunParams* P0, const SweepArgs* Ap, RunParams* sP, unsigned int* __restrict__ next_group) {
+  const RunParams& P = SWEEP ? *sP : *P0;
+  const SweepArgs& A = *Ap;  // dereferenced in the sweep instantiation only
   __shared__ int s_ppref[kHitGroup + 1];  // slot-count prefix: the flattened work items
   __shared__ int s_nh[kHitGroup];         // hits of the event
   __shared__ int s_nd[kHitGroup];         // of which double-phe
@@ -422,11 +510,12 @@ __global__ void __launch_bounds__(kHitBlock, NB_HIT_MINB)
   constexpr int PER = kHitGroup / kHitBlock;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const nb200_detector& det = P.det;
-  const Work& W = P.work;
-  const uint64_t n_groups = (P.n_events + kHitGroup - 1) / kHitGroup;
+  const Work& W = SWEEP ? A.work : P0->work;
+  const uint64_t n_launch = SWEEP ? A.n_slots : P0->n_events;  // workspace entries of this launch
+  const uint64_t n_groups = (n_launch + kHitGroup - 1) / kHitGroup;
+  uint32_t cur_point = 0xffffffffu;
   uint32_t q_addr = uint32_t(__cvta_generic_to_shared(&s_q[wid][0]));
   asm volatile("" : "+r"(q_addr));  // opaque: keep it in a register instead of recomputing it at every push
-  const bool all_special = det.sPEeff < 1.;  // efficiency draws: every slot goes through the finisher
 
   // groups are handed out by a device counter (zeroed before the launch): their cost follows their hit
   // counts, so a static stride leaves the last wave ragged
@@ -437,18 +526,31 @@ __global__ void __launch_bounds__(kHitBlock, NB_HIT_MINB)
     const uint64_t grp = s_grp;
     if (grp >= n_groups) break;
     const uint64_t gbase = grp * kHitGroup;
-    const uint64_t ev0 = P.first_event + P.chunk_off + gbase;
+    uint64_t ev0, n_valid = n_launch;  // event id of workspace entry gbase; entries >= n_valid are idle
+    if (SWEEP) {
+      const uint64_t slot = A.slot0 + gbase;
+      const uint32_t point = uint32_t(slot / A.n_pad);
+      if (point != cur_point) {
+        sweep_load_params(sP, A.params, point);
+        cur_point = point;
+      }
+      const uint64_t i0 = slot - uint64_t(point) * A.n_pad;
+      ev0 = A.first_event + i0;
+      n_valid = i0 < A.n_per_point ? min(n_launch, gbase + (A.n_per_point - i0)) : gbase;
+    } else
+      ev0 = P0->first_event + P0->chunk_off + gbase;
+    const bool all_special = det.sPEeff < 1.;  // efficiency draws: every slot goes through the finisher
     // slot counts of my PER consecutive events -> exclusive prefix over the group
     int cnt[PER];
     int mine = 0;
 #pragma unroll
     for (int k = 0; k < PER; ++k) {
       const uint64_t idx = gbase + uint64_t(tid) * PER + k;
-      int nh = (idx < P.n_events) ? W.nHits[idx] : 0;  // negative: Parametric S1 (k_post)
+      int nh = (idx < n_valid) ? W.nHits[idx] : 0;  // negative: Parametric S1 (k_post)
       nh = nh > 0 ? nh : 0;
-      int nd = (idx < P.n_events) ? W.nphe[idx] : 0;  // k_pre left the double-phe count here
+      int nd = (idx < n_valid) ? W.nphe[idx] : 0;  // k_pre left the double-phe count here
       nd = nd < 0 ? 0 : (nd > nh ? nh : nd);
-      cnt[k] = nd + ((nh - nd + 1) >> 1);
+      cnt[k] = hit_slots(nh, nd);
       mine += cnt[k];
       s_nh[tid * PER + k] = nh;
       s_nd[tid * PER + k] = nd;
@@ -467,7 +569,7 @@ __global__ void __launch_bounds__(kHitBlock, NB_HIT_MINB)
     const int h0 = int((long long)H * tid / kHitBlock);
     const int h1 = int((long long)H * (tid + 1) / kHitBlock);
     const int maxlen = __reduce_max_sync(0xffffffffu, h1 - h0);
-    int e = 0, e_end = 0, nd = 0, jlast = -1, j = 0;  // jlast: the slot holding a lone single hit, if any
+    int e = 0, e_end = 0, nd = 0, ns = 0, j = 0;
     bool sp = false;
     int h = h0;  // running slot index; this thread owns [h0, h1)
     if (h1 > h0) {
@@ -483,8 +585,7 @@ __global__ void __launch_bounds__(kHitBlock, NB_HIT_MINB)
       e = lo;
       e_end = s_ppref[e + 1];
       nd = s_nd[e];
-      const int ns = s_nh[e] - nd;
-      jlast = (ns & 1) ? nd + (ns >> 1) : -1;
+      ns = s_nh[e] - nd;
       sp = all_special || !(nd + ns > det.coinLevel);
       j = h0 - s_ppref[e];
     }
@@ -509,32 +610,38 @@ __global__ void __launch_bounds__(kHitBlock, NB_HIT_MINB)
             e_end = s_ppref[e + 1];
           } while (e_end == h);
           nd = s_nd[e];
-          const int ns = s_nh[e] - nd;
-          jlast = (ns & 1) ? nd + (ns >> 1) : -1;
+          ns = s_nh[e] - nd;
           sp = all_special || !(nd + ns > det.coinLevel);
           j = 0;
           const uint64_t hev = ev0 + e;
           pev = philox_event_prep(uint32_t(hev), uint32_t(hev >> 32), STREAM_HIT, P.rk);
         }
-        // one Philox block per slot, 64 bits per photo-electron: 28 (abscissa) + 11 (layer) for the
-        // ziggurat normal, 4 for the truncation pre-test (21 spare)
+        // one Philox block per slot, 42 bits per photo-electron: 27 (abscissa) + 11 (layer) for the
+        // ziggurat normal, 4 for the truncation pre-test
         const u128 r = philox4x32_10_rk_event(pev, uint32_t(j), P.rk);
-        double za, zb;
-        const bool ka = zig_fast(r.x, r.y, s_zk, s_zw, za), kb = zig_fast(r.z, r.w, s_zk, s_zw, zb);
-        const double sa = fma(P.pe_sig, za, P.pe_mu), sb = fma(P.pe_sig, zb, P.pe_mu);
-        const bool dp = j < nd;
-        const bool hasb = j != jlast;
+        uint32_t A0, A1, A2, L0, L1, L2;
+        pe_fields(r, 0, A0, L0);
+        pe_fields(r, 1, A1, L1);
+        pe_fields(r, 2, A2, L2);
+        double z0, z1, z2;
+        const bool f0 = zig_fast(A0, L0, s_zk, s_zw, z0), f1 = zig_fast(A1, L1, s_zk, s_zw, z1),
+                   f2 = zig_fast(A2, L2, s_zk, s_zw, z2);
+        const double v0 = fma(P.pe_sig, z0, P.pe_mu), v1 = fma(P.pe_sig, z1, P.pe_mu), v2 = fma(P.pe_sig, z2, P.pe_mu);
+        const bool dbl = j < nd;
+        const int nv = slot_valid(j, nd, ns);
         // truncation pre-test (nb_params.h): above pe_cut nothing to do; below it a 4-bit uniform
         // settles it unless it is 15 or the acceptance is under 15/16 (S below pe_sfast)
-        const bool ca = sa <= P.pe_cut && (sa < P.pe_sfast || (r.x & 0xFu) == 15u);
-        const bool cb = sb <= P.pe_cut && (sb < P.pe_sfast || (r.z & 0xFu) == 15u);
-        queue = sp || !ka || ca || (hasb && (!kb || cb));
+        const bool c0 = v0 <= P.pe_cut && (v0 < P.pe_sfast || (A0 & NB_PE_PRETEST_MASK) == NB_PE_PRETEST_MASK);
+        const bool c1 = v1 <= P.pe_cut && (v1 < P.pe_sfast || (A1 & NB_PE_PRETEST_MASK) == NB_PE_PRETEST_MASK);
+        const bool c2 = v2 <= P.pe_cut && (v2 < P.pe_sfast || (A2 & NB_PE_PRETEST_MASK) == NB_PE_PRETEST_MASK);
+        queue = sp || !f0 || c0 || (nv >= 2 && (!f1 || c1)) || (nv >= 3 && (!f2 || c2));
         if (!queue) {
           // areas are summed as integers in units of 2^-32 phe: fma(a, 2^32, 1.5 * 2^52) rounds a 2^32 to the
           // nearest integer (ties to even, as __double2ll_rn) and leaves it in the low mantissa bits; the raw
           // words are added up and the offsets taken out at the flush (a_spike of them)
-          const double a1 = dp ? sa + sb : sa;
-          const double a2 = (hasb && !dp) ? sb : -DBL_MAX;
+          const double a1 = dbl ? v0 + v1 : v0;
+          const double a2 = dbl ? (nv >= 3 ? v2 : -DBL_MAX) : (nv >= 2 ? v1 : -DBL_MAX);
+          const double a3 = (!dbl && nv >= 3) ? v2 : -DBL_MAX;
           if (a1 > det.sPEthr) {
             a_spike += 1u;
             a_fx += (unsigned long long)__double_as_longlong(fma(a1, NB_AREA_FX, NB_AREA_MAGIC));
@@ -542,6 +649,10 @@ __global__ void __launch_bounds__(kHitBlock, NB_HIT_MINB)
           if (a2 > det.sPEthr) {
             a_spike += 1u;
             a_fx += (unsigned long long)__double_as_longlong(fma(a2, NB_AREA_FX, NB_AREA_MAGIC));
+          }
+          if (a3 > det.sPEthr) {
+            a_spike += 1u;
+            a_fx += (unsigned long long)__double_as_longlong(fma(a3, NB_AREA_FX, NB_AREA_MAGIC));
           }
         }
       }
@@ -571,7 +682,7 @@ __global__ void __launch_bounds__(kHitBlock, NB_HIT_MINB)
     for (int jj = 0; jj < PER; ++jj) {
       const int i = jj * kHitBlock + tid;  // coalesced
       const uint64_t idx = gbase + i;
-      if (idx < P.n_events) {
+      if (idx < n_valid) {
         W.area[idx] = double(s_area[i]) * (1. / NB_AREA_FX);
         W.spike[idx] = int(s_spike[i]);
         W.nphe[idx] = s_nh[i] + s_nd[i];
@@ -581,130 +692,193 @@ __global__ void __launch_bounds__(kHitBlock, NB_HIT_MINB)
   }
 }
 
+
+__global__ void __launch_bounds__(kHitBlock, NB_HIT_MINB)
+    k_hits(const __grid_constant__ RunParams P, unsigned int* __restrict__ next_group) {
+  hits_body<false>(&P, nullptr, nullptr, next_group);
+}
+
+__global__ void __launch_bounds__(kHitBlock, NB_HIT_MINB)
+    k_hits_sweep(const __grid_constant__ SweepArgs A, unsigned int* __restrict__ next_group) {
+  __shared__ __align__(16) RunParams sP;
+  hits_body<true>(nullptr, &A, &sP, next_group);
+}
+
+// one event of k_post.  s_band / s_h2: the block's shared-memory band accumulator (band_smem) ; gband: the global
+// accumulator the block flushes into (used directly when the band does not fit in shared memory)
+NB_D void post_body(const RunParams& P, const Work& W, uint64_t idx, uint64_t gidx, uint64_t ev, bool active,
+                    unsigned long long* s_band, unsigned int* s_h2, unsigned long long* gband, bool band_smem,
+                    int* __restrict__ err_flag) {
+  const nb200_detector& det = P.det;
+  const int nb = P.ana.numBins, lb = P.ana.logBins;
+  const bool cli = !P.vec_mode;
+  Stream g;
+  g.init(P.seed, ev, STREAM_POST);
+  double keV = W.keV[idx];
+  const double px = W.px[idx], py = W.py[idx], pz = W.pz[idx], sx = W.sx[idx], sy = W.sy[idx];
+  const double field = W.field[idx], dt = W.dt[idx];
+  Yields y{W.yNph[idx], W.yNe[idx], 0., W.yL[idx], field, -999.};
+  S1Pre pre;
+  pre.posDepSm = W.posDepSm[idx];
+  pre.fitSm = W.fitSm[idx];
+  const int nh = W.nHits[idx];
+  pre.full = nh >= 0;
+  pre.nHits = pre.full ? nh : -(nh + 1);
+  pre.eff = 0.;
+  S1Acc acc{0., 0, 0};
+  if (pre.full) {
+    if (nh > 0) {
+      acc.area = W.area[idx];
+      acc.spike = W.spike[idx];
+      acc.nphe = W.nphe[idx];
+    }
+  } else
+    s1_parametric(g, ev, P, pre.nHits, acc);
+  double scint[9], scint2[9];
+  const PostDraws D = post_draws(g);
+  NB_LOCKSTEP();
+  s1_epilogue(g, P, pre, acc, D, scint);
+  int Ne = W.electrons[idx];
+  if (cli && pz < det.cathode) Ne = 0;  // execNEST.cpp:1107
+  NB_LOCKSTEP();
+  get_s2(g, ev, P, D, Ne, px, py, pz, sx, sy, dt, field, scint2);
+  NB_LOCKSTEP();
+  double signal1 = 0., signal2 = 0., signalE = 0., keVee = 0.;
+  const double keV_true = keV;
+  if (cli) {
+    select_signals(P.ana, scint, scint2, signal1, signal2);
+    signalE = reconstruct_energy(P, y, scint, scint2, signal1, signal2, field, keV, keVee);
+  }
+  NB_LOCKSTEP();
+  if (!active) return;
+  if (cli) {
+    if (P.do_band) {
+      bool acc_ok = false;
+      double xv = 0., yv = 0.;
+      int bin = band_bin(P, signal1, signal2, acc_ok, xv, yv);
+      if (bin >= 0) {
+        unsigned long long* B = band_smem ? s_band : gband;
+        unsigned long long* b = B + size_t(bin) * BAND_WORDS;
+        if (acc_ok) {
+          atomicAdd(&b[0], 1ull);
+          atomicAdd(&b[2], (unsigned long long)(long long)llrint(xv * NB200_FX_S1));
+          atomicAdd(&b[3], (unsigned long long)(long long)llrint(yv * NB200_FX_Y));
+          atomicAdd(&b[4], (unsigned long long)(long long)llrint(yv * yv * NB200_FX_Y2));
+          atomicAdd(&b[5], (unsigned long long)(long long)llrint(yv * yv * yv * NB200_FX_Y3));
+          if (yv != 0. && lb > 0) {
+            int jb = int((yv - P.ana.logMin) / (P.ana.logMax - P.ana.logMin) * double(lb));
+            jb = min(max(jb, 0), lb - 1);
+            if (band_smem)
+              atomicAdd(&s_h2[bin * lb + jb], 1u);
+            else
+              atomicAdd(&gband[size_t(nb) * BAND_WORDS + size_t(bin) * lb + jb], 1ull);
+          }
+        } else
+          atomicAdd(&b[1], 1ull);
+      }
+    }
+  }
+  if (P.write_soa) {
+    const SoaDev& o = P.soa;
+    if (o.energy_kev) o.energy_kev[gidx] = keV_true;
+    if (o.x_mm) o.x_mm[gidx] = px;
+    if (o.y_mm) o.y_mm[gidx] = py;
+    if (o.z_mm) o.z_mm[gidx] = pz;
+    if (o.field) o.field[gidx] = field;
+    if (o.driftTime) o.driftTime[gidx] = dt;
+    if (o.smear_x) o.smear_x[gidx] = sx;
+    if (o.smear_y) o.smear_y[gidx] = sy;
+    if (o.photons) o.photons[gidx] = W.photons[idx];
+    if (o.electrons) o.electrons[gidx] = Ne;
+    if (o.ions) o.ions[gidx] = W.ions[idx];
+    if (o.excitons) o.excitons[gidx] = W.excitons[idx];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      if (o.s1[k]) o.s1[k][gidx] = scint[k];
+      if (o.s2[k]) o.s2[k][gidx] = scint2[k];
+    }
+    if (o.signal1) o.signal1[gidx] = signal1;
+    if (o.signal2) o.signal2[gidx] = signal2;
+    if (o.signalE) o.signalE[gidx] = cli ? signalE : keV;
+    if (o.Nph_mean) o.Nph_mean[gidx] = y.Nph;
+    if (o.Ne_mean) o.Ne_mean[gidx] = y.Ne;
+    if (o.keVee) o.keVee[gidx] = keVee;
+  }
+}
+
+NB_D void band_smem_zero(unsigned long long* s_band, unsigned int* s_h2, int nb, int lb) {
+  for (int i = threadIdx.x; i < nb * BAND_WORDS; i += kPostBlock) s_band[i] = 0ull;
+  for (int i = threadIdx.x; i < nb * lb; i += kPostBlock) s_h2[i] = 0u;
+  __syncthreads();
+}
+NB_D void band_smem_flush(const unsigned long long* s_band, const unsigned int* s_h2, int nb, int lb,
+                          unsigned long long* gband) {
+  __syncthreads();
+  for (int i = threadIdx.x; i < nb * BAND_WORDS; i += kPostBlock) {
+    unsigned long long v = s_band[i];
+    if (v) atomicAdd(&gband[i], v);
+  }
+  for (int i = threadIdx.x; i < nb * lb; i += kPostBlock) {
+    unsigned int v = s_h2[i];
+    if (v) atomicAdd(&gband[size_t(nb) * BAND_WORDS + i], (unsigned long long)v);
+  }
+}
+
 __global__ void __launch_bounds__(kPostBlock, NB_POST_MINB)
     k_post(const __grid_constant__ RunParams P, int* __restrict__ err_flag) {
   extern __shared__ __align__(16) unsigned long long s_band[];  // [numBins*6] then u32 hist2d
   const int tid = threadIdx.x;
-  const nb200_detector& det = P.det;
-  const Work& W = P.work;
   const int nb = P.ana.numBins, lb = P.ana.logBins;
   const bool band_smem = P.do_band && P.band_in_smem;
   unsigned int* s_h2 = reinterpret_cast<unsigned int*>(s_band + size_t(nb) * BAND_WORDS);
-  if (band_smem) {
-    for (int i = tid; i < nb * BAND_WORDS; i += kPostBlock) s_band[i] = 0ull;
-    for (int i = tid; i < nb * lb; i += kPostBlock) s_h2[i] = 0u;
-    __syncthreads();
-  }
-  const bool cli = !P.vec_mode;
+  if (band_smem) band_smem_zero(s_band, s_h2, nb, lb);
   for (uint64_t base = blockIdx.x * uint64_t(kPostBlock); base < P.n_events;
        base += uint64_t(gridDim.x) * kPostBlock) {
     const bool active = base + tid < P.n_events;
     const uint64_t idx = active ? base + tid : P.n_events - 1;
     const uint64_t gidx = P.chunk_off + idx;
-    const uint64_t ev = P.first_event + gidx;
-    Stream g;
-    g.init(P.seed, ev, STREAM_POST);
-    double keV = W.keV[idx];
-    const double px = W.px[idx], py = W.py[idx], pz = W.pz[idx], sx = W.sx[idx], sy = W.sy[idx];
-    const double field = W.field[idx], dt = W.dt[idx];
-    Yields y{W.yNph[idx], W.yNe[idx], 0., W.yL[idx], field, -999.};
-    S1Pre pre;
-    pre.posDepSm = W.posDepSm[idx];
-    pre.fitSm = W.fitSm[idx];
-    const int nh = W.nHits[idx];
-    pre.full = nh >= 0;
-    pre.nHits = pre.full ? nh : -(nh + 1);
-    pre.eff = 0.;
-    S1Acc acc{0., 0, 0};
-    if (pre.full) {
-      if (nh > 0) {
-        acc.area = W.area[idx];
-        acc.spike = W.spike[idx];
-        acc.nphe = W.nphe[idx];
-      }
-    } else
-      s1_parametric(g, ev, P, pre.nHits, acc);
-    double scint[9], scint2[9];
-    NB_LOCKSTEP();
-    s1_epilogue(g, P, pre, acc, scint);
-    int Ne = W.electrons[idx];
-    if (cli && pz < det.cathode) Ne = 0;  // execNEST.cpp:1107
-    NB_LOCKSTEP();
-    get_s2(g, ev, P, Ne, px, py, pz, sx, sy, dt, field, scint2);
-    NB_LOCKSTEP();
-    double signal1 = 0., signal2 = 0., signalE = 0., keVee = 0.;
-    const double keV_true = keV;
-    if (cli) {
-      select_signals(P.ana, scint, scint2, signal1, signal2);
-      signalE = reconstruct_energy(P, y, scint, scint2, signal1, signal2, field, keV, keVee);
-    }
-    NB_LOCKSTEP();
-    if (!active) continue;
-    if (cli) {
-      if (P.do_band) {
-        bool acc_ok = false;
-        double xv = 0., yv = 0.;
-        int bin = band_bin(P, signal1, signal2, acc_ok, xv, yv);
-        if (bin >= 0) {
-          unsigned long long* B = band_smem ? s_band : P.band;
-          unsigned long long* b = B + size_t(bin) * BAND_WORDS;
-          if (acc_ok) {
-            atomicAdd(&b[0], 1ull);
-            atomicAdd(&b[2], (unsigned long long)(long long)llrint(xv * NB200_FX_S1));
-            atomicAdd(&b[3], (unsigned long long)(long long)llrint(yv * NB200_FX_Y));
-            atomicAdd(&b[4], (unsigned long long)(long long)llrint(yv * yv * NB200_FX_Y2));
-            atomicAdd(&b[5], (unsigned long long)(long long)llrint(yv * yv * yv * NB200_FX_Y3));
-            if (yv != 0. && lb > 0) {
-              int jb = int((yv - P.ana.logMin) / (P.ana.logMax - P.ana.logMin) * double(lb));
-              jb = min(max(jb, 0), lb - 1);
-              if (band_smem)
-                atomicAdd(&s_h2[bin * lb + jb], 1u);
-              else
-                atomicAdd(&P.band[size_t(nb) * BAND_WORDS + size_t(bin) * lb + jb], 1ull);
-            }
-          } else
-            atomicAdd(&b[1], 1ull);
-        }
-      }
-    }
-    if (P.write_soa) {
-      const SoaDev& o = P.soa;
-      if (o.energy_kev) o.energy_kev[gidx] = keV_true;
-      if (o.x_mm) o.x_mm[gidx] = px;
-      if (o.y_mm) o.y_mm[gidx] = py;
-      if (o.z_mm) o.z_mm[gidx] = pz;
-      if (o.field) o.field[gidx] = field;
-      if (o.driftTime) o.driftTime[gidx] = dt;
-      if (o.smear_x) o.smear_x[gidx] = sx;
-      if (o.smear_y) o.smear_y[gidx] = sy;
-      if (o.photons) o.photons[gidx] = W.photons[idx];
-      if (o.electrons) o.electrons[gidx] = Ne;
-      if (o.ions) o.ions[gidx] = W.ions[idx];
-      if (o.excitons) o.excitons[gidx] = W.excitons[idx];
-#pragma unroll
-      for (int k = 0; k < 9; ++k) {
-        if (o.s1[k]) o.s1[k][gidx] = scint[k];
-        if (o.s2[k]) o.s2[k][gidx] = scint2[k];
-      }
-      if (o.signal1) o.signal1[gidx] = signal1;
-      if (o.signal2) o.signal2[gidx] = signal2;
-      if (o.signalE) o.signalE[gidx] = cli ? signalE : keV;
-      if (o.Nph_mean) o.Nph_mean[gidx] = y.Nph;
-      if (o.Ne_mean) o.Ne_mean[gidx] = y.Ne;
-      if (o.keVee) o.keVee[gidx] = keVee;
-    }
+    post_body(P, P.work, idx, gidx, P.first_event + gidx, active, s_band, s_h2, P.band, band_smem, err_flag);
   }
-  if (band_smem) {
-    __syncthreads();
-    for (int i = tid; i < nb * BAND_WORDS; i += kPostBlock) {
-      unsigned long long v = s_band[i];
-      if (v) atomicAdd(&P.band[i], v);
+  if (band_smem) band_smem_flush(s_band, s_h2, nb, lb, P.band);
+}
+
+// sweep: a block takes a contiguous run of 1024-slot tiles (few point changes) and flushes its shared band into
+// the point's slab whenever the point changes
+__global__ void __launch_bounds__(kPostBlock, NB_POST_MINB)
+    k_post_sweep(const __grid_constant__ SweepArgs A, int band_in_smem, int* __restrict__ err_flag) {
+  extern __shared__ __align__(16) unsigned long long s_band[];
+  __shared__ __align__(16) RunParams sP;
+  const int tid = threadIdx.x;
+  const uint64_t n_tiles = (A.n_slots + kPostBlock - 1) / kPostBlock;
+  const uint64_t t0 = n_tiles * blockIdx.x / gridDim.x, t1 = n_tiles * (blockIdx.x + 1) / gridDim.x;
+  uint32_t cur = 0xffffffffu;
+  int nb = 0, lb = 0;
+  unsigned int* s_h2 = nullptr;
+  unsigned long long* gband = nullptr;
+  bool band_smem = false;
+  for (uint64_t t = t0; t < t1; ++t) {
+    const uint64_t base = t * kPostBlock;
+    const uint64_t slot = A.slot0 + base;
+    const uint32_t point = uint32_t(slot / A.n_pad);
+    if (point != cur) {
+      if (cur != 0xffffffffu && band_smem) band_smem_flush(s_band, s_h2, nb, lb, gband);
+      sweep_load_params(&sP, A.params, point);
+      cur = point;
+      nb = sP.ana.numBins;
+      lb = sP.ana.logBins;
+      s_h2 = reinterpret_cast<unsigned int*>(s_band + size_t(nb) * BAND_WORDS);
+      gband = A.bands + uint64_t(point) * A.band_words;
+      band_smem = sP.do_band && band_in_smem;
+      if (band_smem) band_smem_zero(s_band, s_h2, nb, lb);
     }
-    for (int i = tid; i < nb * lb; i += kPostBlock) {
-      unsigned int v = s_h2[i];
-      if (v) atomicAdd(&P.band[size_t(nb) * BAND_WORDS + i], (unsigned long long)v);
-    }
+    const uint64_t it0 = slot - uint64_t(point) * A.n_pad;  // event index of the tile's first slot (< n_per_point)
+    const uint64_t i = it0 + tid;
+    const bool active = i < A.n_per_point;
+    const uint64_t ie = active ? i : A.n_per_point - 1;
+    // padding lanes redo the point's last event (its workspace entry is in this tile) and store nothing
+    post_body(sP, A.work, base + (ie - it0), ie, A.first_event + ie, active, s_band, s_h2, gband, band_smem, err_flag);
   }
+  if (cur != 0xffffffffu && band_smem) band_smem_flush(s_band, s_h2, nb, lb, gband);
 }
 
 // CalculateG2's single-electron Monte Carlo (NEST.cpp:2169-2215): one thread = one electron
@@ -751,9 +925,10 @@ __global__ void k_hitmath(size_t n, const uint32_t* __restrict__ bits, double* _
   }
 }
 
-// test hook (nb200_debug_normal): the hit loop's ziggurat normal exactly as k_hits and its slow
-// finisher draw it -- pair j of event `first + i`, both hits; kind[.] = 0 core, 1 wedge / tail
-__global__ void __launch_bounds__(256) k_zignormal(uint64_t seed, uint64_t first, size_t pairs,
+// test hook (nb200_debug_normal): the hit loop's ziggurat normals exactly as k_hits and its finisher draw them
+// (pe_normal, the function both go through): the three photo-electrons of slot i % 1024 of event
+// first + i / 1024; kind[.] = 0 layer core (finished in the main loop), 1 wedge / tail completion
+__global__ void __launch_bounds__(256) k_zignormal(uint64_t seed, uint64_t first, size_t slots,
                                                    double* __restrict__ out, unsigned char* __restrict__ kind) {
   __shared__ double s_zw[NB_ZIG_N];
   __shared__ uint32_t s_zk[NB_ZIG_N];
@@ -764,24 +939,17 @@ __global__ void __launch_bounds__(256) k_zignormal(uint64_t seed, uint64_t first
   __syncthreads();
   uint32_t rk[20];
   philox_round_keys(seed, rk);
-  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < pairs; i += size_t(gridDim.x) * blockDim.x) {
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < slots; i += size_t(gridDim.x) * blockDim.x) {
     const uint64_t ev = first + (i >> 10);
     const uint32_t j = uint32_t(i & 1023u), e0 = uint32_t(ev), e1 = uint32_t(ev >> 32);
     const u128 r = philox4x32_10_rk(e0, e1, j, STREAM_HIT, rk);
-    double za, zb;
-    const bool ka = zig_fast(r.x, r.y, s_zk, s_zw, za), kb = zig_fast(r.z, r.w, s_zk, s_zw, zb);
-    // as hits_finish_slow: the spare word of the hit's STREAM_HIT2 block decides the first wedge test
-    if (!ka)
-      za = zig_finish(r.x, r.y, philox4x32_10_rk(e0, e1, 2 * j, STREAM_HIT2, rk).z, true, e0, e1, 2 * j, STREAM_ZIG,
-                      uint32_t(seed), uint32_t(seed >> 32));
-    if (!kb)
-      zb = zig_finish(r.z, r.w, philox4x32_10_rk(e0, e1, 2 * j + 1, STREAM_HIT2, rk).z, (j & 1u) != 0u, e0, e1, 2 * j + 1,
-                      STREAM_ZIG, uint32_t(seed), uint32_t(seed >> 32));
-    out[2 * i] = za;
-    out[2 * i + 1] = zb;
-    if (kind) {
-      kind[2 * i] = ka ? 0 : 1;
-      kind[2 * i + 1] = kb ? 0 : 1;
+    const u128 t = philox4x32_10_rk(e0, e1, j, STREAM_HIT2, rk);
+#pragma unroll
+    for (int which = 0; which < 3; ++which) {
+      uint32_t A;
+      bool fast;
+      out[3 * i + which] = pe_normal(r, t, which, e0, e1, j, uint32_t(seed), uint32_t(seed >> 32), s_zk, s_zw, A, fast);
+      if (kind) kind[3 * i + which] = fast ? 0 : 1;
     }
   }
 }
@@ -856,7 +1024,8 @@ __global__ void __launch_bounds__(256) k_s2(const __grid_constant__ RunParams P,
     Stream g;
     g.init(P.seed, ev, STREAM_POST);
     double o[9];
-    get_s2(g, ev, P, a.Ne[i], a.pos[i], a.pos[a.n + i], a.pos[2 * a.n + i], a.pos[3 * a.n + i], a.pos[4 * a.n + i], a.dt[i],
+    const PostDraws D = post_draws(g);
+    get_s2(g, ev, P, D, a.Ne[i], a.pos[i], a.pos[a.n + i], a.pos[2 * a.n + i], a.pos[3 * a.n + i], a.pos[4 * a.n + i], a.dt[i],
            a.field[i], o);
 #pragma unroll
     for (int k = 0; k < 9; ++k) a.out[k * a.n + i] = o[k];
@@ -914,7 +1083,8 @@ __global__ void __launch_bounds__(256) k_s1post(const __grid_constant__ RunParam
     } else
       s1_parametric(g, ev, P, pre.nHits, acc);
     double scint[9];
-    s1_epilogue(g, P, pre, acc, scint);
+    const PostDraws D = post_draws(g);
+    s1_epilogue(g, P, pre, acc, D, scint);
 #pragma unroll
     for (int k = 0; k < 9; ++k) a.out[k * a.stride + gi] = scint[k];
   }

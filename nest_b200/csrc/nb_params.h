@@ -63,6 +63,7 @@ struct RunParams {
   double pe_inv_tau16;   // 16 / pe_tau: index scale of the Phi bounds table (pe_accept_exact)
   const uint2* dpe_alias;  // alias tables of Binomial(2^b, P_dphe) (nb_rng.cuh: binomial_fixed_p), or null
   double coin_u_min;     // exp(-coinWind/20): -20 ln u < coinWind <=> u > this  NEST.cpp:1422
+  double coin_pow[11];   // pow(numPMTs, 1 - k), k = 0..10: the 2-fold coincidence probability  NEST.cpp:1655
   double below_thr_pct;  // Parametric S1 threshold percentile       NEST.cpp:1437-1457
   double recon_mult;     // MultFact prefactor, execNEST.cpp:1179-1182
   double wimp_dr0[9];    // WIMP_dRate(0) per Xe isotope             TestSpectra.cpp:459,466

@@ -352,7 +352,7 @@ NB_D double log_pos(double x) {
 // Layer i covers |x| < x_i at heights f(x_i)..f(x_{i+1}), x_0 = V/f(R) (base strip + tail),
 // x_1 = R, x_2048 = 0.  Tables are built by nb200_create (host, double) and staged in shared
 // memory by k_hits:  zk[i] = floor(2^28 x_{i+1}/x_i), zw[i] = x_i / 2^28.
-// Abscissa: t = 2 s + 1 with s the signed 28-bit field of the word (odd t: symmetric, no atom
+// Abscissa: t = 8 s + 4 with s the signed 26-bit field at the top of the word (symmetric, no atom
 // at zero), x = t zw[i]; it lies inside the next layer (certain accept) iff |t| < zk[i].
 #define NB_ZIG_N (1 << NB_ZIG_BITS)
 __device__ uint32_t g_zig_k[NB_ZIG_N];
@@ -361,15 +361,17 @@ __device__ double g_zig_f[NB_ZIG_N + 1];  // f(x_i) = exp(-x_i^2/2), f[N] = 1
 __device__ double g_zig_R;
 
 static __constant__ double c_zigk[1] = {4503601774854144.0};  // 2^52 + 2^31 (constant-bank operand)
-NB_D int32_t zig_t(uint32_t w0) { return (int32_t(w0) >> 3) | 1; }
+// abscissa from the top 27 bits of the word: t = 8 s + 4 with s the signed 26-bit field -- symmetric, no atom at
+// zero, on the scale of the 28-bit tables above (|t| < 2^28).  Bits 4..1 of the word are free for the caller
+// (the hit loop's truncation pre-test), bit 0 is unused.
+NB_D int32_t zig_t(uint32_t w0) { return ((int32_t(w0) >> 3) & ~7) | 4; }
 // double(t) without the conversion unit: 2^52 + 2^31 + t has t in its low mantissa bits
 NB_D double zig_td(int32_t t) {
   return __hiloint2double(0x43300000, t ^ int32_t(0x80000000)) - c_zigk[0];
 }
-// fast path: z is the normal iff the return value is true
-NB_D bool zig_fast(uint32_t w0, uint32_t w1, const uint32_t* zk, const double* zw, double& z) {
+// fast path: z is the normal iff the return value is true.  w0: abscissa word, i: layer index
+NB_D bool zig_fast(uint32_t w0, uint32_t i, const uint32_t* zk, const double* zw, double& z) {
   const int32_t t = zig_t(w0);
-  const uint32_t i = w1 >> (32 - NB_ZIG_BITS);
   z = zig_td(t) * zw[i];
   return uint32_t(abs(t)) < zk[i];
 }
@@ -383,10 +385,9 @@ NB_D bool zig_wedge(uint32_t i, int32_t t, double u, double& x) {
   const double f0 = g_zig_f[i], f1 = g_zig_f[i + 1];
   return fma(u, f1 - f0, f0) < exp(-0.5 * x * x);
 }
-__device__ __noinline__ double zig_finish(uint32_t w0, uint32_t w1, uint32_t spare, bool has_spare, uint32_t e0,
+__device__ __noinline__ double zig_finish(uint32_t w0, uint32_t i, uint32_t spare, bool has_spare, uint32_t e0,
                                           uint32_t e1, uint32_t k, uint32_t stream, uint32_t k0, uint32_t k1) {
   int32_t t = zig_t(w0);
-  uint32_t i = w1 >> (32 - NB_ZIG_BITS);
   bool have = true;  // (i, t) awaits its wedge / tail decision
   double x;
   if (has_spare && i != 0u) {
@@ -419,6 +420,29 @@ __device__ __noinline__ double zig_finish(uint32_t w0, uint32_t w1, uint32_t spa
   return 0.;
 }
 
+// The hit loop packs THREE photo-electrons into one Philox block (128 bits): each takes 27 bits of abscissa,
+// 4 bits of truncation pre-test and NB_ZIG_BITS (<= 11) bits of layer index.  Field `which` of block r:
+// abscissa word A (top 27 bits abscissa, bits 4..1 pre-test, bit 0 unused) and layer index L.
+//   0: A = x,                    L = top bits of y
+//   1: A = y << B | z >> (32-B), L = the next B bits of z
+//   2: A = z << 2B | w >> (32-2B), L = the low B bits of w (bit B-1 of w is A's unused bit 0 when B = 11)
+NB_D void pe_fields(const u128& r, int which, uint32_t& A, uint32_t& L) {
+  constexpr int B = NB_ZIG_BITS;
+  static_assert(B <= 11, "three photo-electron fields must fit one Philox block");
+  constexpr uint32_t M = (1u << B) - 1u;
+  if (which == 0) {
+    A = r.x;
+    L = r.y >> (32 - B);
+  } else if (which == 1) {
+    A = __funnelshift_l(r.z, r.y, B);
+    L = (r.z >> (32 - 2 * B)) & M;
+  } else {
+    A = __funnelshift_l(r.w, r.z, 2 * B);
+    L = r.w & M;
+  }
+}
+#define NB_PE_PRETEST_MASK 0x1Eu  // bits 4..1 of the abscissa word: all set = the 1-in-16 that needs the exact test
+
 // ---- samplers (device) -------------------------------------------------------------
 
 // two independent standard normals from one Box-Muller transform.  The reference's
@@ -437,6 +461,15 @@ NB_D void normal_pair(Stream& g, double& z0, double& z1) {
   uint32_t a, b, c, d;
   g.next2(a, b);
   g.next2(c, d);
+  double2 z = box_muller(a, b, c);
+  z0 = z.x;
+  z1 = z.y;
+}
+// the same, also handing out the block's unused fourth word (a 32-bit uniform for a yes/no draw)
+NB_D void normal_pair_spare(Stream& g, double& z0, double& z1, uint32_t& spare) {
+  uint32_t a, b, c;
+  g.next2(a, b);
+  g.next2(c, spare);
   double2 z = box_muller(a, b, c);
   z0 = z.x;
   z1 = z.y;
@@ -534,74 +567,47 @@ NB_D int nth_set_bit(unsigned m, int n) {
   return pos;
 }
 
-// One of the four terms of BTRS's exact acceptance test for candidate k of Binomial(n, p), r = p/q,
-// m = floor((n+1)p), X/Y = v alpha/(a/us^2 + b):
-//   accept  <=>  log(X/Y) <= h(m) + (n+1) log(nm1/nk1) + (k+1/2) log(r nk1/(k+1)) - fc(k) - fc(n-k)
-//   term 0: (m+1/2) log((m+1)/(r nm1)) + fc(m)       term 1: (n+1) log(nm1/nk1) + fc(n-m)
-//   term 2: (k+1/2) log(r nk1/(k+1)) - fc(k)         term 3: -log(X/Y) - fc(n-k)
-// accept <=> (t0 + t1) + (t2 + t3) >= 0.  Both the warp-cooperative and the per-lane evaluation
-// go through this function and this summation order, so a draw does not depend on which is used.
-NB_D double btrs_term(int t, double dn, double m, double r, double kk, double X, double Y) {
-  const double nm1 = dn - m + 1., nk1 = dn - kk + 1.;
-  double w, num, den, sarg, sg;
-  if (t == 0) {
-    w = m + 0.5; num = m + 1.; den = r * nm1; sarg = m; sg = 1.;
-  } else if (t == 1) {
-    w = dn + 1.; num = nm1; den = nk1; sarg = dn - m; sg = 1.;
-  } else if (t == 2) {
-    w = kk + 0.5; num = r * nk1; den = kk + 1.; sarg = kk; sg = -1.;
-  } else {
-    w = -1.; num = X; den = Y; sarg = dn - kk; sg = -1.;
-  }
-  return fma(w, log_pos(num / den), sg * stirling_tail(sarg));
+// ln(k!) for k < NB_LFACT_N, filled by nb200_create (host lgammal): the exact acceptance test of the binomial
+// sampler reads its four log-factorials instead of evaluating four logarithms and four Stirling tails
+#define NB_LFACT_N (1 << 17)
+__device__ double g_lfact[NB_LFACT_N];
+NB_D double log_factorial(double k) {
+  if (k < double(NB_LFACT_N)) return __ldg(&g_lfact[int(k)]);
+  // Stirling: ln k! = (k + 1/2) ln(k + 1) - (k + 1) + ln(2 pi)/2 + tail(k)
+  return fma(k + 0.5, log_pos(k + 1.), -(k + 1.)) + 0.91893853320467274178 + stirling_tail(k);
 }
 
-// binom_draw RandomGen.cpp:132-134 = std::binomial_distribution<int64_t>(n,p).  Exact
-// binomial sampler: sequential CDF inversion while n*min(p,1-p) < 10, Hormann's BTRS
-// transformed rejection (J. Stat. Comput. Simul. 46 (1993) 101) above.  Draws from its own
-// counter stream (seed; event, stream) so that it can live out of line.
+// binom_draw RandomGen.cpp:132-134 = std::binomial_distribution<int64_t>(n,p).  Exact binomial sampler:
+// sequential CDF inversion while n*min(p,1-p) < 10, Hormann's BTRS transformed rejection (J. Stat. Comput.
+// Simul. 46 (1993) 101) above.  Draws from its own counter stream (seed; event, stream) -- candidate k of a
+// BTRS draw is Philox block k of that stream -- so that it can live out of line.
 //
-// BTRS accepts 86 % of its candidates on a cheap test; the others need the exact log-pmf
-// bound: four logarithms and four Stirling tails.  Per lane that is ~330 instructions which a
-// warp executes for the ~5 lanes that need it in an iteration -- the single most expensive
-// piece of k_post.  When a full warp is inside the sampler (the chain kernels) the bound is
-// evaluated by the WARP instead: lane 4c+t takes term t of pending candidate c (eight
-// candidates per pass), the four terms are summed by two shuffles, and the owner of the
-// candidate reads the sum back.  One division, one logarithm and one Stirling tail per lane per
-// pass, at full lane occupancy.  (The paper's BTRD squeeze was measured too and is slower: some
-// lane of a warp nearly always needs the exact test anyway.)  A partial warp runs the plain loop.
-#ifndef NB_BINOM_COOP
-#define NB_BINOM_COOP 1
-#endif
+// BTRS accepts ~75 % of its candidates on a cheap test; the others need the exact log-pmf ratio
+//     ln f(k)/f(m) = ln m! + ln (n-m)! - ln k! - ln (n-k)! + (k - m) ln(p/q),   m = floor((n+1) p).
+// Round 1 evaluated it with four logarithms and four Stirling tails (~330 instructions, shared out over the
+// lanes of the warp: ~1200 warp-instructions per call, 35 % of k_post at 19 active lanes).  Here the
+// log-factorials come from a table (g_lfact: 1 MB, L2-resident; the m-terms and ln(p/q) once per draw), so a
+// test is two loads, one logarithm and a handful of FMAs, cheap enough to run per lane.  The table holds
+// ln k! to 1e-16 relative; the sum of four terms of up to 1e6 carries ~1e-9 of absolute error, i.e. the
+// acceptance probability of a candidate is exact to ~1e-9 relative (tests/test_gpu_samplers.py: chi^2
+// against the exact pmf, n up to 1.2e6).
 __device__ __noinline__ long long binomial(uint64_t seed, uint64_t event, uint32_t stream, long long n,
                                            double p) {
-#if NB_BINOM_COOP
-  const unsigned grp = __activemask();
-  const bool trivial = !(n > 0) || !(p > 0.) || p >= 1.;
-  if (grp != 0xffffffffu || __all_sync(grp, trivial)) {
-#else
-  {
-#endif
-    if (!(n > 0) || !(p > 0.)) return 0;
-    if (p >= 1.) return n;
-  }
-  Stream g;
-  g.init(seed, event, stream);
+  if (!(n > 0) || !(p > 0.)) return 0;
+  if (p >= 1.) return n;
   const bool flip = p > 0.5;
   const double pp = flip ? 1. - p : p;
   const double q = 1. - pp;
   const double dn = double(n);
+  const uint32_t k0 = uint32_t(seed), k1 = uint32_t(seed >> 32), e0 = uint32_t(event), e1 = uint32_t(event >> 32);
   long long k = 0;
-#if NB_BINOM_COOP
-  const bool inversion = !trivial && dn * pp < 10.;
-#else
-  const bool inversion = dn * pp < 10.;
-#endif
-  if (inversion) {
-    double r0 = exp(dn * log1p(-pp));
-    double s = pp / q;
-    for (;;) {
-      double u = g.uniform();
+  if (dn * pp < 10.) {
+    // q^n = exp(n ln q), q in [1/2, 1): the bit-built logarithm (absolute error ~1e-16, times n < 10/pp)
+    const double r0 = exp(dn * log_pos(q));
+    const double s = pp / q;
+    for (uint32_t att = 0;; ++att) {  // one uniform per attempt: words (x,y), then (z,w) of block att/2
+      const u128 w = philox_block(e0, e1, att >> 1, stream, k0, k1);
+      double u = (att & 1u) ? u53(w.z, w.w) : u53(w.x, w.y);
       double r = r0;
       long long x = 0;
       bool ok = true;
@@ -619,94 +625,33 @@ __device__ __noinline__ long long binomial(uint64_t seed, uint64_t event, uint32
         break;
       }
     }
-  }
-#if NB_BINOM_COOP
-  if (grp == 0xffffffffu) {
-    const bool need = !trivial && !inversion;
-    if (__any_sync(grp, need)) {
-      const int lane = int(threadIdx.x & 31u);
-      const unsigned lt = (1u << lane) - 1u;
-      // setup (harmless numbers in the lanes that do not draw)
-      const double npq = need ? dn * pp * q : 100.;
-      const double spq = sqrt(npq);
-      const double b = 1.15 + 2.53 * spq;
-      const double rb = 1. / b;
-      const double a = -0.0873 + 0.0248 * b + 0.01 * pp;
-      const double c = dn * pp + 0.5;
-      const double vr = 0.92 - 4.2 * rb;
-      const double r = pp / q;
-      const double alpha = (2.83 + 5.1 * rb) * spq;
-      const double m = floor((dn + 1.) * pp);
-      bool done = !need;
-      double kk = 0.;
-      const int role_c = lane >> 2, role_t = lane & 3;
-      for (;;) {
-        bool pend = false;
-        double X = 1., Y = 1.;
-        if (!done) {
-          const double u = g.uniform() - 0.5;
-          const double v = g.uniform();
-          const double us = 0.5 - fabs(u);
-          kk = floor((2. * a / us + b) * u + c);
-          if (us >= 0.07 && v <= vr)
-            done = true;
-          else if (!(kk < 0. || kk > dn)) {
-            pend = true;
-            const double us2 = us * us;
-            X = v * alpha * us2;  // v alpha / (a/us^2 + b) = X / Y
-            Y = a + b * us2;
-          }
-        }
-        unsigned pm = __ballot_sync(grp, pend);
-        while (pm) {  // warp-uniform
-          const int np = __popc(pm);
-          const int rank = __popc(pm & lt);  // of a pending lane among the pending
-          const bool have = role_c < np;
-          const int src = have ? nth_set_bit(pm, role_c) : lane;
-          const double c_dn = __shfl_sync(grp, dn, src), c_m = __shfl_sync(grp, m, src);
-          const double c_r = __shfl_sync(grp, r, src), c_kk = __shfl_sync(grp, kk, src);
-          const double c_X = __shfl_sync(grp, X, src), c_Y = __shfl_sync(grp, Y, src);
-          double val = have ? btrs_term(role_t, c_dn, c_m, c_r, c_kk, c_X, c_Y) : 0.;
-          val += __shfl_xor_sync(grp, val, 1);
-          val += __shfl_xor_sync(grp, val, 2);
-          const double mine = __shfl_sync(grp, val, (rank & 7) << 2);
-          if (pend && rank < 8) {
-            pend = false;
-            if (mine >= 0.) done = true;
-          }
-          pm = (np > 8) ? (pm & ~((2u << nth_set_bit(pm, 7)) - 1u)) : 0u;
-        }
-        if (__all_sync(grp, done)) break;
-      }
-      if (need) k = (long long)kk;
-    }
-    if (trivial) return (p >= 1. && n > 0) ? n : 0;
-    return flip ? n - k : k;
-  }
-#endif
-  if (!inversion) {
+  } else {
     const double spq = sqrt(dn * pp * q);
     const double b = 1.15 + 2.53 * spq;
     const double rb = 1. / b;
     const double a = -0.0873 + 0.0248 * b + 0.01 * pp;
     const double c = dn * pp + 0.5;
     const double vr = 0.92 - 4.2 * rb;
-    const double r = pp / q;
     const double alpha = (2.83 + 5.1 * rb) * spq;
     const double m = floor((dn + 1.) * pp);
-    double kk;
-    for (;;) {
-      const double u = g.uniform() - 0.5;
-      const double v = g.uniform();
+    // the per-draw terms of the exact test: loaded here so that their (L2) latency is hidden behind the first candidate
+    const double h = log_factorial(m) + log_factorial(dn - m);
+    const double logr = log_pos(pp / q);
+    double kk = 0.;
+    for (uint32_t att = 0;; ++att) {
+      const u128 w = philox_block(e0, e1, att, stream, k0, k1);
+      const double u = u53(w.x, w.y) - 0.5;
+      const double v = u53(w.z, w.w);
       const double us = 0.5 - fabs(u);
       kk = floor((2. * a / us + b) * u + c);
       if (us >= 0.07 && v <= vr) break;
       if (kk < 0. || kk > dn) continue;
+      const double lk = log_factorial(kk), lnk = log_factorial(dn - kk);  // issued before the logarithms below
       const double us2 = us * us;
-      const double X = v * alpha * us2, Y = a + b * us2;
-      const double t01 = btrs_term(0, dn, m, r, kk, X, Y) + btrs_term(1, dn, m, r, kk, X, Y);
-      const double t23 = btrs_term(2, dn, m, r, kk, X, Y) + btrs_term(3, dn, m, r, kk, X, Y);
-      if (t01 + t23 >= 0.) break;
+      // ln( v alpha / (a/us^2 + b) )
+      const double lhs = log_pos(v * alpha * us2) - log_pos(a + b * us2);
+      const double rhs = (h - lk) - lnk + (kk - m) * logr;
+      if (lhs <= rhs) break;
     }
     k = (long long)kk;
   }

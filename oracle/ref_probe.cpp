@@ -26,7 +26,7 @@ using namespace NEST;
 // compile-time "flags" of analysis.hh, defined in the execNEST.cpp object
 extern int verbosity, usePD, useS2, numBins;
 extern bool MCtruthE, MCtruthPos;
-extern double minS1, maxS1, minS2, maxS2, logMin, logMax, z_step;
+extern double minS1, maxS1, minS2, maxS2, logMin, logMax, z_step, E_step;
 extern double minTimeSeparation;  // execNEST.cpp:38
 extern double band[NUMBINS_MAX][7];
 extern NEST::S1CalculationMode s1CalculationMode;
@@ -170,6 +170,56 @@ void ref_spectrum(int kind, uint64_t seed, int n, double eMin, double eMax, doub
   }
 }
 
+// TestSpectra::WIMP_dRate (TestSpectra.cpp:251-390) draws its own Xe isotope (:278).  Call i runs on the generator
+// seeded with seed + i, after one SelectRanXeAtom under the same seed has told us which isotope that will be:
+// out[i] = the rate, A_out[i] = the isotope it was computed for.
+void ref_wimp_drate(uint64_t seed, int n, const double* ER, double mass, double day, double* out, double* A_out) {
+  RandomGen* r = RandomGen::rndm();
+  for (int i = 0; i < n; ++i) {
+    r->SetSeed(seed + uint64_t(i));
+    A_out[i] = double(r->SelectRanXeAtom());
+    r->SetSeed(seed + uint64_t(i));
+    out[i] = TestSpectra::WIMP_dRate(ER[i], mass, day);
+  }
+}
+
+// TestSpectra::WIMP_prep_spectrum (TestSpectra.cpp:392-454) on the generator seeded with `seed`: the isotopes of its
+// WIMP_dRate calls are then the first draws of that stream (ref_sampler kind 6 lists them).
+// base, exponent: 100 doubles each; out3 = integral, xMax, divisor.  1 where the reference throws.
+int ref_wimp_prep(uint64_t seed, double mass, double eStep, double day, double* base, double* exponent, double* out3) {
+  RandomGen::rndm()->SetSeed(seed);
+  try {
+    TestSpectra::WIMP_spectrum_prep p = TestSpectra::WIMP_prep_spectrum(mass, eStep, day);
+    for (int i = 0; i < 100; ++i) { base[i] = p.base[i]; exponent[i] = p.exponent[i]; }
+    out3[0] = p.integral; out3[1] = p.xMax; out3[2] = p.divisor;
+  } catch (std::exception& e) {
+    fprintf(stderr, "ref_wimp_prep: %s\n", e.what());
+    return 1;
+  }
+  return 0;
+}
+
+// n draws of TestSpectra::WIMP_spectrum (TestSpectra.cpp:456-499) from the table of ref_wimp_prep(seed_prep), the
+// generator re-seeded with seed_draw before the first draw
+int ref_wimp_spectrum(uint64_t seed_prep, uint64_t seed_draw, int n, double mass, double eStep, double day, double* out) {
+  RandomGen::rndm()->SetSeed(seed_prep);
+  try {
+    TestSpectra::WIMP_spectrum_prep p = TestSpectra::WIMP_prep_spectrum(mass, eStep, day);
+    RandomGen::rndm()->SetSeed(seed_draw);
+    for (int i = 0; i < n; ++i) out[i] = TestSpectra::WIMP_spectrum(p, mass, day);
+  } catch (std::exception& e) {
+    fprintf(stderr, "ref_wimp_spectrum: %s\n", e.what());
+    return 1;
+  }
+  return 0;
+}
+
+// the Poisson-fluctuated event count of the WIMP / 8B / pp / atmNu branches (execNEST.cpp:482-488, 490, 529, 536)
+void ref_poisson(uint64_t seed, int n, double mean, double* out) {
+  RandomGen::rndm()->SetSeed(seed);
+  for (int i = 0; i < n; ++i) out[i] = double(RandomGen::rndm()->poisson_draw(mean));
+}
+
 // GetS1 on fixed quanta/position; out [n][9]
 void ref_s1(uint64_t seed, int n, int Nph, const double* pos /*xyz*/, const double* spos,
             double vD, double vDmid, int species, double field, double energy, int mode,
@@ -232,6 +282,15 @@ int ref_chain(uint64_t seed, int n, int species, int src_kind, double eMin, doub
   RandomGen::rndm()->SetSeed(seed);
   auto NRYieldsParam = vec(nrpar, 12), ERYieldsParam = vec(erpar, 10), NRERWidthsParam = vec(widths, nw);
   INTERACTION_TYPE type_num = INTERACTION_TYPE(species);
+  TestSpectra::WIMP_spectrum_prep wimp_prep;
+  if (src_kind == NB200_SRC_WIMP) {  // execNEST.cpp:474-481: eMin is the WIMP mass; day 0; E_step of analysis.hh
+    try {
+      wimp_prep = TestSpectra::WIMP_prep_spectrum(eMin, E_step, 0.);
+    } catch (std::exception& e) {
+      fprintf(stderr, "ref_chain: %s\n", e.what());
+      return 1;
+    }
+  }
   double rho = n_.SetDensity(detector->get_T_Kelvin(), detector->get_p_bar());
   double Wq_eV = NESTcalc::WorkFunction(rho, detector->get_molarMass(), detector->get_OldW13eV()).Wq_eV;
   std::vector<double> g2_params = n_.CalculateG2(g2_verbosity);
@@ -249,6 +308,7 @@ int ref_chain(uint64_t seed, int n, int species, int src_kind, double eMin, doub
       double keV;
       if (src_kind == NB200_SRC_MONO || type_num == Kr83m) keV = eMin;
       else if (src_kind == NB200_SRC_CH3T) keV = TestSpectra::CH3T_spectrum(eMin, eMax);
+      else if (src_kind == NB200_SRC_WIMP) keV = TestSpectra::WIMP_spectrum(wimp_prep, eMin, 0.);
       else if (src_kind == NB200_SRC_B8) keV = TestSpectra::B8_spectrum(eMin, eMax);
       else if (src_kind == NB200_SRC_DD) keV = TestSpectra::DD_spectrum(eMin, eMax, 13., 0.12, 71.2, 20., -20.5);
       else if (src_kind == NB200_SRC_AMBE) keV = TestSpectra::PowLawFit_spectrum(eMin, eMax, -0.95351);
@@ -259,7 +319,7 @@ int ref_chain(uint64_t seed, int n, int species, int src_kind, double eMin, doub
       else if (src_kind == NB200_SRC_GAUSS) keV = RandomGen::rndm()->rand_zero_trunc_gauss(eMin, eMax);
       else if (src_kind == NB200_SRC_EXP) keV = RandomGen::rndm()->rand_exponential(-eMax * log(2.), 0., eMin);
       else keV = eMin + (eMax - eMin) * RandomGen::rndm()->rand_uniform();
-      if (type_num != B8 && type_num != Kr83m && type_num != ppSolar && type_num != atmNu && eMax > 0. &&
+      if (type_num != WIMP && type_num != B8 && type_num != Kr83m && type_num != ppSolar && type_num != atmNu && eMax > 0. &&
           eMin < eMax) {
         if (keV > eMax) keV = eMax;
         if (keV < eMin) keV = eMin;

@@ -11,7 +11,7 @@ RHO_LUX = 2.8886336386968878
 
 def gpu_chain(ctx, seed, n, species, src_kind, eMin, eMax, inField=180.0, fixed_pos=0, xyz=(0, 0, 0),
               er_model=-1, multFact=1.0, model_which=1, skewER=None, ana=None, det=None, band=None,
-              first_event=0, par=()):
+              first_event=0, par=(), wimp=None):
     det = det or capi.detector("LUX_Run03")
     rc = capi.prepare(det, inField, (ana.z_step if ana else 0.0))
     mo = capi.model(model_which)
@@ -28,6 +28,8 @@ def gpu_chain(ctx, seed, n, species, src_kind, eMin, eMax, inField=180.0, fixed_
         mo.massNum, mo.atomNum = det.molarMass, 0.0
     ana = ana or capi.analysis(0)
     src = capi.source(src_kind, species, eMin, eMax, inField, fixed_pos, xyz, par)
+    if wimp is not None:  # capi.WimpTable (TestSpectra::WIMP_spectrum_prep)
+        wimp.attach(src)
     cols = ctx.run(det, mo, ana, src, rc, seed, n, first_event=first_event, band=band)
     out = np.zeros((n, refprobe.SIGE + 1))
     C = refprobe.COL

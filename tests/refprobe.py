@@ -123,6 +123,39 @@ class Probe:
             nb = f(C.c_int(s1.size), _p(s1), _p(s2), _p(out))
         return out[:nb]
 
+    # ---- WIMP (reference probe only: TestSpectra.cpp:251-499) ----
+    def wimp_drate(self, seed, ER, mass, day=0.0):
+        """WIMP_dRate at ER[i] on the generator seeded seed + i -> (rate, isotope it drew)"""
+        ER = _arr(ER)
+        out, A = np.zeros(ER.size), np.zeros(ER.size)
+        self._f("wimp_drate")(C.c_uint64(seed), C.c_int(ER.size), _p(ER), C.c_double(mass), C.c_double(day), _p(out), _p(A))
+        return out, A.astype(int)
+
+    def wimp_prep(self, seed, mass, eStep=5.0, day=0.0):
+        """WIMP_prep_spectrum under `seed` -> (base[100], exponent[100], integral, xMax, divisor)"""
+        base, expo, o3 = np.zeros(100), np.zeros(100), np.zeros(3)
+        f = self._f("wimp_prep")
+        f.restype = C.c_int
+        rc = f(C.c_uint64(seed), C.c_double(mass), C.c_double(eStep), C.c_double(day), _p(base), _p(expo), _p(o3))
+        if rc:
+            raise RuntimeError("reference WIMP_prep_spectrum threw")
+        return base, expo, o3[0], o3[1], o3[2]
+
+    def wimp_spectrum(self, seed_prep, seed_draw, n, mass, eStep=5.0, day=0.0):
+        out = np.zeros(n)
+        f = self._f("wimp_spectrum")
+        f.restype = C.c_int
+        rc = f(C.c_uint64(seed_prep), C.c_uint64(seed_draw), C.c_int(n), C.c_double(mass), C.c_double(eStep),
+               C.c_double(day), _p(out))
+        if rc:
+            raise RuntimeError("reference WIMP_spectrum threw")
+        return out
+
+    def poisson(self, seed, n, mean):
+        out = np.zeros(n)
+        self._f("poisson")(C.c_uint64(seed), C.c_int(n), C.c_double(mean), _p(out))
+        return out
+
     def lar(self, seed, species, E, field, density):
         E = _arr(E)
         F = _arr(np.broadcast_to(field, E.shape))
