@@ -220,6 +220,11 @@ typedef struct nb200_soa_out {
  * y^2, y^3 (y = log10(S2/S1) or the 0 the reference pushes when y is outside
  * (logMin,logMax), :1551-1555); plus the numBins x logBins 2-D histogram of y.
  * All arrays are caller-owned (HOST), sized by nb200_band_hist_bytes(). */
+/* sumS1 (the band's X: S1, or S2 for useS2 == 2) is in units of 1 / nb200_band_scale_x(ana): 2^-20 (NB200_FX_S1)
+ * while the analysis keeps X below 1024, else the largest power of two with X * scale < 2^30.  A bin's 64-bit
+ * sums hold at least 2^63 / (6.4 * 2^30) = 1.3e9 accepted events for |log10| < 6.4 (2^33 for sumS1);
+ * nb200_band_finalize refuses (NB200_EINVAL) an accumulator in which a bin's count exceeds what its sums can
+ * carry.  Split longer runs over several accumulators. */
 #define NB200_FX_S1 1048576.0        /* 2^20  */
 #define NB200_FX_Y 1073741824.0      /* 2^30  */
 #define NB200_FX_Y2 67108864.0       /* 2^26  */
@@ -323,6 +328,19 @@ int nb200_run(nb200_ctx* ctx, const nb200_detector* det, const nb200_model* mode
               const nb200_run_consts* rc, uint64_t seed, uint64_t first_event,
               uint64_t n_events, nb200_soa_out* soa, nb200_band_hist* hist);
 
+/* Batched parameter sweep (BASELINE config 4): n_points grid points -- one detector, model, source and set of
+ * run constants each (arrays of n_points), one shared analysis -- every point simulating event ids
+ * [first_event, first_event + n_events) under `seed`, one band accumulator per point (bands[n_points],
+ * ACCUMULATED into).  Replaces a shell loop of execNEST processes over a parameter grid (the reference's
+ * loopNEST mode, src/execNEST.cpp:103-159 driven by examples/loopNEST.in:10-54): the grid-point index is part
+ * of the launch, the per-point parameter blocks live in device memory, and blocks of every point share the
+ * GPU, so points of 1e4..1e6 events run at the rate of one large run instead of being launch- and tail-bound.
+ * A point's band is bit for bit the band of nb200_run with that point's parameters and the same seed / event
+ * range.  List sources and vec_mode are not accepted here. */
+int nb200_run_sweep(nb200_ctx* ctx, size_t n_points, const nb200_detector* dets, const nb200_model* models,
+                    const nb200_analysis* ana, const nb200_source* srcs, const nb200_run_consts* rcs, uint64_t seed,
+                    uint64_t first_event, uint64_t n_events, nb200_band_hist* bands);
+
 /* Device-resident variant used for throughput measurement: the band accumulator
  * stays in device memory owned by ctx between calls; fetch adds it into hist. */
 int nb200_run_async(nb200_ctx* ctx, const nb200_detector* det, const nb200_model* model,
@@ -343,6 +361,7 @@ int nb200_allreduce_hist(nb200_ctx* ctx, void* nccl_comm);
 /* GetBand's final statistics (execNEST.cpp:1582-1618) from the accumulator:
  * band[j][0..6] = centre, mean S1, mean y, sigma (N-1), sigma/sqrt(N), eff, skew */
 size_t nb200_band_hist_bytes(const nb200_analysis* ana);
+double nb200_band_scale_x(const nb200_analysis* ana);
 int nb200_band_finalize(const nb200_analysis* ana, const nb200_band_hist* hist,
                         double* band /* [numBins][7] */);
 

@@ -101,9 +101,9 @@ class BandHist(C.Structure):
 EXPORTS = [
     "nb200_abi_version", "nb200_sizeof", "nb200_create", "nb200_destroy", "nb200_last_error", "nb200_set_stream",
     "nb200_synchronize", "nb200_detector_builtin", "nb200_model_default", "nb200_analysis_default",
-    "nb200_prepare", "nb200_wimp_prep", "nb200_wimp_prep_iso", "nb200_wimp_drate", "nb200_poisson", "nb200_yields", "nb200_quanta", "nb200_s2", "nb200_s1", "nb200_run", "nb200_run_async",
+    "nb200_prepare", "nb200_wimp_prep", "nb200_wimp_prep_iso", "nb200_wimp_drate", "nb200_poisson", "nb200_yields", "nb200_quanta", "nb200_s2", "nb200_s1", "nb200_run", "nb200_run_sweep", "nb200_run_async",
     "nb200_band_reset", "nb200_band_attach", "nb200_fp64_peak", "nb200_timing_enable", "nb200_timing_read", "nb200_se_stats", "nb200_band_fetch", "nb200_band_device_buffer", "nb200_allreduce_hist",
-    "nb200_band_hist_bytes", "nb200_band_finalize", "nb200_band_chi2", "nb200_band_leakage", "nb200_band_fit_gauss", "nb200_band_leakage_gauss", "nb200_hist_fit", "nb200_hist_fit_cov", "nb200_band_leakage_skew_cov", "nb200_graph_fit", "nb200_band_leakage_skew", "nb200_lar", "nb200_launch_count",
+    "nb200_band_hist_bytes", "nb200_band_scale_x", "nb200_band_finalize", "nb200_band_chi2", "nb200_band_leakage", "nb200_band_fit_gauss", "nb200_band_leakage_gauss", "nb200_hist_fit", "nb200_hist_fit_cov", "nb200_band_leakage_skew_cov", "nb200_graph_fit", "nb200_band_leakage_skew", "nb200_lar", "nb200_launch_count",
     "nb200_debug_hitmath", "nb200_debug_binomial", "nb200_debug_normal", "nb200_debug_binomial_fixed",
     "nb200_debug_zig_tables", "nb200_debug_alias_tables", "nb200_debug_maps", "nb200_drift_table", "nb200_density", "nb200_drift_velocity_liquid"]
 
@@ -162,6 +162,9 @@ def lib():
                 C.POINTER(RunConsts), C.c_uint64, C.c_uint64, C.c_uint64]
     L.nb200_run.argtypes = run_args + [C.POINTER(SoaOut), C.POINTER(BandHist)]
     L.nb200_run_async.argtypes = run_args + [C.POINTER(SoaOut)]
+    L.nb200_run_sweep.argtypes = [vp, C.c_size_t, C.POINTER(Detector), C.POINTER(Model), C.POINTER(Analysis),
+                                  C.POINTER(Source), C.POINTER(RunConsts), C.c_uint64, C.c_uint64, C.c_uint64,
+                                  C.POINTER(BandHist)]
     L.nb200_band_reset.argtypes = [vp, C.POINTER(Analysis)]
     L.nb200_band_fetch.argtypes = [vp, C.POINTER(BandHist)]
     L.nb200_band_attach.argtypes = [vp, C.POINTER(Analysis), vp]
@@ -173,6 +176,8 @@ def lib():
     L.nb200_allreduce_hist.argtypes = [vp, vp]
     L.nb200_band_hist_bytes.argtypes = [C.POINTER(Analysis)]
     L.nb200_band_hist_bytes.restype = C.c_size_t
+    L.nb200_band_scale_x.argtypes = [C.POINTER(Analysis)]
+    L.nb200_band_scale_x.restype = C.c_double
     L.nb200_band_finalize.argtypes = [C.POINTER(Analysis), C.POINTER(BandHist), c_dp]
     L.nb200_band_chi2.argtypes = [C.c_int, C.c_int, c_dp, c_dp, C.c_int, c_dp]
     L.nb200_band_leakage.argtypes = [C.POINTER(Analysis), C.POINTER(BandHist), c_dp, c_dp, c_dp, c_dp, c_dp]
@@ -529,6 +534,19 @@ class Context:
                                     seed, first_event, n, C.byref(soa) if names else None,
                                     C.byref(band.c) if band is not None else None))
         return cols
+
+    def run_sweep(self, dets, models, ana, srcs, rcs, seed, n, first_event=0):
+        """nb200_run_sweep over len(dets) grid points -> list of Band (one per point)"""
+        k = len(dets)
+        if not (len(models) == len(srcs) == len(rcs) == k):
+            raise ValueError("one detector, model, source and run-constants block per grid point")
+        D, M, S, R = (Detector * k)(*dets), (Model * k)(*models), (Source * k)(*srcs), (RunConsts * k)(*rcs)
+        bands = [Band(ana) for _ in range(k)]
+        B = (BandHist * k)(*[b.c for b in bands])
+        self._check(lib().nb200_run_sweep(self.h, k, D, M, C.byref(ana), S, R, seed, first_event, n, B))
+        for b, c in zip(bands, B):
+            b.c.n_events = c.n_events
+        return bands
 
     def band_reset(self, ana):
         self._check(lib().nb200_band_reset(self.h, C.byref(ana)))

@@ -36,11 +36,19 @@ struct nb200_ctx {
   size_t band_tmp_words = 0;
   // cached device copies of map LUTs / WIMP tables / drift table
   struct Blob {
-    const void* host;
+    uint64_t hash;
     size_t bytes;
     void* dev;
   };
   std::vector<Blob> blobs;
+  // tables already resolved during the current API call (host pointer -> device copy): a sweep's points share
+  // their maps, which are then hashed once per call instead of once per point
+  struct Memo {
+    const void* host;
+    size_t bytes;
+    void* dev;
+  };
+  std::vector<Memo> call_memo;
   // double-buffered device staging + copy stream for nb200_run's host outputs (kept across calls)
   void* d_stage[2] = {nullptr, nullptr};
   size_t stage_bytes = 0;
@@ -59,8 +67,18 @@ struct nb200_ctx {
   nb200_detector vtable_det;
   double vtable_zstep = 0.;
   double* d_vtable = nullptr;
-  void* d_dpe = nullptr;  // alias tables of Binomial(2^b, P_dphe)
-  double dpe_p = -1.;
+  // alias tables of Binomial(2^b, P_dphe), one per distinct P_dphe seen (a sweep may mix detectors)
+  struct Dpe {
+    double p;
+    void* dev;
+  };
+  std::vector<Dpe> dpe;
+  // nb200_run_sweep: per-point RunParams and band slabs
+  void* d_sweep_params = nullptr;
+  size_t sweep_params_bytes = 0;
+  unsigned long long* d_sweep_bands = nullptr;
+  size_t sweep_band_words = 0;
+  int occ_pre_sweep = 0, occ_hits_sweep = 0;
 };
 
 namespace {
@@ -98,22 +116,51 @@ int fail(nb200_ctx* c, int code, const std::string& msg) {
       return fail(c, NB200_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));     \
   } while (0)
 
+// fixed-point scale of the band's sum of X (S1, or S2 for useS2 == 2): 2^-20 units while X stays below 1024,
+// coarser for larger X so that X * scale < 2^30 and a bin holds 2^33 events before its 64-bit sum could wrap
+double band_scale_x(const nb200_analysis* a) {
+  const double mx = a->useS2 == 2 ? fabs(a->maxS2) : fabs(a->maxS1);
+  if (!(mx > 1024.)) return NB200_FX_S1;
+  const int e = int(ceil(log2(mx)));
+  return ldexp(1., std::max(0, 30 - e));
+}
+
 size_t band_word_count(const nb200_analysis* a) {
   return size_t(a->numBins) * BAND_WORDS + size_t(a->numBins) * size_t(a->logBins > 0 ? a->logBins : 0);
 }
 
-// upload (or reuse) a host table; keyed on pointer+size+content hash
+// FNV-1a over the table's bytes
+uint64_t blob_hash(const void* p, size_t n) {
+  const unsigned char* b = static_cast<const unsigned char*>(p);
+  uint64_t h = 1469598103934665603ull;
+  for (size_t i = 0; i < n; ++i) h = (h ^ b[i]) * 1099511628211ull;
+  return h;
+}
+// upload (or reuse) a host table; keyed on size + content hash: a table is copied once per context, never
+// rewritten while kernels of an earlier call may still read it, whatever host address it comes from
 int upload_blob(nb200_ctx* c, const void* host, size_t bytes, void** dev) {
-  for (auto& b : c->blobs)
-    if (b.host == host && b.bytes == bytes) {
-      NB_CUDA(c, cudaMemcpyAsync(b.dev, host, bytes, cudaMemcpyHostToDevice, c->stream));
-      *dev = b.dev;
+  for (auto& m : c->call_memo)
+    if (m.host == host && m.bytes == bytes) {
+      *dev = m.dev;
       return 0;
     }
+  const uint64_t h = blob_hash(host, bytes);
+  for (auto& b : c->blobs)
+    if (b.bytes == bytes && b.hash == h) {
+      *dev = b.dev;
+      c->call_memo.push_back({host, bytes, b.dev});
+      return 0;
+    }
+  if (c->blobs.size() >= 256) {  // bounded: drop everything not in use by queued work
+    NB_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (auto& b : c->blobs) cudaFree(b.dev);
+    c->blobs.clear();
+  }
   void* d = nullptr;
   NB_CUDA(c, cudaMalloc(&d, bytes));
-  NB_CUDA(c, cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, c->stream));
-  c->blobs.push_back({host, bytes, d});
+  NB_CUDA(c, cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice));  // synchronous: the host table may be a temporary
+  c->blobs.push_back({h, bytes, d});
+  c->call_memo.push_back({host, bytes, d});
   *dev = d;
   return 0;
 }
@@ -163,7 +210,8 @@ int validate(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo, con
 // Everything the kernel needs beyond the caller's PODs
 int build_params(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo, const nb200_analysis* ana,
                  const nb200_source* src, const nb200_run_consts* rc, uint64_t seed, uint64_t first,
-                 uint64_t n, RunParams* P) {
+                 uint64_t n, RunParams* P, bool keep_memo = false) {
+  if (!keep_memo) c->call_memo.clear();
   int r = validate(c, det, mo, ana, src);
   if (r) return r;
   if (!rc) return fail(c, NB200_EINVAL, "null run constants (call nb200_prepare)");
@@ -245,6 +293,7 @@ int build_params(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo,
     P->recon_mult = 0.5 * (1. + erf((det->sPEthr - 1.) / (det->sPEres * sqrt(2.)))) /
                     (det->sPEres * sqrt(2. * M_PI));
   }
+  P->band_fx_x = band_scale_x(ana);
   if (ana->useS2 == 2) {
     P->band_width = (ana->maxS2 - ana->minS2) / double(ana->numBins);
     P->band_border = ana->minS2;
@@ -279,15 +328,17 @@ int build_params(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo,
   }
   P->dpe_alias = nullptr;
   if (det->P_dphe > 0. && det->P_dphe < 1.) {  // alias tables of Binomial(2^b, P_dphe) for k_pre's double-phe count
-    if (!c->d_dpe || c->dpe_p != det->P_dphe) {
+    void* dtab = nullptr;
+    for (auto& e : c->dpe)
+      if (e.p == det->P_dphe) dtab = e.dev;
+    if (!dtab) {
       std::vector<AliasEntry> tab(NB_ALIAS_ENTRIES);
       build_binomial_alias(det->P_dphe, tab.data());
-      if (!c->d_dpe) NB_CUDA(c, cudaMalloc(&c->d_dpe, sizeof(AliasEntry) * tab.size()));
-      NB_CUDA(c, cudaMemcpyAsync(c->d_dpe, tab.data(), sizeof(AliasEntry) * tab.size(), cudaMemcpyHostToDevice, c->stream));
-      NB_CUDA(c, cudaStreamSynchronize(c->stream));  // tab goes out of scope
-      c->dpe_p = det->P_dphe;
+      NB_CUDA(c, cudaMalloc(&dtab, sizeof(AliasEntry) * tab.size()));
+      NB_CUDA(c, cudaMemcpy(dtab, tab.data(), sizeof(AliasEntry) * tab.size(), cudaMemcpyHostToDevice));
+      c->dpe.push_back({det->P_dphe, dtab});
     }
-    P->dpe_alias = static_cast<const uint2*>(c->d_dpe);
+    P->dpe_alias = static_cast<const uint2*>(dtab);
   }
   if (src->kind == NB200_SRC_WIMP) {
     void* d = nullptr;
@@ -527,7 +578,9 @@ void nb200_destroy(nb200_ctx* c) {
   if (c->d_band && !c->band_external) cudaFree(c->d_band);
   if (c->d_band_tmp) cudaFree(c->d_band_tmp);
   if (c->d_vtable) cudaFree(c->d_vtable);
-  if (c->d_dpe) cudaFree(c->d_dpe);
+  for (auto& e : c->dpe) cudaFree(e.dev);
+  if (c->d_sweep_params) cudaFree(c->d_sweep_params);
+  if (c->d_sweep_bands) cudaFree(c->d_sweep_bands);
   if (c->d_work) cudaFree(c->d_work);
   for (int b = 0; b < 2; ++b) {
     if (c->d_stage[b]) cudaFree(c->d_stage[b]);
@@ -1064,6 +1117,7 @@ int nb200_s1(nb200_ctx* c, const nb200_detector* det, const nb200_run_consts* rc
 // ---- the chain ---------------------------------------------------------------------------
 
 size_t nb200_band_hist_bytes(const nb200_analysis* a) { return a ? band_word_count(a) * 8 : 0; }
+double nb200_band_scale_x(const nb200_analysis* a) { return a ? band_scale_x(a) : 0.; }
 
 int nb200_band_reset(nb200_ctx* c, const nb200_analysis* ana) {
   if (!c || !ana) return NB200_EINVAL;
@@ -1259,7 +1313,9 @@ int nb200_run(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo, co
   }
 
   tr.mark("staging");
-  int rcode = 0;
+  RunParams P0;
+  int rcode = build_params(c, det, mo, ana, src, rc, seed, first_event, n_events, &P0);
+  if (rcode) return rcode;
   uint64_t ichunk = 0;
   for (uint64_t done = 0; done < n_events && !rcode; done += chunk_max, ++ichunk) {
     const uint64_t m = std::min<uint64_t>(chunk_max, n_events - done);
@@ -1286,9 +1342,13 @@ int nb200_run(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo, co
         }
       }
     }
-    RunParams P;
-    rcode = build_params(c, det, mo, ana, &s, rc, seed, first_event + done, m, &P);
-    if (rcode) break;
+    RunParams P = P0;  // built once for the call; per chunk only the event range and the list pointers move
+    P.first_event = first_event + done;
+    P.n_events = m;
+    P.src.E = s.E;
+    P.src.x = s.x;
+    P.src.y = s.y;
+    P.src.z = s.z;
     if (soa) {
       P.write_soa = 1;
       nb200_soa_out tmp = *soa;
@@ -1352,6 +1412,115 @@ int nb200_run(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo, co
   return rcode;
 }
 
+// Batched parameter sweep: see SweepArgs in nb_kernels.cuh
+int nb200_run_sweep(nb200_ctx* c, size_t n_points, const nb200_detector* dets, const nb200_model* models,
+                    const nb200_analysis* ana, const nb200_source* srcs, const nb200_run_consts* rcs, uint64_t seed,
+                    uint64_t first_event, uint64_t n_events, nb200_band_hist* bands) {
+  if (!c) return NB200_EINVAL;
+  if (!dets || !models || !ana || !srcs || !rcs || !bands) return fail(c, NB200_EINVAL, "null argument");
+  if (n_points == 0 || n_events == 0) return 0;
+  if (n_points > (1u << 24)) return fail(c, NB200_EINVAL, "too many grid points");
+  NB_CUDA(c, cudaSetDevice(c->device));
+  Trace tr("nb200_run_sweep");
+  std::vector<RunParams> Ps(n_points);
+  for (size_t p = 0; p < n_points; ++p) {
+    if (srcs[p].kind == NB200_SRC_LIST || srcs[p].vec_mode)
+      return fail(c, NB200_EINVAL, "nb200_run_sweep: list sources / runNESTvec semantics are per-point calls (nb200_run)");
+    if (bands[p].numBins != ana->numBins || bands[p].logBins != ana->logBins)
+      return fail(c, NB200_EINVAL, "band geometry mismatch");
+    int r = build_params(c, &dets[p], &models[p], ana, &srcs[p], &rcs[p], seed, first_event, n_events, &Ps[p], p != 0);
+    if (r) return r;
+    Ps[p].do_band = 1;
+  }
+  tr.mark("per-point parameters");
+  const size_t words = band_word_count(ana);
+  size_t smem = size_t(ana->numBins) * BAND_WORDS * 8 + size_t(ana->numBins) * size_t(ana->logBins) * 4;
+  int band_in_smem = 1;
+  if (smem > 150 * 1024) {
+    band_in_smem = 0;
+    smem = 0;
+  }
+  if (!c->occ_pre_sweep) {
+    NB_CUDA(c, cudaFuncSetAttribute(k_post_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024));
+    NB_CUDA(c, cudaFuncSetAttribute(k_hits_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kHitDynSmem)));
+    NB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_pre_sweep, k_pre_sweep, kPreBlock, 0));
+    NB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_hits_sweep, k_hits_sweep, kHitBlock, kHitDynSmem));
+    if (c->occ_pre_sweep < 1) c->occ_pre_sweep = 1;
+    if (c->occ_hits_sweep < 1) c->occ_hits_sweep = 1;
+  }
+  int occ_post = 1;
+  NB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_post, k_post_sweep, kPostBlock, smem));
+  if (occ_post < 1) occ_post = 1;
+  const size_t pbytes = sizeof(RunParams) * n_points;
+  if (pbytes > c->sweep_params_bytes) {
+    if (c->d_sweep_params) cudaFree(c->d_sweep_params);
+    c->d_sweep_params = nullptr;
+    c->sweep_params_bytes = 0;
+    NB_CUDA(c, cudaMalloc(&c->d_sweep_params, pbytes));
+    c->sweep_params_bytes = pbytes;
+  }
+  if (words * n_points > c->sweep_band_words) {
+    if (c->d_sweep_bands) cudaFree(c->d_sweep_bands);
+    c->d_sweep_bands = nullptr;
+    c->sweep_band_words = 0;
+    NB_CUDA(c, cudaMalloc(&c->d_sweep_bands, words * n_points * 8));
+    c->sweep_band_words = words * n_points;
+  }
+  NB_CUDA(c, cudaMemcpyAsync(c->d_sweep_params, Ps.data(), pbytes, cudaMemcpyHostToDevice, c->stream));
+  NB_CUDA(c, cudaMemsetAsync(c->d_sweep_bands, 0, words * n_points * 8, c->stream));
+  SweepArgs A;
+  std::memset(&A, 0, sizeof A);
+  A.params = static_cast<const RunParams*>(c->d_sweep_params);
+  A.bands = c->d_sweep_bands;
+  A.band_words = words;
+  A.n_per_point = n_events;
+  A.n_pad = (n_events + 1023) / 1024 * 1024;
+  A.first_event = first_event;
+  const uint64_t total = uint64_t(n_points) * A.n_pad;
+  int r = ensure_workspace(c, total, &A.work);
+  if (r) return r;
+  const uint64_t cap = c->work_cap / 1024 * 1024;
+  const uint64_t sm = uint64_t(c->sm_count);
+  for (uint64_t off = 0; off < total; off += cap) {
+    const uint64_t m = std::min<uint64_t>(cap, total - off);
+    A.slot0 = off;
+    A.n_slots = m;
+    unsigned g_pre = unsigned(std::min<uint64_t>((m + kPreBlock - 1) / kPreBlock, sm * c->occ_pre_sweep * 8));
+    unsigned g_hits = unsigned(std::min<uint64_t>((m + kHitGroup - 1) / kHitGroup, sm * c->occ_hits_sweep));
+    unsigned g_post = unsigned(std::min<uint64_t>((m + kPostBlock - 1) / kPostBlock, sm * occ_post));
+    k_pre_sweep<<<g_pre, kPreBlock, 0, c->stream>>>(A, c->d_err);
+    cudaMemsetAsync(c->d_err + 1, 0, sizeof(int), c->stream);
+    k_hits_sweep<<<g_hits, kHitBlock, kHitDynSmem, c->stream>>>(A, reinterpret_cast<unsigned int*>(c->d_err + 1));
+    k_post_sweep<<<g_post, kPostBlock, smem, c->stream>>>(A, band_in_smem, c->d_err);
+    NB_CUDA(c, cudaGetLastError());
+    c->launches += 3;
+  }
+  tr.mark("launched");
+  std::vector<unsigned long long> w(words * n_points);
+  NB_CUDA(c, cudaMemcpyAsync(w.data(), c->d_sweep_bands, w.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+  r = check_device_error(c);  // synchronises (Ps must also outlive the copy above)
+  if (r) return r;
+  tr.mark("kernels done");
+  for (size_t p = 0; p < n_points; ++p) {
+    nb200_band_hist* h = &bands[p];
+    const unsigned long long* wp = &w[p * words];
+    for (int j = 0; j < h->numBins; ++j) {
+      const unsigned long long* b = wp + size_t(j) * BAND_WORDS;
+      if (h->accepted) h->accepted[j] += b[0];
+      if (h->rejected) h->rejected[j] += b[1];
+      if (h->sumS1) h->sumS1[j] += (int64_t)b[2];
+      if (h->sumY) h->sumY[j] += (int64_t)b[3];
+      if (h->sumY2) h->sumY2[j] += (int64_t)b[4];
+      if (h->sumY3) h->sumY3[j] += (int64_t)b[5];
+    }
+    if (h->hist2d)
+      for (size_t i = 0; i < size_t(h->numBins) * size_t(h->logBins); ++i)
+        h->hist2d[i] += wp[size_t(h->numBins) * BAND_WORDS + i];
+    h->n_events += n_events;
+  }
+  return 0;
+}
+
 // GetBand's closing statistics (execNEST.cpp:1582-1618) from the integer accumulator
 int nb200_band_finalize(const nb200_analysis* ana, const nb200_band_hist* h, double* band) {
   if (!ana || !h || !band) return NB200_EINVAL;
@@ -1364,11 +1533,24 @@ int nb200_band_finalize(const nb200_analysis* ana, const nb200_band_hist* h, dou
     binWidth = (ana->maxS1 - ana->minS1) / double(ana->numBins);
     border = ana->minS1;
   }
+  // The sums are 64-bit integers: refuse a bin that holds so many events that one of them could have wrapped
+  // (conservative bound from the analysis ranges; ~1.4e9 accepted events per bin for the shipped analyses)
+  const double fx_x = band_scale_x(ana);
+  {
+    const double mx = ana->useS2 == 2 ? fabs(ana->maxS2) : fabs(ana->maxS1);
+    const double ly = std::max(fabs(ana->logMin), fabs(ana->logMax));
+    const double per_event = std::max(std::max(mx * fx_x, ly * NB200_FX_Y), std::max(ly * ly * NB200_FX_Y2, ly * ly * ly * NB200_FX_Y3));
+    for (int j = 0; j < ana->numBins; ++j)
+      if (double(h->accepted[j]) * per_event >= 9.2e18)
+        return fail(nullptr, NB200_EINVAL,
+                    "band accumulator: a bin holds more events than its 64-bit fixed-point sums can carry; "
+                    "accumulate fewer events per nb200_band_hist (or more bins) and merge the statistics");
+  }
   for (int j = 0; j < ana->numBins; ++j) {
     double* b = band + 7 * size_t(j);
     const double N = double(h->accepted[j]);
     const double Sy = double(h->sumY[j]) / NB200_FX_Y, Sy2 = double(h->sumY2[j]) / NB200_FX_Y2,
-                 Sy3 = double(h->sumY3[j]) / NB200_FX_Y3, Sx = double(h->sumS1[j]) / NB200_FX_S1;
+                 Sy3 = double(h->sumY3[j]) / NB200_FX_Y3, Sx = double(h->sumS1[j]) / fx_x;
     b[0] = border + binWidth / 2. + double(j) * binWidth;
     b[1] = Sx / N;
     const double mu = Sy / N;

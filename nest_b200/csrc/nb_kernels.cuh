@@ -666,13 +666,17 @@ NB_D void hits_body(const RunParams* P0, const SweepArgs* Ap, RunParams* sP, uns
         __syncwarp();
         if (qcount >= 32) {
           qcount -= 32;
+#ifndef NB_HITS_DROP_SLOW  // timing experiment only: the fast path alone (queued slots are lost)
           hits_finish_slow(P, s_nh, s_nd, s_area, s_spike, ev0, &s_q[wid][qcount], 32, lane, s_zk, s_zw);
+#endif
         }
       }
       ++j;
       ++h;
     }
+#ifndef NB_HITS_DROP_SLOW
     if (qcount > 0) hits_finish_slow(P, s_nh, s_nd, s_area, s_spike, ev0, &s_q[wid][0], qcount, lane, s_zk, s_zw);
+#endif
     if (h1 > h0) {
       smem_add64(&s_area[e], a_fx - (unsigned long long)a_spike * NB_AREA_MAGIC_BITS);
       atomicAdd(&s_spike[e], a_spike);
@@ -761,7 +765,7 @@ NB_D void post_body(const RunParams& P, const Work& W, uint64_t idx, uint64_t gi
         unsigned long long* b = B + size_t(bin) * BAND_WORDS;
         if (acc_ok) {
           atomicAdd(&b[0], 1ull);
-          atomicAdd(&b[2], (unsigned long long)(long long)llrint(xv * NB200_FX_S1));
+          atomicAdd(&b[2], (unsigned long long)(long long)llrint(xv * P.band_fx_x));
           atomicAdd(&b[3], (unsigned long long)(long long)llrint(yv * NB200_FX_Y));
           atomicAdd(&b[4], (unsigned long long)(long long)llrint(yv * yv * NB200_FX_Y2));
           atomicAdd(&b[5], (unsigned long long)(long long)llrint(yv * yv * yv * NB200_FX_Y3));

@@ -74,6 +74,7 @@ struct RunParams {
   double z_lo, z_hi;
   int32_t z_direct, _pad_z;
   double band_width, band_border;  // GetBand bin geometry           execNEST.cpp:1521-1527
+  double band_fx_x;                // fixed-point scale of the band's sum of X (nb200_band_scale_x)
   // GetDriftVelocity_Liquid rows bracketing T_Kelvin (NEST.cpp:2429-2502); dv_mode 0 blend,
   // 1 = T on the lower node, 2 = T on the upper node
   double dv_row[2][7];

@@ -105,7 +105,7 @@ bool band_of_file(const char* name, BandOfFile& B) {
         B.inputs[j].push_back(S1[i]);
         B.outputs[j].push_back(y);
         ++acc[j];
-        sS1[j] += llrint(S1[i] * NB200_FX_S1);
+        sS1[j] += llrint(S1[i] * nb200_band_scale_x(&ana));
         sY[j] += llrint(y * NB200_FX_Y);
         sY2[j] += llrint(y * y * NB200_FX_Y2);
         sY3[j] += llrint(y * y * y * NB200_FX_Y3);

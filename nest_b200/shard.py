@@ -52,7 +52,7 @@ def band_words_from_signals(ana, coin_level, signal1, signal2):
         b = words[6 * j:6 * j + 6]
         b[0] = good.sum()
         b[1] = (m & ~good).sum()
-        b[2] = np.rint(X[good] * capi.FX_S1).astype(np.int64).sum()
+        b[2] = np.rint(X[good] * capi.lib().nb200_band_scale_x(ana)).astype(np.int64).sum()
         b[3] = np.rint(y * capi.FX_Y).astype(np.int64).sum()
         b[4] = np.rint(y * y * capi.FX_Y2).astype(np.int64).sum()
         b[5] = np.rint(y * y * y * capi.FX_Y3).astype(np.int64).sum()

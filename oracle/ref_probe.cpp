@@ -46,6 +46,15 @@ extern "C" {
 
 int ref_set_verbosity(int v) { int o = verbosity; verbosity = v; return o; }
 
+// detector parameters of a sweep grid point on the probe's LUX_Run03 instance (VDetector.hh:73-103 setters, as the
+// reference's loopNEST mode uses them, execNEST.cpp:134-144); a negative value restores the header's default
+void ref_lux_set(double g1, double g1_gas, double E_gas) {
+  DetectorExample_LUX_RUN03 def;
+  lux()->set_g1(g1 >= 0. ? g1 : def.get_g1());
+  lux()->set_g1_gas(g1_gas >= 0. ? g1_gas : def.get_g1_gas());
+  lux()->set_E_gas(E_gas >= 0. ? E_gas : def.get_E_gas());
+}
+
 void ref_analysis(double* out) {
   out[0] = usePD; out[1] = useS2; out[2] = numBins; out[3] = minS1; out[4] = maxS1;
   out[5] = minS2; out[6] = maxS2; out[7] = logMin; out[8] = logMax;

@@ -123,6 +123,10 @@ class Probe:
             nb = f(C.c_int(s1.size), _p(s1), _p(s2), _p(out))
         return out[:nb]
 
+    def lux_set(self, g1=-1.0, g1_gas=-1.0, E_gas=-1.0):
+        """reference probe only: g1 / g1_gas / E_gas of its LUX_Run03 instance (negative = header default)"""
+        self.L.ref_lux_set(C.c_double(g1), C.c_double(g1_gas), C.c_double(E_gas))
+
     # ---- WIMP (reference probe only: TestSpectra.cpp:251-499) ----
     def wimp_drate(self, seed, ER, mass, day=0.0):
         """WIMP_dRate at ER[i] on the generator seeded seed + i -> (rate, isotope it drew)"""
