@@ -69,6 +69,28 @@ def ncu_traffic():
     return {"traffic": tot, "traffic_unit": "bytes per launch (dram read + write)",
             "traffic_source": os.path.relpath(best[-1], ROOT)}
 
+def ncu_utilisation():
+    """issue-slot utilisation, active lanes and FP64 pipe busy of k_hits from the committed `ncu --set full` capture"""
+    import glob
+    import re
+    best = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_k_hits_ncu_full.txt")))
+    if not best:
+        return {}
+    want = {"smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_active_pct",
+            "smsp__thread_inst_executed_per_inst_executed.ratio": "active_lanes_of_32",
+            "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active": "fp64_pipe_busy_pct"}
+    got = {}
+    for ln in open(best[-1]):
+        f = ln.split()
+        if f and f[0] in want:
+            try:
+                got[want[f[0]]] = float(f[-1])
+            except ValueError:
+                pass
+    got["utilisation_source"] = os.path.relpath(best[-1], ROOT)
+    return got
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -78,6 +100,10 @@ def parse():
     ap.add_argument("--events", type=float, default=1e8, help="events per step per GPU")
     ap.add_argument("--e2e-events", type=float, default=2e7, help="events per end-to-end step per GPU")
     ap.add_argument("--ref-events", type=float, default=2e5, help="events per reference process per step")
+    ap.add_argument("--other-events", type=float, default=2e7, help="events per rank for configs 1 and 3")
+    ap.add_argument("--lar-events", type=float, default=2e7, help="LAr events per rank and species (config 5)")
+    ap.add_argument("--sweep-events", type=float, default=1e5, help="events per grid point of the config-4 sweep")
+    ap.add_argument("--checksum-events", type=float, default=8e7, help="global id range of the band checksum")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -99,6 +125,29 @@ def run_reference_processes(nproc, n_events, seed0):
     if any(p.returncode != 0 for p in procs):
         raise RuntimeError("reference process failed")
     return dt
+
+
+def reference_band(n_events, seed):
+    """one reference process with its stderr kept: wall seconds and the band table GetBand prints at the end
+    (execNEST.cpp:1428-1434: centre, actual, mean, mean error, sigma, skew, eff) as [numBins][7] in GetBand order"""
+    import re
+    import numpy as np
+    t0 = time.perf_counter()
+    r = subprocess.run([REF_BIN, str(int(n_events)), "NR", "0", "100", "180", "-1", str(seed)], stdout=subprocess.DEVNULL,
+                       stderr=subprocess.PIPE, text=True)
+    dt = time.perf_counter() - t0
+    if r.returncode != 0:
+        raise RuntimeError("reference process failed")
+    b = []
+    for ln in r.stderr.splitlines():
+        f = ln.split()
+        if len(f) == 7 and re.match(r"^[0-9.]+$", f[0]):
+            try:
+                v = [float(x) for x in f]
+            except ValueError:
+                continue
+            b.append([v[0], v[1], v[2], v[4], v[3], v[6] / 100., v[5]])
+    return dt, np.array(b)
 
 
 def reference_arm(a):
@@ -256,45 +305,69 @@ def main():
     ne = int(a.e2e_events)
     cli_cols = ["signalE", "field", "driftTime", "smear_x", "smear_y", "z_mm", "photons", "electrons", "s1_2",
                 "s1_5", "s1_7", "s2_0", "s2_4", "s2_7"]
-    soa = capi.SoaOut()
-    soa.mem_kind = capi.MEM_HOST
-    pinned = {}
-    d2h = 0
-    for nme in cli_cols:
-        is_int = nme in capi.SOA_I32
-        t = torch.empty(ne, dtype=torch.int32 if is_int else torch.float64, pin_memory=True)
-        pinned[nme] = t
-        d2h += t.numel() * t.element_size()
-        if nme.startswith("s1_") or nme.startswith("s2_"):
-            getattr(soa, nme[:2])[int(nme[3:])] = t.data_ptr()
-        else:
-            setattr(soa, nme, t.data_ptr())
-    hband = capi.Band(ana)
-    d2h += nwords * 8
     h2d = C.sizeof(capi.Detector) + C.sizeof(capi.Model) + C.sizeof(capi.Analysis) + C.sizeof(capi.Source) + \
         C.sizeof(capi.RunConsts)
 
-    def e2e_step(i):
-        first = (10_000 + i * world + rank) * ne
-        ctx._check(capi.lib().nb200_run(ctx.h, C.byref(det), C.byref(mo), C.byref(ana), C.byref(src), C.byref(rc),
-                                        seed, first, ne, C.byref(soa), C.byref(hband.c)))
+    def e2e_run(f32):
+        """events/s through nb200_run with pinned HOST columns (the 14 the reference CLI prints) + band; f32 = the
+        packed record (NB200_SOA_F32: float columns)"""
+        soa = capi.SoaOut()
+        soa.mem_kind = capi.MEM_HOST
+        soa.flags = capi.SOA_F32_FLAG if f32 else 0
+        pinned = {}
+        d2h = 0
+        for nme in cli_cols:
+            is_int = nme in capi.SOA_I32
+            t = torch.empty(ne, dtype=torch.int32 if is_int else (torch.float32 if f32 else torch.float64), pin_memory=True)
+            pinned[nme] = t
+            d2h += t.numel() * t.element_size()
+            if nme.startswith("s1_") or nme.startswith("s2_"):
+                getattr(soa, nme[:2])[int(nme[3:])] = t.data_ptr()
+            else:
+                setattr(soa, nme, t.data_ptr())
+        hband = capi.Band(ana)
+        d2h += nwords * 8
 
-    e2e_steps = max(2, min(a.steps, 3))
-    e2e_step(0)
+        def e2e_step(i):
+            first = (10_000 + i * world + rank) * ne
+            ctx._check(capi.lib().nb200_run(ctx.h, C.byref(det), C.byref(mo), C.byref(ana), C.byref(src), C.byref(rc),
+                                            seed, first, ne, C.byref(soa), C.byref(hband.c)))
+
+        steps = max(2, min(a.steps, 3))
+        e2e_step(0)
+        barrier()
+        t0 = time.perf_counter()
+        g0 = torch.cuda.Event(enable_timing=True)
+        g1 = torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for i in range(steps):
+            e2e_step(1 + i)
+        g1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        tt = torch.tensor([max(g0.elapsed_time(g1) * 1e-3, wall)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(ne) * world * steps / float(tt.item()), d2h, steps
+
+    e2e_value, d2h, e2e_steps = e2e_run(False)
+    e2e_packed, d2h_packed, _ = e2e_run(True)
+
+    # the host's ingest ceiling for this many GPUs: plain cudaMemcpyAsync D2H into pinned memory, every rank at once
+    ing_bytes = 1 << 30
+    dsrc = torch.empty(ing_bytes, dtype=torch.uint8, device="cuda")
+    hdst = torch.empty(ing_bytes, dtype=torch.uint8, pin_memory=True)
+    hdst.copy_(dsrc, non_blocking=True)
     barrier()
     t0 = time.perf_counter()
-    g0 = torch.cuda.Event(enable_timing=True)
-    g1 = torch.cuda.Event(enable_timing=True)
-    g0.record()
-    for i in range(e2e_steps):
-        e2e_step(1 + i)
-    g1.record()
+    for _ in range(4):
+        hdst.copy_(dsrc, non_blocking=True)
     barrier()
-    wall = time.perf_counter() - t0
-    tt = torch.tensor([max(g0.elapsed_time(g1) * 1e-3, wall)], device="cuda", dtype=torch.float64)
+    tt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    e2e_value = float(ne) * world * e2e_steps / float(tt.item())
+    host_ingest_gbs = 4.0 * ing_bytes * world / float(tt.item()) / 1e9
+    del dsrc, hdst
 
     # mean S1 hits per event of this workload (for the algorithmic flop count)
     smp = ctx.run(det, mo, ana, src, rc, seed, 200000, first_event=77_000_000_000, columns=["s1_0"])
@@ -312,54 +385,147 @@ def main():
         "gpu_launches": int(gpu_launches),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "events_per_step_per_gpu": ne, "steps": e2e_steps,
-                "api": "nb200_run (C-ABI), pinned host SoA of the 14 CLI columns + band",
+                "api": "nb200_run (C-ABI), pinned host SoA of the 14 CLI columns (f64, as the reference prints doubles) + band",
+                "packed_f32": {"value": e2e_packed, "d2h_bytes_per_step": int(d2h_packed),
+                               "api": "the same call with NB200_SOA_F32 (float columns, 56 B/event)"},
+                "host_ingest_gbs": host_ingest_gbs,
+                "host_ingest_note": "plain cudaMemcpyAsync D2H of 1 GiB x 4 into pinned memory, all ranks at once: the "
+                                    "ceiling the e2e record stream runs against",
+                "record_stream_gbs": e2e_value * (d2h / ne) / 1e9, "record_stream_gbs_packed": e2e_packed * (d2h_packed / ne) / 1e9,
                 "cpu_affinity": numa},
         "clocks": sampler.summary(),
     }
 
-    if rank == 0 and world == 1:
-        # the other BASELINE configurations on the same device (band-only, device resident), for information:
-        # config 1 (ER flat 0.1-20 keV, the reference's own CPU-runnable case) and config 3 (CH3T, DD)
-        others = {}
-        for name, s_, er_model in [
-                ("config1_ER_flat_0.1-20keV", capi.source(capi.SRC_FLAT, capi.beta, 0.1, 20.0, 180.0), 0),
-                ("config3_CH3T", capi.source(capi.SRC_CH3T, capi.CH3T, 0.0, 18.5898, 180.0), -1),
-                ("config3_DD", capi.source(capi.SRC_DD, capi.DD, 0.0, 80.0, 180.0, par=(13., 0.12, 71.2, 20., -20.5)), -1)]:
-            m_ = capi.model(1)
-            m_.er_model = er_model
-            if s_.species >= 6:
-                m_.massNum = det.molarMass
-            n_ = 20_000_000
-            for rep in range(2):  # first pass warms up
-                band_t.zero_()
-                t0_, t1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                t0_.record()
-                ctx.run_async(det, m_, ana, s_, rc, seed, 0, n_)
-                t1_.record()
-                torch.cuda.synchronize()
-            others[name] = n_ / (t0_.elapsed_time(t1_) * 1e-3)
-        # config 5: LArNEST NR mean yields + default fluctuations, device-resident in and out (120 B/event:
-        # E and field in, 9 yield columns and 4 fluctuation columns out) -- the HBM-bound member of the family
-        n_ = 20_000_000
-        E_ = torch.rand(n_, dtype=torch.float64, device="cuda") * 999.9 + 0.1
-        F_ = torch.rand(n_, dtype=torch.float64, device="cuda") * 999.0 + 1.0
-        Y_ = torch.empty((9, n_), dtype=torch.float64, device="cuda")
-        Fl_ = torch.empty((4, n_), dtype=torch.float64, device="cuda")
-        torch.cuda.synchronize()
+    # ---- the other BASELINE configurations, every rank its shard, accumulators combined over NCCL ----------------
+    others = {}
+
+    def timed(fn, reps=2):
+        """seconds of the last of `reps` calls, max over ranks (CUDA events on the chain's stream)"""
+        for rep in range(reps):
+            barrier()
+            t0_, t1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0_.record()
+            fn()
+            t1_.record()
+            barrier()
+        tt_ = torch.tensor([t0_.elapsed_time(t1_) * 1e-3], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt_, op=dist.ReduceOp.MAX)
+        return float(tt_.item())
+
+    # config 1 (ER flat 0.1-20 keV, the reference's own CPU-runnable case) and config 3 (CH3T, DD): band all-reduce
+    n3 = int(a.other_events)
+    for name, s_, er_model in [
+            ("config1_ER_flat_0.1-20keV", capi.source(capi.SRC_FLAT, capi.beta, 0.1, 20.0, 180.0), 0),
+            ("config3_CH3T", capi.source(capi.SRC_CH3T, capi.CH3T, 0.0, 18.5898, 180.0), -1),
+            ("config3_DD", capi.source(capi.SRC_DD, capi.DD, 0.0, 80.0, 180.0, par=(13., 0.12, 71.2, 20., -20.5)), -1)]:
+        m_ = capi.model(1)
+        m_.er_model = er_model
+        if s_.species >= 6:
+            m_.massNum = det.molarMass
+
+        def run3():
+            band_t.zero_()
+            ctx.run_async(det, m_, ana, s_, rc, seed, rank * n3, n3)
+            if world > 1:
+                dist.all_reduce(band_t)
+        others[name] = n3 * world / timed(run3)
+
+    # config 5: LArNEST NR / ER / alpha mean yields + default fluctuations over an (E, field) grid, device-resident in
+    # and out (E and field in, 9 yield and 4 fluctuation columns out = 120 B/event: the HBM-bound member of the
+    # family); the moments of the fluctuated quanta are summed on the device and all-reduced
+    nl = int(a.lar_events)
+    E_ = torch.rand(nl, dtype=torch.float64, device="cuda") * 999.9 + 0.1
+    F_ = torch.rand(nl, dtype=torch.float64, device="cuda") * 999.0 + 1.0
+    Y_ = torch.empty((9, nl), dtype=torch.float64, device="cuda")
+    Fl_ = torch.empty((4, nl), dtype=torch.float64, device="cuda")
+    lar_gbs = {}
+    for sp_name, sp_ in (("NR", 0), ("ER", 1), ("alpha", 2)):
+        def run5():
+            ctx.lar_device(sp_, nl, E_.data_ptr(), F_.data_ptr(), 1.393, Y_.data_ptr(), Fl_.data_ptr(), seed=seed,
+                           first_event=rank * nl)
+        t_k = timed(run5)
+        mom = torch.stack([Fl_.sum(dim=1), (Fl_ * Fl_).sum(dim=1)])
+        if world > 1:
+            dist.all_reduce(mom)
+        others["config5_LAr_%s_yields+fluctuations" % sp_name] = nl * world / t_k
+        lar_gbs[sp_name] = 120.0 * nl / t_k / 1e9
+    del E_, F_, Y_, Fl_
+    out["other_workloads_events_per_s"] = others
+    out["other_workloads_note"] = ("%d events per rank and configuration (chain) / %d (LAr), band or moment accumulators "
+                                   "all-reduced over NCCL at N > 1; device-resident, CUDA events, max over ranks" % (n3, nl))
+    out["lar_hbm_gbs_per_gpu"] = lar_gbs
+
+    # config 4: batched sweep -- drift field x g1 x g1_gas grid (10 x 5 x 5 points), 50 GeV WIMP and 8B, 1e5 events per
+    # grid point, one band per point; the points are dealt round-robin to the ranks (no collective: a point is whole)
+    fields = [60., 100., 140., 180., 240., 300., 400., 500., 700., 1000.]
+    g1s = [0.09, 0.10, 0.117, 0.13, 0.15]
+    g1gs = [0.07, 0.085, 0.10, 0.115, 0.13]
+    wt = capi.WimpTable(50.0, 5.0, 0.0, seed=seed)
+    tprep = time.perf_counter()
+    grid = []
+    k = 0
+    for f_ in fields:
+        for g1_ in g1s:
+            for gg_ in g1gs:
+                if k % world == rank:
+                    d_ = capi.detector("LUX_Run03")
+                    d_.g1, d_.g1_gas = g1_, gg_
+                    grid.append((d_, capi.prepare(d_, f_), f_))
+                k += 1
+    tprep = time.perf_counter() - tprep
+    npt = int(a.sweep_events)
+    sweep = {"grid": "10 fields x 5 g1 x 5 g1_gas = %d points" % k, "events_per_point": npt,
+             "host_prepare_s_per_point": tprep / max(len(grid), 1)}
+    for sname in ("WIMP50", "B8"):
+        dets_ = [g[0] for g in grid]
+        rcs_ = [g[1] for g in grid]
+        mods_ = [capi.model(1) for _ in grid]
+        if sname == "WIMP50":
+            srcs_ = [wt.attach(capi.source(capi.SRC_WIMP, capi.WIMP, 50.0, 1e-36, g[2])) for g in grid]
+        else:
+            srcs_ = [capi.source(capi.SRC_B8, capi.B8, 0.0, 5.0, g[2]) for g in grid]
+        ts = None
         for rep in range(2):
+            barrier()
+            t0 = time.perf_counter()
+            ctx.run_sweep(dets_, mods_, ana, srcs_, rcs_, seed, npt)
             ctx.synchronize()
-            t0w = time.perf_counter()
-            ctx.lar_device(0, n_, E_.data_ptr(), F_.data_ptr(), 1.393, Y_.data_ptr(), Fl_.data_ptr(), seed=seed)
-            ctx.synchronize()
-            dtw = time.perf_counter() - t0w
-        others["config5_LAr_NR_yields+fluctuations"] = n_ / dtw
-        out["other_workloads_events_per_s"] = others
-        out["lar_hbm_gbs"] = 120.0 * n_ / dtw / 1e9
-        del E_, F_, Y_, Fl_
+            ts = time.perf_counter() - t0
+        tt_ = torch.tensor([ts], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt_, op=dist.ReduceOp.MAX)
+        sweep[sname + "_events_per_s"] = float(k) * npt / float(tt_.item())
+        # the same source as ONE large run (the rate a sweep point would see if it were not small)
+        big = 20_000_000
+
+        def run_big():
+            band_t.zero_()
+            ctx.run_async(grid[0][0], mods_[0], ana, srcs_[0], grid[0][1], seed, rank * big, big)
+        sweep[sname + "_large_run_events_per_s"] = big * world / timed(run_big)
+        sweep[sname + "_sweep_over_large_run"] = sweep[sname + "_events_per_s"] / sweep[sname + "_large_run_events_per_s"]
+    sweep["timing"] = "wall clock around nb200_run_sweep (host parameter blocks, launches, band copy-back), max over ranks"
+    out["config4_sweep"] = sweep
+    out["config4_sweep_events_per_s"] = sweep["WIMP50_events_per_s"]
+
+    # identical integers at every GPU count: the band of global event ids [0, 8e7) of the bench workload, each rank its
+    # contiguous shard, all-reduced; the checksum must not depend on N (SURVEY 4, test (4))
+    from nest_b200 import shard
+    import hashlib
+    lo, hi = shard.event_range(rank, world, int(a.checksum_events))
+    band_t.zero_()
+    ctx.run_async(det, mo, ana, src, rc, seed, lo, hi - lo)
+    if world > 1:
+        dist.all_reduce(band_t)
+    torch.cuda.synchronize()
+    out["band_checksum_fixed_ids"] = {"ids": "[0, %d)" % int(a.checksum_events),
+                                      "sha256_16": hashlib.sha256(band_t.cpu().numpy().tobytes()).hexdigest()[:16],
+                                      "accepted": int(band_t[:ana.numBins * 6].view(ana.numBins, 6)[:, 0].sum().item())}
+
     if rank == 0:
         peak = ctx.fp64_peak()
-        # dominant kernel: k_hits, the per-hit S1 loop.  Algorithmic work per launch = SURVEY 8(d)'s
-        # F_hit = 192 DFMA-equivalent flop per PMT hit x the hits one launch processes.
+        # dominant kernel: k_hits (+ its deferred finisher), the per-hit S1 loop.  Algorithmic work per launch =
+        # SURVEY 8(d)'s F_hit = 192 DFMA-equivalent flop per PMT hit x the hits one launch processes.
         n_hit_launches = max(stage_launches[1], 1)
         hits_ms = stage_ms["k_hits"] / n_hit_launches
         events_per_launch = float(n) * a.steps / n_hit_launches
@@ -367,38 +533,58 @@ def main():
         chain_ms = sum(stage_ms.values()) / a.steps
         out["roofline"] = {
             "bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            **ncu_traffic(), "kernel": "k_hits", "kernel_ms_per_launch": hits_ms,
+            **ncu_traffic(), "kernel": "k_hits + k_hits_finish", "kernel_ms_per_launch": hits_ms,
             "kernel_launches": int(n_hit_launches), "hits_per_launch": events_per_launch * mean_hits,
             "flops_per_hit": F_HIT, "mean_s1_hits": mean_hits,
             "stage_ms_per_step": {k: v / a.steps for k, v in stage_ms.items()},
             "kernel_share_of_step": stage_ms["k_hits"] / max(sum(stage_ms.values()), 1e-9),
             "chain_flops_per_event": flops_per_event,
             "chain_achieved_tflops": float(n) * flops_per_event / (chain_ms * 1e-3) / 1e12,
-            "peak_source": "measured on this device by nb200_fp64_peak (register-resident DFMA chain, CUDA "
-                           "events); MEASURED_PEAKS.json carries HBM and bf16 figures only (nominal FP64 37.2)",
+            "chain_frac_of_peak": float(n) * flops_per_event / (chain_ms * 1e-3) / 1e12 / peak,
+            "peak_nominal_tflops": 37.2,
+            "frac_of_nominal": achieved / 37.2,
+            "peak_source": "measured on this device by nb200_fp64_peak: a register-resident chain of dependent DFMAs, "
+                           "8 independent chains per thread, 148 x 8 blocks of 256 threads, timed with CUDA events "
+                           "(2 flop per DFMA); MEASURED_PEAKS.json carries HBM and bf16 figures only and the profiling "
+                           "guide states no FP64 fallback.  Nominal: 148 SM x 64 FP64 lanes x 2 x 1.965 GHz = 37.2 TFLOP/s",
+            **ncu_utilisation(),
             "note": "FP64 CUDA-core roofline, not HBM or tensor: no contraction, and in band-only mode the only HBM "
                     "stream is the 140 B/event stage workspace (see hbm_workspace_frac).  `achieved` counts the "
                     "REFERENCE algorithm's per-hit work (SURVEY 8d: 192 DFMA-equivalent flop per PMT hit: two "
-                    "Box-Muller normals, a Bernoulli, ...) delivered per second; the kernel itself executes far "
-                    "fewer FP64 instructions per hit (ziggurat normal, one normal per photo-electron, per-event "
-                    "double-phe count): ncu shows its FP64 pipe ~11 % busy and 65 % of issue slots used "
-                    "(profiles/r01_k_hits_ncu_full.txt, DESIGN.md section 5)",
+                    "Box-Muller normals, a Bernoulli, ...) delivered per second -- an algorithmic delivery rate, NOT "
+                    "pipe utilisation: the kernel executes far fewer FP64 instructions per hit (ziggurat normal, one "
+                    "normal per photo-electron, per-event double-phe count); issue_active / active lanes / FP64 pipe "
+                    "busy from the committed ncu capture are alongside",
             "hbm_workspace_frac": None}
         try:
             with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
                 mp = json.load(f)
             out["roofline"]["hbm_workspace_frac"] = (value / world) * 140.0 * 2 / 1e9 / mp["hbm_gbs"]
             out["roofline"]["hbm_output_stream_frac_e2e"] = (e2e_value / world) * (d2h / ne) / 1e9 / mp["hbm_gbs"]
+            out["lar_hbm_frac"] = {k: v / mp["hbm_gbs"] for k, v in lar_gbs.items()}
         except Exception:
             pass
         if world == 1 and not a.no_cpu_baseline and os.path.exists(REF_BIN):
             nref = 500000
-            t0 = time.perf_counter()
-            run_reference_processes(1, nref, 1)
-            dt = time.perf_counter() - t0
+            dt, bref = reference_band(nref, 1)
             out["cpu_baseline"] = {"value": nref / dt, "unit": UNIT, "cores": 1, "kind": "reference",
                                    "sample": "1 process, %d events of `execNEST_ref_lux N NR 0 100 180 -1 1` "
                                              "(unmodified reference, stdout to /dev/null)" % nref}
+            # the second half of BASELINE's metric: band chi^2 against the reference (its own band table from the run
+            # above vs the band of the last timed step), rootNEST's goodness of fit (examples/rootNEST.cpp:600-643)
+            try:
+                bg = band.finalize()
+                ok = np.isfinite(bg).all(axis=1) & np.isfinite(bref).all(axis=1) & (bref[:, 4] > 0)
+                chi = capi.band_chi2(bg[ok], bref[ok], useS2=0, free_param=0)
+                out["band_chi2"] = {"mean_per_dof": float(chi[0]), "width_per_dof": float(chi[1]), "bins": int(ok.sum()),
+                                    "gpu_events": int(band.c.n_events), "reference_events": nref,
+                                    "mean_pct_diff": float(chi[4]), "width_pct_diff": float(chi[5]),
+                                    "method": "nb200_band_chi2 = rootNEST's reduced chi^2 between two bands; width "
+                                              "error sigma/sqrt(2N) as rootNEST; the 1e8 vs 1e8 comparison with the "
+                                              "fourth-moment width error and a reference-vs-reference null is "
+                                              "profiles/r02_parity_1e8.txt"}
+            except Exception as e:  # the bench line must not die on its diagnostics
+                out["band_chi2"] = {"error": str(e)}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -199,10 +199,15 @@ typedef struct nb200_run_consts {
  *   quanta NEST.hh:171-178, truth as NESTObservableArray execNEST.hh:30-44,
  *   signal1/signal2/signalE execNEST.cpp:1121-1158,1245-1250. */
 enum { NB200_MEM_HOST = 0, NB200_MEM_DEVICE = 1 };
+/* nb200_soa_out.flags: NB200_SOA_F32 = the packed record -- every `double*` column below is an array of FLOAT
+ * (4 bytes per entry; the int32 columns are unchanged): half the bytes over PCIe for callers that histogram or plot
+ * the signals (7 significant digits; the reference CLI prints %.6f).  Default 0: doubles, as the reference's own
+ * vectors. */
+enum { NB200_SOA_F32 = 1 };
 
 typedef struct nb200_soa_out {
   int32_t mem_kind;
-  int32_t _pad;
+  int32_t flags;
   double *energy_kev, *x_mm, *y_mm, *z_mm, *field, *driftTime;
   double *smear_x, *smear_y;
   int32_t *photons, *electrons, *ions, *excitons;

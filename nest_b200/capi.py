@@ -22,6 +22,7 @@ MAP_CONST, MAP_LUX_RUN03, MAP_LUT_RZ = 0, 1, 2
 (SRC_MONO, SRC_FLAT, SRC_GAUSS, SRC_EXP, SRC_CH3T, SRC_DD, SRC_B8, SRC_LIST, SRC_WIMP,
  SRC_AMBE, SRC_C14, SRC_CF, SRC_PPSOLAR, SRC_ATMNU) = range(14)
 MEM_HOST, MEM_DEVICE = 0, 1
+SOA_F32_FLAG = 1  # nb200_soa_out.flags: the packed record (float columns)
 FX_S1, FX_Y, FX_Y2, FX_Y3 = 2.0 ** 20, 2.0 ** 30, 2.0 ** 26, 2.0 ** 22
 
 c_dp = C.POINTER(C.c_double)
@@ -87,7 +88,7 @@ SOA_TAIL = ["signal1", "signal2", "signalE", "Nph_mean", "Ne_mean", "deltaT_ns",
 
 
 class SoaOut(C.Structure):
-    _fields_ = ([("mem_kind", C.c_int32), ("_pad", C.c_int32)] + [(n, C.c_void_p) for n in SOA_F64] +
+    _fields_ = ([("mem_kind", C.c_int32), ("flags", C.c_int32)] + [(n, C.c_void_p) for n in SOA_F64] +
                 [(n, C.c_void_p) for n in SOA_I32] + [("s1", C.c_void_p * 9), ("s2", C.c_void_p * 9)] +
                 [(n, C.c_void_p) for n in SOA_TAIL])
 
@@ -513,21 +514,23 @@ class Context:
                                    first_event, MEM_HOST, _dptr(out)))
         return out
 
-    def run(self, det, mo, ana, src, rc, seed, n, first_event=0, columns=None, band=None):
-        """nb200_run with host outputs. columns: names from SOA_COLUMNS (None = all)."""
+    def run(self, det, mo, ana, src, rc, seed, n, first_event=0, columns=None, band=None, f32=False):
+        """nb200_run with host outputs. columns: names from SOA_COLUMNS (None = all); f32: the packed record."""
         cols = {}
         soa = SoaOut()
         soa.mem_kind = MEM_HOST
+        soa.flags = SOA_F32_FLAG if f32 else 0
+        ft = np.float32 if f32 else np.float64
         names = SOA_COLUMNS if columns is None else columns
         for nme in names:
             if nme in SOA_I32:
                 a = np.zeros(n, np.int32)
                 setattr(soa, nme, a.ctypes.data)
             elif nme.startswith("s1_") or nme.startswith("s2_"):
-                a = np.zeros(n, np.float64)
+                a = np.zeros(n, ft)
                 getattr(soa, nme[:2])[int(nme[3:])] = a.ctypes.data
             else:
-                a = np.zeros(n, np.float64)
+                a = np.zeros(n, ft)
                 setattr(soa, nme, a.ctypes.data)
             cols[nme] = a
         self._check(lib().nb200_run(self.h, C.byref(det), C.byref(mo), C.byref(ana), C.byref(src), C.byref(rc),

@@ -24,7 +24,9 @@ struct nb200_ctx {
   cudaStream_t stream = nullptr;
   std::string err;
   uint64_t launches = 0;
-  int* d_err = nullptr;  // [0] error flags of the kernels, [1] k_hits group counter
+  int* d_err = nullptr;  // [0] error flags of the kernels, [1] k_hits group counter, [2] deferred-queue fill
+  SlotEntry* d_hitq = nullptr;  // k_hits -> k_hits_finish queue (nb_kernels.cuh)
+  unsigned int hitq_cap = 0;
   // device-resident band accumulator (async API)
   unsigned long long* d_band = nullptr;
   bool band_external = false;
@@ -404,6 +406,32 @@ int ensure_occupancy(nb200_ctx* c) {
   return 0;
 }
 
+// the deferred-finisher queue: 6 entries per workspace event (LUX NR 0-100 keV queues 2 per event; what does not
+// fit is finished inside k_hits), allocated with the workspace
+int ensure_hit_queue(nb200_ctx* c, HitQueue* q) {
+  const uint64_t want = std::min<uint64_t>(std::max<uint64_t>(c->work_cap, 1024) * 6, 1u << 28);
+  if (want > c->hitq_cap) {
+    if (c->d_hitq) cudaFree(c->d_hitq);
+    c->d_hitq = nullptr;
+    c->hitq_cap = 0;
+    NB_CUDA(c, cudaMalloc(&c->d_hitq, want * sizeof(SlotEntry)));
+    c->hitq_cap = unsigned(want);
+  }
+  q->entries = c->d_hitq;
+  q->count = reinterpret_cast<unsigned int*>(c->d_err + 2);
+  q->cap = c->hitq_cap;
+  return 0;
+}
+
+// k_hits + k_hits_finish for the m events of Q's workspace chunk
+void launch_hits(nb200_ctx* c, const RunParams& Q, uint64_t m, const HitQueue& hq) {
+  const uint64_t sm = uint64_t(c->sm_count);
+  const unsigned g_hits = unsigned(std::min<uint64_t>((m + kHitGroup - 1) / kHitGroup, sm * c->occ_hits));  // persistent
+  cudaMemsetAsync(c->d_err + 1, 0, 2 * sizeof(int), c->stream);
+  k_hits<<<g_hits, kHitBlock, kHitDynSmem, c->stream>>>(Q, reinterpret_cast<unsigned int*>(c->d_err + 1), hq);
+  k_hits_finish<<<unsigned(sm * 16), kFinBlock, 0, c->stream>>>(Q, hq);
+}
+
 // k_pre -> k_hits -> k_post over the call's events in chunks of the workspace size
 int launch_event(nb200_ctx* c, RunParams& P) {
   if (P.n_events == 0) return 0;
@@ -422,6 +450,8 @@ int launch_event(nb200_ctx* c, RunParams& P) {
   if (c->occ_post < 1) c->occ_post = 1;
   int r = ensure_workspace(c, P.n_events, &P.work);
   if (r) return r;
+  HitQueue hq;
+  if ((r = ensure_hit_queue(c, &hq))) return r;
   const uint64_t total = P.n_events, cap = c->work_cap;
   for (uint64_t off = 0; off < total; off += cap) {
     const uint64_t m = std::min<uint64_t>(cap, total - off);
@@ -430,7 +460,6 @@ int launch_event(nb200_ctx* c, RunParams& P) {
     Q.chunk_off = P.chunk_off + off;
     const uint64_t sm = uint64_t(c->sm_count);
     unsigned g_pre = unsigned(std::min<uint64_t>((m + kPreBlock - 1) / kPreBlock, sm * c->occ_pre * 8));
-    unsigned g_hits = unsigned(std::min<uint64_t>((m + kHitGroup - 1) / kHitGroup, sm * c->occ_hits));  // persistent
     unsigned g_post = unsigned(std::min<uint64_t>((m + kPostBlock - 1) / kPostBlock, sm * c->occ_post));
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     if (c->timing)
@@ -438,8 +467,7 @@ int launch_event(nb200_ctx* c, RunParams& P) {
     if (c->timing) cudaEventRecord(ev[0], c->stream);
     k_pre<<<g_pre, kPreBlock, 0, c->stream>>>(Q, c->d_err);
     if (c->timing) cudaEventRecord(ev[1], c->stream);
-    cudaMemsetAsync(c->d_err + 1, 0, sizeof(int), c->stream);
-    k_hits<<<g_hits, kHitBlock, kHitDynSmem, c->stream>>>(Q, reinterpret_cast<unsigned int*>(c->d_err + 1));
+    launch_hits(c, Q, m, hq);
     if (c->timing) cudaEventRecord(ev[2], c->stream);
     k_post<<<g_post, kPostBlock, smem, c->stream>>>(Q, c->d_err);
     if (c->timing) {
@@ -447,7 +475,7 @@ int launch_event(nb200_ctx* c, RunParams& P) {
       for (auto& e : ev) c->tev.push_back(e);
     }
     NB_CUDA(c, cudaGetLastError());
-    c->launches += 3;
+    c->launches += 4;
   }
   return 0;
 }
@@ -514,7 +542,7 @@ int nb200_create(int device, nb200_ctx** out) {
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaMalloc(&c->d_err, 2 * sizeof(int)) != cudaSuccess || cudaMemset(c->d_err, 0, 2 * sizeof(int)) != cudaSuccess) {
+      cudaMalloc(&c->d_err, 4 * sizeof(int)) != cudaSuccess || cudaMemset(c->d_err, 0, 4 * sizeof(int)) != cudaSuccess) {
     g_err_noctx = std::string("context setup: ") + cudaGetErrorString(cudaGetLastError());
     delete c;
     return NB200_ECUDA;
@@ -590,6 +618,7 @@ void nb200_destroy(nb200_ctx* c) {
   if (c->d_list) cudaFree(c->d_list);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->d_err) cudaFree(c->d_err);
+  if (c->d_hitq) cudaFree(c->d_hitq);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
 }
@@ -1057,6 +1086,8 @@ int nb200_s1(nb200_ctx* c, const nb200_detector* det, const nb200_run_consts* rc
   if (r) return r;
   if ((r = ensure_occupancy(c))) return r;
   if ((r = ensure_workspace(c, n, &P.work))) return r;
+  HitQueue hq;
+  if ((r = ensure_hit_queue(c, &hq))) return r;
   S1Args a;
   a.stride = n;
   a.off = 0;
@@ -1096,13 +1127,11 @@ int nb200_s1(nb200_ctx* c, const nb200_detector* det, const nb200_run_consts* rc
     Q.chunk_off = off;
     a.off = off;
     const unsigned g1 = unsigned(std::min<uint64_t>((m + 255) / 256, sm * 8));
-    const unsigned g_hits = unsigned(std::min<uint64_t>((m + kHitGroup - 1) / kHitGroup, sm * c->occ_hits));
     k_s1pre<<<g1, 256, 0, c->stream>>>(Q, a);
-    cudaMemsetAsync(c->d_err + 1, 0, sizeof(int), c->stream);
-    k_hits<<<g_hits, kHitBlock, kHitDynSmem, c->stream>>>(Q, reinterpret_cast<unsigned int*>(c->d_err + 1));
+    launch_hits(c, Q, m, hq);
     k_s1post<<<g1, 256, 0, c->stream>>>(Q, a);
     cudaError_t le = cudaGetLastError();
-    c->launches += 3;
+    c->launches += 4;
     if (le != cudaSuccess) r = fail(c, NB200_ECUDA, std::string("nb200_s1: ") + cudaGetErrorString(le));
   }
   if (!r && mem_kind == NB200_MEM_HOST) {
@@ -1163,7 +1192,7 @@ int nb200_run_async(nb200_ctx* c, const nb200_detector* det, const nb200_model* 
     return fail(c, NB200_EINVAL, "nb200_run_async needs a device-resident energy list");
   if (soa) {
     if (soa->mem_kind != NB200_MEM_DEVICE) return fail(c, NB200_EINVAL, "nb200_run_async needs device SoA pointers");
-    P.write_soa = 1;
+    P.write_soa = (soa->flags & NB200_SOA_F32) ? 2 : 1;
     static_assert(sizeof(SoaDev) == sizeof(nb200_soa_out) - 8, "SoA layouts must match");
     std::memcpy(&P.soa, reinterpret_cast<const char*>(soa) + 8, sizeof(SoaDev));
   }
@@ -1238,6 +1267,7 @@ int nb200_run(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo, co
   if (n_events == 0) return 0;
   Trace tr("nb200_run");
   const bool host_soa = soa && soa->mem_kind == NB200_MEM_HOST;
+  const bool f32 = soa && (soa->flags & NB200_SOA_F32);
   const bool host_list = src->kind == NB200_SRC_LIST && src->list_mem_kind == NB200_MEM_HOST;
   // Host outputs: the kernels of chunk i write into device staging buffer i%2 while the copy
   // stream drains buffer (i-1)%2 to the caller's arrays, so PCIe and compute overlap.
@@ -1258,7 +1288,7 @@ int nb200_run(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo, co
     void** hp = reinterpret_cast<void**>(reinterpret_cast<char*>(soa) + 8);
     for (size_t k = 0; k < ncol; ++k) {
       if (!hp[k]) continue;
-      const size_t elt = (k >= 8 && k < 12) ? 4 : 8;
+      const size_t elt = ((k >= 8 && k < 12) || f32) ? 4 : 8;
       cols.push_back({k, elt, per_chunk, hp[k]});
       per_chunk += ((elt * cap + 255) / 256) * 256;
     }
@@ -1350,7 +1380,7 @@ int nb200_run(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo, co
     P.src.y = s.y;
     P.src.z = s.z;
     if (soa) {
-      P.write_soa = 1;
+      P.write_soa = f32 ? 2 : 1;
       nb200_soa_out tmp = *soa;
       void** dp = reinterpret_cast<void**>(reinterpret_cast<char*>(&tmp) + 8);
       if (host_soa) {
@@ -1359,7 +1389,7 @@ int nb200_run(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo, co
         if (ichunk >= 2) cudaStreamWaitEvent(c->stream, c->ev_copied[buf], 0);  // buffer drained?
       } else {  // caller's device columns, advanced to this chunk
         for (size_t k = 0; k < ncol; ++k)
-          if (dp[k]) dp[k] = static_cast<char*>(dp[k]) + ((k >= 8 && k < 12) ? 4 : 8) * done;
+          if (dp[k]) dp[k] = static_cast<char*>(dp[k]) + (((k >= 8 && k < 12) || f32) ? 4 : 8) * done;
       }
       std::memcpy(&P.soa, reinterpret_cast<const char*>(&tmp) + 8, sizeof(SoaDev));
     }
@@ -1479,6 +1509,8 @@ int nb200_run_sweep(nb200_ctx* c, size_t n_points, const nb200_detector* dets, c
   const uint64_t total = uint64_t(n_points) * A.n_pad;
   int r = ensure_workspace(c, total, &A.work);
   if (r) return r;
+  HitQueue hq;
+  if ((r = ensure_hit_queue(c, &hq))) return r;
   const uint64_t cap = c->work_cap / 1024 * 1024;
   const uint64_t sm = uint64_t(c->sm_count);
   for (uint64_t off = 0; off < total; off += cap) {
@@ -1489,11 +1521,12 @@ int nb200_run_sweep(nb200_ctx* c, size_t n_points, const nb200_detector* dets, c
     unsigned g_hits = unsigned(std::min<uint64_t>((m + kHitGroup - 1) / kHitGroup, sm * c->occ_hits_sweep));
     unsigned g_post = unsigned(std::min<uint64_t>((m + kPostBlock - 1) / kPostBlock, sm * occ_post));
     k_pre_sweep<<<g_pre, kPreBlock, 0, c->stream>>>(A, c->d_err);
-    cudaMemsetAsync(c->d_err + 1, 0, sizeof(int), c->stream);
-    k_hits_sweep<<<g_hits, kHitBlock, kHitDynSmem, c->stream>>>(A, reinterpret_cast<unsigned int*>(c->d_err + 1));
+    cudaMemsetAsync(c->d_err + 1, 0, 2 * sizeof(int), c->stream);
+    k_hits_sweep<<<g_hits, kHitBlock, kHitDynSmem, c->stream>>>(A, reinterpret_cast<unsigned int*>(c->d_err + 1), hq);
+    k_hits_finish_sweep<<<unsigned(sm * 16), kFinBlock, 0, c->stream>>>(A, hq);
     k_post_sweep<<<g_post, kPostBlock, smem, c->stream>>>(A, band_in_smem, c->d_err);
     NB_CUDA(c, cudaGetLastError());
-    c->launches += 3;
+    c->launches += 4;
   }
   tr.mark("launched");
   std::vector<unsigned long long> w(words * n_points);

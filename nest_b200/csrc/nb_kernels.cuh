@@ -197,6 +197,14 @@ NB_D void sweep_load_params(RunParams* sP, const RunParams* gP, uint32_t point) 
   __syncthreads();
 }
 
+// SoA column store: double, or float when the caller asked for the packed record (write_soa == 2)
+NB_D void soa_put(double* col, uint64_t i, double v, bool f32) {
+  if (f32)
+    reinterpret_cast<float*>(col)[i] = float(v);
+  else
+    col[i] = v;
+}
+
 // one event of k_pre: W index idx (workspace), gidx (index within the call: lists, SoA columns), event id ev
 NB_D void pre_body(const RunParams& P, const Work& W, uint64_t idx, uint64_t gidx, uint64_t ev, bool active,
                    int* __restrict__ err_flag) {
@@ -292,7 +300,7 @@ NB_D void pre_body(const RunParams& P, const Work& W, uint64_t idx, uint64_t gid
   NB_LOCKSTEP();
   if (!active) return;
 
-  if (P.write_soa && P.soa.deltaT_ns) P.soa.deltaT_ns[gidx] = y.dT;
+  if (P.write_soa && P.soa.deltaT_ns) soa_put(P.soa.deltaT_ns, gidx, y.dT, P.write_soa == 2);
   W.keV[idx] = keV;
   W.px[idx] = px;
   W.py[idx] = py;
@@ -417,39 +425,46 @@ NB_D double pe_normal(const u128& r, const u128& t, int which, uint32_t e0, uint
   return z;
 }
 
-// one photo-electron in full: normal, truncation pre-test, exact residual test (uniform: word `which` of t),
-// joint redraw
+// status of a photo-electron of a queued slot while it is being finished
+enum { PE_FINAL = 0, PE_NEED_ZIG = 1, PE_NEED_REDRAW = 2 };
+
+// a photo-electron after its normal z: area sv, truncation pre-test (pre-test bits of the abscissa word A) and exact
+// residual test (uniform: word `which` of t).  PE_FINAL, or PE_NEED_REDRAW when the pair (S, T) has to be redrawn.
+NB_D int pe_after_normal(const RunParams& P, const u128& t, int which, uint32_t A, double z, double& sv) {
+  sv = fma(P.pe_sig, z, P.pe_mu);
+  if (sv <= P.pe_cut && (sv < P.pe_sfast || (A & NB_PE_PRETEST_MASK) == NB_PE_PRETEST_MASK)) {
+    const uint32_t uw = which == 0 ? t.x : (which == 1 ? t.y : t.z);
+    if (!pe_accept_exact(P, sv, u32d(uw))) return PE_NEED_REDRAW;
+  }
+  return PE_FINAL;
+}
+NB_D double pe_redraw_of(const RunParams& P, uint64_t ev, uint32_t j, int which) {
+  return pe_redraw(P.seed, ev, j * 96u + uint32_t(which) * 32u, P.pe_mu, P.pe_sig, P.pe_cut, P.pe_tau, P.pe_rho, P.pe_m0);
+}
+
+// one photo-electron in full: normal, truncation pre-test, exact residual test, joint redraw
 NB_D double pe_full(const RunParams& P, const u128& r, const u128& t, int which, uint64_t ev, uint32_t j,
                     const uint32_t* zk, const double* zw) {
   uint32_t A;
   bool fast;
   const double z = pe_normal(r, t, which, uint32_t(ev), uint32_t(ev >> 32), j, uint32_t(P.seed), uint32_t(P.seed >> 32), zk,
                              zw, A, fast);
-  double sv = fma(P.pe_sig, z, P.pe_mu);
-  if (sv <= P.pe_cut && (sv < P.pe_sfast || (A & NB_PE_PRETEST_MASK) == NB_PE_PRETEST_MASK)) {
-    const uint32_t uw = which == 0 ? t.x : (which == 1 ? t.y : t.z);
-    if (!pe_accept_exact(P, sv, u32d(uw)))
-      sv = pe_redraw(P.seed, ev, j * 96u + uint32_t(which) * 32u, P.pe_mu, P.pe_sig, P.pe_cut, P.pe_tau, P.pe_rho, P.pe_m0);
-  }
+  double sv;
+  if (pe_after_normal(P, t, which, A, z, sv) == PE_NEED_REDRAW) sv = pe_redraw_of(P, ev, j, which);
   return sv;
 }
 
-// up to 32 queued slots, everything the reference does for their hits
-// (out of line: its register needs must not shape the main loop).  The photo-electrons of a slot are walked by a
-// rolled loop: one call site each for the wedge / tail completion and the joint redraw, so that the lanes of a
-// warp that need one -- a few per pass, for different photo-electrons -- go through it together.
-__device__ __noinline__ void hits_finish_slow(const RunParams& P, const int* s_nh, const int* s_nd,
-                                             unsigned long long* s_area, unsigned int* s_spike, uint64_t ev0,
-                                             const SlotEntry* q, int count, int lane, const uint32_t* zk,
-                                             const double* zw) {
+// One queued slot in full -- everything the reference does for its hits (wedge / tail of the ziggurat, exact
+// truncation test, joint redraw, efficiency and coincidence-window draws).  commit(area, pass_coin) books one hit.
+// The photo-electrons are walked by a rolled loop: one call site each for the wedge / tail completion and the joint
+// redraw, so that the lanes of a warp that need one -- a few per pass, for different photo-electrons -- go through it
+// together.
+template <class Commit>
+NB_D void finish_slot(const RunParams& P, int nh, int nd, uint32_t j, uint64_t ev, const uint32_t* zk, const double* zw,
+                      bool live, const Commit& commit) {
   const nb200_detector& det = P.det;
-  const bool live = lane < count;
-  const SlotEntry en = live ? q[lane] : SlotEntry{0u, 0u};
-  const int e = int(en.e), nh = s_nh[e], nd = s_nd[e];
-  const uint32_t j = en.j;
   const bool dbl = int(j) < nd;
   const int nv = live ? slot_valid(int(j), nd, nh - nd) : 0;
-  const uint64_t ev = ev0 + uint64_t(e);
   const uint32_t e0 = uint32_t(ev), e1 = uint32_t(ev >> 32);
   const u128 r = philox4x32_10_rk(e0, e1, j, STREAM_HIT, P.rk);
   const u128 t = philox4x32_10_rk(e0, e1, j, STREAM_HIT2, P.rk);
@@ -480,18 +495,258 @@ __device__ __noinline__ void hits_finish_slow(const RunParams& P, const int* s_n
         const int hit = dbl ? which - 1 : which;
         const uint32_t cw = hit == 0 ? c.w : (hit == 1 ? c2.x : c2.y);
         const bool coin = !coin_draws || u32d(cw) > P.coin_u_min;
-        hit_commit(P, s_area, s_spike, e, (dbl && which == 1) ? first + sv : sv, coin);
+        commit((dbl && which == 1) ? first + sv : sv, coin);
       }
     }
   }
+}
+
+// up to 32 queued slots finished inside k_hits (out of line: its register needs must not shape the main loop).
+// Only the overflow path of the deferred queue (below) and detectors whose every slot is special end up here.
+__device__ __noinline__ void hits_finish_slow(const RunParams& P, const int* s_nh, const int* s_nd,
+                                             unsigned long long* s_area, unsigned int* s_spike, uint64_t ev0,
+                                             const SlotEntry* q, int count, int lane, const uint32_t* zk,
+                                             const double* zw) {
+  const bool live = lane < count;
+  const SlotEntry en = live ? q[lane] : SlotEntry{0u, 0u};
+  const int e = int(en.e);
+  finish_slot(P, s_nh[e], s_nd[e], en.j, ev0 + uint64_t(e), zk, zw, live,
+              [&](double a, bool coin) { hit_commit(P, s_area, s_spike, e, a, coin); });
   __syncwarp();
+}
+
+// ---- deferred finisher --------------------------------------------------------------------------------------
+// Measured (profiles/r02_k_hits_deferred.txt): finishing the queued slots inside k_hits cost 36 % of its time for
+// 6.5 % of the slots -- the finisher ran at 16 of 32 lanes with its rare sub-paths at 1-2, and stalled a main loop
+// that has only four warps per scheduler to hide anything behind.  k_hits therefore only WRITES its per-warp queue,
+// 32 entries at a time, to a queue in device memory (one atomicAdd per 32 entries), leaves the event sums as
+// integers in the workspace, and a second kernel finishes the queued slots -- one per thread, every lane busy --
+// adding their hits to the event sums with global atomics (integer adds: order does not matter, results stay
+// bit-identical for any batch split).  Entries that do not fit the queue are finished in place as before.
+struct HitQueue {
+  SlotEntry* entries;   // e = workspace index of the event, j = slot
+  unsigned int* count;  // entries pushed (may exceed cap: the excess was finished in place)
+  unsigned int cap;
+};
+
+// A queued slot is slow for one of its photo-electrons only, and for one of three rare reasons: the exact
+// truncation test (most), a wedge / tail completion, a joint redraw.  Finishing every slot straight through
+// (finish_slot) makes a warp execute the redraw and the completion in nearly every pass for the one or two lanes
+// that need them (measured: 1500 warp-instructions per 32 slots).  The finisher therefore works in stages, each
+// dense: stage 0 does what every queued slot needs (its two Philox blocks, the layer-core normals, the pre-tests
+// and exact tests) and books the slots that this settles; the others are parked, with what is already known, in a
+// per-warp queue and completed 32 at a time -- every lane then has a pending photo-electron.  Slots of events that
+// need efficiency / coincidence draws go through finish_slot, also 32 at a time.  Every value is computed by the
+// functions finish_slot uses, with the same streams: which path finishes a slot does not change its result.
+struct SlowItem {
+  uint32_t e, j;
+  double v[3];
+  uint32_t st;  // status of photo-electron k in bits [2k+1 : 2k]
+  uint32_t pad;
+};
+constexpr int kFinBlock = 128;
+constexpr int kFinWarps = kFinBlock / 32;
+
+struct FinCtx {
+  const RunParams* P;
+  const Work* W;
+  uint64_t ev;
+  int nh, nd;
+};
+template <bool SWEEP>
+NB_D FinCtx fin_resolve(const RunParams* P0, const SweepArgs* Ap, uint64_t idx) {
+  FinCtx c;
+  if (SWEEP) {
+    const uint64_t slot = Ap->slot0 + idx;
+    const uint32_t point = uint32_t(slot / Ap->n_pad);
+    c.P = Ap->params + point;  // device memory: the lanes of a warp may belong to different grid points
+    c.W = &Ap->work;
+    c.ev = Ap->first_event + (slot - uint64_t(point) * Ap->n_pad);
+  } else {
+    c.P = P0;
+    c.W = &P0->work;
+    c.ev = P0->first_event + P0->chunk_off + idx;
+  }
+  int nh = c.W->nHits[idx];
+  c.nh = nh > 0 ? nh : 0;
+  c.nd = c.W->nphe[idx] - c.nh;  // k_hits left Nphe = nHits + nD there
+  return c;
+}
+// the hits of a finished slot (no efficiency / coincidence draws) into the event's sums
+NB_D void fin_commit(const RunParams& P, const Work& W, uint64_t idx, bool dbl, int nv, double v0, double v1, double v2) {
+  const double thr = P.det.sPEthr;
+  const double a0 = dbl ? v0 + v1 : v0;
+  const double a1 = dbl ? (nv >= 3 ? v2 : -DBL_MAX) : (nv >= 2 ? v1 : -DBL_MAX);
+  const double a2 = (!dbl && nv >= 3) ? v2 : -DBL_MAX;
+  unsigned long long fx = 0ull;
+  int spikes = 0;
+  if (a0 > thr) fx += (unsigned long long)__double2ll_rn(a0 * NB_AREA_FX), ++spikes;
+  if (a1 > thr) fx += (unsigned long long)__double2ll_rn(a1 * NB_AREA_FX), ++spikes;
+  if (a2 > thr) fx += (unsigned long long)__double2ll_rn(a2 * NB_AREA_FX), ++spikes;
+  if (spikes) {
+    atomicAdd(&reinterpret_cast<unsigned long long*>(W.area)[idx], fx);
+    atomicAdd(&W.spike[idx], spikes);
+  }
+}
+
+template <bool SWEEP>
+NB_D void hits_finish_body(const RunParams* P0, const SweepArgs* Ap, const HitQueue Q) {
+  __shared__ double s_zw[NB_ZIG_N];
+  __shared__ uint32_t s_zk[NB_ZIG_N];
+  __shared__ __align__(8) SlowItem s_slow[kFinWarps][64];
+  __shared__ __align__(8) SlotEntry s_spec[kFinWarps][64];
+  for (int i = threadIdx.x; i < NB_ZIG_N; i += kFinBlock) {
+    s_zw[i] = g_zig_w[i];
+    s_zk[i] = g_zig_k[i];
+  }
+  __syncthreads();
+  const unsigned int n = min(*Q.count, Q.cap);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  const unsigned int nwarps = gridDim.x * kFinWarps, warp_id = blockIdx.x * kFinWarps + wid;
+
+  // stage 1: up to 32 parked slots, each with at least one pending photo-electron
+  auto run_slow = [&](const SlowItem* items, int count) {
+    const bool live = lane < count;
+    SlowItem it = live ? items[lane] : SlowItem{0u, 0u, {0., 0., 0.}, 0u, 0u};
+    const FinCtx c = fin_resolve<SWEEP>(P0, Ap, live ? it.e : 0u);
+    const RunParams& P = *c.P;
+    const uint32_t e0 = uint32_t(c.ev), e1 = uint32_t(c.ev >> 32);
+    const u128 r = philox4x32_10_rk(e0, e1, it.j, STREAM_HIT, P.rk);
+    const u128 t = philox4x32_10_rk(e0, e1, it.j, STREAM_HIT2, P.rk);
+    double v0 = it.v[0], v1 = it.v[1], v2 = it.v[2];
+    uint32_t st = live ? it.st : 0u;
+#pragma unroll 1
+    while (__any_sync(0xffffffffu, st != 0u)) {
+      if (st != 0u) {
+        const int which = (st & 3u) ? 0 : ((st & 12u) ? 1 : 2);
+        int s1 = int((st >> (2 * which)) & 3u);
+        double sv = 0.;
+        if (s1 == PE_NEED_ZIG) {
+          uint32_t A, L;
+          pe_fields(r, which, A, L);
+          const double z = zig_finish(A, L, t.w, which == 0, e0, e1, 3u * it.j + uint32_t(which), STREAM_ZIG, uint32_t(P.seed),
+                                      uint32_t(P.seed >> 32));
+          s1 = pe_after_normal(P, t, which, A, z, sv);
+        }
+        if (s1 == PE_NEED_REDRAW) sv = pe_redraw_of(P, c.ev, it.j, which);
+        if (which == 0)
+          v0 = sv;
+        else if (which == 1)
+          v1 = sv;
+        else
+          v2 = sv;
+        st &= ~(3u << (2 * which));
+      }
+    }
+    if (live) fin_commit(P, *c.W, it.e, int(it.j) < c.nd, slot_valid(int(it.j), c.nd, c.nh - c.nd), v0, v1, v2);
+    __syncwarp();
+  };
+  // slots of events that draw efficiencies / coincidence windows: the full per-slot code
+  auto run_special = [&](const SlotEntry* ents, int count) {
+    const bool live = lane < count;
+    const SlotEntry en = live ? ents[lane] : SlotEntry{0u, 0u};
+    const FinCtx c = fin_resolve<SWEEP>(P0, Ap, en.e);
+    const RunParams& P = *c.P;
+    const Work& W = *c.W;
+    const uint64_t idx = en.e;
+    finish_slot(P, c.nh, c.nd, en.j, c.ev, s_zk, s_zw, live, [&](double a, bool coin) {
+      if (a > P.det.sPEthr && coin) {
+        atomicAdd(&reinterpret_cast<unsigned long long*>(W.area)[idx], (unsigned long long)__double2ll_rn(a * NB_AREA_FX));
+        atomicAdd(&W.spike[idx], 1);
+      }
+    });
+    __syncwarp();
+  };
+
+  int nslow = 0, nspec = 0;  // warp-uniform fills of the two per-warp queues
+  for (unsigned int base = warp_id * 32u; base < n; base += nwarps * 32u) {
+    const unsigned int i = base + lane;
+    const SlotEntry en = i < n ? Q.entries[i] : SlotEntry{0xffffffffu, 0u};
+    const bool live = en.j != 0xffffffffu;  // (sentinel: an entry reserved but never written, see k_hits)
+    const FinCtx c = fin_resolve<SWEEP>(P0, Ap, live ? en.e : 0u);
+    const RunParams& P = *c.P;
+    const bool special = live && (P.det.sPEeff < 1. || !(c.nh > P.det.coinLevel));
+    bool slow = false;
+    SlowItem it{en.e, en.j, {0., 0., 0.}, 0u, 0u};
+    if (live && !special) {
+      const uint32_t e0 = uint32_t(c.ev), e1 = uint32_t(c.ev >> 32);
+      const u128 r = philox4x32_10_rk(e0, e1, en.j, STREAM_HIT, P.rk);
+      const u128 t = philox4x32_10_rk(e0, e1, en.j, STREAM_HIT2, P.rk);
+      const int nv = slot_valid(int(en.j), c.nd, c.nh - c.nd);
+#pragma unroll
+      for (int which = 0; which < 3; ++which) {
+        if (which < nv) {
+          uint32_t A, L;
+          pe_fields(r, which, A, L);
+          double z, sv = 0.;
+          int s1 = PE_NEED_ZIG;
+          if (zig_fast(A, L, s_zk, s_zw, z)) s1 = pe_after_normal(P, t, which, A, z, sv);
+          it.v[which] = sv;
+          it.st |= uint32_t(s1) << (2 * which);
+        }
+      }
+      if (it.st == 0u)
+        fin_commit(P, *c.W, en.e, int(en.j) < c.nd, nv, it.v[0], it.v[1], it.v[2]);
+      else
+        slow = true;
+    }
+    const unsigned ms = __ballot_sync(0xffffffffu, special);
+    if (ms) {
+      if (special) s_spec[wid][nspec + __popc(ms & lt)] = en;
+      nspec += __popc(ms);
+      __syncwarp();
+      if (nspec >= 32) {
+        nspec -= 32;
+        run_special(&s_spec[wid][nspec], 32);
+      }
+    }
+    const unsigned mq = __ballot_sync(0xffffffffu, slow);
+    if (mq) {
+      if (slow) s_slow[wid][nslow + __popc(mq & lt)] = it;
+      nslow += __popc(mq);
+      __syncwarp();
+      if (nslow >= 32) {
+        nslow -= 32;
+        run_slow(&s_slow[wid][nslow], 32);
+      }
+    }
+  }
+  if (nspec > 0) run_special(&s_spec[wid][0], nspec);
+  if (nslow > 0) run_slow(&s_slow[wid][0], nslow);
+}
+
+__global__ void __launch_bounds__(kFinBlock) k_hits_finish(const __grid_constant__ RunParams P, const HitQueue Q) {
+  hits_finish_body<false>(&P, nullptr, Q);
+}
+__global__ void __launch_bounds__(kFinBlock) k_hits_finish_sweep(const __grid_constant__ SweepArgs A, const HitQueue Q) {
+  hits_finish_body<true>(nullptr, &A, Q);
+}
+
+// `count` (<= 32) entries of a warp's queue to the deferred finisher's queue (e made a workspace index); false when
+// they have to be finished in place: detectors whose every slot is special, or a full queue (the part of a
+// reservation that still lies below the capacity is filled with sentinels the finisher skips)
+NB_D bool queue_push(const HitQueue& Q, bool in_place, const SlotEntry* q, int count, int lane, uint32_t gbase) {
+  if (in_place) return false;
+  unsigned int at = 0;
+  if (lane == 0) at = atomicAdd(Q.count, (unsigned int)count);
+  at = __shfl_sync(0xffffffffu, at, 0);
+  const bool fits = at + (unsigned int)count <= Q.cap;
+  if (lane < count && at + lane < Q.cap) {
+    SlotEntry en = q[lane];
+    en.e += gbase;
+    if (!fits) en.j = 0xffffffffu;
+    Q.entries[at + lane] = en;
+  }
+  return fits;
 }
 
 // the body of k_hits / k_hits_sweep.  SWEEP = false: P0 is the launch's RunParams (kernel parameter, constant bank).
 // SWEEP = true: a group's RunParams is copied from A.params[point] into the shared sP whenever the block moves to
 // another grid point; n_events and the event ids come from the sweep's slot layout.
 template <bool SWEEP>
-NB_D void hits_body(const RunParams* P0, const SweepArgs* Ap, RunParams* sP, unsigned int* __restrict__ next_group) {
+NB_D void hits_body(const RunParams* P0, const SweepArgs* Ap, RunParams* sP, unsigned int* __restrict__ next_group,
+                    const HitQueue Q) {
   const RunParams& P = SWEEP ? *sP : *P0;
   const SweepArgs& A = *Ap;  // dereferenced in the sweep instantiation only
   __shared__ int s_ppref[kHitGroup + 1];  // slot-count prefix: the flattened work items
@@ -666,17 +921,18 @@ NB_D void hits_body(const RunParams* P0, const SweepArgs* Ap, RunParams* sP, uns
         __syncwarp();
         if (qcount >= 32) {
           qcount -= 32;
-#ifndef NB_HITS_DROP_SLOW  // timing experiment only: the fast path alone (queued slots are lost)
-          hits_finish_slow(P, s_nh, s_nd, s_area, s_spike, ev0, &s_q[wid][qcount], 32, lane, s_zk, s_zw);
-#endif
+          // hand the 32 entries at [qcount, qcount + 32) to the deferred finisher
+          if (!queue_push(Q, all_special, &s_q[wid][qcount], 32, lane, uint32_t(gbase)))
+            hits_finish_slow(P, s_nh, s_nd, s_area, s_spike, ev0, &s_q[wid][qcount], 32, lane, s_zk, s_zw);
         }
       }
       ++j;
       ++h;
     }
-#ifndef NB_HITS_DROP_SLOW
-    if (qcount > 0) hits_finish_slow(P, s_nh, s_nd, s_area, s_spike, ev0, &s_q[wid][0], qcount, lane, s_zk, s_zw);
-#endif
+    if (qcount > 0) {  // the group's leftovers
+      if (!queue_push(Q, all_special, &s_q[wid][0], qcount, lane, uint32_t(gbase)))
+        hits_finish_slow(P, s_nh, s_nd, s_area, s_spike, ev0, &s_q[wid][0], qcount, lane, s_zk, s_zw);
+    }
     if (h1 > h0) {
       smem_add64(&s_area[e], a_fx - (unsigned long long)a_spike * NB_AREA_MAGIC_BITS);
       atomicAdd(&s_spike[e], a_spike);
@@ -687,7 +943,7 @@ NB_D void hits_body(const RunParams* P0, const SweepArgs* Ap, RunParams* sP, uns
       const int i = jj * kHitBlock + tid;  // coalesced
       const uint64_t idx = gbase + i;
       if (idx < n_valid) {
-        W.area[idx] = double(s_area[i]) * (1. / NB_AREA_FX);
+        reinterpret_cast<unsigned long long*>(W.area)[idx] = s_area[i];  // 2^-32 phe; the finisher adds to it
         W.spike[idx] = int(s_spike[i]);
         W.nphe[idx] = s_nh[i] + s_nd[i];
       }
@@ -698,14 +954,14 @@ NB_D void hits_body(const RunParams* P0, const SweepArgs* Ap, RunParams* sP, uns
 
 
 __global__ void __launch_bounds__(kHitBlock, NB_HIT_MINB)
-    k_hits(const __grid_constant__ RunParams P, unsigned int* __restrict__ next_group) {
-  hits_body<false>(&P, nullptr, nullptr, next_group);
+    k_hits(const __grid_constant__ RunParams P, unsigned int* __restrict__ next_group, const HitQueue Q) {
+  hits_body<false>(&P, nullptr, nullptr, next_group, Q);
 }
 
 __global__ void __launch_bounds__(kHitBlock, NB_HIT_MINB)
-    k_hits_sweep(const __grid_constant__ SweepArgs A, unsigned int* __restrict__ next_group) {
+    k_hits_sweep(const __grid_constant__ SweepArgs A, unsigned int* __restrict__ next_group, const HitQueue Q) {
   __shared__ __align__(16) RunParams sP;
-  hits_body<true>(nullptr, &A, &sP, next_group);
+  hits_body<true>(nullptr, &A, &sP, next_group, Q);
 }
 
 // one event of k_post.  s_band / s_h2: the block's shared-memory band accumulator (band_smem) ; gband: the global
@@ -732,7 +988,7 @@ NB_D void post_body(const RunParams& P, const Work& W, uint64_t idx, uint64_t gi
   S1Acc acc{0., 0, 0};
   if (pre.full) {
     if (nh > 0) {
-      acc.area = W.area[idx];
+      acc.area = double(reinterpret_cast<const unsigned long long*>(W.area)[idx]) * (1. / NB_AREA_FX);
       acc.spike = W.spike[idx];
       acc.nphe = W.nphe[idx];
     }
@@ -784,29 +1040,30 @@ NB_D void post_body(const RunParams& P, const Work& W, uint64_t idx, uint64_t gi
   }
   if (P.write_soa) {
     const SoaDev& o = P.soa;
-    if (o.energy_kev) o.energy_kev[gidx] = keV_true;
-    if (o.x_mm) o.x_mm[gidx] = px;
-    if (o.y_mm) o.y_mm[gidx] = py;
-    if (o.z_mm) o.z_mm[gidx] = pz;
-    if (o.field) o.field[gidx] = field;
-    if (o.driftTime) o.driftTime[gidx] = dt;
-    if (o.smear_x) o.smear_x[gidx] = sx;
-    if (o.smear_y) o.smear_y[gidx] = sy;
+    const bool f32 = P.write_soa == 2;
+    if (o.energy_kev) soa_put(o.energy_kev, gidx, keV_true, f32);
+    if (o.x_mm) soa_put(o.x_mm, gidx, px, f32);
+    if (o.y_mm) soa_put(o.y_mm, gidx, py, f32);
+    if (o.z_mm) soa_put(o.z_mm, gidx, pz, f32);
+    if (o.field) soa_put(o.field, gidx, field, f32);
+    if (o.driftTime) soa_put(o.driftTime, gidx, dt, f32);
+    if (o.smear_x) soa_put(o.smear_x, gidx, sx, f32);
+    if (o.smear_y) soa_put(o.smear_y, gidx, sy, f32);
     if (o.photons) o.photons[gidx] = W.photons[idx];
     if (o.electrons) o.electrons[gidx] = Ne;
     if (o.ions) o.ions[gidx] = W.ions[idx];
     if (o.excitons) o.excitons[gidx] = W.excitons[idx];
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
-      if (o.s1[k]) o.s1[k][gidx] = scint[k];
-      if (o.s2[k]) o.s2[k][gidx] = scint2[k];
+      if (o.s1[k]) soa_put(o.s1[k], gidx, scint[k], f32);
+      if (o.s2[k]) soa_put(o.s2[k], gidx, scint2[k], f32);
     }
-    if (o.signal1) o.signal1[gidx] = signal1;
-    if (o.signal2) o.signal2[gidx] = signal2;
-    if (o.signalE) o.signalE[gidx] = cli ? signalE : keV;
-    if (o.Nph_mean) o.Nph_mean[gidx] = y.Nph;
-    if (o.Ne_mean) o.Ne_mean[gidx] = y.Ne;
-    if (o.keVee) o.keVee[gidx] = keVee;
+    if (o.signal1) soa_put(o.signal1, gidx, signal1, f32);
+    if (o.signal2) soa_put(o.signal2, gidx, signal2, f32);
+    if (o.signalE) soa_put(o.signalE, gidx, cli ? signalE : keV, f32);
+    if (o.Nph_mean) soa_put(o.Nph_mean, gidx, y.Nph, f32);
+    if (o.Ne_mean) soa_put(o.Ne_mean, gidx, y.Ne, f32);
+    if (o.keVee) soa_put(o.keVee, gidx, keVee, f32);
   }
 }
 
@@ -1080,7 +1337,7 @@ __global__ void __launch_bounds__(256) k_s1post(const __grid_constant__ RunParam
     S1Acc acc{0., 0, 0};
     if (pre.full) {
       if (nh > 0) {
-        acc.area = W.area[idx];
+        acc.area = double(reinterpret_cast<const unsigned long long*>(W.area)[idx]) * (1. / NB_AREA_FX);
         acc.spike = W.spike[idx];
         acc.nphe = W.nphe[idx];
       }
