@@ -325,6 +325,33 @@ int nb200_s1(nb200_ctx* ctx, const nb200_detector* det, const nb200_run_consts* 
              const int32_t* Nph, const double* pos, const double* energy, uint64_t seed, uint64_t first_event,
              int mem_kind, double* out);
 
+/* The width model of GetQuanta as a call of its own: replaces NESTcalc::RecombOmegaNR (NEST.cpp:164-171),
+ * RecombOmegaER (:173-225) and FanoER (:227-246) for n records (efield [V/cm], elecFrac, numQuanta).
+ * out [3][n] = omega_NR, omega_ER, Fano_ER.  NB200_EPHYSICS where the reference throws (fewer than 13 width
+ * parameters; NRERWidthsParam[9] > [8]). */
+int nb200_widths(nb200_ctx* ctx, const nb200_detector* det, const nb200_model* model, size_t n, const double* efield,
+                 const double* elecFrac, const double* numQuanta, double density, int mem_kind, double* out);
+
+/* Replaces NESTcalc::GetSpike (NEST.cpp:2243-2268; NEST.hh:345) for n records: pos [3][n] = the dx, dy, dz the
+ * reference takes [mm], scint [9][n] = the scintillation[] GetS1 returned; rc->vD_middle is the reference's dS_mid.
+ * out [2][n] = smeared spike count, and the same corrected to the detector centre.  Record i draws from
+ * Philox(seed; event first_event + i). */
+int nb200_spike(nb200_ctx* ctx, const nb200_detector* det, const nb200_run_consts* rc, size_t n, const double* pos,
+                const double* scint, uint64_t seed, uint64_t first_event, int mem_kind, double* out);
+
+/* Replaces NESTcalc::xyResolution (NEST.cpp:2699-2736; NEST.hh:404) for n records: true x, y [mm] and the S2
+ * size A_top [phd] -> out [2][n] smeared x, y.  Record i draws from Philox(seed; event first_event + i). */
+int nb200_xy_resolution(nb200_ctx* ctx, const nb200_detector* det, size_t n, const double* x, const double* y,
+                        const double* A_top, uint64_t seed, uint64_t first_event, int mem_kind, double* out);
+
+/* The energy samplers alone: replaces TestSpectra::CH3T_spectrum / C14_spectrum / B8_spectrum / PowLawFit_spectrum
+ * (AmBe) / Cf_spectrum / DD_spectrum / ppSolar_spectrum / atmNu_spectrum / WIMP_spectrum (src/TestSpectra.cpp:31-499,
+ * include/NEST/TestSpectra.hh:50-69) and the flat / Gauss / exponential defaults of execNEST.cpp:769-781 for n
+ * draws: src->kind, eMin, eMax, par[] (and the WIMP table) as for nb200_run; out [n] keV.  Draw i is the energy
+ * event first_event + i of an nb200_run with the same source and seed would get. */
+int nb200_spectrum(nb200_ctx* ctx, const nb200_source* src, size_t n, uint64_t seed, uint64_t first_event,
+                   int mem_kind, double* out);
+
 /* The per-event chain: replaces the loop body of execNEST() (execNEST.cpp:676-1414)
  * and of runNESTvec() (:357-406) for event ids [first_event, first_event+n).
  * soa and hist may each be NULL.  hist is ACCUMULATED into (caller zeroes it). */

@@ -102,7 +102,7 @@ class BandHist(C.Structure):
 EXPORTS = [
     "nb200_abi_version", "nb200_sizeof", "nb200_create", "nb200_destroy", "nb200_last_error", "nb200_set_stream",
     "nb200_synchronize", "nb200_detector_builtin", "nb200_model_default", "nb200_analysis_default",
-    "nb200_prepare", "nb200_wimp_prep", "nb200_wimp_prep_iso", "nb200_wimp_drate", "nb200_poisson", "nb200_yields", "nb200_quanta", "nb200_s2", "nb200_s1", "nb200_run", "nb200_run_sweep", "nb200_run_async",
+    "nb200_prepare", "nb200_wimp_prep", "nb200_wimp_prep_iso", "nb200_wimp_drate", "nb200_poisson", "nb200_yields", "nb200_quanta", "nb200_s2", "nb200_s1", "nb200_widths", "nb200_spike", "nb200_xy_resolution", "nb200_spectrum", "nb200_run", "nb200_run_sweep", "nb200_run_async",
     "nb200_band_reset", "nb200_band_attach", "nb200_fp64_peak", "nb200_timing_enable", "nb200_timing_read", "nb200_se_stats", "nb200_band_fetch", "nb200_band_device_buffer", "nb200_allreduce_hist",
     "nb200_band_hist_bytes", "nb200_band_scale_x", "nb200_band_finalize", "nb200_band_chi2", "nb200_band_leakage", "nb200_band_fit_gauss", "nb200_band_leakage_gauss", "nb200_hist_fit", "nb200_hist_fit_cov", "nb200_band_leakage_skew_cov", "nb200_graph_fit", "nb200_band_leakage_skew", "nb200_lar", "nb200_launch_count",
     "nb200_debug_hitmath", "nb200_debug_binomial", "nb200_debug_normal", "nb200_debug_binomial_fixed",
@@ -159,6 +159,11 @@ def lib():
                            C.c_uint64, C.c_int, vp]
     L.nb200_s1.argtypes = [vp, C.POINTER(Detector), C.POINTER(RunConsts), C.c_int, C.c_size_t, vp, vp, vp, C.c_uint64,
                            C.c_uint64, C.c_int, vp]
+    L.nb200_widths.argtypes = [vp, C.POINTER(Detector), C.POINTER(Model), C.c_size_t, vp, vp, vp, C.c_double, C.c_int, vp]
+    L.nb200_spike.argtypes = [vp, C.POINTER(Detector), C.POINTER(RunConsts), C.c_size_t, vp, vp, C.c_uint64, C.c_uint64,
+                              C.c_int, vp]
+    L.nb200_xy_resolution.argtypes = [vp, C.POINTER(Detector), C.c_size_t, vp, vp, vp, C.c_uint64, C.c_uint64, C.c_int, vp]
+    L.nb200_spectrum.argtypes = [vp, C.POINTER(Source), C.c_size_t, C.c_uint64, C.c_uint64, C.c_int, vp]
     run_args = [vp, C.POINTER(Detector), C.POINTER(Model), C.POINTER(Analysis), C.POINTER(Source),
                 C.POINTER(RunConsts), C.c_uint64, C.c_uint64, C.c_uint64]
     L.nb200_run.argtypes = run_args + [C.POINTER(SoaOut), C.POINTER(BandHist)]
@@ -483,6 +488,40 @@ class Context:
         self._check(lib().nb200_quanta(self.h, C.byref(det), C.byref(mo), n, _dptr(y), density, seed, first_event,
                                        MEM_HOST, _dptr(qi), _dptr(qd)))
         return qi, qd
+
+    def widths(self, det, mo, efield, elecFrac, numQuanta, density):
+        """RecombOmegaNR / RecombOmegaER / FanoER for n records -> [3][n]"""
+        f = np.ascontiguousarray(efield, np.float64)
+        e = np.ascontiguousarray(np.broadcast_to(elecFrac, f.shape), np.float64)
+        q = np.ascontiguousarray(np.broadcast_to(numQuanta, f.shape), np.float64)
+        out = np.zeros((3, f.size))
+        self._check(lib().nb200_widths(self.h, C.byref(det), C.byref(mo), f.size, _dptr(f), _dptr(e), _dptr(q), density,
+                                       MEM_HOST, _dptr(out)))
+        return out
+
+    def spike(self, det, rc, pos, scint, seed, first_event=0):
+        """GetSpike for n records: pos [3][n], scint [9][n] -> [2][n]"""
+        p = np.ascontiguousarray(pos, np.float64)
+        sc = np.ascontiguousarray(scint, np.float64)
+        n = p.shape[1]
+        out = np.zeros((2, n))
+        self._check(lib().nb200_spike(self.h, C.byref(det), C.byref(rc), n, _dptr(p), _dptr(sc), seed, first_event,
+                                      MEM_HOST, _dptr(out)))
+        return out
+
+    def xy_resolution(self, det, x, y, A_top, seed, first_event=0):
+        x = np.ascontiguousarray(x, np.float64)
+        y = np.ascontiguousarray(np.broadcast_to(y, x.shape), np.float64)
+        a = np.ascontiguousarray(np.broadcast_to(A_top, x.shape), np.float64)
+        out = np.zeros((2, x.size))
+        self._check(lib().nb200_xy_resolution(self.h, C.byref(det), x.size, _dptr(x), _dptr(y), _dptr(a), seed,
+                                              first_event, MEM_HOST, _dptr(out)))
+        return out
+
+    def spectrum(self, src, n, seed, first_event=0):
+        out = np.zeros(int(n))
+        self._check(lib().nb200_spectrum(self.h, C.byref(src), out.size, seed, first_event, MEM_HOST, _dptr(out)))
+        return out
 
     def s2(self, det, rc, Ne, pos, dt, field, seed, first_event=0):
         """GetS2 (Full) on the device for n records: Ne [n], pos [5][n] (truth x, y, z, smeared x, y), dt [n], field

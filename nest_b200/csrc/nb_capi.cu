@@ -209,6 +209,77 @@ int validate(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo, con
   return 0;
 }
 
+int check_device_error(nb200_ctx* c);
+
+// WIMP source: the spectrum table to device memory, WIMP_dRate(0) per isotope (TestSpectra.cpp:459, 466)
+int upload_wimp_source(nb200_ctx* c, const nb200_source* src, RunParams* P) {
+  if (src->kind != NB200_SRC_WIMP) return 0;
+  if (!src->wimp_base || !src->wimp_exponent) return fail(c, NB200_EINVAL, "WIMP source without nb200_wimp_prep table");
+  void* d = nullptr;
+  int r;
+  if ((r = upload_blob(c, src->wimp_base, sizeof(double) * 100, &d))) return r;
+  P->src.wimp_base = static_cast<const double*>(d);
+  if ((r = upload_blob(c, src->wimp_exponent, sizeof(double) * 100, &d))) return r;
+  P->src.wimp_exponent = static_cast<const double*>(d);
+  for (int k = 0; k < 9; ++k) {
+    bool ok;
+    P->wimp_dr0[k] = host::wimp_drate(0., src->wimp_mass, src->wimp_day, double(host::kXeIsotopes[k]), &ok);
+    if (!ok) return fail(c, NB200_EPHYSICS, "\tThe velocity integral in the WIMP generator broke!!!");
+  }
+  return 0;
+}
+
+// host <-> device staging of the small stage calls: inputs copied in, outputs copied back by finish()
+struct Staged {
+  nb200_ctx* c;
+  bool host;
+  std::vector<void*> owned;
+  struct Out {
+    void* host;
+    void* dev;
+    size_t bytes;
+  };
+  std::vector<Out> outs;
+  cudaError_t err = cudaSuccess;
+  Staged(nb200_ctx* c_, int mem_kind) : c(c_), host(mem_kind == NB200_MEM_HOST) {}
+  template <class T>
+  const T* in(const T* p, size_t count) {
+    if (!host || !p) return p;
+    void* d = nullptr;
+    if (err == cudaSuccess) err = cudaMalloc(&d, count * sizeof(T));
+    if (err == cudaSuccess) {
+      owned.push_back(d);
+      err = cudaMemcpyAsync(d, p, count * sizeof(T), cudaMemcpyHostToDevice, c->stream);
+    }
+    return static_cast<const T*>(d);
+  }
+  template <class T>
+  T* out(T* p, size_t count) {
+    if (!host || !p) return p;
+    void* d = nullptr;
+    if (err == cudaSuccess) err = cudaMalloc(&d, count * sizeof(T));
+    if (err == cudaSuccess) {
+      owned.push_back(d);
+      outs.push_back({p, d, count * sizeof(T)});
+    }
+    return static_cast<T*>(d);
+  }
+  int finish(int rc, const char* what) {
+    cudaError_t le = cudaGetLastError();
+    if (!rc && err != cudaSuccess) rc = fail(c, NB200_ENOMEM, cudaGetErrorString(err));
+    if (!rc && le != cudaSuccess) rc = fail(c, NB200_ECUDA, std::string(what) + ": " + cudaGetErrorString(le));
+    if (!rc)
+      for (auto& o : outs) {
+        cudaError_t e = cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, c->stream);
+        if (e != cudaSuccess) rc = fail(c, NB200_ECUDA, cudaGetErrorString(e));
+      }
+    if (!rc) rc = check_device_error(c);  // synchronises
+    else cudaStreamSynchronize(c->stream);
+    for (void* q : owned) cudaFree(q);
+    return rc;
+  }
+};
+
 // Everything the kernel needs beyond the caller's PODs
 int build_params(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo, const nb200_analysis* ana,
                  const nb200_source* src, const nb200_run_consts* rc, uint64_t seed, uint64_t first,
@@ -342,18 +413,7 @@ int build_params(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo,
     }
     P->dpe_alias = static_cast<const uint2*>(dtab);
   }
-  if (src->kind == NB200_SRC_WIMP) {
-    void* d = nullptr;
-    if ((r = upload_blob(c, src->wimp_base, sizeof(double) * 100, &d))) return r;
-    P->src.wimp_base = static_cast<const double*>(d);
-    if ((r = upload_blob(c, src->wimp_exponent, sizeof(double) * 100, &d))) return r;
-    P->src.wimp_exponent = static_cast<const double*>(d);
-    for (int k = 0; k < 9; ++k) {
-      bool ok;
-      P->wimp_dr0[k] = host::wimp_drate(0., src->wimp_mass, src->wimp_day, double(host::kXeIsotopes[k]), &ok);
-      if (!ok) return fail(c, NB200_EPHYSICS, "\tThe velocity integral in the WIMP generator broke!!!");
-    }
-  }
+  if ((r = upload_wimp_source(c, src, P))) return r;
   P->seed = seed;
   philox_round_keys(seed, P->rk);
   P->first_event = first;
@@ -429,7 +489,7 @@ void launch_hits(nb200_ctx* c, const RunParams& Q, uint64_t m, const HitQueue& h
   const unsigned g_hits = unsigned(std::min<uint64_t>((m + kHitGroup - 1) / kHitGroup, sm * c->occ_hits));  // persistent
   cudaMemsetAsync(c->d_err + 1, 0, 2 * sizeof(int), c->stream);
   k_hits<<<g_hits, kHitBlock, kHitDynSmem, c->stream>>>(Q, reinterpret_cast<unsigned int*>(c->d_err + 1), hq);
-  k_hits_finish<<<unsigned(sm * 16), kFinBlock, 0, c->stream>>>(Q, hq);
+  k_hits_finish<<<unsigned(sm * NB_FIN_MINB * 2), kFinBlock, 0, c->stream>>>(Q, hq);
 }
 
 // k_pre -> k_hits -> k_post over the call's events in chunks of the workspace size
@@ -1143,6 +1203,135 @@ int nb200_s1(nb200_ctx* c, const nb200_detector* det, const nb200_run_consts* rc
   return r;
 }
 
+// ---- the remaining NESTcalc model methods as stage calls -------------------------------------------------------
+
+int nb200_widths(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo, size_t n, const double* efield,
+                 const double* elecFrac, const double* numQuanta, double density, int mem_kind, double* out) {
+  if (!c) return NB200_EINVAL;
+  if (!det || !mo || !efield || !elecFrac || !numQuanta || !out) return fail(c, NB200_EINVAL, "null argument");
+  if (mo->n_widths < 13)
+    return fail(c, NB200_EPHYSICS, "ERROR: You need a minimum of 13 free parameters for the resolution model.");
+  if (mo->NRERWidthsParam[9] > mo->NRERWidthsParam[8])  // RecombOmegaER's throw, NEST.cpp:183-184
+    return fail(c, NB200_EPHYSICS,
+                "Low-E r-fluct Gauss peak's width greater than centroid. This is physically wrong so "
+                "please check your inputs, in NRERWidthsParam: they must be in the old wrong order.");
+  if (n == 0) return 0;
+  NB_CUDA(c, cudaSetDevice(c->device));
+  Staged st(c, mem_kind);
+  WidthsParams P;
+  std::memset(&P, 0, sizeof P);
+  P.model = *mo;
+  P.inGas = det->inGas;
+  P.density = density;
+  P.n = n;
+  P.efield = st.in(efield, n);
+  P.elecFrac = st.in(elecFrac, n);
+  P.nq = st.in(numQuanta, n);
+  P.out = st.out(out, 3 * n);
+  if (st.err == cudaSuccess) {
+    k_widths<<<unsigned(std::min<uint64_t>((n + 255) / 256, uint64_t(c->sm_count) * 8)), 256, 0, c->stream>>>(P);
+    ++c->launches;
+  }
+  return st.finish(0, "k_widths");
+}
+
+namespace {
+// RunParams for the stage calls that need the detector and the per-run constants but no source / analysis
+int stage_params(nb200_ctx* c, const nb200_detector* det, const nb200_run_consts* rc, uint64_t seed, uint64_t first_event,
+                 uint64_t n, RunParams* P) {
+  nb200_model mo;
+  nb200_model_default(1, &mo);
+  nb200_analysis ana;
+  nb200_analysis_default(0, &ana);
+  nb200_source src;
+  std::memset(&src, 0, sizeof src);
+  src.kind = NB200_SRC_MONO;
+  src.species = NB200_beta;
+  src.eMin = src.eMax = 1.;
+  src.fixed_pos = 1;
+  src.inField = rc->field >= 0. ? rc->field : 0.;
+  return build_params(c, det, &mo, &ana, &src, rc, seed, first_event, n, P);
+}
+}  // namespace
+
+int nb200_spike(nb200_ctx* c, const nb200_detector* det, const nb200_run_consts* rc, size_t n, const double* pos,
+                const double* scint, uint64_t seed, uint64_t first_event, int mem_kind, double* out) {
+  if (!c) return NB200_EINVAL;
+  if (!det || !rc || !pos || !scint || !out) return fail(c, NB200_EINVAL, "null argument");
+  if (n == 0) return 0;
+  NB_CUDA(c, cudaSetDevice(c->device));
+  RunParams P;
+  int r = stage_params(c, det, rc, seed, first_event, n, &P);
+  if (r) return r;
+  Staged st(c, mem_kind);
+  SpikeArgs a;
+  a.n = n;
+  a.pos = st.in(pos, 3 * n);
+  a.scint = st.in(scint, 9 * n);
+  a.out = st.out(out, 2 * n);
+  if (st.err == cudaSuccess) {
+    k_spike<<<unsigned(std::min<uint64_t>((n + 255) / 256, uint64_t(c->sm_count) * 8)), 256, 0, c->stream>>>(P, a);
+    ++c->launches;
+  }
+  return st.finish(0, "k_spike");
+}
+
+int nb200_xy_resolution(nb200_ctx* c, const nb200_detector* det, size_t n, const double* x, const double* y,
+                        const double* A_top, uint64_t seed, uint64_t first_event, int mem_kind, double* out) {
+  if (!c) return NB200_EINVAL;
+  if (!det || !x || !y || !A_top || !out) return fail(c, NB200_EINVAL, "null argument");
+  if (n == 0) return 0;
+  NB_CUDA(c, cudaSetDevice(c->device));
+  RunParams P;
+  std::memset(&P, 0, sizeof P);
+  P.det = *det;
+  int r;
+  if ((r = upload_map(c, &P.det.FitTBA))) return r;
+  P.det.FitS1.lut = P.det.FitS2.lut = P.det.FitEF.lut = nullptr;  // not read by xyResolution
+  P.seed = seed;
+  P.first_event = first_event;
+  Staged st(c, mem_kind);
+  XyArgs a;
+  a.n = n;
+  a.x = st.in(x, n);
+  a.y = st.in(y, n);
+  a.A_top = st.in(A_top, n);
+  a.out = st.out(out, 2 * n);
+  if (st.err == cudaSuccess) {
+    k_xyres<<<unsigned(std::min<uint64_t>((n + 255) / 256, uint64_t(c->sm_count) * 8)), 256, 0, c->stream>>>(P, a);
+    ++c->launches;
+  }
+  return st.finish(0, "k_xyres");
+}
+
+int nb200_spectrum(nb200_ctx* c, const nb200_source* src, size_t n, uint64_t seed, uint64_t first_event, int mem_kind,
+                   double* out) {
+  if (!c) return NB200_EINVAL;
+  if (!src || !out) return fail(c, NB200_EINVAL, "null argument");
+  if (src->kind < NB200_SRC_MONO || src->kind > NB200_SRC_ATMNU || src->kind == NB200_SRC_LIST)
+    return fail(c, NB200_EINVAL, "nb200_spectrum: not a sampled source kind");
+  if (n == 0) return 0;
+  NB_CUDA(c, cudaSetDevice(c->device));
+  c->call_memo.clear();
+  RunParams P;
+  std::memset(&P, 0, sizeof P);
+  P.src = *src;
+  int r = upload_wimp_source(c, src, &P);
+  if (r) return r;
+  P.seed = seed;
+  philox_round_keys(seed, P.rk);
+  P.first_event = first_event;
+  P.n_events = n;
+  P.species = src->species;
+  Staged st(c, mem_kind);
+  double* dout = st.out(out, n);
+  if (st.err == cudaSuccess) {
+    k_spectrum<<<unsigned(std::min<uint64_t>((n + 255) / 256, uint64_t(c->sm_count) * 8)), 256, 0, c->stream>>>(P, dout);
+    ++c->launches;
+  }
+  return st.finish(0, "k_spectrum");
+}
+
 // ---- the chain ---------------------------------------------------------------------------
 
 size_t nb200_band_hist_bytes(const nb200_analysis* a) { return a ? band_word_count(a) * 8 : 0; }
@@ -1523,7 +1712,7 @@ int nb200_run_sweep(nb200_ctx* c, size_t n_points, const nb200_detector* dets, c
     k_pre_sweep<<<g_pre, kPreBlock, 0, c->stream>>>(A, c->d_err);
     cudaMemsetAsync(c->d_err + 1, 0, 2 * sizeof(int), c->stream);
     k_hits_sweep<<<g_hits, kHitBlock, kHitDynSmem, c->stream>>>(A, reinterpret_cast<unsigned int*>(c->d_err + 1), hq);
-    k_hits_finish_sweep<<<unsigned(sm * 16), kFinBlock, 0, c->stream>>>(A, hq);
+    k_hits_finish_sweep<<<unsigned(sm * NB_FIN_MINB * 2), kFinBlock, 0, c->stream>>>(A, hq);
     k_post_sweep<<<g_post, kPostBlock, smem, c->stream>>>(A, band_in_smem, c->d_err);
     NB_CUDA(c, cudaGetLastError());
     c->launches += 4;

@@ -544,6 +544,9 @@ struct SlowItem {
   uint32_t st;  // status of photo-electron k in bits [2k+1 : 2k]
   uint32_t pad;
 };
+#ifndef NB_FIN_MINB
+#define NB_FIN_MINB 8
+#endif
 constexpr int kFinBlock = 128;
 constexpr int kFinWarps = kFinBlock / 32;
 
@@ -591,15 +594,12 @@ NB_D void fin_commit(const RunParams& P, const Work& W, uint64_t idx, bool dbl, 
 
 template <bool SWEEP>
 NB_D void hits_finish_body(const RunParams* P0, const SweepArgs* Ap, const HitQueue Q) {
-  __shared__ double s_zw[NB_ZIG_N];
-  __shared__ uint32_t s_zk[NB_ZIG_N];
+  // the kernel waits on device memory (queue entries, the events' hit counts, the atomics): it wants warps, not
+  // shared-memory tables -- the ziggurat layers are read through L1 from their global copies
+  const uint32_t* const s_zk = g_zig_k;
+  const double* const s_zw = g_zig_w;
   __shared__ __align__(8) SlowItem s_slow[kFinWarps][64];
   __shared__ __align__(8) SlotEntry s_spec[kFinWarps][64];
-  for (int i = threadIdx.x; i < NB_ZIG_N; i += kFinBlock) {
-    s_zw[i] = g_zig_w[i];
-    s_zk[i] = g_zig_k[i];
-  }
-  __syncthreads();
   const unsigned int n = min(*Q.count, Q.cap);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
@@ -716,10 +716,10 @@ NB_D void hits_finish_body(const RunParams* P0, const SweepArgs* Ap, const HitQu
   if (nslow > 0) run_slow(&s_slow[wid][0], nslow);
 }
 
-__global__ void __launch_bounds__(kFinBlock) k_hits_finish(const __grid_constant__ RunParams P, const HitQueue Q) {
+__global__ void __launch_bounds__(kFinBlock, NB_FIN_MINB) k_hits_finish(const __grid_constant__ RunParams P, const HitQueue Q) {
   hits_finish_body<false>(&P, nullptr, Q);
 }
-__global__ void __launch_bounds__(kFinBlock) k_hits_finish_sweep(const __grid_constant__ SweepArgs A, const HitQueue Q) {
+__global__ void __launch_bounds__(kFinBlock, NB_FIN_MINB) k_hits_finish_sweep(const __grid_constant__ SweepArgs A, const HitQueue Q) {
   hits_finish_body<true>(nullptr, &A, Q);
 }
 
@@ -1348,6 +1348,83 @@ __global__ void __launch_bounds__(256) k_s1post(const __grid_constant__ RunParam
     s1_epilogue(g, P, pre, acc, D, scint);
 #pragma unroll
     for (int k = 0; k < 9; ++k) a.out[k * a.stride + gi] = scint[k];
+  }
+}
+
+// ---- the remaining public model methods of NESTcalc as stage calls (NEST.hh:311-333, 345, 404) ---------------------
+// k_widths: RecombOmegaNR (NEST.cpp:164-171), RecombOmegaER (:173-225) and FanoER (:227-246) for n records;
+// out: 3 columns of n.
+struct WidthsParams {
+  nb200_model model;
+  int32_t inGas, _pad;
+  double density;
+  uint64_t n;
+  const double *efield, *elecFrac, *nq;
+  double* out;
+};
+__global__ void __launch_bounds__(256) k_widths(const __grid_constant__ WidthsParams P) {
+  const double* w = P.model.NRERWidthsParam;
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < P.n; i += uint64_t(gridDim.x) * blockDim.x) {
+    P.out[i] = recomb_omega_nr(P.elecFrac[i], w);
+    P.out[P.n + i] = recomb_omega_er(P.efield[i], P.elecFrac[i], P.nq[i], w, P.model.n_widths, nullptr);
+    P.out[2 * P.n + i] = fano_er(P.density, P.nq[i], P.efield[i], w, P.inGas != 0);
+  }
+}
+
+// k_spike: NESTcalc::GetSpike (NEST.cpp:2243-2268) for n records: pos 3 columns (dx, dy, dz), scint 9 columns
+// (scintillation[0..8] of GetS1); out 2 columns (smeared and position-corrected spike count).
+struct SpikeArgs {
+  uint64_t n;
+  const double *pos, *scint;
+  double* out;
+};
+__global__ void __launch_bounds__(256) k_spike(const __grid_constant__ RunParams P, const SpikeArgs a) {
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < a.n; i += uint64_t(gridDim.x) * blockDim.x) {
+    const double s4 = a.scint[4 * a.n + i], s5 = a.scint[5 * a.n + i], s6 = a.scint[6 * a.n + i], s7 = a.scint[7 * a.n + i];
+    double o0, o1;
+    if (s7 > NB_SPIKES_MAXM) {
+      o0 = s4;
+      o1 = s5;
+    } else {
+      Stream g;
+      g.init(P.seed, P.first_event + i, STREAM_POST);
+      o0 = zero_trunc_gauss(g, s6, (P.det.sPEres / 4.) * sqrt(fabs(s6)));
+      o1 = o0 / fit_s1(P.det.FitS1, a.pos[i], a.pos[a.n + i], a.pos[2 * a.n + i]) * P.s1_center;
+    }
+    a.out[i] = o0;
+    a.out[a.n + i] = o1;
+  }
+}
+
+// k_xyres: NESTcalc::xyResolution (NEST.cpp:2699-2736) for n records; out 2 columns (smeared x, y)
+struct XyArgs {
+  uint64_t n;
+  const double *x, *y, *A_top;
+  double* out;
+};
+__global__ void __launch_bounds__(256) k_xyres(const __grid_constant__ RunParams P, const XyArgs a) {
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < a.n; i += uint64_t(gridDim.x) * blockDim.x) {
+    Stream g;
+    g.init(P.seed, P.first_event + i, STREAM_MAIN);
+    double sx, sy;
+    xy_resolution(g, P.det, a.x[i], a.y[i], a.A_top[i], sx, sy);
+    a.out[i] = sx;
+    a.out[a.n + i] = sy;
+  }
+}
+
+// k_spectrum: the energy samplers alone (TestSpectra::*_spectrum, src/TestSpectra.cpp:31-499; flat / Gauss /
+// exponential of execNEST.cpp:769-781): n energies, the same device function and streams as the chain's k_pre
+__global__ void __launch_bounds__(256) k_spectrum(const __grid_constant__ RunParams P, double* __restrict__ out) {
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  const uint64_t n_pad = (P.n_events + 31) / 32 * 32;  // whole warps: the box rejections share candidates across a warp
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n_pad; i += stride) {
+    const bool active = i < P.n_events;
+    const uint64_t ie = active ? i : P.n_events - 1;
+    Stream g;
+    g.init(P.seed, P.first_event + ie, STREAM_MAIN);
+    const double keV = sample_energy(g, P, ie);
+    if (active) out[i] = keV;
   }
 }
 

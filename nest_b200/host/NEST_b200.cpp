@@ -179,6 +179,8 @@ vector<YieldResult> NESTcalc::GetYields(INTERACTION_TYPE species, const vector<d
   nb200_model m;
   fill_model(&m, NRYieldsParam, ERYieldsParam, default_NRERWidthsParam);
   m.er_model = -1;
+  const bool nrlike = species <= Cf || species == atmNu;
+  if (nrlike && nearlyEqual(massNum, 0.)) massNum = double(RandomGen::rndm()->SelectRanXeAtom());  // NEST.cpp:789-795
   m.massNum = massNum;
   m.atomNum = atomNum;
   const size_t n = energy.size();
@@ -195,6 +197,137 @@ YieldResult NESTcalc::GetYields(INTERACTION_TYPE species, double energy, double 
                                 const vector<double>& ERYieldsParam) {
   return GetYields(species, vector<double>{energy}, density, vector<double>{dfield}, massNum, atomNum,
                    NRYieldsParam, ERYieldsParam)[0];
+}
+
+// ---- the model methods behind GetYields: NEST.hh:256-303 ---------------------------------------------------------
+vector<YieldResult> NESTcalc::yields_by(int er_model, int species, const vector<double>& energy, double density,
+                                        const vector<double>& dfield, double massNum, double atomNum,
+                                        const vector<double>& nr, const vector<double>& er, double multFact) {
+  if (energy.size() != dfield.size()) throw runtime_error("GetYield*: energy and field lists differ in length");
+  nb200_model m;
+  fill_model(&m, nr, er, default_NRERWidthsParam);
+  m.er_model = er_model;
+  m.multFact = multFact;
+  m.massNum = massNum;
+  m.atomNum = atomNum;
+  const size_t n = energy.size();
+  vector<double> out(6 * n);
+  Device::check(nb200_yields(Device::get(), &flat(), &m, species, n, energy.data(), dfield.data(), density, NB200_MEM_HOST,
+                             out.data()));
+  vector<YieldResult> r(n);
+  for (size_t i = 0; i < n; ++i)
+    r[i] = YieldResult{out[i], out[n + i], out[2 * n + i], out[3 * n + i], out[4 * n + i], out[5 * n + i]};
+  return r;
+}
+vector<YieldResult> NESTcalc::GetYieldGamma(const vector<double>& energy, double density, const vector<double>& dfield,
+                                            double multFact) {
+  return yields_by(1, gammaRay, energy, density, dfield, 0., 0., default_NRYieldsParam, default_ERYieldsParam, multFact);
+}
+vector<YieldResult> NESTcalc::GetYieldERWeighted(const vector<double>& energy, double density, const vector<double>& dfield,
+                                                 const vector<double>& ERYieldsParam) {
+  return yields_by(2, NEST::beta, energy, density, dfield, 0., 0., default_NRYieldsParam, ERYieldsParam, 1.);
+}
+vector<YieldResult> NESTcalc::GetYieldNR(const vector<double>& energy, double density, const vector<double>& dfield,
+                                         double massNum, const vector<double>& NRYieldsParam) {
+  // massNum ~ 0: the reference draws one Xe isotope per call (NEST.cpp:789-795, RandomGen::SelectRanXeAtom); so here
+  if (nearlyEqual(massNum, 0.)) massNum = double(RandomGen::rndm()->SelectRanXeAtom());
+  return yields_by(-1, NR, energy, density, dfield, massNum, 0., NRYieldsParam, default_ERYieldsParam, 1.);
+}
+vector<YieldResult> NESTcalc::GetYieldIon(const vector<double>& energy, double density, const vector<double>& dfield,
+                                          double massNum, double atomNum, const vector<double>& NRYieldsParam) {
+  return yields_by(-1, ion, energy, density, dfield, massNum, atomNum, NRYieldsParam, default_ERYieldsParam, 1.);
+}
+vector<YieldResult> NESTcalc::GetYieldBetaGR(const vector<double>& energy, double density, const vector<double>& dfield,
+                                             const vector<double>& ERYieldsParam, double multFact) {
+  return yields_by(0, NEST::beta, energy, density, dfield, 0., 0., default_NRYieldsParam, ERYieldsParam, multFact);
+}
+YieldResult NESTcalc::GetYieldGamma(double energy, double density, double dfield, double multFact) {
+  return GetYieldGamma(vector<double>{energy}, density, vector<double>{dfield}, multFact)[0];
+}
+YieldResult NESTcalc::GetYieldERWeighted(double energy, double density, double dfield, const vector<double>& ERYieldsParam) {
+  return GetYieldERWeighted(vector<double>{energy}, density, vector<double>{dfield}, ERYieldsParam)[0];
+}
+YieldResult NESTcalc::GetYieldNR(double energy, double density, double dfield, double massNum,
+                                 const vector<double>& NRYieldsParam) {
+  return GetYieldNR(vector<double>{energy}, density, vector<double>{dfield}, massNum, NRYieldsParam)[0];
+}
+YieldResult NESTcalc::GetYieldIon(double energy, double density, double dfield, double massNum, double atomNum,
+                                  const vector<double>& NRYieldsParam) {
+  return GetYieldIon(vector<double>{energy}, density, vector<double>{dfield}, massNum, atomNum, NRYieldsParam)[0];
+}
+YieldResult NESTcalc::GetYieldKr83m(double energy, double density, double dfield, double maxTimeSeparation,
+                                    double minTimeSeparation) {
+  return yields_by(-1, Kr83m, vector<double>{energy}, density, vector<double>{dfield}, maxTimeSeparation, minTimeSeparation,
+                   default_NRYieldsParam, default_ERYieldsParam, 1.)[0];
+}
+YieldResult NESTcalc::GetYieldBetaGR(double energy, double density, double dfield, const vector<double>& ERYieldsParam,
+                                     double multFact) {
+  return GetYieldBetaGR(vector<double>{energy}, density, vector<double>{dfield}, ERYieldsParam, multFact)[0];
+}
+YieldResult NESTcalc::YieldResultValidity(YieldResult& res, const double energy, const double Wq_eV) {  // NEST.cpp:1254-1271
+  if (res.PhotonYield > energy / W_SCINT) res.PhotonYield = energy / W_SCINT;
+  if (res.ElectronYield > energy / W_SCINT) res.ElectronYield = energy / W_SCINT;
+  if (res.PhotonYield < 0.) res.PhotonYield = 0.;
+  if (res.ElectronYield < 0.) res.ElectronYield = 0.;
+  res.Lindhard = std::max(0., std::min(res.Lindhard, 1.));
+  if (energy < 0.001 * Wq_eV / res.Lindhard) {
+    res.PhotonYield = 0.;
+    res.ElectronYield = 0.;
+  }
+  return res;
+}
+
+// ---- the width model: NEST.cpp:164-246 -----------------------------------------------------------------------------
+vector<vector<double>> NESTcalc::Widths(const vector<double>& efield, const vector<double>& elecFrac,
+                                        const vector<double>& numQuanta, double density,
+                                        const vector<double>& NRERWidthsParam) {
+  const size_t n = efield.size();
+  if (elecFrac.size() != n || numQuanta.size() != n) throw runtime_error("Widths: lists differ in length");
+  nb200_model m;
+  fill_model(&m, default_NRYieldsParam, default_ERYieldsParam, NRERWidthsParam);
+  vector<double> out(3 * n);
+  Device::check(nb200_widths(Device::get(), &flat(), &m, n, efield.data(), elecFrac.data(), numQuanta.data(), density,
+                             NB200_MEM_HOST, out.data()));
+  vector<vector<double>> r(n, vector<double>(3));
+  for (size_t i = 0; i < n; ++i) r[i] = {out[i], out[n + i], out[2 * n + i]};
+  return r;
+}
+double NESTcalc::RecombOmegaNR(double elecFrac, const vector<double>& w) {
+  return Widths({100.}, {elecFrac}, {100.}, 2.9, w)[0][0];
+}
+double NESTcalc::RecombOmegaER(double efield, double elecFrac, double numQuanta, const vector<double>& w) {
+  return Widths({efield}, {elecFrac}, {numQuanta}, 2.9, w)[0][1];
+}
+double NESTcalc::FanoER(double density, double Nq_mean, double efield, const vector<double>& w) {
+  return Widths({efield}, {0.5}, {Nq_mean}, density, w)[0][2];
+}
+
+// ---- GetSpike / xyResolution: NEST.cpp:2243-2268, 2699-2736 -----------------------------------------------------------
+const vector<double>& NESTcalc::GetSpike(int, double dx, double dy, double dz, double, double dS_mid,
+                                         const vector<double>& origScint) {
+  if (origScint.size() < 9) throw runtime_error("GetSpike: origScint must hold scintillation[0..8]");
+  nb200_run_consts c = prepared(rc_field > -12345. ? rc_field : 180.);
+  c.vD_middle = dS_mid;
+  const double pos[3] = {dx, dy, dz};
+  double out[2] = {0., 0.};
+  Device::check(nb200_spike(Device::get(), &flat(), &c, 1, pos, origScint.data(), call_seed, call_index++, NB200_MEM_HOST, out));
+  newSpike[0] = out[0];
+  newSpike[1] = out[1];
+  return newSpike;
+}
+vector<vector<double>> NESTcalc::xyResolution(const vector<double>& x, const vector<double>& y, const vector<double>& A_top) {
+  const size_t n = x.size();
+  if (y.size() != n || A_top.size() != n) throw runtime_error("xyResolution: lists differ in length");
+  vector<double> out(2 * n);
+  Device::check(nb200_xy_resolution(Device::get(), &flat(), n, x.data(), y.data(), A_top.data(), call_seed, call_index,
+                                    NB200_MEM_HOST, out.data()));
+  call_index += n;
+  vector<vector<double>> r(n, vector<double>(2));
+  for (size_t i = 0; i < n; ++i) r[i] = {out[i], out[n + i]};
+  return r;
+}
+vector<double> NESTcalc::xyResolution(double xPos_mm, double yPos_mm, double A_top) {
+  return xyResolution(vector<double>{xPos_mm}, vector<double>{yPos_mm}, vector<double>{A_top})[0];
 }
 
 // ---- GetQuanta / FullCalculation: NEST.cpp:248-432, 17-40 ----------------------------------------------
@@ -354,6 +487,108 @@ LArYieldResult LArNEST::GetYields(LArInteraction species, double energy, double,
 }
 
 // ---- runNESTvec: execNEST.cpp:329-409 ----------------------------------------------------------------
+// ---- TestSpectra: include/NEST/TestSpectra.hh:38-73 over nb200_spectrum ------------------------------------------------
+namespace {
+struct SpectrumBlock {  // the energies drawn ahead for the scalar calls
+  int kind = -1;
+  double emin = 0., emax = 0., par[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
+  double wkey[4] = {0., 0., 0., 0.};  // WIMP: mass, day, xMax, base[0]
+  vector<double> e;
+  size_t next = 0;
+};
+SpectrumBlock g_block;
+uint64_t g_spec_seed = 0, g_spec_index = 0;
+}  // namespace
+
+void TestSpectra::SetSeed(uint64_t seed) {
+  g_spec_seed = seed;
+  g_spec_index = 0;
+  g_block.kind = -1;
+}
+vector<double> TestSpectra::spectrum_vec(int kind, size_t n, double emin, double emax, const vector<double>& par,
+                                         const WIMP_spectrum_prep* wprep, double mass, double day) {
+  nb200_source s;
+  std::memset(&s, 0, sizeof s);
+  s.kind = kind;
+  s.eMin = emin;
+  s.eMax = emax;
+  for (size_t i = 0; i < par.size() && i < 8; ++i) s.par[i] = par[i];
+  if (kind == NB200_SRC_WIMP) {
+    if (!wprep) throw runtime_error("WIMP_spectrum: no WIMP_spectrum_prep");
+    s.species = NB200_WIMP;
+    s.wimp_base = wprep->base;
+    s.wimp_exponent = wprep->exponent;
+    s.wimp_xMax = wprep->xMax;
+    s.wimp_divisor = wprep->divisor;
+    s.wimp_mass = mass;
+    s.wimp_day = day;
+  }
+  vector<double> out(n);
+  NEST::Device::check(nb200_spectrum(NEST::Device::get(), &s, n, g_spec_seed, g_spec_index, NB200_MEM_HOST, out.data()));
+  g_spec_index += n;
+  return out;
+}
+namespace {
+double next_energy(int kind, double emin, double emax, const vector<double>& par = {},
+                   const TestSpectra::WIMP_spectrum_prep* w = nullptr, double mass = 0., double day = 0.) {
+  SpectrumBlock& b = g_block;
+  double p8[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
+  for (size_t i = 0; i < par.size() && i < 8; ++i) p8[i] = par[i];
+  const double wk[4] = {mass, day, w ? w->xMax : 0., w ? w->base[0] : 0.};
+  const bool same = b.kind == kind && b.emin == emin && b.emax == emax && std::memcmp(b.par, p8, sizeof p8) == 0 &&
+                    std::memcmp(b.wkey, wk, sizeof wk) == 0;
+  if (!same || b.next >= b.e.size()) {
+    b.e = TestSpectra::spectrum_vec(kind, 16384, emin, emax, par, w, mass, day);
+    b.kind = kind;
+    b.emin = emin;
+    b.emax = emax;
+    std::memcpy(b.par, p8, sizeof p8);
+    std::memcpy(b.wkey, wk, sizeof wk);
+    b.next = 0;
+  }
+  return b.e[b.next++];
+}
+}  // namespace
+double TestSpectra::CH3T_spectrum(double emin, double emax) { return next_energy(NB200_SRC_CH3T, emin, emax); }
+double TestSpectra::C14_spectrum(double emin, double emax) { return next_energy(NB200_SRC_C14, emin, emax); }
+double TestSpectra::B8_spectrum(double emin, double emax) { return next_energy(NB200_SRC_B8, emin, emax); }
+double TestSpectra::AmBe_spectrum(double emin, double emax) { return PowLawFit_spectrum(emin, emax, -0.95351); }
+double TestSpectra::PowLawFit_spectrum(double emin, double emax, double exp) {
+  return next_energy(NB200_SRC_AMBE, emin, emax, {exp});
+}
+double TestSpectra::Cf_spectrum(double emin, double emax) { return next_energy(NB200_SRC_CF, emin, emax); }
+double TestSpectra::DD_spectrum(double xMin, double xMax, double expFall, double peakFrac, double peakMu, double peakSig,
+                                double peakSkew) {
+  return next_energy(NB200_SRC_DD, xMin, xMax, {expFall, peakFrac, peakMu, peakSig, peakSkew});
+}
+double TestSpectra::ppSolar_spectrum(double emin, double emax) { return next_energy(NB200_SRC_PPSOLAR, emin, emax); }
+double TestSpectra::atmNu_spectrum(double emin, double emax) { return next_energy(NB200_SRC_ATMNU, emin, emax); }
+double TestSpectra::WIMP_dRate(double ER, double mWimp, double day) {
+  // the reference draws a random Xe isotope inside (TestSpectra.cpp:278): natural abundances, host Philox stream
+  static const int iso[9] = {124, 126, 128, 129, 130, 131, 132, 134, 136};
+  static const double cum[9] = {0.090, 0.180, 2.100, 28.54, 32.62, 53.80, 80.69, 91.13, 100.};
+  const double u = double(nb200_poisson(1e9, g_spec_seed + 77 + g_spec_index++) % 1000000007ull) / 1000000007. * 100.;
+  int A = 136;
+  for (int k = 0; k < 9; ++k)
+    if (u <= cum[k]) {
+      A = iso[k];
+      break;
+    }
+  int ok = 1;
+  const double v = nb200_wimp_drate(ER, mWimp, day, A, &ok);
+  if (!ok) throw runtime_error("\tThe velocity integral in the WIMP generator broke!!!");
+  return v;
+}
+TestSpectra::WIMP_spectrum_prep TestSpectra::WIMP_prep_spectrum(double mass, double eStep, double day) {
+  WIMP_spectrum_prep p;
+  int rc = nb200_wimp_prep(mass, eStep, day, g_spec_seed, p.base, p.exponent, &p.integral, &p.xMax, &p.divisor);
+  if (rc) throw runtime_error(nb200_last_error(nullptr));
+  return p;
+}
+double TestSpectra::WIMP_spectrum(WIMP_spectrum_prep wprep, double mass, double day) {
+  return next_energy(NB200_SRC_WIMP, 0., 0., {}, &wprep, mass, day);
+}
+
 NESTObservableArray runNESTvec(VDetector* detector, INTERACTION_TYPE particleType, vector<double> eList,
                                vector<vector<double>> pos3dxyz, double inField, int seed,
                                vector<double> ERYieldsParam, vector<double> NRYieldsParam,

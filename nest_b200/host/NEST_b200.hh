@@ -79,6 +79,14 @@ class RandomGen {
     while (r <= 0.) r = rand_gauss(mean, sigma);
     return r;
   }
+  int SelectRanXeAtom() {  // src/RandomGen.cpp:159-182: natural abundances, cumulative per cent
+    const double iso = rand_uniform() * 100.;
+    static const double cum[8] = {0.090, 0.180, 2.100, 28.54, 32.62, 53.80, 80.69, 91.13};
+    static const int A[9] = {124, 126, 128, 129, 130, 131, 132, 134, 136};
+    for (int k = 0; k < 8; ++k)
+      if (iso <= cum[k]) return A[k];
+    return A[8];
+  }
   double rand_exponential(double half_life, double t_min = -1, double t_max = -1) {
     double r = rand_uniform(), r_min = 0, r_max = 1;
     if (t_min >= 0) r_min = 1 - std::exp(-t_min * std::log(2.) / half_life);
@@ -251,6 +259,55 @@ class NESTcalc {
                                      const std::vector<double>& NRYieldsParam = default_NRYieldsParam,
                                      const std::vector<double>& ERYieldsParam = default_ERYieldsParam);
 
+  // The model methods GetYields dispatches to (NEST.hh:256-303), public and virtual in the reference and called
+  // directly by nestpy and execNEST.cpp:1032-1048: each is nb200_yields with the matching switch; scalar as in the
+  // reference, and a vector form (one launch for n energies / fields).  GetYieldKr83m draws its decay-time
+  // separation (the reference: RandomGen) from the Philox stream of this object's next call number.
+  YieldResult GetYieldGamma(double energy, double density, double dfield, double multFact = 1.);
+  YieldResult GetYieldERWeighted(double energy, double density, double dfield,
+                                 const std::vector<double>& ERYieldsParam = default_ERYieldsParam);
+  YieldResult GetYieldNR(double energy, double density, double dfield, double massNum,
+                         const std::vector<double>& NRYieldsParam = default_NRYieldsParam);
+  YieldResult GetYieldIon(double energy, double density, double dfield, double massNum, double atomNum,
+                          const std::vector<double>& NRYieldsParam = default_NRYieldsParam);
+  YieldResult GetYieldKr83m(double energy, double density, double dfield, double maxTimeSeparation = 1000.,
+                            double minTimeSeparation = 300.);
+  YieldResult GetYieldBetaGR(double energy, double density, double dfield,
+                             const std::vector<double>& ERYieldsParam = default_ERYieldsParam, double multFact = 1.);
+  std::vector<YieldResult> GetYieldGamma(const std::vector<double>& energy, double density,
+                                         const std::vector<double>& dfield, double multFact = 1.);
+  std::vector<YieldResult> GetYieldERWeighted(const std::vector<double>& energy, double density,
+                                              const std::vector<double>& dfield,
+                                              const std::vector<double>& ERYieldsParam = default_ERYieldsParam);
+  std::vector<YieldResult> GetYieldNR(const std::vector<double>& energy, double density, const std::vector<double>& dfield,
+                                      double massNum, const std::vector<double>& NRYieldsParam = default_NRYieldsParam);
+  std::vector<YieldResult> GetYieldIon(const std::vector<double>& energy, double density, const std::vector<double>& dfield,
+                                       double massNum, double atomNum,
+                                       const std::vector<double>& NRYieldsParam = default_NRYieldsParam);
+  std::vector<YieldResult> GetYieldBetaGR(const std::vector<double>& energy, double density,
+                                          const std::vector<double>& dfield,
+                                          const std::vector<double>& ERYieldsParam = default_ERYieldsParam,
+                                          double multFact = 1.);
+  // NEST.cpp:1254-1271: the clamps every GetYield* applies to its result (in place, and returned)
+  YieldResult YieldResultValidity(YieldResult& res, const double energy, const double Wq_eV);
+  // NEST.cpp:164-246 on the device (nb200_widths): the width model GetQuanta uses; vector forms = one launch
+  double RecombOmegaNR(double elecFrac, const std::vector<double>& NRERWidthsParam = default_NRERWidthsParam);
+  double RecombOmegaER(double efield, double elecFrac, double numQuanta,
+                       const std::vector<double>& NRERWidthsParam = default_NRERWidthsParam);
+  double FanoER(double density, double Nq_mean, double efield,
+                const std::vector<double>& NRERWidthsParam = default_NRERWidthsParam);
+  // rows of {omega_NR, omega_ER, Fano_ER} for n (efield, elecFrac, numQuanta) records
+  std::vector<std::vector<double>> Widths(const std::vector<double>& efield, const std::vector<double>& elecFrac,
+                                          const std::vector<double>& numQuanta, double density,
+                                          const std::vector<double>& NRERWidthsParam = default_NRERWidthsParam);
+  // NEST.cpp:2243-2268 (NEST.hh:345) on the device: member scratch of two values, valid until the next call
+  const std::vector<double>& GetSpike(int Nph, double dx, double dy, double dz, double driftSpeed, double dS_mid,
+                                      const std::vector<double>& origScint);
+  // NEST.cpp:2699-2736 (NEST.hh:404) on the device; the vector form smears n positions in one launch (rows {x, y})
+  std::vector<double> xyResolution(double xPos_mm, double yPos_mm, double A_top);
+  std::vector<std::vector<double>> xyResolution(const std::vector<double>& xPos_mm, const std::vector<double>& yPos_mm,
+                                                const std::vector<double>& A_top);
+
   // NEST.cpp:248-432 on the device.  The reference draws from its process-wide RandomGen; here call number k of this
   // object draws from the Philox streams of event k under the seed given to SetSeed (default 0), so a sequence of
   // calls is reproducible and the vector form equals the same calls made one by one.
@@ -306,6 +363,10 @@ class NESTcalc {
   nb200_run_consts rc{};
   double rc_field = -12345.;
   std::vector<double> ionization = std::vector<double>(9, 0.), scintillation = std::vector<double>(9, 0.);
+  std::vector<double> newSpike = std::vector<double>(2, 0.);
+  std::vector<YieldResult> yields_by(int er_model, int species, const std::vector<double>& energy, double density,
+                                     const std::vector<double>& dfield, double massNum, double atomNum,
+                                     const std::vector<double>& nr, const std::vector<double>& er, double multFact);
 };
 
 // ---- liquid argon: include/NEST/LArNEST.hh:19-42, LArParameters.hh:27-34 ----
@@ -336,6 +397,44 @@ class LArNEST : public NESTcalc {
 };
 
 }  // namespace NEST
+
+// include/NEST/TestSpectra.hh:38-73: the energy samplers, static as in the reference.  Each scalar call hands out
+// the next energy of a block the device drew in one launch (nb200_spectrum; 16384 at a time, redrawn when the
+// arguments change), so that reference-style loops `for (...) keV = TestSpectra::CH3T_spectrum(0, 18.6)` do not pay a
+// launch per energy; the *_vec forms return n energies of one launch.  TestSpectra::SetSeed replaces
+// RandomGen::rndm()->SetSeed for these streams.  Gamma_spectrum (line tables of GammaHandler) and ZeplinBackground
+// are outside the hot path.
+class TestSpectra {
+ public:
+  TestSpectra() = default;
+  struct WIMP_spectrum_prep {
+    double base[100] = {1.};
+    double exponent[100] = {0.};
+    double integral = 0.;
+    double xMax = 0.;
+    double divisor = 1.;
+  };
+  WIMP_spectrum_prep wimp_spectrum_prep;
+
+  static double CH3T_spectrum(double emin, double emax);
+  static double C14_spectrum(double emin, double emax);
+  static double B8_spectrum(double emin, double emax);
+  static double AmBe_spectrum(double emin, double emax);
+  static double PowLawFit_spectrum(double emin, double emax, double exp);
+  static double Cf_spectrum(double emin, double emax);
+  static double DD_spectrum(double xMin, double xMax, double expFall, double peakFrac, double peakMu, double peakSig,
+                            double peakSkew);
+  static double ppSolar_spectrum(double emin, double emax);
+  static double atmNu_spectrum(double emin, double emax);
+  static double WIMP_dRate(double ER, double mWimp, double day);  // random Xe isotope per call, as the reference
+  static WIMP_spectrum_prep WIMP_prep_spectrum(double mass, double eStep, double day);
+  static double WIMP_spectrum(WIMP_spectrum_prep wprep, double mass, double day);
+  // n energies in one launch: kind = NB200_SRC_*, par = the source's shape parameters (nb200_source::par)
+  static std::vector<double> spectrum_vec(int kind, size_t n, double emin, double emax,
+                                          const std::vector<double>& par = {}, const WIMP_spectrum_prep* wprep = nullptr,
+                                          double mass = 0., double day = 0.);
+  static void SetSeed(uint64_t seed);
+};
 
 // include/NEST/execNEST.hh:10-65 (vectors filled by store_signals, :259-326)
 class NESTObservableArray {

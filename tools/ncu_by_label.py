@@ -24,7 +24,7 @@ def main():
     for fn in os.listdir(sassd):
         if fn.endswith(".cubin"):
             os.remove(os.path.join(sassd, fn))
-    subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "nest_b200", "csrc", "libnest_b200.so")], cwd=sassd,
+    subprocess.run(["cuobjdump", "-xelf", "all", os.environ.get("NB200_SASS_LIB", os.path.join(ROOT, "nest_b200", "csrc", "libnest_b200.so"))], cwd=sassd,
                    stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     cub = [fn for fn in os.listdir(sassd) if fn.endswith(".cubin")][0]
     sass = subprocess.run(["nvdisasm", "-g", cub], cwd=sassd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
