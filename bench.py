@@ -434,9 +434,12 @@ def main():
     # config 5: LArNEST NR / ER / alpha mean yields + default fluctuations over an (E, field) grid, device-resident in
     # and out (E and field in, 9 yield and 4 fluctuation columns out = 120 B/event: the HBM-bound member of the
     # family); the moments of the fluctuated quanta are summed on the device and all-reduced
-    nl = int(a.lar_events)
-    E_ = torch.rand(nl, dtype=torch.float64, device="cuda") * 999.9 + 0.1
-    F_ = torch.rand(nl, dtype=torch.float64, device="cuda") * 999.0 + 1.0
+    # the grid of examples/LArNEST/LArNESTMeanYieldsBenchmarks.cpp:31-41 (50 000 energies 0.1..1000 keV) repeated
+    # over drift fields 1 (the benchmark's "0"), 50, 100, ... 1000 V/cm, field varying slowest
+    nl = int(a.lar_events) // 50000 * 50000
+    E_ = (0.1 + (1000.0 - 0.1) / 50000.0 * torch.arange(50000, dtype=torch.float64, device="cuda")).repeat(nl // 50000)
+    fld = torch.tensor([1.0] + [50.0 * k for k in range(1, 21)], dtype=torch.float64, device="cuda")
+    F_ = fld[torch.arange(nl // 50000, device="cuda") % fld.numel()].repeat_interleave(50000)
     Y_ = torch.empty((9, nl), dtype=torch.float64, device="cuda")
     Fl_ = torch.empty((4, nl), dtype=torch.float64, device="cuda")
     lar_gbs = {}

@@ -186,7 +186,7 @@ int validate(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo, con
   // execNEST.cpp:419-426
   if (det->TopDrift <= 0. || det->anode <= 0. || det->gate <= 0.)
     return fail(c, NB200_EINVAL, "ERROR, unphysical value(s) of position within the detector geometry.");
-  if (mo->n_widths < 13 || mo->n_widths > 17)  // NEST.cpp:255-259
+  if (mo->n_widths < 13)  // NEST.cpp:255-259 (entries beyond the 17 that are read are ignored, as in the reference)
     return fail(c, NB200_EPHYSICS, "ERROR: You need a minimum of 13 free parameters for the resolution model.");
   if (ana->numBins < 1 || ana->numBins > 1000)  // NUMBINS_MAX TestSpectra.hh:34, execNEST.cpp:1510-1516
     return fail(c, NB200_EINVAL, "ERROR: Too many bins. Decrease numBins (analysis.hh) or increase NUMBINS_MAX");
@@ -291,6 +291,7 @@ int build_params(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo,
   std::memset(P, 0, sizeof *P);
   P->det = *det;
   P->model = *mo;
+  if (P->model.n_widths > 17) P->model.n_widths = 17;
   P->ana = *ana;
   P->src = *src;
   P->rc = *rc;
@@ -687,14 +688,23 @@ const char* nb200_last_error(const nb200_ctx* c) { return c ? c->err.c_str() : g
 
 int nb200_set_stream(nb200_ctx* c, void* s) {
   if (!c) return NB200_EINVAL;
-  c->stream = s ? static_cast<cudaStream_t>(s) : c->own_stream;
+  cudaStream_t ns = s ? static_cast<cudaStream_t>(s) : c->own_stream;
+  if (ns != c->stream) {
+    // kernels queued on the old stream share this context's workspace, queue and counters with whatever is
+    // launched next: let them finish before the switch
+    NB_CUDA(c, cudaSetDevice(c->device));
+    NB_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->stream = ns;
+  }
   return 0;
 }
 
+// also reports what the kernels of asynchronous calls flagged (the reference throws / returns 1 for these:
+// "Quanta not conserved", "min greater than max", unsupported species)
 int nb200_synchronize(nb200_ctx* c) {
   if (!c) return NB200_EINVAL;
-  NB_CUDA(c, cudaStreamSynchronize(c->stream));
-  return 0;
+  NB_CUDA(c, cudaSetDevice(c->device));
+  return check_device_error(c);  // synchronises the stream
 }
 
 uint64_t nb200_launch_count(const nb200_ctx* c) { return c ? c->launches : 0; }
@@ -1003,11 +1013,20 @@ int nb200_quanta(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo,
   if (mo->n_widths < 13)  // NEST.cpp:258-262
     return fail(c, NB200_EPHYSICS, "ERROR: You need a minimum of 13 free parameters for the resolution model.");
   if (n == 0) return 0;
+  if (mo->NRERWidthsParam[9] > mo->NRERWidthsParam[8] && mem_kind == NB200_MEM_HOST) {
+    // RecombOmegaER throws on its first call (NEST.cpp:183-184): any record with Lindhard == 1 reaches it
+    for (size_t i = 0; i < n; ++i)
+      if (nearly_equal(yields[3 * n + i], 1.) && yields[i] + yields[n + i] > 0.)
+        return fail(c, NB200_EPHYSICS,
+                    "Low-E r-fluct Gauss peak's width greater than centroid. This is physically wrong so "
+                    "please check your inputs, in NRERWidthsParam: they must be in the old wrong order.");
+  }
   NB_CUDA(c, cudaSetDevice(c->device));
   QuantaParams P;
   std::memset(&P, 0, sizeof P);
   P.det = *det;
   P.model = *mo;
+  if (P.model.n_widths > 17) P.model.n_widths = 17;
   P.density = density;
   P.n = n;
   P.seed = seed;
@@ -1390,9 +1409,10 @@ int nb200_run_async(nb200_ctx* c, const nb200_detector* det, const nb200_model* 
       return fail(c, NB200_EINVAL, "band accumulator geometry differs from the analysis (call nb200_band_reset)");
     P.do_band = 1;
     P.band = c->d_band;
-    c->band_events += n_events;
   }
-  return launch_event(c, P);
+  r = launch_event(c, P);
+  if (!r && P.do_band) c->band_events += n_events;
+  return r;
 }
 
 int nb200_band_fetch(nb200_ctx* c, nb200_band_hist* h) {

@@ -1155,8 +1155,8 @@ __global__ void k_se(const __grid_constant__ RunParams P, int n, double* __restr
   sincospi(2. * g.uniform(), &sn, &cs);
   const double r = d.radius * sqrt(g.uniform());
   const double posDep = fit_s2(d.FitS2, r * cs, r * sn) / P.s2_center;
-  long long nHits = binomial(P.seed, uint64_t(i), STREAM_BIN_S2HIT, Nph, d.g1_gas * posDep);
-  double Nphe = double(nHits + binomial(P.seed, uint64_t(i), STREAM_BIN_S2DPE, nHits, d.P_dphe));
+  long long nHits = binomial(P.seed, uint64_t(i), STREAM_BIN_SE_HIT, Nph, d.g1_gas * posDep);
+  double Nphe = double(nHits + binomial(P.seed, uint64_t(i), STREAM_BIN_SE_DPE, nHits, d.P_dphe));
   double area = gauss(g, Nphe, d.sPEres * sqrt(Nphe), true);
   double sig;
   if (d.noiseQuadratic[1] != 0) {
@@ -1439,9 +1439,14 @@ struct LArParams {
 };
 
 __global__ void __launch_bounds__(256) k_lar(const __grid_constant__ LArParams P) {
-  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < P.n;
-       i += uint64_t(gridDim.x) * blockDim.x) {
-    LArYields y = lar_yields(P.species, P.E[i], P.field[i], P.density);
+  LArFieldTerms ft;
+  ft.field = ft.density = __longlong_as_double(0x7ff8000000000000ll);  // NaN: matches no field
+  // a block walks one contiguous range of the list (not a grid stride): lists that sweep the field slowly keep each
+  // thread on one field for many events, which is what the memo above needs
+  const uint64_t per = ((P.n + gridDim.x - 1) / gridDim.x + blockDim.x - 1) / blockDim.x * blockDim.x;
+  const uint64_t lo = blockIdx.x * per, hi = lo + per < P.n ? lo + per : P.n;
+  for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    LArYields y = lar_yields(P.species, P.E[i], P.field[i], P.density, ft);
     if (P.yields) {
       P.yields[i] = y.TotalYield;
       P.yields[P.n + i] = y.QuantaYield;

@@ -48,6 +48,7 @@ enum : uint32_t {
   STREAM_BIN_NI = 32, STREAM_BIN_S1 = 33, STREAM_BIN_NEE = 34, STREAM_BIN_S2HIT = 35,
   STREAM_BIN_S2DPE = 36, STREAM_BIN_PAR0 = 37, STREAM_BIN_PAR1 = 38, STREAM_BIN_PAR2 = 39,
   STREAM_BIN_LAR = 40, STREAM_BIN_S1DPE = 41, /* 42: its BTRS fall-back */
+  STREAM_BIN_SE_HIT = 48, STREAM_BIN_SE_DPE = 49,  // CalculateG2's single-electron Monte Carlo (not the chain's events)
   STREAM_HOST = 16   // host-side draws (Poisson event count, WIMP table)
 };
 
