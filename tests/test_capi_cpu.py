@@ -208,3 +208,26 @@ def test_alias_tables_reproduce_the_binomial_pmf(built, prob):
         exact = stats.binom.pmf(np.arange(K), m, prob)
         assert abs(pmf.sum() - 1) < 1e-12
         assert np.abs(pmf - exact).max() < 2.0 ** -31, (b, np.abs(pmf - exact).max())
+
+
+def test_band_scale_and_overflow_guard(built):
+    """the band's sum of X is a 64-bit fixed-point integer: its scale follows the analysis range (2^-20 units while X
+    stays below 1024, coarser beyond), and nb200_band_finalize refuses an accumulator whose bins hold more events than
+    their sums can carry instead of returning wrapped statistics"""
+    capi = built
+    a0 = capi.analysis(0)
+    assert capi.lib().nb200_band_scale_x(C.byref(a0)) == 2.0 ** 20
+    a2 = capi.analysis(1)
+    a2.useS2 = 2                      # X = S2 up to maxS2 = 9e4 < 2^17
+    assert capi.lib().nb200_band_scale_x(C.byref(a2)) == 2.0 ** 13
+    b = capi.Band(a0)
+    b.accepted[:] = 1000
+    b.sumS1[:] = np.int64(1000 * 50.0 * 2 ** 20)
+    b.sumY[:] = np.int64(1000 * 2.0 * 2 ** 30)
+    b.sumY2[:] = np.int64(1000 * 4.01 * 2 ** 26)
+    b.sumY3[:] = np.int64(1000 * 8.1 * 2 ** 22)
+    out = b.finalize()
+    assert np.allclose(out[:, 1], 50.0) and np.allclose(out[:, 2], 2.0)
+    b.accepted[3] = np.uint64(3_000_000_000)      # x |log10| < 3.6 x 2^30 would pass 2^63
+    with pytest.raises(capi.NestB200Error):
+        b.finalize()

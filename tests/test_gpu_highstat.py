@@ -1,94 +1,73 @@
-"""High-statistics parity: 4e7 GPU events against 4.8e6 events of the unmodified reference (one
-process per core, distinct seeds), config 2 (NR 0-100 keV) and config 1 (ER 0.1-20 keV).  Band means
-and widths by the reference's chi^2 (examples/rootNEST.cpp:619-643) and 1-D chi^2 on the integer
-quanta and corrected pulse areas."""
+"""High-statistics parity with a null control: 4e7 GPU events against 1.6e7 events of the unmodified reference (two
+independent samples A, B of 8e6, one worker per core), config 1 (ER 0.1-20 keV) and config 2 (NR 0-100 keV).
+
+Same estimators as tools/parity_highstat.py (whose 1e8-vs-1e8 run is profiles/r02_parity_1e8.txt): band mean and width
+chi^2 with the width error from each bin's fourth moment (GetBand's pushed zeros fatten the tails: with the Gaussian
+sigma/sqrt(2N) even reference-vs-reference reads >1 per dof), KS distances of Nph / Ne / S1c / S2c, the in-window
+fraction -- gated on p-values, and the reference-vs-reference comparison run beside it as the null."""
 import multiprocessing as mp
 import os
 import sys
 
 import numpy as np
 import pytest
-from scipy import stats
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-COLS = ["Nph", "Ne", "s1c", "s2c"]
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+P_GATE = 1e-3
 
 
-def _edges(cfg):
-    if cfg == "NR":
-        return {"Nph": np.arange(0, 1801, 20.), "Ne": np.arange(0, 361, 4.), "s1c": np.arange(0, 241, 3.),
-                "s2c": np.arange(0, 6001, 75.)}
-    return {"Nph": np.arange(0, 1601, 20.), "Ne": np.arange(0, 801, 10.), "s1c": np.arange(0, 201, 2.5),
-            "s2c": np.arange(0, 12001, 150.)}
-
-
-def _ref_worker(args):
-    cfg, seed, n = args
-    sys.path.insert(0, ROOT)
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import refprobe
-    from helpers import ref_chain
-    from nest_b200 import capi, shard
-    r = refprobe.reference()
-    if cfg == "NR":
-        a = ref_chain(r, seed, n, capi.NR, capi.SRC_FLAT, 0.0, 100.0)
-    else:
-        a = ref_chain(r, seed, n, capi.beta, capi.SRC_FLAT, 0.1, 20.0, er_model=0)
+@pytest.fixture(scope="module")
+def samples(ctx, ref):
+    import parity_highstat as ph
+    from nest_b200 import capi
     ana = capi.analysis(0)
-    words = shard.band_words_from_signals(ana, 2, a[:, refprobe.SIG1], a[:, refprobe.SIG2])
-    ed = _edges(cfg)
-    h = {"Nph": np.histogram(a[:, refprobe.COL["Nph"]], ed["Nph"])[0],
-         "Ne": np.histogram(a[:, refprobe.COL["Ne"]], ed["Ne"])[0],
-         "s1c": np.histogram(np.abs(a[:, refprobe.S1_0 + 5]), ed["s1c"])[0],
-         "s2c": np.histogram(np.abs(a[:, refprobe.S2_0 + 7]), ed["s2c"])[0]}
-    return words, h
-
-
-def chi2_hist(a, b):
-    """two-sample chi^2 of histograms with different totals; bins with few counts merged away"""
-    a, b = a.astype(float), b.astype(float)
-    ok = (a + b) > 50
-    a, b = a[ok], b[ok]
-    A, B = a.sum(), b.sum()
-    c = np.sum((np.sqrt(B / A) * a - np.sqrt(A / B) * b) ** 2 / (a + b))
-    dof = len(a) - 1
-    return c, dof, stats.chi2.sf(c, dof)
-
-
-@pytest.mark.parametrize("cfg", ["NR", "ER"])
-def test_band_and_spectra_at_high_statistics(ctx, ref, cfg):
-    from helpers import band_chi2
-    from nest_b200 import capi, shard
-    cores = min(len(os.sched_getaffinity(0)), 16)
-    n_ref = 300000
+    cores = min(len(os.sched_getaffinity(0)), 32)
+    chunk, n_ref = 250_000, 8_000_000
+    tasks = []
+    for name in ph.CONFIGS:
+        for s, base in (("A", 3_000_000), ("B", 4_000_000)):
+            for i in range(n_ref // chunk):
+                tasks.append(((name, s), (name, base + i, chunk)))
+    acc = {(name, s): ph.Acc(ana.numBins) for name in ph.CONFIGS for s in "AB"}
     with mp.get_context("spawn").Pool(cores) as pool:
-        parts = pool.map(_ref_worker, [(cfg, 100 + k, n_ref) for k in range(cores)])
-    ana = capi.analysis(0)
-    ref_words = sum(p[0] for p in parts)
-    ref_h = {c: sum(p[1][c] for p in parts) for c in COLS}
-    band_ref = shard.band_from_words(ana, ref_words).finalize()
-    # GPU: band from 4e7 events (device accumulator), spectra from 8e6 events (host columns)
-    det = capi.detector("LUX_Run03")
-    rc = capi.prepare(det, 180.0)
-    mo = capi.model(1)
-    if cfg == "NR":
-        src = capi.source(capi.SRC_FLAT, capi.NR, 0.0, 100.0, 180.0)
-    else:
-        src = capi.source(capi.SRC_FLAT, capi.beta, 0.1, 20.0, 180.0)
-        mo.er_model = 0
-    band = capi.Band(ana)
-    ctx.run(det, mo, ana, src, rc, 7, 40_000_000, columns=[], band=band)
-    band_gpu = band.finalize()
-    cm, cw, dof = band_chi2(band_gpu, band_ref)
-    assert cm < 1.6 and cw < 1.6, "%s band chi2/dof: mean %.2f width %.2f (dof %d)" % (cfg, cm, cw, dof)
-    # efficiencies per bin agree (accepted / (accepted + rejected))
-    ok = (band_ref[:, 5] > 0) & np.isfinite(band_ref[:, 5]) & (ref_words[:ana.numBins * 6].reshape(-1, 6)[:, 0] > 2000)
-    assert np.abs(band_gpu[ok][:, 5] - band_ref[ok][:, 5]).max() < 0.01
-    cols = ctx.run(det, mo, ana, src, rc, 8, 8_000_000, columns=["photons", "electrons", "s1_5", "s2_7"])
-    ed = _edges(cfg)
-    gh = {"Nph": np.histogram(cols["photons"], ed["Nph"])[0], "Ne": np.histogram(cols["electrons"], ed["Ne"])[0],
-          "s1c": np.histogram(np.abs(cols["s1_5"]), ed["s1c"])[0], "s2c": np.histogram(np.abs(cols["s2_7"]), ed["s2c"])[0]}
-    for c in COLS:
-        chi, dof, p = chi2_hist(gh[c], ref_h[c])
-        assert p > 1e-4, "%s %s: chi2 %.1f / %d dof (p = %.2e)" % (cfg, c, chi, dof, p)
+        for (key, _), (_, a) in zip(tasks, pool.imap(ph.ref_worker, [t for _, t in tasks], chunksize=1)):
+            acc[key].add(a)
+    gpu = {name: ph.gpu_sample(ctx, name, 40_000_000, seed=77) for name in ph.CONFIGS}
+    return ph, ana, acc, gpu
+
+
+@pytest.mark.parametrize("name", ["config1_ER_0.1-20keV", "config2_NR_0-100keV"])
+def test_band_and_spectra_at_high_statistics(samples, name):
+    ph, ana, acc, gpu = samples
+    both = ph.Acc(ana.numBins).add(acc[(name, "A")]).add(acc[(name, "B")])      # 1.6e7 reference events
+    b = ph.chi2_pair(gpu[name], both)
+    null = ph.chi2_pair(acc[(name, "A")], acc[(name, "B")])
+    msg = "%s gpu-vs-ref %r | null (ref-vs-ref) %r" % (name, b, null)
+    assert b["dof"] >= 90, msg
+    assert b["p_mean"] > P_GATE and b["p_width"] > P_GATE, msg
+    assert null["p_mean"] > 1e-4 and null["p_width"] > 1e-4, msg          # the estimator itself is sound
+    assert abs(b["accepted_z"]) < 4.0, msg
+    assert b["max_abs_mean_diff"] < 2e-3 and b["max_rel_width_diff"] < 0.02, msg
+    ks = ph.ks_pair(gpu[name], both)
+    for k, v in ks.items():
+        assert v["p"] > P_GATE, (name, k, v)
+
+
+def test_er_leakage_below_the_nr_band_mean(samples):
+    """examples/rootNEST.cpp:880-915: the fraction of ER events below the NR centroid per S1 bin, GPU vs reference"""
+    from scipy import stats
+    ph, ana, acc, gpu = samples
+    er, nr = "config1_ER_0.1-20keV", "config2_NR_0-100keV"
+    ref_er = ph.Acc(ana.numBins).add(acc[(er, "A")]).add(acc[(er, "B")])
+    ref_nr = ph.Acc(ana.numBins).add(acc[(nr, "A")]).add(acc[(nr, "B")])
+    bg, tg = ph.leakage(gpu[er], gpu[nr], ana)
+    br, tr = ph.leakage(ref_er, ref_nr, ana)
+    ok = (tg >= 2000) & (tr >= 2000)
+    pg, pr = bg[ok] / tg[ok], br[ok] / tr[ok]
+    var = pg * (1 - pg) / tg[ok] + pr * (1 - pr) / tr[ok]
+    chi2 = float(((pg - pr) ** 2 / np.maximum(var, 1e-300)).sum())
+    assert stats.chi2.sf(chi2, int(ok.sum())) > P_GATE, (chi2, int(ok.sum()))
+    tot_g, tot_r = bg[ok].sum() / tg[ok].sum(), br[ok].sum() / tr[ok].sum()
+    assert 1e-3 < tot_r < 2e-2 and abs(tot_g - tot_r) < 5 * np.sqrt(tot_r / tr[ok].sum() + tot_g / tg[ok].sum())

@@ -160,3 +160,43 @@ def test_full_size_config2_is_the_sum_of_its_eight_shards(ctx):
     assert abs(acc / n - 0.619) < 0.005        # fraction of 0-100 keV NR events inside the S1/S2 window
     b = full.finalize()
     assert np.all(np.diff(b[:, 1]) > 0) and np.all(b[:, 4] < 2e-3)   # every bin populated: mean error < 0.002 dex
+
+
+def test_packed_f32_record_is_the_f64_record_rounded(ctx):
+    """NB200_SOA_F32: the same events, every double column stored as float (half the bytes over PCIe)"""
+    det = capi.detector("LUX_Run03")
+    rc = capi.prepare(det, 180.0)
+    mo, ana = capi.model(1), capi.analysis(0)
+    src = capi.source(capi.SRC_FLAT, capi.NR, 0.0, 100.0, 180.0)
+    n = (1 << 20) + 4321          # more than one host chunk
+    cols = ["signalE", "driftTime", "smear_x", "z_mm", "photons", "electrons", "s1_2", "s1_7", "s2_0", "s2_4", "s2_7"]
+    a = ctx.run(det, mo, ana, src, rc, 3, n, columns=cols)
+    b = ctx.run(det, mo, ana, src, rc, 3, n, columns=cols, f32=True)
+    for k in cols:
+        if k in capi.SOA_I32:
+            assert b[k].dtype == np.int32 and np.array_equal(a[k], b[k]), k
+        else:
+            assert b[k].dtype == np.float32 and np.array_equal(a[k].astype(np.float32), b[k]), k
+
+
+def test_band_over_s2_uses_the_coarser_sum_scale(ctx):
+    """useS2 = 2 bins the band in S2 (up to maxS2 = 9e4): the sum of X is kept in 2^-13 units there, and the
+    accumulator still equals the host recomputation from the per-event signals, word for word"""
+    from nest_b200 import shard
+    det = capi.detector("LUX_Run03")
+    rc = capi.prepare(det, 180.0)
+    mo = capi.model(1)
+    ana = capi.analysis(0)
+    ana.useS2, ana.maxS2, ana.minS2, ana.numBins, ana.logMin, ana.logMax = 2, 9e4, 100.0, 60, -3.6, -0.6
+    src = capi.source(capi.SRC_FLAT, capi.NR, 0.0, 100.0, 180.0)
+    band = capi.Band(ana)
+    cols = ctx.run(det, mo, ana, src, rc, 8, 300000, columns=["signal1", "signal2"], band=band)
+    words = shard.band_words_from_signals(ana, det.coinLevel, cols["signal1"], cols["signal2"])
+    nb = ana.numBins
+    got = band.words()
+    per_g = np.stack([got[i * nb:(i + 1) * nb] for i in range(6)], axis=1)   # Band.words(): column-major
+    per_h = words[:nb * 6].reshape(nb, 6)
+    assert np.array_equal(per_g[:, :2], per_h[:, :2])
+    assert np.array_equal(per_g[:, 2], per_h[:, 2])      # sum of X in 2^-13 units
+    assert capi.lib().nb200_band_scale_x(C.byref(ana)) == 2.0 ** 13
+    assert np.isfinite(band.finalize()[band.accepted > 100]).all()
