@@ -373,7 +373,16 @@ int nb200_run_sweep(nb200_ctx* ctx, size_t n_points, const nb200_detector* dets,
                     const nb200_analysis* ana, const nb200_source* srcs, const nb200_run_consts* rcs, uint64_t seed,
                     uint64_t first_event, uint64_t n_events, nb200_band_hist* bands);
 
-/* Device-resident variant used for throughput measurement: the band accumulator
+/* Band post-processing for the bands of the LAST nb200_run_sweep on this context, on the device (they are still in
+ * device memory): per grid point GetBand's statistics (execNEST.cpp:1582-1618; stats [n_points][numBins][7] as
+ * nb200_band_finalize), rootNEST's goodness of fit against target_band [numBins][7] (examples/rootNEST.cpp:600-643;
+ * gof [n_points][6] as nb200_band_chi2) and the events below the line centroid[numBins] (:880-915; leak
+ * [n_points][3] = below, all, ratio, as nb200_band_leakage's total).  Any output may be NULL; all pointers HOST.
+ * What a fit over the grid reads back is then 6 numbers per point instead of a 28 KB accumulator. */
+int nb200_sweep_band_post(nb200_ctx* ctx, size_t n_points, const nb200_analysis* ana, const double* target_band,
+                          int free_param, const double* centroid, double* stats, double* gof, double* leak);
+
+/* Device-resident variant used for throughput measurement: the band accumulator/* Device-resident variant used for throughput measurement: the band accumulator
  * stays in device memory owned by ctx between calls; fetch adds it into hist. */
 int nb200_run_async(nb200_ctx* ctx, const nb200_detector* det, const nb200_model* model,
                     const nb200_analysis* ana, const nb200_source* src,

@@ -102,7 +102,7 @@ class BandHist(C.Structure):
 EXPORTS = [
     "nb200_abi_version", "nb200_sizeof", "nb200_create", "nb200_destroy", "nb200_last_error", "nb200_set_stream",
     "nb200_synchronize", "nb200_detector_builtin", "nb200_model_default", "nb200_analysis_default",
-    "nb200_prepare", "nb200_wimp_prep", "nb200_wimp_prep_iso", "nb200_wimp_drate", "nb200_poisson", "nb200_yields", "nb200_quanta", "nb200_s2", "nb200_s1", "nb200_widths", "nb200_spike", "nb200_xy_resolution", "nb200_spectrum", "nb200_run", "nb200_run_sweep", "nb200_run_async",
+    "nb200_prepare", "nb200_wimp_prep", "nb200_wimp_prep_iso", "nb200_wimp_drate", "nb200_poisson", "nb200_yields", "nb200_quanta", "nb200_s2", "nb200_s1", "nb200_widths", "nb200_spike", "nb200_xy_resolution", "nb200_spectrum", "nb200_run", "nb200_run_sweep", "nb200_sweep_band_post", "nb200_run_async",
     "nb200_band_reset", "nb200_band_attach", "nb200_fp64_peak", "nb200_timing_enable", "nb200_timing_read", "nb200_se_stats", "nb200_band_fetch", "nb200_band_device_buffer", "nb200_allreduce_hist",
     "nb200_band_hist_bytes", "nb200_band_scale_x", "nb200_band_finalize", "nb200_band_chi2", "nb200_band_leakage", "nb200_band_fit_gauss", "nb200_band_leakage_gauss", "nb200_hist_fit", "nb200_hist_fit_cov", "nb200_band_leakage_skew_cov", "nb200_graph_fit", "nb200_band_leakage_skew", "nb200_lar", "nb200_launch_count",
     "nb200_debug_hitmath", "nb200_debug_binomial", "nb200_debug_normal", "nb200_debug_binomial_fixed",
@@ -171,6 +171,7 @@ def lib():
     L.nb200_run_sweep.argtypes = [vp, C.c_size_t, C.POINTER(Detector), C.POINTER(Model), C.POINTER(Analysis),
                                   C.POINTER(Source), C.POINTER(RunConsts), C.c_uint64, C.c_uint64, C.c_uint64,
                                   C.POINTER(BandHist)]
+    L.nb200_sweep_band_post.argtypes = [vp, C.c_size_t, C.POINTER(Analysis), c_dp, C.c_int, c_dp, c_dp, c_dp, c_dp]
     L.nb200_band_reset.argtypes = [vp, C.POINTER(Analysis)]
     L.nb200_band_fetch.argtypes = [vp, C.POINTER(BandHist)]
     L.nb200_band_attach.argtypes = [vp, C.POINTER(Analysis), vp]
@@ -589,6 +590,20 @@ class Context:
         for b, c in zip(bands, B):
             b.c.n_events = c.n_events
         return bands
+
+    def sweep_band_post(self, n_points, ana, target=None, free_param=2, centroid=None, want_stats=True):
+        """statistics / goodness of fit / leakage of the last sweep's bands, computed on the device
+        -> (stats [n][numBins][7] or None, gof [n][6] or None, leak [n][3] or None)"""
+        nb = ana.numBins
+        tgt = None if target is None else np.ascontiguousarray(target, np.float64)
+        cen = None if centroid is None else np.ascontiguousarray(centroid, np.float64)
+        stats = np.zeros((n_points, nb, 7)) if want_stats else None
+        gof = np.zeros((n_points, 6)) if tgt is not None else None
+        leak = np.zeros((n_points, 3)) if cen is not None else None
+        p = lambda a: a.ctypes.data_as(c_dp) if a is not None else None
+        self._check(lib().nb200_sweep_band_post(self.h, n_points, C.byref(ana), p(tgt), free_param, p(cen), p(stats),
+                                                p(gof), p(leak)))
+        return stats, gof, leak
 
     def band_reset(self, ana):
         self._check(lib().nb200_band_reset(self.h, C.byref(ana)))

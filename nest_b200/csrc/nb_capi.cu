@@ -81,6 +81,7 @@ struct nb200_ctx {
   unsigned long long* d_sweep_bands = nullptr;
   size_t sweep_band_words = 0;
   int occ_pre_sweep = 0, occ_hits_sweep = 0;
+  size_t sweep_last_points = 0, sweep_last_words = 0;  // shape of the bands the last nb200_run_sweep left on the device
 };
 
 namespace {
@@ -1738,6 +1739,8 @@ int nb200_run_sweep(nb200_ctx* c, size_t n_points, const nb200_detector* dets, c
     c->launches += 4;
   }
   tr.mark("launched");
+  c->sweep_last_points = n_points;
+  c->sweep_last_words = words;
   std::vector<unsigned long long> w(words * n_points);
   NB_CUDA(c, cudaMemcpyAsync(w.data(), c->d_sweep_bands, w.size() * 8, cudaMemcpyDeviceToHost, c->stream));
   r = check_device_error(c);  // synchronises (Ps must also outlive the copy above)
@@ -1761,6 +1764,49 @@ int nb200_run_sweep(nb200_ctx* c, size_t n_points, const nb200_detector* dets, c
     h->n_events += n_events;
   }
   return 0;
+}
+
+// Band post-processing of the last sweep's bands on the device (k_band_post)
+int nb200_sweep_band_post(nb200_ctx* c, size_t n_points, const nb200_analysis* ana, const double* target_band,
+                          int free_param, const double* centroid, double* stats, double* gof, double* leak) {
+  if (!c || !ana) return NB200_EINVAL;
+  if (n_points == 0) return 0;
+  const size_t words = band_word_count(ana);
+  if (!c->d_sweep_bands || words * n_points > c->sweep_band_words || c->sweep_last_points != n_points ||
+      c->sweep_last_words != words)
+    return fail(c, NB200_EINVAL, "nb200_sweep_band_post: no sweep of this shape on this context (call nb200_run_sweep first)");
+  if ((gof && !target_band) || (leak && !centroid)) return fail(c, NB200_EINVAL, "gof needs a target band, leak a centroid line");
+  if (ana->numBins > 256) return fail(c, NB200_EINVAL, "nb200_sweep_band_post: at most 256 S1 bins");
+  NB_CUDA(c, cudaSetDevice(c->device));
+  Staged st(c, NB200_MEM_HOST);
+  BandPostArgs A;
+  std::memset(&A, 0, sizeof A);
+  A.bands = c->d_sweep_bands;
+  A.band_words = words;
+  A.numBins = ana->numBins;
+  A.logBins = ana->logBins;
+  A.useS2 = ana->useS2;
+  A.free_param = free_param;
+  if (ana->useS2 == 2) {
+    A.binWidth = (ana->maxS2 - ana->minS2) / double(ana->numBins);
+    A.border = ana->minS2;
+  } else {
+    A.binWidth = (ana->maxS1 - ana->minS1) / double(ana->numBins);
+    A.border = ana->minS1;
+  }
+  A.fx_x = band_scale_x(ana);
+  A.logMin = ana->logMin;
+  A.logMax = ana->logMax;
+  A.target = st.in(target_band, size_t(ana->numBins) * 7);
+  A.centroid = st.in(centroid, size_t(ana->numBins));
+  A.stats = st.out(stats, n_points * size_t(ana->numBins) * 7);
+  A.gof = st.out(gof, n_points * 6);
+  A.leak = st.out(leak, n_points * 3);
+  if (st.err == cudaSuccess) {
+    k_band_post<<<unsigned(n_points), 256, 0, c->stream>>>(A);
+    ++c->launches;
+  }
+  return st.finish(0, "k_band_post");
 }
 
 // GetBand's closing statistics (execNEST.cpp:1582-1618) from the integer accumulator

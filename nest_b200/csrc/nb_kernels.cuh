@@ -1351,6 +1351,105 @@ __global__ void __launch_bounds__(256) k_s1post(const __grid_constant__ RunParam
   }
 }
 
+// ---- band post-processing for batched bands, on the device --------------------------------------------
+// A sweep leaves hundreds of band accumulators in device memory; what a fit over the grid wants back from each is a
+// handful of numbers, not 28 KB: GetBand's statistics (execNEST.cpp:1582-1618), rootNEST's goodness of fit against a
+// target band (examples/rootNEST.cpp:600-643) and the leakage below a centroid line (:880-915).  One block per grid
+// point, one thread per S1 bin for the statistics, a block reduction for the sums -- the same formulas, in the same
+// order per bin, as nb200_band_finalize / nb200_band_chi2 / nb200_band_leakage on the host.
+struct BandPostArgs {
+  const unsigned long long* bands;  // [n_points][band_words]
+  uint64_t band_words;
+  int32_t numBins, logBins, useS2, free_param;
+  double border, binWidth, fx_x, logMin, logMax;
+  const double* target;    // [numBins][7] band to compare with, or null
+  const double* centroid;  // [numBins] leakage line, or null
+  double* stats;           // [n_points][numBins][7] or null
+  double* gof;             // [n_points][6] or null (needs target)
+  double* leak;            // [n_points][3] = events below, all events, ratio; or null (needs centroid)
+};
+__global__ void __launch_bounds__(256) k_band_post(const __grid_constant__ BandPostArgs A) {
+  __shared__ double s_red[6][256];
+  const unsigned long long* B = A.bands + uint64_t(blockIdx.x) * A.band_words;
+  double acc[6] = {0., 0., 0., 0., 0., 0.};  // chi2 mean, chi2 width, pct mean, pct width, leak below, leak all
+  for (int j = threadIdx.x; j < A.numBins; j += blockDim.x) {
+    const unsigned long long* b = B + size_t(j) * BAND_WORDS;
+    const double N = double(b[0]);
+    const double Sx = double((long long)b[2]) / A.fx_x, Sy = double((long long)b[3]) / NB200_FX_Y,
+                 Sy2 = double((long long)b[4]) / NB200_FX_Y2, Sy3 = double((long long)b[5]) / NB200_FX_Y3;
+    double st[7];
+    st[0] = A.border + A.binWidth / 2. + double(j) * A.binWidth;
+    st[1] = Sx / N;
+    const double mu = Sy / N;
+    st[2] = mu;
+    const double var = (Sy2 - 2. * mu * Sy + N * mu * mu) / (N - 1.);
+    st[3] = sqrt(var);
+    st[4] = st[3] / sqrt(N);
+    st[5] = N / (N + double(b[1]));
+    const double m3 = Sy3 - 3. * mu * Sy2 + 3. * mu * mu * Sy - N * mu * mu * mu;
+    st[6] = m3 / (st[3] * st[3] * st[3]) / (N - 2.);
+    if (A.stats)
+      for (int k = 0; k < 7; ++k) A.stats[(uint64_t(blockIdx.x) * A.numBins + j) * 7 + k] = st[k];
+    if (A.target) {
+      const double* y = A.target + 7 * size_t(j);
+      const bool ok = isfinite(st[2]) && isfinite(y[2]) && isfinite(st[3]) && isfinite(y[3]) && st[4] > 0. && y[4] > 0.;
+      if (ok && ((A.useS2 == 0 && fabs(st[2]) < 5.) || A.useS2 != 0)) {
+        double error = sqrt(st[4] * st[4] + y[4] * y[4]);
+        acc[0] += (y[2] - st[2]) / error * ((y[2] - st[2]) / error);
+        error = sqrt(0.5 * (st[4] * st[4] + y[4] * y[4]));
+        acc[1] += (y[3] - st[3]) / error * ((y[3] - st[3]) / error);
+        acc[2] += 100. * (y[2] - st[2]) / y[2];
+        acc[3] += 100. * (y[3] - st[3]) / y[3];
+      }
+    }
+    if (A.centroid && A.logBins > 0) {
+      const unsigned long long* row = B + size_t(A.numBins) * BAND_WORDS + size_t(j) * A.logBins;
+      const double w = (A.logMax - A.logMin) / double(A.logBins);
+      const double pos = (A.centroid[j] - A.logMin) / w;
+      double in_hist = 0., below = 0.;
+      for (int k = 0; k < A.logBins; ++k) {
+        const double c = double(row[k]);
+        in_hist += c;
+        if (double(k + 1) <= pos)
+          below += c;
+        else if (double(k) < pos)
+          below += c * (pos - double(k));
+      }
+      if (A.centroid[j] > 0.) below += N - in_hist;
+      if (N > 0.) {
+        acc[4] += below;
+        acc[5] += N;
+      }
+    }
+  }
+  for (int k = 0; k < 6; ++k) s_red[k][threadIdx.x] = acc[k];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // summed in bin order by one thread: the same order of additions as the host functions
+    double t[6] = {0., 0., 0., 0., 0., 0.};
+    // thread i holds bins i, i + 256, ...: with numBins <= 256 (every shipped analysis) thread order = bin order
+    for (int i = 0; i < int(blockDim.x); ++i)
+      for (int k = 0; k < 6; ++k) t[k] += s_red[k][i];
+    if (A.gof) {
+      const int DoF = A.numBins - abs(A.free_param);
+      double* o = A.gof + 6 * uint64_t(blockIdx.x);
+      const double c0 = t[0] / double(DoF - 1), c1 = t[1] / double(DoF - 1);
+      o[0] = c0;
+      o[1] = c1;
+      o[2] = 0.5 * (c0 + c1);
+      o[3] = sqrt(c0 * c1);
+      o[4] = -(t[2] / double(A.numBins));
+      o[5] = -(t[3] / double(A.numBins));
+    }
+    if (A.leak) {
+      double* o = A.leak + 3 * uint64_t(blockIdx.x);
+      o[0] = t[4];
+      o[1] = t[5];
+      o[2] = t[4] / t[5];
+    }
+  }
+}
+
 // ---- the remaining public model methods of NESTcalc as stage calls (NEST.hh:311-333, 345, 404) ---------------------
 // k_widths: RecombOmegaNR (NEST.cpp:164-171), RecombOmegaER (:173-225) and FanoER (:227-246) for n records;
 // out: 3 columns of n.

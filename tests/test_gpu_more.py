@@ -187,7 +187,7 @@ def test_band_over_s2_uses_the_coarser_sum_scale(ctx):
     rc = capi.prepare(det, 180.0)
     mo = capi.model(1)
     ana = capi.analysis(0)
-    ana.useS2, ana.maxS2, ana.minS2, ana.numBins, ana.logMin, ana.logMax = 2, 9e4, 100.0, 60, -3.6, -0.6
+    ana.useS2, ana.maxS2, ana.minS2, ana.numBins = 2, 9e4, 100.0, 60      # y = log10(S2 / S1), binned in S2
     src = capi.source(capi.SRC_FLAT, capi.NR, 0.0, 100.0, 180.0)
     band = capi.Band(ana)
     cols = ctx.run(det, mo, ana, src, rc, 8, 300000, columns=["signal1", "signal2"], band=band)

@@ -124,3 +124,27 @@ def test_sweep_points_match_reference(ctx, ref):
                     assert cm < 2.5 and cw < 2.5, (POINTS[k], cm, cw, dof)
     finally:
         ref.lux_set()
+
+
+def test_sweep_band_post_on_device_equals_the_host_functions(ctx):
+    """statistics, rootNEST's goodness of fit and leakage of a sweep's bands computed on the device (k_band_post)
+    against nb200_band_finalize / nb200_band_chi2 / nb200_band_leakage on the copied-back accumulators"""
+    ana = capi.analysis(0)
+    dets, mods, srcs, rcs, keys = grid_points((100.0, 180.0, 400.0), (0.10, 0.117), (0.09, 0.1), "nr")
+    n = 400_000
+    bands = ctx.run_sweep(dets, mods, ana, srcs, rcs, seed=2, n=n)
+    target = bands[3].finalize()                      # one grid point's band plays the data band
+    ok = np.isfinite(target).all(axis=1)
+    centroid = np.where(ok, target[:, 2] - 0.05, 1.0)
+    stats_d, gof_d, leak_d = ctx.sweep_band_post(len(bands), ana, target=target, free_param=2, centroid=centroid)
+    for k, b in enumerate(bands):
+        st = b.finalize()
+        assert np.array_equal(np.isnan(st), np.isnan(stats_d[k]))
+        m = np.isfinite(st)
+        assert np.max(np.abs(st[m] - stats_d[k][m]) / np.maximum(np.abs(st[m]), 1e-300)) < 1e-12
+        chi = capi.band_chi2(st, target, useS2=0, free_param=2)
+        assert np.allclose(gof_d[k], chi, rtol=1e-10, atol=1e-12), (keys[k], gof_d[k], chi)
+        _, _, _, tot = b.leakage(centroid)
+        assert np.allclose(leak_d[k], tot, rtol=1e-12), (keys[k], leak_d[k], tot)
+    assert gof_d[3][0] == 0.0 and gof_d[3][1] == 0.0      # the target against itself
+    assert np.argmin(gof_d[:, 2]) == 3
