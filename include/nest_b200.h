@@ -382,7 +382,7 @@ int nb200_run_sweep(nb200_ctx* ctx, size_t n_points, const nb200_detector* dets,
 int nb200_sweep_band_post(nb200_ctx* ctx, size_t n_points, const nb200_analysis* ana, const double* target_band,
                           int free_param, const double* centroid, double* stats, double* gof, double* leak);
 
-/* Device-resident variant used for throughput measurement: the band accumulator/* Device-resident variant used for throughput measurement: the band accumulator
+/* Device-resident variant used for throughput measurement: the band accumulator
  * stays in device memory owned by ctx between calls; fetch adds it into hist. */
 int nb200_run_async(nb200_ctx* ctx, const nb200_detector* det, const nb200_model* model,
                     const nb200_analysis* ana, const nb200_source* src,
