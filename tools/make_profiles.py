@@ -12,7 +12,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
-KERNEL = "_ZN2nb6k_hitsENS_9RunParamsEPj"
+KERNEL = "_ZN2nb6k_hitsENS_9RunParamsEPjNS_8HitQueueE"
 
 
 def nm(s):
@@ -37,8 +37,9 @@ def main():
         f.write("%-46s %8s %12s %8s\n" % ("kernel", "launches", "total ms", "share"))
         for k, v in agg.items():
             f.write("%-46s %8d %12.3f %7.1f%%\n" % (k, v[0], v[1], 100 * v[1] / tot))
-        chain = sum(agg[k][1] for k in ("k_pre", "k_hits", "k_post"))
-        f.write("\nchain kernels only (ncu): " + ", ".join("%s %.1f%%" % (k, 100 * agg[k][1] / chain) for k in ("k_pre", "k_hits", "k_post")) + "\n")
+        ck = [k for k in ("k_pre", "k_hits", "k_hits_finish", "k_post") if k in agg]
+        chain = sum(agg[k][1] for k in ck)
+        f.write("\nchain kernels only (ncu): " + ", ".join("%s %.1f%%" % (k, 100 * agg[k][1] / chain) for k in ck) + "\n")
         s = b["roofline"]["stage_ms_per_step"]
         t = sum(s.values())
         f.write("bench.py CUDA-event stage shares (same build, no profiler): " + ", ".join("%s %.1f%%" % (k, 100 * v / t) for k, v in s.items()) + "\n")
@@ -48,9 +49,11 @@ def main():
     json.dump(b, open(os.path.join(out, "%s_bench_n1.json" % tag), "w"), indent=1)
     if refarm:
         json.dump(json.load(open(refarm)), open(os.path.join(out, "%s_bench_reference_arm.json" % tag), "w"), indent=1)
-    kernels = [("k_hits", "_ZN2nb6k_hitsENS_9RunParamsEPj", rep)]
-    for short, mangled in (("k_pre", "_ZN2nb5k_preENS_9RunParamsEPi"), ("k_post", "_ZN2nb6k_postENS_9RunParamsEPi")):
-        cand = rep.replace("k_hits", short)
+    kernels = [("k_hits", KERNEL, rep)]
+    for short, mangled in (("k_pre", "_ZN2nb5k_preENS_9RunParamsEPi"), ("k_post", "_ZN2nb6k_postENS_9RunParamsEPi"),
+                           ("k_hits_finish", "_ZN2nb13k_hits_finishENS_9RunParamsENS_8HitQueueE"),
+                           ("k_lar", "_ZN2nb5k_larENS_9LArParamsE")):
+        cand = rep.replace("k_hits.", short + ".")
         if cand != rep and os.path.exists(cand):
             kernels.append((short, mangled, cand))
     sassd = os.path.join(ROOT, "gpurun_out", "sass")
@@ -78,8 +81,8 @@ def main():
         rr = list(csv.reader(raw.splitlines()))
         hdr, units, vals = rr[0], rr[1], rr[2]
         with open(os.path.join(out, "%s_%s_ncu_full.txt" % (tag, short)), "w") as f:
-            f.write("ncu --set full --clock-control none --import-source on -k regex:%s -s 30 -c 1 python bench.py --steps 2 --warmup 1 --no-cpu-baseline   (B200)\n" % short)
-            f.write("one launch of %s inside the bench command: 2^22 NR events (0-100 keV flat, LUX_Run03), ~3.3e8 S1 PMT hits\n\n" % short)
+            f.write("ncu --set full --clock-control none --import-source on -k regex:^%s$ -s 1 -c 1 python tools/profile_run.py --events 4e6 --launches 2   (B200)\n" % short)
+            f.write("one launch of %s: 4e6 events of the bench workload (NR 0-100 keV flat, LUX_Run03), ~3.2e8 S1 PMT hits%s\n\n" % (short, "" if short != "k_lar" else " -- k_lar: tools/profile_lar.py, 2e7 ER events with fluctuations"))
             for h, u, v in zip(hdr, units, vals):
                 if h in want or ("issue_stalled" in h and "per_issue_active" in h) or h.startswith("smsp__inst_executed_op_local") or h.startswith("l1tex__t_bytes_pipe_lsu_mem_local"):
                     f.write("%-92s %-16s %s\n" % (h, u, v))
