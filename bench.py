@@ -472,16 +472,15 @@ def main():
     g1gs = [0.07, 0.085, 0.10, 0.115, 0.13]
     wt = capi.WimpTable(50.0, 5.0, 0.0, seed=seed)
     tprep = time.perf_counter()
+    from nest_b200 import shard
+    points = [(f_, g1_, gg_) for f_ in fields for g1_ in g1s for gg_ in g1gs]
+    k = len(points)
     grid = []
-    k = 0
-    for f_ in fields:
-        for g1_ in g1s:
-            for gg_ in g1gs:
-                if k % world == rank:
-                    d_ = capi.detector("LUX_Run03")
-                    d_.g1, d_.g1_gas = g1_, gg_
-                    grid.append((d_, capi.prepare(d_, f_), f_))
-                k += 1
+    for ip in shard.sweep_points(rank, world, k):
+        f_, g1_, gg_ = points[ip]
+        d_ = capi.detector("LUX_Run03")
+        d_.g1, d_.g1_gas = g1_, gg_
+        grid.append((d_, capi.prepare(d_, f_), f_))
     tprep = time.perf_counter() - tprep
     npt = int(a.sweep_events)
     sweep = {"grid": "10 fields x 5 g1 x 5 g1_gas = %d points" % k, "events_per_point": npt,
@@ -524,7 +523,6 @@ def main():
 
     # identical integers at every GPU count: the band of global event ids [0, 8e7) of the bench workload, each rank its
     # contiguous shard, all-reduced; the checksum must not depend on N (test (4))
-    from nest_b200 import shard
     import hashlib
     lo, hi = shard.event_range(rank, world, int(a.checksum_events))
     band_t.zero_()

@@ -16,6 +16,14 @@ def event_range(rank, world, n_total, first_event=0):
     return first_event + lo, first_event + hi
 
 
+def sweep_points(rank, world, n_points):
+    """grid points of a parameter sweep (config 4) that `rank` simulates: dealt round-robin, so that neighbouring
+    points -- which cost about the same -- spread over the ranks.  A point is whole on one rank: no collective."""
+    if world < 1 or not (0 <= rank < world) or n_points < 0:
+        raise ValueError("bad shard request rank=%r world=%r points=%r" % (rank, world, n_points))
+    return list(range(rank, int(n_points), int(world)))
+
+
 def band_words_from_signals(ana, coin_level, signal1, signal2):
     """The integer band accumulator (same words and fixed-point scales as the device kernel,
     include/nest_b200.h) computed on the host from per-event signals: GetBand's binning and
