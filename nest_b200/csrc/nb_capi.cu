@@ -919,8 +919,10 @@ extern "C" {
 int nb200_wimp_prep(double mass, double eStep, double dayNum, uint64_t seed, double* base, double* exponent,
                     double* integral, double* xMaxOut, double* divisorOut) {
   if (!base || !exponent || !integral || !xMaxOut || !divisorOut) return NB200_EINVAL;
+  uint32_t rk[20];
+  philox_round_keys(seed, rk);
   Stream g;
-  g.init(seed, 0, STREAM_HOST);
+  g.init(rk, 0, STREAM_HOST);
   return wimp_prep_core(mass, eStep, dayNum, [&](int* A) { *A = host::select_xe_atom(g); return true; }, base, exponent,
                         integral, xMaxOut, divisorOut);
 }
@@ -946,8 +948,10 @@ double nb200_wimp_drate(double ER_keV, double mass_GeV, double dayNum, int isoto
 }
 
 uint64_t nb200_poisson(double mean, uint64_t seed) {
+  uint32_t rk[20];
+  philox_round_keys(seed, rk);
   HostUrbg u;
-  u.s.init(seed, 1, STREAM_HOST);
+  u.s.init(rk, 1, STREAM_HOST);
   return std::poisson_distribution<uint64_t>(mean)(u);
 }
 
@@ -968,7 +972,7 @@ int nb200_yields(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo,
   P.which = mo->er_model;
   P.density = density;
   P.n = n;
-  P.seed = 0;
+  philox_round_keys(0, P.rk);
   double *dE = nullptr, *dF = nullptr, *dO = nullptr;
   if (mem_kind == NB200_MEM_HOST) {
     cudaError_t e = cudaMalloc(&dE, n * 8);
@@ -1030,7 +1034,7 @@ int nb200_quanta(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo,
   if (P.model.n_widths > 17) P.model.n_widths = 17;
   P.density = density;
   P.n = n;
-  P.seed = seed;
+  philox_round_keys(seed, P.rk);
   P.first_event = first_event;
   std::vector<void*> fr;
   auto cleanup = [&]() {
@@ -1309,6 +1313,7 @@ int nb200_xy_resolution(nb200_ctx* c, const nb200_detector* det, size_t n, const
   if ((r = upload_map(c, &P.det.FitTBA))) return r;
   P.det.FitS1.lut = P.det.FitS2.lut = P.det.FitEF.lut = nullptr;  // not read by xyResolution
   P.seed = seed;
+  philox_round_keys(seed, P.rk);
   P.first_event = first_event;
   Staged st(c, mem_kind);
   XyArgs a;
@@ -1716,6 +1721,7 @@ int nb200_run_sweep(nb200_ctx* c, size_t n_points, const nb200_detector* dets, c
   A.n_per_point = n_events;
   A.n_pad = (n_events + 1023) / 1024 * 1024;
   A.first_event = first_event;
+  philox_round_keys(seed, A.rk);
   const uint64_t total = uint64_t(n_points) * A.n_pad;
   int r = ensure_workspace(c, total, &A.work);
   if (r) return r;
@@ -2279,6 +2285,7 @@ int nb200_se_stats(nb200_ctx* c, const nb200_detector* det, const nb200_run_cons
   P.det.FitEF.lut = nullptr;
   P.s2_center = fit_s2(det->FitS2, 0., 0.);
   P.seed = seed;
+  philox_round_keys(seed, P.rk);
   double* d = nullptr;
   NB_CUDA(c, cudaMalloc(&d, sizeof(double) * n));
   k_se<<<(n + 127) / 128, 128, 0, c->stream>>>(P, n, d);
@@ -2405,8 +2412,10 @@ int nb200_debug_binomial(nb200_ctx* c, uint64_t seed, uint64_t first_event, size
   NB_CUDA(c, cudaSetDevice(c->device));
   long long* dout = nullptr;
   NB_CUDA(c, cudaMalloc(&dout, count * 8));
+  RoundKeys K;
+  philox_round_keys(seed, K.k);
   k_binomial<<<unsigned(std::min<size_t>((count + 255) / 256, 148 * 8)), 256, 0, c->stream>>>(
-      seed, first_event, count, (long long)n, p, dout);
+      K, first_event, count, (long long)n, p, dout);
   ++c->launches;
   cudaMemcpyAsync(out, dout, count * 8, cudaMemcpyDeviceToHost, c->stream);
   cudaError_t e = cudaStreamSynchronize(c->stream);
@@ -2487,8 +2496,10 @@ int nb200_debug_binomial_fixed(nb200_ctx* c, uint64_t seed, uint64_t first_event
     return fail(c, NB200_ENOMEM, "cudaMalloc");
   }
   cudaMemcpyAsync(dtab, tab.data(), sizeof(AliasEntry) * tab.size(), cudaMemcpyHostToDevice, c->stream);
+  RoundKeys K;
+  philox_round_keys(seed, K.k);
   k_binomial_fixed<<<unsigned(std::min<size_t>((count + 255) / 256, 148 * 8)), 256, 0, c->stream>>>(
-      seed, first_event, count, n, static_cast<const uint2*>(dtab), dout);
+      K, first_event, count, n, static_cast<const uint2*>(dtab), dout);
   ++c->launches;
   cudaMemcpyAsync(out, dout, count * 8, cudaMemcpyDeviceToHost, c->stream);
   cudaError_t e = cudaStreamSynchronize(c->stream);
@@ -2512,7 +2523,7 @@ int nb200_lar(nb200_ctx* c, int species, size_t n, const double* E, const double
   std::memset(&P, 0, sizeof P);
   P.species = species;
   P.n = n;
-  P.seed = seed;
+  philox_round_keys(seed, P.rk);
   P.first_event = first_event;
   P.density = density;
   std::vector<void*> fr;

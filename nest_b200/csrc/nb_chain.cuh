@@ -98,7 +98,7 @@ NB_D double fano_er(double density, double Nq_mean, double efield, const double*
 NB_D int to_int_round(double x) { return int(floor(x + 0.5)); }
 
 // NESTcalc::GetQuanta NEST.cpp:248-432
-NB_D Quanta get_quanta(Stream& g, uint64_t seed, uint64_t ev, const Yields& y, double density,
+NB_D Quanta get_quanta(Stream& g, uint64_t ev, const Yields& y, double density,
                        const nb200_detector& det, const nb200_model& mo, int* err, const YieldHoist* h = nullptr) {
   const double* w = mo.NRERWidthsParam;
   Quanta q{0, 0, 0, 0, 0., 0.};
@@ -124,7 +124,7 @@ NB_D Quanta get_quanta(Stream& g, uint64_t seed, uint64_t ev, const Yields& y, d
       double Fano = fano_er(density, Nq_mean, y.field, w, det.inGas != 0);
       Nq_actual = to_int_round(gauss(g, Nq_mean, sqrt(Fano * Nq_mean), true));
     }
-    Ni = int(binomial(seed, ev, STREAM_BIN_NI, Nq_actual, alf));
+    Ni = int(binomial(g.rk, ev, STREAM_BIN_NI, Nq_actual, alf));
     Nex = Nq_actual - Ni;
   } else {
     // two independent Gaussians (:294-311); both come from one Box-Muller pair
@@ -256,7 +256,7 @@ NB_D double s1_eff(const nb200_detector& det, int nHits) {
 }
 
 // GetS1 up to the per-hit loop: NEST.cpp:1288-1362
-NB_D S1Pre s1_prelude(uint64_t ev, const RunParams& P, int Nph, double tx, double ty, double tz,
+NB_D S1Pre s1_prelude(const uint32_t* rk, uint64_t ev, const RunParams& P, int Nph, double tx, double ty, double tz,
                       double sx, double sy, double sz, double energy) {
   const nb200_detector& det = P.det;
   S1Pre r;
@@ -273,7 +273,7 @@ NB_D S1Pre s1_prelude(uint64_t ev, const RunParams& P, int Nph, double tx, doubl
     g1_XYZ = 0.;
     r.posDepSm = 0.;
   }
-  r.nHits = int(binomial(P.seed, ev, STREAM_BIN_S1, Nph, g1_XYZ));
+  r.nHits = int(binomial(rk, ev, STREAM_BIN_S1, Nph, g1_XYZ));
   r.eff = s1_eff(det, r.nHits);
   int mode = P.ana.s1mode;
   if (mode == NB200_S1_HYBRID) mode = energy < 100. ? NB200_S1_FULL : NB200_S1_PARAMETRIC;
@@ -284,9 +284,9 @@ NB_D S1Pre s1_prelude(uint64_t ev, const RunParams& P, int Nph, double tx, doubl
   const int nh = r.full ? r.nHits : 0;
   const bool tab = P.dpe_alias != nullptr && nh < NB_ALIAS_MAXN;  // P_dphe in (0,1) and a moderate hit count
   if (tab)
-    r.nDP = binomial_fixed_p(P.seed, ev, STREAM_BIN_S1DPE, nh, P.dpe_alias);
+    r.nDP = binomial_fixed_p(rk, ev, STREAM_BIN_S1DPE, nh, P.dpe_alias);
   else  // large events (or P_dphe of 0 / 1): the general sampler
-    r.nDP = int(binomial(P.seed, ev, STREAM_BIN_S1DPE + 1u, nh, det.P_dphe));
+    r.nDP = int(binomial(rk, ev, STREAM_BIN_S1DPE + 1u, nh, det.P_dphe));
   return r;
 }
 
@@ -390,11 +390,11 @@ __device__ __noinline__ double pe_redraw(uint64_t seed, uint64_t event, uint32_t
 // Parametric S1, NEST.cpp:1432-1481
 NB_D void s1_parametric(Stream& g, uint64_t ev, const RunParams& P, int nHits, S1Acc& acc) {
   const nb200_detector& det = P.det;
-  int Nphe = nHits + int(binomial(P.seed, ev, STREAM_BIN_PAR0, nHits, det.P_dphe));
+  int Nphe = nHits + int(binomial(g.rk, ev, STREAM_BIN_PAR0, nHits, det.P_dphe));
   double eff = s1_eff(det, nHits);
-  double Nphe_det = double(binomial(P.seed, ev, STREAM_BIN_PAR1, Nphe, 1. - (1. - eff) / (1. + det.P_dphe)));
+  double Nphe_det = double(binomial(g.rk, ev, STREAM_BIN_PAR1, Nphe, 1. - (1. - eff) / (1. + det.P_dphe)));
   acc.area = gauss(g, Nphe_det * (1. / P.rc.NewMean), det.sPEres * sqrt(Nphe_det / P.rc.NewMean), true);
-  acc.spike = int(binomial(P.seed, ev, STREAM_BIN_PAR2, nHits, eff * (1. - P.below_thr_pct)));
+  acc.spike = int(binomial(g.rk, ev, STREAM_BIN_PAR2, nHits, eff * (1. - P.below_thr_pct)));
   acc.nphe = Nphe;
 }
 
@@ -441,10 +441,10 @@ NB_D void s1_epilogue(Stream& g, const RunParams& P, const S1Pre& pre, const S1A
   pulseArea = (pulseArea < 0.) ? 0. : pulseArea;
   if (pulseArea < det.sPEthr) pulseArea = 0.;
   if (spike < 0) spike = 0;
-  double pulseAreaC = pulseArea / pre.posDepSm;
-  double Nphd = pulseArea / (1. + det.P_dphe);
-  double NphdC = pulseAreaC / (1. + det.P_dphe);
-  double spikeC = spike / pre.posDepSm;
+  double pulseAreaC = div_z(pulseArea, pre.posDepSm);
+  double Nphd = div_z(pulseArea, 1. + det.P_dphe);
+  double NphdC = div_z(pulseAreaC, 1. + det.P_dphe);
+  double spikeC = div_z(spike, pre.posDepSm);
   out[0] = pre.nHits;
   out[1] = acc.nphe;
   out[2] = pulseArea;
@@ -522,21 +522,21 @@ NB_D void get_s2(Stream& g, uint64_t ev, const RunParams& P, const PostDraws& D,
     posDepSm = 0.;
   }
   const double life = exp(-dt / det.eLife_us);
-  long long Nee = binomial(P.seed, ev, STREAM_BIN_NEE, Ne, ExtEff * life);
+  long long Nee = binomial(g.rk, ev, STREAM_BIN_NEE, Ne, ExtEff * life);
   double mu = elYield * double(Nee);
   const double z0 = D.z_s2ph, z1 = D.z_s2area;  // one Box-Muller pair: photon number here, pulse area below
   double nraw = mu + sqrt(det.s2Fano * elYield * double(Nee)) * z0;
   double nphd = floor(((nraw < 0.) ? 0. : nraw) + 0.5);
   long long Nph = (long long)nphd;
-  long long nHits = binomial(P.seed, ev, STREAM_BIN_S2HIT, Nph, det.g1_gas * posDep);
+  long long nHits = binomial(g.rk, ev, STREAM_BIN_S2HIT, Nph, det.g1_gas * posDep);
   // second photo-electrons: Binomial(nHits, P_dphe), fixed probability -> alias tables (nb_rng.cuh)
   const bool tab = P.dpe_alias != nullptr && nHits < NB_ALIAS_MAXN;
   long long Nphe = nHits;
   if (tab)
-    Nphe += binomial_fixed_p(P.seed, ev, STREAM_BIN_S2DPE, int(nHits), P.dpe_alias);
+    Nphe += binomial_fixed_p(g.rk, ev, STREAM_BIN_S2DPE, int(nHits), P.dpe_alias);
   else  // very large S2 (or P_dphe of 0 / 1): the general sampler
-    Nphe += binomial(P.seed, ev, STREAM_BIN_S2DPE + 8u, nHits, det.P_dphe);
-  double m = double(Nphe) / P.rc.NewMean;
+    Nphe += binomial(g.rk, ev, STREAM_BIN_S2DPE + 8u, nHits, det.P_dphe);
+  double m = div_z(double(Nphe), P.rc.NewMean);
   double pulseArea = m + det.sPEres * sqrt(m) * z1;
   pulseArea = (pulseArea < 0.) ? 0. : pulseArea;
   double sig;
@@ -547,9 +547,9 @@ NB_D void get_s2(Stream& g, uint64_t ev, const RunParams& P, const PostDraws& D,
     sig = det.noiseLinear[1] * pulseArea;
   if (sig != 0.) pulseArea = pulseArea + sig * D.z_s2noise;  // rand_gauss(pulseArea, sig, true)
   pulseArea = (pulseArea < 0.) ? 0. : pulseArea;
-  double pulseAreaC = pulseArea / life / posDepSm;
-  double Nphd = pulseArea / (1. + det.P_dphe);
-  double NphdC = pulseAreaC / (1. + det.P_dphe);
+  double pulseAreaC = div_z(div_z(pulseArea, life), posDepSm);
+  double Nphd = div_z(pulseArea, 1. + det.P_dphe);
+  double NphdC = div_z(pulseAreaC, 1. + det.P_dphe);
   out[0] = double(Nee);
   out[1] = double(Nph);
   out[2] = double(nHits);
@@ -604,7 +604,7 @@ NB_D double box_reject(Stream& g, double xMin, double xMax, double yMax, const F
     double x = xMin;
     bool need = true;
     {
-      const u128 r = philox_block(g.e0, g.e1, kdone, g.sid, g.k0, g.k1);
+      const u128 r = philox4x32_10_rk(g.e0, g.e1, kdone, g.sid, g.rk);
       const double x0 = xMin + (xMax - xMin) * u53(r.x, r.y);
       const double y0 = yMax * u53(r.z, r.w);
       ++kdone;
@@ -625,7 +625,7 @@ NB_D double box_reject(Stream& g, double xMin, double xMax, double yMax, const F
       bool ok = false;
       double xc = 0.;
       if (serve) {
-        const u128 r = philox_block(te0, te1, tk + uint32_t(t), g.sid, g.k0, g.k1);
+        const u128 r = philox4x32_10_rk(te0, te1, tk + uint32_t(t), g.sid, g.rk);
         xc = xMin + (xMax - xMin) * u53(r.x, r.y);
         const double y0 = yMax * u53(r.z, r.w);
         ok = !(y0 > f(xc));
@@ -823,12 +823,12 @@ struct WimpAttempt {
   bool acc;     // ... and accepted
   bool odd;     // no table interval holds x0: the reference would reuse the previous f (:458) -- replay
 };
-NB_D WimpAttempt wimp_attempt(const RunParams& P, uint32_t e0, uint32_t e1, uint32_t sid, uint32_t k0, uint32_t k1,
+NB_D WimpAttempt wimp_attempt(const RunParams& P, uint32_t e0, uint32_t e1, uint32_t sid, const uint32_t* rk,
                               uint32_t k, double yMax) {
   const nb200_source& S = P.src;
   const double xMax = S.wimp_xMax, step = 1. / S.wimp_divisor;
-  const u128 r = philox_block(e0, e1, 1u + 2u * k, sid, k0, k1);
-  const u128 q = philox_block(e0, e1, 2u + 2u * k, sid, k0, k1);
+  const u128 r = philox4x32_10_rk(e0, e1, 1u + 2u * k, sid, rk);
+  const u128 q = philox4x32_10_rk(e0, e1, 2u + 2u * k, sid, rk);
   WimpAttempt w;
   w.x0 = xMax * u53(r.x, r.y);
   const double y0 = yMax * u53(r.z, r.w);
@@ -854,8 +854,8 @@ NB_D double wimp_sequential(const RunParams& P, const Stream& g, double yMax, ui
   int count = 0;
   double f = 0.00;  // FuncValue persists across tries (:458)
   for (uint32_t k = 0; k < 1000000u; ++k) {
-    const u128 r = philox_block(g.e0, g.e1, 1u + 2u * k, g.sid, g.k0, g.k1);
-    const u128 q = philox_block(g.e0, g.e1, 2u + 2u * k, g.sid, g.k0, g.k1);
+    const u128 r = philox4x32_10_rk(g.e0, g.e1, 1u + 2u * k, g.sid, g.rk);
+    const u128 q = philox4x32_10_rk(g.e0, g.e1, 2u + 2u * k, g.sid, g.rk);
     const double x0 = xMax * u53(r.x, r.y), y0 = yMax * u53(r.z, r.w);
     const double a = P.wimp_dr0[xe_isotope_index(xe_isotope_of(u53(q.x, q.y)))];
     const double b = P.wimp_dr0[xe_isotope_index(xe_isotope_of(u53(q.z, q.w)))];
@@ -873,7 +873,7 @@ NB_D double wimp_sequential(const RunParams& P, const Stream& g, double yMax, ui
 }
 NB_D double wimp_spectrum(Stream& g, const RunParams& P) {
   // requires a fresh stream (the first draw of the event)
-  const u128 r0 = philox_block(g.e0, g.e1, 0u, g.sid, g.k0, g.k1);
+  const u128 r0 = philox4x32_10_rk(g.e0, g.e1, 0u, g.sid, g.rk);
   const double yMax = P.wimp_dr0[xe_isotope_index(xe_isotope_of(u53(r0.x, r0.y)))];
   uint32_t attempts = 0;
   double x = 0.;
@@ -885,7 +885,7 @@ NB_D double wimp_spectrum(Stream& g, const RunParams& P) {
     int count = 0;
     bool need = true, replay = false;
     {
-      const WimpAttempt w = wimp_attempt(P, g.e0, g.e1, g.sid, g.k0, g.k1, 0u, yMax);
+      const WimpAttempt w = wimp_attempt(P, g.e0, g.e1, g.sid, g.rk, 0u, yMax);
       attempts = 1u;
       if (w.odd)
         replay = true, need = false;
@@ -905,7 +905,7 @@ NB_D double wimp_spectrum(Stream& g, const RunParams& P) {
       const uint32_t tk = __shfl_sync(grp, attempts, target);
       const double tyMax = __shfl_sync(grp, yMax, target);
       WimpAttempt w{0., false, false, false};
-      if (serve) w = wimp_attempt(P, te0, te1, g.sid, g.k0, g.k1, tk + uint32_t(t), tyMax);
+      if (serve) w = wimp_attempt(P, te0, te1, g.sid, g.rk, tk + uint32_t(t), tyMax);
       const unsigned pm = __ballot_sync(grp, w.passed), am = __ballot_sync(grp, w.acc), om = __ballot_sync(grp, w.odd);
       int src = lane;
       bool got = false;

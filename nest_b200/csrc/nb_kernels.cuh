@@ -18,7 +18,8 @@ struct YieldsParams {
   nb200_model model;
   int32_t species, which;
   double density;
-  uint64_t n, seed;
+  uint64_t n;
+  uint32_t rk[20];  // Philox round keys of the seed
   const double *E, *field;
   double* out;
 };
@@ -41,11 +42,11 @@ __global__ void __launch_bounds__(256) k_yields(const __grid_constant__ YieldsPa
       const bool nrlike = P.species <= NB200_Cf || P.species == NB200_atmNu;
       if ((nrlike && nearly_equal(P.model.massNum, 0.)) || P.species == NB200_ion) {
         Stream g;
-        g.init(P.seed, i, STREAM_MAIN);
+        g.init(P.rk, i, STREAM_MAIN);
         A2 = select_xe_atom(g);
       } else if (P.species == NB200_Kr83m) {
         Stream g;
-        g.init(P.seed, i, STREAM_MAIN);
+        g.init(P.rk, i, STREAM_MAIN);
         u01 = g.uniform();
       }
       y = get_yields(P.species, E, P.density, F, P.model.massNum, P.model.atomNum, A2, P.det, P.model,
@@ -185,6 +186,7 @@ struct SweepArgs {
   uint64_t n_per_point, n_pad;
   uint64_t slot0, n_slots;  // this launch: slots [slot0, slot0 + n_slots); workspace index = slot - slot0
   uint64_t first_event;
+  uint32_t rk[20];  // Philox round keys of the sweep's seed (one seed for all points): constant-bank operands
   Work work;
 };
 // RunParams of `point` into this block's shared copy (all threads; barriers inside)
@@ -206,12 +208,12 @@ NB_D void soa_put(double* col, uint64_t i, double v, bool f32) {
 }
 
 // one event of k_pre: W index idx (workspace), gidx (index within the call: lists, SoA columns), event id ev
-NB_D void pre_body(const RunParams& P, const Work& W, uint64_t idx, uint64_t gidx, uint64_t ev, bool active,
+NB_D void pre_body(const uint32_t* rk, const RunParams& P, const Work& W, uint64_t idx, uint64_t gidx, uint64_t ev, bool active,
                    int* __restrict__ err_flag) {
   const nb200_detector& det = P.det;
   const bool cli = !P.vec_mode;
   Stream g;
-  g.init(P.seed, ev, STREAM_MAIN);
+  g.init(rk, ev, STREAM_MAIN);
   double px, py, pz, sx, sy, field = 0., dt = 0., vD = P.rc.vD;
   Yields y{0., 0., 0., 0., 0., 0.};
   Quanta q{0, 0, 0, 0, 0., 0.};
@@ -284,7 +286,7 @@ NB_D void pre_body(const RunParams& P, const Work& W, uint64_t idx, uint64_t gid
     }
   }
   NB_LOCKSTEP();
-  if (!cli || keV > 0.001 * P.rc.Wq_eV) q = get_quanta(g, P.seed, ev, y, P.rc.rho, det, P.model, &err, &P.hoist);
+  if (!cli || keV > 0.001 * P.rc.Wq_eV) q = get_quanta(g, ev, y, P.rc.rho, det, P.model, &err, &P.hoist);
   NB_LOCKSTEP();
   if (cli && (det.noiseBaseline[2] != 0. || det.noiseBaseline[3] != 0.))
     q.electrons += to_int_round(gauss(g, det.noiseBaseline[2], det.noiseBaseline[3], false));
@@ -296,7 +298,7 @@ NB_D void pre_body(const RunParams& P, const Work& W, uint64_t idx, uint64_t gid
     if (!P.ana.MCtruthPos && Nphd_S2 > NB_PHE_MIN) xy_resolution(g, det, px, py, Nphd_S2, sx, sy);
   }
   NB_LOCKSTEP();
-  S1Pre pre = s1_prelude(ev, P, q.photons, px, py, pz, sx, sy, pz, keV);
+  S1Pre pre = s1_prelude(rk, ev, P, q.photons, px, py, pz, sx, sy, pz, keV);
   NB_LOCKSTEP();
   if (!active) return;
 
@@ -334,7 +336,7 @@ __global__ void __launch_bounds__(kPreBlock, NB_PRE_MINB)
     const bool active = base + threadIdx.x < P.n_events;
     const uint64_t idx = active ? base + threadIdx.x : P.n_events - 1;
     const uint64_t gidx = P.chunk_off + idx;
-    pre_body(P, P.work, idx, gidx, P.first_event + gidx, active, err_flag);
+    pre_body(P.rk, P, P.work, idx, gidx, P.first_event + gidx, active, err_flag);
   }
 }
 
@@ -352,7 +354,7 @@ __global__ void __launch_bounds__(kPreBlock, NB_PRE_MINB)
     const uint64_t i = slot - uint64_t(point) * A.n_pad + threadIdx.x;  // event index within the point
     const bool active = i < A.n_per_point;
     const uint64_t ie = active ? i : A.n_per_point - 1;
-    pre_body(sP, A.work, base + threadIdx.x, ie, A.first_event + ie, active, err_flag);
+    pre_body(A.rk, sP, A.work, base + threadIdx.x, ie, A.first_event + ie, active, err_flag);
   }
 }
 
@@ -598,6 +600,7 @@ NB_D void hits_finish_body(const RunParams* P0, const SweepArgs* Ap, const HitQu
   // shared-memory tables -- the ziggurat layers are read through L1 from their global copies
   const uint32_t* const s_zk = g_zig_k;
   const double* const s_zw = g_zig_w;
+  const uint32_t* const rk = SWEEP ? Ap->rk : P0->rk;  // kernel-parameter constants either way
   __shared__ __align__(8) SlowItem s_slow[kFinWarps][64];
   __shared__ __align__(8) SlotEntry s_spec[kFinWarps][64];
   const unsigned int n = min(*Q.count, Q.cap);
@@ -612,8 +615,8 @@ NB_D void hits_finish_body(const RunParams* P0, const SweepArgs* Ap, const HitQu
     const FinCtx c = fin_resolve<SWEEP>(P0, Ap, live ? it.e : 0u);
     const RunParams& P = *c.P;
     const uint32_t e0 = uint32_t(c.ev), e1 = uint32_t(c.ev >> 32);
-    const u128 r = philox4x32_10_rk(e0, e1, it.j, STREAM_HIT, P.rk);
-    const u128 t = philox4x32_10_rk(e0, e1, it.j, STREAM_HIT2, P.rk);
+    const u128 r = philox4x32_10_rk(e0, e1, it.j, STREAM_HIT, rk);
+    const u128 t = philox4x32_10_rk(e0, e1, it.j, STREAM_HIT2, rk);
     double v0 = it.v[0], v1 = it.v[1], v2 = it.v[2];
     uint32_t st = live ? it.st : 0u;
 #pragma unroll 1
@@ -671,8 +674,8 @@ NB_D void hits_finish_body(const RunParams* P0, const SweepArgs* Ap, const HitQu
     SlowItem it{en.e, en.j, {0., 0., 0.}, 0u, 0u};
     if (live && !special) {
       const uint32_t e0 = uint32_t(c.ev), e1 = uint32_t(c.ev >> 32);
-      const u128 r = philox4x32_10_rk(e0, e1, en.j, STREAM_HIT, P.rk);
-      const u128 t = philox4x32_10_rk(e0, e1, en.j, STREAM_HIT2, P.rk);
+      const u128 r = philox4x32_10_rk(e0, e1, en.j, STREAM_HIT, rk);
+      const u128 t = philox4x32_10_rk(e0, e1, en.j, STREAM_HIT2, rk);
       const int nv = slot_valid(int(en.j), c.nd, c.nh - c.nd);
 #pragma unroll
       for (int which = 0; which < 3; ++which) {
@@ -749,6 +752,7 @@ NB_D void hits_body(const RunParams* P0, const SweepArgs* Ap, RunParams* sP, uns
                     const HitQueue Q) {
   const RunParams& P = SWEEP ? *sP : *P0;
   const SweepArgs& A = *Ap;  // dereferenced in the sweep instantiation only
+  const uint32_t* const rk = SWEEP ? Ap->rk : P0->rk;  // kernel-parameter constants either way
   __shared__ int s_ppref[kHitGroup + 1];  // slot-count prefix: the flattened work items
   __shared__ int s_nh[kHitGroup];         // hits of the event
   __shared__ int s_nd[kHitGroup];         // of which double-phe
@@ -847,7 +851,7 @@ NB_D void hits_body(const RunParams* P0, const SweepArgs* Ap, RunParams* sP, uns
     PhiloxEvent pev;  // the per-event part of the slot blocks' first Philox round
     {
       const uint64_t hev = ev0 + e;
-      pev = philox_event_prep(uint32_t(hev), uint32_t(hev >> 32), STREAM_HIT, P.rk);
+      pev = philox_event_prep(uint32_t(hev), uint32_t(hev >> 32), STREAM_HIT, rk);
     }
     unsigned long long a_fx = 0ull;
     unsigned int a_spike = 0u;
@@ -869,11 +873,11 @@ NB_D void hits_body(const RunParams* P0, const SweepArgs* Ap, RunParams* sP, uns
           sp = all_special || !(nd + ns > det.coinLevel);
           j = 0;
           const uint64_t hev = ev0 + e;
-          pev = philox_event_prep(uint32_t(hev), uint32_t(hev >> 32), STREAM_HIT, P.rk);
+          pev = philox_event_prep(uint32_t(hev), uint32_t(hev >> 32), STREAM_HIT, rk);
         }
         // one Philox block per slot, 42 bits per photo-electron: 27 (abscissa) + 11 (layer) for the
         // ziggurat normal, 4 for the truncation pre-test
-        const u128 r = philox4x32_10_rk_event(pev, uint32_t(j), P.rk);
+        const u128 r = philox4x32_10_rk_event(pev, uint32_t(j), rk);
         uint32_t A0, A1, A2, L0, L1, L2;
         pe_fields(r, 0, A0, L0);
         pe_fields(r, 1, A1, L1);
@@ -966,14 +970,14 @@ __global__ void __launch_bounds__(kHitBlock, NB_HIT_MINB)
 
 // one event of k_post.  s_band / s_h2: the block's shared-memory band accumulator (band_smem) ; gband: the global
 // accumulator the block flushes into (used directly when the band does not fit in shared memory)
-NB_D void post_body(const RunParams& P, const Work& W, uint64_t idx, uint64_t gidx, uint64_t ev, bool active,
+NB_D void post_body(const uint32_t* rk, const RunParams& P, const Work& W, uint64_t idx, uint64_t gidx, uint64_t ev, bool active,
                     unsigned long long* s_band, unsigned int* s_h2, unsigned long long* gband, bool band_smem,
                     int* __restrict__ err_flag) {
   const nb200_detector& det = P.det;
   const int nb = P.ana.numBins, lb = P.ana.logBins;
   const bool cli = !P.vec_mode;
   Stream g;
-  g.init(P.seed, ev, STREAM_POST);
+  g.init(rk, ev, STREAM_POST);
   double keV = W.keV[idx];
   const double px = W.px[idx], py = W.py[idx], pz = W.pz[idx], sx = W.sx[idx], sy = W.sy[idx];
   const double field = W.field[idx], dt = W.dt[idx];
@@ -1098,7 +1102,7 @@ __global__ void __launch_bounds__(kPostBlock, NB_POST_MINB)
     const bool active = base + tid < P.n_events;
     const uint64_t idx = active ? base + tid : P.n_events - 1;
     const uint64_t gidx = P.chunk_off + idx;
-    post_body(P, P.work, idx, gidx, P.first_event + gidx, active, s_band, s_h2, P.band, band_smem, err_flag);
+    post_body(P.rk, P, P.work, idx, gidx, P.first_event + gidx, active, s_band, s_h2, P.band, band_smem, err_flag);
   }
   if (band_smem) band_smem_flush(s_band, s_h2, nb, lb, P.band);
 }
@@ -1137,7 +1141,7 @@ __global__ void __launch_bounds__(kPostBlock, NB_POST_MINB)
     const bool active = i < A.n_per_point;
     const uint64_t ie = active ? i : A.n_per_point - 1;
     // padding lanes redo the point's last event (its workspace entry is in this tile) and store nothing
-    post_body(sP, A.work, base + (ie - it0), ie, A.first_event + ie, active, s_band, s_h2, gband, band_smem, err_flag);
+    post_body(A.rk, sP, A.work, base + (ie - it0), ie, A.first_event + ie, active, s_band, s_h2, gband, band_smem, err_flag);
   }
   if (cur != 0xffffffffu && band_smem) band_smem_flush(s_band, s_h2, nb, lb, gband);
 }
@@ -1149,14 +1153,14 @@ __global__ void k_se(const __grid_constant__ RunParams P, int n, double* __restr
   const nb200_detector& d = P.det;
   const double elYield = P.rc.g2_params[0];
   Stream g;
-  g.init(P.seed, uint64_t(i), STREAM_SE);
+  g.init(P.rk, uint64_t(i), STREAM_SE);
   long long Nph = (long long)floor(gauss(g, elYield, sqrt(d.s2Fano * elYield), true) + 0.5);
   double sn, cs;
   sincospi(2. * g.uniform(), &sn, &cs);
   const double r = d.radius * sqrt(g.uniform());
   const double posDep = fit_s2(d.FitS2, r * cs, r * sn) / P.s2_center;
-  long long nHits = binomial(P.seed, uint64_t(i), STREAM_BIN_SE_HIT, Nph, d.g1_gas * posDep);
-  double Nphe = double(nHits + binomial(P.seed, uint64_t(i), STREAM_BIN_SE_DPE, nHits, d.P_dphe));
+  long long nHits = binomial(P.rk, uint64_t(i), STREAM_BIN_SE_HIT, Nph, d.g1_gas * posDep);
+  double Nphe = double(nHits + binomial(P.rk, uint64_t(i), STREAM_BIN_SE_DPE, nHits, d.P_dphe));
   double area = gauss(g, Nphe, d.sPEres * sqrt(Nphe), true);
   double sig;
   if (d.noiseQuadratic[1] != 0) {
@@ -1216,17 +1220,23 @@ __global__ void __launch_bounds__(256) k_zignormal(uint64_t seed, uint64_t first
 }
 
 // k_binomial: the binomial sampler alone (test hook, nb200_debug_binomial)
-__global__ void __launch_bounds__(256) k_binomial(uint64_t seed, uint64_t first, size_t count, long long n, double p,
-                                                  long long* __restrict__ out) {
+struct RoundKeys {
+  uint32_t k[20];  // philox_round_keys(seed): a kernel parameter, so constant-bank operands
+};
+__global__ void __launch_bounds__(256) k_binomial(const __grid_constant__ RoundKeys K, uint64_t first, size_t count,
+                                                  long long n, double p, long long* __restrict__ out) {
+  const uint32_t* const rk = K.k;
   for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < count; i += size_t(gridDim.x) * blockDim.x)
-    out[i] = binomial(seed, first + i, STREAM_BIN_S1, n, p);
+    out[i] = binomial(rk, first + i, STREAM_BIN_S1, n, p);
 }
 
 // test hook (nb200_debug_binomial_fixed): the alias-table sampler of k_pre's double-phe count
-__global__ void __launch_bounds__(256) k_binomial_fixed(uint64_t seed, uint64_t first, size_t count, int n,
-                                                        const uint2* __restrict__ tab, long long* __restrict__ out) {
+__global__ void __launch_bounds__(256) k_binomial_fixed(const __grid_constant__ RoundKeys K, uint64_t first,
+                                                        size_t count, int n, const uint2* __restrict__ tab,
+                                                        long long* __restrict__ out) {
+  const uint32_t* const rk = K.k;
   for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < count; i += size_t(gridDim.x) * blockDim.x)
-    out[i] = binomial_fixed_p(seed, first + i, STREAM_BIN_S1DPE, n, tab);
+    out[i] = binomial_fixed_p(rk, first + i, STREAM_BIN_S1DPE, n, tab);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -1238,7 +1248,8 @@ struct QuantaParams {
   nb200_detector det;
   nb200_model model;
   double density;
-  uint64_t n, seed, first_event;
+  uint64_t n, first_event;
+  uint32_t rk[20];  // Philox round keys of the seed
   const double* y;
   int32_t* qi;
   double* qd;
@@ -1256,9 +1267,9 @@ __global__ void __launch_bounds__(256) k_quanta(const __grid_constant__ QuantaPa
     y.dT = P.y[5 * P.n + i];
     const uint64_t ev = P.first_event + i;
     Stream g;
-    g.init(P.seed, ev, STREAM_MAIN);
+    g.init(P.rk, ev, STREAM_MAIN);
     int err = 0;
-    const Quanta q = get_quanta(g, P.seed, ev, y, P.density, P.det, P.model, &err);
+    const Quanta q = get_quanta(g, ev, y, P.density, P.det, P.model, &err);
     if (err) atomicOr(err_flag, err);
     P.qi[i] = q.photons;
     P.qi[P.n + i] = q.electrons;
@@ -1283,7 +1294,7 @@ __global__ void __launch_bounds__(256) k_s2(const __grid_constant__ RunParams P,
   for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < a.n; i += uint64_t(gridDim.x) * blockDim.x) {
     const uint64_t ev = P.first_event + i;
     Stream g;
-    g.init(P.seed, ev, STREAM_POST);
+    g.init(P.rk, ev, STREAM_POST);
     double o[9];
     const PostDraws D = post_draws(g);
     get_s2(g, ev, P, D, a.Ne[i], a.pos[i], a.pos[a.n + i], a.pos[2 * a.n + i], a.pos[3 * a.n + i], a.pos[4 * a.n + i], a.dt[i],
@@ -1310,7 +1321,7 @@ __global__ void __launch_bounds__(256) k_s1pre(const __grid_constant__ RunParams
   for (uint64_t idx = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; idx < P.n_events;
        idx += uint64_t(gridDim.x) * blockDim.x) {
     const uint64_t gi = a.off + idx, ev = P.first_event + P.chunk_off + idx;
-    const S1Pre pre = s1_prelude(ev, P, a.Nph[gi], a.pos[gi], a.pos[a.stride + gi], a.pos[2 * a.stride + gi],
+    const S1Pre pre = s1_prelude(P.rk, ev, P, a.Nph[gi], a.pos[gi], a.pos[a.stride + gi], a.pos[2 * a.stride + gi],
                                  a.pos[3 * a.stride + gi], a.pos[4 * a.stride + gi], a.pos[5 * a.stride + gi], a.energy[gi]);
     W.posDepSm[idx] = pre.posDepSm;
     W.fitSm[idx] = pre.fitSm;
@@ -1325,7 +1336,7 @@ __global__ void __launch_bounds__(256) k_s1post(const __grid_constant__ RunParam
        idx += uint64_t(gridDim.x) * blockDim.x) {
     const uint64_t gi = a.off + idx, ev = P.first_event + P.chunk_off + idx;
     Stream g;
-    g.init(P.seed, ev, STREAM_POST);
+    g.init(P.rk, ev, STREAM_POST);
     S1Pre pre;
     pre.posDepSm = W.posDepSm[idx];
     pre.fitSm = W.fitSm[idx];
@@ -1486,7 +1497,7 @@ __global__ void __launch_bounds__(256) k_spike(const __grid_constant__ RunParams
       o1 = s5;
     } else {
       Stream g;
-      g.init(P.seed, P.first_event + i, STREAM_POST);
+      g.init(P.rk, P.first_event + i, STREAM_POST);
       o0 = zero_trunc_gauss(g, s6, (P.det.sPEres / 4.) * sqrt(fabs(s6)));
       o1 = o0 / fit_s1(P.det.FitS1, a.pos[i], a.pos[a.n + i], a.pos[2 * a.n + i]) * P.s1_center;
     }
@@ -1504,7 +1515,7 @@ struct XyArgs {
 __global__ void __launch_bounds__(256) k_xyres(const __grid_constant__ RunParams P, const XyArgs a) {
   for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < a.n; i += uint64_t(gridDim.x) * blockDim.x) {
     Stream g;
-    g.init(P.seed, P.first_event + i, STREAM_MAIN);
+    g.init(P.rk, P.first_event + i, STREAM_MAIN);
     double sx, sy;
     xy_resolution(g, P.det, a.x[i], a.y[i], a.A_top[i], sx, sy);
     a.out[i] = sx;
@@ -1521,7 +1532,7 @@ __global__ void __launch_bounds__(256) k_spectrum(const __grid_constant__ RunPar
     const bool active = i < P.n_events;
     const uint64_t ie = active ? i : P.n_events - 1;
     Stream g;
-    g.init(P.seed, P.first_event + ie, STREAM_MAIN);
+    g.init(P.rk, P.first_event + ie, STREAM_MAIN);
     const double keV = sample_energy(g, P, ie);
     if (active) out[i] = keV;
   }
@@ -1531,7 +1542,8 @@ __global__ void __launch_bounds__(256) k_spectrum(const __grid_constant__ RunPar
 // -------------------------------------------------------------------------------------------
 struct LArParams {
   int32_t species;
-  uint64_t n, seed, first_event;
+  uint64_t n, first_event;
+  uint32_t rk[20];  // Philox round keys of the seed
   double density;
   const double *E, *field;
   double *yields, *fluct;  // [9][n], [4][n]; either may be null
@@ -1559,9 +1571,9 @@ __global__ void __launch_bounds__(256) k_lar(const __grid_constant__ LArParams P
     }
     if (P.fluct) {
       Stream g;
-      g.init(P.seed, P.first_event + i, STREAM_LAR);
+      g.init(P.rk, P.first_event + i, STREAM_LAR);
       double f[4];
-      lar_fluctuations(g, P.seed, P.first_event + i, y, f);
+      lar_fluctuations(g, P.first_event + i, y, f);
       P.fluct[i] = f[0];
       P.fluct[P.n + i] = f[1];
       P.fluct[2 * P.n + i] = f[2];

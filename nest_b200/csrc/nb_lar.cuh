@@ -116,7 +116,7 @@ NB_D LArYields lar_yields(int species, double energy, double efield, double dens
 }
 
 // GetDefaultFluctuations LArNEST.cpp:363-406.  out = {Nph, Ne, Nex, Nion fluctuated}
-NB_D void lar_fluctuations(Stream& g, uint64_t seed, uint64_t ev, const LArYields& y, double* out) {
+NB_D void lar_fluctuations(Stream& g, uint64_t ev, const LArYields& y, double* out) {
   const double Fano = 0.1115;
   double NexOverNion = y.Nex / y.Nion;
   double p_r = (y.Nph - y.Nex) / y.Nion;
@@ -126,7 +126,7 @@ NB_D void lar_fluctuations(Stream& g, uint64_t seed, uint64_t ev, const LArYield
   if (y.Lindhard == 1.) {  // exact comparison, as the reference (:374)
     Nq = floor(gauss(g, Nq_mean, sqrt(Fano * Nq_mean), true) + 0.5);
     if (Nq < 0.) Nq = 0.;
-    Nion = double(binomial(seed, ev, STREAM_BIN_LAR, (long long)Nq, alf));
+    Nion = double(binomial(g.rk, ev, STREAM_BIN_LAR, (long long)Nq, alf));
     if (Nion > Nq) Nion = Nq;
     Nex = Nq - Nion;
   } else {

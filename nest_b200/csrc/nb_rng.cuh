@@ -83,18 +83,20 @@ NB_HD u128 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uin
 }
 
 #ifdef __CUDACC__
-// Out-of-line copy for the per-event scalar streams: those stages are long straight-line code
-// whose cost is instruction fetch, so the ~60-instruction block function is shared, not inlined.
-// (The S1 hit loop inlines philox4x32_10 directly.)
+// Out-of-line copy for the rare completions of the hit loop (zig_finish, pe_redraw): those are subroutines of
+// k_hits and its finisher, and what they need in registers is taken from the callers' budget -- with the block
+// function in line they cost the hit loop its spill-free main loop (152 bytes of spills, k_hits + 12 %).
 __device__ __noinline__ u128 philox_block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
                                           uint32_t k1) {
   return philox4x32_10(c0, c1, c2, c3, k0, k1);
 }
 #endif
 
-// Same function with the 10 round keys taken from a precomputed table (rk[2r], rk[2r+1]); in the
-// hit loop the table sits in the kernel's constant bank, so each round is two IMAD.WIDE and two
-// three-input LOP3 with a constant operand -- no key-schedule adds.
+// Same function with the 10 round keys taken from a precomputed table (rk[2r], rk[2r+1]).  The kernels
+// pass a pointer into their own parameter block (RunParams::rk, SweepArgs::rk, ...): once everything is
+// inlined the table is a constant-bank operand, so each round is two IMAD.WIDE and two three-input LOP3
+// with a constant operand -- no key-schedule adds (2 of the 6 instructions of a round; the scalar stages
+// k_pre / k_post issue-bind in their Philox phases, all warps of a block being in step).
 NB_HD void philox_round_keys(uint64_t seed, uint32_t* rk) {
   uint32_t k0 = uint32_t(seed), k1 = uint32_t(seed >> 32);
   for (int r = 0; r < 10; ++r) {
@@ -164,15 +166,16 @@ NB_HD double u53(uint32_t hi, uint32_t lo) {
 // 32-bit uniform on (0,1) for yes/no decisions and angles
 NB_HD double u32d(uint32_t a) { return (double(a) + 0.5) * 2.3283064365386962891e-10; }
 
-// Sequential stream over one (seed, event, stream) triple.
+// Sequential stream over one (seed, event, stream) triple; the seed comes as its 20 round keys
+// (philox_round_keys), which the stream only points to.
 struct Stream {
-  uint32_t k0, k1, e0, e1, blk, sid;
+  const uint32_t* rk;
+  uint32_t e0, e1, blk, sid;
   uint32_t s0, s1;  // second half of the last block
   bool have;
 
-  NB_HD void init(uint64_t seed, uint64_t event, uint32_t stream) {
-    k0 = uint32_t(seed);
-    k1 = uint32_t(seed >> 32);
+  NB_HD void init(const uint32_t* keys, uint64_t event, uint32_t stream) {
+    rk = keys;
     e0 = uint32_t(event);
     e1 = uint32_t(event >> 32);
     blk = 0;
@@ -187,11 +190,7 @@ struct Stream {
       b = s1;
       return;
     }
-#ifdef __CUDA_ARCH__
-    u128 r = philox_block(e0, e1, blk, sid, k0, k1);
-#else
-    u128 r = philox4x32_10(e0, e1, blk, sid, k0, k1);
-#endif
+    u128 r = philox4x32_10_rk(e0, e1, blk, sid, rk);
     ++blk;
     s0 = r.z;
     s1 = r.w;
@@ -580,8 +579,10 @@ NB_D double log_factorial(double k) {
 
 // binom_draw RandomGen.cpp:132-134 = std::binomial_distribution<int64_t>(n,p).  Exact binomial sampler:
 // sequential CDF inversion while n*min(p,1-p) < 10, Hormann's BTRS transformed rejection (J. Stat. Comput.
-// Simul. 46 (1993) 101) above.  Draws from its own counter stream (seed; event, stream) -- candidate k of a
-// BTRS draw is Philox block k of that stream -- so that it can live out of line.
+// Simul. 46 (1993) 101) above.  Draws from its own counter stream (seed; event, stream): candidate k of a
+// BTRS draw is Philox block k of that stream.  In line at its call sites (with the block function): the
+// scalar stages run their blocks in step, so code size costs nothing, and the inlined Philox reads its round
+// keys as constant operands (measured against the out-of-line version: k_pre -3.5 %, k_post -4 %).
 //
 // BTRS accepts ~75 % of its candidates on a cheap test; the others need the exact log-pmf ratio
 //     ln f(k)/f(m) = ln m! + ln (n-m)! - ln k! - ln (n-k)! + (k - m) ln(p/q),   m = floor((n+1) p).
@@ -592,34 +593,37 @@ NB_D double log_factorial(double k) {
 // ln k! to 1e-16 relative; the sum of four terms of up to 1e6 carries ~1e-9 of absolute error, i.e. the
 // acceptance probability of a candidate is exact to ~1e-9 relative (tests/test_gpu_samplers.py: chi^2
 // against the exact pmf, n up to 1.2e6).
-__device__ __noinline__ long long binomial(uint64_t seed, uint64_t event, uint32_t stream, long long n,
-                                           double p) {
+NB_D long long binomial(const uint32_t* rk, uint64_t event, uint32_t stream, long long n, double p) {
   if (!(n > 0) || !(p > 0.)) return 0;
   if (p >= 1.) return n;
   const bool flip = p > 0.5;
   const double pp = flip ? 1. - p : p;
   const double q = 1. - pp;
   const double dn = double(n);
-  const uint32_t k0 = uint32_t(seed), k1 = uint32_t(seed >> 32), e0 = uint32_t(event), e1 = uint32_t(event >> 32);
+  const uint32_t e0 = uint32_t(event), e1 = uint32_t(event >> 32);
   long long k = 0;
   if (dn * pp < 10.) {
     // q^n = exp(n ln q), q in [1/2, 1): the bit-built logarithm (absolute error ~1e-16, times n < 10/pp)
     const double r0 = exp(dn * log_pos(q));
     const double s = pp / q;
     for (uint32_t att = 0;; ++att) {  // one uniform per attempt: words (x,y), then (z,w) of block att/2
-      const u128 w = philox_block(e0, e1, att >> 1, stream, k0, k1);
+      const u128 w = philox4x32_10_rk(e0, e1, att >> 1, stream, rk);
       double u = (att & 1u) ? u53(w.z, w.w) : u53(w.x, w.y);
       double r = r0;
-      long long x = 0;
+      // x counts up as an int, n - x + 1 down as a double (integers below 2^53: the same values as the
+      // 64-bit integer arithmetic it replaces, without its conversions)
+      int x = 0;
+      double left = dn;  // n - x
       bool ok = true;
       while (u > r) {
         u -= r;
         ++x;
-        if (x > n || x > 200) {
+        if (left < 1. || x > 200) {  // x > n
           ok = false;
           break;
         }
-        r *= s * (double(n - x + 1) * __ldg(&g_rcptab[x]));  // x <= 200
+        r *= s * (left * __ldg(&g_rcptab[x]));  // x <= 200
+        left -= 1.;
       }
       if (ok) {
         k = x;
@@ -640,7 +644,7 @@ __device__ __noinline__ long long binomial(uint64_t seed, uint64_t event, uint32
     const double logr = log_pos(pp / q);
     double kk = 0.;
     for (uint32_t att = 0;; ++att) {
-      const u128 w = philox_block(e0, e1, att, stream, k0, k1);
+      const u128 w = philox4x32_10_rk(e0, e1, att, stream, rk);
       const double u = u53(w.x, w.y) - 0.5;
       const double v = u53(w.z, w.w);
       const double us = 0.5 - fabs(u);
@@ -672,9 +676,10 @@ NB_D int alias_draw(const uint2* __restrict__ t, uint32_t K, uint32_t w) {
   const uint2 en = __ldg(t + idx);
   return uint32_t(pr) < en.x ? int(idx) : int(en.y);
 }
-NB_D int binomial_fixed_p(uint64_t seed, uint64_t event, uint32_t stream, int n, const uint2* __restrict__ tab) {
+NB_D int binomial_fixed_p(const uint32_t* rk, uint64_t event, uint32_t stream, int n,
+                          const uint2* __restrict__ tab) {
   Stream g;
-  g.init(seed, event, stream);
+  g.init(rk, event, stream);
   uint32_t a = 0u, b = 0u;
   bool have = false;
   int k = 0;

@@ -34,7 +34,20 @@ NB_HD bool nearly_equal(double a, double b, double eps = 1e-9) {
   if (a == b) return true;
   double absA = fabs(a), absB = fabs(b), diff = fabs(a - b);
   if (a == 0 || b == 0 || (absA + absB < DBL_MIN)) return diff < (eps * DBL_MIN);
-  return diff / fmin(absA + absB, DBL_MAX) < eps;
+  const double sum = fmin(absA + absB, DBL_MAX);
+  // diff / sum < eps, decided without the division unless the quotient is within a factor two of eps
+  if (diff > 2. * eps * sum) return false;
+  if (diff < 0.5 * eps * sum) return true;
+  return diff / sum < eps;
+}
+
+// a / b for a numerator that is often exactly zero (an event without a signal) and a positive finite b: the
+// quotient is then a itself, and the division is given a numerator of one so that it stays on its in-line
+// path (a zero numerator sends the lane through the out-of-line special-case routine, ~60 instructions)
+NB_HD double div_z(double a, double b) {
+  const bool z = a == 0. && b > 0. && b < DBL_MAX;
+  const double q = (z ? 1. : a) / b;
+  return z ? a : q;
 }
 
 struct Yields {  // YieldResult NEST.hh:162-169

@@ -44,8 +44,10 @@ int main() {
     }
   }
   {  // Stream: blocks 0, 1, 2, ... of (seed; event, block, stream), words (x,y) then (z,w)
+    uint32_t keys[20];
+    philox_round_keys(42ull, keys);
     Stream g;
-    g.init(42ull, 0x100000007ull, STREAM_POST);
+    g.init(keys, 0x100000007ull, STREAM_POST);
     for (uint32_t blk = 0; blk < 50; ++blk) {
       const u128 r = philox4x32_10(7u, 1u, blk, STREAM_POST, 42u, 0u);
       uint32_t a, b;
