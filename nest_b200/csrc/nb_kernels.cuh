@@ -81,29 +81,36 @@ __global__ void __launch_bounds__(256) k_yields(const __grid_constant__ YieldsPa
 //           S2, signal selection, energy reconstruction, band accumulation (shared-memory
 //           integer accumulators flushed once per block) and the optional SoA record.
 // -------------------------------------------------------------------------------------------
+// block-wide exclusive prefix sum of a pair of counts (k_hits: slots, and events that have slots)
 template <int T>
-__device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp) {
+__device__ __forceinline__ int2 block_exclusive_scan2(int2 v, int2* s_warp) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  int x = v;
+  int2 x = v;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    int t = __shfl_up_sync(0xffffffffu, x, o);
-    if (lane >= o) x += t;
+    const int tx = __shfl_up_sync(0xffffffffu, x.x, o), ty = __shfl_up_sync(0xffffffffu, x.y, o);
+    if (lane >= o) {
+      x.x += tx;
+      x.y += ty;
+    }
   }
   if (lane == 31) s_warp[wid] = x;
   __syncthreads();
   if (wid == 0) {
-    int w = (lane < T / 32) ? s_warp[lane] : 0;
+    int2 w = (lane < T / 32) ? s_warp[lane] : make_int2(0, 0);
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      int t = __shfl_up_sync(0xffffffffu, w, o);
-      if (lane >= o) w += t;
+      const int tx = __shfl_up_sync(0xffffffffu, w.x, o), ty = __shfl_up_sync(0xffffffffu, w.y, o);
+      if (lane >= o) {
+        w.x += tx;
+        w.y += ty;
+      }
     }
     if (lane < T / 32) s_warp[lane] = w;
   }
   __syncthreads();
-  int base = wid ? s_warp[wid - 1] : 0;
-  return base + x - v;
+  const int2 base = wid ? s_warp[wid - 1] : make_int2(0, 0);
+  return make_int2(base.x + x.x - v.x, base.y + x.y - v.y);
 }
 
 // GetDriftVelocity_Liquid (NEST.cpp:2482-2502) for the detector temperature; the two
@@ -753,12 +760,18 @@ NB_D void hits_body(const RunParams* P0, const SweepArgs* Ap, RunParams* sP, uns
   const RunParams& P = SWEEP ? *sP : *P0;
   const SweepArgs& A = *Ap;  // dereferenced in the sweep instantiation only
   const uint32_t* const rk = SWEEP ? Ap->rk : P0->rk;  // kernel-parameter constants either way
-  __shared__ int s_ppref[kHitGroup + 1];  // slot-count prefix: the flattened work items
+  // the flattened work items: the group's events that have slots, in order -- {end of the event's slots in the
+  // group's slot numbering, event index in the group | its special flag << 31, double-phe hits, single hits};
+  // entry [number of such events] is a sentinel no slot index reaches
+  __shared__ __align__(16) uint4 s_rec[kHitGroup + 1];
   __shared__ int s_nh[kHitGroup];         // hits of the event
   __shared__ int s_nd[kHitGroup];         // of which double-phe
-  __shared__ unsigned long long s_area[kHitGroup];
+  __shared__ unsigned long long s_area[kHitGroup];   // the main loop's sums
   __shared__ unsigned int s_spike[kHitGroup];
-  __shared__ int s_warp[32];
+  __shared__ unsigned long long s_farea[kHitGroup];  // what hits_finish_slow adds (kept apart: see the flush below)
+  __shared__ unsigned int s_fspike[kHitGroup];
+  __shared__ int2 s_warp[32];
+  __shared__ int s_tot[2];  // slots, events with slots
   __shared__ __align__(8) SlotEntry s_q[kHitBlock / 32][kSlotCap];
   extern __shared__ __align__(16) double s_zw[];  // kHitDynSmem: zw[NB_ZIG_N] then zk[NB_ZIG_N]
   uint32_t* const s_zk = reinterpret_cast<uint32_t*>(s_zw + NB_ZIG_N);
@@ -799,9 +812,9 @@ NB_D void hits_body(const RunParams* P0, const SweepArgs* Ap, RunParams* sP, uns
     } else
       ev0 = P0->first_event + P0->chunk_off + gbase;
     const bool all_special = det.sPEeff < 1.;  // efficiency draws: every slot goes through the finisher
-    // slot counts of my PER consecutive events -> exclusive prefix over the group
-    int cnt[PER];
-    int mine = 0;
+    // slot counts of my PER consecutive events -> exclusive prefix over the group, and the list of events with slots
+    int cnt[PER], nhs[PER], nds[PER];
+    int2 mine = make_int2(0, 0);
 #pragma unroll
     for (int k = 0; k < PER; ++k) {
       const uint64_t idx = gbase + uint64_t(tid) * PER + k;
@@ -810,43 +823,58 @@ NB_D void hits_body(const RunParams* P0, const SweepArgs* Ap, RunParams* sP, uns
       int nd = (idx < n_valid) ? W.nphe[idx] : 0;  // k_pre left the double-phe count here
       nd = nd < 0 ? 0 : (nd > nh ? nh : nd);
       cnt[k] = hit_slots(nh, nd);
-      mine += cnt[k];
+      nhs[k] = nh;
+      nds[k] = nd;
+      mine.x += cnt[k];
+      mine.y += cnt[k] > 0 ? 1 : 0;
       s_nh[tid * PER + k] = nh;
       s_nd[tid * PER + k] = nd;
       s_area[tid * PER + k] = 0ull;
       s_spike[tid * PER + k] = 0u;
+      s_farea[tid * PER + k] = 0ull;
+      s_fspike[tid * PER + k] = 0u;
     }
-    int off = block_exclusive_scan<kHitBlock>(mine, s_warp);
+    int2 off = block_exclusive_scan2<kHitBlock>(mine, s_warp);
 #pragma unroll
     for (int k = 0; k < PER; ++k) {
-      s_ppref[tid * PER + k] = off;
-      off += cnt[k];
+      if (cnt[k] > 0) {
+        off.x += cnt[k];
+        const bool spk = all_special || !(nhs[k] > det.coinLevel);
+        s_rec[off.y++] = make_uint4(uint32_t(off.x), uint32_t(tid * PER + k) | (spk ? 0x80000000u : 0u), uint32_t(nds[k]),
+                                    uint32_t(nhs[k] - nds[k]));
+      }
     }
-    if (tid == kHitBlock - 1) s_ppref[kHitGroup] = off;
+    if (tid == kHitBlock - 1) {
+      s_tot[0] = off.x;
+      s_tot[1] = off.y;
+      s_rec[off.y] = make_uint4(0x7fffffffu, 0u, 0u, 0u);
+    }
     __syncthreads();
-    const int H = s_ppref[kHitGroup];  // slots in this group
+    const int H = s_tot[0];  // slots in this group
     const int h0 = int((long long)H * tid / kHitBlock);
     const int h1 = int((long long)H * (tid + 1) / kHitBlock);
     const int maxlen = __reduce_max_sync(0xffffffffu, h1 - h0);
-    int e = 0, e_end = 0, nd = 0, ns = 0, j = 0;
+    int c = 0, e = 0, e_end = 0, nd = 0, ns = 0, j = 0;
     bool sp = false;
     int h = h0;  // running slot index; this thread owns [h0, h1)
     if (h1 > h0) {
-      // event owning slot h0: largest e with s_ppref[e] <= h0
-      int lo = 0, hi = kHitGroup;
+      // the event owning slot h0: the first entry whose slots end beyond h0
+      int lo = -1, hi = s_tot[1] - 1;  // end[lo] <= h0 < end[hi]
       while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (s_ppref[mid] <= h0)
+        const int mid = (lo + hi) >> 1;
+        if (int(s_rec[mid].x) <= h0)
           lo = mid;
         else
           hi = mid;
       }
-      e = lo;
-      e_end = s_ppref[e + 1];
-      nd = s_nd[e];
-      ns = s_nh[e] - nd;
-      sp = all_special || !(nd + ns > det.coinLevel);
-      j = h0 - s_ppref[e];
+      c = hi;
+      const uint4 rec = s_rec[c];
+      e = int(rec.y & 0x7fffffffu);
+      sp = (rec.y >> 31) != 0u;
+      e_end = int(rec.x);
+      nd = int(rec.z);
+      ns = int(rec.w);
+      j = h0 - (c > 0 ? int(s_rec[c - 1].x) : 0);
     }
     PhiloxEvent pev;  // the per-event part of the slot blocks' first Philox round
     {
@@ -855,22 +883,36 @@ NB_D void hits_body(const RunParams* P0, const SweepArgs* Ap, RunParams* sP, uns
     }
     unsigned long long a_fx = 0ull;
     unsigned int a_spike = 0u;
+    // An event a thread crosses INTO and later out of lies wholly inside its slot range: nobody else's main loop adds
+    // to it, so its sums are stored, not added.  Only the first event of the range (it may have begun in the previous
+    // thread's) and the last (flushed after the loop) go through the shared-memory atomics.  A lane crosses every
+    // ~27 slots, a warp in 70 % of its iterations, at 1-2 active lanes: the crossing is one record load, two stores
+    // and the per-event part of the Philox block (it was the atomics with their carry, a walk over the events
+    // without slots and four dependent loads: 12 % of the kernel's warp instructions).
+    bool first = true;
     int qcount = 0;  // warp-uniform queue fill
     for (int it = maxlen; it > 0; --it) {
       bool queue = false;
       if (h < h1) {
-        if (h == e_end) {  // crossed into the next event with hits: flush, then advance
-          smem_add64(&s_area[e], a_fx - (unsigned long long)a_spike * NB_AREA_MAGIC_BITS);
-          atomicAdd(&s_spike[e], a_spike);
+        if (h == e_end) {  // crossed into the next event with slots: flush, then advance
+          const unsigned long long a_ev = a_fx - (unsigned long long)a_spike * NB_AREA_MAGIC_BITS;
+          if (first) {
+            smem_add64(&s_area[e], a_ev);
+            atomicAdd(&s_spike[e], a_spike);
+            first = false;
+          } else {
+            s_area[e] = a_ev;
+            s_spike[e] = a_spike;
+          }
           a_fx = 0ull;
           a_spike = 0u;
-          do {
-            ++e;
-            e_end = s_ppref[e + 1];
-          } while (e_end == h);
-          nd = s_nd[e];
-          ns = s_nh[e] - nd;
-          sp = all_special || !(nd + ns > det.coinLevel);
+          ++c;
+          const uint4 rec = s_rec[c];
+          e = int(rec.y & 0x7fffffffu);
+          sp = (rec.y >> 31) != 0u;
+          e_end = int(rec.x);
+          nd = int(rec.z);
+          ns = int(rec.w);
           j = 0;
           const uint64_t hev = ev0 + e;
           pev = philox_event_prep(uint32_t(hev), uint32_t(hev >> 32), STREAM_HIT, rk);
@@ -927,7 +969,7 @@ NB_D void hits_body(const RunParams* P0, const SweepArgs* Ap, RunParams* sP, uns
           qcount -= 32;
           // hand the 32 entries at [qcount, qcount + 32) to the deferred finisher
           if (!queue_push(Q, all_special, &s_q[wid][qcount], 32, lane, uint32_t(gbase)))
-            hits_finish_slow(P, s_nh, s_nd, s_area, s_spike, ev0, &s_q[wid][qcount], 32, lane, s_zk, s_zw);
+            hits_finish_slow(P, s_nh, s_nd, s_farea, s_fspike, ev0, &s_q[wid][qcount], 32, lane, s_zk, s_zw);
         }
       }
       ++j;
@@ -935,7 +977,7 @@ NB_D void hits_body(const RunParams* P0, const SweepArgs* Ap, RunParams* sP, uns
     }
     if (qcount > 0) {  // the group's leftovers
       if (!queue_push(Q, all_special, &s_q[wid][0], qcount, lane, uint32_t(gbase)))
-        hits_finish_slow(P, s_nh, s_nd, s_area, s_spike, ev0, &s_q[wid][0], qcount, lane, s_zk, s_zw);
+        hits_finish_slow(P, s_nh, s_nd, s_farea, s_fspike, ev0, &s_q[wid][0], qcount, lane, s_zk, s_zw);
     }
     if (h1 > h0) {
       smem_add64(&s_area[e], a_fx - (unsigned long long)a_spike * NB_AREA_MAGIC_BITS);
@@ -947,8 +989,8 @@ NB_D void hits_body(const RunParams* P0, const SweepArgs* Ap, RunParams* sP, uns
       const int i = jj * kHitBlock + tid;  // coalesced
       const uint64_t idx = gbase + i;
       if (idx < n_valid) {
-        reinterpret_cast<unsigned long long*>(W.area)[idx] = s_area[i];  // 2^-32 phe; the finisher adds to it
-        W.spike[idx] = int(s_spike[i]);
+        reinterpret_cast<unsigned long long*>(W.area)[idx] = s_area[i] + s_farea[i];  // 2^-32 phe; the finisher adds to it
+        W.spike[idx] = int(s_spike[i] + s_fspike[i]);
         W.nphe[idx] = s_nh[i] + s_nd[i];
       }
     }
