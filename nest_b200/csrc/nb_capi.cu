@@ -64,6 +64,7 @@ struct nb200_ctx {
   // k_pre -> k_hits -> k_post workspace (one chunk)
   void* d_work = nullptr;
   uint64_t work_cap = 0;
+  int chunk_log2 = 24;  // chunk_events(); NB200_CHUNK_LOG2 overrides
   int occ_pre = 0, occ_hits = 0, occ_post = 0;
   std::vector<double> vtable_host;
   nb200_detector vtable_det;
@@ -425,24 +426,34 @@ int build_params(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo,
   return 0;
 }
 
-// events per internal chunk: the workspace holds one chunk (140 B/event); large enough that the
-// ragged last wave of each kernel is a few per cent of its run time
-// ~2^22, rounded to a whole number of waves of the one-block-per-SM lockstep kernel (k_post: sm_count blocks
-// of 1024 events per sweep; 28 sweeps of 148 x 1024 on B200), which also makes it a whole number of k_hits
-// groups per resident block
+// events per internal chunk: the workspace holds one chunk (140 B/event, + 48 B/event of deferred queue).
+// ~2^chunk_log2, rounded to a whole number of waves of the one-block-per-SM lockstep kernel (k_post: sm_count
+// blocks of 1024 events per sweep; 113 sweeps of 148 x 1024 on B200 at 2^24), which also makes it a whole number of
+// k_hits groups per resident block.  Every chunk costs four kernel boundaries (drain, launch, ramp, the blocks'
+// table loads and band flushes) of ~20 us each; measured on B200, 10^8 events: 2^21 83.1 ms, 2^22 80.7, 2^23 79.2,
+// 2^24 78.8, 2^25 78.6, 2^26 78.6.  2^24 (3.2 GB of device memory once a call is that large) is the default;
+// a device that cannot give that much falls back to smaller chunks (ensure_workspace).
 uint64_t chunk_events(const nb200_ctx* c) {
   const uint64_t wave = uint64_t(c->sm_count > 0 ? c->sm_count : 148) * 1024u;
-  return std::max<uint64_t>(1, ((1ull << 22) + wave / 2) / wave) * wave;
+  return std::max<uint64_t>(1, ((1ull << c->chunk_log2) + wave / 2) / wave) * wave;
 }
 
 int ensure_workspace(nb200_ctx* c, uint64_t n, Work* w) {
-  const uint64_t need = std::min<uint64_t>(chunk_events(c), std::max<uint64_t>(n, 1024));
-  if (need > c->work_cap) {
+  for (;;) {
+    const uint64_t chunk = chunk_events(c);
+    const uint64_t need = std::min<uint64_t>(chunk, std::max<uint64_t>(n, 1024));
+    if (need <= c->work_cap) break;
     if (c->d_work) cudaFree(c->d_work);
     c->d_work = nullptr;
     c->work_cap = 0;
-    NB_CUDA(c, cudaMalloc(&c->d_work, need * (WORK_F64 * 8 + WORK_I32 * 4)));
-    c->work_cap = need;
+    const cudaError_t e = cudaMalloc(&c->d_work, need * (WORK_F64 * 8 + WORK_I32 * 4));
+    if (e == cudaSuccess) {
+      c->work_cap = need;
+      break;
+    }
+    cudaGetLastError();  // clear the allocation failure
+    if (need < chunk || c->chunk_log2 <= 20) return fail(c, NB200_ENOMEM, std::string("workspace: ") + cudaGetErrorString(e));
+    --c->chunk_log2;  // a full chunk did not fit: halve it, for this context's lifetime
   }
   const uint64_t cap = c->work_cap;
   double* f = static_cast<double*>(c->d_work);
@@ -471,13 +482,19 @@ int ensure_occupancy(nb200_ctx* c) {
 // the deferred-finisher queue: 6 entries per workspace event (LUX NR 0-100 keV queues 2 per event; what does not
 // fit is finished inside k_hits), allocated with the workspace
 int ensure_hit_queue(nb200_ctx* c, HitQueue* q) {
-  const uint64_t want = std::min<uint64_t>(std::max<uint64_t>(c->work_cap, 1024) * 6, 1u << 28);
-  if (want > c->hitq_cap) {
+  uint64_t want = std::min<uint64_t>(std::max<uint64_t>(c->work_cap, 1024) * 6, 1u << 28);
+  while (want > c->hitq_cap) {
     if (c->d_hitq) cudaFree(c->d_hitq);
     c->d_hitq = nullptr;
     c->hitq_cap = 0;
-    NB_CUDA(c, cudaMalloc(&c->d_hitq, want * sizeof(SlotEntry)));
-    c->hitq_cap = unsigned(want);
+    const cudaError_t e = cudaMalloc(&c->d_hitq, want * sizeof(SlotEntry));
+    if (e == cudaSuccess) {
+      c->hitq_cap = unsigned(want);
+      break;
+    }
+    cudaGetLastError();
+    if (want <= 1024) return fail(c, NB200_ENOMEM, std::string("deferred queue: ") + cudaGetErrorString(e));
+    want /= 2;  // a shorter queue only moves more of the finishing into k_hits
   }
   q->entries = c->d_hitq;
   q->count = reinterpret_cast<unsigned int*>(c->d_err + 2);
@@ -610,6 +627,7 @@ int nb200_create(int device, nb200_ctx** out) {
     return NB200_ECUDA;
   }
   c->stream = c->own_stream;
+  if (const char* e = std::getenv("NB200_CHUNK_LOG2")) c->chunk_log2 = std::min(28, std::max(16, std::atoi(e)));
   {  // Phi table of the photo-electron acceptance bounds (nb_chain.cuh)
     double tab[NB_PHI_N];
     for (int k = 0; k < NB_PHI_N; ++k) tab[k] = 0.5 * erfc(-(-8. + double(k) / 16.) * 0.70710678118654752440);

@@ -29,6 +29,20 @@ def ctx(built):
     c.close()
 
 
+@pytest.fixture()
+def ctx_small_chunks(built):
+    """A context whose internal chunk is 2^22 events (the default is 2^24), so that tests of a few million events
+    cross chunk boundaries."""
+    import os
+    os.environ["NB200_CHUNK_LOG2"] = "22"
+    try:
+        c = built.Context(0)
+    finally:
+        del os.environ["NB200_CHUNK_LOG2"]
+    yield c
+    c.close()
+
+
 @pytest.fixture(scope="session")
 def ref():
     """The unmodified reference (oracle/_ref/libnestprobe.so); prebuilt files travel to the GPU box."""

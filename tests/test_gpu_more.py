@@ -112,15 +112,16 @@ def test_wimp_source(ctx, ref):
     assert (E == 0).mean() < 0.02            # the reference's 100-try bail-out returns 0 keV (TestSpectra.cpp:491-495)
 
 
-def test_chunked_launch_equals_single_and_properties_at_size(ctx):
-    """N beyond one internal chunk (~2^22 events): same integers as the sum of its parts, and the
+def test_chunked_launch_equals_single_and_properties_at_size(ctx_small_chunks):
+    """N beyond one internal chunk (2^22 events in this context): same integers as the sum of its parts, and the
     size-independent invariants of the band accumulator"""
+    ctx = ctx_small_chunks
     ana = capi.analysis(0)
     det = capi.detector("LUX_Run03")
     rc = capi.prepare(det, 180.0)
     mo = capi.model(1)
     src = capi.source(capi.SRC_FLAT, capi.NR, 0.0, 100.0, 180.0)
-    n = (1 << 22) + 312345     # the internal chunk is 28 x 148 x 1024 = 4 243 456 events on a B200
+    n = (1 << 22) + 312345     # the internal chunk is 28 x 148 x 1024 = 4 243 456 events on a B200 at 2^22
     full = capi.Band(ana)
     ctx.run(det, mo, ana, src, rc, 1, n, columns=[], band=full)
     parts = capi.Band(ana)

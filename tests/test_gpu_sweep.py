@@ -53,8 +53,10 @@ def test_sweep_is_bit_equal_to_per_point_runs(ctx, kind, n):
     assert len(distinct) == 12   # every grid point is its own physics
 
 
-def test_sweep_spanning_several_workspace_chunks(ctx):
-    """points x padded events beyond one workspace chunk (4.24e6 slots): chunk boundaries fall inside points"""
+def test_sweep_spanning_several_workspace_chunks(ctx_small_chunks):
+    """points x padded events beyond one workspace chunk (4.24e6 slots in this context): chunk boundaries fall inside
+    points"""
+    ctx = ctx_small_chunks
     ana = capi.analysis(0)
     dets, mods, srcs, rcs, keys = grid_points((180.0, 400.0), (0.117,), (0.1, 0.12, 0.14), "nr")
     n = 1_200_003
