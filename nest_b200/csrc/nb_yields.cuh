@@ -46,7 +46,11 @@ NB_HD bool nearly_equal(double a, double b, double eps = 1e-9) {
 // path (a zero numerator sends the lane through the out-of-line special-case routine, ~60 instructions)
 NB_HD double div_z(double a, double b) {
   const bool z = a == 0. && b > 0. && b < DBL_MAX;
-  const double q = (z ? 1. : a) / b;
+  double num = z ? 1. : a;
+#ifdef __CUDA_ARCH__
+  asm volatile("" : "+d"(num));  // opaque: otherwise the select is folded away (the quotient of a z lane is unused) and a / b comes back
+#endif
+  const double q = num / b;
   return z ? a : q;
 }
 

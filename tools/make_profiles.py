@@ -32,7 +32,7 @@ def main():
     tot = sum(v[1] for v in agg.values())
     b = json.load(open(bench))
     with open(os.path.join(out, "%s_bench_launch_list.txt" % tag), "w") as f:
-        f.write("ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv python bench.py --steps 2 --warmup 1   (B200)\n")
+        f.write("ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline   (B200)\n")
         f.write("all %d launches of the bench command (cold-cache, serialised: compare SHARES, not absolutes)\n\n" % len(rows))
         f.write("%-46s %8s %12s %8s\n" % ("kernel", "launches", "total ms", "share"))
         for k, v in agg.items():
