@@ -254,6 +254,10 @@ int nb200_abi_version(void);
  * which = 0 nb200_map, 1 nb200_detector, 2 nb200_model, 3 nb200_analysis, 4 nb200_source,
  * 5 nb200_run_consts, 6 nb200_soa_out, 7 nb200_band_hist; -1 for anything else */
 int nb200_sizeof(int which);
+/* One context per device and host thread.  Device memory: the stage workspace and the deferred-hit queue grow with the
+ * largest call so far, up to one internal chunk of 2^24 events (188 B/event: 3.2 GB); a device that cannot give that
+ * falls back to smaller chunks, and the environment variable NB200_CHUNK_LOG2 (16..28, read here) sets the size.
+ * Results do not depend on the chunk size. */
 int nb200_create(int device, nb200_ctx** out);
 void nb200_destroy(nb200_ctx* ctx);
 const char* nb200_last_error(const nb200_ctx* ctx);
