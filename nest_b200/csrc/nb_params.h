@@ -8,6 +8,12 @@
 
 #include "../../include/nest_b200.h"
 
+#ifndef __CUDACC__
+struct uint2 {  // plain C++ builds of these headers (tests/host_checks.cpp): the one CUDA vector type named below
+  unsigned int x, y;
+};
+#endif
+
 namespace nb {
 
 // packed band accumulator in device memory (u64 words), per S1 bin

@@ -1,9 +1,14 @@
 // Host-side checks of nest_b200/csrc/nb_rng.cuh (compiled and run by tests/test_host_rng_cpu.py; g++, no GPU):
 // the Philox4x32-10 block function against the Random123 known-answer vectors, the round-key and
-// per-event-prepared variants against it, and the sequential Stream's word order.
+// per-event-prepared variants against it, the sequential Stream's word order, and the two arithmetic shortcuts of
+// nb_yields.cuh (nearly_equal without its division, div_z) against the plain expressions they replace.
 #include <cstdio>
 #include <cstdint>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
 #include "../nest_b200/csrc/nb_rng.cuh"
+#include "../nest_b200/csrc/nb_yields.cuh"
 
 static int fails = 0;
 #define CHECK(c)                                          \
@@ -62,6 +67,41 @@ int main() {
     CHECK(u53(0xffffffffu, 0xfffff000u) < 1. && u53(0xffffffffu, 0xfffff000u) > 0.9999999999999997);
     CHECK(u32d(0u) > 0. && u32d(0xffffffffu) < 1.);
     CHECK(u53(0x80000000u, 0u) == 0.5 + 1.1102230246251565404e-16 * 0.5);
+  }
+  {  // nearly_equal decides diff / sum < eps without the division unless the quotient is within a factor 2 of eps:
+     // the same answer as ValidityTests::nearlyEqual (ValidityTests.cpp:6-21) written out, on 4e6 pairs that crowd
+     // the threshold, plus the special cases
+    auto plain = [](double a, double b, double eps) {
+      if (a == b) return true;
+      const double absA = std::fabs(a), absB = std::fabs(b), diff = std::fabs(a - b);
+      if (a == 0 || b == 0 || (absA + absB < DBL_MIN)) return diff < (eps * DBL_MIN);
+      return diff / std::fmin(absA + absB, DBL_MAX) < eps;
+    };
+    uint32_t keys[20];
+    philox_round_keys(7ull, keys);
+    Stream g;
+    g.init(keys, 1ull, STREAM_HOST);
+    int bad = 0;
+    for (int i = 0; i < 4000000 && bad < 5; ++i) {
+      const double a = std::ldexp(g.uniform() - 0.5, int(g.uniform() * 600.) - 300);
+      // relative distance log-uniform around 2e-9 (the quotient's threshold for eps = 1e-9), every few draws exact
+      const double rel = 2e-9 * std::exp((g.uniform() - 0.5) * ((i & 3) ? 2.0 : 40.0));
+      const double b = (i % 7 == 0) ? a : a * (1. + ((i & 1) ? rel : -rel));
+      if (nearly_equal(a, b) != plain(a, b, 1e-9)) ++bad;
+      if (nearly_equal(a, 1.) != plain(a, 1., 1e-9)) ++bad;
+    }
+    CHECK(bad == 0);
+    const double sp[] = {0., -0., 1., -1., DBL_MIN, 4.9e-324, 1e-320, DBL_MAX, -DBL_MAX, 1. + 2e-9, 1. + 1.9999e-9, 1. + 2.0001e-9};
+    for (double a : sp)
+      for (double b : sp) CHECK(nearly_equal(a, b) == plain(a, b, 1e-9));
+  }
+  {  // div_z(a, b) has the bits of a / b, whatever the operands
+    const double v[] = {0., -0., 1., -1., 3.5, 1e-310, DBL_MIN, DBL_MAX, 1e300, INFINITY, -INFINITY, NAN, 0.37, -2e-9};
+    for (double a : v)
+      for (double b : v) {
+        const double q = a / b, z = div_z(a, b);
+        CHECK(std::memcmp(&q, &z, 8) == 0 || (std::isnan(q) && std::isnan(z)));
+      }
   }
   std::printf(fails ? "host checks: %d failure(s)\n" : "host checks ok\n", fails);
   return fails != 0;
