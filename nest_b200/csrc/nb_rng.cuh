@@ -44,7 +44,7 @@ enum : uint32_t {
   STREAM_ZIGX = 11,  // ... of a joint (S, T) redraw (11: S, 12: T)
   STREAM_LAR = 8,
   STREAM_SE = 9,     // CalculateG2's single-electron Monte Carlo
-  // each binomial draw owns a stream (the sampler is an out-of-line subroutine)
+  // each binomial draw owns a stream: candidate k of a draw is Philox block k of it, whatever else the event consumes
   STREAM_BIN_NI = 32, STREAM_BIN_S1 = 33, STREAM_BIN_NEE = 34, STREAM_BIN_S2HIT = 35,
   STREAM_BIN_S2DPE = 36, STREAM_BIN_PAR0 = 37, STREAM_BIN_PAR1 = 38, STREAM_BIN_PAR2 = 39,
   STREAM_BIN_LAR = 40, STREAM_BIN_S1DPE = 41, /* 42: its BTRS fall-back */
@@ -292,8 +292,8 @@ NB_D void sincos_bits(uint32_t z, double& s, double& c) {
   s = __hiloint2double(__double2hiint(b) ^ int(ss), __double2loint(b));
 }
 
-// The same table in global memory for the per-event stages (k_pre / k_post and the samplers they
-// call out of line), which have no shared-memory staging: a random index into constant memory
+// The same table in global memory for the per-event stages (k_pre / k_post and their samplers),
+// which have no shared-memory staging: a random index into constant memory
 // would serialise, a read-only global load is one instruction and stays in L1.
 static __device__ const double g_lntab[64] = {
     0.98461538461538461538, 0.015504186535965254151, 0.95522388059701492537, 0.045809536031294203167,
