@@ -81,6 +81,8 @@ struct nb200_ctx {
   size_t sweep_params_bytes = 0;
   unsigned long long* d_sweep_bands = nullptr;
   size_t sweep_band_words = 0;
+  unsigned long long* h_sweep_bands = nullptr;  // pinned staging of the sweep's bands
+  size_t h_sweep_words = 0;
   int occ_pre_sweep = 0, occ_hits_sweep = 0;
   size_t sweep_last_points = 0, sweep_last_words = 0;  // shape of the bands the last nb200_run_sweep left on the device
 };
@@ -689,6 +691,7 @@ void nb200_destroy(nb200_ctx* c) {
   for (auto& e : c->dpe) cudaFree(e.dev);
   if (c->d_sweep_params) cudaFree(c->d_sweep_params);
   if (c->d_sweep_bands) cudaFree(c->d_sweep_bands);
+  if (c->h_sweep_bands) cudaFreeHost(c->h_sweep_bands);
   if (c->d_work) cudaFree(c->d_work);
   for (int b = 0; b < 2; ++b) {
     if (c->d_stage[b]) cudaFree(c->d_stage[b]);
@@ -1765,8 +1768,17 @@ int nb200_run_sweep(nb200_ctx* c, size_t n_points, const nb200_detector* dets, c
   tr.mark("launched");
   c->sweep_last_points = n_points;
   c->sweep_last_words = words;
-  std::vector<unsigned long long> w(words * n_points);
-  NB_CUDA(c, cudaMemcpyAsync(w.data(), c->d_sweep_bands, w.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+  // the bands come back through a pinned buffer kept with the context (7 MB for 250 LUX bands: 0.1 ms instead of
+  // the 0.7 ms of a pageable copy, 3 % of such a sweep)
+  if (words * n_points > c->h_sweep_words) {
+    if (c->h_sweep_bands) cudaFreeHost(c->h_sweep_bands);
+    c->h_sweep_bands = nullptr;
+    c->h_sweep_words = 0;
+    NB_CUDA(c, cudaMallocHost(&c->h_sweep_bands, words * n_points * 8));
+    c->h_sweep_words = words * n_points;
+  }
+  const unsigned long long* w = c->h_sweep_bands;
+  NB_CUDA(c, cudaMemcpyAsync(c->h_sweep_bands, c->d_sweep_bands, words * n_points * 8, cudaMemcpyDeviceToHost, c->stream));
   r = check_device_error(c);  // synchronises (Ps must also outlive the copy above)
   if (r) return r;
   tr.mark("kernels done");

@@ -351,7 +351,12 @@ __global__ void __launch_bounds__(kPreBlock, NB_PRE_MINB)
     k_pre_sweep(const __grid_constant__ SweepArgs A, int* __restrict__ err_flag) {
   __shared__ __align__(16) RunParams sP;
   uint32_t cur = 0xffffffffu;
-  for (uint64_t base = blockIdx.x * uint64_t(kPreBlock); base < A.n_slots; base += uint64_t(gridDim.x) * kPreBlock) {
+  // a block takes a contiguous range of tiles (not a grid stride): it then stays on one grid point for many tiles
+  // and reloads its parameter copy only when the range crosses into the next point
+  const uint64_t n_tiles = (A.n_slots + kPreBlock - 1) / kPreBlock;
+  const uint64_t t0 = n_tiles * blockIdx.x / gridDim.x, t1 = n_tiles * (blockIdx.x + 1) / gridDim.x;
+  for (uint64_t t = t0; t < t1; ++t) {
+    const uint64_t base = t * kPreBlock;
     const uint64_t slot = A.slot0 + base;  // first slot of this tile: multiple of kPreBlock
     const uint32_t point = uint32_t(slot / A.n_pad);
     if (point != cur) {
