@@ -386,6 +386,26 @@ int nb200_run_sweep(nb200_ctx* ctx, size_t n_points, const nb200_detector* dets,
 int nb200_sweep_band_post(nb200_ctx* ctx, size_t n_points, const nb200_analysis* ana, const double* target_band,
                           int free_param, const double* centroid, double* stats, double* gof, double* leak);
 
+/* Per-bin band fits on the device (k_band_fit, one thread per grid point and S1 bin), for the bands of
+ * the LAST nb200_run_sweep on this context (nb200_sweep_band_fit) or for the context's own device accumulator
+ * (nb200_band_fit_device, after nb200_run_async):
+ *   model 0 -- GetBand_Gaussian (examples/rootNEST.cpp:1309-1359): fit [n_points][numBins][8], each row exactly what
+ *     nb200_band_fit_gauss writes for that slice (the same statements run on the device);
+ *   model 1 -- the skew-Gaussian band (:1360-1507): "skewband" (:1361-1364) fitted to the slice's row over the log bins
+ *     whose centres lie in mean +- 3 sigma (GetBand's moments; widened by 0.5 as :1322-1327 when the window reaches
+ *     beyond 2 / 3), from EstimateSkew's start values (:1567-1585, :1367-1374): fit [n_points][numBins][12] = {A, xi,
+ *     omega, alpha, xi error, omega error, alpha error, cov(xi, omega), cov(xi, alpha), cov(omega, alpha), chi^2 per
+ *     degree of freedom, bins used} -- what nb200_hist_fit_cov(1, ...) gives for that window and start.
+ * Rows without a fit (too few filled bins, no minimum) are zeros.  line [numBins] (or NULL) with leak [n_points][numBins]
+ * (or NULL): the fraction below the line read off each slice's fit -- (1 - erf(n_sigma / sqrt 2)) / 2 (:848) or the
+ * skew-normal CDF with the reference's Owen's-T quadrature (:700-735, 1587-1602), as nb200_band_leakage_gauss /
+ * nb200_band_leakage_skew.  All pointers HOST.  A fit over a 250-point grid is one launch of 24 500 threads instead of
+ * 250 accumulators copied back and fitted on the host. */
+int nb200_sweep_band_fit(nb200_ctx* ctx, size_t n_points, const nb200_analysis* ana, int model, const double* line,
+                         double* fit, double* leak);
+int nb200_band_fit_device(nb200_ctx* ctx, const nb200_analysis* ana, int model, const double* line, double* fit,
+                          double* leak);
+
 /* Device-resident variant used for throughput measurement: the band accumulator
  * stays in device memory owned by ctx between calls; fetch adds it into hist. */
 int nb200_run_async(nb200_ctx* ctx, const nb200_detector* det, const nb200_model* model,

@@ -102,7 +102,7 @@ class BandHist(C.Structure):
 EXPORTS = [
     "nb200_abi_version", "nb200_sizeof", "nb200_create", "nb200_destroy", "nb200_last_error", "nb200_set_stream",
     "nb200_synchronize", "nb200_detector_builtin", "nb200_model_default", "nb200_analysis_default",
-    "nb200_prepare", "nb200_wimp_prep", "nb200_wimp_prep_iso", "nb200_wimp_drate", "nb200_poisson", "nb200_yields", "nb200_quanta", "nb200_s2", "nb200_s1", "nb200_widths", "nb200_spike", "nb200_xy_resolution", "nb200_spectrum", "nb200_run", "nb200_run_sweep", "nb200_sweep_band_post", "nb200_run_async",
+    "nb200_prepare", "nb200_wimp_prep", "nb200_wimp_prep_iso", "nb200_wimp_drate", "nb200_poisson", "nb200_yields", "nb200_quanta", "nb200_s2", "nb200_s1", "nb200_widths", "nb200_spike", "nb200_xy_resolution", "nb200_spectrum", "nb200_run", "nb200_run_sweep", "nb200_sweep_band_post", "nb200_sweep_band_fit", "nb200_band_fit_device", "nb200_run_async",
     "nb200_band_reset", "nb200_band_attach", "nb200_fp64_peak", "nb200_timing_enable", "nb200_timing_read", "nb200_se_stats", "nb200_band_fetch", "nb200_band_device_buffer", "nb200_allreduce_hist",
     "nb200_band_hist_bytes", "nb200_band_scale_x", "nb200_band_finalize", "nb200_band_chi2", "nb200_band_leakage", "nb200_band_fit_gauss", "nb200_band_leakage_gauss", "nb200_hist_fit", "nb200_hist_fit_cov", "nb200_band_leakage_skew_cov", "nb200_graph_fit", "nb200_band_leakage_skew", "nb200_lar", "nb200_launch_count",
     "nb200_debug_hitmath", "nb200_debug_binomial", "nb200_debug_normal", "nb200_debug_binomial_fixed",
@@ -172,6 +172,8 @@ def lib():
                                   C.POINTER(Source), C.POINTER(RunConsts), C.c_uint64, C.c_uint64, C.c_uint64,
                                   C.POINTER(BandHist)]
     L.nb200_sweep_band_post.argtypes = [vp, C.c_size_t, C.POINTER(Analysis), c_dp, C.c_int, c_dp, c_dp, c_dp, c_dp]
+    L.nb200_sweep_band_fit.argtypes = [vp, C.c_size_t, C.POINTER(Analysis), C.c_int, c_dp, c_dp, c_dp]
+    L.nb200_band_fit_device.argtypes = [vp, C.POINTER(Analysis), C.c_int, c_dp, c_dp, c_dp]
     L.nb200_band_reset.argtypes = [vp, C.POINTER(Analysis)]
     L.nb200_band_fetch.argtypes = [vp, C.POINTER(BandHist)]
     L.nb200_band_attach.argtypes = [vp, C.POINTER(Analysis), vp]
@@ -604,6 +606,25 @@ class Context:
         self._check(lib().nb200_sweep_band_post(self.h, n_points, C.byref(ana), p(tgt), free_param, p(cen), p(stats),
                                                 p(gof), p(leak)))
         return stats, gof, leak
+
+    def sweep_band_fit(self, n_points, ana, model=0, line=None):
+        """per-bin Gaussian (model 0: 8 columns as band_fit_gauss) or skew-Gaussian (model 1: 12 columns) fits of the
+        last sweep's bands on the device -> (fit [n][numBins][cols], leak [n][numBins] below `line` or None)"""
+        ln = None if line is None else np.ascontiguousarray(line, np.float64)
+        fit = np.zeros((n_points, ana.numBins, 8 if model == 0 else 12))
+        leak = np.zeros((n_points, ana.numBins)) if ln is not None else None
+        p = lambda a: a.ctypes.data_as(c_dp) if a is not None else None
+        self._check(lib().nb200_sweep_band_fit(self.h, n_points, C.byref(ana), model, p(ln), p(fit), p(leak)))
+        return fit, leak
+
+    def band_fit_device(self, ana, model=0, line=None):
+        """the same for the context's own device accumulator (after run_async) -> (fit [numBins][cols], leak or None)"""
+        ln = None if line is None else np.ascontiguousarray(line, np.float64)
+        fit = np.zeros((ana.numBins, 8 if model == 0 else 12))
+        leak = np.zeros(ana.numBins) if ln is not None else None
+        p = lambda a: a.ctypes.data_as(c_dp) if a is not None else None
+        self._check(lib().nb200_band_fit_device(self.h, C.byref(ana), model, p(ln), p(fit), p(leak)))
+        return fit, leak
 
     def band_reset(self, ana):
         self._check(lib().nb200_band_reset(self.h, C.byref(ana)))

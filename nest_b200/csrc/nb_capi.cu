@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "nb_host.h"
+#include "nb_fit.h"
 #include "nb_kernels.cuh"
 
 using namespace nb;
@@ -216,6 +217,22 @@ int validate(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo, con
 int check_device_error(nb200_ctx* c);
 
 // WIMP source: the spectrum table to device memory, WIMP_dRate(0) per isotope (TestSpectra.cpp:459, 466)
+// device copy of the alias tables of Binomial(2^b, p) (binomial_fixed_p), built once per distinct p and context
+static int alias_table_for(nb200_ctx* c, double p, const uint2** out) {
+  void* dtab = nullptr;
+  for (auto& e : c->dpe)
+    if (e.p == p) dtab = e.dev;
+  if (!dtab) {
+    std::vector<AliasEntry> tab(NB_ALIAS_ENTRIES);
+    build_binomial_alias(p, tab.data());
+    NB_CUDA(c, cudaMalloc(&dtab, sizeof(AliasEntry) * tab.size()));
+    NB_CUDA(c, cudaMemcpy(dtab, tab.data(), sizeof(AliasEntry) * tab.size(), cudaMemcpyHostToDevice));
+    c->dpe.push_back({p, dtab});
+  }
+  *out = static_cast<const uint2*>(dtab);
+  return 0;
+}
+
 int upload_wimp_source(nb200_ctx* c, const nb200_source* src, RunParams* P) {
   if (src->kind != NB200_SRC_WIMP) return 0;
   if (!src->wimp_base || !src->wimp_exponent) return fail(c, NB200_EINVAL, "WIMP source without nb200_wimp_prep table");
@@ -405,19 +422,8 @@ int build_params(nb200_ctx* c, const nb200_detector* det, const nb200_model* mo,
     P->vtable_n = int(c->vtable_host.size());
   }
   P->dpe_alias = nullptr;
-  if (det->P_dphe > 0. && det->P_dphe < 1.) {  // alias tables of Binomial(2^b, P_dphe) for k_pre's double-phe count
-    void* dtab = nullptr;
-    for (auto& e : c->dpe)
-      if (e.p == det->P_dphe) dtab = e.dev;
-    if (!dtab) {
-      std::vector<AliasEntry> tab(NB_ALIAS_ENTRIES);
-      build_binomial_alias(det->P_dphe, tab.data());
-      NB_CUDA(c, cudaMalloc(&dtab, sizeof(AliasEntry) * tab.size()));
-      NB_CUDA(c, cudaMemcpy(dtab, tab.data(), sizeof(AliasEntry) * tab.size(), cudaMemcpyHostToDevice));
-      c->dpe.push_back({det->P_dphe, dtab});
-    }
-    P->dpe_alias = static_cast<const uint2*>(dtab);
-  }
+  if (det->P_dphe > 0. && det->P_dphe < 1.)  // alias tables of Binomial(2^b, P_dphe) for k_pre's double-phe count
+    if ((r = alias_table_for(c, det->P_dphe, &P->dpe_alias))) return r;
   if ((r = upload_wimp_source(c, src, P))) return r;
   P->seed = seed;
   philox_round_keys(seed, P->rk);
@@ -1845,6 +1851,54 @@ int nb200_sweep_band_post(nb200_ctx* c, size_t n_points, const nb200_analysis* a
   return st.finish(0, "k_band_post");
 }
 
+// Per-bin fits of device-resident bands (k_band_fit): the last sweep's, or the context's own accumulator
+static int band_fit_device(nb200_ctx* c, const unsigned long long* bands, size_t n_points, const nb200_analysis* ana,
+                           int model, const double* line, double* fit, double* leak) {
+  if (model != 0 && model != 1) return fail(c, NB200_EINVAL, "band fit model must be 0 (Gaussian) or 1 (skew-Gaussian)");
+  if (!fit) return fail(c, NB200_EINVAL, "null argument");
+  if (leak && !line) return fail(c, NB200_EINVAL, "the leakage needs a line");
+  if (ana->logBins < 4) return fail(c, NB200_EINVAL, "band fits need logBins >= 4");
+  NB_CUDA(c, cudaSetDevice(c->device));
+  Staged st(c, NB200_MEM_HOST);
+  BandFitArgs A;
+  std::memset(&A, 0, sizeof A);
+  A.bands = bands;
+  A.band_words = band_word_count(ana);
+  A.numBins = ana->numBins;
+  A.logBins = ana->logBins;
+  A.model = model;
+  A.cols = model == 0 ? 8 : 12;
+  A.n_rows = uint64_t(n_points) * uint64_t(ana->numBins);
+  A.logMin = ana->logMin;
+  A.logMax = ana->logMax;
+  A.line = st.in(line, size_t(ana->numBins));
+  A.fit = st.out(fit, size_t(A.n_rows) * size_t(A.cols));
+  A.leak = st.out(leak, size_t(A.n_rows));
+  if (st.err == cudaSuccess) {
+    k_band_fit<<<unsigned((A.n_rows + 127) / 128), 128, 0, c->stream>>>(A);
+    ++c->launches;
+  }
+  return st.finish(0, "k_band_fit");
+}
+int nb200_sweep_band_fit(nb200_ctx* c, size_t n_points, const nb200_analysis* ana, int model, const double* line,
+                         double* fit, double* leak) {
+  if (!c || !ana) return NB200_EINVAL;
+  if (n_points == 0) return 0;
+  const size_t words = band_word_count(ana);
+  if (!c->d_sweep_bands || words * n_points > c->sweep_band_words || c->sweep_last_points != n_points ||
+      c->sweep_last_words != words)
+    return fail(c, NB200_EINVAL, "nb200_sweep_band_fit: no sweep of this shape on this context (call nb200_run_sweep first)");
+  return band_fit_device(c, c->d_sweep_bands, n_points, ana, model, line, fit, leak);
+}
+int nb200_band_fit_device(nb200_ctx* c, const nb200_analysis* ana, int model, const double* line, double* fit,
+                          double* leak) {
+  if (!c || !ana) return NB200_EINVAL;
+  if (!c->d_band) return fail(c, NB200_EINVAL, "no device band accumulator (call nb200_band_reset)");
+  if (ana->numBins != c->band_numBins || ana->logBins != c->band_logBins || band_word_count(ana) != c->band_words)
+    return fail(c, NB200_EINVAL, "band geometry mismatch");
+  return band_fit_device(c, c->d_band, 1, ana, model, line, fit, leak);
+}
+
 // GetBand's closing statistics (execNEST.cpp:1582-1618) from the integer accumulator
 int nb200_band_finalize(const nb200_analysis* ana, const nb200_band_hist* h, double* band) {
   if (!ana || !h || !band) return NB200_EINVAL;
@@ -1963,177 +2017,18 @@ int nb200_band_leakage(const nb200_analysis* ana, const nb200_band_hist* h, cons
 
 }  // extern "C"
 namespace {
-// Weighted least squares of f(x) = A exp(-(x - mu)^2 / (2 s^2)) to one row of the 2-D histogram: function taken
-// at the bin centres, weights 1/content, empty bins left out -- what ROOT's TH1::Fit minimises by default and
-// so what examples/rootNEST.cpp:1336-1338 asks for.  Levenberg-Marquardt with the analytic Jacobian; the
-// parameter errors are the square roots of the diagonal of (J^T W J)^-1 at the minimum (MIGRAD's parabolic
-// errors for a chi^2).  Returns the number of points used, or 0 when there are fewer than four or no minimum.
-constexpr int kFitMaxPar = 4;
-bool solve_n(int n, const double M[kFitMaxPar][kFitMaxPar], const double* v, double* x) {
-  double a[kFitMaxPar][kFitMaxPar + 1];
-  for (int i = 0; i < n; ++i) {
-    for (int j = 0; j < n; ++j) a[i][j] = M[i][j];
-    a[i][n] = v[i];
-  }
-  for (int c = 0; c < n; ++c) {
-    int piv = c;
-    for (int r = c + 1; r < n; ++r)
-      if (std::fabs(a[r][c]) > std::fabs(a[piv][c])) piv = r;
-    if (!(std::fabs(a[piv][c]) > 0.)) return false;
-    for (int j = 0; j <= n; ++j) std::swap(a[c][j], a[piv][j]);
-    for (int r = 0; r < n; ++r) {
-      if (r == c) continue;
-      const double f = a[r][c] / a[c][c];
-      for (int j = c; j <= n; ++j) a[r][j] -= f * a[c][j];
-    }
-  }
-  for (int i = 0; i < n; ++i) x[i] = a[i][n] / a[i][i];
-  return true;
-}
-
-// model 0: A exp(-(x - mu)^2 / (2 s^2))                                          (ROOT's "gaus";   p = A, mu, s)
-// model 1: A / (w sqrt(2 pi)) exp(-(x - xi)^2 / (2 w^2)) (1 + erf(al (x - xi) / (w sqrt 2)))
-//                                                     (rootNEST.cpp:1361-1364 "skewband"; p = A, xi, w, al)
-// model 2: p0 / (x + p1) + p2 x + p3                         (rootNEST.cpp:856-857, the Woods function through the NR means)
-// model 3: p0 + (p1 - p0) / (1 + (x / p2)^p3)                 (rootNEST.cpp:870-871, its sigmoid fallback)
-inline int model_npar(int model) { return model == 0 ? 3 : 4; }
-inline bool model_domain(int model, const double* p) {
-  if (model <= 1) return p[0] > 0. && p[2] > 0.;
-  if (model == 3) return p[2] > 0.;
-  return true;
-}
-inline double model_eval(int model, const double* p, double x, double* g) {
-  if (model == 2) {
-    if (g) {
-      g[0] = 1. / (x + p[1]);
-      g[1] = -p[0] / ((x + p[1]) * (x + p[1]));
-      g[2] = x;
-      g[3] = 1.;
-    }
-    return p[0] / (x + p[1]) + p[2] * x + p[3];
-  }
-  if (model == 3) {
-    const double u = std::pow(x / p[2], p[3]), D = 1. + u;
-    if (g) {
-      g[0] = 1. - 1. / D;
-      g[1] = 1. / D;
-      g[2] = (p[1] - p[0]) / (D * D) * u * p[3] / p[2];
-      g[3] = -(p[1] - p[0]) / (D * D) * u * std::log(x / p[2]);
-    }
-    return p[0] + (p[1] - p[0]) / D;
-  }
-  const double z = (x - p[1]) / p[2], e = std::exp(-0.5 * z * z);
-  if (model == 0) {
-    const double f = p[0] * e;
-    if (g) {
-      g[0] = e;
-      g[1] = f * z / p[2];
-      g[2] = f * z * z / p[2];
-    }
-    return f;
-  }
-  const double G = e / (p[2] * std::sqrt(2. * M_PI)), t = p[3] * z / std::sqrt(2.);
-  const double E = 1. + std::erf(t), dE = 2. / std::sqrt(M_PI) * std::exp(-t * t);  // d erf / dt
-  if (g) {
-    g[0] = G * E;
-    g[1] = p[0] * G * (z * E - dE * p[3] / std::sqrt(2.)) / p[2];
-    g[2] = p[0] * G * ((z * z - 1.) * E - dE * p[3] * z / std::sqrt(2.)) / p[2];
-    g[3] = p[0] * G * dE * z / std::sqrt(2.);
-  }
-  return p[0] * G * E;
-}
-
-// sum of w_k (y_k - f(x_k))^2 and, on request, J^T W J and J^T W r
-double points_chi2(int model, int npts, const double* xs, const double* ys, const double* ws, const double* p,
-                   double JtJ[kFitMaxPar][kFitMaxPar], double* Jtr) {
-  const int n = model_npar(model);
-  double chi = 0., g[kFitMaxPar];
-  if (JtJ)
-    for (int i = 0; i < n; ++i) {
-      Jtr[i] = 0.;
-      for (int j = 0; j < n; ++j) JtJ[i][j] = 0.;
-    }
-  for (int k = 0; k < npts; ++k) {
-    const double r = ys[k] - model_eval(model, p, xs[k], JtJ ? g : nullptr);
-    chi += ws[k] * r * r;
-    if (JtJ)
-      for (int i = 0; i < n; ++i) {
-        Jtr[i] += ws[k] * g[i] * r;
-        for (int j = 0; j < n; ++j) JtJ[i][j] += ws[k] * g[i] * g[j];
-      }
-  }
-  return chi;
-}
-
-// Levenberg-Marquardt on weighted points; false when there are too few points or no minimum was found
+// The fits themselves live in nb_fit.h (one implementation for these host entry points and for k_band_fit on the
+// device): weighted least squares by Levenberg-Marquardt with analytic Jacobians, errors from (J^T W J)^-1.
+inline int model_npar(int model) { return fit_npar(model); }
 bool fit_points(int model, int npts, const double* xs, const double* ys, const double* ws, double* p, double* err, double* chi2,
                 double* cov = nullptr) {
-  const int n = model_npar(model);
-  if (npts <= n || !model_domain(model, p)) return false;
-  double JtJ[kFitMaxPar][kFitMaxPar], Jtr[kFitMaxPar], lambda = 1e-3;
-  double chi = points_chi2(model, npts, xs, ys, ws, p, JtJ, Jtr);
-  if (!std::isfinite(chi)) return false;
-  for (int it = 0; it < 1000; ++it) {
-    double M[kFitMaxPar][kFitMaxPar], step[kFitMaxPar], q[kFitMaxPar];
-    for (int i = 0; i < n; ++i)
-      for (int j = 0; j < n; ++j) M[i][j] = JtJ[i][j] * (i == j ? 1. + lambda : 1.);
-    if (!solve_n(n, M, Jtr, step)) return false;
-    for (int i = 0; i < n; ++i) q[i] = p[i] + step[i];
-    double trial = model_domain(model, q) ? points_chi2(model, npts, xs, ys, ws, q, nullptr, nullptr) : INFINITY;
-    if (!std::isfinite(trial)) trial = INFINITY;
-    if (trial <= chi) {
-      bool done = chi - trial <= 1e-13 * chi;
-      for (int i = 0; i < n; ++i) done = done && std::fabs(step[i]) <= 1e-9 * (std::fabs(p[i]) + (model <= 1 ? p[2] : 1e-3));
-      for (int i = 0; i < n; ++i) p[i] = q[i];
-      chi = points_chi2(model, npts, xs, ys, ws, p, JtJ, Jtr);
-      lambda = lambda > 1e-12 ? lambda * 0.1 : lambda;
-      if (done) break;
-    } else {
-      lambda *= 10.;
-      if (lambda > 1e12) break;  // no downhill step left: p is the minimum to rounding
-    }
-  }
-  // covariance = (J^T W J)^-1, column by column
-  for (int i = 0; i < n; ++i) {
-    double unit[kFitMaxPar] = {0., 0., 0., 0.}, col[kFitMaxPar];
-    unit[i] = 1.;
-    if (!solve_n(n, JtJ, unit, col) || !(col[i] > 0.)) {
-      if (model <= 1) return false;
-      col[i] = 0.;  // a curve with a flat direction (a straight line has no Woods pole): the minimum stands, the error does not
-    }
-    err[i] = std::sqrt(col[i]);
-    if (cov)
-      for (int j = 0; j < n; ++j) cov[j * n + i] = col[j];
-  }
-  *chi2 = chi;
-  return true;
+  return fit_lm(model, FitPoints{xs, ys, ws, npts}, p, err, chi2, cov) != 0;
 }
-
 // a histogram row as weighted points: bin centres, contents, weights 1/content, empty bins left out (TH1::Fit's default
 // chi^2); returns the number of bins used, 0 when there are too few or no minimum was found
 int fit_hist_row(int model, const uint64_t* row, int lb, double x0, double w, double* p, double* err, double* chi2,
                  double* cov = nullptr) {
-  std::vector<double> xs, ys, ws;
-  for (int k = 0; k < lb; ++k) {
-    if (!row[k]) continue;
-    xs.push_back(x0 + (double(k) + 0.5) * w);
-    ys.push_back(double(row[k]));
-    ws.push_back(1. / double(row[k]));
-  }
-  if (!fit_points(model, int(xs.size()), xs.data(), ys.data(), ws.data(), p, err, chi2, cov)) return 0;
-  return int(xs.size());
-}
-
-// rootNEST.cpp:1587-1602: Owen's T by the reference's own midpoint rule (2500 steps), so that leakages agree digit for digit
-double owens_t_ref(double h, double a) {
-  const int nIntSteps = 2500;
-  const double dx = a / nIntSteps;
-  double T = 0.;
-  for (int k = 0; k < nIntSteps; ++k) {
-    const double x = (k + 0.5) * dx;
-    T += std::exp(-0.5 * h * h * (1 + x * x)) / (1 + x * x) * dx;
-  }
-  return T / (2. * M_PI);
+  return fit_lm(model, FitRow<uint64_t>{row, lb, x0, w}, p, err, chi2, cov);
 }
 }  // namespace
 extern "C" {
@@ -2143,44 +2038,8 @@ int nb200_band_fit_gauss(const nb200_analysis* ana, const nb200_band_hist* h, do
   if (!ana || !h || !fit || !h->accepted || !h->sumY || !h->sumY2 || !h->hist2d || h->logBins < 4) return NB200_EINVAL;
   const int nb = h->numBins, lb = h->logBins;
   const double w = (ana->logMax - ana->logMin) / double(lb);
-  for (int j = 0; j < nb; ++j) {
-    double* o = fit + 8 * size_t(j);
-    const uint64_t* row = h->hist2d + size_t(j) * lb;
-    for (int i = 0; i < 8; ++i) o[i] = 0.;
-    // start values from the histogram's own moments (the y = 0 entries are outside the axis: ROOT's underflow)
-    double n = 0., sx = 0., sxx = 0.;
-    for (int k = 0; k < lb; ++k) {
-      const double c = double(row[k]), x = ana->logMin + (double(k) + 0.5) * w;
-      n += c;
-      sx += c * x;
-      sxx += c * x * x;
-    }
-    if (!(n > 1.)) continue;
-    const double mu = sx / n;
-    const double var = sxx / n - mu * mu + w * w / 12.;
-    double p[4] = {n * w / std::sqrt(2. * M_PI * var), mu, std::sqrt(var), 0.}, err[4] = {0., 0., 0., 0.}, chi = 0.;
-    const int used = fit_hist_row(0, row, lb, ana->logMin, w, p, err, &chi);
-    if (!used) continue;
-    o[0] = p[0];
-    o[1] = p[1];
-    o[2] = p[2];
-    o[3] = err[1];
-    o[4] = err[2];
-    o[5] = used > 3 ? chi / double(used - 3) : 0.;
-    // the reference's own goodness figure (:1346-1357) in its own indexing: TH1F::operator[](k) is ROOT bin k
-    // (k = 0 the underflow, which holds the events pushed as y = 0), the model taken at logMin + k w
-    double g = 0.;
-    for (int k = 0; k < lb; ++k) {
-      const double x = ana->logMin + double(k) * w;
-      const double model = p[0] * std::exp(-0.5 * (x - p[1]) * (x - p[1]) / (p[2] * p[2]));
-      const double content = k == 0 ? double(h->accepted[j]) - n : double(row[k - 1]);
-      const double denom = std::max(float(model + content), 1.f);
-      g += (content - model) * (content - model) / denom;
-    }
-    g /= double(lb) - 3. - 1.;
-    o[6] = (std::isnan(g) || g < 0. || g >= DBL_MAX) ? 0. : g;
-    o[7] = double(used);
-  }
+  for (int j = 0; j < nb; ++j)
+    fit_gauss_row(h->hist2d + size_t(j) * lb, lb, ana->logMin, w, double(h->accepted[j]), fit + 8 * size_t(j));
   return 0;
 }
 
@@ -2555,6 +2414,7 @@ int nb200_lar(nb200_ctx* c, int species, size_t n, const double* E, const double
   P.n = n;
   philox_round_keys(seed, P.rk);
   P.first_event = first_event;
+  P.seed = seed;
   P.density = density;
   std::vector<void*> fr;
   auto cleanup = [&]() {
@@ -2583,7 +2443,12 @@ int nb200_lar(nb200_ctx* c, int species, size_t n, const double* E, const double
     P.fluct = fluct;
   }
   unsigned grid = unsigned(std::min<uint64_t>((n + 255) / 256, uint64_t(c->sm_count) * 8));
-  k_lar<<<grid, 256, 0, c->stream>>>(P);
+  if (species == 0)
+    k_lar<0><<<grid, 256, 0, c->stream>>>(P);
+  else if (species == 1)
+    k_lar<1><<<grid, 256, 0, c->stream>>>(P);
+  else
+    k_lar<2><<<grid, 256, 0, c->stream>>>(P);
   cudaError_t le = cudaGetLastError();
   ++c->launches;
   int rc = 0;

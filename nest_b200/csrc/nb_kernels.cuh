@@ -3,6 +3,7 @@
 // yields + fluctuations).
 #pragma once
 #include "nb_chain.cuh"
+#include "nb_fit.h"
 #include "nb_lar.cuh"
 
 namespace nb {
@@ -1508,6 +1509,53 @@ __global__ void __launch_bounds__(256) k_band_post(const __grid_constant__ BandP
   }
 }
 
+// k_band_fit: the per-bin fits of the band post-processing for batched bands -- GetBand_Gaussian (examples/rootNEST.cpp:
+// 1309-1359) or the skew-Gaussian band (:1360-1507) of every S1 slice of every grid point, and the leakage below a line
+// read off the fits (:700-738, 848 Gaussian; :700-735, 1587-1602 skew-normal CDF with the reference's Owen's-T
+// quadrature).  One thread per (grid point, S1 bin): a slice is <= logBins points and a few dozen Levenberg-Marquardt
+// steps, a sweep has hundreds of points x ~100 bins of them, and the statements are nb_fit.h's -- the very functions the
+// host entry points (nb200_band_fit_gauss, nb200_hist_fit_cov, nb200_band_leakage_gauss / _skew) run.
+struct BandFitArgs {
+  const unsigned long long* bands;  // [n_points][band_words]
+  uint64_t band_words, n_rows;      // n_rows = n_points * numBins
+  int32_t numBins, logBins, model, cols;  // model 0: 8 columns, model 1: 12
+  double logMin, logMax;
+  const double* line;  // [numBins] leakage line, or null
+  double* fit;         // [n_points][numBins][cols]
+  double* leak;        // [n_points][numBins] or null (needs line)
+};
+__global__ void __launch_bounds__(128) k_band_fit(const __grid_constant__ BandFitArgs A) {
+  const uint64_t t = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+  if (t >= A.n_rows) return;
+  const uint64_t point = t / uint64_t(A.numBins);
+  const int j = int(t - point * uint64_t(A.numBins));
+  const unsigned long long* B = A.bands + point * A.band_words;
+  const unsigned long long* b = B + size_t(j) * BAND_WORDS;
+  const unsigned long long* row = B + size_t(A.numBins) * BAND_WORDS + size_t(j) * A.logBins;
+  const double w = (A.logMax - A.logMin) / double(A.logBins);
+  const double N = double(b[0]);
+  double o[12];
+  double leak = 0.;
+  if (A.model == 0) {
+    fit_gauss_row(row, A.logBins, A.logMin, w, N, o);
+    if (A.line && o[7] > 0.) leak = (1. - erf((o[1] - A.line[j]) / o[2] / sqrt(2.))) / 2.;
+  } else {
+    // GetBand's moments of the slice (execNEST.cpp:1582-1618), as k_band_post
+    const double Sy = double((long long)b[3]) / NB200_FX_Y, Sy2 = double((long long)b[4]) / NB200_FX_Y2,
+                 Sy3 = double((long long)b[5]) / NB200_FX_Y3;
+    const double mu = Sy / N;
+    const double sd = sqrt((Sy2 - 2. * mu * Sy + N * mu * mu) / (N - 1.));
+    const double m3 = Sy3 - 3. * mu * Sy2 + 3. * mu * mu * Sy - N * mu * mu * mu;
+    fit_skew_row(row, A.logBins, A.logMin, w, mu, sd, m3 / (sd * sd * sd) / N, o, nullptr, nullptr);
+    if (A.line && o[11] > 0.) {
+      const double c = A.line[j];
+      leak = 0.5 + 0.5 * erf((c - o[1]) / o[2] / sqrt(2.)) - 2. * owens_t_ref((c - o[1]) / o[2], o[3]);
+    }
+  }
+  for (int k = 0; k < A.cols; ++k) A.fit[t * uint64_t(A.cols) + k] = o[k];
+  if (A.leak) A.leak[t] = leak;
+}
+
 // ---- the remaining public model methods of NESTcalc as stage calls (NEST.hh:311-333, 345, 404) ---------------------
 // k_widths: RecombOmegaNR (NEST.cpp:164-171), RecombOmegaER (:173-225) and FanoER (:227-246) for n records;
 // out: 3 columns of n.
@@ -1589,44 +1637,107 @@ __global__ void __launch_bounds__(256) k_spectrum(const __grid_constant__ RunPar
 // -------------------------------------------------------------------------------------------
 struct LArParams {
   int32_t species;
-  uint64_t n, first_event;
+  uint64_t n, first_event, seed;
   uint32_t rk[20];  // Philox round keys of the seed
   double density;
   const double *E, *field;
   double *yields, *fluct;  // [9][n], [4][n]; either may be null
 };
 
-__global__ void __launch_bounds__(256) k_lar(const __grid_constant__ LArParams P) {
+template <int SPECIES>
+#ifndef NB_LAR_MINB
+#define NB_LAR_MINB 3
+#endif
+__global__ void __launch_bounds__(256, NB_LAR_MINB) k_lar(const __grid_constant__ LArParams P) {
+  constexpr bool QUEUE = SPECIES == 1;  // ER: the Lindhard == 1 branch's binomial draws are regrouped (nb_lar.cuh)
+  __shared__ __align__(8) LArPending s_q[QUEUE ? 8 : 1][QUEUE ? 64 : 1];
   LArFieldTerms ft;
   ft.field = ft.density = __longlong_as_double(0x7ff8000000000000ll);  // NaN: matches no field
   // a block walks one contiguous range of the list (not a grid stride): lists that sweep the field slowly keep each
   // thread on one field for many events, which is what the memo above needs
   const uint64_t per = ((P.n + gridDim.x - 1) / gridDim.x + blockDim.x - 1) / blockDim.x * blockDim.x;
   const uint64_t lo = blockIdx.x * per, hi = lo + per < P.n ? lo + per : P.n;
-  for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    LArYields y = lar_yields(P.species, P.E[i], P.field[i], P.density, ft);
-    if (P.yields) {
-      P.yields[i] = y.TotalYield;
-      P.yields[P.n + i] = y.QuantaYield;
-      P.yields[2 * P.n + i] = y.LightYield;
-      P.yields[3 * P.n + i] = y.Nph;
-      P.yields[4 * P.n + i] = y.Ne;
-      P.yields[5 * P.n + i] = y.Nex;
-      P.yields[6 * P.n + i] = y.Nion;
-      P.yields[7 * P.n + i] = y.Lindhard;
-      P.yields[8 * P.n + i] = y.ElectricField;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  int qn = 0;  // warp-uniform fill of this warp's queue
+  // up to 32 pending draws, one candidate each; the rejected go back on the queue
+  auto pass = [&]() {
+    const int take = qn < 32 ? qn : 32;
+    qn -= take;
+    const bool live = lane < take;
+    LArPending e = live ? s_q[QUEUE ? wid : 0][qn + lane] : LArPending{0., 0., 0u, 0u};
+    __syncwarp();
+    bool again = false;
+    if (live) {
+      double Nion;
+      const uint64_t i = lo + e.off;
+      if (lar_binomial_try(P.rk, P.first_event + i, e.att, e.Nq, Nion)) {
+        if (Nion > e.Nq) Nion = e.Nq;
+        double f[4];
+        lar_fluct_store(e.Nq - Nion, Nion, e.p_r, f);
+        double* o = P.fluct + i;
+        o[0] = f[0];
+        o[P.n] = f[1];
+        o[2 * P.n] = f[2];
+        o[3 * P.n] = f[3];
+      } else {
+        again = true;
+        ++e.att;
+      }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, again);
+    if (again) s_q[QUEUE ? wid : 0][qn + __popc(m & lt)] = e;
+    qn += __popc(m);
+    __syncwarp();
+  };
+  // whole warps walk the range together (the queue's ballots want every lane); the next event's inputs are loaded
+  // while this one is computed
+  uint64_t i = lo + threadIdx.x;
+  double E = i < hi ? P.E[i] : 1., F = i < hi ? P.field[i] : 1.;
+  for (uint64_t i0 = lo + (threadIdx.x & ~31u); i0 < hi; i0 += blockDim.x, i += blockDim.x) {
+    const bool active = i < hi;
+    const uint64_t nx = i + blockDim.x;
+    const double En = nx < hi ? P.E[nx] : 1., Fn = nx < hi ? P.field[nx] : 1.;
+    LArYields y = lar_yields(SPECIES, E, F, P.density, ft);
+    if (P.yields && active) {
+      double* o = P.yields + i;
+      o[0] = y.TotalYield;
+      o[P.n] = y.QuantaYield;
+      o[2 * P.n] = y.LightYield;
+      o[3 * P.n] = y.Nph;
+      o[4 * P.n] = y.Ne;
+      o[5 * P.n] = y.Nex;
+      o[6 * P.n] = y.Nion;
+      o[7 * P.n] = y.Lindhard;
+      o[8 * P.n] = y.ElectricField;
     }
     if (P.fluct) {
-      Stream g;
-      g.init(P.rk, P.first_event + i, STREAM_LAR);
-      double f[4];
-      lar_fluctuations(g, P.first_event + i, y, f);
-      P.fluct[i] = f[0];
-      P.fluct[P.n + i] = f[1];
-      P.fluct[2 * P.n + i] = f[2];
-      P.fluct[3 * P.n + i] = f[3];
+      double f[4], p_r = 0., pend = -1.;
+      if (active) {
+        pend = lar_fluct_head(P.rk, P.seed, P.first_event + i, y, QUEUE, p_r, f);
+        if (pend < 0.) {
+          double* o = P.fluct + i;
+          o[0] = f[0];
+          o[P.n] = f[1];
+          o[2 * P.n] = f[2];
+          o[3 * P.n] = f[3];
+        }
+      }
+      if (QUEUE) {
+        const unsigned m = __ballot_sync(0xffffffffu, pend >= 0.);
+        if (m) {
+          if (pend >= 0.) s_q[wid][qn + __popc(m & lt)] = LArPending{pend, p_r, uint32_t(i - lo), 0u};
+          qn += __popc(m);
+          __syncwarp();
+          while (qn >= 32) pass();
+        }
+      }
     }
+    E = En;
+    F = Fn;
   }
+  if (QUEUE)
+    while (qn > 0) pass();
 }
 
 }  // namespace nb

@@ -577,6 +577,44 @@ NB_D double log_factorial(double k) {
   return fma(k + 0.5, log_pos(k + 1.), -(k + 1.)) + 0.91893853320467274178 + stirling_tail(k);
 }
 
+// Hormann's BTRS (see binomial below) in two pieces, so that callers that regroup their draws (k_lar: one candidate
+// per lane and pass, rejected draws re-queued) run the very statements of the in-line loop: the per-draw constants,
+// and one candidate from one Philox block.  pp = min(p, 1 - p), q = 1 - pp, n pp >= 10.
+struct Btrs {
+  double dn, b, a, c, vr, alpha, m, h, logr;
+};
+NB_D Btrs btrs_setup(double dn, double pp, double q) {
+  Btrs s;
+  s.dn = dn;
+  const double spq = sqrt(dn * pp * q);
+  s.b = 1.15 + 2.53 * spq;
+  const double rb = 1. / s.b;
+  s.a = -0.0873 + 0.0248 * s.b + 0.01 * pp;
+  s.c = dn * pp + 0.5;
+  s.vr = 0.92 - 4.2 * rb;
+  s.alpha = (2.83 + 5.1 * rb) * spq;
+  s.m = floor((dn + 1.) * pp);
+  // the per-draw terms of the exact test: loaded here so that their (L2) latency is hidden behind the first candidate
+  s.h = log_factorial(s.m) + log_factorial(dn - s.m);
+  s.logr = log_pos(pp / q);
+  return s;
+}
+// candidate from block w: true when accepted (kk: the variate for pp)
+NB_D bool btrs_try(const Btrs& s, const u128& w, double& kk) {
+  const double u = u53(w.x, w.y) - 0.5;
+  const double v = u53(w.z, w.w);
+  const double us = 0.5 - fabs(u);
+  kk = floor((2. * s.a / us + s.b) * u + s.c);
+  if (us >= 0.07 && v <= s.vr) return true;
+  if (kk < 0. || kk > s.dn) return false;
+  const double lk = log_factorial(kk), lnk = log_factorial(s.dn - kk);  // issued before the logarithms below
+  const double us2 = us * us;
+  // ln( v alpha / (a/us^2 + b) )
+  const double lhs = log_pos(v * s.alpha * us2) - log_pos(s.a + s.b * us2);
+  const double rhs = (s.h - lk) - lnk + (kk - s.m) * s.logr;
+  return lhs <= rhs;
+}
+
 // binom_draw RandomGen.cpp:132-134 = std::binomial_distribution<int64_t>(n,p).  Exact binomial sampler:
 // sequential CDF inversion while n*min(p,1-p) < 10, Hormann's BTRS transformed rejection (J. Stat. Comput.
 // Simul. 46 (1993) 101) above.  Draws from its own counter stream (seed; event, stream): candidate k of a
@@ -631,32 +669,11 @@ NB_D long long binomial(const uint32_t* rk, uint64_t event, uint32_t stream, lon
       }
     }
   } else {
-    const double spq = sqrt(dn * pp * q);
-    const double b = 1.15 + 2.53 * spq;
-    const double rb = 1. / b;
-    const double a = -0.0873 + 0.0248 * b + 0.01 * pp;
-    const double c = dn * pp + 0.5;
-    const double vr = 0.92 - 4.2 * rb;
-    const double alpha = (2.83 + 5.1 * rb) * spq;
-    const double m = floor((dn + 1.) * pp);
-    // the per-draw terms of the exact test: loaded here so that their (L2) latency is hidden behind the first candidate
-    const double h = log_factorial(m) + log_factorial(dn - m);
-    const double logr = log_pos(pp / q);
+    const Btrs B = btrs_setup(dn, pp, q);
     double kk = 0.;
     for (uint32_t att = 0;; ++att) {
       const u128 w = philox4x32_10_rk(e0, e1, att, stream, rk);
-      const double u = u53(w.x, w.y) - 0.5;
-      const double v = u53(w.z, w.w);
-      const double us = 0.5 - fabs(u);
-      kk = floor((2. * a / us + b) * u + c);
-      if (us >= 0.07 && v <= vr) break;
-      if (kk < 0. || kk > dn) continue;
-      const double lk = log_factorial(kk), lnk = log_factorial(dn - kk);  // issued before the logarithms below
-      const double us2 = us * us;
-      // ln( v alpha / (a/us^2 + b) )
-      const double lhs = log_pos(v * alpha * us2) - log_pos(a + b * us2);
-      const double rhs = (h - lk) - lnk + (kk - m) * logr;
-      if (lhs <= rhs) break;
+      if (btrs_try(B, w, kk)) break;
     }
     k = (long long)kk;
   }

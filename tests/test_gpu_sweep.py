@@ -150,3 +150,100 @@ def test_sweep_band_post_on_device_equals_the_host_functions(ctx):
         assert np.allclose(leak_d[k], tot, rtol=1e-12), (keys[k], leak_d[k], tot)
     assert gof_d[3][0] == 0.0 and gof_d[3][1] == 0.0      # the target against itself
     assert np.argmin(gof_d[:, 2]) == 3
+
+
+def _skew_window_fit_on_host(ana, band, j):
+    """the skew-Gaussian fit k_band_fit makes for slice j, redone with the host entry points: GetBand's moments
+    (nb200_band_finalize), the window mean +- 3 sigma on the fixed log axis, EstimateSkew's start values
+    (examples/rootNEST.cpp:1567-1585, 1367-1374), nb200_hist_fit_cov(1, ...)"""
+    st = band.finalize()
+    lb, N = ana.logBins, float(band.accepted[j])
+    w = (ana.logMax - ana.logMin) / lb
+    mean, sd = st[j, 2], st[j, 3]
+    if not (sd > 0 and np.isfinite(mean) and np.isfinite(st[j, 6])):
+        return None
+    skew = st[j, 6] * (N - 2.0) / N
+    lo, hi = mean - 3 * sd, mean + 3 * sd
+    if lo > 2.0 or hi > 3.0:
+        lo, hi = lo - 0.5, hi + 0.5
+    x = ana.logMin + (np.arange(lb) + 0.5) * w
+    inw = np.nonzero((x >= lo) & (x < hi))[0]
+    if inw.size == 0:
+        return None
+    k0, k1 = int(inw[0]), int(inw[-1]) + 1
+    row = band.hist2d.reshape(ana.numBins, lb)[j, k0:k1]
+    n = float(row.sum())
+    if not n > 1:
+        return None
+    if skew == 0.0:
+        skew = 1e-9
+    skew = np.sign(skew) * min(0.7, abs(skew))
+    s23 = abs(skew) ** (2.0 / 3.0)
+    delta0 = np.sign(skew) * np.sqrt(np.pi / 2 * s23 / (s23 + ((4 - np.pi) / 2) ** (2.0 / 3.0)))
+    alpha0 = delta0 / np.sqrt(1 - delta0 * delta0)
+    dE = alpha0 / np.sqrt(1 + alpha0 * alpha0)
+    omega0 = sd / np.sqrt(1 - 2 * dE * dE / np.pi)
+    start = [n * w, mean - omega0 * dE * np.sqrt(2 / np.pi), omega0, alpha0]
+    try:
+        par, cov, chi = capi.hist_fit_cov(1, row, ana.logMin + k0 * w, ana.logMin + k1 * w, start)
+    except capi.NestB200Error:
+        return None
+    return par, cov, chi, int(np.count_nonzero(row))
+
+
+def test_per_bin_band_fits_on_device_equal_the_host_functions(ctx):
+    """the Gaussian and skew-Gaussian fits of every S1 slice of every grid point's band and the leakage
+    read off them, computed on the device (k_band_fit: nb_fit.h's statements, one thread per slice), against the host
+    entry points on the copied-back accumulators (nb200_band_fit_gauss, nb200_hist_fit_cov, nb200_band_leakage_gauss /
+    _skew)"""
+    ana = capi.analysis(0)
+    dets, mods, srcs, rcs, keys = grid_points((100.0, 180.0, 400.0), (0.10, 0.117), (0.1,), "nr")
+    bands = ctx.run_sweep(dets, mods, ana, srcs, rcs, seed=4, n=400_000)
+    nr_line = bands[1].finalize()[:, 2]
+    line = np.where(np.isfinite(nr_line), nr_line - 0.1, 1.0)
+    # Gaussian
+    fit_d, leak_d = ctx.sweep_band_fit(len(bands), ana, model=0, line=line)
+    fitted = 0
+    for k, b in enumerate(bands):
+        fh = b.fit_gauss()
+        assert np.array_equal(fh[:, 7], fit_d[k][:, 7]), keys[k]               # same slices fitted, same points used
+        m = fh[:, 7] > 0
+        fitted += int(m.sum())
+        assert np.allclose(fit_d[k][m][:, :5], fh[m][:, :5], rtol=1e-7, atol=1e-10), keys[k]
+        assert np.allclose(fit_d[k][m][:, 5:7], fh[m][:, 5:7], rtol=1e-6, atol=1e-9), keys[k]
+        nr = np.zeros_like(fh)
+        nr[:, 1] = line
+        lk = capi.band_leakage_gauss(fh, nr, 0.0)[:, 1]
+        assert np.allclose(leak_d[k][m], lk[m], rtol=1e-6, atol=1e-12), keys[k]
+        assert np.all(leak_d[k][~m] == 0.0)
+    assert fitted > 300
+    # skew-Gaussian
+    fit_s, leak_s = ctx.sweep_band_fit(len(bands), ana, model=1, line=line)
+    checked = 0
+    for k in (0, 3, 5):
+        b = bands[k]
+        for j in range(0, ana.numBins, 5):
+            h = _skew_window_fit_on_host(ana, b, j)
+            if h is None:
+                assert fit_s[k][j, 11] == 0.0, (keys[k], j)
+                continue
+            par, cov, chi, used = h
+            o = fit_s[k][j]
+            assert o[11] == used, (keys[k], j, o[11], used)
+            assert np.allclose(o[:4], par, rtol=1e-6, atol=1e-9), (keys[k], j, o[:4], par)
+            assert np.allclose(o[4:7], np.sqrt(np.diag(cov))[1:], rtol=1e-5), (keys[k], j)
+            assert np.allclose(o[7:10], [cov[1, 2], cov[1, 3], cov[2, 3]], rtol=1e-4, atol=1e-12), (keys[k], j)
+            assert abs(o[10] - chi) <= 1e-6 * max(chi, 1.0), (keys[k], j, o[10], chi)
+            lk, _, _ = capi.band_leakage_skew([par[1]], [par[2]], [0.0], [par[3]], [line[j]])
+            assert abs(leak_s[k][j] - lk[0]) < 1e-7, (keys[k], j, leak_s[k][j], lk[0])
+            checked += 1
+    assert checked >= 30
+    # the context's own accumulator (nb200_run_async) goes through the same kernel
+    ctx.band_reset(ana)
+    ctx.run_async(dets[1], mods[1], ana, srcs[1], rcs[1], 4, 0, 400_000)
+    one, _ = ctx.band_fit_device(ana, model=0)
+    assert np.array_equal(one, fit_d[1])
+    with pytest.raises(capi.NestB200Error):
+        ctx.sweep_band_fit(len(bands) + 1, ana)            # no sweep of that shape
+    with pytest.raises(capi.NestB200Error):
+        ctx.sweep_band_fit(len(bands), ana, model=2)
