@@ -353,6 +353,27 @@ def main():
     e2e_value, d2h, e2e_steps = e2e_run(False)
     e2e_packed, d2h_packed, _ = e2e_run(True)
 
+    def e2e_band_only():
+        """the same call with no event records: nb200_run with a HOST band accumulator only (what is left of the
+        reference's output when its per-event rows go to /dev/null, as in the reference arm: the band table)"""
+        hband = capi.Band(ana)
+        nb_ = int(n)
+
+        def step_(i):
+            ctx._check(capi.lib().nb200_run(ctx.h, C.byref(det), C.byref(mo), C.byref(ana), C.byref(src), C.byref(rc),
+                                            seed, (20_000 + i * world + rank) * nb_, nb_, None, C.byref(hband.c)))
+        step_(0)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(2):
+            step_(1 + i)
+        barrier()
+        tt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(nb_) * world * 2 / float(tt.item())
+    e2e_band = e2e_band_only()
+
     # the host's ingest ceiling for this many GPUs: plain cudaMemcpyAsync D2H into pinned memory, every rank at once
     ing_bytes = 1 << 30
     dsrc = torch.empty(ing_bytes, dtype=torch.uint8, device="cuda")
@@ -388,6 +409,9 @@ def main():
                 "api": "nb200_run (C-ABI), pinned host SoA of the 14 CLI columns (f64, as the reference prints doubles) + band",
                 "packed_f32": {"value": e2e_packed, "d2h_bytes_per_step": int(d2h_packed),
                                "api": "the same call with NB200_SOA_F32 (float columns, 56 B/event)"},
+                "band_only": {"value": e2e_band, "d2h_bytes_per_step": int(nwords * 8), "events_per_step_per_gpu": int(n),
+                              "api": "the same call without event records (soa = NULL): host band accumulator only, "
+                                     "wall clock"},
                 "host_ingest_gbs": host_ingest_gbs,
                 "host_ingest_note": "plain cudaMemcpyAsync D2H of 1 GiB x 4 into pinned memory, all ranks at once: the "
                                     "ceiling the e2e record stream runs against",
@@ -517,6 +541,29 @@ def main():
             ctx.run_async(grid[0][0], mods_[0], ana, srcs_[0], grid[0][1], seed, rank * big, big)
         sweep[sname + "_large_run_events_per_s"] = big * world / timed(run_big)
         sweep[sname + "_sweep_over_large_run"] = sweep[sname + "_events_per_s"] / sweep[sname + "_large_run_events_per_s"]
+    # band post-processing of the sweep just made (the 8B one), SURVEY 8f-4: Gaussian and skew-Gaussian fit of every S1
+    # slice of every grid point on the device (k_band_fit, one launch) against the same fits by the host entry point on
+    # the copied-back accumulators (a sample of points, scaled)
+    kp = len(grid)
+    hb = [capi.Band(ana) for _ in range(kp)]  # fresh host accumulators: the timed calls above added three sweeps into theirs
+    Bk = (capi.BandHist * kp)(*[b_.c for b_ in hb])
+    ctx._check(capi.lib().nb200_run_sweep(ctx.h, kp, Dk, Mk, C.byref(ana), Sk, Rk, seed, 0, npt, Bk))
+    t0 = time.perf_counter()
+    fit_d, _ = ctx.sweep_band_fit(kp, ana, model=0)
+    t_dev0 = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    ctx.sweep_band_fit(kp, ana, model=1)
+    t_dev1 = time.perf_counter() - t0
+    ns_ = min(kp, 8)
+    t0 = time.perf_counter()
+    fit_h = [hb[i_].fit_gauss() for i_ in range(ns_)]
+    t_host = (time.perf_counter() - t0) * kp / ns_
+    sweep["band_fit"] = {"rows": kp * ana.numBins, "device_gauss_ms": t_dev0 * 1e3, "device_skew_ms": t_dev1 * 1e3,
+                         "host_gauss_ms_scaled": t_host * 1e3,
+                         "max_rel_diff_vs_host": float(max(
+                             np.max(np.abs(fit_d[i_][:, :3] - fit_h[i_][:, :3]) / np.maximum(np.abs(fit_h[i_][:, :3]), 1e-12))
+                             for i_ in range(ns_))),
+                         "note": "nb200_sweep_band_fit (wall clock incl. result copy-back) vs nb200_band_fit_gauss on the host"}
     sweep["timing"] = "wall clock around nb200_run_sweep (host parameter blocks, launches, band copy-back), max over ranks"
     out["config4_sweep"] = sweep
     out["config4_sweep_events_per_s"] = sweep["WIMP50_events_per_s"]

@@ -635,7 +635,7 @@ int nb200_create(int device, nb200_ctx** out) {
     return NB200_ECUDA;
   }
   c->stream = c->own_stream;
-  if (const char* e = std::getenv("NB200_CHUNK_LOG2")) c->chunk_log2 = std::min(28, std::max(16, std::atoi(e)));
+  if (const char* e = std::getenv("NB200_CHUNK_LOG2")) c->chunk_log2 = std::min(25, std::max(16, std::atoi(e)));  // <= 2^25: queue entries index a chunk with 26 bits
   {  // Phi table of the photo-electron acceptance bounds (nb_chain.cuh)
     double tab[NB_PHI_N];
     for (int k = 0; k < NB_PHI_N; ++k) tab[k] = 0.5 * erfc(-(-8. + double(k) / 16.) * 0.70710678118654752440);

@@ -394,6 +394,16 @@ __global__ void __launch_bounds__(kPreBlock, NB_PRE_MINB)
 struct SlotEntry {
   uint32_t j, e;
 };
+// What the deferred finisher needs to know of a queued slot's event travels in the top bits of e (the workspace index
+// takes the low 26: chunks are <= 2^25 events): valid photo-electrons (slot_valid), double hit, special event.  Without
+// them the finisher had to fetch the event's hit counts before it could start on the slot -- a second dependent trip
+// to device memory for a kernel that does nothing but wait on it; now only special events' counts are fetched.
+constexpr uint32_t kEntIdxBits = 26, kEntIdxMask = (1u << kEntIdxBits) - 1u;
+constexpr uint32_t kEntDbl = 1u << 28, kEntSpecial = 1u << 29;
+NB_D uint32_t ent_flags(int nv, bool dbl, bool special) {
+  return (uint32_t(nv) << kEntIdxBits) | (dbl ? kEntDbl : 0u) | (special ? kEntSpecial : 0u);
+}
+NB_D int ent_nv(uint32_t e) { return int((e >> kEntIdxBits) & 3u); }
 constexpr int kSlotCap = 64;  // <= 31 left over + 32 pushed per iteration
 constexpr size_t kHitDynSmem = NB_ZIG_N * (sizeof(double) + sizeof(uint32_t));  // ziggurat tables (opt-in: > 48 KB total)
 
@@ -524,7 +534,7 @@ __device__ __noinline__ void hits_finish_slow(const RunParams& P, const int* s_n
                                              const double* zw) {
   const bool live = lane < count;
   const SlotEntry en = live ? q[lane] : SlotEntry{0u, 0u};
-  const int e = int(en.e);
+  const int e = int(en.e & kEntIdxMask);
   finish_slot(P, s_nh[e], s_nd[e], en.j, ev0 + uint64_t(e), zk, zw, live,
               [&](double a, bool coin) { hit_commit(P, s_area, s_spike, e, a, coin); });
   __syncwarp();
@@ -562,6 +572,7 @@ struct SlowItem {
 #ifndef NB_FIN_MINB
 #define NB_FIN_MINB 8
 #endif
+
 constexpr int kFinBlock = 128;
 constexpr int kFinWarps = kFinBlock / 32;
 
@@ -569,8 +580,9 @@ struct FinCtx {
   const RunParams* P;
   const Work* W;
   uint64_t ev;
-  int nh, nd;
+  int nh, nd;  // fin_counts only
 };
+// where a queued slot's event lives: parameters, workspace, event id (no memory access)
 template <bool SWEEP>
 NB_D FinCtx fin_resolve(const RunParams* P0, const SweepArgs* Ap, uint64_t idx) {
   FinCtx c;
@@ -585,10 +597,14 @@ NB_D FinCtx fin_resolve(const RunParams* P0, const SweepArgs* Ap, uint64_t idx) 
     c.W = &P0->work;
     c.ev = P0->first_event + P0->chunk_off + idx;
   }
+  c.nh = c.nd = 0;
+  return c;
+}
+// the event's hit counts (special events only: the others' entries carry what the finisher needs)
+NB_D void fin_counts(FinCtx& c, uint64_t idx) {
   int nh = c.W->nHits[idx];
   c.nh = nh > 0 ? nh : 0;
   c.nd = c.W->nphe[idx] - c.nh;  // k_hits left Nphe = nHits + nD there
-  return c;
 }
 // the hits of a finished slot (no efficiency / coincidence draws) into the event's sums
 NB_D void fin_commit(const RunParams& P, const Work& W, uint64_t idx, bool dbl, int nv, double v0, double v1, double v2) {
@@ -625,7 +641,7 @@ NB_D void hits_finish_body(const RunParams* P0, const SweepArgs* Ap, const HitQu
   auto run_slow = [&](const SlowItem* items, int count) {
     const bool live = lane < count;
     SlowItem it = live ? items[lane] : SlowItem{0u, 0u, {0., 0., 0.}, 0u, 0u};
-    const FinCtx c = fin_resolve<SWEEP>(P0, Ap, live ? it.e : 0u);
+    const FinCtx c = fin_resolve<SWEEP>(P0, Ap, it.e & kEntIdxMask);
     const RunParams& P = *c.P;
     const uint32_t e0 = uint32_t(c.ev), e1 = uint32_t(c.ev >> 32);
     const u128 r = philox4x32_10_rk(e0, e1, it.j, STREAM_HIT, rk);
@@ -655,17 +671,18 @@ NB_D void hits_finish_body(const RunParams* P0, const SweepArgs* Ap, const HitQu
         st &= ~(3u << (2 * which));
       }
     }
-    if (live) fin_commit(P, *c.W, it.e, int(it.j) < c.nd, slot_valid(int(it.j), c.nd, c.nh - c.nd), v0, v1, v2);
+    if (live) fin_commit(P, *c.W, it.e & kEntIdxMask, (it.e & kEntDbl) != 0u, ent_nv(it.e), v0, v1, v2);
     __syncwarp();
   };
   // slots of events that draw efficiencies / coincidence windows: the full per-slot code
   auto run_special = [&](const SlotEntry* ents, int count) {
     const bool live = lane < count;
     const SlotEntry en = live ? ents[lane] : SlotEntry{0u, 0u};
-    const FinCtx c = fin_resolve<SWEEP>(P0, Ap, en.e);
+    const uint64_t idx = en.e & kEntIdxMask;
+    FinCtx c = fin_resolve<SWEEP>(P0, Ap, idx);
+    fin_counts(c, idx);
     const RunParams& P = *c.P;
     const Work& W = *c.W;
-    const uint64_t idx = en.e;
     finish_slot(P, c.nh, c.nd, en.j, c.ev, s_zk, s_zw, live, [&](double a, bool coin) {
       if (a > P.det.sPEthr && coin) {
         atomicAdd(&reinterpret_cast<unsigned long long*>(W.area)[idx], (unsigned long long)__double2ll_rn(a * NB_AREA_FX));
@@ -680,16 +697,16 @@ NB_D void hits_finish_body(const RunParams* P0, const SweepArgs* Ap, const HitQu
     const unsigned int i = base + lane;
     const SlotEntry en = i < n ? Q.entries[i] : SlotEntry{0xffffffffu, 0u};
     const bool live = en.j != 0xffffffffu;  // (sentinel: an entry reserved but never written, see k_hits)
-    const FinCtx c = fin_resolve<SWEEP>(P0, Ap, live ? en.e : 0u);
+    const FinCtx c = fin_resolve<SWEEP>(P0, Ap, live ? (en.e & kEntIdxMask) : 0u);
     const RunParams& P = *c.P;
-    const bool special = live && (P.det.sPEeff < 1. || !(c.nh > P.det.coinLevel));
+    const bool special = live && (en.e & kEntSpecial) != 0u;
     bool slow = false;
     SlowItem it{en.e, en.j, {0., 0., 0.}, 0u, 0u};
     if (live && !special) {
       const uint32_t e0 = uint32_t(c.ev), e1 = uint32_t(c.ev >> 32);
       const u128 r = philox4x32_10_rk(e0, e1, en.j, STREAM_HIT, rk);
       const u128 t = philox4x32_10_rk(e0, e1, en.j, STREAM_HIT2, rk);
-      const int nv = slot_valid(int(en.j), c.nd, c.nh - c.nd);
+      const int nv = ent_nv(en.e);
 #pragma unroll
       for (int which = 0; which < 3; ++which) {
         if (which < nv) {
@@ -703,7 +720,7 @@ NB_D void hits_finish_body(const RunParams* P0, const SweepArgs* Ap, const HitQu
         }
       }
       if (it.st == 0u)
-        fin_commit(P, *c.W, en.e, int(en.j) < c.nd, nv, it.v[0], it.v[1], it.v[2]);
+        fin_commit(P, *c.W, en.e & kEntIdxMask, (en.e & kEntDbl) != 0u, nv, it.v[0], it.v[1], it.v[2]);
       else
         slow = true;
     }
@@ -899,6 +916,7 @@ NB_D void hits_body(const RunParams* P0, const SweepArgs* Ap, RunParams* sP, uns
     int qcount = 0;  // warp-uniform queue fill
     for (int it = maxlen; it > 0; --it) {
       bool queue = false;
+      uint32_t qflags = 0u;  // what the deferred finisher needs of the slot's event (ent_flags)
       if (h < h1) {
         if (h == e_end) {  // crossed into the next event with slots: flush, then advance
           const unsigned long long a_ev = a_fx - (unsigned long long)a_spike * NB_AREA_MAGIC_BITS;
@@ -942,6 +960,7 @@ NB_D void hits_body(const RunParams* P0, const SweepArgs* Ap, RunParams* sP, uns
         const bool c1 = v1 <= P.pe_cut && (v1 < P.pe_sfast || (A1 & NB_PE_PRETEST_MASK) == NB_PE_PRETEST_MASK);
         const bool c2 = v2 <= P.pe_cut && (v2 < P.pe_sfast || (A2 & NB_PE_PRETEST_MASK) == NB_PE_PRETEST_MASK);
         queue = sp || !f0 || c0 || (nv >= 2 && (!f1 || c1)) || (nv >= 3 && (!f2 || c2));
+        qflags = ent_flags(nv, dbl, sp);
         if (!queue) {
           // areas are summed as integers in units of 2^-32 phe: fma(a, 2^32, 1.5 * 2^52) rounds a 2^32 to the
           // nearest integer (ties to even, as __double2ll_rn) and leaves it in the low mantissa bits; the raw
@@ -967,7 +986,7 @@ NB_D void hits_body(const RunParams* P0, const SweepArgs* Ap, RunParams* sP, uns
       if (m) {
         if (queue) {
           const uint32_t at = q_addr + uint32_t(qcount + __popc(m & ((1u << lane) - 1u))) * uint32_t(sizeof(SlotEntry));
-          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(at), "r"(uint32_t(j)), "r"(uint32_t(e)) : "memory");
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(at), "r"(uint32_t(j)), "r"(uint32_t(e) | qflags) : "memory");
         }
         qcount += __popc(m);
         __syncwarp();
