@@ -6,7 +6,10 @@
 // Levenberg-Marquardt with analytic Jacobians, parameter errors from (J^T W J)^-1 at the minimum (MIGRAD's parabolic
 // errors for a chi^2).  The functions are __host__ __device__: the host entry points of include/nest_b200.h
 // (nb200_band_fit_gauss, nb200_hist_fit*, nb200_graph_fit) and the device kernel that fits the bands of a whole sweep
-// (k_band_fit, one thread per grid point and S1 bin) run the same statements in the same order.
+// (k_band_fit, one WARP per grid point and S1 bin) run the same statements; only the sums over a slice's bins differ:
+// they are written once, over the bins a member of a cooperating group owns, and completed by the group's reduction
+// (FitSerial: one member, nothing to do -- the host; FitWarp: 32 lanes, bins dealt round-robin, butterfly all-reduce,
+// which leaves bit-identical totals in every lane, so the lanes walk the minimiser in step).
 #pragma once
 #include <cmath>
 #include <cstdint>
@@ -20,6 +23,28 @@
 namespace nb {
 
 constexpr int kFitMaxPar = 4;
+
+// who sums: one thread ...
+struct FitSerial {
+  NB_FIT_HD static int first() { return 0; }
+  NB_FIT_HD static int step() { return 1; }
+  NB_FIT_HD static void sum(double*, int) {}
+  NB_FIT_HD static int imin(int v) { return v; }
+  NB_FIT_HD static int imax(int v) { return v; }
+};
+#ifdef __CUDACC__
+// ... or the 32 lanes of a warp (all of them must be there: full-mask shuffles)
+struct FitWarp {
+  __device__ static int first() { return int(threadIdx.x & 31u); }
+  __device__ static int step() { return 32; }
+  __device__ static void sum(double* v, int n) {
+    for (int i = 0; i < n; ++i)
+      for (int m = 16; m > 0; m >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], m);
+  }
+  __device__ static int imin(int v) { return __reduce_min_sync(0xffffffffu, v); }
+  __device__ static int imax(int v) { return __reduce_max_sync(0xffffffffu, v); }
+};
+#endif
 
 // Gauss-Jordan with partial pivoting on an n x n system (n <= 4); false when singular
 NB_FIT_HD bool fit_solve(int n, const double M[kFitMaxPar][kFitMaxPar], const double* v, double* x) {
@@ -103,9 +128,10 @@ NB_FIT_HD double fit_model(int model, const double* p, double x, double* g) {
 
 // Point sets.  A histogram row as TH1::Fit sees it by default: the function at the bin centres, weights 1 / content,
 // empty bins left out (weight 0 here: fit_chi2 skips them).  T: uint64_t (host API) or unsigned long long (the
-// device accumulator).
-template <class T>
+// device accumulator); G: who sums (above).
+template <class T, class G = FitSerial>
 struct FitRow {
+  typedef G Group;
   const T* row;
   int lb;
   double x0, w;
@@ -114,12 +140,14 @@ struct FitRow {
   NB_FIT_HD double y(int k) const { return double(row[k]); }
   NB_FIT_HD double wgt(int k) const { return row[k] ? 1. / double(row[k]) : 0.; }
   NB_FIT_HD int used() const {
-    int n = 0;
-    for (int k = 0; k < lb; ++k) n += row[k] ? 1 : 0;
-    return n;
+    double n = 0.;
+    for (int k = G::first(); k < lb; k += G::step()) n += row[k] ? 1. : 0.;
+    G::sum(&n, 1);
+    return int(n);
   }
 };
 struct FitPoints {
+  typedef FitSerial Group;
   const double *xs, *ys, *ws;
   int n;
   NB_FIT_HD int size() const { return n; }
@@ -132,26 +160,35 @@ struct FitPoints {
 // sum of w_k (y_k - f(x_k))^2 and, on request, J^T W J and J^T W r
 template <class Pts>
 NB_FIT_HD double fit_chi2(int model, const Pts& pts, const double* p, double JtJ[kFitMaxPar][kFitMaxPar], double* Jtr) {
+  typedef typename Pts::Group G;
   const int n = fit_npar(model);
-  double chi = 0., g[kFitMaxPar];
-  if (JtJ)
-    for (int i = 0; i < n; ++i) {
-      Jtr[i] = 0.;
-      for (int j = 0; j < n; ++j) JtJ[i][j] = 0.;
-    }
+  // acc: chi^2, J^T W r [n], the upper triangle of J^T W J row by row
+  double acc[1 + kFitMaxPar + kFitMaxPar * (kFitMaxPar + 1) / 2], g[kFitMaxPar];
+  const int nacc = JtJ ? 1 + n + n * (n + 1) / 2 : 1;
+  for (int i = 0; i < nacc; ++i) acc[i] = 0.;
   const int m = pts.size();
-  for (int k = 0; k < m; ++k) {
+  for (int k = G::first(); k < m; k += G::step()) {
     const double w = pts.wgt(k);
     if (!(w > 0.)) continue;
     const double r = pts.y(k) - fit_model(model, p, pts.x(k), JtJ ? g : nullptr);
-    chi += w * r * r;
-    if (JtJ)
+    acc[0] += w * r * r;
+    if (JtJ) {
+      int t = 1 + n;
       for (int i = 0; i < n; ++i) {
-        Jtr[i] += w * g[i] * r;
-        for (int j = 0; j < n; ++j) JtJ[i][j] += w * g[i] * g[j];
+        acc[1 + i] += w * g[i] * r;
+        for (int j = i; j < n; ++j) acc[t++] += w * g[i] * g[j];
       }
+    }
   }
-  return chi;
+  G::sum(acc, nacc);
+  if (JtJ) {
+    int t = 1 + n;
+    for (int i = 0; i < n; ++i) {
+      Jtr[i] = acc[1 + i];
+      for (int j = i; j < n; ++j) JtJ[i][j] = JtJ[j][i] = acc[t++];
+    }
+  }
+  return acc[0];
 }
 
 // Levenberg-Marquardt on weighted points; returns the number of points used, 0 when there are too few or no minimum
@@ -232,24 +269,27 @@ NB_FIT_HD void skew_start(double mean, double sd, double skew, double* start) {
 // One S1 slice of GetBand_Gaussian (examples/rootNEST.cpp:1309-1359, skewness == 0): Gaussian fit of the slice's row of
 // the 2-D histogram.  o[8] = {A, mean, sigma, mean error, sigma error, chi^2 per degree of freedom, the reference's own
 // goodness figure band[j][8] (:1346-1357), points used}; zeros when fewer than four log bins are filled or no minimum
-// was found.  accepted: the slice's event count (those outside the axis are ROOT's underflow bin).
-template <class T>
+// was found.  accepted: the slice's event count (those outside the axis are ROOT's underflow bin).  Every member of
+// the group G calls it and gets the same o.
+template <class G, class T>
 NB_FIT_HD void fit_gauss_row(const T* row, int lb, double logMin, double w, double accepted, double* o) {
   const double kPi = 3.14159265358979323846;
   for (int i = 0; i < 8; ++i) o[i] = 0.;
   // start values from the histogram's own moments (the y = 0 entries are outside the axis: ROOT's underflow)
-  double n = 0., sx = 0., sxx = 0.;
-  for (int k = 0; k < lb; ++k) {
+  double mo[3] = {0., 0., 0.};  // n, sum x, sum x^2
+  for (int k = G::first(); k < lb; k += G::step()) {
     const double c = double(row[k]), x = logMin + (double(k) + 0.5) * w;
-    n += c;
-    sx += c * x;
-    sxx += c * x * x;
+    mo[0] += c;
+    mo[1] += c * x;
+    mo[2] += c * x * x;
   }
+  G::sum(mo, 3);
+  const double n = mo[0];
   if (!(n > 1.)) return;
-  const double mu = sx / n;
-  const double var = sxx / n - mu * mu + w * w / 12.;
+  const double mu = mo[1] / n;
+  const double var = mo[2] / n - mu * mu + w * w / 12.;
   double p[4] = {n * w / sqrt(2. * kPi * var), mu, sqrt(var), 0.}, err[4] = {0., 0., 0., 0.}, chi = 0.;
-  const int used = fit_lm(0, FitRow<T>{row, lb, logMin, w}, p, err, &chi, nullptr);
+  const int used = fit_lm(0, FitRow<T, G>{row, lb, logMin, w}, p, err, &chi, nullptr);
   if (!used) return;
   o[0] = p[0];
   o[1] = p[1];
@@ -260,7 +300,7 @@ NB_FIT_HD void fit_gauss_row(const T* row, int lb, double logMin, double w, doub
   // the reference's own goodness figure (:1346-1357) in its own indexing: TH1F::operator[](k) is ROOT bin k
   // (k = 0 the underflow, which holds the events pushed as y = 0), the model taken at logMin + k w
   double g = 0.;
-  for (int k = 0; k < lb; ++k) {
+  for (int k = G::first(); k < lb; k += G::step()) {
     const double x = logMin + double(k) * w;
     const double model = p[0] * exp(-0.5 * (x - p[1]) * (x - p[1]) / (p[2] * p[2]));
     const double content = k == 0 ? accepted - n : double(row[k - 1]);
@@ -268,6 +308,7 @@ NB_FIT_HD void fit_gauss_row(const T* row, int lb, double logMin, double w, doub
     const double denom = fd > 1.f ? fd : 1.f;
     g += (content - model) * (content - model) / denom;
   }
+  G::sum(&g, 1);
   g /= double(lb) - 3. - 1.;
   o[6] = (g != g || g < 0. || g >= 1.7976931348623157e308) ? 0. : g;
   o[7] = double(used);
@@ -279,13 +320,9 @@ NB_FIT_HD void fit_gauss_row(const T* row, int lb, double logMin, double w, doub
 // EstimateSkew's start values.  mean, sd, skew: GetBand's moments of the slice (skew = mean of ((y - mean) / sd)^3).
 // o[12] = {A, xi, omega, alpha, xi error, omega error, alpha error, cov(xi, omega), cov(xi, alpha), cov(omega, alpha),
 // chi^2 per degree of freedom, points used}; zeros when the window holds too few filled bins or no minimum was found.
-// k_lo / k_hi (or null): the window's bin range, for callers that want to redo the fit elsewhere.
-template <class T>
-NB_FIT_HD void fit_skew_row(const T* row, int lb, double logMin, double w, double mean, double sd, double skew, double* o,
-                            int* k_lo, int* k_hi) {
+template <class G, class T>
+NB_FIT_HD void fit_skew_row(const T* row, int lb, double logMin, double w, double mean, double sd, double skew, double* o) {
   for (int i = 0; i < 12; ++i) o[i] = 0.;
-  if (k_lo) *k_lo = 0;
-  if (k_hi) *k_hi = 0;
   if (!(sd > 0.) || !isfinite(mean) || !isfinite(skew)) return;
   double lo = mean - 3. * sd, hi = mean + 3. * sd;
   if (lo > 2. || hi > 3.) {
@@ -294,21 +331,22 @@ NB_FIT_HD void fit_skew_row(const T* row, int lb, double logMin, double w, doubl
   }
   int k0 = lb, k1 = 0;
   double n = 0.;
-  for (int k = 0; k < lb; ++k) {
+  for (int k = G::first(); k < lb; k += G::step()) {
     const double x = logMin + (double(k) + 0.5) * w;
     if (x >= lo && x < hi) {
       if (k < k0) k0 = k;
-      k1 = k + 1;
+      if (k + 1 > k1) k1 = k + 1;
       n += double(row[k]);
     }
   }
+  k0 = G::imin(k0);
+  k1 = G::imax(k1);
+  G::sum(&n, 1);
   if (k1 <= k0 || !(n > 1.)) return;
-  if (k_lo) *k_lo = k0;
-  if (k_hi) *k_hi = k1;
   double p[4], err[4] = {0., 0., 0., 0.}, cov[16], chi = 0.;
   skew_start(mean, sd, skew, p);
   p[0] = n * w;  // the function integrates to its amplitude: events in the window times the bin width
-  const int used = fit_lm(1, FitRow<T>{row + k0, k1 - k0, logMin + double(k0) * w, w}, p, err, &chi, cov);
+  const int used = fit_lm(1, FitRow<T, G>{row + k0, k1 - k0, logMin + double(k0) * w, w}, p, err, &chi, cov);
   if (!used) return;
   o[0] = p[0];
   o[1] = p[1];
@@ -322,6 +360,20 @@ NB_FIT_HD void fit_skew_row(const T* row, int lb, double logMin, double w, doubl
   o[9] = cov[2 * 4 + 3];
   o[10] = used > 4 ? chi / double(used - 4) : 0.;
   o[11] = double(used);
+}
+
+// rootNEST.cpp:1587-1602 by a group: the midpoint rule's 2500 terms dealt out over the members
+template <class G>
+NB_FIT_HD double owens_t_ref_by(double h, double a) {
+  const int nIntSteps = 2500;
+  const double dx = a / nIntSteps;
+  double T = 0.;
+  for (int k = G::first(); k < nIntSteps; k += G::step()) {
+    const double x = (k + 0.5) * dx;
+    T += exp(-0.5 * h * h * (1 + x * x)) / (1 + x * x) * dx;
+  }
+  G::sum(&T, 1);
+  return T / (2. * 3.14159265358979323846);
 }
 
 }  // namespace nb

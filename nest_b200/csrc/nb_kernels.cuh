@@ -1531,9 +1531,11 @@ __global__ void __launch_bounds__(256) k_band_post(const __grid_constant__ BandP
 // k_band_fit: the per-bin fits of the band post-processing for batched bands -- GetBand_Gaussian (examples/rootNEST.cpp:
 // 1309-1359) or the skew-Gaussian band (:1360-1507) of every S1 slice of every grid point, and the leakage below a line
 // read off the fits (:700-738, 848 Gaussian; :700-735, 1587-1602 skew-normal CDF with the reference's Owen's-T
-// quadrature).  One thread per (grid point, S1 bin): a slice is <= logBins points and a few dozen Levenberg-Marquardt
-// steps, a sweep has hundreds of points x ~100 bins of them, and the statements are nb_fit.h's -- the very functions the
-// host entry points (nb200_band_fit_gauss, nb200_hist_fit_cov, nb200_band_leakage_gauss / _skew) run.
+// quadrature).  One WARP per (grid point, S1 bin): the lanes share out the slice's log bins (the sums of the chi^2,
+// J^T W r and J^T W J are 15 butterfly all-reduces per evaluation) and walk the minimiser in step -- a sweep has hundreds
+// of points x ~100 bins of such slices.  The statements are nb_fit.h's, the very functions the host entry points
+// (nb200_band_fit_gauss, nb200_hist_fit_cov, nb200_band_leakage_gauss / _skew) run with a group of one.  (One THREAD per
+// slice, the first version, measured 7.7 ms for 24 500 slices: 1.3 warps per scheduler, each a serial chain of exp.)
 struct BandFitArgs {
   const unsigned long long* bands;  // [n_points][band_words]
   uint64_t band_words, n_rows;      // n_rows = n_points * numBins
@@ -1543,8 +1545,9 @@ struct BandFitArgs {
   double* fit;         // [n_points][numBins][cols]
   double* leak;        // [n_points][numBins] or null (needs line)
 };
-__global__ void __launch_bounds__(128) k_band_fit(const __grid_constant__ BandFitArgs A) {
-  const uint64_t t = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+constexpr int kBandFitRows = 4;  // slices (warps) per block
+__global__ void __launch_bounds__(kBandFitRows * 32) k_band_fit(const __grid_constant__ BandFitArgs A) {
+  const uint64_t t = blockIdx.x * uint64_t(kBandFitRows) + (threadIdx.x >> 5);  // the warp's slice
   if (t >= A.n_rows) return;
   const uint64_t point = t / uint64_t(A.numBins);
   const int j = int(t - point * uint64_t(A.numBins));
@@ -1556,7 +1559,7 @@ __global__ void __launch_bounds__(128) k_band_fit(const __grid_constant__ BandFi
   double o[12];
   double leak = 0.;
   if (A.model == 0) {
-    fit_gauss_row(row, A.logBins, A.logMin, w, N, o);
+    fit_gauss_row<FitWarp>(row, A.logBins, A.logMin, w, N, o);
     if (A.line && o[7] > 0.) leak = (1. - erf((o[1] - A.line[j]) / o[2] / sqrt(2.))) / 2.;
   } else {
     // GetBand's moments of the slice (execNEST.cpp:1582-1618), as k_band_post
@@ -1565,14 +1568,16 @@ __global__ void __launch_bounds__(128) k_band_fit(const __grid_constant__ BandFi
     const double mu = Sy / N;
     const double sd = sqrt((Sy2 - 2. * mu * Sy + N * mu * mu) / (N - 1.));
     const double m3 = Sy3 - 3. * mu * Sy2 + 3. * mu * mu * Sy - N * mu * mu * mu;
-    fit_skew_row(row, A.logBins, A.logMin, w, mu, sd, m3 / (sd * sd * sd) / N, o, nullptr, nullptr);
-    if (A.line && o[11] > 0.) {
+    fit_skew_row<FitWarp>(row, A.logBins, A.logMin, w, mu, sd, m3 / (sd * sd * sd) / N, o);
+    if (A.line && o[11] > 0.) {  // (warp-uniform: every lane holds the same o)
       const double c = A.line[j];
-      leak = 0.5 + 0.5 * erf((c - o[1]) / o[2] / sqrt(2.)) - 2. * owens_t_ref((c - o[1]) / o[2], o[3]);
+      leak = 0.5 + 0.5 * erf((c - o[1]) / o[2] / sqrt(2.)) - 2. * owens_t_ref_by<FitWarp>((c - o[1]) / o[2], o[3]);
     }
   }
-  for (int k = 0; k < A.cols; ++k) A.fit[t * uint64_t(A.cols) + k] = o[k];
-  if (A.leak) A.leak[t] = leak;
+  if ((threadIdx.x & 31u) == 0u) {
+    for (int k = 0; k < A.cols; ++k) A.fit[t * uint64_t(A.cols) + k] = o[k];
+    if (A.leak) A.leak[t] = leak;
+  }
 }
 
 // ---- the remaining public model methods of NESTcalc as stage calls (NEST.hh:311-333, 345, 404) ---------------------

@@ -90,7 +90,9 @@ NB_D LArYields lar_recombination_fast(double Total, double Ye, double Yph, doubl
   double Nq = Ne + Nph;
   double Nion = Nq * (1.0 / (1 + NB_LAR_NEXONI));
   double Nex = Nq - Nion;
-  double Lindhard = (Total * (1.0 / energy)) * NB_LAR_WQ * 1e-3;
+  // (1 / energy overflows for subnormal energies, where the quotient itself does not)
+  const double TE = fabs(energy) >= 1e-300 ? Total * (1.0 / energy) : Total / energy;
+  double Lindhard = TE * NB_LAR_WQ * 1e-3;
   return LArYields{Total, Ye, Yph, Nph, Ne, Nex, Nion, Lindhard, efield};
 }
 

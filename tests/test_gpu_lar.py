@@ -58,3 +58,24 @@ def test_lar_batch_invariance(ctx):
     assert np.array_equal(a, np.hstack([b1, b2]))
     with pytest.raises(capi.NestB200Error):
         ctx.lar(3, E, 500.0, 1.393)      # dE/dx and LET models are outside this path
+
+
+@pytest.mark.parametrize("species", [0, 1, 2])
+def test_lar_edge_energies(ctx, ref, species):
+    """the bit-built logarithm of k_lar only takes positive normal finite energies; zero, negative, subnormal, huge and
+    non-finite ones go through libm and must give the reference's zeros / inf / NaN column by column"""
+    E = np.array([0.0, -1.0, 1e-310, 2.3e-308, 1e-300, 1e-30, 1e30, 1e300, np.inf, np.nan, 0.1, 1000.0])
+    if species == 1:
+        # the reference's own FullCalculation does not return for ER energies whose `Lindhard == 1.` branch hands
+        # std::binomial_distribution a count that does not fit an int64 (or a NaN): the tiny and the ordinary only
+        E = np.array([1e-310, 2.3e-308, 1e-300, 1e-30, 0.1, 1000.0])
+    with np.errstate(all="ignore"):
+        y, _ = ctx.lar(species, E, 500.0, 1.393, want_fluct=False)
+        ry, _ = ref.lar(1, species, E, 500.0, 1.393)
+        for k in range(9):
+            a, b = y[k], ry[:, k]
+            assert np.array_equal(np.isnan(a), np.isnan(b)), (species, k, a, b)
+            assert np.array_equal(np.isinf(a), np.isinf(b)), (species, k, a, b)
+            m = np.isfinite(a) & np.isfinite(b)
+            d = np.abs(a[m] - b[m]) / np.maximum(np.maximum(np.abs(a[m]), np.abs(b[m])), 1e-300)
+            assert d.size == 0 or d.max() <= 1e-12, (species, k, a, b)
