@@ -12,7 +12,7 @@ if [ "$part" = a ]; then
   bash tools/gpu_ncu3.sh ${tag} NR k_pre k_hits
 else
   bash tools/gpu_ncu3.sh ${tag} NR k_hits_finish k_post
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:^k_lar\$ -s 1 -c 1 -f -o gpurun_out/${tag}_k_lar \
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:^k_lar -s 1 -c 1 -f -o gpurun_out/${tag}_k_lar \
      python tools/profile_lar.py 1 > gpurun_out/${tag}_k_lar.log 2>&1
   tail -2 gpurun_out/${tag}_k_lar.log
 fi

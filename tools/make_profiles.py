@@ -52,7 +52,7 @@ def main():
     kernels = [("k_hits", KERNEL, rep)]
     for short, mangled in (("k_pre", "_ZN2nb5k_preENS_9RunParamsEPi"), ("k_post", "_ZN2nb6k_postENS_9RunParamsEPi"),
                            ("k_hits_finish", "_ZN2nb13k_hits_finishENS_9RunParamsENS_8HitQueueE"),
-                           ("k_lar", "_ZN2nb5k_larENS_9LArParamsE")):
+                           ("k_lar", "_ZN2nb5k_larILi1EEEvNS_9LArParamsE")):
         cand = rep.replace("k_hits.", short + ".")
         if cand != rep and os.path.exists(cand):
             kernels.append((short, mangled, cand))
