@@ -543,6 +543,12 @@ int nb200_debug_normal(nb200_ctx* ctx, uint64_t seed, uint64_t first_event, size
 int nb200_debug_binomial(nb200_ctx* ctx, uint64_t seed, uint64_t first_event, size_t count, int64_t n,
                          double p, int64_t* out);
 
+/* Test hook: the same sampler with a trial count per draw (n[count], HOST), on the binomial stream of a given caller:
+ * which_stream 0 = the chain's S1 hit count, 1 = LArNEST's fluctuations.  k_lar makes the latter's draws regrouped
+ * (queued per warp, one candidate per lane and pass); tests/test_gpu_lar.py requires them to equal these. */
+int nb200_debug_binomial_list(nb200_ctx* ctx, uint64_t seed, uint64_t first_event, size_t count, const int64_t* n,
+                              double p, int which_stream, int64_t* out);
+
 /* Test hook: the same for the alias-table sampler that draws an event's number of double-phe hits,
  * Binomial(nHits, P_dphe) (the hit-by-hit decision of NEST.cpp:1391, taken once per event; also the
  * second photo-electrons of S2, NEST.cpp:1984): 0 < p < 1, 0 <= n < 65536. */

@@ -105,7 +105,7 @@ EXPORTS = [
     "nb200_prepare", "nb200_wimp_prep", "nb200_wimp_prep_iso", "nb200_wimp_drate", "nb200_poisson", "nb200_yields", "nb200_quanta", "nb200_s2", "nb200_s1", "nb200_widths", "nb200_spike", "nb200_xy_resolution", "nb200_spectrum", "nb200_run", "nb200_run_sweep", "nb200_sweep_band_post", "nb200_sweep_band_fit", "nb200_band_fit_device", "nb200_run_async",
     "nb200_band_reset", "nb200_band_attach", "nb200_fp64_peak", "nb200_timing_enable", "nb200_timing_read", "nb200_se_stats", "nb200_band_fetch", "nb200_band_device_buffer", "nb200_allreduce_hist",
     "nb200_band_hist_bytes", "nb200_band_scale_x", "nb200_band_finalize", "nb200_band_chi2", "nb200_band_leakage", "nb200_band_fit_gauss", "nb200_band_leakage_gauss", "nb200_hist_fit", "nb200_hist_fit_cov", "nb200_band_leakage_skew_cov", "nb200_graph_fit", "nb200_band_leakage_skew", "nb200_lar", "nb200_launch_count",
-    "nb200_debug_hitmath", "nb200_debug_binomial", "nb200_debug_normal", "nb200_debug_binomial_fixed",
+    "nb200_debug_hitmath", "nb200_debug_binomial", "nb200_debug_binomial_list", "nb200_debug_normal", "nb200_debug_binomial_fixed",
     "nb200_debug_zig_tables", "nb200_debug_alias_tables", "nb200_debug_maps", "nb200_drift_table", "nb200_density", "nb200_drift_velocity_liquid"]
 
 _lib = None
@@ -202,6 +202,7 @@ def lib():
     L.nb200_debug_hitmath.argtypes = [vp, C.c_size_t, vp, vp]
     L.nb200_debug_binomial.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_size_t, C.c_int64, C.c_double, vp]
     L.nb200_debug_binomial_fixed.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_size_t, C.c_int, C.c_double, vp]
+    L.nb200_debug_binomial_list.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_size_t, vp, C.c_double, C.c_int, vp]
     L.nb200_debug_zig_tables.argtypes = [C.c_int, vp, vp, vp, vp]
     L.nb200_debug_alias_tables.argtypes = [C.c_double, C.c_int, vp, vp]
     L.nb200_debug_normal.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_size_t, vp, vp]
@@ -669,6 +670,15 @@ class Context:
     def debug_binomial(self, n, p, count, seed=1, first_event=0):
         out = np.empty(int(count), np.int64)
         self._check(lib().nb200_debug_binomial(self.h, seed, first_event, out.size, int(n), float(p), _dptr(out)))
+        return out
+
+    def debug_binomial_list(self, n, p, which_stream, seed=1, first_event=0):
+        """the in-line binomial sampler, draw i with n[i] trials on the stream of event first_event + i
+        (which_stream 0: the chain's S1 hit count, 1: LArNEST's fluctuations)"""
+        nn = np.ascontiguousarray(n, np.int64)
+        out = np.empty(nn.size, np.int64)
+        self._check(lib().nb200_debug_binomial_list(self.h, seed, first_event, nn.size, _dptr(nn), float(p),
+                                                    int(which_stream), _dptr(out)))
         return out
 
     def debug_binomial_fixed(self, n, p, count, seed=1, first_event=0):

@@ -2332,6 +2332,31 @@ int nb200_debug_binomial(nb200_ctx* c, uint64_t seed, uint64_t first_event, size
   return 0;
 }
 
+int nb200_debug_binomial_list(nb200_ctx* c, uint64_t seed, uint64_t first_event, size_t count, const int64_t* n, double p,
+                              int which_stream, int64_t* out) {
+  if (!c || !out || !n || which_stream < 0 || which_stream > 1) return NB200_EINVAL;
+  if (count == 0) return 0;
+  NB_CUDA(c, cudaSetDevice(c->device));
+  long long *dn = nullptr, *dout = nullptr;
+  NB_CUDA(c, cudaMalloc(&dn, count * 8));
+  if (cudaMalloc(&dout, count * 8) != cudaSuccess) {
+    cudaFree(dn);
+    return fail(c, NB200_ENOMEM, "cudaMalloc");
+  }
+  cudaMemcpyAsync(dn, n, count * 8, cudaMemcpyHostToDevice, c->stream);
+  RoundKeys K;
+  philox_round_keys(seed, K.k);
+  k_binomial_list<<<unsigned(std::min<size_t>((count + 255) / 256, 148 * 8)), 256, 0, c->stream>>>(
+      K, first_event, count, dn, p, which_stream == 1 ? uint32_t(STREAM_BIN_LAR) : uint32_t(STREAM_BIN_S1), dout);
+  ++c->launches;
+  cudaMemcpyAsync(out, dout, count * 8, cudaMemcpyDeviceToHost, c->stream);
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  cudaFree(dn);
+  cudaFree(dout);
+  if (e != cudaSuccess) return fail(c, NB200_ECUDA, cudaGetErrorString(e));
+  return 0;
+}
+
 // host-only test hooks (no device needed): the tables the samplers above are built on
 double nb200_drift_velocity_liquid(double Kelvin, double field) {
   bool ok = true;

@@ -1297,6 +1297,16 @@ __global__ void __launch_bounds__(256) k_binomial(const __grid_constant__ RoundK
     out[i] = binomial(rk, first + i, STREAM_BIN_S1, n, p);
 }
 
+// test hook (nb200_debug_binomial_list): the in-line sampler with a trial count per draw, on the stream a given caller
+// uses -- what k_lar's queued draws (nb_lar.cuh) must reproduce bit for bit
+__global__ void __launch_bounds__(256) k_binomial_list(const __grid_constant__ RoundKeys K, uint64_t first, size_t count,
+                                                       const long long* __restrict__ n, double p, uint32_t stream,
+                                                       long long* __restrict__ out) {
+  const uint32_t* const rk = K.k;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < count; i += size_t(gridDim.x) * blockDim.x)
+    out[i] = binomial(rk, first + i, stream, n[i], p);
+}
+
 // test hook (nb200_debug_binomial_fixed): the alias-table sampler of k_pre's double-phe count
 __global__ void __launch_bounds__(256) k_binomial_fixed(const __grid_constant__ RoundKeys K, uint64_t first,
                                                         size_t count, int n, const uint2* __restrict__ tab,

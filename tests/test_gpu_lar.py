@@ -79,3 +79,31 @@ def test_lar_edge_energies(ctx, ref, species):
             m = np.isfinite(a) & np.isfinite(b)
             d = np.abs(a[m] - b[m]) / np.maximum(np.maximum(np.abs(a[m]), np.abs(b[m])), 1e-300)
             assert d.size == 0 or d.max() <= 1e-12, (species, k, a, b)
+
+
+def test_lar_queued_binomial_draws_equal_the_inline_sampler(ctx):
+    """ER events on the `Lindhard == 1.` branch draw Nion ~ Binomial(Nq, 1 / 1.21).  k_lar queues those draws per warp
+    and makes them one candidate per lane and pass (nb_lar.cuh); candidate k of an event's draw is Philox block k of
+    its stream whoever makes it, so every Nion must be what the in-line sampler returns for that event and Nq --
+    and the moments must be the binomial's"""
+    E = np.linspace(0.5, 900.0, 40_000)
+    y, f = ctx.lar(1, E, 500.0, 1.393, seed=21, first_event=1000)
+    exact = y[7] == 1.0
+    assert 0.4 < exact.mean() < 0.7
+    nion, nex = f[3], f[2]
+    nq = (nion + nex)[exact].astype(np.int64)
+    alf = 1.0 / (1.0 + 0.21)
+    # the in-line sampler on the same events (draw i of the hook = event first_event + i)
+    idx = np.nonzero(exact)[0]
+    n_all = np.zeros(E.size, np.int64)
+    n_all[idx] = nq
+    inline = ctx.debug_binomial_list(n_all, alf, 1, seed=21, first_event=1000)
+    assert np.array_equal(inline[idx], nion[exact].astype(np.int64))
+    # batch split anywhere (the queue's contents differ, the results must not)
+    _, f2 = ctx.lar(1, E[777:], 500.0, 1.393, seed=21, first_event=1777)
+    assert np.array_equal(f[:, 777:], f2)
+    # moments of Nion given Nq
+    z = (nion[exact] - nq * alf) / np.sqrt(np.maximum(nq, 1) * alf * (1 - alf))
+    big = nq > 50
+    assert abs(z[big].mean()) < 4.0 / np.sqrt(big.sum())
+    assert abs(z[big].var() - 1.0) < 0.03
