@@ -12,6 +12,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libnestprobe.so")
 ORC_SO = os.path.join(ROOT, "oracle", "liboracle.so")
 REF_BIN_LUX = os.path.join(ROOT, "oracle", "_ref", "execNEST_ref_lux")
+# ... with analysis.hh's switches taken from NEST_REF_* environment variables (oracle/shim_lux_env)
+REF_BIN_LUX_ENV = os.path.join(ROOT, "oracle", "_ref", "execNEST_ref_lux_env")
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "execNEST_ref")  # the reference exactly as shipped (LZ_WS2024)
 
 dp = C.POINTER(C.c_double)

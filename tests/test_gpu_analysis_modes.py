@@ -1,0 +1,128 @@
+"""The analysis.hh switches other than the two shipped settings (usePD = 2 / useS2 = 0 with LUX_Run03, usePD = 1 /
+useS2 = 1 in analysis_G2.hh): usePD 0 / 1 / 2 (pulse areas in phe, phd, spike counts: execNEST.cpp:1121-1158 signal
+selection, :1170-1250 energy reconstruction), useS2 0 / 1 / 2 (band axes, GetBand :1508-1621), MCtruthE, MCtruthPos.
+The chain's selection, reconstruction and band on the GPU against the CPU restatement (oracle port) event column by
+event column; the restatement and the GPU command line are pinned to the reference itself in these modes by
+test_cli_analysis_modes_match_the_reference_binary (the reference binary with its analysis globals set at start-up)."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+from scipy import stats
+
+import refprobe
+from helpers import band_chi2, gpu_chain, ks_report, ref_chain
+from nest_b200 import capi
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+MODES = [  # usePD, useS2, MCtruthE, MCtruthPos, minS1, maxS1, minS2, maxS2
+    (0, 0, 0, 0, 2.0, 165.0, 80.0, 2.0e4),
+    (1, 0, 0, 0, 1.5, 120.0, 60.0, 1.5e4),
+    (0, 1, 0, 0, 2.0, 165.0, 80.0, 2.0e4),
+    (2, 1, 1, 0, 1.5, 99.5, 42.0, 1.0e4),
+    (1, 2, 0, 1, 1.5, 120.0, 60.0, 1.5e4),
+    (2, 2, 1, 1, 1.5, 99.5, 42.0, 1.0e4),
+]
+
+
+def _ana(mode):
+    usePD, useS2, tE, tP, a, b, c, d = mode
+    ana = capi.analysis(0)
+    ana.usePD, ana.useS2, ana.MCtruthE, ana.MCtruthPos = usePD, useS2, tE, tP
+    ana.minS1, ana.maxS1, ana.minS2, ana.maxS2 = a, b, c, d
+    if useS2 == 1:
+        ana.logMin, ana.logMax = 1.5, 4.5     # y = log10(S2)
+    return ana
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("species,er_model,emin,emax", [(capi.beta, 0, 0.1, 20.0), (capi.NR, -1, 0.5, 60.0)])
+def test_analysis_modes_against_the_restatement(ctx, mode, species, er_model, emin, emax):
+    orc = refprobe.oracle()
+    if orc is None:
+        pytest.skip("oracle/liboracle.so not built")
+    ana = _ana(mode)
+    n = 40000
+    band = capi.Band(ana)
+    g, _ = gpu_chain(ctx, 11, n, species, capi.SRC_FLAT, emin, emax, er_model=er_model, ana=ana, band=band)
+    r = ref_chain(orc, 12, n, species, capi.SRC_FLAT, emin, emax, er_model=er_model, ana=ana)
+    # (helpers.gpu_chain fills "keV_out" with signalE, the probes with the printed energy: the same number unless
+    # MCtruthE keeps the true energy there while signalE of a sub-threshold event is 0 -- signalE has its own column)
+    ks = ks_report(g, r, skip=("keV_out",) if mode[2] else ())
+    bad = {k: v for k, v in ks.items() if v < 1e-4}
+    assert not bad, (mode, bad)
+    # the selected signals must not be trivial in these settings
+    assert (g[:, refprobe.SIG1] > 0).mean() > 0.2 and (g[:, refprobe.SIG2] > 0).mean() > 0.2
+    # band: the GPU accumulator against GetBand (restated) on the GPU's own signals -- same events, so equal to rounding
+    # -- and against GetBand on the restatement's events statistically
+    gb = band.finalize()
+    # execNEST.cpp:1424-1427: useS2 == 2 hands GetBand the two signal vectors the other way round
+    a1, a2 = (refprobe.SIG2, refprobe.SIG1) if ana.useS2 == 2 else (refprobe.SIG1, refprobe.SIG2)
+    bs = orc.getband(g[:, a1], g[:, a2], ana=ana)
+    assert len(bs) == len(gb)
+    # (bins of a few events are left out: their width is the difference of two fixed-point sums of nearly equal size)
+    ok = np.isfinite(bs).all(axis=1) & np.isfinite(gb).all(axis=1) & (band.accepted > 30)
+    assert ok.sum() >= 5, (mode, ok.sum())
+    assert np.allclose(gb[ok][:, :6], bs[ok][:, :6], rtol=1e-5, atol=1e-7), (mode, np.abs(gb[ok][:, :6] / bs[ok][:, :6] - 1).max(axis=0))
+    rb = orc.getband(r[:, a1], r[:, a2], ana=ana)
+    pop = ok & np.isfinite(rb).all(axis=1) & (band.accepted > 100)
+    if pop.sum() > 5:
+        cm, cw, dof = band_chi2(gb[pop], rb[pop])
+        assert cm < 2.5 and cw < 2.5, (mode, cm, cw, dof)
+
+
+CLI = os.path.join(ROOT, "nest_b200", "host", "execNEST_b200")
+
+
+def _env(mode, prefix):
+    usePD, useS2, tE, tP, a, b, c, d = mode
+    e = dict(os.environ)
+    e.update({prefix + "USEPD": str(usePD), prefix + "USES2": str(useS2), prefix + "MCTRUTHE": str(tE),
+              prefix + "MCTRUTHPOS": str(tP), prefix + "MINS1": repr(a), prefix + "MAXS1": repr(b),
+              prefix + "MINS2": repr(c), prefix + "MAXS2": repr(d)})
+    if useS2 == 1:
+        e.update({prefix + "LOGMIN": "1.5", prefix + "LOGMAX": "4.5"})
+    return e
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("args", [("30000", "ER", "0.1", "20", "180", "-1", "1"), ("30000", "NR", "0.5", "60", "180", "-1", "2")])
+def test_cli_analysis_modes_match_the_reference_binary(mode, args):
+    """the command line in the same modes against the reference ITSELF: oracle/_ref/execNEST_ref_lux_env is the
+    unmodified src/execNEST.cpp whose analysis.hh globals are set from the environment before main() (oracle/
+    shim_lux_env); same argv, same header lines, event columns by KS, band table by rootNEST's chi^2"""
+    from test_gpu_cli import band_of, rows_of
+    if not os.path.exists(CLI) or not os.path.exists(refprobe.REF_BIN_LUX_ENV):
+        pytest.skip("execNEST_b200 / execNEST_ref_lux_env not built")
+    rg = subprocess.run([CLI] + list(args), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=_env(mode, "NB200_"))
+    rr = subprocess.run([refprobe.REF_BIN_LUX_ENV] + list(args), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                        env=_env(mode, "NEST_REF_"))
+    assert rg.returncode == 0 and rr.returncode == 0, (rg.stderr[-400:], rr.stderr[-400:])
+    hg = [ln for ln in rg.stdout.splitlines() if not re.match(r"^-?[0-9]", ln)]
+    hr = [ln for ln in rr.stdout.splitlines() if not re.match(r"^-?[0-9]", ln)]
+    assert len(hg) == len(hr)
+    for a, b in zip(hg, hr):
+        if a.startswith("g1 = "):
+            assert a.split("SE_mean")[0] == b.split("SE_mean")[0]
+        else:
+            assert a == b, (mode, a, b)          # the column titles change with usePD / MCtruthE / MCtruthPos
+    g, r = rows_of(rg.stdout), rows_of(rr.stdout)
+    assert g.shape == r.shape and g.shape[1] == 14 and g.shape[0] > 0.5 * int(args[0]), (g.shape, r.shape)
+    names = ["keV", "field", "dt", "x", "y", "z", "Nph", "Ne", "S1", "S1c", "spikeC", "Nee", "S2", "S2c"]
+    for j, nme in enumerate(names):
+        if np.all(g[:, j] == g[0, j]):
+            assert np.all(r[:, j] == g[0, j]), nme
+            continue
+        p = stats.ks_2samp(g[:, j], r[:, j]).pvalue
+        assert p > 1e-4, (mode, nme, p, g[:, j].mean(), r[:, j].mean())
+    bg, br = band_of(rg.stderr), band_of(rr.stderr)
+    assert bg.shape == br.shape == (98, 7), (bg.shape, br.shape)
+    assert np.array_equal(bg[:, 0], br[:, 0])
+    ok = np.isfinite(bg).all(axis=1) & np.isfinite(br).all(axis=1) & (bg[:, 4] > 0) & (br[:, 4] > 0)
+    if ok.sum() > 8:
+        cm, cw, dof = band_chi2(bg[ok], br[ok])
+        assert cm < 2.5 and cw < 2.5, (mode, cm, cw, dof)
