@@ -3,6 +3,7 @@
 // from libnest_b200.so; reference lines are cited where behaviour is mirrored.
 #include "NEST_b200.hh"
 
+#include <mutex>
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
@@ -19,6 +20,19 @@ using namespace NEST;
 namespace {
 const double kHiEregime = 1E+2;  // execNEST.hh:25
 const double kPHE_MIN = 1e-6;
+
+// NEST.cpp:1154-1159: the first evaluation of the beta model with a free m5 (ERYieldsParam[4] < 0, the default) says so
+// on stderr, once per process and whatever the verbosity.  The model is evaluated on the device here: the notice is
+// given when a call is about to route events to it (GetYieldBetaGR, GetYieldERWeighted, the default branch of
+// GetYields :1245-1249: beta, CH3T, 14C, pp solar).
+void beta_model_m5_notice(const nb200_model& m, int species) {
+  const bool other_model = species <= Cf || species == atmNu || species == ion || species == gammaRay ||
+                           species == Kr83m || species == fullGamma_PE;
+  const bool beta = m.er_model == 0 || m.er_model == 2 || (m.er_model < 0 && !other_model);
+  if (!beta || !(m.ERYieldsParam[4] < 0.)) return;
+  static std::once_flag said;
+  std::call_once(said, []() { cerr << "Warning: m5 is slightly energy dependent in the beta model" << endl; });
+}
 
 bool nearlyEqual(double a, double b, double eps = 1e-9) {  // ValidityTests.cpp:6-21
   if (a == b) return true;
@@ -184,6 +198,7 @@ vector<YieldResult> NESTcalc::GetYields(INTERACTION_TYPE species, const vector<d
   m.massNum = massNum;
   m.atomNum = atomNum;
   const size_t n = energy.size();
+  if (n) beta_model_m5_notice(m, int(species));
   vector<double> out(6 * n);
   Device::check(nb200_yields(Device::get(), &flat(), &m, int(species), n, energy.data(), dfield.data(), density,
                              NB200_MEM_HOST, out.data()));
@@ -211,6 +226,7 @@ vector<YieldResult> NESTcalc::yields_by(int er_model, int species, const vector<
   m.massNum = massNum;
   m.atomNum = atomNum;
   const size_t n = energy.size();
+  if (n) beta_model_m5_notice(m, species);
   vector<double> out(6 * n);
   Device::check(nb200_yields(Device::get(), &flat(), &m, species, n, energy.data(), dfield.data(), density, NB200_MEM_HOST,
                              out.data()));
@@ -641,6 +657,7 @@ NESTObservableArray runNESTvec(VDetector* detector, INTERACTION_TYPE particleTyp
     o.s1[k] = s1[k].data();
     o.s2[k] = s2[k].data();
   }
+  beta_model_m5_notice(m, s.species);
   Device::check(nb200_run(Device::get(), &calc.flat(), &m, &ana, &s, &rc, uint64_t(seed), 0, n, &o, nullptr));
   r.energy_kev = eList;
   r.x_mm = x; r.y_mm = y; r.z_mm = z;
@@ -952,6 +969,7 @@ int execNEST(VDetector* detector, double numEvts, const string& type, double eMi
     H.accepted = acc.data(); H.rejected = rej.data(); H.sumS1 = sS1.data(); H.sumY = sY.data();
     H.sumY2 = sY2.data(); H.sumY3 = sY3.data(); H.hist2d = h2.data();
     bool warnedCathode = false;
+    beta_model_m5_notice(M, S.species);
     for (uint64_t done = 0; done < N; done += chunk) {
       const uint64_t m = min<uint64_t>(chunk, N - done);
       int rc_ = nb200_run(Device::get(), &n.flat(), &M, &ana, &S, &rc, useed, done, m, &o, mono ? nullptr : &H);

@@ -14,6 +14,7 @@ int main(int argc, char** argv) {
   // the switches a user of the reference edits in analysis.hh before compiling (include/NEST/analysis.hh:16-48)
   {
     NEST::Analysis& A = nest_b200_cli::analysis;
+    if (const char* v = std::getenv("NB200_PRINTSUBTHR")) A.PrintSubThr = short(std::atoi(v));
     if (const char* v = std::getenv("NB200_USEPD")) A.usePD = std::atoi(v);
     if (const char* v = std::getenv("NB200_USES2")) A.useS2 = std::atoi(v);
     if (const char* v = std::getenv("NB200_MCTRUTHE")) A.MCtruthE = std::atoi(v) != 0;

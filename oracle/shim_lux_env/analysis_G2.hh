@@ -20,6 +20,8 @@ struct nb200_ref_analysis_from_env {
     if (const char* s = std::getenv(n)) v = std::atof(s);
   }
   nb200_ref_analysis_from_env() {
+    i("NEST_REF_VERBOSITY", verbosity);
+    if (const char* s = std::getenv("NEST_REF_PRINTSUBTHR")) PrintSubThr = short(std::atoi(s));
     i("NEST_REF_USEPD", usePD);
     i("NEST_REF_USES2", useS2);
     b("NEST_REF_MCTRUTHE", MCtruthE);

@@ -126,3 +126,66 @@ def test_cli_analysis_modes_match_the_reference_binary(mode, args):
     if ok.sum() > 8:
         cm, cw, dof = band_chi2(bg[ok], br[ok])
         assert cm < 2.5 and cw < 2.5, (mode, cm, cw, dof)
+
+
+def _numeric_rows(out):
+    rows = []
+    for ln in out.splitlines():
+        if re.match(r"^-?[0-9]", ln):
+            try:
+                rows.append([float(v) for v in re.split(r"[\t,]\s*", ln.strip()) if v != ""])
+            except ValueError:
+                pass
+    width = max((len(r) for r in rows), default=0)
+    return np.array([r for r in rows if len(r) == width])
+
+
+@pytest.mark.parametrize("extra,args", [
+    ({"PRINTSUBTHR": "-1"}, ("20000", "NR", "0", "25", "180", "-1", "1")),     # rows inside the S1 / S2 windows only
+    ({"PRINTSUBTHR": "0"}, ("20000", "NR", "0", "25", "180", "-1", "1")),      # rows above threshold only
+    ({"PRINTSUBTHR": "-1", "USEPD": "0", "MINS1": "3.0", "MAXS1": "60.0"}, ("20000", "ER", "0.1", "12", "180", "-1", "1")),
+    ({"VERBOSITY": "2"}, ("8000", "ER", "0.1", "20", "180", "-1", "1")),        # rows carry Z alone (execNEST.cpp:1377-1380)
+    ({"VERBOSITY": "0"}, ("8000", "ER", "0.1", "20", "180", "-1", "1")),
+    ({"VERBOSITY": "-1"}, ("8000", "ER", "0.1", "20", "180", "-1", "1")),
+])
+def test_cli_print_switches_match_the_reference_binary(extra, args):
+    """PrintSubThr (-1 / 0 / 1: which events get a row, execNEST.cpp:1336-1359) and verbosity (what is printed at all, the
+    row format): number of rows, header lines and columns against the reference binary with the same switches"""
+    if not os.path.exists(CLI) or not os.path.exists(refprobe.REF_BIN_LUX_ENV):
+        pytest.skip("execNEST_b200 / execNEST_ref_lux_env not built")
+    eg, er = dict(os.environ), dict(os.environ)
+    for k, v in extra.items():
+        eg["NB200_" + k] = v
+        er["NEST_REF_" + k] = v
+    rg = subprocess.run([CLI] + list(args), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=eg)
+    rr = subprocess.run([refprobe.REF_BIN_LUX_ENV] + list(args), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=er)
+    assert rg.returncode == rr.returncode == 0, (rg.stderr[-300:], rr.stderr[-300:])
+    hg = [ln for ln in rg.stdout.splitlines() if not re.match(r"^-?[0-9]", ln)]
+    hr = [ln for ln in rr.stdout.splitlines() if not re.match(r"^-?[0-9]", ln)]
+    assert [a.split("SE_mean")[0] for a in hg] == [b.split("SE_mean")[0] for b in hr], (extra, hg, hr)
+    g, r = _numeric_rows(rg.stdout), _numeric_rows(rr.stdout)
+    n = int(args[0])
+    assert g.ndim == r.ndim
+    if r.size == 0:
+        assert g.size == 0
+    else:
+        assert g.shape[1] == r.shape[1], (extra, g.shape, r.shape)
+        # the number of rows is itself a random variable when sub-threshold events are left out
+        pr = r.shape[0] / n
+        assert abs(g.shape[0] - r.shape[0]) <= 5.0 * np.sqrt(2 * n * max(pr * (1 - pr), 1e-9)) + 1e-9, (extra, g.shape, r.shape)
+        for j in range(r.shape[1]):
+            if np.all(r[:, j] == r[0, j]) and np.all(g[:, j] == g[0, j]):
+                assert r[0, j] == g[0, j], (extra, j)
+                continue
+            p = stats.ks_2samp(g[:, j], r[:, j]).pvalue
+            assert p > 1e-4, (extra, j, p, g[:, j].mean(), r[:, j].mean())
+    # stderr: the same kinds of lines (band table present or not, warnings) -- compare the non-numeric ones
+    def text(err):
+        # (the "Insufficient number of ... events" hint depends on which bins a finite sample leaves empty)
+        return set(ln for ln in err.splitlines() if ln.strip() and not re.match(r"^-?[0-9]", ln) and "SE_mean" not in ln and
+                   "Insufficient number" not in ln)
+    tg, tr = text(rg.stderr), text(rr.stderr)
+    assert tg == tr, (extra, "only here:", sorted(tg - tr), "only in the reference:", sorted(tr - tg))
+    ng = sum(1 for ln in rg.stderr.splitlines() if re.match(r"^[0-9]", ln))
+    nr_ = sum(1 for ln in rr.stderr.splitlines() if re.match(r"^[0-9]", ln))
+    assert ng == nr_, (extra, ng, nr_)
