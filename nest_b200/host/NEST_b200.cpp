@@ -931,7 +931,10 @@ int execNEST(VDetector* detector, double numEvts, const string& type, double eMi
       if (type_num == Kr83m && (eMin < 10. || eMin > 40.)) fprintf(stdout, "t [ns]\t\t");  // :900-901
       if (eMax > kHiEregime) fprintf(stdout, "Energy [keV]");
       else fprintf(stdout, A.MCtruthE ? "E_truth [keV]" : "E_recon [keV]");
-      if (verbosity >= 2)
+      if (seed == -2)  // :918-935 (the dE/dx basis is not part of this path)
+        printf("\tfield [V/cm]\ttDrift [us]\tX,Y,Z [mm]\tNph\t\tNe-\t\tS1 [PE or phe]\tS1_3Dcor [phd]\tspikeC(NON-INT)\tNe-"
+               "Extr\tS2_rawArea [PE]\tS2_3Dcorr [phd]\n");
+      else if (verbosity >= 2)
         printf("\tfield [V/cm]\ttDrift [us]\tZ [mm]\tNph\tNe-\tS1 [PE or phe]\tS1_3Dcor [phd]\tspikeC(NON-INT)\tNe-Extr"
                "\tS2_rawArea [PE]\tS2_3Dcorr [phd]\n");
       else
@@ -946,6 +949,8 @@ int execNEST(VDetector* detector, double numEvts, const string& type, double eMi
     const uint64_t cap = min<uint64_t>(N, chunk);
     vector<double> cE(cap), cEtrue(cap), cF(cap), cDt(cap), cSx(cap), cSy(cap), cZ(cap), sig1(cap), sig2(cap);
     vector<int32_t> cNph(cap), cNe(cap);
+    const bool means = seed < 0 && seed != -1;  // :1367: rows carry the mean yields in place of the quanta
+    vector<double> cYph(means ? cap : 0), cYne(means ? cap : 0);
     vector<vector<double>> s1(9, vector<double>(cap)), s2(9, vector<double>(cap));
     vector<double> cDeltaT(cap), cKeVee(cap);
     double keVee = 0.;
@@ -957,6 +962,7 @@ int execNEST(VDetector* detector, double numEvts, const string& type, double eMi
     o.smear_x = cSx.data(); o.smear_y = cSy.data(); o.z_mm = cZ.data(); o.photons = cNph.data();
     o.electrons = cNe.data(); o.signal1 = sig1.data(); o.signal2 = sig2.data();
     o.deltaT_ns = cDeltaT.data(); o.keVee = cKeVee.data();
+    if (means) { o.Nph_mean = cYph.data(); o.Ne_mean = cYne.data(); }
     for (int k = 0; k < 9; ++k) {
       o.s1[k] = s1[k].data();
       o.s2[k] = s2[k].data();
@@ -1019,7 +1025,10 @@ int execNEST(VDetector* detector, double numEvts, const string& type, double eMi
         if (!print) continue;
         const double keV = A.MCtruthE ? cEtrue[j] : cE[j];
         if (type_num == Kr83m && verbosity > 0 && (eMin < 10. || eMin > 40.)) printf("%.6f\t", cDeltaT[j]);  // :1360-1361
-        if (verbosity >= 2)
+        if (means)
+          printf("%.6f\t%.6f\t%.6f\t%.0f, %.0f, %.0f\t%lf\t%lf\t", keV, cF[j], cDt[j], cSx[j], cSy[j], cZ[j], cYph[j],
+                 cYne[j]);
+        else if (verbosity >= 2)
           printf("%.6f\t%.6f\t%.6f\t%.0f\t%d\t%d\t", keV, cF[j], cDt[j], cZ[j], cNph[j], cNe[j]);
         else
           printf("%.6f\t%.6f\t%.6f\t%.0f, %.0f, %.0f\t%d\t%d\t", keV, cF[j], cDt[j], cSx[j], cSy[j], cZ[j], cNph[j],

@@ -189,3 +189,44 @@ def test_cli_print_switches_match_the_reference_binary(extra, args):
     ng = sum(1 for ln in rg.stderr.splitlines() if re.match(r"^[0-9]", ln))
     nr_ = sum(1 for ln in rr.stderr.splitlines() if re.match(r"^[0-9]", ln))
     assert ng == nr_, (extra, ng, nr_)
+
+
+@pytest.mark.parametrize("args", [
+    ("20000", "ER", "1", "15", "180", "50,-30,200", "1"),        # fixed vertex
+    ("20000", "NR", "2", "40", "180", "50,-30,-1", "2"),          # fixed x, y; z drawn (execNEST.cpp:846-848)
+    ("20000", "ER", "1", "15", "180", "-999,-999,150", "3"),      # x, y drawn; fixed z (:849-854)
+    ("20000", "ER", "1", "15", "-1", "-1", "4"),                  # FitEF field at a random vertex (:857-861)
+    ("20000", "NR", "2", "40", "-1", "30,40,-1", "5"),
+    ("20000", "NR", "1", "50", "180", "-1", "-2"),                # negative seed: rows carry the mean yields (:1363-1376)
+    ("20000", "beta", "1", "15", "180", "-1", "-5"),
+])
+def test_cli_position_field_and_seed_modes_match_the_reference_binary(args):
+    """the command line's position argument in its three forms, the FitEF field mode and the negative-seed mode (mean
+    yields printed in place of the quanta) against the unmodified reference binary: same header, rows column by column"""
+    if not os.path.exists(CLI) or not os.path.exists(refprobe.REF_BIN_LUX):
+        pytest.skip("execNEST_b200 / execNEST_ref_lux not built")
+    rg = subprocess.run([CLI] + list(args), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    rr = subprocess.run([refprobe.REF_BIN_LUX] + list(args), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert rg.returncode == rr.returncode == 0, (rg.stderr[-300:], rr.stderr[-300:])
+    hg = [ln.split("SE_mean")[0] for ln in rg.stdout.splitlines() if not re.match(r"^-?[0-9]", ln)]
+    hr = [ln.split("SE_mean")[0] for ln in rr.stdout.splitlines() if not re.match(r"^-?[0-9]", ln)]
+    assert hg == hr, (args, hg, hr)
+    g, r = _numeric_rows(rg.stdout), _numeric_rows(rr.stdout)
+    assert g.shape == r.shape and g.shape[0] == int(args[0]), (args, g.shape, r.shape)
+    for j in range(r.shape[1]):
+        if np.all(r[:, j] == r[0, j]) or np.all(g[:, j] == g[0, j]):
+            assert np.all(g[:, j] == r[0, j]) and np.all(r[:, j] == r[0, j]), (args, j, g[0, j], r[0, j])
+            continue
+        p = stats.ks_2samp(g[:, j], r[:, j]).pvalue
+        assert p > 1e-4, (args, j, p, g[:, j].mean(), r[:, j].mean())
+
+
+def test_cli_outside_the_detector_fails_like_the_reference():
+    if not os.path.exists(CLI) or not os.path.exists(refprobe.REF_BIN_LUX):
+        pytest.skip("execNEST_b200 / execNEST_ref_lux not built")
+    for args in [("100", "ER", "1", "15", "180", "400,0,100", "1"),        # beyond radmax (:835-840)
+                 ("100", "ER", "1", "15", "180", "0,0,100"),               # fine (no seed)
+                 ("100", "ER", "1", "15", "180", "0;0;100", "1")]:         # not a position
+        rg = subprocess.run([CLI] + list(args), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        rr = subprocess.run([refprobe.REF_BIN_LUX] + list(args), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        assert (rg.returncode != 0) == (rr.returncode != 0), (args, rg.returncode, rr.returncode, rg.stderr[-200:], rr.stderr[-200:])
