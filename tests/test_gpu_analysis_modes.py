@@ -230,3 +230,42 @@ def test_cli_outside_the_detector_fails_like_the_reference():
         rg = subprocess.run([CLI] + list(args), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
         rr = subprocess.run([refprobe.REF_BIN_LUX] + list(args), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
         assert (rg.returncode != 0) == (rr.returncode != 0), (args, rg.returncode, rr.returncode, rg.stderr[-200:], rr.stderr[-200:])
+
+
+@pytest.mark.parametrize("args,stdin,expected", [
+    (("15000", "D-D", "0", "80", "180", "-1", "1"), None, 15000),
+    (("15000", "AmBe", "0", "200", "180", "-1", "1"), None, 15000),
+    (("15000", "252Cf", "0", "200", "180", "-1", "1"), None, 15000),
+    (("15000", "14C", "0", "156", "180", "-1", "1"), None, 15000),
+    (("15000", "x-ray", "5", "40", "180", "-1", "1"), None, 15000),
+    (("15000", "Compton", "0.5", "30", "180", "-1", "1"), None, 15000),
+    (("15000", "tritium", "0", "18.6", "180", "-1", "1"), None, 15000),
+    (("15000", "-1", "1", "50", "180", "-1", "1"), None, 15000),                 # "-1": the default type, NR (:472-473)
+    (("5000000", "8B", "0", "4", "180", "-1", "1"), None, 0.0026 * 5e6),          # Poisson-fluctuated counts (:485-488)
+    (("10000000", "pp-solar", "0", "250", "180", "-1", "1"), None, 0.0011794 * 1e7),
+    (("60000000000", "atm_nu", "0", "100", "180", "-1", "1"), None, 1.5764e-7 * 6e10),
+    (("10000", "alpha", "4000", "6000", "180", "-1", "1"), None, 10000),
+    (("10000", "nucleus", "10", "200", "180", "-1", "1"), "82\n206\n", 10000),   # A, Z from stdin (:496-505)
+    (("10000", "ion", "5", "60", "180", "-1", "1"), "54\n131\n", 10000),         # Z = 54: plain NR (:506)
+])
+def test_cli_types_match_the_reference_binary(args, stdin, expected):
+    """the type argument in its aliases, the Poisson-fluctuated event counts of the rate-normalised sources and the ion's
+    A, Z read from stdin: row count and every column against the unmodified reference binary"""
+    if not os.path.exists(CLI) or not os.path.exists(refprobe.REF_BIN_LUX):
+        pytest.skip("execNEST_b200 / execNEST_ref_lux not built")
+    rg = subprocess.run([CLI] + list(args), input=stdin, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    rr = subprocess.run([refprobe.REF_BIN_LUX] + list(args), input=stdin, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert rg.returncode == rr.returncode == 0, (args, rg.stderr[-300:], rr.stderr[-300:])
+    hg = [ln.split("SE_mean")[0] for ln in rg.stdout.splitlines() if not re.match(r"^-?[0-9]", ln)]
+    hr = [ln.split("SE_mean")[0] for ln in rr.stdout.splitlines() if not re.match(r"^-?[0-9]", ln)]
+    assert hg == hr, (args, hg, hr)
+    g, r = _numeric_rows(rg.stdout), _numeric_rows(rr.stdout)
+    assert g.shape[1] == r.shape[1], (args, g.shape, r.shape)
+    tol = 5.0 * np.sqrt(expected) if expected != int(args[0]) else 0.0
+    assert abs(g.shape[0] - expected) <= tol and abs(r.shape[0] - expected) <= tol, (args, g.shape, r.shape, expected)
+    for j in range(r.shape[1]):
+        if np.all(r[:, j] == r[0, j]) or np.all(g[:, j] == g[0, j]):
+            assert np.all(g[:, j] == r[0, j]) and np.all(r[:, j] == r[0, j]), (args, j, g[0, j], r[0, j])
+            continue
+        p = stats.ks_2samp(g[:, j], r[:, j]).pvalue
+        assert p > 1e-4, (args, j, p, g[:, j].mean(), r[:, j].mean())
