@@ -269,3 +269,44 @@ def test_cli_types_match_the_reference_binary(args, stdin, expected):
             continue
         p = stats.ks_2samp(g[:, j], r[:, j]).pvalue
         assert p > 1e-4, (args, j, p, g[:, j].mean(), r[:, j].mean())
+
+
+DET_DIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+@pytest.mark.parametrize("det", ["xenon10", "xenonnt", "lz2022", "g3", "zeplin"])
+@pytest.mark.parametrize("args", [("30000", "NR", "0", "70", "-1", "-1", "1"), ("30000", "beta", "0.1", "25", "-1", "-1", "2"),
+                                  ("20000", "NR", "1", "50", "250", "-1", "3")])
+def test_every_shipped_detector_header_matches_the_reference_built_with_it(det, args):
+    """the other detector headers the reference ships (XENON10, XENONnT SR0, LZ WS2022, the projected G3, ZEPLIN-III),
+    each UNMODIFIED: nest-b200's command line compiled with the header against the VDetector mirror (position maps through
+    (r,z) lookup tables, `FitEF` field at -1) against the unmodified src/execNEST.cpp instantiating the same class --
+    banner (g1, g2, density, drift speed), rows column by column, band table"""
+    from test_gpu_cli import band_of, rows_of
+    cli, ref = os.path.join(DET_DIR, "execNEST_b200_" + det), os.path.join(DET_DIR, "execNEST_ref_" + det)
+    if not (os.path.exists(cli) and os.path.exists(ref)):
+        pytest.skip("oracle/_ref/execNEST_{b200,ref}_%s not built (needs the reference tree at build time)" % det)
+    rg = subprocess.run([cli] + list(args), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    rr = subprocess.run([ref] + list(args), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert rg.returncode == rr.returncode == 0, (det, rg.stderr[-400:], rr.stderr[-400:])
+    hg = [ln.split("SE_mean")[0] for ln in rg.stdout.splitlines() if not re.match(r"^-?[0-9]", ln)]
+    hr = [ln.split("SE_mean")[0] for ln in rr.stdout.splitlines() if not re.match(r"^-?[0-9]", ln)]
+    assert hg == hr, (det, hg, hr)
+    g, r = rows_of(rg.stdout), rows_of(rr.stdout)
+    n = int(args[0])
+    assert g.shape[1] == r.shape[1] == 14 and 0 < r.shape[0] <= n
+    assert abs(g.shape[0] - r.shape[0]) < 5 * np.sqrt(2 * max(n - r.shape[0], 25)), (det, g.shape, r.shape)
+    names = ["keV", "field", "dt", "x", "y", "z", "Nph", "Ne", "S1", "S1c", "spikeC", "Nee", "S2", "S2c"]
+    for j, nme in enumerate(names):
+        if np.all(g[:, j] == g[0, j]) or np.all(r[:, j] == r[0, j]):
+            assert np.all(r[:, j] == g[0, j]) and np.all(g[:, j] == g[0, j]), (det, nme, g[0, j], r[0, j])
+            continue
+        p = stats.ks_2samp(g[:, j], r[:, j]).pvalue
+        assert p > 1e-4, (det, nme, p, g[:, j].mean(), r[:, j].mean())
+    bg, br = band_of(rg.stderr), band_of(rr.stderr)
+    assert bg.shape == br.shape and bg.shape[0] > 10
+    assert np.array_equal(bg[:, 0], br[:, 0])
+    ok = np.isfinite(bg).all(axis=1) & np.isfinite(br).all(axis=1) & (bg[:, 4] > 0) & (br[:, 4] > 0)
+    if ok.sum() > 8:
+        cm, cw, dof = band_chi2(bg[ok], br[ok])
+        assert cm < 2.5 and cw < 2.5, (det, cm, cw, dof)
