@@ -310,3 +310,36 @@ def test_every_shipped_detector_header_matches_the_reference_built_with_it(det, 
     if ok.sum() > 8:
         cm, cw, dof = band_chi2(bg[ok], br[ok])
         assert cm < 2.5 and cw < 2.5, (det, cm, cw, dof)
+
+
+@pytest.mark.parametrize("args", [
+    ("10000", "NR", "1", "50", "0", "-1", "1"),             # zero field: warned about, simulated (S2 vanishes)
+    ("10000", "beta", "1", "20", "0.5", "-1", "1"),         # below FIELD_MIN
+    ("10000", "NR", "1", "50", "5000", "-1", "1"),          # beyond the drift-speed table's range
+    ("10000", "gamma", "200", "1500", "180", "-1", "1"),    # "Energy [keV]" header, %e rows above 1 MeV, Parametric S1 (Hybrid)
+    ("10000", "NR", "100", "330", "180", "-1", "1"),        # up to the NR model's validity cap
+    ("10000", "beta", "500", "3000", "180", "-1", "1"),
+    ("10000", "NR", "0.001", "0.6", "180", "-1", "1"),      # mostly below one quantum
+    ("10000", "beta", "0.005", "0.3", "180", "-1", "1"),
+])
+def test_cli_field_and_energy_regimes_match_the_reference_binary(args):
+    """the corners of the field and energy arguments: zero and sub-threshold fields, fields beyond the drift-speed fit,
+    MeV energies (header, row format, S1 mode switch), the NR validity cap, energies of a few quanta"""
+    if not os.path.exists(CLI) or not os.path.exists(refprobe.REF_BIN_LUX):
+        pytest.skip("execNEST_b200 / execNEST_ref_lux not built")
+    rg = subprocess.run([CLI] + list(args), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    rr = subprocess.run([refprobe.REF_BIN_LUX] + list(args), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert rg.returncode == rr.returncode, (args, rg.returncode, rr.returncode, rg.stderr[-300:], rr.stderr[-300:])
+    if rr.returncode != 0:
+        return
+    hg = [ln.split("SE_mean")[0] for ln in rg.stdout.splitlines() if not re.match(r"^-?[0-9]", ln)]
+    hr = [ln.split("SE_mean")[0] for ln in rr.stdout.splitlines() if not re.match(r"^-?[0-9]", ln)]
+    assert hg == hr, (args, hg, hr)
+    g, r = _numeric_rows(rg.stdout), _numeric_rows(rr.stdout)
+    assert g.shape == r.shape and g.shape[0] == int(args[0]), (args, g.shape, r.shape)
+    for j in range(r.shape[1]):
+        if np.all(r[:, j] == r[0, j]) or np.all(g[:, j] == g[0, j]):
+            assert np.all(g[:, j] == r[0, j]) and np.all(r[:, j] == r[0, j]), (args, j, g[0, j], r[0, j])
+            continue
+        p = stats.ks_2samp(g[:, j], r[:, j]).pvalue
+        assert p > 1e-4, (args, j, p, g[:, j].mean(), r[:, j].mean())
