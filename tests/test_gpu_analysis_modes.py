@@ -274,20 +274,25 @@ def test_cli_types_match_the_reference_binary(args, stdin, expected):
 DET_DIR = os.path.join(ROOT, "oracle", "_ref")
 
 
-@pytest.mark.parametrize("det", ["xenon10", "xenonnt", "lz2022", "g3", "zeplin"])
+@pytest.mark.parametrize("det", ["xenon10", "xenonnt", "lz2022", "g3", "zeplin",
+                                 # user-style detectors derived from LUX_Run03 (oracle/shim_variants/LUX_variants.hh): bottom-array
+                                 # S2 + 3-fold coincidence; sPEeff < 1 with linear / quadratic / baseline noise; no coincidence
+                                 # requirement with a short electron lifetime and weak extraction; another (T, p, W) point
+                                 "luxbot3", "luxnoisy", "luxnocoin", "luxwarm"])
 @pytest.mark.parametrize("args", [("30000", "NR", "0", "70", "-1", "-1", "1"), ("30000", "beta", "0.1", "25", "-1", "-1", "2"),
                                   ("20000", "NR", "1", "50", "250", "-1", "3")])
 def test_every_shipped_detector_header_matches_the_reference_built_with_it(det, args):
     """the other detector headers the reference ships (XENON10, XENONnT SR0, LZ WS2022, the projected G3, ZEPLIN-III),
-    each UNMODIFIED: nest-b200's command line compiled with the header against the VDetector mirror (position maps through
+    each UNMODIFIED, and four user-style detectors derived from the reference's LUX_Run03 that reach the detector-parameter
+    branches of GetS1 / GetS2 the shipped ones do not: nest-b200's command line compiled with the header against the VDetector mirror (position maps through
     (r,z) lookup tables, `FitEF` field at -1) against the unmodified src/execNEST.cpp instantiating the same class --
     banner (g1, g2, density, drift speed), rows column by column, band table"""
     from test_gpu_cli import band_of, rows_of
     cli, ref = os.path.join(DET_DIR, "execNEST_b200_" + det), os.path.join(DET_DIR, "execNEST_ref_" + det)
     if not (os.path.exists(cli) and os.path.exists(ref)):
         pytest.skip("oracle/_ref/execNEST_{b200,ref}_%s not built (needs the reference tree at build time)" % det)
-    rg = subprocess.run([cli] + list(args), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
-    rr = subprocess.run([ref] + list(args), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    rg = subprocess.run([cli] + list(args), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+    rr = subprocess.run([ref] + list(args), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
     assert rg.returncode == rr.returncode == 0, (det, rg.stderr[-400:], rr.stderr[-400:])
     hg = [ln.split("SE_mean")[0] for ln in rg.stdout.splitlines() if not re.match(r"^-?[0-9]", ln)]
     hr = [ln.split("SE_mean")[0] for ln in rr.stdout.splitlines() if not re.match(r"^-?[0-9]", ln)]
