@@ -826,8 +826,31 @@ int execNEST(VDetector* detector, double numEvts, const string& type, double eMi
     const double rho = rc.rho, Wq_eV = rc.Wq_eV;
     n.CalculateG2(verbosity);
     const double g2 = fabs(rc.g2_params[3]), g1 = detector->get_g1();
-    (void)g1;
-    (void)g2;
+    // the mean yields at the top of the energy range, for the warnings about the S1 / S2 windows :635-668, 1441-1452
+    YieldResult yieldsMax{};
+    {
+      const double centralZ = (detector->get_gate() * 0.8 + detector->get_cathode() * 1.03) / 2.;
+      double centralField = detector->FitEF(0.0, 0.0, centralZ);
+      if (inField != -1.) centralField = inField;
+      try {
+        if (type_num == WIMP)
+          yieldsMax = n.GetYields(NR, 25.0, rho, centralField, detector->get_molarMass(), M.atomNum, NRYieldsParam, ERYieldsParam);
+        else if (type_num == B8)
+          yieldsMax = n.GetYields(NR, 5.00, rho, centralField, detector->get_molarMass(), M.atomNum, NRYieldsParam, ERYieldsParam);
+        else {
+          double energyMaximum = eMax < 0. ? 1. / fabs(eMax) : eMax;
+          if (!energyMaximum || std::isnan(energyMaximum)) energyMaximum = 1.;
+          if (type_num == Kr83m)
+            yieldsMax = n.GetYields(Kr83m, eMin, rho, centralField, 400., 100., NRYieldsParam, ERYieldsParam);
+          else
+            yieldsMax = n.GetYields(type_num, energyMaximum, rho, centralField, M.massNum, M.atomNum, NRYieldsParam, ERYieldsParam);
+        }
+      } catch (exception&) {
+        yieldsMax = YieldResult{};  // these yields only feed warnings: a refusal here must not end the run
+      }
+    }
+    if ((g1 * yieldsMax.PhotonYield) > (2. * A.maxS1) && eMin != eMax && type_num != Kr83m && verbosity > 0)
+      cerr << "\nWARNING: Your energy maximum may be too high given your maxS1.\n";
     if (type_num < 6) M.massNum = 0;  // :670
     if (type_num == Kr83m) {           // :671, 1052: max / min time separation ride in massNum / atomNum
       M.massNum = maxTimeSep;
@@ -1048,15 +1071,21 @@ int execNEST(VDetector* detector, double numEvts, const string& type, double eMi
         vector<double> band(size_t(ana.numBins) * 7);
         nb200_band_finalize(&ana, &H, band.data());
         fprintf(stderr, "Bin Center\tBin Actual\tHist Mean\tMean Error\tHist Sigma\tSkewness\t\tEff[%%>thr]\n");
-        bool warned = false;
+        bool warned = false;  // (the reference sets eMax = -999 after the first hint: one per run)
         for (int j = 0; j < ana.numBins; ++j) {
           const double* b = &band[7 * size_t(j)];
           fprintf(stderr, "%lf\t%lf\t%lf\t%lf\t%lf\t%lf\t\t%lf\n", b[0], b[1], b[2], b[4], b[3], b[6], b[5] * 100.);
           bool bad = false;
           for (int k = 0; k < 6; ++k) bad = bad || b[k] <= 0.0 || std::isnan(b[k]);
-          if (bad && !warned && verbosity > 0) {
-            cerr << "WARNING: Insufficient number of events to populate some bins. Adjust minS1/maxS1/minS2/maxS2, up "
-                    "the stats, change E range\n";
+          if (bad && !warned) {  // :1435-1454
+            if (verbosity > 0) {
+              if (((g1 * yieldsMax.PhotonYield) < A.maxS1 || (g2 * yieldsMax.ElectronYield) < A.maxS2) && j != 0)
+                cerr << "WARNING: Insufficient number of high-energy events to populate highest bins is likely. Decrease "
+                        "maxS1 and/or increase maxS2. Also: up the stats, change E range\n";
+              else
+                cerr << "WARNING: Insufficient number of low-energy events to populate lowest bins is likely. Increase "
+                        "minS1 and/or decrease minS2,s2_thr. Up the stats, change E range\n";
+            }
             warned = true;
           }
         }

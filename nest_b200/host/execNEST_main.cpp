@@ -25,6 +25,8 @@ int main(int argc, char** argv) {
     if (const char* v = std::getenv("NB200_MAXS2")) A.maxS2 = std::atof(v);
     if (const char* v = std::getenv("NB200_LOGMIN")) A.logMin = std::atof(v);
     if (const char* v = std::getenv("NB200_LOGMAX")) A.logMax = std::atof(v);
+    if (const char* v = std::getenv("NB200_NUMBINS")) A.numBins = std::atoi(v);
+    if (const char* v = std::getenv("NB200_S1MODE")) A.s1CalculationMode = NEST::S1CalculationMode(std::atoi(v));  // Full, Parametric, Hybrid
   }
   auto* detector = new DetectorExample_LUX_RUN03();
   int rc = nest_b200_cli::main_like(detector, argc, argv);

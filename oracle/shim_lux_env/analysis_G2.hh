@@ -32,6 +32,8 @@ struct nb200_ref_analysis_from_env {
     d("NEST_REF_MAXS2", maxS2);
     d("NEST_REF_LOGMIN", logMin);
     d("NEST_REF_LOGMAX", logMax);
+    i("NEST_REF_NUMBINS", numBins);
+    if (const char* s = std::getenv("NEST_REF_S1MODE")) s1CalculationMode = NEST::S1CalculationMode(std::atoi(s));
   }
 } nb200_ref_analysis_from_env_instance;
 }  // namespace

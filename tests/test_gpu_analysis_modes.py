@@ -144,6 +144,10 @@ def _numeric_rows(out):
     ({"PRINTSUBTHR": "-1"}, ("20000", "NR", "0", "25", "180", "-1", "1")),     # rows inside the S1 / S2 windows only
     ({"PRINTSUBTHR": "0"}, ("20000", "NR", "0", "25", "180", "-1", "1")),      # rows above threshold only
     ({"PRINTSUBTHR": "-1", "USEPD": "0", "MINS1": "3.0", "MAXS1": "60.0"}, ("20000", "ER", "0.1", "12", "180", "-1", "1")),
+    ({"S1MODE": "0"}, ("20000", "gamma", "60", "300", "180", "-1", "1")),       # Full S1 also above 100 keV
+    ({"S1MODE": "1"}, ("20000", "ER", "0.5", "25", "180", "-1", "1")),          # Parametric S1 also below 100 keV
+    ({"S1MODE": "1", "USEPD": "1", "MINS1": "2.0", "MAXS1": "110."}, ("20000", "NR", "1", "60", "180", "-1", "2")),
+    ({"NUMBINS": "25", "MAXS1": "76.5"}, ("20000", "ER", "0.1", "20", "180", "-1", "1")),   # another band binning
     ({"VERBOSITY": "2"}, ("8000", "ER", "0.1", "20", "180", "-1", "1")),        # rows carry Z alone (execNEST.cpp:1377-1380)
     ({"VERBOSITY": "0"}, ("8000", "ER", "0.1", "20", "180", "-1", "1")),
     ({"VERBOSITY": "-1"}, ("8000", "ER", "0.1", "20", "180", "-1", "1")),
@@ -189,6 +193,15 @@ def test_cli_print_switches_match_the_reference_binary(extra, args):
     ng = sum(1 for ln in rg.stderr.splitlines() if re.match(r"^[0-9]", ln))
     nr_ = sum(1 for ln in rr.stderr.splitlines() if re.match(r"^[0-9]", ln))
     assert ng == nr_, (extra, ng, nr_)
+    from test_gpu_cli import band_of
+    bg, br = band_of(rg.stderr), band_of(rr.stderr)
+    assert bg.shape == br.shape
+    if bg.size:
+        assert np.array_equal(bg[:, 0], br[:, 0])
+        ok = np.isfinite(bg).all(axis=1) & np.isfinite(br).all(axis=1) & (bg[:, 4] > 0) & (br[:, 4] > 0)
+        if ok.sum() > 8:
+            cm, cw, dof = band_chi2(bg[ok], br[ok])
+            assert cm < 2.5 and cw < 2.5, (extra, cm, cw, dof)
 
 
 @pytest.mark.parametrize("args", [
