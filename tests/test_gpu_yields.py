@@ -111,3 +111,38 @@ def test_survey_pinned_values(ctx):
     for i, e in enumerate(expn):
         for k in range(4):
             assert abs(n[k][i] - e[k]) <= TOL * abs(e[k])
+
+
+@pytest.mark.parametrize("trial", [0, 1, 2])
+def test_yields_with_user_parameter_vectors(ctx, ref, trial):
+    """the mean-yield models with the parameter vectors a user fits instead of the defaults: ERYieldsParam entries >= 0
+    replace the built-in field / density fits of the beta model one by one (NEST.cpp:1135-1180: each m_i has its own
+    `< 0 means default` switch), NRYieldsParam moves every term of the NR model (:773-854) -- 1e-12 against the reference"""
+    rng = np.random.default_rng(100 + trial)
+    det = capi.detector("LUX_Run03")
+    capi.prepare(det, 180.0)
+    mo = capi.model(1)
+    nr0 = np.array(list(mo.NRYieldsParam))
+    nr = nr0 * (1.0 + 0.15 * rng.uniform(-1, 1, nr0.size))
+    # plausible explicit values for m1..m10 of the beta model; a random subset stays at -1 (built-in fit)
+    er = np.array([30.0, 75.0, 1.2, 3.0, 25.0, 0.0, 60.0, 4.0, 0.3, 0.04]) * (1.0 + 0.2 * rng.uniform(-1, 1, 10))
+    keep_default = rng.uniform(size=10) < (0.0 if trial == 0 else 0.4)
+    er[keep_default] = -1.0
+    er[5] = 0.0 if not keep_default[5] else -1.0
+    for i in range(12):
+        mo.NRYieldsParam[i] = nr[i]
+    for i in range(10):
+        mo.ERYieldsParam[i] = er[i]
+    mo.massNum, mo.atomNum = 131.293, 54.0
+    for name, species, er_model, which_ref, mult, erange in [
+            ("NR", capi.NR, -1, 0, 1.0, (0.05, 330.0)), ("beta", capi.beta, -1, 0, 1.0, (0.01, 3000.0)),
+            ("betaGR_mult", capi.beta, 0, 1, 1.1, (0.01, 3000.0)), ("ERweighted", capi.beta, 2, 3, 1.0, (0.01, 3000.0))]:
+        mo.er_model, mo.multFact = er_model, mult
+        E, F = grid(erange[0], erange[1], 200, FIELDS)
+        got = ctx.yields(det, mo, species, E, F, RHO_LUX)
+        exp = ref.yields(which_ref, species, E, F, RHO_LUX, 131.293, 54.0, list(nr), list(er), mult).T
+        for k, col in enumerate(["Nph", "Ne", "NexONi", "L", "field", "dT"]):
+            r = relerr(got[k], exp[k])
+            assert r.max() <= TOL, "%s %s trial %d: max rel err %.3e at E=%g F=%g (gpu %r ref %r) er=%s" % (
+                name, col, trial, r.max(), E[r.argmax()], F[r.argmax()], got[k][r.argmax()], exp[k][r.argmax()], er)
+        assert np.array_equal(got[0] == 0, exp[0] == 0) and np.array_equal(got[1] == 0, exp[1] == 0)
