@@ -207,3 +207,48 @@ def test_s1_stage_does_not_depend_on_batching(ctx):
     assert 0.6 * det.g1 < ratio < 1.4 * det.g1
     with pytest.raises(capi.NestB200Error):
         ctx.s1(det, rc, Nph, pos, E, seed=5, mode=3)     # Waveform: not part of this path
+
+
+@pytest.mark.parametrize("wset", ["default", "perturbed_single", "perturbed_double"])
+@pytest.mark.parametrize("name,skew", [("beta 5 keV", -999.0), ("beta 5 keV", 1.5), ("gamma 41.5 keV", -999.0),
+                                        ("NR 10 keV", 0.0), ("alpha 5.3 MeV", 0.0)])
+def test_quanta_stage_with_other_width_parameters(ctx, ref, wset, name, skew):
+    """GetQuanta with the width parameters other than the command line's: the library defaults (NEST.hh:122-123, [8] < 1:
+    RecombOmegaER's single skew-Gaussian in field and energy, NEST.cpp:173-196) and user-fitted sets in both regimes of
+    [8], with SkewnessER = -999 (the LUX skew model of :379-388) and a fixed skewness -- against the reference"""
+    if name not in RECORDS:
+        pytest.skip("record not in this file's table")
+    y6, _ = RECORDS[name]
+    n = 20000
+    det = capi.detector("LUX_Run03")
+    capi.prepare(det, 180.0)
+    mo = capi.model(0 if wset == "default" else 1)
+    w = np.array(list(mo.NRERWidthsParam)[:mo.n_widths])
+    rng = np.random.default_rng(7)
+    if wset == "perturbed_single":
+        w = np.array(list(capi.model(0).NRERWidthsParam)[:13]) * (1.0 + 0.2 * rng.uniform(-1, 1, 13))
+        w[8] = 0.6                                   # < 1: single-Gaussian branch; [9] must stay below it (:255-262 guards)
+        w[9] = 0.25
+    elif wset == "perturbed_double":
+        w = w * (1.0 + 0.1 * rng.uniform(-1, 1, w.size))
+        w[8] = 2.2                                   # >= 1: the double Gaussian in log10(Nq) (:197-222)
+    mo.n_widths = len(w)
+    for i, v in enumerate(w):
+        mo.NRERWidthsParam[i] = v
+    mo.SkewnessER = skew
+    qi, qd = ctx.quanta(det, mo, np.tile(np.array(y6)[:, None], (1, n)), RHO_LUX, seed=21)
+    ri, rd = ref.quanta(22, n, y6, RHO_LUX, list(w), skew)
+    assert np.all(qi[0] + qi[1] == qi[2] + qi[3])
+    made, rmade = qd[0] != 0, rd[:, 0] != 0
+    if made.any() and rmade.any():
+        assert qd[0][made][0] == pytest.approx(rd[rmade, 0][0], rel=1e-12)          # recombination probability
+    for k, col in enumerate(("photons", "electrons", "ions", "excitons")):
+        a, b = qi[k].astype(float), ri[:, k].astype(float)
+        if np.all(a == a[0]) and np.all(b == b[0]):
+            assert a[0] == b[0], col
+            continue
+        assert stats.ks_2samp(a, b).pvalue > 1e-4, (wset, name, skew, col, a.mean(), b.mean(), a.std(), b.std())
+    lut = {int(a): b for a, b in zip(ri[rmade, 2], rd[rmade, 1])}
+    pairs = [(qd[1][i], lut[int(qi[2][i])]) for i in np.nonzero(made)[0] if int(qi[2][i]) in lut]
+    if pairs:
+        assert max(abs(a - b) / max(abs(b), 1e-300) for a, b in pairs) < 1e-10                  # Variance(Ni)
