@@ -107,3 +107,24 @@ def test_lar_queued_binomial_draws_equal_the_inline_sampler(ctx):
     big = nq > 50
     assert abs(z[big].mean()) < 4.0 / np.sqrt(big.sum())
     assert abs(z[big].var() - 1.0) < 0.03
+
+
+@pytest.mark.parametrize("species", [0, 1, 2])
+def test_lar_field_and_density_corners(ctx, ref, species):
+    """fields from zero to far beyond the benchmarks' 1 kV/cm and other densities: the field-only factors kept per thread
+    (LArFieldTerms) are re-evaluated at every change and must give the reference's values, infinities and NaN alike"""
+    E = np.array([0.5, 3.0, 20.0, 150.0, 900.0])
+    for rho in (1.393, 1.2, 1.5):
+        for F in (0.0, 1e-3, 0.3, 7.0, 2.5e3, 1e5):
+            # one call with the field changing from event to event (the memo's worst case), in both directions
+            Fs = np.array([F, 1.0, F, 1000.0, F])
+            with np.errstate(all="ignore"):
+                y, _ = ctx.lar(species, E, Fs, rho, want_fluct=False)
+                ry = np.vstack([ref.lar(1, species, E[i:i + 1], float(Fs[i]), rho)[0] for i in range(E.size)])
+            for k in range(9):
+                a, b = y[k], ry[:, k]
+                assert np.array_equal(np.isnan(a), np.isnan(b)), (species, rho, F, k, a, b)
+                assert np.array_equal(np.isinf(a), np.isinf(b)), (species, rho, F, k, a, b)
+                m = np.isfinite(a) & np.isfinite(b)
+                d = np.abs(a[m] - b[m]) / np.maximum(np.maximum(np.abs(a[m]), np.abs(b[m])), 1e-300)
+                assert d.size == 0 or d.max() <= 1e-12, (species, rho, F, k, a, b)
