@@ -258,6 +258,8 @@ def test_cli_outside_the_detector_fails_like_the_reference():
     (("10000000", "pp-solar", "0", "250", "180", "-1", "1"), None, 0.0011794 * 1e7),
     (("60000000000", "atm_nu", "0", "100", "180", "-1", "1"), None, 1.5764e-7 * 6e10),
     (("10000", "alpha", "4000", "6000", "180", "-1", "1"), None, 10000),
+    (("10000", "83mKr", "32.1", "300", "180", "-1", "1"), None, 10000),          # the 32.1 keV line alone, times <= 300 ns
+    (("10000", "Kr83", "41.5", "1000", "-1", "-1", "1"), None, 10000),           # both lines merged, FitEF field
     (("10000", "nucleus", "10", "200", "180", "-1", "1"), "82\n206\n", 10000),   # A, Z from stdin (:496-505)
     (("10000", "ion", "5", "60", "180", "-1", "1"), "54\n131\n", 10000),         # Z = 54: plain NR (:506)
 ])
