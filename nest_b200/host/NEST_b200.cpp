@@ -824,6 +824,19 @@ int execNEST(VDetector* detector, double numEvts, const string& type, double eMi
       return 1;
     }
     const double rho = rc.rho, Wq_eV = rc.Wq_eV;
+    if (inField != -1. && rc.vD_middle == 0.1) {
+      // NEST.cpp:2504-2519: GetDriftVelocity_Liquid found a non-positive speed and took 0.1 mm/us (the per-run constants
+      // take the same value); the reference says so at each of its two calls for a uniform field, whatever the verbosity
+      for (int k = 0; k < 2; ++k) {
+        cerr << "\nWARNING: DRIFT SPEED NON-POSITIVE. Setting to 0.1 mm/us\t"
+             << "Line Number ~1950 of NEST.cpp, in function NESTcalc::GetDriftVelocity_Liquid\t"
+             << "Stop bothering Matthew about this, and fix underlying cause in your code!\n";
+        if (inField < 1e2 && inField >= 1.) cerr << "FIELD MAY BE TOO LOW. ";
+        else if (inField > 1e4) cerr << "FIELD MAYBE TOO HIGH. ";
+        else cerr << "Something unknown went wrong: are you in a noble element?? ";
+        cerr << "EF = " << inField << " V/cm. T = " << detector->get_T_Kelvin() << " Kelvin" << endl;
+      }
+    }
     n.CalculateG2(verbosity);
     const double g2 = fabs(rc.g2_params[3]), g1 = detector->get_g1();
     // the mean yields at the top of the energy range, for the warnings about the S1 / S2 windows :635-668, 1441-1452
@@ -998,6 +1011,7 @@ int execNEST(VDetector* detector, double numEvts, const string& type, double eMi
     H.accepted = acc.data(); H.rejected = rej.data(); H.sumS1 = sS1.data(); H.sumY = sY.data();
     H.sumY2 = sY2.data(); H.sumY3 = sY3.data(); H.hist2d = h2.data();
     bool warnedCathode = false;
+    double lastField = inField;  // the reference's `field` after its event loop: the last event's
     beta_model_m5_notice(M, S.species);
     for (uint64_t done = 0; done < N; done += chunk) {
       const uint64_t m = min<uint64_t>(chunk, N - done);
@@ -1008,6 +1022,16 @@ int execNEST(VDetector* detector, double numEvts, const string& type, double eMi
       }
       for (uint64_t j = 0; j < m; ++j) {
         keVee += cKeVee[j];
+        if (verbosity > 0) {  // per event, as the reference: :869-876
+          if (nearlyEqual(cF[j], 0.) || std::isnan(cF[j]))
+            cerr << "\nWARNING: A LITERAL ZERO (or undefined) FIELD MAY YIELD WEIRD RESULTS. USE A SMALL VALUE INSTEAD.\n";
+          if (cF[j] > 12e3 || detector->get_E_gas() > 17e3)
+            cerr << "\nWARNING: Your field is >12,000 V/cm. No data out here. Are you sure about this?\n";
+          // :968-971, first event (for a FitEF field the drift speed at the centre stands in for the event's own)
+          if (done + j == 0 && detector->get_dt_max() > (detector->get_TopDrift() - 0.) / rc.vD_middle && cF[j] >= 1.)
+            cerr << "WARNING: dt_max is greater than max possible" << endl;
+        }
+        lastField = cF[j];
         if (mono && done + j < 10 && verbosity > 0) {  // :1160-1168
           if (s1[3][j] > A.maxS1 || s1[5][j] > A.maxS1 || s1[7][j] > A.maxS1)
             cerr << "WARNING: Some S1 pulse areas are greater than maxS1" << endl;
@@ -1146,7 +1170,7 @@ int execNEST(VDetector* detector, double numEvts, const string& type, double eMi
           fprintf(stderr, "\n");
         if ((m1 <= 0.0 || v1 <= 0.0 || m2 <= 0.0 || v2 <= 0.0 || std::isnan(m1) || std::isnan(v1) || std::isnan(m2) ||
              std::isnan(v2)) &&
-            rc.field >= 1.) {  // :1481-1495
+            lastField >= 1.) {  // :1481-1495
           if (verbosity > 0) {
             if (numEvts > 1)
               cerr << "CAUTION: YOUR S1 and/or S2 MIN and/or MAX may be set to be too restrictive, please check.\n";
@@ -1154,7 +1178,7 @@ int execNEST(VDetector* detector, double numEvts, const string& type, double eMi
               cerr << "CAUTION: Poor stats. You must have at least 2 events to calculate S1 and S2 and E "
                       "resolutions.\n";
           }
-        } else if ((nearlyEqual(eM, eMin) || nearlyEqual(eM, eMax) || eV <= 1E-6) && rc.field >= 1.)
+        } else if ((nearlyEqual(eM, eMin) || nearlyEqual(eM, eMax) || eV <= 1E-6) && lastField >= 1.)
           if (verbosity > 0)
             cerr << "If your energy resolution is 0% then you probably still have MC truth energy on." << endl;
       }

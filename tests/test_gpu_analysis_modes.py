@@ -224,6 +224,8 @@ def test_cli_position_field_and_seed_modes_match_the_reference_binary(args):
     hg = [ln.split("SE_mean")[0] for ln in rg.stdout.splitlines() if not re.match(r"^-?[0-9]", ln)]
     hr = [ln.split("SE_mean")[0] for ln in rr.stdout.splitlines() if not re.match(r"^-?[0-9]", ln)]
     assert hg == hr, (args, hg, hr)
+    tg, tr = _stderr_text(rg.stderr), _stderr_text(rr.stderr)
+    assert tg == tr, "%s\nonly here:\n  %s\nonly in the reference:\n  %s" % (args, "\n  ".join(sorted(tg - tr)), "\n  ".join(sorted(tr - tg)))
     g, r = _numeric_rows(rg.stdout), _numeric_rows(rr.stdout)
     assert g.shape == r.shape and g.shape[0] == int(args[0]), (args, g.shape, r.shape)
     for j in range(r.shape[1]):
@@ -243,6 +245,18 @@ def test_cli_outside_the_detector_fails_like_the_reference():
         rg = subprocess.run([CLI] + list(args), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
         rr = subprocess.run([refprobe.REF_BIN_LUX] + list(args), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
         assert (rg.returncode != 0) == (rr.returncode != 0), (args, rg.returncode, rr.returncode, rg.stderr[-200:], rr.stderr[-200:])
+
+
+def _stderr_text(err):
+    """the non-numeric lines a run leaves on stderr (prompts, notices, warnings), without the ones that depend on the
+    sample (which band bins a finite run leaves empty) or carry a Monte-Carlo number"""
+    out = set()
+    for ln in err.splitlines():
+        t = ln.strip()
+        if not t or re.match(r"^-?[0-9]", t) or "SE_mean" in t or "Insufficient number" in t:
+            continue
+        out.add(t)
+    return out
 
 
 @pytest.mark.parametrize("args,stdin,expected", [
@@ -274,6 +288,8 @@ def test_cli_types_match_the_reference_binary(args, stdin, expected):
     hg = [ln.split("SE_mean")[0] for ln in rg.stdout.splitlines() if not re.match(r"^-?[0-9]", ln)]
     hr = [ln.split("SE_mean")[0] for ln in rr.stdout.splitlines() if not re.match(r"^-?[0-9]", ln)]
     assert hg == hr, (args, hg, hr)
+    tg, tr = _stderr_text(rg.stderr), _stderr_text(rr.stderr)
+    assert tg == tr, "%s\nonly here:\n  %s\nonly in the reference:\n  %s" % (args, "\n  ".join(sorted(tg - tr)), "\n  ".join(sorted(tr - tg)))
     g, r = _numeric_rows(rg.stdout), _numeric_rows(rr.stdout)
     assert g.shape[1] == r.shape[1], (args, g.shape, r.shape)
     tol = 5.0 * np.sqrt(expected) if expected != int(args[0]) else 0.0
@@ -355,6 +371,8 @@ def test_cli_field_and_energy_regimes_match_the_reference_binary(args):
     hg = [ln.split("SE_mean")[0] for ln in rg.stdout.splitlines() if not re.match(r"^-?[0-9]", ln)]
     hr = [ln.split("SE_mean")[0] for ln in rr.stdout.splitlines() if not re.match(r"^-?[0-9]", ln)]
     assert hg == hr, (args, hg, hr)
+    tg, tr = _stderr_text(rg.stderr), _stderr_text(rr.stderr)
+    assert tg == tr, "%s\nonly here:\n  %s\nonly in the reference:\n  %s" % (args, "\n  ".join(sorted(tg - tr)), "\n  ".join(sorted(tr - tg)))
     g, r = _numeric_rows(rg.stdout), _numeric_rows(rr.stdout)
     assert g.shape == r.shape and g.shape[0] == int(args[0]), (args, g.shape, r.shape)
     for j in range(r.shape[1]):
