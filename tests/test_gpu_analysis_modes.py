@@ -110,6 +110,8 @@ def test_cli_analysis_modes_match_the_reference_binary(mode, args):
             assert a.split("SE_mean")[0] == b.split("SE_mean")[0]
         else:
             assert a == b, (mode, a, b)          # the column titles change with usePD / MCtruthE / MCtruthPos
+    tg, tr = _stderr_text(rg.stderr), _stderr_text(rr.stderr)
+    assert tg == tr, "%s %s\nonly here:\n  %s\nonly in the reference:\n  %s" % (mode, args, "\n  ".join(sorted(tg - tr)), "\n  ".join(sorted(tr - tg)))
     g, r = rows_of(rg.stdout), rows_of(rr.stdout)
     assert g.shape == r.shape and g.shape[1] == 14 and g.shape[0] > 0.5 * int(args[0]), (g.shape, r.shape)
     names = ["keV", "field", "dt", "x", "y", "z", "Nph", "Ne", "S1", "S1c", "spikeC", "Nee", "S2", "S2c"]
@@ -328,6 +330,8 @@ def test_every_shipped_detector_header_matches_the_reference_built_with_it(det, 
     hg = [ln.split("SE_mean")[0] for ln in rg.stdout.splitlines() if not re.match(r"^-?[0-9]", ln)]
     hr = [ln.split("SE_mean")[0] for ln in rr.stdout.splitlines() if not re.match(r"^-?[0-9]", ln)]
     assert hg == hr, (det, hg, hr)
+    tg, tr = _stderr_text(rg.stderr), _stderr_text(rr.stderr)
+    assert tg == tr, "%s %s\nonly here:\n  %s\nonly in the reference:\n  %s" % (det, args, "\n  ".join(sorted(tg - tr)), "\n  ".join(sorted(tr - tg)))
     g, r = rows_of(rg.stdout), rows_of(rr.stdout)
     n = int(args[0])
     assert g.shape[1] == r.shape[1] == 14 and 0 < r.shape[0] <= n
