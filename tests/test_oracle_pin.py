@@ -170,3 +170,26 @@ def test_oracle_stage_calls_equal_live_reference(orc, ref):
         a = ref.s2(7, 3000, Ne, pos, spos, dt, rc.vD, field)
         b = orc.s2(7, 3000, Ne, pos, spos, dt, rc.vD, field)
         assert np.array_equal(a, b), name
+
+
+def test_env_configurable_reference_binary_is_the_reference_when_nothing_is_set():
+    """oracle/_ref/execNEST_ref_lux_env (analysis globals settable from NEST_REF_* variables, oracle/shim_lux_env) must be
+    execNEST_ref_lux when no variable is set -- byte for byte -- and must obey a variable when one is"""
+    import os
+    import subprocess
+    import refprobe
+    if not (os.path.exists(refprobe.REF_BIN_LUX) and os.path.exists(refprobe.REF_BIN_LUX_ENV)):
+        pytest.skip("reference binaries not built")
+    args = ["300", "ER", "0.1", "20", "180", "-1", "1"]
+    env = {k: v for k, v in os.environ.items() if not k.startswith("NEST_REF_")}
+    a = subprocess.run([refprobe.REF_BIN_LUX] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
+    b = subprocess.run([refprobe.REF_BIN_LUX_ENV] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
+    assert a.returncode == b.returncode == 0
+    assert a.stdout == b.stdout and a.stderr == b.stderr
+    env["NEST_REF_USEPD"] = "0"
+    c = subprocess.run([refprobe.REF_BIN_LUX_ENV] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
+    assert c.returncode == 0 and c.stdout != a.stdout                      # areas in phe: the energy column moves
+    rows_a = [ln.split(b"\t") for ln in a.stdout.splitlines() if ln[:1].isdigit()]
+    rows_c = [ln.split(b"\t") for ln in c.stdout.splitlines() if ln[:1].isdigit()]
+    assert len(rows_a) == len(rows_c) == 300
+    assert all(x[1:] == y[1:] for x, y in zip(rows_a, rows_c))             # same events: everything but E_recon equal
