@@ -193,3 +193,60 @@ def test_env_configurable_reference_binary_is_the_reference_when_nothing_is_set(
     rows_c = [ln.split(b"\t") for ln in c.stdout.splitlines() if ln[:1].isdigit()]
     assert len(rows_a) == len(rows_c) == 300
     assert all(x[1:] == y[1:] for x, y in zip(rows_a, rows_c))             # same events: everything but E_recon equal
+
+
+@pytest.mark.parametrize("usePD,useS2,tE,tP,win", [(0, 0, 0, 0, (2.0, 165.0, 80.0, 2.0e4)), (1, 0, 0, 0, (1.5, 120.0, 60.0, 1.5e4)),
+                                                    (2, 1, 1, 0, (1.5, 99.5, 42.0, 1.0e4)), (1, 2, 0, 1, (1.5, 120.0, 60.0, 1.5e4)),
+                                                    (0, 1, 0, 1, (2.0, 165.0, 80.0, 2.0e4))])
+@pytest.mark.parametrize("species,tname,emin,emax", [(8, "beta", 0.1, 20.0), (0, "NR", 0.5, 60.0)])
+def test_oracle_reproduces_reference_binary_in_other_analysis_modes(orc, usePD, useS2, tE, tP, win, species, tname, emin, emax):
+    """the restatement's signal selection, energy reconstruction (execNEST.cpp:1121-1250), MC-truth switches and GetBand in
+    the analysis modes the shipped settings do not reach, against the reference binary with the same switches
+    (execNEST_ref_lux_env): the printed energy and position of every row and the whole band table, digit for digit"""
+    if not os.path.exists(refprobe.REF_BIN_LUX_ENV):
+        pytest.skip("oracle/_ref/execNEST_ref_lux_env not built")
+    n = 4000
+    env = {k: v for k, v in os.environ.items() if not k.startswith("NEST_REF_")}
+    env.update({"NEST_REF_USEPD": str(usePD), "NEST_REF_USES2": str(useS2), "NEST_REF_MCTRUTHE": str(tE),
+                "NEST_REF_MCTRUTHPOS": str(tP), "NEST_REF_MINS1": repr(win[0]), "NEST_REF_MAXS1": repr(win[1]),
+                "NEST_REF_MINS2": repr(win[2]), "NEST_REF_MAXS2": repr(win[3])})
+    if useS2 == 1:
+        env.update({"NEST_REF_LOGMIN": "1.5", "NEST_REF_LOGMAX": "4.5"})
+    r = subprocess.run([refprobe.REF_BIN_LUX_ENV, str(n), tname, repr(emin), repr(emax), "180", "-1", "1"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, check=True, env=env)
+    rows = [ln for ln in r.stdout.splitlines() if (ln[:1].isdigit() or ln[:1] == "-") and ln.count("\t") >= 11]
+    assert len(rows) == n
+    ana = capi.analysis(0)
+    ana.usePD, ana.useS2, ana.MCtruthE, ana.MCtruthPos = usePD, useS2, tE, tP
+    ana.minS1, ana.maxS1, ana.minS2, ana.maxS2 = win
+    if useS2 == 1:
+        ana.logMin, ana.logMax = 1.5, 4.5
+    mo = capi.model(1)
+    o = orc.chain(1, n, species, capi.SRC_FLAT, emin, emax, 180.0, 0, [0., 0., 0.], -1, 1.0, list(mo.NRYieldsParam),
+                  list(mo.ERYieldsParam), list(mo.NRERWidthsParam)[:13], 0.0, 1, ana=ana)
+    C = refprobe.COL
+    for j, ln in enumerate(rows):
+        f = ln.split("\t")
+        # energy as printed (reconstructed in this mode's units, or the true one), position (smeared, or the true one)
+        xs, ys = (o[j, C["x"]], o[j, C["y"]]) if tP else (o[j, C["sx"]], o[j, C["sy"]])
+        exp = "%.6f\t%.6f\t%.6f\t%.0f, %.0f, %.0f\t%d\t%d" % (o[j, C["keV_out"]], o[j, C["field"]], o[j, C["dt"]], xs, ys,
+                                                          o[j, C["z"]], o[j, C["Nph"]], o[j, C["Ne"]])
+        assert "\t".join(f[:6]) == exp, (j, ln, exp)
+    # the band table on stderr against GetBand (restated) on the restatement's own signals
+    band = []
+    for ln in r.stderr.splitlines():
+        g = ln.split()
+        if len(g) == 7:
+            try:
+                band.append([float(v) for v in g])
+            except ValueError:
+                pass
+    band = np.array(band)
+    a1, a2 = (refprobe.SIG2, refprobe.SIG1) if useS2 == 2 else (refprobe.SIG1, refprobe.SIG2)
+    ob = orc.getband(o[:, a1], o[:, a2], ana=ana)
+    assert band.shape == (ana.numBins, 7) and len(ob) == ana.numBins
+    # printed columns: centre, actual, mean, mean error, sigma, skew, eff[%] <- GetBand's 0, 1, 2, 4, 3, 6, 5 * 100
+    exp = np.column_stack([ob[:, 0], ob[:, 1], ob[:, 2], ob[:, 4], ob[:, 3], ob[:, 6], ob[:, 5] * 100.0])
+    both = np.isfinite(band) & np.isfinite(exp)
+    assert np.array_equal(np.isnan(band), np.isnan(exp))
+    assert np.allclose(band[both], exp[both], rtol=0, atol=6e-7)           # "%lf": six decimals
