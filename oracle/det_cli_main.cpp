@@ -12,7 +12,9 @@
 #include NB_DET_HEADER
 
 int main(int argc, char** argv) {
+#ifndef NB_DET_LUX_ANALYSIS
   nest_b200_cli::analysis = NEST::Analysis::G2();  // src/execNEST.cpp is compiled with analysis_G2.hh
+#endif  // (else the analysis.hh settings, the mirror's default: the reference side is built with oracle/shim_lux_ana)
   if (const char* v = std::getenv("NB200_VERBOSITY")) nest_b200_cli::analysis.verbosity = std::atoi(v);
   auto* detector = new NB_DET_CLASS();
   int rc = nest_b200_cli::main_like(detector, argc, argv);

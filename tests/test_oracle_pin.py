@@ -3,6 +3,7 @@ reproduce the UNMODIFIED reference bit for bit -- against the committed golden f
 (tests/golden/reference_lux_run03.npz, outputs of the compiled reference) everywhere, and against
 the reference library / binary themselves wherever oracle/_ref has been built."""
 import ast
+import ctypes as C
 import os
 import subprocess
 
@@ -250,3 +251,55 @@ def test_oracle_reproduces_reference_binary_in_other_analysis_modes(orc, usePD, 
     both = np.isfinite(band) & np.isfinite(exp)
     assert np.array_equal(np.isnan(band), np.isnan(exp))
     assert np.allclose(band[both], exp[both], rtol=0, atol=6e-7)           # "%lf": six decimals
+
+
+VARIANTS = {   # oracle/shim_variants/LUX_variants.hh, as changes to the flattened LUX_Run03
+    "luxbot3": dict(s2_thr=-150.0, coinLevel=3),
+    "luxnoisy": dict(sPEeff=0.85, sPEthr=0.5, P_dphe=0.25, noiseLinear=(3.e-2, 2.e-2), noiseQuadratic=(1.e-4, 2.e-5),
+                     noiseBaseline=(0.02, 0.1, 0.0, 0.0)),
+    "luxnocoin": dict(coinLevel=0, eLife_us=250.0, E_gas=5.0, s2Fano=1.5, coinWind=50.0),
+    "luxwarm": dict(T_Kelvin=170.0, p_bar=1.7, OldW13eV=0, PosResFlat=5.0, PosResBase=120.0, coinLevel=1),
+}
+
+
+@pytest.mark.parametrize("variant", list(VARIANTS))
+@pytest.mark.parametrize("species,tname,emin,emax", [(8, "ER", 0.1, 20.0), (0, "NR", 0.5, 60.0)])
+def test_oracle_reproduces_reference_binary_for_user_detectors(orc, variant, species, tname, emin, emax):
+    """the restatement's detector-parameter branches -- bottom-array S2, 3-fold / no coincidence, sPEeff < 1, linear,
+    quadratic and baseline noise, other lifetime / extraction field / S2 Fano factor / (T, p, W) -- against the reference
+    binary built with the same LUX-derived user detector (oracle/_ref/execNEST_ref_<variant>): rows digit for digit"""
+    path = os.path.join(os.path.dirname(refprobe.REF_BIN_LUX), "execNEST_ref_" + variant)
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/execNEST_ref_%s not built" % variant)
+    n = 300
+    r = subprocess.run([path, str(n), tname, repr(emin), repr(emax), "180", "-1", "1"], stdout=subprocess.PIPE,
+                       stderr=subprocess.DEVNULL, text=True, check=True)
+    rows = [ln for ln in r.stdout.splitlines() if (ln[:1].isdigit() or ln[:1] == "-") and ln.count("\t") >= 11]
+    assert len(rows) == n
+    saved = capi.Detector.from_buffer_copy(orc.det)
+    try:
+        for k, v in VARIANTS[variant].items():
+            if isinstance(v, tuple):
+                for i, x in enumerate(v):
+                    getattr(orc.det, k)[i] = x
+            else:
+                setattr(orc.det, k, v)
+        capi.prepare(orc.det, 180.0)
+        mo = capi.model(1)
+        er_model = 0 if tname == "ER" else -1
+        ana = capi.analysis(0)
+        o = orc.chain(1, n, species, capi.SRC_FLAT, emin, emax, 180.0, 0, [0., 0., 0.], er_model, 1.0, list(mo.NRYieldsParam),
+                      list(mo.ERYieldsParam), list(mo.NRERWidthsParam)[:13], 0.0, 1, ana=ana)
+    finally:
+        C.memmove(C.byref(orc.det), C.byref(saved), C.sizeof(saved))
+    Cc = refprobe.COL
+    for j, ln in enumerate(rows):
+        s1, s2 = o[j, refprobe.S1_0:refprobe.S1_0 + 9], o[j, refprobe.S2_0:refprobe.S2_0 + 9]
+        exp = "%.6f\t%.6f\t%.6f\t%.0f, %.0f, %.0f\t%d\t%d\t" % (
+            o[j, Cc["keV_out"]], o[j, Cc["field"]], o[j, Cc["dt"]], o[j, Cc["sx"]], o[j, Cc["sy"]], o[j, Cc["z"]],
+            o[j, Cc["Nph"]], o[j, Cc["Ne"]])
+        if o[j, Cc["keV_out"]] > 1000. or s1[5] > ana.maxS1 or s2[7] > ana.maxS2:
+            exp += "%e\t%e\t%e\t%d\t%e\t%e" % (s1[2], s1[5], s1[7], int(s2[0]), s2[4], s2[7])
+        else:
+            exp += "%.6f\t%.6f\t%.6f\t%i\t%.6f\t%.6f" % (s1[2], s1[5], s1[7], int(s2[0]), s2[4], s2[7])
+        assert ln.strip() == exp, (variant, j, ln, exp)
